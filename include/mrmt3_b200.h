@@ -1,0 +1,152 @@
+/* mrmt3_b200 -- C ABI of the B200-native MR-MT3 transcription hot path.
+ *
+ * The reference (gudgud96/MR-MT3) is pure Python and has no FFI layer; its boundary for this
+ * path is the Python object API listed in SURVEY.md section 8(b).  Each entry point below names
+ * the reference interface it stands behind (file:line in the reference checkout).  The Python
+ * classes in `mr-mt3_b200/` (same names, arguments and state-dict keys as the reference's) bind
+ * these with ctypes; see INTEGRATION.md for the stub a reference maintainer would add.
+ *
+ * Conventions
+ *   - every function returns 0 on success, non-zero on failure; `mrmt3_last_error` gives the
+ *     message.  No C++ exception crosses this boundary.
+ *   - one handle per device; a handle is NOT thread-safe (the reference is single-threaded).
+ *   - the caller owns every input/output buffer; the library owns its packed bf16 weight copy,
+ *     the KV-cache pages and its workspaces (inside the handle).
+ *   - pointers are DEVICE pointers unless the parameter name ends in `_host`.
+ *   - `stream` is a cudaStream_t passed as void*; work is enqueued on it.  Functions that run
+ *     the greedy loop synchronise that stream internally when they poll for early exit and
+ *     before they return (the reference syncs once per token, models/t5.py:294).
+ *   - there is no CPU fallback anywhere behind this interface.
+ */
+#ifndef MRMT3_B200_H_
+#define MRMT3_B200_H_
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct mrmt3_handle mrmt3_handle;
+
+/* mem_variant */
+#define MRMT3_MEM_NONE 0        /* models/t5.py T5ForConditionalGeneration               */
+#define MRMT3_MEM_V1_PREPEND 1  /* models/t5_segmem.py T5SegMem.generate_2                */
+#define MRMT3_MEM_V2_APPEND 2   /* models/t5_segmem_v2_with_prev.py T5SegMemV2WithPrev    */
+
+/* flags of mrmt3_logmel / mrmt3_transcribe_host */
+#define MRMT3_MEL_NORM 1        /* inference.py:113-118 clip [-12,5] -> [0,1]             */
+
+typedef struct mrmt3_config {
+    int32_t d_model;          /* 512  (pretrained/config.json)                             */
+    int32_t n_heads;          /* 6                                                         */
+    int32_t d_kv;             /* 64                                                        */
+    int32_t d_ff;             /* 1024                                                      */
+    int32_t vocab;            /* 1536                                                      */
+    int32_t n_enc_layers;     /* 8                                                         */
+    int32_t n_dec_layers;     /* 8                                                         */
+    int32_t mem_variant;      /* MRMT3_MEM_*                                               */
+    int32_t n_mem_layers;     /* segmem_num_layers (models/t5_segmem.py:52), 0 when NONE   */
+    int32_t mem_len;          /* segmem_length L_agg (models/t5_segmem.py:53)              */
+    int32_t start_id;         /* decoder_start_token_id = 0                                */
+    int32_t eos_id;           /* 1                                                         */
+    int32_t pad_id;           /* 0                                                         */
+    float ln_eps;             /* layer_norm_epsilon = 1e-6                                 */
+} mrmt3_config;
+
+/* ---- lifetime ------------------------------------------------------------------------- */
+/* Replaces: T5ForConditionalGeneration(config) / T5SegMem*(config, segmem_num_layers,
+ * segmem_length) + .cuda()  (models/t5.py:46-80, models/t5_segmem.py:47-66,
+ * inference.py:56,183). */
+int mrmt3_create(const mrmt3_config* cfg, int device, mrmt3_handle** out);
+void mrmt3_destroy(mrmt3_handle* h);
+/* message of the last failure on this handle (h == NULL: last mrmt3_create failure) */
+const char* mrmt3_last_error(const mrmt3_handle* h);
+/* number of kernels this handle has launched so far (bench.py's gpu_launches) */
+int64_t mrmt3_launch_count(const mrmt3_handle* h);
+
+/* ---- weights -------------------------------------------------------------------------- */
+/* Replaces: model.load_state_dict(sd) (test.py:106-110, train.py:80-83).  `name` is the
+ * reference's state-dict key (weight contract); `data` is fp32 row-major
+ * (rows, cols) on the host or on the device (norm weights / inv_freq: rows = 1).  The library
+ * converts to its packed bf16 layout.  Returns 3 for a key it does not know. */
+int mrmt3_set_weight(mrmt3_handle* h, const char* name, const float* data, int rows, int cols);
+/* after the last mrmt3_set_weight: checks that every tensor the configuration needs is there */
+int mrmt3_commit_weights(mrmt3_handle* h);
+/* Optional: dense (1025, 512) fp32 HOST mel filterbank; default is the exact-arithmetic HTK
+ * table, the Python binding passes torchaudio's fp32 table (contrib/spectrograms.py:130-139). */
+int mrmt3_set_mel_filterbank(mrmt3_handle* h, const float* fb_host);
+
+/* ---- frontend --------------------------------------------------------------------------
+ * Replaces: InferenceHandler._compute_spectrograms + the pad zeroing of _preprocess
+ * (inference.py:97-127) = spectrograms.compute_spectrogram per 256-frame segment
+ * (contrib/spectrograms.py:105-145).
+ * Segment i reads audio[seg_start[i] : seg_start[i]+seg_len[i]]; samples of its 32768+1920
+ * sample window at or past seg_len read as zeros (seg_len <= 32768 reproduces the reference's
+ * per-segment transform; up to 34688 lets the last frames see the following samples, which is
+ * how compute_spectrogram on a longer signal is tiled).  valid_frames[i] = `paddings[i]`; rows at or
+ * past it are zero.  Outputs (n_seg, 256, 512): out_f32 and/or out_bf16 (either may be NULL). */
+int mrmt3_logmel(mrmt3_handle* h, const float* audio, const int64_t* seg_start,
+                 const int32_t* seg_len, const int32_t* valid_frames, int n_seg, int flags,
+                 float* out_f32, void* out_bf16, void* stream);
+
+/* ---- encoder ---------------------------------------------------------------------------
+ * Replaces: self.proj + self.encoder(...) (models/t5.py:253-258, T5Stack :507-702).
+ * mel (B,256,512) fp32 -> enc_out (B,256,512) fp32 (final-normed encoder states). */
+int mrmt3_encode(mrmt3_handle* h, const float* mel, int B, float* enc_out, void* stream);
+
+/* ---- greedy transcription --------------------------------------------------------------
+ * Replaces: T5ForConditionalGeneration.generate (models/t5.py:251-302).
+ * mel (B,256,512) fp32 -> out_ids (B, max_length+1) int64, col 0 = start token, rows padded
+ * with pad_id after their EOS; *steps_host = number of decode steps the reference loop would
+ * have run (its output is out_ids[:, :1+steps]).
+ * Debug / parity hooks (both may be NULL): forced_ids (B, max_length+1) int64 feeds these
+ * tokens instead of the arg-max (teacher forcing through the KV-cached step kernels);
+ * logits_out (B, max_length, vocab) fp32 receives every step's logits. */
+int mrmt3_generate(mrmt3_handle* h, const float* mel, int B, int max_length, int64_t* out_ids,
+                   int32_t* steps_host, const int64_t* forced_ids, float* logits_out,
+                   void* stream);
+
+/* Replaces: T5SegMemV2WithPrev.generate (models/t5_segmem_v2_with_prev.py:226-297) and
+ * T5SegMem.generate_2 (models/t5_segmem.py:172-252), batched ACROSS tracks: the segments of
+ * one track are decoded in order (each one's memory block is built from the previous output
+ * row), and all tracks advance one segment per round so the decode batch is n_tracks wide.
+ * mel (S_total,256,512) fp32, tracks concatenated; seg_counts_host[n_tracks] segments per
+ * track (sum = S_total).  out_ids (S_total, max_length) int64 in the same order.
+ * n_tracks = 1 is exactly the reference call on one (S,256,512) batch.
+ * logits_out (optional): (S_total, max_length, vocab) fp32. */
+int mrmt3_generate_segmem(mrmt3_handle* h, const float* mel, const int32_t* seg_counts_host,
+                          int n_tracks, int max_length, int64_t* out_ids, float* logits_out,
+                          void* stream);
+
+/* ---- teacher-forced forward ------------------------------------------------------------
+ * Replaces: model.forward / get_model_outputs (models/t5.py:99-249,
+ * models/t5_segmem_v2_with_prev.py:60-224): logits (B, L, vocab) fp32 for
+ * decoder_input_ids (B, L) int64 (= _shift_right(labels)); targets_prev (B, Lp) int64 with
+ * -100 already replaced by pad (NULL when mem_variant == NONE). */
+int mrmt3_forward_logits(mrmt3_handle* h, const float* mel, int B, const int64_t* decoder_input_ids,
+                         int L, const int64_t* targets_prev, int Lp, float* logits_out,
+                         void* stream);
+
+/* memory block alone (models/t5_segmem_v2_with_prev.py:121-123): prev_ids (B, Lp) int64 ->
+ * mem_out (B, min(mem_len, Lp), 512) fp32 */
+int mrmt3_memory_block(mrmt3_handle* h, const int64_t* prev_ids, int B, int Lp, float* mem_out,
+                       void* stream);
+
+/* ---- end to end from host buffers ------------------------------------------------------
+ * Replaces: InferenceHandler.inference up to the token rows (inference.py:149-191): pinned or
+ * pageable HOST audio in, HOST token rows out; H2D, log-mel, encode, greedy decode and D2H all
+ * inside the call.  Segment tables as in mrmt3_logmel but on the host.  When the handle has a
+ * memory variant, seg_counts_host/n_tracks describe the tracks (as mrmt3_generate_segmem) and
+ * out_ids_host is (n_seg, max_length); otherwise seg_counts_host may be NULL and out_ids_host
+ * is (n_seg, max_length+1) with *steps_host set. */
+int mrmt3_transcribe_host(mrmt3_handle* h, const float* audio_host, int64_t n_samples,
+                          const int64_t* seg_start_host, const int32_t* seg_len_host,
+                          const int32_t* valid_frames_host, int n_seg,
+                          const int32_t* seg_counts_host, int n_tracks, int flags, int max_length,
+                          int64_t* out_ids_host, int32_t* steps_host, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* MRMT3_B200_H_ */

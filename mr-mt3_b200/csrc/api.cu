@@ -1,0 +1,181 @@
+// extern "C" boundary (include/mrmt3_b200.h).  Status -> int + message; nothing throws across.
+#include <new>
+
+#include "model.cuh"
+
+namespace mrmt3 {
+Status handle_init(mrmt3_handle* h);
+void handle_destroy(mrmt3_handle* h);
+Status set_weight(mrmt3_handle* h, const std::string& name, const float* data, int rows, int cols);
+Status commit_weights(mrmt3_handle* h);
+Status api_encode(mrmt3_handle* h, const float* mel, int B, float* enc_out, cudaStream_t s);
+Status generate_base(mrmt3_handle* h, const float* mel_f32, const bf16* mel_bf16, int B, int max_length,
+                     long long* out_ids, int* steps_host, const long long* forced, float* logits_out,
+                     cudaStream_t s);
+Status generate_segmem(mrmt3_handle* h, const float* mel_f32, const bf16* mel_bf16, const int* seg_counts,
+                       int n_tracks, int max_length, long long* out_ids, float* logits_out, cudaStream_t s);
+Status api_memory_block(mrmt3_handle* h, const long long* prev_ids, int B, int Lp, float* mem_out, cudaStream_t s);
+Status api_forward_logits(mrmt3_handle* h, const float* mel, int B, const long long* dec_ids, int L,
+                          const long long* targets_prev, int Lp, float* logits_out, cudaStream_t s);
+Status api_logmel(mrmt3_handle* h, const float* audio, const long long* seg_start, const int* seg_len,
+                  const int* valid_frames, int n_seg, int flags, float* out_f32, bf16* out_bf16, cudaStream_t s);
+Status api_transcribe_host(mrmt3_handle* h, const float* audio_host, long long n_samples,
+                           const long long* seg_start_host, const int* seg_len_host,
+                           const int* valid_frames_host, int n_seg, const int* seg_counts_host, int n_tracks,
+                           int flags, int max_length, long long* out_ids_host, int* steps_host, cudaStream_t s);
+}  // namespace mrmt3
+
+using namespace mrmt3;
+
+static std::string g_create_error;
+
+static int finish(mrmt3_handle* h, const Status& st) {
+    if (st.ok()) return 0;
+    if (h) h->err = st.msg;
+    // leave the CUDA error state clean for the caller's next call
+    cudaGetLastError();
+    return st.code ? st.code : 1;
+}
+
+#define GUARD(h)                         \
+    if (!(h)) return 1;                  \
+    try {
+#define END_GUARD(h)                                             \
+    }                                                            \
+    catch (const std::exception& e) {                            \
+        (h)->err = std::string("C++ exception: ") + e.what();    \
+        return 1;                                                \
+    }                                                            \
+    catch (...) {                                                \
+        (h)->err = "unknown C++ exception";                      \
+        return 1;                                                \
+    }
+
+#pragma GCC visibility push(default)
+extern "C" {
+
+int mrmt3_create(const mrmt3_config* cfg, int device, mrmt3_handle** out) {
+    if (!cfg || !out) {
+        g_create_error = "null argument";
+        return 1;
+    }
+    *out = nullptr;
+    mrmt3_handle* h = new (std::nothrow) mrmt3_handle();
+    if (!h) {
+        g_create_error = "out of host memory";
+        return 1;
+    }
+    try {
+        h->cfg = *cfg;
+        h->device = device;
+        Status st = handle_init(h);
+        if (!st.ok()) {
+            g_create_error = st.msg;
+            cudaGetLastError();
+            handle_destroy(h);
+            delete h;
+            return st.code ? st.code : 1;
+        }
+    } catch (const std::exception& e) {
+        g_create_error = std::string("C++ exception: ") + e.what();
+        delete h;
+        return 1;
+    }
+    *out = h;
+    return 0;
+}
+
+void mrmt3_destroy(mrmt3_handle* h) {
+    if (!h) return;
+    try {
+        handle_destroy(h);
+    } catch (...) {
+    }
+    delete h;
+}
+
+const char* mrmt3_last_error(const mrmt3_handle* h) { return h ? h->err.c_str() : g_create_error.c_str(); }
+
+int64_t mrmt3_launch_count(const mrmt3_handle* h) { return h ? h->launches : 0; }
+
+int mrmt3_set_weight(mrmt3_handle* h, const char* name, const float* data, int rows, int cols) {
+    GUARD(h)
+    if (!name || !data) return finish(h, Error(1, "null argument"));
+    return finish(h, set_weight(h, name, data, rows, cols));
+    END_GUARD(h)
+}
+
+int mrmt3_commit_weights(mrmt3_handle* h) {
+    GUARD(h)
+    return finish(h, commit_weights(h));
+    END_GUARD(h)
+}
+
+int mrmt3_set_mel_filterbank(mrmt3_handle* h, const float* fb_host) {
+    GUARD(h)
+    if (!fb_host) return finish(h, Error(1, "null argument"));
+    cudaSetDevice(h->device);
+    return finish(h, h->frontend.set_filterbank(fb_host));
+    END_GUARD(h)
+}
+
+int mrmt3_logmel(mrmt3_handle* h, const float* audio, const int64_t* seg_start, const int32_t* seg_len,
+                 const int32_t* valid_frames, int n_seg, int flags, float* out_f32, void* out_bf16,
+                 void* stream) {
+    GUARD(h)
+    return finish(h, api_logmel(h, audio, (const long long*)seg_start, seg_len, valid_frames, n_seg, flags,
+                                out_f32, (bf16*)out_bf16, (cudaStream_t)stream));
+    END_GUARD(h)
+}
+
+int mrmt3_encode(mrmt3_handle* h, const float* mel, int B, float* enc_out, void* stream) {
+    GUARD(h)
+    return finish(h, api_encode(h, mel, B, enc_out, (cudaStream_t)stream));
+    END_GUARD(h)
+}
+
+int mrmt3_generate(mrmt3_handle* h, const float* mel, int B, int max_length, int64_t* out_ids,
+                   int32_t* steps_host, const int64_t* forced_ids, float* logits_out, void* stream) {
+    GUARD(h)
+    return finish(h, generate_base(h, mel, nullptr, B, max_length, (long long*)out_ids, steps_host,
+                                   (const long long*)forced_ids, logits_out, (cudaStream_t)stream));
+    END_GUARD(h)
+}
+
+int mrmt3_generate_segmem(mrmt3_handle* h, const float* mel, const int32_t* seg_counts_host, int n_tracks,
+                          int max_length, int64_t* out_ids, float* logits_out, void* stream) {
+    GUARD(h)
+    if (!seg_counts_host) return finish(h, Error(1, "null seg_counts_host"));
+    return finish(h, generate_segmem(h, mel, nullptr, seg_counts_host, n_tracks, max_length,
+                                     (long long*)out_ids, logits_out, (cudaStream_t)stream));
+    END_GUARD(h)
+}
+
+int mrmt3_forward_logits(mrmt3_handle* h, const float* mel, int B, const int64_t* decoder_input_ids, int L,
+                         const int64_t* targets_prev, int Lp, float* logits_out, void* stream) {
+    GUARD(h)
+    return finish(h, api_forward_logits(h, mel, B, (const long long*)decoder_input_ids, L,
+                                        (const long long*)targets_prev, Lp, logits_out, (cudaStream_t)stream));
+    END_GUARD(h)
+}
+
+int mrmt3_memory_block(mrmt3_handle* h, const int64_t* prev_ids, int B, int Lp, float* mem_out, void* stream) {
+    GUARD(h)
+    return finish(h, api_memory_block(h, (const long long*)prev_ids, B, Lp, mem_out, (cudaStream_t)stream));
+    END_GUARD(h)
+}
+
+int mrmt3_transcribe_host(mrmt3_handle* h, const float* audio_host, int64_t n_samples,
+                          const int64_t* seg_start_host, const int32_t* seg_len_host,
+                          const int32_t* valid_frames_host, int n_seg, const int32_t* seg_counts_host,
+                          int n_tracks, int flags, int max_length, int64_t* out_ids_host, int32_t* steps_host,
+                          void* stream) {
+    GUARD(h)
+    return finish(h, api_transcribe_host(h, audio_host, n_samples, (const long long*)seg_start_host, seg_len_host,
+                                         valid_frames_host, n_seg, seg_counts_host, n_tracks, flags, max_length,
+                                         (long long*)out_ids_host, steps_host, (cudaStream_t)stream));
+    END_GUARD(h)
+}
+
+}  // extern "C"
+#pragma GCC visibility pop

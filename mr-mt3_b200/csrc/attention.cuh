@@ -1,0 +1,57 @@
+// Parameter blocks and launchers of the attention kernels (attention.cu).
+#pragma once
+#include "common.cuh"
+
+namespace mrmt3 {
+
+// whole-sequence attention; strides in elements: element (b, head, row, d) of X lives at
+// X + b*x_batch_stride + head*x_head_stride + row*x_row_stride + d
+struct AttnFullParams {
+    const bf16* Q;
+    long q_batch_stride;
+    long q_head_stride;
+    int q_row_stride;
+    const bf16* K;
+    long k_batch_stride;
+    long k_head_stride;
+    int k_row_stride;
+    const bf16* V;
+    long v_batch_stride;
+    long v_head_stride;
+    int v_row_stride;
+    bf16* O;
+    long o_batch_stride;
+    long o_head_stride;
+    int o_row_stride;
+    int Tq, Tk;
+    int causal;         // key j visible to query i iff j <= i + causal_offset
+    int causal_offset;
+};
+Status launch_attn_full(const AttnFullParams& p, int batch, cudaStream_t stream);
+
+// decode-step attention (one query per lane and head)
+struct AttnDecodeParams {
+    const bf16* q;        // (lanes, q_stride): self -> fused [q|k|v] row; cross -> q row
+    int q_stride;
+    bf16* out;            // (lanes, out_stride) context, heads concatenated
+    int out_stride;
+    const bf16* kv_pool;  // self: page pool; cross: cross cache
+    int layer;
+    int n_layers;
+    // paged self-attention
+    const int* step_ptr;     // device scalar: position of the token being decoded
+    int pos_offset;
+    const int* block_table;  // (lanes, max_pages) page ids
+    int max_pages;
+    size_t page_stride;      // elements per page (all layers, k and v, all heads)
+    // cross-attention
+    int tk_cap;
+    int n_keys;              // keys per lane when n_keys_ptr == nullptr
+    const int* n_keys_ptr;   // optional per-lane key count
+    // early-exit mask: lanes with active[lane] == 0 are skipped
+    const int* active;
+};
+Status launch_attn_decode(const AttnDecodeParams& p, int n_lanes, bool paged, cudaStream_t stream);
+int attn_decode_max_keys();
+
+}  // namespace mrmt3

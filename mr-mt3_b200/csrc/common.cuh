@@ -1,0 +1,132 @@
+// Shared device/host helpers for the mrmt3_b200 CUDA library (sm_100a only).
+#pragma once
+#include <cuda_bf16.h>
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include <cstdio>
+#include <string>
+
+namespace mrmt3 {
+
+typedef __nv_bfloat16 bf16;
+typedef __nv_bfloat162 bf162;
+
+// model constants of the path (reference pretrained/config.json, contrib/spectrograms.py:34-41)
+constexpr int kDModel = 512;
+constexpr int kHeads = 6;
+constexpr int kDKV = 64;
+constexpr int kInner = kHeads * kDKV;  // 384
+constexpr int kDFF = 1024;
+constexpr int kVocab = 1536;
+constexpr int kSegFrames = 256;
+constexpr int kHop = 128;
+constexpr int kNFFT = 2048;
+constexpr int kMels = 512;
+constexpr int kSegSamples = kSegFrames * kHop;  // 32768
+constexpr int kKVPage = 128;                    // positions per KV-cache page
+
+// ---- error plumbing: no C++ exceptions cross the C ABI -------------------------------------
+struct Status {
+    int code;
+    std::string msg;
+    bool ok() const { return code == 0; }
+};
+
+#define MRMT3_CUDA_TRY(expr)                                                               \
+    do {                                                                                   \
+        cudaError_t _e = (expr);                                                           \
+        if (_e != cudaSuccess) {                                                           \
+            char _b[512];                                                                  \
+            snprintf(_b, sizeof(_b), "%s:%d: %s -> %s", __FILE__, __LINE__, #expr,         \
+                     cudaGetErrorString(_e));                                              \
+            return ::mrmt3::Status{(int)_e == 0 ? 1 : (int)_e, _b};                        \
+        }                                                                                  \
+    } while (0)
+
+#define MRMT3_TRY(expr)                  \
+    do {                                 \
+        ::mrmt3::Status _s = (expr);     \
+        if (!_s.ok()) return _s;         \
+    } while (0)
+
+#define MRMT3_CHECK_LAUNCH() MRMT3_CUDA_TRY(cudaGetLastError())
+
+inline Status OkStatus() { return Status{0, ""}; }
+inline Status Error(int code, const std::string& m) { return Status{code, m}; }
+
+// ---- small device helpers -------------------------------------------------------------------
+__device__ __forceinline__ uint32_t smem_u32(const void* p) {
+    return static_cast<uint32_t>(__cvta_generic_to_shared(p));
+}
+
+// cp.async 16 B with zero-fill when !pred (src-size 0)
+__device__ __forceinline__ void cp_async16(void* smem_dst, const void* gmem_src, bool pred) {
+    uint32_t d = smem_u32(smem_dst);
+    int sz = pred ? 16 : 0;
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;\n" ::"r"(d), "l"(gmem_src), "r"(sz));
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;\n" ::); }
+template <int N>
+__device__ __forceinline__ void cp_async_wait() {
+    asm volatile("cp.async.wait_group %0;\n" ::"n"(N));
+}
+
+__device__ __forceinline__ void ldmatrix_x4(uint32_t& r0, uint32_t& r1, uint32_t& r2, uint32_t& r3,
+                                            uint32_t addr) {
+    asm volatile("ldmatrix.sync.aligned.m8n8.x4.shared.b16 {%0,%1,%2,%3}, [%4];\n"
+                 : "=r"(r0), "=r"(r1), "=r"(r2), "=r"(r3)
+                 : "r"(addr));
+}
+__device__ __forceinline__ void ldmatrix_x4_trans(uint32_t& r0, uint32_t& r1, uint32_t& r2,
+                                                  uint32_t& r3, uint32_t addr) {
+    asm volatile("ldmatrix.sync.aligned.m8n8.x4.trans.shared.b16 {%0,%1,%2,%3}, [%4];\n"
+                 : "=r"(r0), "=r"(r1), "=r"(r2), "=r"(r3)
+                 : "r"(addr));
+}
+
+// D(16x8,f32) += A(16x16,bf16,row) * B(16x8,bf16,col)
+__device__ __forceinline__ void mma_bf16_16816(float (&d)[4], const uint32_t (&a)[4], uint32_t b0,
+                                               uint32_t b1) {
+    asm volatile(
+        "mma.sync.aligned.m16n8k16.row.col.f32.bf16.bf16.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, "
+        "{%8,%9}, {%0,%1,%2,%3};\n"
+        : "+f"(d[0]), "+f"(d[1]), "+f"(d[2]), "+f"(d[3])
+        : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1));
+}
+
+__device__ __forceinline__ uint32_t pack_bf16(float lo, float hi) {
+    bf162 v = __floats2bfloat162_rn(lo, hi);
+    return *reinterpret_cast<uint32_t*>(&v);
+}
+
+__device__ __forceinline__ float warp_sum(float v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    return v;
+}
+__device__ __forceinline__ float warp_max(float v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v = fmaxf(v, __shfl_xor_sync(0xffffffffu, v, o));
+    return v;
+}
+
+// gelu_new (tanh form), reference via HF ACT2FN["gelu_new"]
+__device__ __forceinline__ float gelu_new(float a) {
+    const float k = 0.7978845608028654f;  // sqrt(2/pi)
+    float inner = k * (a + 0.044715f * a * a * a);
+    return 0.5f * a * (1.0f + tanhf(inner));
+}
+
+// streaming 16 B load that does not allocate in L1 (KV cache / one-shot reads)
+__device__ __forceinline__ uint4 ld_stream16(const void* p) {
+    uint4 r;
+    asm volatile("ld.global.nc.L1::no_allocate.v4.u32 {%0,%1,%2,%3}, [%4];\n"
+                 : "=r"(r.x), "=r"(r.y), "=r"(r.z), "=r"(r.w)
+                 : "l"(p));
+    return r;
+}
+
+inline int ceil_div(int a, int b) { return (a + b - 1) / b; }
+
+}  // namespace mrmt3

@@ -1,0 +1,989 @@
+// Host-side drivers of the path: weight packing, encoder, memory block, cross-K/V projection,
+// the KV-cached greedy decode loop (CUDA-graph replay per step, masked early exit) and the
+// cross-track segment scheduler of MR-MT3.  Mirrors, stage by stage, what the reference does in
+// models/t5.py:251-302 and models/t5_segmem_v2_with_prev.py:226-297 -- with a KV cache instead
+// of the reference's full-prefix recompute.
+#include "model.cuh"
+
+#include <algorithm>
+#include <cmath>
+#include <cstring>
+
+#include "gemm_mma.cuh"
+
+using namespace mrmt3;
+
+namespace mrmt3 {
+
+// ---------------------------------------------------------------------------------------------
+Status DeviceBuffer::reserve(size_t bytes, bool* moved) {
+    if (moved) *moved = false;
+    if (bytes <= cap) return OkStatus();
+    if (p) MRMT3_CUDA_TRY(cudaFree(p));
+    p = nullptr;
+    cap = 0;
+    size_t want = (bytes + 255) & ~size_t(255);
+    MRMT3_CUDA_TRY(cudaMalloc(&p, want));
+    cap = want;
+    if (moved) *moved = true;
+    return OkStatus();
+}
+void DeviceBuffer::release() {
+    if (p) cudaFree(p);
+    p = nullptr;
+    cap = 0;
+}
+
+Status RowWorkspace::reserve(int r) {
+    if (r <= rows) return OkStatus();
+    size_t n = (size_t)r;
+    MRMT3_TRY(x_bf16.reserve(n * kDModel * sizeof(bf16)));
+    MRMT3_TRY(h32.reserve(n * kDModel * sizeof(float)));
+    MRMT3_TRY(n_bf16.reserve(n * kDModel * sizeof(bf16)));
+    MRMT3_TRY(qkv.reserve(n * 3 * kInner * sizeof(bf16)));
+    MRMT3_TRY(ctx.reserve(n * kInner * sizeof(bf16)));
+    MRMT3_TRY(ff.reserve(n * kDFF * sizeof(bf16)));
+    MRMT3_TRY(qc.reserve(n * kInner * sizeof(bf16)));
+    rows = r;
+    return OkStatus();
+}
+void RowWorkspace::release() {
+    x_bf16.release(); h32.release(); n_bf16.release(); qkv.release(); ctx.release();
+    ff.release(); qc.release(); hc32.release(); ctx_c.release();
+    rows = 0;
+}
+
+constexpr int kMaxLanes = 512;    // decode lanes per wave
+constexpr int kEncChunk = 256;    // encoder segments per pass (bounds the row workspace)
+constexpr int kNPos = 5000;       // FixedPositionalEmbedding max_length, reference models/t5.py:706
+constexpr int kPollEvery = 8;     // decode steps between early-exit polls
+
+#define RUN(h, call)          \
+    do {                      \
+        MRMT3_TRY(call);      \
+        ++(h)->launches;      \
+    } while (0)
+
+static size_t page_elems(const mrmt3_handle* h) {
+    return (size_t)h->cfg.n_dec_layers * 2 * kHeads * kKVPage * kDKV;
+}
+
+// ---------------------------------------------------------------------------------------------
+// weights
+static Status arena_take(mrmt3_handle* h, size_t bytes, void** out) {
+    size_t off = (h->arena_used + 255) & ~size_t(255);
+    if (off + bytes > h->arena.cap) return Error(2, "weight arena overflow");
+    *out = (char*)h->arena.p + off;
+    h->arena_used = off + bytes;
+    return OkStatus();
+}
+
+static Status alloc_stack(mrmt3_handle* h, StackW& st, int n_layers, bool decoder) {
+    st.layers.resize(n_layers);
+    for (auto& L : st.layers) {
+        MRMT3_TRY(arena_take(h, (size_t)3 * kInner * kDModel * 2, (void**)&L.wqkv));
+        MRMT3_TRY(arena_take(h, (size_t)kDModel * kInner * 2, (void**)&L.wo));
+        MRMT3_TRY(arena_take(h, kDModel * 4, (void**)&L.ln_self));
+        if (decoder) {
+            MRMT3_TRY(arena_take(h, (size_t)kInner * kDModel * 2, (void**)&L.cq));
+            MRMT3_TRY(arena_take(h, (size_t)kDModel * kInner * 2, (void**)&L.co));
+            MRMT3_TRY(arena_take(h, kDModel * 4, (void**)&L.ln_cross));
+        }
+        MRMT3_TRY(arena_take(h, (size_t)2 * kDFF * kDModel * 2, (void**)&L.wi));
+        MRMT3_TRY(arena_take(h, (size_t)kDModel * kDFF * 2, (void**)&L.wff));
+        MRMT3_TRY(arena_take(h, kDModel * 4, (void**)&L.ln_ff));
+    }
+    MRMT3_TRY(arena_take(h, kDModel * 4, (void**)&st.final_ln));
+    return OkStatus();
+}
+
+Status handle_init(mrmt3_handle* h) {
+    const mrmt3_config& c = h->cfg;
+    if (c.d_model != kDModel || c.n_heads != kHeads || c.d_kv != kDKV || c.d_ff != kDFF ||
+        c.vocab != kVocab)
+        return Error(2, "this build is specialised for the MT3 shape: d_model 512, 6 heads x 64, "
+                        "d_ff 1024, vocab 1536 (reference pretrained/config.json)");
+    if (c.n_enc_layers < 1 || c.n_dec_layers < 1 || c.n_enc_layers > 64 || c.n_dec_layers > 64)
+        return Error(2, "bad layer count");
+    if (c.mem_variant < 0 || c.mem_variant > 2) return Error(2, "bad mem_variant");
+    if (c.mem_variant != MRMT3_MEM_NONE && (c.n_mem_layers < 1 || c.mem_len < 1 || c.mem_len > 512))
+        return Error(2, "memory variant needs n_mem_layers >= 1 and 1 <= mem_len <= 512");
+    MRMT3_CUDA_TRY(cudaSetDevice(h->device));
+    int n_mem = c.mem_variant ? c.n_mem_layers : 0;
+    size_t per_enc = (size_t)(3 * kInner * kDModel + kDModel * kInner + 2 * kDFF * kDModel + kDModel * kDFF) * 2 + 3 * 4096;
+    size_t per_dec = per_enc + (size_t)(2 * kInner * kDModel) * 2 + 2 * 4096;
+    size_t total = (size_t)kDModel * kDModel * 2 * 2 + (size_t)kVocab * kDModel * (4 + 2) +
+                   (size_t)c.n_dec_layers * 2 * kInner * kDModel * 2 +
+                   per_enc * (c.n_enc_layers + n_mem) + per_dec * c.n_dec_layers +
+                   (size_t)kNPos * kDModel * 4 + (1 << 20);
+    MRMT3_TRY(h->arena.reserve(total));
+    MRMT3_CUDA_TRY(cudaMemset(h->arena.p, 0, h->arena.cap));
+    MRMT3_TRY(arena_take(h, (size_t)kDModel * kDModel * 2, (void**)&h->proj));
+    MRMT3_TRY(arena_take(h, (size_t)kVocab * kDModel * 4, (void**)&h->emb));
+    MRMT3_TRY(arena_take(h, (size_t)kVocab * kDModel * 2, (void**)&h->lm_head));
+    MRMT3_TRY(arena_take(h, (size_t)c.n_dec_layers * 2 * kInner * kDModel * 2, (void**)&h->cross_kv_w));
+    MRMT3_TRY(alloc_stack(h, h->enc, c.n_enc_layers, false));
+    MRMT3_TRY(alloc_stack(h, h->dec, c.n_dec_layers, true));
+    if (n_mem) {
+        MRMT3_TRY(arena_take(h, (size_t)kDModel * kDModel * 2, (void**)&h->segmem_proj));
+        MRMT3_TRY(alloc_stack(h, h->mem, n_mem, false));
+    }
+    MRMT3_TRY(arena_take(h, (size_t)kNPos * kDModel * 4, (void**)&h->pe));
+    h->n_pos = kNPos;
+    MRMT3_TRY(h->stage.reserve((size_t)2 * kDFF * kDModel * 4));
+    MRMT3_TRY(h->frontend.init());
+    MRMT3_CUDA_TRY(cudaMallocHost((void**)&h->h_pinned, (kMaxLanes + 64) * sizeof(int)));
+    MRMT3_CUDA_TRY(cudaEventCreateWithFlags(&h->poll_ev[0], cudaEventDisableTiming));
+    MRMT3_CUDA_TRY(cudaEventCreateWithFlags(&h->poll_ev[1], cudaEventDisableTiming));
+    const char* ng = getenv("MRMT3_NO_GRAPH");
+    h->use_graphs = !(ng && ng[0] == '1');
+    return OkStatus();
+}
+
+static void destroy_graphs(mrmt3_handle* h) {
+    for (auto& kv : h->graphs)
+        if (kv.second.exec) cudaGraphExecDestroy(kv.second.exec);
+    h->graphs.clear();
+}
+
+// buffers whose address is baked into captured decode-step graphs
+static Status reserve_graph_visible(mrmt3_handle* h, DeviceBuffer& b, size_t bytes) {
+    bool moved = false;
+    MRMT3_TRY(b.reserve(bytes, &moved));
+    if (moved) destroy_graphs(h);
+    return OkStatus();
+}
+
+void handle_destroy(mrmt3_handle* h) {
+    cudaSetDevice(h->device);
+    cudaDeviceSynchronize();
+    destroy_graphs(h);
+    h->frontend.destroy();
+    h->arena.release(); h->stage.release(); h->rows.release(); h->enc_bf16.release();
+    h->mem_bf16.release(); h->mem_f32.release(); h->mel_f32.release(); h->mel_bf16.release();
+    h->audio.release(); h->seg_tab.release(); h->ids_dev.release(); h->tok_out.release(); h->dummy_ids.release();
+    h->d_h32.release(); h->d_n_bf16.release(); h->d_qkv.release(); h->d_ctx.release();
+    h->d_qc.release(); h->d_ff.release(); h->d_logits.release(); h->d_state.release();
+    h->kv_pool.release(); h->block_table.release(); h->cross_cache.release(); h->lane_tab.release();
+    if (h->h_pinned) cudaFreeHost(h->h_pinned);
+    if (h->poll_ev[0]) cudaEventDestroy(h->poll_ev[0]);
+    if (h->poll_ev[1]) cudaEventDestroy(h->poll_ev[1]);
+}
+
+static Status pack(mrmt3_handle* h, const float* src, int rows, int cols, int want_rows,
+                   int want_cols, bf16* dst, int row_mul, int row_off) {
+    if (rows != want_rows || cols != want_cols) {
+        char b[160];
+        snprintf(b, sizeof(b), "shape mismatch: got (%d,%d), expected (%d,%d)", rows, cols, want_rows, want_cols);
+        return Error(2, b);
+    }
+    size_t bytes = (size_t)rows * cols * 4;
+    MRMT3_TRY(h->stage.reserve(bytes));
+    MRMT3_CUDA_TRY(cudaMemcpy(h->stage.p, src, bytes, cudaMemcpyDefault));
+    MRMT3_TRY(launch_pack_weight(h->stage.as<float>(), dst, rows, cols, row_mul, row_off, 0));
+    MRMT3_CUDA_TRY(cudaStreamSynchronize(0));
+    return OkStatus();
+}
+
+static Status copy_f32(const float* src, int rows, int cols, int want, float* dst) {
+    if (rows * cols != want) return Error(2, "shape mismatch for fp32 vector");
+    MRMT3_CUDA_TRY(cudaMemcpy(dst, src, (size_t)want * 4, cudaMemcpyDefault));
+    return OkStatus();
+}
+
+Status set_weight(mrmt3_handle* h, const std::string& name, const float* data, int rows, int cols) {
+    MRMT3_CUDA_TRY(cudaSetDevice(h->device));
+    const int d = kDModel, in = kInner;
+    Status st = OkStatus();
+    bool known = true;
+    if (name == "proj.weight") st = pack(h, data, rows, cols, d, d, h->proj, 1, 0);
+    else if (name == "decoder_embed_tokens.weight") st = copy_f32(data, rows, cols, kVocab * d, h->emb);
+    else if (name == "lm_head.weight") st = pack(h, data, rows, cols, kVocab, d, h->lm_head, 1, 0);
+    else if (name == "segmem_proj.weight") {
+        if (!h->segmem_proj) return Error(3, "segmem_proj.weight given to a model without a memory variant");
+        st = pack(h, data, rows, cols, d, d, h->segmem_proj, 1, 0);
+    } else if (name == "decoder.block.0.layer.1.EncDecAttention.relative_attention_bias.weight") {
+        return OkStatus();  // ignored by the reference too (models/t5.py:43-45)
+    } else {
+        struct { const char* n; StackW* s; bool dec; } stacks[] = {
+            {"encoder.", &h->enc, false}, {"decoder.", &h->dec, true}, {"segmem_encoder.", &h->mem, false}};
+        known = false;
+        for (auto& sk : stacks) {
+            size_t pl = strlen(sk.n);
+            if (name.compare(0, pl, sk.n) != 0) continue;
+            std::string rest = name.substr(pl);
+            if (sk.s == &h->mem && !h->segmem_proj) return Error(3, "segmem weights given to a model without a memory variant");
+            if (rest == "embed_tokens.weight") return OkStatus();  // alias of proj / embedding / segmem_proj
+            if (rest == "pos_emb.inv_freq") {
+                if (rows * cols != 256) return Error(2, "inv_freq must have 256 entries");
+                MRMT3_CUDA_TRY(cudaMemcpy(h->inv_freq, data, 256 * 4, cudaMemcpyDefault));
+                h->have_inv_freq = true;
+                return OkStatus();
+            }
+            if (rest == "final_layer_norm.weight") { known = true; st = copy_f32(data, rows, cols, d, sk.s->final_ln); break; }
+            int bi = -1, li = -1, consumed = 0;
+            if (sscanf(rest.c_str(), "block.%d.layer.%d.%n", &bi, &li, &consumed) < 2 || consumed == 0) break;
+            if (bi < 0 || bi >= (int)sk.s->layers.size()) return Error(3, "block index out of range: " + name);
+            LayerW& L = sk.s->layers[bi];
+            std::string sub = rest.substr(consumed);
+            const int ff_idx = sk.dec ? 2 : 1;
+            known = true;
+            if (li == 0 && sub == "SelfAttention.q.weight") st = pack(h, data, rows, cols, in, d, L.wqkv, 1, 0);
+            else if (li == 0 && sub == "SelfAttention.k.weight") st = pack(h, data, rows, cols, in, d, L.wqkv, 1, in);
+            else if (li == 0 && sub == "SelfAttention.v.weight") st = pack(h, data, rows, cols, in, d, L.wqkv, 1, 2 * in);
+            else if (li == 0 && sub == "SelfAttention.o.weight") st = pack(h, data, rows, cols, d, in, L.wo, 1, 0);
+            else if (li == 0 && sub == "layer_norm.weight") st = copy_f32(data, rows, cols, d, L.ln_self);
+            else if (sk.dec && li == 1 && sub == "EncDecAttention.q.weight") st = pack(h, data, rows, cols, in, d, L.cq, 1, 0);
+            else if (sk.dec && li == 1 && sub == "EncDecAttention.k.weight") st = pack(h, data, rows, cols, in, d, h->cross_kv_w, 1, bi * 2 * in);
+            else if (sk.dec && li == 1 && sub == "EncDecAttention.v.weight") st = pack(h, data, rows, cols, in, d, h->cross_kv_w, 1, bi * 2 * in + in);
+            else if (sk.dec && li == 1 && sub == "EncDecAttention.o.weight") st = pack(h, data, rows, cols, d, in, L.co, 1, 0);
+            else if (sk.dec && li == 1 && sub == "layer_norm.weight") st = copy_f32(data, rows, cols, d, L.ln_cross);
+            else if (li == ff_idx && sub == "DenseReluDense.wi_0.weight") st = pack(h, data, rows, cols, kDFF, d, L.wi, 2, 0);
+            else if (li == ff_idx && sub == "DenseReluDense.wi_1.weight") st = pack(h, data, rows, cols, kDFF, d, L.wi, 2, 1);
+            else if (li == ff_idx && sub == "DenseReluDense.wo.weight") st = pack(h, data, rows, cols, d, kDFF, L.wff, 1, 0);
+            else if (li == ff_idx && sub == "layer_norm.weight") st = copy_f32(data, rows, cols, d, L.ln_ff);
+            else known = false;
+            break;
+        }
+    }
+    if (!known) return Error(3, "unknown state-dict key: " + name);
+    if (!st.ok()) return Error(st.code, name + ": " + st.msg);
+    h->seen.insert(name);
+    h->committed = false;
+    return OkStatus();
+}
+
+static void required_stack(std::vector<std::string>& req, const std::string& s, int n, bool dec) {
+    for (int i = 0; i < n; ++i) {
+        std::string p = s + ".block." + std::to_string(i) + ".layer.";
+        for (const char* w : {"q", "k", "v", "o"}) req.push_back(p + "0.SelfAttention." + w + ".weight");
+        req.push_back(p + "0.layer_norm.weight");
+        int f = 1;
+        if (dec) {
+            for (const char* w : {"q", "k", "v", "o"}) req.push_back(p + "1.EncDecAttention." + w + ".weight");
+            req.push_back(p + "1.layer_norm.weight");
+            f = 2;
+        }
+        for (const char* w : {"wi_0", "wi_1", "wo"})
+            req.push_back(p + std::to_string(f) + ".DenseReluDense." + w + ".weight");
+        req.push_back(p + std::to_string(f) + ".layer_norm.weight");
+    }
+    req.push_back(s + ".final_layer_norm.weight");
+}
+
+Status commit_weights(mrmt3_handle* h) {
+    MRMT3_CUDA_TRY(cudaSetDevice(h->device));
+    std::vector<std::string> req = {"proj.weight", "decoder_embed_tokens.weight", "lm_head.weight"};
+    required_stack(req, "encoder", h->cfg.n_enc_layers, false);
+    required_stack(req, "decoder", h->cfg.n_dec_layers, true);
+    if (h->cfg.mem_variant) {
+        req.push_back("segmem_proj.weight");
+        required_stack(req, "segmem_encoder", h->cfg.n_mem_layers, false);
+    }
+    for (auto& r : req)
+        if (!h->seen.count(r)) return Error(4, "missing weight: " + r);
+    // sinusoid table, reference FixedPositionalEmbedding (models/t5.py:705-719): fp32 product
+    // position * inv_freq, then sin | cos halves
+    if (!h->have_inv_freq)
+        for (int j = 0; j < 256; ++j) h->inv_freq[j] = 1.0f / powf(10000.0f, (float)(2 * j) / (float)kDModel);
+    std::vector<float> pe((size_t)kNPos * kDModel);
+    for (int p = 0; p < kNPos; ++p)
+        for (int j = 0; j < 256; ++j) {
+            float ang = (float)p * h->inv_freq[j];
+            pe[(size_t)p * kDModel + j] = (float)std::sin((double)ang);
+            pe[(size_t)p * kDModel + 256 + j] = (float)std::cos((double)ang);
+        }
+    MRMT3_CUDA_TRY(cudaMemcpy(h->pe, pe.data(), pe.size() * 4, cudaMemcpyHostToDevice));
+    h->committed = true;
+    return OkStatus();
+}
+
+// ---------------------------------------------------------------------------------------------
+// encoder-type stack over `rows` rows organised as sequences of T rows.  Input: rows.h32 holds
+// embed + PE.  q_rows < T restricts the LAST layer's queries (and everything after it) to the
+// first q_rows rows of each sequence (memory block: only L_agg outputs are consumed, and a
+// row's output depends on other rows only through K/V, so this is exact).  Output: final-normed
+// states as bf16 (out_bf16) and/or fp32 (out_f32), (n_seq * q_rows, d).
+static Status run_encoder_stack(mrmt3_handle* h, const StackW& st, int n_seq, int T, int q_rows,
+                                bf16* out_bf16, float* out_f32, cudaStream_t s) {
+    RowWorkspace& w = h->rows;
+    const int M = n_seq * T;
+    float* hcur = w.h32.as<float>();
+    int Mcur = M;
+    const float eps = h->cfg.ln_eps;
+    for (size_t li = 0; li < st.layers.size(); ++li) {
+        const LayerW& L = st.layers[li];
+        const bool reduce = (li + 1 == st.layers.size()) && q_rows < T;
+        RUN(h, launch_rmsnorm(hcur, L.ln_self, eps, w.n_bf16.as<bf16>(), nullptr, M, nullptr, 1, s));
+        RUN(h, launch_gemm_mma(w.n_bf16.as<bf16>(), kDModel, ARowMap{nullptr, 1}, L.wqkv, kDModel, M,
+                               3 * kInner, kDModel, EpiStoreBf16{w.qkv.as<bf16>(), 3 * kInner}, s));
+        AttnFullParams ap{};
+        ap.Q = w.qkv.as<bf16>();
+        ap.K = ap.Q + kInner;
+        ap.V = ap.Q + 2 * kInner;
+        ap.q_batch_stride = ap.k_batch_stride = ap.v_batch_stride = (long)T * 3 * kInner;
+        ap.q_head_stride = ap.k_head_stride = ap.v_head_stride = kDKV;
+        ap.q_row_stride = ap.k_row_stride = ap.v_row_stride = 3 * kInner;
+        ap.Tk = T;
+        ap.causal = 0;
+        ap.causal_offset = 0;
+        ap.o_head_stride = kDKV;
+        ap.o_row_stride = kInner;
+        if (reduce) {
+            MRMT3_TRY(w.ctx_c.reserve((size_t)n_seq * q_rows * kInner * sizeof(bf16)));
+            MRMT3_TRY(w.hc32.reserve((size_t)n_seq * q_rows * kDModel * sizeof(float)));
+            ap.Tq = q_rows;
+            ap.O = w.ctx_c.as<bf16>();
+            ap.o_batch_stride = (long)q_rows * kInner;
+            RUN(h, launch_attn_full(ap, n_seq, s));
+            RUN(h, launch_gather_rows(hcur, w.hc32.as<float>(), n_seq, q_rows, T, s));
+            hcur = w.hc32.as<float>();
+            Mcur = n_seq * q_rows;
+            RUN(h, launch_gemm_mma(w.ctx_c.as<bf16>(), kInner, ARowMap{nullptr, 1}, L.wo, kInner, Mcur,
+                                   kDModel, kInner, EpiResidual{hcur, kDModel}, s));
+        } else {
+            ap.Tq = T;
+            ap.O = w.ctx.as<bf16>();
+            ap.o_batch_stride = (long)T * kInner;
+            RUN(h, launch_attn_full(ap, n_seq, s));
+            RUN(h, launch_gemm_mma(w.ctx.as<bf16>(), kInner, ARowMap{nullptr, 1}, L.wo, kInner, M, kDModel,
+                                   kInner, EpiResidual{hcur, kDModel}, s));
+        }
+        RUN(h, launch_rmsnorm(hcur, L.ln_ff, eps, w.n_bf16.as<bf16>(), nullptr, Mcur, nullptr, 1, s));
+        RUN(h, launch_gemm_mma(w.n_bf16.as<bf16>(), kDModel, ARowMap{nullptr, 1}, L.wi, kDModel, Mcur,
+                               2 * kDFF, kDModel, EpiGatedGelu{w.ff.as<bf16>(), kDFF}, s));
+        RUN(h, launch_gemm_mma(w.ff.as<bf16>(), kDFF, ARowMap{nullptr, 1}, L.wff, kDFF, Mcur, kDModel,
+                               kDFF, EpiResidual{hcur, kDModel}, s));
+    }
+    if (Mcur == M && q_rows < T) {
+        // no layer reduced (cannot happen with >= 1 layer), keep the contract anyway
+        MRMT3_TRY(w.hc32.reserve((size_t)n_seq * q_rows * kDModel * sizeof(float)));
+        RUN(h, launch_gather_rows(hcur, w.hc32.as<float>(), n_seq, q_rows, T, s));
+        hcur = w.hc32.as<float>();
+        Mcur = n_seq * q_rows;
+    }
+    RUN(h, launch_rmsnorm(hcur, st.final_ln, eps, out_bf16, out_f32, Mcur, nullptr, 1, s));
+    return OkStatus();
+}
+
+// proj + encoder over n_seg segments (reference models/t5.py:253-258).  Exactly one of
+// mel_f32 / mel_bf16 is given.
+static Status encode_segments(mrmt3_handle* h, const float* mel_f32, const bf16* mel_bf16, int n_seg,
+                              bf16* enc_out_bf16, float* enc_out_f32, cudaStream_t s) {
+    for (int c0 = 0; c0 < n_seg; c0 += kEncChunk) {
+        const int n = std::min(kEncChunk, n_seg - c0);
+        const int M = n * kSegFrames;
+        MRMT3_TRY(h->rows.reserve(M));
+        const bf16* x;
+        if (mel_bf16) {
+            x = mel_bf16 + (size_t)c0 * kSegFrames * kMels;
+        } else {
+            RUN(h, launch_cast_bf16(mel_f32 + (size_t)c0 * kSegFrames * kMels, h->rows.x_bf16.as<bf16>(),
+                                    (size_t)M * kMels, s));
+            x = h->rows.x_bf16.as<bf16>();
+        }
+        RUN(h, launch_gemm_mma(x, kDModel, ARowMap{nullptr, 1}, h->proj, kDModel, M, kDModel, kDModel,
+                               EpiPosAdd{h->rows.h32.as<float>(), kDModel, h->pe, kSegFrames, 0}, s));
+        MRMT3_TRY(run_encoder_stack(
+            h, h->enc, n, kSegFrames, kSegFrames,
+            enc_out_bf16 ? enc_out_bf16 + (size_t)c0 * kSegFrames * kDModel : nullptr,
+            enc_out_f32 ? enc_out_f32 + (size_t)c0 * kSegFrames * kDModel : nullptr, s));
+    }
+    return OkStatus();
+}
+
+// MR-MT3 memory block (reference models/t5_segmem_v2_with_prev.py:263-266):
+// Emb[ids] -> segmem_proj -> +PE -> memory encoder over all Lp positions -> first n_mem rows.
+// ids of lane l: ids[(src_row ? src_row[l] : l) * ids_stride + 0..Lp)
+static Status memory_block(mrmt3_handle* h, const long long* ids, long ids_stride, const int* src_row,
+                           int n_lanes, int Lp, int n_mem, bf16* out_bf16, float* out_f32,
+                           cudaStream_t s) {
+    const int chunk = std::max(1, (kEncChunk * kSegFrames) / Lp);
+    for (int c0 = 0; c0 < n_lanes; c0 += chunk) {
+        const int n = std::min(chunk, n_lanes - c0);
+        const int M = n * Lp;
+        MRMT3_TRY(h->rows.reserve(M));
+        RUN(h, launch_embed_bf16(src_row ? ids : ids + (size_t)c0 * ids_stride, ids_stride, Lp, n,
+                                 src_row ? src_row + c0 : nullptr, h->emb, h->rows.x_bf16.as<bf16>(), s));
+        RUN(h, launch_gemm_mma(h->rows.x_bf16.as<bf16>(), kDModel, ARowMap{nullptr, 1}, h->segmem_proj,
+                               kDModel, M, kDModel, kDModel,
+                               EpiPosAdd{h->rows.h32.as<float>(), kDModel, h->pe, Lp, 0}, s));
+        MRMT3_TRY(run_encoder_stack(h, h->mem, n, Lp, n_mem,
+                                    out_bf16 ? out_bf16 + (size_t)c0 * n_mem * kDModel : nullptr,
+                                    out_f32 ? out_f32 + (size_t)c0 * n_mem * kDModel : nullptr, s));
+    }
+    return OkStatus();
+}
+
+// ---------------------------------------------------------------------------------------------
+// decode lanes
+struct LaneArrays {
+    int *step, *n_active, *ticket, *tok, *active, *finish_step;
+    int *out_row, *prev_row, *init_active, *seg_index;
+};
+
+static LaneArrays lane_arrays(const mrmt3_handle* h) {
+    LaneArrays a;
+    int* s = h->d_state.as<int>();
+    a.step = s;
+    a.n_active = s + 1;
+    a.ticket = s + 2;
+    a.tok = s + 16;
+    a.active = a.tok + h->lane_cap;
+    a.finish_step = a.active + h->lane_cap;
+    int* t = h->lane_tab.as<int>();
+    a.out_row = t;
+    a.prev_row = t + h->lane_cap;
+    a.init_active = t + 2 * h->lane_cap;
+    a.seg_index = t + 3 * h->lane_cap;
+    return a;
+}
+
+static Status ensure_decode_capacity(mrmt3_handle* h, int n_lanes, int tk, int max_positions) {
+    const int pages = ceil_div(max_positions, kKVPage);
+    if (max_positions > attn_decode_max_keys())
+        return Error(2, "max_length (+ memory prefix) exceeds the decode attention key capacity");
+    if (n_lanes <= h->lane_cap && tk <= h->tk_cap && pages <= h->page_cap) return OkStatus();
+    MRMT3_CUDA_TRY(cudaDeviceSynchronize());
+    destroy_graphs(h);
+    const int cap = std::max(n_lanes, h->lane_cap);
+    const int tkc = std::max(tk, h->tk_cap);
+    const int pgc = std::max(pages, h->page_cap);
+    const size_t c = (size_t)cap;
+    MRMT3_TRY(h->d_h32.reserve(c * kDModel * 4));
+    MRMT3_TRY(h->d_n_bf16.reserve(c * kDModel * 2));
+    MRMT3_TRY(h->d_qkv.reserve(c * 3 * kInner * 2));
+    MRMT3_TRY(h->d_ctx.reserve(c * kInner * 2));
+    MRMT3_TRY(h->d_qc.reserve(c * kInner * 2));
+    MRMT3_TRY(h->d_ff.reserve(c * kDFF * 2));
+    MRMT3_TRY(h->d_logits.reserve(c * kVocab * 4));
+    MRMT3_TRY(h->d_state.reserve((16 + 3 * c) * sizeof(int)));
+    MRMT3_TRY(h->lane_tab.reserve(4 * c * sizeof(int)));
+    MRMT3_TRY(h->kv_pool.reserve(c * pgc * page_elems(h) * sizeof(bf16)));
+    MRMT3_TRY(h->cross_cache.reserve(c * h->cfg.n_dec_layers * 2 * kHeads * (size_t)tkc * kDKV * sizeof(bf16)));
+    MRMT3_TRY(h->block_table.reserve(c * pgc * sizeof(int)));
+    MRMT3_CUDA_TRY(cudaMemset(h->d_h32.p, 0, h->d_h32.cap));
+    MRMT3_CUDA_TRY(cudaMemset(h->d_state.p, 0, h->d_state.cap));
+    MRMT3_CUDA_TRY(cudaMemset(h->lane_tab.p, 0, h->lane_tab.cap));
+    // static page assignment: lane l owns pages [l*pgc, (l+1)*pgc)
+    std::vector<int> bt(c * pgc);
+    for (size_t i = 0; i < bt.size(); ++i) bt[i] = (int)i;
+    MRMT3_CUDA_TRY(cudaMemcpy(h->block_table.p, bt.data(), bt.size() * sizeof(int), cudaMemcpyHostToDevice));
+    h->lane_cap = cap;
+    h->tk_cap = tkc;
+    h->page_cap = pgc;
+    return OkStatus();
+}
+
+struct StepPlan {
+    int n_lanes, tk;
+    DecodeState st;
+    const float* prefix;   // V1 memory prefix rows (lanes, prefix_len, d) fp32 or nullptr
+    float* ext_logits;     // optional (rows, max_tokens, V) sink
+};
+
+// all kernels of one decode step.  kind 0: token step (lm_head + arg-max); kind 1: memory-prefix
+// step of the V1 variant (no token is produced).
+static Status enqueue_step(mrmt3_handle* h, const StepPlan& pl, int kind, cudaStream_t s) {
+    const int n = pl.n_lanes;
+    const float eps = h->cfg.ln_eps;
+    float* H = h->d_h32.as<float>();
+    bf16* nb = h->d_n_bf16.as<bf16>();
+    bf16* qkv = h->d_qkv.as<bf16>();
+    bf16* ctx = h->d_ctx.as<bf16>();
+    bf16* qc = h->d_qc.as<bf16>();
+    bf16* ff = h->d_ff.as<bf16>();
+    const ARowMap id{nullptr, 1};
+    RUN(h, launch_decode_embed(pl.st, h->emb, h->pe, pl.prefix, pl.st.prefix_len * kDModel, H, n, s));
+    for (int li = 0; li < h->cfg.n_dec_layers; ++li) {
+        const LayerW& L = h->dec.layers[li];
+        RUN(h, launch_rmsnorm(H, L.ln_self, eps, nb, nullptr, n, pl.st.active, 1, s));
+        RUN(h, launch_gemm_mma(nb, kDModel, id, L.wqkv, kDModel, n, 3 * kInner, kDModel,
+                               EpiStoreBf16{qkv, 3 * kInner}, s));
+        AttnDecodeParams ap{};
+        ap.q = qkv;
+        ap.q_stride = 3 * kInner;
+        ap.out = ctx;
+        ap.out_stride = kInner;
+        ap.kv_pool = h->kv_pool.as<bf16>();
+        ap.layer = li;
+        ap.n_layers = h->cfg.n_dec_layers;
+        ap.step_ptr = pl.st.step;
+        ap.pos_offset = 0;
+        ap.block_table = h->block_table.as<int>();
+        ap.max_pages = h->page_cap;
+        ap.page_stride = page_elems(h);
+        ap.active = pl.st.active;
+        RUN(h, launch_attn_decode(ap, n, true, s));
+        RUN(h, launch_gemm_mma(ctx, kInner, id, L.wo, kInner, n, kDModel, kInner, EpiResidual{H, kDModel}, s));
+
+        RUN(h, launch_rmsnorm(H, L.ln_cross, eps, nb, nullptr, n, pl.st.active, 1, s));
+        RUN(h, launch_gemm_mma(nb, kDModel, id, L.cq, kDModel, n, kInner, kDModel, EpiStoreBf16{qc, kInner}, s));
+        AttnDecodeParams cp{};
+        cp.q = qc;
+        cp.q_stride = kInner;
+        cp.out = ctx;
+        cp.out_stride = kInner;
+        cp.kv_pool = h->cross_cache.as<bf16>();
+        cp.layer = li;
+        cp.n_layers = h->cfg.n_dec_layers;
+        cp.tk_cap = h->tk_cap;
+        cp.n_keys = pl.tk;
+        cp.active = pl.st.active;
+        RUN(h, launch_attn_decode(cp, n, false, s));
+        RUN(h, launch_gemm_mma(ctx, kInner, id, L.co, kInner, n, kDModel, kInner, EpiResidual{H, kDModel}, s));
+
+        RUN(h, launch_rmsnorm(H, L.ln_ff, eps, nb, nullptr, n, pl.st.active, 1, s));
+        RUN(h, launch_gemm_mma(nb, kDModel, id, L.wi, kDModel, n, 2 * kDFF, kDModel, EpiGatedGelu{ff, kDFF}, s));
+        RUN(h, launch_gemm_mma(ff, kDFF, id, L.wff, kDFF, n, kDModel, kDFF, EpiResidual{H, kDModel}, s));
+    }
+    if (kind == 1) {
+        RUN(h, launch_advance_only(pl.st, s));
+        return OkStatus();
+    }
+    RUN(h, launch_rmsnorm(H, h->dec.final_ln, eps, nb, nullptr, n, pl.st.active, 1, s));
+    if (pl.ext_logits) {
+        const size_t lane_stride = (size_t)pl.st.max_tokens * kVocab;
+        RUN(h, launch_gemm_mma(nb, kDModel, id, h->lm_head, kDModel, n, kVocab, kDModel,
+                               EpiStoreF32Step{pl.ext_logits, kVocab, lane_stride, pl.st.step,
+                                               pl.st.prefix_len, pl.st.out_row}, s));
+        RUN(h, launch_argmax_advance(pl.st, pl.ext_logits, lane_stride, kVocab, n, kVocab, s));
+    } else {
+        float* lg = h->d_logits.as<float>();
+        RUN(h, launch_gemm_mma(nb, kDModel, id, h->lm_head, kDModel, n, kVocab, kDModel,
+                               EpiStoreF32{lg, kVocab}, s));
+        RUN(h, launch_argmax_advance(pl.st, lg, kVocab, 0, n, kVocab, s));
+    }
+    return OkStatus();
+}
+
+static Status get_graph(mrmt3_handle* h, const StepPlan& pl, int kind, StepGraph** out) {
+    StepGraphKey key{pl.n_lanes, pl.tk, pl.st.max_tokens, pl.st.prefix_len, kind};
+    auto it = h->graphs.find(key);
+    if (it != h->graphs.end()) {
+        *out = &it->second;
+        return OkStatus();
+    }
+    cudaStream_t cs;
+    MRMT3_CUDA_TRY(cudaStreamCreateWithFlags(&cs, cudaStreamNonBlocking));
+    StepGraph g;
+    int64_t before = h->launches;
+    cudaGraph_t graph = nullptr;
+    cudaError_t e = cudaStreamBeginCapture(cs, cudaStreamCaptureModeThreadLocal);
+    Status st = OkStatus();
+    if (e == cudaSuccess) {
+        st = enqueue_step(h, pl, kind, cs);
+        e = cudaStreamEndCapture(cs, &graph);
+    }
+    g.n_kernels = (int)(h->launches - before);
+    h->launches = before;  // capture launches nothing; replays are counted when launched
+    if (st.ok() && e == cudaSuccess) e = cudaGraphInstantiate(&g.exec, graph, 0);
+    if (graph) cudaGraphDestroy(graph);
+    cudaStreamDestroy(cs);
+    if (!st.ok()) return st;
+    if (e != cudaSuccess) return Error((int)e, std::string("decode-step graph capture failed: ") + cudaGetErrorString(e));
+    auto ins = h->graphs.emplace(key, g);
+    *out = &ins.first->second;
+    return OkStatus();
+}
+
+// Greedy loop over lanes whose state was set by launch_decode_init.  Runs n_prefix prefix steps,
+// then up to max_tokens token steps, stopping early once every lane has emitted EOS (polled
+// every kPollEvery steps without draining the queue).
+static Status run_decode(mrmt3_handle* h, StepPlan pl, int n_prefix, bool debug_mode, cudaStream_t s) {
+    const bool graphs = h->use_graphs && !debug_mode;
+    StepGraph *g_tok = nullptr, *g_pre = nullptr;
+    if (graphs) {
+        MRMT3_TRY(get_graph(h, pl, 0, &g_tok));
+        if (n_prefix) MRMT3_TRY(get_graph(h, pl, 1, &g_pre));
+    }
+    for (int i = 0; i < n_prefix; ++i) {
+        if (graphs) {
+            MRMT3_CUDA_TRY(cudaGraphLaunch(g_pre->exec, s));
+            h->launches += g_pre->n_kernels;
+        } else {
+            MRMT3_TRY(enqueue_step(h, pl, 1, s));
+        }
+    }
+    int polls = 0;
+    bool pending[2] = {false, false};
+    bool all_done = false;
+    const bool may_exit_early = pl.st.forced == nullptr;
+    for (int t = 0; t < pl.st.max_tokens && !all_done; ++t) {
+        if (graphs) {
+            MRMT3_CUDA_TRY(cudaGraphLaunch(g_tok->exec, s));
+            h->launches += g_tok->n_kernels;
+        } else {
+            MRMT3_TRY(enqueue_step(h, pl, 0, s));
+        }
+        if (may_exit_early && (t + 1) % kPollEvery == 0 && t + 1 < pl.st.max_tokens) {
+            const int slot = polls & 1;
+            MRMT3_CUDA_TRY(cudaMemcpyAsync(&h->h_pinned[slot], pl.st.n_active, sizeof(int),
+                                           cudaMemcpyDeviceToHost, s));
+            MRMT3_CUDA_TRY(cudaEventRecord(h->poll_ev[slot], s));
+            pending[slot] = true;
+            const int prev = slot ^ 1;
+            if (pending[prev]) {  // look at the poll issued kPollEvery steps ago
+                MRMT3_CUDA_TRY(cudaEventSynchronize(h->poll_ev[prev]));
+                pending[prev] = false;
+                if (h->h_pinned[prev] == 0) all_done = true;
+            }
+            ++polls;
+        }
+    }
+    MRMT3_CUDA_TRY(cudaStreamSynchronize(s));
+    return OkStatus();
+}
+
+static DecodeState make_state(mrmt3_handle* h, long long* out, int out_stride, int max_tokens,
+                              int prefix_len, const long long* forced) {
+    LaneArrays a = lane_arrays(h);
+    DecodeState st{};
+    st.step = a.step;
+    st.tok = a.tok;
+    st.active = a.active;
+    st.finish_step = a.finish_step;
+    st.n_active = a.n_active;
+    st.ticket = a.ticket;
+    st.out = out;
+    st.out_row = a.out_row;
+    st.out_stride = out_stride;
+    st.prefix_len = prefix_len;
+    st.forced = forced;
+    st.forced_stride = out_stride;
+    st.eos_id = h->cfg.eos_id;
+    st.pad_id = h->cfg.pad_id;
+    st.max_tokens = max_tokens;
+    return st;
+}
+
+// cross K/V of every decoder layer for `n_lanes` lanes: encoder rows (gathered through
+// seg_index when given) and, for the V2 variant, the memory rows appended at key 256.
+static Status project_cross_kv(mrmt3_handle* h, const bf16* enc, const int* seg_index, int n_lanes,
+                               const bf16* mem, int n_mem, cudaStream_t s) {
+    const int N = h->cfg.n_dec_layers * 2 * kInner;
+    RUN(h, launch_gemm_mma(enc, kDModel, ARowMap{seg_index, kSegFrames}, h->cross_kv_w, kDModel,
+                           n_lanes * kSegFrames, N, kDModel,
+                           EpiCrossKV{h->cross_cache.as<bf16>(), kSegFrames, 0, h->cfg.n_dec_layers,
+                                      h->tk_cap, nullptr}, s));
+    if (mem && n_mem > 0)
+        RUN(h, launch_gemm_mma(mem, kDModel, ARowMap{nullptr, 1}, h->cross_kv_w, kDModel, n_lanes * n_mem, N,
+                               kDModel,
+                               EpiCrossKV{h->cross_cache.as<bf16>(), n_mem, kSegFrames,
+                                          h->cfg.n_dec_layers, h->tk_cap, nullptr}, s));
+    return OkStatus();
+}
+
+// ---------------------------------------------------------------------------------------------
+// public drivers
+Status api_encode(mrmt3_handle* h, const float* mel, int B, float* enc_out, cudaStream_t s) {
+    if (!h->committed) return Error(5, "weights not committed");
+    MRMT3_CUDA_TRY(cudaSetDevice(h->device));
+    return encode_segments(h, mel, nullptr, B, nullptr, enc_out, s);
+}
+
+// shared by mrmt3_generate and the e2e path (mel as fp32 or bf16)
+Status generate_base(mrmt3_handle* h, const float* mel_f32, const bf16* mel_bf16, int B, int max_length,
+                     long long* out_ids, int* steps_host, const long long* forced, float* logits_out,
+                     cudaStream_t s) {
+    if (!h->committed) return Error(5, "weights not committed");
+    if (h->cfg.mem_variant != MRMT3_MEM_NONE)
+        return Error(2, "mrmt3_generate is the plain MT3 loop; use mrmt3_generate_segmem for memory variants");
+    if (B <= 0 || max_length <= 0) return Error(2, "B and max_length must be positive");
+    MRMT3_CUDA_TRY(cudaSetDevice(h->device));
+    const int stride = max_length + 1;
+    MRMT3_TRY(reserve_graph_visible(h, h->tok_out, (size_t)B * stride * sizeof(long long)));
+    long long* tok = h->tok_out.as<long long>();
+    MRMT3_CUDA_TRY(cudaMemsetAsync(tok, 0, (size_t)B * stride * sizeof(long long), s));
+    int steps = 0;
+    for (int c0 = 0; c0 < B; c0 += kMaxLanes) {
+        const int n = std::min(kMaxLanes, B - c0);
+        MRMT3_TRY(ensure_decode_capacity(h, n, kSegFrames, max_length));
+        MRMT3_TRY(h->enc_bf16.reserve((size_t)n * kSegFrames * kDModel * sizeof(bf16)));
+        MRMT3_TRY(encode_segments(h, mel_f32 ? mel_f32 + (size_t)c0 * kSegFrames * kMels : nullptr,
+                                  mel_bf16 ? mel_bf16 + (size_t)c0 * kSegFrames * kMels : nullptr, n,
+                                  h->enc_bf16.as<bf16>(), nullptr, s));
+        MRMT3_TRY(project_cross_kv(h, h->enc_bf16.as<bf16>(), nullptr, n, nullptr, 0, s));
+        LaneArrays a = lane_arrays(h);
+        std::vector<int> rows(n);
+        for (int i = 0; i < n; ++i) rows[i] = c0 + i;
+        MRMT3_CUDA_TRY(cudaMemcpyAsync(a.out_row, rows.data(), n * sizeof(int), cudaMemcpyHostToDevice, s));
+        MRMT3_CUDA_TRY(cudaStreamSynchronize(s));  // `rows` is pageable host memory
+        StepPlan pl{};
+        pl.n_lanes = n;
+        pl.tk = kSegFrames;
+        pl.st = make_state(h, tok, stride, max_length, 0, forced);
+        pl.prefix = nullptr;
+        pl.ext_logits = logits_out;
+        RUN(h, launch_decode_init(pl.st, n, nullptr, n, h->cfg.start_id, s));
+        MRMT3_TRY(run_decode(h, pl, 0, forced != nullptr || logits_out != nullptr, s));
+        MRMT3_CUDA_TRY(cudaMemcpyAsync(h->h_pinned + 8, a.finish_step, n * sizeof(int), cudaMemcpyDeviceToHost, s));
+        MRMT3_CUDA_TRY(cudaStreamSynchronize(s));
+        for (int i = 0; i < n; ++i) steps = std::max(steps, h->h_pinned[8 + i]);
+    }
+    MRMT3_CUDA_TRY(cudaMemcpyAsync(out_ids, tok, (size_t)B * stride * sizeof(long long),
+                                   cudaMemcpyDeviceToDevice, s));
+    MRMT3_CUDA_TRY(cudaStreamSynchronize(s));
+    if (steps_host) *steps_host = steps;
+    return OkStatus();
+}
+
+// MR-MT3 greedy transcription batched across tracks (see include/mrmt3_b200.h).
+Status generate_segmem(mrmt3_handle* h, const float* mel_f32, const bf16* mel_bf16, const int* seg_counts,
+                       int n_tracks, int max_length, long long* out_ids, float* logits_out,
+                       cudaStream_t s) {
+    if (!h->committed) return Error(5, "weights not committed");
+    if (h->cfg.mem_variant == MRMT3_MEM_NONE) return Error(2, "model has no memory variant");
+    if (n_tracks <= 0 || max_length <= 0) return Error(2, "n_tracks and max_length must be positive");
+    MRMT3_CUDA_TRY(cudaSetDevice(h->device));
+    const bool v1 = h->cfg.mem_variant == MRMT3_MEM_V1_PREPEND;
+    const int n_mem = std::min(h->cfg.mem_len, max_length);
+    if (v1 && max_length < h->cfg.mem_len)
+        return Error(2, "V1 (generate_2) needs max_length >= segmem_length (reference models/t5_segmem.py:213)");
+    std::vector<long long> seg_base(n_tracks);
+    long long total = 0;
+    int max_segs = 0;
+    for (int t = 0; t < n_tracks; ++t) {
+        if (seg_counts[t] < 0) return Error(2, "negative segment count");
+        seg_base[t] = total;
+        total += seg_counts[t];
+        max_segs = std::max(max_segs, seg_counts[t]);
+    }
+    if (total == 0) return OkStatus();
+    const int S = (int)total;
+    const int stride = max_length + 1;
+
+    // 1. encoder over every segment of every track (batched; no sequential dependency)
+    MRMT3_TRY(h->enc_bf16.reserve((size_t)S * kSegFrames * kDModel * sizeof(bf16)));
+    MRMT3_TRY(encode_segments(h, mel_f32, mel_bf16, S, h->enc_bf16.as<bf16>(), nullptr, s));
+
+    // 2. token rows (S, max_length+1) + the dummy memory ids of the first segment
+    MRMT3_TRY(reserve_graph_visible(h, h->tok_out, (size_t)S * stride * sizeof(long long)));
+    long long* tok = h->tok_out.as<long long>();
+    MRMT3_CUDA_TRY(cudaMemsetAsync(tok, 0, (size_t)S * stride * sizeof(long long), s));
+    MRMT3_TRY(h->dummy_ids.reserve((size_t)max_length * sizeof(long long)));
+    {
+        std::vector<long long> dummy(max_length, 0);
+        if (v1) {
+            dummy[0] = 1;                                  // reference models/t5_segmem.py:194
+        } else {
+            dummy[0] = 1134;                               // tie token, t5_segmem_v2_with_prev.py:257
+            if (max_length > 1) dummy[1] = 1;
+        }
+        MRMT3_CUDA_TRY(cudaMemcpyAsync(h->dummy_ids.p, dummy.data(), dummy.size() * sizeof(long long),
+                                       cudaMemcpyHostToDevice, s));
+        MRMT3_CUDA_TRY(cudaStreamSynchronize(s));
+    }
+
+    // 3. waves of at most kMaxLanes tracks; inside a wave every track advances one segment per round
+    for (int w0 = 0; w0 < n_tracks; w0 += kMaxLanes) {
+        const int n = std::min(kMaxLanes, n_tracks - w0);
+        int wave_segs = 0;
+        for (int i = 0; i < n; ++i) wave_segs = std::max(wave_segs, seg_counts[w0 + i]);
+        const int tk = v1 ? kSegFrames : kSegFrames + n_mem;
+        const int prefix = v1 ? n_mem : 0;
+        MRMT3_TRY(ensure_decode_capacity(h, n, tk, max_length + prefix));
+        MRMT3_TRY(h->mem_bf16.reserve((size_t)n * n_mem * kDModel * sizeof(bf16)));
+        MRMT3_TRY(reserve_graph_visible(h, h->mem_f32, (size_t)n * n_mem * kDModel * sizeof(float)));
+        LaneArrays a = lane_arrays(h);
+        std::vector<int> tab(4 * (size_t)n);
+        for (int r = 0; r < wave_segs; ++r) {
+            int n_active = 0;
+            for (int i = 0; i < n; ++i) {
+                const int cnt = seg_counts[w0 + i];
+                const bool on = r < cnt;
+                const int seg = (int)seg_base[w0 + i] + (on ? r : std::max(cnt - 1, 0));
+                tab[i] = seg;                                        // out_row
+                tab[n + i] = (r > 0 && on) ? seg - 1 : seg;          // prev_row (r == 0: unused)
+                tab[2 * n + i] = on ? 1 : 0;                         // init_active
+                tab[3 * n + i] = seg;                                // seg_index
+                n_active += on;
+            }
+            MRMT3_CUDA_TRY(cudaMemcpyAsync(a.out_row, tab.data(), n * sizeof(int), cudaMemcpyHostToDevice, s));
+            MRMT3_CUDA_TRY(cudaMemcpyAsync(a.prev_row, tab.data() + n, n * sizeof(int), cudaMemcpyHostToDevice, s));
+            MRMT3_CUDA_TRY(cudaMemcpyAsync(a.init_active, tab.data() + 2 * n, n * sizeof(int), cudaMemcpyHostToDevice, s));
+            MRMT3_CUDA_TRY(cudaMemcpyAsync(a.seg_index, tab.data() + 3 * n, n * sizeof(int), cudaMemcpyHostToDevice, s));
+            MRMT3_CUDA_TRY(cudaStreamSynchronize(s));
+            // memory block from the previous output row (or the dummy ids)
+            if (r == 0)
+                MRMT3_TRY(memory_block(h, h->dummy_ids.as<long long>(), 0, nullptr, n, max_length, n_mem,
+                                       h->mem_bf16.as<bf16>(), h->mem_f32.as<float>(), s));
+            else
+                MRMT3_TRY(memory_block(h, tok, stride, a.prev_row, n, max_length, n_mem,
+                                       h->mem_bf16.as<bf16>(), h->mem_f32.as<float>(), s));
+            MRMT3_TRY(project_cross_kv(h, h->enc_bf16.as<bf16>(), a.seg_index, n,
+                                       v1 ? nullptr : h->mem_bf16.as<bf16>(), v1 ? 0 : n_mem, s));
+            StepPlan pl{};
+            pl.n_lanes = n;
+            pl.tk = tk;
+            pl.st = make_state(h, tok, stride, max_length, prefix, nullptr);
+            pl.prefix = v1 ? h->mem_f32.as<float>() : nullptr;
+            pl.ext_logits = logits_out;
+            RUN(h, launch_decode_init(pl.st, n, a.init_active, n_active, h->cfg.start_id, s));
+            MRMT3_TRY(run_decode(h, pl, prefix, logits_out != nullptr, s));
+        }
+    }
+    // 4. (S, max_length+1) -> (S, max_length): F.pad incl. the negative pad that drops the last
+    //    token of a row that never emitted EOS (reference t5_segmem_v2_with_prev.py:287-291)
+    MRMT3_CUDA_TRY(cudaMemcpy2DAsync(out_ids, (size_t)max_length * sizeof(long long), tok,
+                                     (size_t)stride * sizeof(long long), (size_t)max_length * sizeof(long long),
+                                     S, cudaMemcpyDeviceToDevice, s));
+    MRMT3_CUDA_TRY(cudaStreamSynchronize(s));
+    return OkStatus();
+}
+
+Status api_memory_block(mrmt3_handle* h, const long long* prev_ids, int B, int Lp, float* mem_out,
+                        cudaStream_t s) {
+    if (!h->committed) return Error(5, "weights not committed");
+    if (h->cfg.mem_variant == MRMT3_MEM_NONE) return Error(2, "model has no memory variant");
+    MRMT3_CUDA_TRY(cudaSetDevice(h->device));
+    const int n_mem = std::min(h->cfg.mem_len, Lp);
+    return memory_block(h, prev_ids, Lp, nullptr, B, Lp, n_mem, nullptr, mem_out, s);
+}
+
+// teacher-forced forward (reference models/t5.py:99-249, t5_segmem_v2_with_prev.py:60-224)
+Status api_forward_logits(mrmt3_handle* h, const float* mel, int B, const long long* dec_ids, int L,
+                          const long long* targets_prev, int Lp, float* logits_out, cudaStream_t s) {
+    if (!h->committed) return Error(5, "weights not committed");
+    if (h->cfg.mem_variant == MRMT3_MEM_V1_PREPEND)
+        return Error(2, "teacher-forced forward is implemented for the MT3 and V2WithPrev models only");
+    if (B <= 0 || L <= 0 || L > kNPos) return Error(2, "bad B or L");
+    MRMT3_CUDA_TRY(cudaSetDevice(h->device));
+    const bool mem = h->cfg.mem_variant == MRMT3_MEM_V2_APPEND;
+    if (mem && (!targets_prev || Lp <= 0)) return Error(2, "targets_prev required for the memory variant");
+    const int n_mem = mem ? std::min(h->cfg.mem_len, Lp) : 0;
+    const int tk = kSegFrames + n_mem;
+    const float eps = h->cfg.ln_eps;
+    for (int c0 = 0; c0 < B; c0 += kMaxLanes) {
+        const int n = std::min(kMaxLanes, B - c0);
+        MRMT3_TRY(ensure_decode_capacity(h, n, tk, 1));
+        MRMT3_TRY(h->enc_bf16.reserve((size_t)n * kSegFrames * kDModel * sizeof(bf16)));
+        MRMT3_TRY(encode_segments(h, mel + (size_t)c0 * kSegFrames * kMels, nullptr, n, h->enc_bf16.as<bf16>(), nullptr, s));
+        if (mem) {
+            MRMT3_TRY(h->mem_bf16.reserve((size_t)n * n_mem * kDModel * sizeof(bf16)));
+            MRMT3_TRY(memory_block(h, targets_prev + (size_t)c0 * Lp, Lp, nullptr, n, Lp, n_mem,
+                                   h->mem_bf16.as<bf16>(), nullptr, s));
+        }
+        MRMT3_TRY(project_cross_kv(h, h->enc_bf16.as<bf16>(), nullptr, n, mem ? h->mem_bf16.as<bf16>() : nullptr, n_mem, s));
+        // decoder over n*L rows, in row chunks of whole sequences
+        const int seq_chunk = std::max(1, (kEncChunk * kSegFrames) / L);
+        for (int b0 = 0; b0 < n; b0 += seq_chunk) {
+            const int nb = std::min(seq_chunk, n - b0);
+            const int M = nb * L;
+            MRMT3_TRY(h->rows.reserve(M));
+            RowWorkspace& w = h->rows;
+            float* H = w.h32.as<float>();
+            const ARowMap id{nullptr, 1};
+            RUN(h, launch_embed_tokens(dec_ids + (size_t)(c0 + b0) * L, h->emb, h->pe, H, nb, L, 0, s));
+            for (int li = 0; li < h->cfg.n_dec_layers; ++li) {
+                const LayerW& Lw = h->dec.layers[li];
+                RUN(h, launch_rmsnorm(H, Lw.ln_self, eps, w.n_bf16.as<bf16>(), nullptr, M, nullptr, 1, s));
+                RUN(h, launch_gemm_mma(w.n_bf16.as<bf16>(), kDModel, id, Lw.wqkv, kDModel, M, 3 * kInner, kDModel,
+                                       EpiStoreBf16{w.qkv.as<bf16>(), 3 * kInner}, s));
+                AttnFullParams ap{};
+                ap.Q = w.qkv.as<bf16>();
+                ap.K = ap.Q + kInner;
+                ap.V = ap.Q + 2 * kInner;
+                ap.q_batch_stride = ap.k_batch_stride = ap.v_batch_stride = (long)L * 3 * kInner;
+                ap.q_head_stride = ap.k_head_stride = ap.v_head_stride = kDKV;
+                ap.q_row_stride = ap.k_row_stride = ap.v_row_stride = 3 * kInner;
+                ap.O = w.ctx.as<bf16>();
+                ap.o_batch_stride = (long)L * kInner;
+                ap.o_head_stride = kDKV;
+                ap.o_row_stride = kInner;
+                ap.Tq = L;
+                ap.Tk = L;
+                ap.causal = 1;
+                ap.causal_offset = 0;
+                RUN(h, launch_attn_full(ap, nb, s));
+                RUN(h, launch_gemm_mma(w.ctx.as<bf16>(), kInner, id, Lw.wo, kInner, M, kDModel, kInner, EpiResidual{H, kDModel}, s));
+
+                RUN(h, launch_rmsnorm(H, Lw.ln_cross, eps, w.n_bf16.as<bf16>(), nullptr, M, nullptr, 1, s));
+                RUN(h, launch_gemm_mma(w.n_bf16.as<bf16>(), kDModel, id, Lw.cq, kDModel, M, kInner, kDModel,
+                                       EpiStoreBf16{w.qc.as<bf16>(), kInner}, s));
+                AttnFullParams cp{};
+                const size_t lane_sz = (size_t)h->cfg.n_dec_layers * 2 * kHeads * h->tk_cap * kDKV;
+                const bf16* kbase = h->cross_cache.as<bf16>() + (size_t)b0 * lane_sz +
+                                    (size_t)li * 2 * kHeads * h->tk_cap * kDKV;
+                cp.Q = w.qc.as<bf16>();
+                cp.q_batch_stride = (long)L * kInner;
+                cp.q_head_stride = kDKV;
+                cp.q_row_stride = kInner;
+                cp.K = kbase;
+                cp.V = kbase + (size_t)kHeads * h->tk_cap * kDKV;
+                cp.k_batch_stride = cp.v_batch_stride = (long)lane_sz;
+                cp.k_head_stride = cp.v_head_stride = (long)h->tk_cap * kDKV;
+                cp.k_row_stride = cp.v_row_stride = kDKV;
+                cp.O = w.ctx.as<bf16>();
+                cp.o_batch_stride = (long)L * kInner;
+                cp.o_head_stride = kDKV;
+                cp.o_row_stride = kInner;
+                cp.Tq = L;
+                cp.Tk = tk;
+                cp.causal = 0;
+                RUN(h, launch_attn_full(cp, nb, s));
+                RUN(h, launch_gemm_mma(w.ctx.as<bf16>(), kInner, id, Lw.co, kInner, M, kDModel, kInner, EpiResidual{H, kDModel}, s));
+
+                RUN(h, launch_rmsnorm(H, Lw.ln_ff, eps, w.n_bf16.as<bf16>(), nullptr, M, nullptr, 1, s));
+                RUN(h, launch_gemm_mma(w.n_bf16.as<bf16>(), kDModel, id, Lw.wi, kDModel, M, 2 * kDFF, kDModel,
+                                       EpiGatedGelu{w.ff.as<bf16>(), kDFF}, s));
+                RUN(h, launch_gemm_mma(w.ff.as<bf16>(), kDFF, id, Lw.wff, kDFF, M, kDModel, kDFF, EpiResidual{H, kDModel}, s));
+            }
+            RUN(h, launch_rmsnorm(H, h->dec.final_ln, eps, w.n_bf16.as<bf16>(), nullptr, M, nullptr, 1, s));
+            RUN(h, launch_gemm_mma(w.n_bf16.as<bf16>(), kDModel, id, h->lm_head, kDModel, M, kVocab, kDModel,
+                                   EpiStoreF32{logits_out + (size_t)(c0 + b0) * L * kVocab, kVocab}, s));
+        }
+    }
+    return OkStatus();
+}
+
+Status api_logmel(mrmt3_handle* h, const float* audio, const long long* seg_start, const int* seg_len,
+                  const int* valid_frames, int n_seg, int flags, float* out_f32, bf16* out_bf16,
+                  cudaStream_t s) {
+    MRMT3_CUDA_TRY(cudaSetDevice(h->device));
+    if (!out_f32 && !out_bf16) return Error(2, "logmel needs at least one output buffer");
+    RUN(h, h->frontend.run(audio, seg_start, seg_len, valid_frames, n_seg, (flags & MRMT3_MEL_NORM) ? 1 : 0,
+                           out_f32, out_bf16, s));
+    return OkStatus();
+}
+
+Status api_transcribe_host(mrmt3_handle* h, const float* audio_host, long long n_samples,
+                           const long long* seg_start_host, const int* seg_len_host,
+                           const int* valid_frames_host, int n_seg, const int* seg_counts_host, int n_tracks,
+                           int flags, int max_length, long long* out_ids_host, int* steps_host,
+                           cudaStream_t s) {
+    if (!h->committed) return Error(5, "weights not committed");
+    if (n_seg <= 0) return Error(2, "n_seg must be positive");
+    MRMT3_CUDA_TRY(cudaSetDevice(h->device));
+    const bool mem = h->cfg.mem_variant != MRMT3_MEM_NONE;
+    if (mem && (!seg_counts_host || n_tracks <= 0)) return Error(2, "memory variants need seg_counts_host/n_tracks");
+    MRMT3_TRY(h->audio.reserve((size_t)n_samples * sizeof(float)));
+    const size_t tab_bytes = (size_t)n_seg * (sizeof(long long) + 2 * sizeof(int));
+    MRMT3_TRY(h->seg_tab.reserve(tab_bytes));
+    long long* d_start = h->seg_tab.as<long long>();
+    int* d_len = reinterpret_cast<int*>(d_start + n_seg);
+    int* d_valid = d_len + n_seg;
+    MRMT3_CUDA_TRY(cudaMemcpyAsync(h->audio.p, audio_host, (size_t)n_samples * sizeof(float), cudaMemcpyHostToDevice, s));
+    MRMT3_CUDA_TRY(cudaMemcpyAsync(d_start, seg_start_host, n_seg * sizeof(long long), cudaMemcpyHostToDevice, s));
+    MRMT3_CUDA_TRY(cudaMemcpyAsync(d_len, seg_len_host, n_seg * sizeof(int), cudaMemcpyHostToDevice, s));
+    if (valid_frames_host)
+        MRMT3_CUDA_TRY(cudaMemcpyAsync(d_valid, valid_frames_host, n_seg * sizeof(int), cudaMemcpyHostToDevice, s));
+    MRMT3_TRY(h->mel_bf16.reserve((size_t)n_seg * kSegFrames * kMels * sizeof(bf16)));
+    MRMT3_TRY(api_logmel(h, h->audio.as<float>(), d_start, d_len, valid_frames_host ? d_valid : nullptr, n_seg,
+                         flags, nullptr, h->mel_bf16.as<bf16>(), s));
+    const int width = mem ? max_length : max_length + 1;
+    DeviceBuffer& ids = h->ids_dev;
+    MRMT3_TRY(ids.reserve((size_t)n_seg * width * sizeof(long long)));
+    if (mem)
+        MRMT3_TRY(generate_segmem(h, nullptr, h->mel_bf16.as<bf16>(), seg_counts_host, n_tracks, max_length,
+                                  ids.as<long long>(), nullptr, s));
+    else
+        MRMT3_TRY(generate_base(h, nullptr, h->mel_bf16.as<bf16>(), n_seg, max_length, ids.as<long long>(),
+                                steps_host, nullptr, nullptr, s));
+    MRMT3_CUDA_TRY(cudaMemcpyAsync(out_ids_host, ids.p, (size_t)n_seg * width * sizeof(long long),
+                                   cudaMemcpyDeviceToHost, s));
+    MRMT3_CUDA_TRY(cudaStreamSynchronize(s));
+    return OkStatus();
+}
+
+}  // namespace mrmt3

@@ -1,0 +1,114 @@
+// The handle behind include/mrmt3_b200.h: packed weights, workspaces, KV-cache pages, CUDA
+// graphs of the decode step, and the host-side drivers of the path (model.cu).
+#pragma once
+#include <map>
+#include <set>
+#include <string>
+#include <vector>
+
+#include "../../include/mrmt3_b200.h"
+#include "attention.cuh"
+#include "common.cuh"
+#include "frontend.cuh"
+#include "layers.cuh"
+
+namespace mrmt3 {
+
+struct DeviceBuffer {
+    void* p = nullptr;
+    size_t cap = 0;
+    // grow-only; *moved set when the address changed
+    Status reserve(size_t bytes, bool* moved = nullptr);
+    void release();
+    template <class T>
+    T* as() const { return reinterpret_cast<T*>(p); }
+};
+
+struct LayerW {
+    bf16* wqkv = nullptr;     // (3*inner, d)  rows [q; k; v]
+    bf16* wo = nullptr;       // (d, inner)
+    float* ln_self = nullptr; // (d)
+    bf16* cq = nullptr;       // (inner, d)    decoder only
+    bf16* co = nullptr;       // (d, inner)    decoder only
+    float* ln_cross = nullptr;
+    bf16* wi = nullptr;       // (2*d_ff, d)   rows interleaved wi_0[j], wi_1[j]
+    bf16* wff = nullptr;      // (d, d_ff)
+    float* ln_ff = nullptr;
+};
+
+struct StackW {
+    std::vector<LayerW> layers;
+    float* final_ln = nullptr;
+};
+
+// row-parallel scratch (encoder / memory block / teacher-forced decoder)
+struct RowWorkspace {
+    DeviceBuffer x_bf16, h32, n_bf16, qkv, ctx, ff, qc, hc32, ctx_c;
+    int rows = 0;
+    Status reserve(int rows_needed);
+    void release();
+};
+
+struct StepGraphKey {
+    int n_lanes, tk, max_tokens, prefix_len, kind;  // kind 0 = token step, 1 = prefix step
+    bool operator<(const StepGraphKey& o) const {
+        if (n_lanes != o.n_lanes) return n_lanes < o.n_lanes;
+        if (tk != o.tk) return tk < o.tk;
+        if (max_tokens != o.max_tokens) return max_tokens < o.max_tokens;
+        if (prefix_len != o.prefix_len) return prefix_len < o.prefix_len;
+        return kind < o.kind;
+    }
+};
+
+struct StepGraph {
+    cudaGraphExec_t exec = nullptr;
+    int n_kernels = 0;
+};
+
+}  // namespace mrmt3
+
+struct mrmt3_handle {
+    mrmt3_config cfg;
+    int device = 0;
+    mutable std::string err;
+    int64_t launches = 0;
+    bool committed = false;
+    bool use_graphs = true;
+
+    mrmt3::Frontend frontend;
+
+    // ---- weights ----
+    mrmt3::DeviceBuffer arena;       // every packed tensor lives here
+    size_t arena_used = 0;
+    mrmt3::bf16* proj = nullptr;         // (d, d)
+    float* emb = nullptr;                // (V, d) fp32
+    mrmt3::bf16* lm_head = nullptr;      // (V, d)
+    mrmt3::bf16* segmem_proj = nullptr;  // (d, d)
+    mrmt3::bf16* cross_kv_w = nullptr;   // (n_dec * 2 * inner, d): layer-major [k; v]
+    mrmt3::StackW enc, dec, mem;
+    float* pe = nullptr;                 // (n_pos, d) fp32 sinusoid table
+    int n_pos = 0;
+    float inv_freq[256];
+    bool have_inv_freq = false;
+    std::set<std::string> seen;
+    mrmt3::DeviceBuffer stage;           // fp32 staging for set_weight
+
+    // ---- workspaces ----
+    mrmt3::RowWorkspace rows;
+    mrmt3::DeviceBuffer enc_bf16;        // (n_seg, 256, d) encoder states of the current call
+    mrmt3::DeviceBuffer mem_bf16, mem_f32;  // (lanes, n_mem, d)
+    mrmt3::DeviceBuffer mel_f32, mel_bf16, audio, seg_tab, ids_dev;  // e2e path
+    mrmt3::DeviceBuffer tok_out;         // (rows, max_length+1) int64 token rows of the call
+    mrmt3::DeviceBuffer dummy_ids;       // (max_length) int64 first-segment memory ids
+
+    // decode lanes
+    int lane_cap = 0, tk_cap = 0, page_cap = 0;  // capacities the buffers below were sized for
+    mrmt3::DeviceBuffer d_h32, d_n_bf16, d_qkv, d_ctx, d_qc, d_ff, d_logits;
+    mrmt3::DeviceBuffer d_state;         // ints: step, n_active, ticket, then per-lane arrays
+    mrmt3::DeviceBuffer kv_pool, block_table, cross_cache;
+    mrmt3::DeviceBuffer lane_tab;        // per-lane int tables (seg index, prev row, active)
+    int* h_pinned = nullptr;             // pinned host ints for polling / finish steps
+
+    std::map<mrmt3::StepGraphKey, mrmt3::StepGraph> graphs;
+    cudaEvent_t poll_ev[2] = {nullptr, nullptr};
+};

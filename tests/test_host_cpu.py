@@ -1,0 +1,154 @@
+"""CPU: the C-ABI library loads and exports every symbol the header declares (no compute calls
+without a GPU), host-side framing equals the oracle, state-dict contract, track sharding incl.
+a world_size-2 gloo gather."""
+import ctypes
+import importlib
+import os
+import re
+
+import numpy as np
+import pytest
+import torch
+
+import mt3_oracle as O
+from helpers import ROOT, load_synthetic
+
+syn = load_synthetic()
+
+
+def _lib():
+    build = importlib.import_module("mr-mt3_b200.build")
+    build.build()
+    return importlib.import_module("mr-mt3_b200._lib")
+
+
+def test_library_exports_every_header_symbol():
+    lib_mod = _lib()
+    header = open(os.path.join(ROOT, "include", "mrmt3_b200.h")).read()
+    declared = set(re.findall(r"\b(mrmt3_[a-z_0-9]+)\s*\(", header))
+    assert declared, "no declarations parsed"
+    assert declared == set(lib_mod.EXPORTED_SYMBOLS)
+    cdll = ctypes.CDLL(lib_mod.LIB_PATH)
+    for name in declared:
+        assert hasattr(cdll, name), name
+    lib_mod.load_library()
+
+
+def test_create_fails_loudly_without_gpu():
+    if torch.cuda.is_available():
+        pytest.skip("GPU present")
+    lib_mod = _lib()
+    with pytest.raises(lib_mod.MrMt3Error):
+        lib_mod.Engine()
+    lib = lib_mod.load_library()
+    cfg = lib_mod.Config(512, 6, 64, 1024, 1536, 8, 8, 0, 0, 64, 0, 1, 0, 1e-6)
+    h = ctypes.c_void_p()
+    rc = lib.mrmt3_create(ctypes.byref(cfg), 0, ctypes.byref(h))
+    assert rc != 0 and not h.value
+    assert len(lib.mrmt3_last_error(None)) > 0
+
+
+def test_model_on_cpu_refuses_to_run():
+    t5 = importlib.import_module("mr-mt3_b200.t5")
+    lib_mod = importlib.import_module("mr-mt3_b200._lib")
+    m = t5.T5ForConditionalGeneration(t5.T5Config())
+    with pytest.raises(lib_mod.MrMt3Error):
+        m.generate(torch.zeros(1, 256, 512))
+
+
+def test_state_dict_contract():
+    t5 = importlib.import_module("mr-mt3_b200.t5")
+    v2 = importlib.import_module("mr-mt3_b200.t5_segmem_v2_with_prev")
+    m = t5.T5ForConditionalGeneration(t5.T5Config())
+    ref = syn.synthetic_state_dict(1)
+    assert len(ref) == 193 and set(m.state_dict()) == set(ref)            # 193 keys
+    m.load_state_dict(ref, strict=True)
+    assert m.proj.weight.data_ptr() == m.encoder.embed_tokens.weight.data_ptr()
+    m2 = v2.T5SegMemV2WithPrev(t5.T5Config(), 1, 64)
+    ref2 = syn.synthetic_state_dict(1, segmem=True)
+    assert set(m2.state_dict()) == set(ref2) and len(ref2) == 206
+    n_params = sum(p.numel() for p in m2.parameters())
+    assert n_params == 48_519_680
+    assert sum(p.numel() for p in m.parameters()) == 45_896_704
+    labels = torch.tensor([[5, 6, -100, -100]])
+    np.testing.assert_array_equal(m._shift_right(labels).numpy(), O.shift_right(labels).numpy())
+
+
+def test_handler_framing_equals_oracle():
+    inf = importlib.import_module("mr-mt3_b200.inference")
+    sp = importlib.import_module("mr-mt3_b200.spectrograms")
+    h = inf.InferenceHandler.__new__(inf.InferenceHandler)
+    h.spectrogram_config = sp.SpectrogramConfig()
+    for n in (1000, 32767, 32768, 40000, 3 * 32768 + 5):
+        audio = syn.synthetic_audio(seed=n, n_samples=n)
+        frames, times = h._audio_to_frames(audio)
+        of, ot = O.audio_to_frames(audio)
+        np.testing.assert_array_equal(frames, of)
+        np.testing.assert_array_equal(times, ot)
+        segs, st, pads = h._split_token_into_length(frames, times)
+        osegs, ost, opads = O.split_into_segments(of, ot)
+        np.testing.assert_array_equal(segs, osegs)
+        np.testing.assert_array_equal(st, ost)
+        assert pads == opads
+    start, length, valid = sp.segment_table(70001)
+    assert list(start) == [0, 32768, 65536] and list(valid) == [256, 256, 35]
+    assert list(length) == [34688, 34688, 70001 - 65536]
+
+
+def test_postprocess_equals_oracle():
+    inf = importlib.import_module("mr-mt3_b200.inference")
+    t5 = importlib.import_module("mr-mt3_b200.t5")
+    h = inf.InferenceHandler.__new__(inf.InferenceHandler)
+    h.model = type("M", (), {"config": t5.T5Config()})()
+    ids = torch.tensor([[0, 10, 11, 1, 0, 0], [0, 7, 8, 9, 12, 13]])
+    pp = h._postprocess_batch(ids)
+    np.testing.assert_array_equal(pp, O.postprocess_batch(ids))
+    preds = h._to_predictions([pp], [np.array([[0.0164, 0.02], [2.048, 2.05]])])
+    np.testing.assert_array_equal(preds[0]["est_tokens"], [7, 8])
+    assert len(preds[1]["est_tokens"]) == 0                                 # no EOS -> empty (R11)
+    assert abs(preds[0]["start_time"] - 0.01) < 1e-9
+
+
+def test_shard_tracks_lpt():
+    sh = importlib.import_module("mr-mt3_b200.sharding")
+    counts = [int(c) for c in np.ceil(syn.slakh_shaped_durations(64, seed=1) * 125 / 256)]
+    for world in (1, 2, 4, 8):
+        shards = sh.shard_tracks(counts, world)
+        assert sorted(sum(shards, [])) == list(range(64))
+        loads = [sum(counts[t] for t in s) for s in shards]
+        assert max(loads) - min(loads) <= max(counts)
+
+
+def _gather_worker(rank, world, port, counts, max_length, q):
+    import torch.distributed as dist
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    sh = importlib.import_module("mr-mt3_b200.sharding")
+    mine = sh.shard_tracks(counts, world)[rank]
+    rows = []
+    for t in mine:
+        for s in range(counts[t]):
+            rows.append(torch.full((max_length,), 1000 * t + s, dtype=torch.int64))
+    local = torch.stack(rows) if rows else torch.zeros((0, max_length), dtype=torch.int64)
+    out = sh.gather_token_rows(local, mine, counts, max_length)
+    if rank == 0:
+        q.put(out.numpy())
+    dist.destroy_process_group()
+
+
+def test_gather_token_rows_gloo_world2():
+    import torch.multiprocessing as mp
+    counts, max_length = [3, 1, 4, 2, 2], 6
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = 29500 + os.getpid() % 2000
+    procs = [ctx.Process(target=_gather_worker, args=(r, 2, port, counts, max_length, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    out = q.get(timeout=120)
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    want = np.concatenate([[1000 * t + s for s in range(c)] for t, c in enumerate(counts)])
+    np.testing.assert_array_equal(out[:, 0], want)
+    assert out.shape == (sum(counts), max_length)
