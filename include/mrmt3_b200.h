@@ -65,6 +65,27 @@ const char* mrmt3_last_error(const mrmt3_handle* h);
 /* number of kernels this handle has launched so far (bench.py's gpu_launches) */
 int64_t mrmt3_launch_count(const mrmt3_handle* h);
 
+/* ---- per-kernel timing (bench.py's roofline leg) ---------------------------------------
+ * While enabled, the decode loop launches eagerly (no CUDA graph) and brackets every kernel
+ * with CUDA events on the launching stream; mrmt3_profile_read returns, per kernel class, the
+ * summed device time in ms and the launch count since mrmt3_profile_enable(h, 1), and resets
+ * them.  Never enabled inside a timed region. */
+#define MRMT3_PROF_EMBED 0
+#define MRMT3_PROF_RMSNORM 1
+#define MRMT3_PROF_GEMM_QKV 2
+#define MRMT3_PROF_ATTN_SELF 3
+#define MRMT3_PROF_GEMM_O 4
+#define MRMT3_PROF_GEMM_CQ 5
+#define MRMT3_PROF_ATTN_CROSS 6
+#define MRMT3_PROF_GEMM_CO 7
+#define MRMT3_PROF_GEMM_WI 8
+#define MRMT3_PROF_GEMM_WFF 9
+#define MRMT3_PROF_LM_HEAD 10
+#define MRMT3_PROF_ARGMAX 11
+#define MRMT3_PROF_NCAT 12
+int mrmt3_profile_enable(mrmt3_handle* h, int on);
+int mrmt3_profile_read(mrmt3_handle* h, double* ms_out, int64_t* launches_out, int n_cat);
+
 /* ---- weights -------------------------------------------------------------------------- */
 /* Replaces: model.load_state_dict(sd) (test.py:106-110, train.py:80-83).  `name` is the
  * reference's state-dict key (weight contract); `data` is fp32 row-major

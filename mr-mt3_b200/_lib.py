@@ -36,6 +36,8 @@ _PROTOTYPES = {
     "mrmt3_destroy": (None, [_c_void_p]),
     "mrmt3_last_error": (ctypes.c_char_p, [_c_void_p]),
     "mrmt3_launch_count": (_c_i64, [_c_void_p]),
+    "mrmt3_profile_enable": (_c_int, [_c_void_p, _c_int]),
+    "mrmt3_profile_read": (_c_int, [_c_void_p, _c_void_p, _c_void_p, _c_int]),
     "mrmt3_set_weight": (_c_int, [_c_void_p, ctypes.c_char_p, _c_void_p, _c_int, _c_int]),
     "mrmt3_commit_weights": (_c_int, [_c_void_p]),
     "mrmt3_set_mel_filterbank": (_c_int, [_c_void_p, _c_void_p]),
@@ -145,6 +147,20 @@ class Engine:
     @property
     def launch_count(self):
         return int(self._lib.mrmt3_launch_count(self._h))
+
+    PROF_NAMES = ("embed", "rmsnorm", "gemm_qkv", "attn_self", "gemm_o", "gemm_cq", "attn_cross",
+                  "gemm_co", "gemm_wi", "gemm_wff", "lm_head", "argmax")
+
+    def profile_enable(self, on=True):
+        self._check(self._lib.mrmt3_profile_enable(self._h, 1 if on else 0))
+
+    def profile_read(self):
+        """{kernel class: (total device ms, launches)} since profile_enable(True)."""
+        n = len(self.PROF_NAMES)
+        ms = (ctypes.c_double * n)()
+        cnt = (ctypes.c_int64 * n)()
+        self._check(self._lib.mrmt3_profile_read(self._h, ms, cnt, n))
+        return {k: (ms[i], int(cnt[i])) for i, k in enumerate(self.PROF_NAMES)}
 
     # ---- weights ------------------------------------------------------------------------------
     def load_state_dict(self, sd, strict=True):

@@ -23,6 +23,7 @@ Status api_transcribe_host(mrmt3_handle* h, const float* audio_host, long long n
                            const long long* seg_start_host, const int* seg_len_host,
                            const int* valid_frames_host, int n_seg, const int* seg_counts_host, int n_tracks,
                            int flags, int max_length, long long* out_ids_host, int* steps_host, cudaStream_t s);
+Status profile_collect(mrmt3_handle* h);
 }  // namespace mrmt3
 
 using namespace mrmt3;
@@ -97,6 +98,31 @@ void mrmt3_destroy(mrmt3_handle* h) {
 const char* mrmt3_last_error(const mrmt3_handle* h) { return h ? h->err.c_str() : g_create_error.c_str(); }
 
 int64_t mrmt3_launch_count(const mrmt3_handle* h) { return h ? h->launches : 0; }
+
+int mrmt3_profile_enable(mrmt3_handle* h, int on) {
+    GUARD(h)
+    h->prof_on = on != 0;
+    for (int i = 0; i < MRMT3_PROF_NCAT; ++i) {
+        h->prof_ms[i] = 0;
+        h->prof_n[i] = 0;
+    }
+    return 0;
+    END_GUARD(h)
+}
+
+int mrmt3_profile_read(mrmt3_handle* h, double* ms_out, int64_t* launches_out, int n_cat) {
+    GUARD(h)
+    Status st = profile_collect(h);
+    if (!st.ok()) return finish(h, st);
+    for (int i = 0; i < n_cat && i < MRMT3_PROF_NCAT; ++i) {
+        if (ms_out) ms_out[i] = h->prof_ms[i];
+        if (launches_out) launches_out[i] = h->prof_n[i];
+        h->prof_ms[i] = 0;
+        h->prof_n[i] = 0;
+    }
+    return 0;
+    END_GUARD(h)
+}
 
 int mrmt3_set_weight(mrmt3_handle* h, const char* name, const float* data, int rows, int cols) {
     GUARD(h)

@@ -64,6 +64,46 @@ constexpr int kPollEvery = 8;     // decode steps between early-exit polls
         ++(h)->launches;      \
     } while (0)
 
+static cudaEvent_t prof_event(mrmt3_handle* h) {
+    if (!h->prof_pool.empty()) {
+        cudaEvent_t e = h->prof_pool.back();
+        h->prof_pool.pop_back();
+        return e;
+    }
+    cudaEvent_t e = nullptr;
+    cudaEventCreate(&e);
+    return e;
+}
+
+// decode-step launch tagged with its kernel class; event-bracketed when profiling is on
+#define RUNC(h, cat, s, call)                                   \
+    do {                                                        \
+        if ((h)->prof_on) {                                     \
+            mrmt3_handle::ProfRec _r{cat, prof_event(h), prof_event(h)}; \
+            cudaEventRecord(_r.a, s);                           \
+            MRMT3_TRY(call);                                    \
+            cudaEventRecord(_r.b, s);                           \
+            (h)->prof_recs.push_back(_r);                       \
+        } else {                                                \
+            MRMT3_TRY(call);                                    \
+        }                                                       \
+        ++(h)->launches;                                        \
+    } while (0)
+
+Status profile_collect(mrmt3_handle* h) {
+    for (auto& r : h->prof_recs) {
+        MRMT3_CUDA_TRY(cudaEventSynchronize(r.b));
+        float ms = 0.f;
+        MRMT3_CUDA_TRY(cudaEventElapsedTime(&ms, r.a, r.b));
+        h->prof_ms[r.cat] += ms;
+        h->prof_n[r.cat] += 1;
+        h->prof_pool.push_back(r.a);
+        h->prof_pool.push_back(r.b);
+    }
+    h->prof_recs.clear();
+    return OkStatus();
+}
+
 static size_t page_elems(const mrmt3_handle* h) {
     return (size_t)h->cfg.n_dec_layers * 2 * kHeads * kKVPage * kDKV;
 }
@@ -494,11 +534,11 @@ static Status enqueue_step(mrmt3_handle* h, const StepPlan& pl, int kind, cudaSt
     bf16* qc = h->d_qc.as<bf16>();
     bf16* ff = h->d_ff.as<bf16>();
     const ARowMap id{nullptr, 1};
-    RUN(h, launch_decode_embed(pl.st, h->emb, h->pe, pl.prefix, pl.st.prefix_len * kDModel, H, n, s));
+    RUNC(h, MRMT3_PROF_EMBED, s, launch_decode_embed(pl.st, h->emb, h->pe, pl.prefix, pl.st.prefix_len * kDModel, H, n, s));
     for (int li = 0; li < h->cfg.n_dec_layers; ++li) {
         const LayerW& L = h->dec.layers[li];
-        RUN(h, launch_rmsnorm(H, L.ln_self, eps, nb, nullptr, n, pl.st.active, 1, s));
-        RUN(h, launch_gemm_mma(nb, kDModel, id, L.wqkv, kDModel, n, 3 * kInner, kDModel,
+        RUNC(h, MRMT3_PROF_RMSNORM, s, launch_rmsnorm(H, L.ln_self, eps, nb, nullptr, n, pl.st.active, 1, s));
+        RUNC(h, MRMT3_PROF_GEMM_QKV, s, launch_gemm_mma(nb, kDModel, id, L.wqkv, kDModel, n, 3 * kInner, kDModel,
                                EpiStoreBf16{qkv, 3 * kInner}, s));
         AttnDecodeParams ap{};
         ap.q = qkv;
@@ -514,11 +554,11 @@ static Status enqueue_step(mrmt3_handle* h, const StepPlan& pl, int kind, cudaSt
         ap.max_pages = h->page_cap;
         ap.page_stride = page_elems(h);
         ap.active = pl.st.active;
-        RUN(h, launch_attn_decode(ap, n, true, s));
-        RUN(h, launch_gemm_mma(ctx, kInner, id, L.wo, kInner, n, kDModel, kInner, EpiResidual{H, kDModel}, s));
+        RUNC(h, MRMT3_PROF_ATTN_SELF, s, launch_attn_decode(ap, n, true, s));
+        RUNC(h, MRMT3_PROF_GEMM_O, s, launch_gemm_mma(ctx, kInner, id, L.wo, kInner, n, kDModel, kInner, EpiResidual{H, kDModel}, s));
 
-        RUN(h, launch_rmsnorm(H, L.ln_cross, eps, nb, nullptr, n, pl.st.active, 1, s));
-        RUN(h, launch_gemm_mma(nb, kDModel, id, L.cq, kDModel, n, kInner, kDModel, EpiStoreBf16{qc, kInner}, s));
+        RUNC(h, MRMT3_PROF_RMSNORM, s, launch_rmsnorm(H, L.ln_cross, eps, nb, nullptr, n, pl.st.active, 1, s));
+        RUNC(h, MRMT3_PROF_GEMM_CQ, s, launch_gemm_mma(nb, kDModel, id, L.cq, kDModel, n, kInner, kDModel, EpiStoreBf16{qc, kInner}, s));
         AttnDecodeParams cp{};
         cp.q = qc;
         cp.q_stride = kInner;
@@ -530,29 +570,29 @@ static Status enqueue_step(mrmt3_handle* h, const StepPlan& pl, int kind, cudaSt
         cp.tk_cap = h->tk_cap;
         cp.n_keys = pl.tk;
         cp.active = pl.st.active;
-        RUN(h, launch_attn_decode(cp, n, false, s));
-        RUN(h, launch_gemm_mma(ctx, kInner, id, L.co, kInner, n, kDModel, kInner, EpiResidual{H, kDModel}, s));
+        RUNC(h, MRMT3_PROF_ATTN_CROSS, s, launch_attn_decode(cp, n, false, s));
+        RUNC(h, MRMT3_PROF_GEMM_CO, s, launch_gemm_mma(ctx, kInner, id, L.co, kInner, n, kDModel, kInner, EpiResidual{H, kDModel}, s));
 
-        RUN(h, launch_rmsnorm(H, L.ln_ff, eps, nb, nullptr, n, pl.st.active, 1, s));
-        RUN(h, launch_gemm_mma(nb, kDModel, id, L.wi, kDModel, n, 2 * kDFF, kDModel, EpiGatedGelu{ff, kDFF}, s));
-        RUN(h, launch_gemm_mma(ff, kDFF, id, L.wff, kDFF, n, kDModel, kDFF, EpiResidual{H, kDModel}, s));
+        RUNC(h, MRMT3_PROF_RMSNORM, s, launch_rmsnorm(H, L.ln_ff, eps, nb, nullptr, n, pl.st.active, 1, s));
+        RUNC(h, MRMT3_PROF_GEMM_WI, s, launch_gemm_mma(nb, kDModel, id, L.wi, kDModel, n, 2 * kDFF, kDModel, EpiGatedGelu{ff, kDFF}, s));
+        RUNC(h, MRMT3_PROF_GEMM_WFF, s, launch_gemm_mma(ff, kDFF, id, L.wff, kDFF, n, kDModel, kDFF, EpiResidual{H, kDModel}, s));
     }
     if (kind == 1) {
-        RUN(h, launch_advance_only(pl.st, s));
+        RUNC(h, MRMT3_PROF_ARGMAX, s, launch_advance_only(pl.st, s));
         return OkStatus();
     }
-    RUN(h, launch_rmsnorm(H, h->dec.final_ln, eps, nb, nullptr, n, pl.st.active, 1, s));
+    RUNC(h, MRMT3_PROF_RMSNORM, s, launch_rmsnorm(H, h->dec.final_ln, eps, nb, nullptr, n, pl.st.active, 1, s));
     if (pl.ext_logits) {
         const size_t lane_stride = (size_t)pl.st.max_tokens * kVocab;
-        RUN(h, launch_gemm_mma(nb, kDModel, id, h->lm_head, kDModel, n, kVocab, kDModel,
+        RUNC(h, MRMT3_PROF_LM_HEAD, s, launch_gemm_mma(nb, kDModel, id, h->lm_head, kDModel, n, kVocab, kDModel,
                                EpiStoreF32Step{pl.ext_logits, kVocab, lane_stride, pl.st.step,
                                                pl.st.prefix_len, pl.st.out_row}, s));
-        RUN(h, launch_argmax_advance(pl.st, pl.ext_logits, lane_stride, kVocab, n, kVocab, s));
+        RUNC(h, MRMT3_PROF_ARGMAX, s, launch_argmax_advance(pl.st, pl.ext_logits, lane_stride, kVocab, n, kVocab, s));
     } else {
         float* lg = h->d_logits.as<float>();
-        RUN(h, launch_gemm_mma(nb, kDModel, id, h->lm_head, kDModel, n, kVocab, kDModel,
+        RUNC(h, MRMT3_PROF_LM_HEAD, s, launch_gemm_mma(nb, kDModel, id, h->lm_head, kDModel, n, kVocab, kDModel,
                                EpiStoreF32{lg, kVocab}, s));
-        RUN(h, launch_argmax_advance(pl.st, lg, kVocab, 0, n, kVocab, s));
+        RUNC(h, MRMT3_PROF_ARGMAX, s, launch_argmax_advance(pl.st, lg, kVocab, 0, n, kVocab, s));
     }
     return OkStatus();
 }
@@ -591,7 +631,7 @@ static Status get_graph(mrmt3_handle* h, const StepPlan& pl, int kind, StepGraph
 // then up to max_tokens token steps, stopping early once every lane has emitted EOS (polled
 // every kPollEvery steps without draining the queue).
 static Status run_decode(mrmt3_handle* h, StepPlan pl, int n_prefix, bool debug_mode, cudaStream_t s) {
-    const bool graphs = h->use_graphs && !debug_mode;
+    const bool graphs = h->use_graphs && !debug_mode && !h->prof_on;
     StepGraph *g_tok = nullptr, *g_pre = nullptr;
     if (graphs) {
         MRMT3_TRY(get_graph(h, pl, 0, &g_tok));
@@ -632,6 +672,7 @@ static Status run_decode(mrmt3_handle* h, StepPlan pl, int n_prefix, bool debug_
         }
     }
     MRMT3_CUDA_TRY(cudaStreamSynchronize(s));
+    if (h->prof_on) MRMT3_TRY(profile_collect(h));
     return OkStatus();
 }
 

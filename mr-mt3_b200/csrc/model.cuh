@@ -110,5 +110,14 @@ struct mrmt3_handle {
     int* h_pinned = nullptr;             // pinned host ints for polling / finish steps
 
     std::map<mrmt3::StepGraphKey, mrmt3::StepGraph> graphs;
+
+    // per-kernel-class timing of the decode step (mrmt3_profile_*): eager launches bracketed by
+    // CUDA events on the launching stream
+    bool prof_on = false;
+    struct ProfRec { int cat; cudaEvent_t a, b; };
+    std::vector<ProfRec> prof_recs;
+    std::vector<cudaEvent_t> prof_pool;
+    double prof_ms[MRMT3_PROF_NCAT] = {0};
+    int64_t prof_n[MRMT3_PROF_NCAT] = {0};
     cudaEvent_t poll_ev[2] = {nullptr, nullptr};
 };
