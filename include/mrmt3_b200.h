@@ -65,6 +65,10 @@ const char* mrmt3_last_error(const mrmt3_handle* h);
 /* number of kernels this handle has launched so far (bench.py's gpu_launches) */
 int64_t mrmt3_launch_count(const mrmt3_handle* h);
 
+/* Tuning knobs (all have working defaults).  key: "group_lanes" = lanes per concurrently
+ * decoding lane group (0 = one group), "use_graphs" = replay the decode step as a CUDA graph. */
+int mrmt3_set_option(mrmt3_handle* h, const char* key, int value);
+
 /* ---- per-kernel timing (bench.py's roofline leg) ---------------------------------------
  * While enabled, the decode loop launches eagerly (no CUDA graph) and brackets every kernel
  * with CUDA events on the launching stream; mrmt3_profile_read returns, per kernel class, the
@@ -85,6 +89,15 @@ int64_t mrmt3_launch_count(const mrmt3_handle* h);
 #define MRMT3_PROF_NCAT 12
 int mrmt3_profile_enable(mrmt3_handle* h, int on);
 int mrmt3_profile_read(mrmt3_handle* h, double* ms_out, int64_t* launches_out, int n_cat);
+
+/* ---- in-graph timeline trace (profiles/, never inside a timed region) --------------------
+ * With tracing on, every decode-step kernel stamps the GPU global timer (ns) when its CTA 0
+ * starts and when its last CTA ends; the stamps of the most recent step are read back as
+ * out[2*i] = begin, out[2*i+1] = end for kernel i of the step (embed, then per layer: qkv,
+ * self-attention, o, cross-q, cross-attention, o, ffn-in, ffn-out, then lm_head, arg-max).
+ * Enabling/disabling drops the captured step graphs.  Returns the number of slots written. */
+int mrmt3_trace_enable(mrmt3_handle* h, int on);
+int mrmt3_trace_read(mrmt3_handle* h, uint64_t* out, int max_slots);
 
 /* ---- weights -------------------------------------------------------------------------- */
 /* Replaces: model.load_state_dict(sd) (test.py:106-110, train.py:80-83).  `name` is the

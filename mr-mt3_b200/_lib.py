@@ -36,6 +36,9 @@ _PROTOTYPES = {
     "mrmt3_destroy": (None, [_c_void_p]),
     "mrmt3_last_error": (ctypes.c_char_p, [_c_void_p]),
     "mrmt3_launch_count": (_c_i64, [_c_void_p]),
+    "mrmt3_set_option": (_c_int, [_c_void_p, ctypes.c_char_p, _c_int]),
+    "mrmt3_trace_enable": (_c_int, [_c_void_p, _c_int]),
+    "mrmt3_trace_read": (_c_int, [_c_void_p, _c_void_p, _c_int]),
     "mrmt3_profile_enable": (_c_int, [_c_void_p, _c_int]),
     "mrmt3_profile_read": (_c_int, [_c_void_p, _c_void_p, _c_void_p, _c_int]),
     "mrmt3_set_weight": (_c_int, [_c_void_p, ctypes.c_char_p, _c_void_p, _c_int, _c_int]),
@@ -150,6 +153,18 @@ class Engine:
 
     PROF_NAMES = ("embed", "rmsnorm", "gemm_qkv", "attn_self", "gemm_o", "gemm_cq", "attn_cross",
                   "gemm_co", "gemm_wi", "gemm_wff", "lm_head", "argmax")
+
+    def set_option(self, key, value):
+        self._check(self._lib.mrmt3_set_option(self._h, key.encode(), int(value)))
+
+    def trace_enable(self, on=True):
+        self._check(self._lib.mrmt3_trace_enable(self._h, 1 if on else 0))
+
+    def trace_read(self, n_slots=75):
+        """[(begin_ns, end_ns)] of the decode-step kernels of the most recent step."""
+        buf = (ctypes.c_uint64 * (2 * n_slots))()
+        n = self._lib.mrmt3_trace_read(self._h, buf, n_slots)
+        return [(int(buf[2 * i]), int(buf[2 * i + 1])) for i in range(n)]
 
     def profile_enable(self, on=True):
         self._check(self._lib.mrmt3_profile_enable(self._h, 1 if on else 0))

@@ -1,4 +1,5 @@
 // extern "C" boundary (include/mrmt3_b200.h).  Status -> int + message; nothing throws across.
+#include <algorithm>
 #include <new>
 
 #include "model.cuh"
@@ -24,6 +25,7 @@ Status api_transcribe_host(mrmt3_handle* h, const float* audio_host, long long n
                            const int* valid_frames_host, int n_seg, const int* seg_counts_host, int n_tracks,
                            int flags, int max_length, long long* out_ids_host, int* steps_host, cudaStream_t s);
 Status profile_collect(mrmt3_handle* h);
+Status trace_enable(mrmt3_handle* h, bool on);
 }  // namespace mrmt3
 
 using namespace mrmt3;
@@ -98,6 +100,38 @@ void mrmt3_destroy(mrmt3_handle* h) {
 const char* mrmt3_last_error(const mrmt3_handle* h) { return h ? h->err.c_str() : g_create_error.c_str(); }
 
 int64_t mrmt3_launch_count(const mrmt3_handle* h) { return h ? h->launches : 0; }
+
+int mrmt3_set_option(mrmt3_handle* h, const char* key, int value) {
+    GUARD(h)
+    if (!key) return finish(h, Error(1, "null key"));
+    std::string k(key);
+    if (k == "group_lanes") h->group_lanes = value;
+    else if (k == "use_graphs") h->use_graphs = value != 0;
+    else if (k == "group_serial") h->group_serial = value != 0;
+    else return finish(h, Error(3, "unknown option: " + k));
+    return 0;
+    END_GUARD(h)
+}
+
+int mrmt3_trace_enable(mrmt3_handle* h, int on) {
+    GUARD(h)
+    cudaSetDevice(h->device);
+    cudaDeviceSynchronize();
+    Status st = trace_enable(h, on != 0);
+    return finish(h, st);
+    END_GUARD(h)
+}
+
+int mrmt3_trace_read(mrmt3_handle* h, uint64_t* out, int max_slots) {
+    GUARD(h)
+    if (!h->trace_buf.p || !out) return 0;
+    cudaSetDevice(h->device);
+    cudaDeviceSynchronize();
+    int n = std::min(max_slots, 256);
+    if (cudaMemcpy(out, h->trace_buf.p, (size_t)n * 16, cudaMemcpyDeviceToHost) != cudaSuccess) return 0;
+    return n;
+    END_GUARD(h)
+}
 
 int mrmt3_profile_enable(mrmt3_handle* h, int on) {
     GUARD(h)

@@ -50,6 +50,7 @@ struct AttnDecodeParams {
     const int* n_keys_ptr;   // optional per-lane key count
     // early-exit mask: lanes with active[lane] == 0 are skipped
     const int* active;
+    TraceSlot trace;
 };
 Status launch_attn_decode(const AttnDecodeParams& p, int n_lanes, bool paged, cudaStream_t stream);
 int attn_decode_max_keys();

@@ -129,4 +129,54 @@ __device__ __forceinline__ uint4 ld_stream16(const void* p) {
 
 inline int ceil_div(int a, int b) { return (a + b - 1) / b; }
 
+// ---- programmatic dependent launch (PDL) -----------------------------------------------------
+// The decode step is a chain of ~70 short dependent kernels.  Launched with the programmatic
+// stream-serialization attribute, kernel N+1 is scheduled while kernel N is still running; it may
+// do anything that does not depend on N (fetch weights, old KV rows) and then blocks in
+// pdl_wait() until N has completed and its writes are visible.  Works eagerly and under stream
+// capture (the edge becomes a programmatic dependency in the CUDA graph).
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;\n" ::: "memory"); }
+__device__ __forceinline__ void pdl_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;\n" ::); }
+
+// ---- in-graph timeline trace ------------------------------------------------------------------
+// When a trace buffer is attached, every decode-step kernel stamps %globaltimer at the entry of its
+// earliest CTA and at the exit of its latest CTA into slot `slot` (two u64 per slot).  The slots
+// are baked into the captured graph, so after a replay the buffer holds the timeline of that step
+// as it really ran inside the graph (overlaps, gaps) -- ncu serialises launches and cannot show it.
+struct TraceSlot {
+    unsigned long long* buf;  // nullptr = tracing off
+    int slot;
+};
+__device__ __forceinline__ unsigned long long global_timer() {
+    unsigned long long t;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+    return t;
+}
+__device__ __forceinline__ void trace_begin(const TraceSlot& t) {
+    // plain store by CTA 0: a later replay overwrites an earlier one (the end stamp is an atomicMax
+    // of a monotonic clock, so it also ends up holding the latest replay)
+    if (t.buf && threadIdx.x == 0 && blockIdx.x == 0 && blockIdx.y == 0 && blockIdx.z == 0)
+        t.buf[2 * t.slot] = global_timer();
+}
+__device__ __forceinline__ void trace_end(const TraceSlot& t) {
+    if (t.buf && threadIdx.x == 0) atomicMax(t.buf + 2 * t.slot + 1, global_timer());
+}
+
+template <class... KArgs, class... Args>
+inline Status launch_pdl(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t stream,
+                         Args... args) {
+    cudaLaunchConfig_t cfg{};
+    cfg.gridDim = grid;
+    cfg.blockDim = block;
+    cfg.dynamicSmemBytes = smem;
+    cfg.stream = stream;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
+    MRMT3_CUDA_TRY(cudaLaunchKernelEx(&cfg, kernel, KArgs(args)...));
+    return OkStatus();
+}
+
 }  // namespace mrmt3

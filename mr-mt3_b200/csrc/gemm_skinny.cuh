@@ -1,0 +1,196 @@
+// Decode-step projections: C[M,N] = A[M,K] * W[N,K]^T with M = number of decode lanes (<= 512).
+//
+// These GEMMs are latency-bound, not tensor-bound (0.1-0.5 GFLOP, operands L2-resident): what
+// matters is how many dependent memory round trips a CTA makes and how many CTAs share the work.
+// So, unlike the pipelined kernel in gemm_mma.cuh, every CTA here issues the loads for its WHOLE
+// K extent up front (K is a compile-time 384/512/1024: at most 128 KB of shared memory), one
+// cp.async group per 64-wide k-tile, and consumes the tiles as they land: one memory latency per
+// CTA instead of K/64.  Tiles are 32 x 32 or 32 x 64 so that M = 256 gives 128-256 CTAs.
+//
+// NORM = true fuses T5LayerNorm (reference via HF modeling_t5.py:55-70) into the GEMM: A holds
+// the un-normalised bf16 copy of the residual stream, W has the norm weight folded into its
+// columns (W'[n,k] = W[n,k] * g[k], packed at commit time), and because K == d_model each CTA
+// sees complete rows, computes sum(x^2) from its shared A tiles and scales the accumulators by
+// rsqrt(mean + eps) in the epilogue:  (x * r * g) W^T == r * (x (W g)^T).
+#pragma once
+#include "gemm_mma.cuh"
+
+namespace mrmt3 {
+
+// residual stream update that also refreshes the bf16 copy the next NORM GEMM reads
+struct EpiResidualBoth {
+    float* H;
+    bf16* Hb;
+    int ldh;
+    __device__ __forceinline__ void operator()(int row, int col, float v0, float v1) const {
+        size_t o = (size_t)row * ldh + col;
+        float2* p = reinterpret_cast<float2*>(H + o);
+        float2 h = *p;
+        h.x += v0;
+        h.y += v1;
+        *p = h;
+        *reinterpret_cast<uint32_t*>(Hb + o) = pack_bf16(h.x, h.y);
+    }
+};
+
+__device__ __forceinline__ void cp_async_wait_dyn(int n) {
+    switch (n) {
+        case 0: cp_async_wait<0>(); break;
+        case 1: cp_async_wait<1>(); break;
+        case 2: cp_async_wait<2>(); break;
+        case 3: cp_async_wait<3>(); break;
+        case 4: cp_async_wait<4>(); break;
+        case 5: cp_async_wait<5>(); break;
+        case 6: cp_async_wait<6>(); break;
+        case 7: cp_async_wait<7>(); break;
+        case 8: cp_async_wait<8>(); break;
+        case 9: cp_async_wait<9>(); break;
+        case 10: cp_async_wait<10>(); break;
+        case 11: cp_async_wait<11>(); break;
+        case 12: cp_async_wait<12>(); break;
+        case 13: cp_async_wait<13>(); break;
+        case 14: cp_async_wait<14>(); break;
+        default: cp_async_wait<15>(); break;
+    }
+}
+
+template <int BN, int K, bool NORM, class Epi>
+__global__ void __launch_bounds__(128)
+    gemm_skinny_kernel(const bf16* __restrict__ A, int lda, const bf16* __restrict__ W, int ldw, int M,
+                       float eps, Epi epi, TraceSlot trace) {
+    constexpr int BM = 32;
+    trace_begin(trace);
+    constexpr int KT = K / 64;
+    constexpr int NI = BN / 16;  // n-blocks of 8 per warp (warp tile 16 x BN/2)
+    static_assert(KT <= 16, "K too large for the single-shot pipeline");
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    bf16* sA = reinterpret_cast<bf16*>(smem_raw);   // [KT][BM*64]
+    bf16* sW = sA + KT * BM * 64;                   // [KT][BN*64]
+    __shared__ float s_scale[BM];
+
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int wm0 = (warp >> 1) * 16;
+    const int wn0 = (warp & 1) * (BN / 2);
+    const int m0 = blockIdx.y * BM;
+    const int n0 = blockIdx.x * BN;
+
+    // Issue every load of this CTA, one commit group per k-tile.  The weight tiles do not depend
+    // on the producer kernel, so they are requested before the programmatic-dependency wait and
+    // their latency overlaps the producer's tail; the activation tiles follow the wait.
+#pragma unroll
+    for (int kt = 0; kt < KT; ++kt) {
+        const int k0 = kt * 64;
+#pragma unroll
+        for (int i = 0; i < (BN * 8) / 128; ++i) {
+            int c = tid + i * 128;
+            int row = c >> 3, ch = c & 7;
+            cp_async16(sW + kt * BN * 64 + row * 64 + ((ch ^ (row & 7)) << 3),
+                       W + (size_t)(n0 + row) * ldw + k0 + ch * 8, true);
+        }
+        cp_async_commit();
+    }
+    pdl_wait();
+    pdl_launch_dependents();
+#pragma unroll
+    for (int kt = 0; kt < KT; ++kt) {
+        const int k0 = kt * 64;
+#pragma unroll
+        for (int i = 0; i < (BM * 8) / 128; ++i) {
+            int c = tid + i * 128;
+            int row = c >> 3, ch = c & 7;
+            bool pred = (m0 + row) < M;
+            cp_async16(sA + kt * BM * 64 + row * 64 + ((ch ^ (row & 7)) << 3),
+                       A + (size_t)(pred ? m0 + row : 0) * lda + k0 + ch * 8, pred);
+        }
+        cp_async_commit();
+    }
+
+    float acc[NI][4];
+#pragma unroll
+    for (int j = 0; j < NI; ++j)
+#pragma unroll
+        for (int r = 0; r < 4; ++r) acc[j][r] = 0.f;
+    float ss = 0.f;  // NORM: partial sum of squares of row tid/4
+
+#pragma unroll
+    for (int kt = 0; kt < KT; ++kt) {
+        cp_async_wait_dyn(KT - 1 - kt);
+        __syncthreads();
+        const uint32_t baseA = smem_u32(sA + kt * BM * 64);
+        const uint32_t baseW = smem_u32(sW + kt * BN * 64);
+        if (NORM) {
+            // 4 threads per row, 2 of the 8 16-byte chunks each.  The chunks are addressed
+            // LOGICALLY (un-swizzled), so the order of the fp32 sum -- and with it the result --
+            // does not depend on where in the tile the row sits (rows must not depend on their
+            // batch neighbours: tests/test_parity_gpu.py::test_lane_groups_do_not_change_tokens)
+            const int row = tid >> 2;
+            const bf16* rp = sA + kt * BM * 64 + row * 64;
+#pragma unroll
+            for (int c = 0; c < 2; ++c) {
+                uint4 raw = *reinterpret_cast<const uint4*>(rp + ((((tid & 3) * 2 + c) ^ (row & 7)) << 3));
+                const bf162* h2 = reinterpret_cast<const bf162*>(&raw);
+#pragma unroll
+                for (int i = 0; i < 4; ++i) {
+                    float2 f = __bfloat1622float2(h2[i]);
+                    ss += f.x * f.x + f.y * f.y;
+                }
+            }
+        }
+#pragma unroll
+        for (int kk = 0; kk < 4; ++kk) {
+            uint32_t af[4];
+            {
+                int row = wm0 + (lane & 15);
+                int ch = kk * 2 + (lane >> 4);
+                ldmatrix_x4(af[0], af[1], af[2], af[3], baseA + row * 128 + ((ch ^ (row & 7)) << 4));
+            }
+#pragma unroll
+            for (int nj = 0; nj < NI / 2; ++nj) {
+                int row = wn0 + nj * 16 + (lane & 7) + ((lane >> 4) << 3);
+                int ch = kk * 2 + ((lane >> 3) & 1);
+                uint32_t b0, b1, b2, b3;
+                ldmatrix_x4(b0, b1, b2, b3, baseW + row * 128 + ((ch ^ (row & 7)) << 4));
+                mma_bf16_16816(acc[nj * 2], af, b0, b1);
+                mma_bf16_16816(acc[nj * 2 + 1], af, b2, b3);
+            }
+        }
+    }
+
+    float sc0 = 1.f, sc1 = 1.f;
+    if (NORM) {
+        ss += __shfl_xor_sync(0xffffffffu, ss, 1);
+        ss += __shfl_xor_sync(0xffffffffu, ss, 2);
+        if ((tid & 3) == 0) s_scale[tid >> 2] = rsqrtf(ss * (1.0f / K) + eps);
+        __syncthreads();
+        sc0 = s_scale[wm0 + (lane >> 2)];
+        sc1 = s_scale[wm0 + (lane >> 2) + 8];
+    }
+#pragma unroll
+    for (int ni = 0; ni < NI; ++ni) {
+        int row = m0 + wm0 + (lane >> 2);
+        int col = n0 + wn0 + ni * 8 + (lane & 3) * 2;
+        if (row < M) epi(row, col, acc[ni][0] * sc0, acc[ni][1] * sc0);
+        if (row + 8 < M) epi(row + 8, col, acc[ni][2] * sc1, acc[ni][3] * sc1);
+    }
+    trace_end(trace);
+}
+
+template <int BN, int K, bool NORM, class Epi>
+Status launch_gemm_skinny(const bf16* A, int lda, const bf16* W, int ldw, int M, int N, float eps,
+                          const Epi& epi, cudaStream_t stream, TraceSlot trace = TraceSlot{nullptr, 0}) {
+    if (M <= 0) return OkStatus();
+    if (N % BN != 0) return Error(2, "gemm_skinny: N must be a multiple of the column tile");
+    static_assert(!NORM || K == kDModel, "fused RMSNorm needs complete rows: K == d_model");
+    auto kern = gemm_skinny_kernel<BN, K, NORM, Epi>;
+    constexpr int smem = (32 + BN) * K * (int)sizeof(bf16);
+    static bool attr_set = false;
+    if (!attr_set) {
+        MRMT3_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+        attr_set = true;
+    }
+    dim3 grid(N / BN, ceil_div(M, 32));
+    MRMT3_TRY(launch_pdl(kern, grid, dim3(128), smem, stream, A, lda, W, ldw, M, eps, epi, trace));
+    return OkStatus();
+}
+
+}  // namespace mrmt3

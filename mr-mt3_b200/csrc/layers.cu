@@ -40,6 +40,37 @@ Status launch_pack_weight(const float* src, bf16* dst, int rows, int cols, int r
     return OkStatus();
 }
 
+__global__ void pack_weight_f32_kernel(const float* __restrict__ src, float* __restrict__ dst, int rows,
+                                       int cols, int row_mul, int row_off) {
+    size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    size_t n = (size_t)rows * cols;
+    if (i >= n) return;
+    int r = (int)(i / cols), c = (int)(i % cols);
+    dst[((size_t)r * row_mul + row_off) * cols + c] = src[i];
+}
+
+Status launch_pack_weight_f32(const float* src, float* dst, int rows, int cols, int row_mul, int row_off,
+                              cudaStream_t s) {
+    size_t n = (size_t)rows * cols;
+    pack_weight_f32_kernel<<<(unsigned)((n + 255) / 256), 256, 0, s>>>(src, dst, rows, cols, row_mul, row_off);
+    MRMT3_CHECK_LAUNCH();
+    return OkStatus();
+}
+
+__global__ void fold_norm_kernel(const float* __restrict__ master, const float* __restrict__ g,
+                                 bf16* __restrict__ dst, int rows, int cols) {
+    size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= (size_t)rows * cols) return;
+    dst[i] = __float2bfloat16(master[i] * g[i % cols]);
+}
+
+Status launch_fold_norm(const float* master, const float* g, bf16* dst, int rows, int cols, cudaStream_t s) {
+    size_t n = (size_t)rows * cols;
+    fold_norm_kernel<<<(unsigned)((n + 255) / 256), 256, 0, s>>>(master, g, dst, rows, cols);
+    MRMT3_CHECK_LAUNCH();
+    return OkStatus();
+}
+
 // ---------------------------------------------------------------------------------------------
 // one warp per row of 512
 __global__ void __launch_bounds__(256)
@@ -152,7 +183,11 @@ Status launch_gather_rows(const float* src, float* dst, int n_lanes, int n, int 
 // ---------------------------------------------------------------------------------------------
 __global__ void decode_embed_kernel(DecodeState st, const float* __restrict__ emb,
                                     const float* __restrict__ pe, const float* __restrict__ prefix,
-                                    int prefix_stride, float* __restrict__ H, int n_lanes) {
+                                    int prefix_stride, float* __restrict__ H, bf16* __restrict__ Hb,
+                                    int n_lanes) {
+    trace_begin(st.trace);
+    pdl_wait();  // tok / active / step come from the previous step's arg-max kernel
+    pdl_launch_dependents();
     int lane = blockIdx.x * 2 + (threadIdx.x >> 7);
     if (lane >= n_lanes) return;
     if (!st.active[lane]) return;
@@ -164,15 +199,18 @@ __global__ void decode_embed_kernel(DecodeState st, const float* __restrict__ em
     else
         e = *reinterpret_cast<const float4*>(emb + (size_t)st.tok[lane] * kDModel + c);
     float4 p = *reinterpret_cast<const float4*>(pe + (size_t)pos * kDModel + c);
-    *reinterpret_cast<float4*>(H + (size_t)lane * kDModel + c) =
-        make_float4(e.x + p.x, e.y + p.y, e.z + p.z, e.w + p.w);
+    const float4 hv = make_float4(e.x + p.x, e.y + p.y, e.z + p.z, e.w + p.w);
+    *reinterpret_cast<float4*>(H + (size_t)lane * kDModel + c) = hv;
+    *reinterpret_cast<uint2*>(Hb + (size_t)lane * kDModel + c) =
+        make_uint2(pack_bf16(hv.x, hv.y), pack_bf16(hv.z, hv.w));
+    trace_end(st.trace);
 }
 
 Status launch_decode_embed(const DecodeState& st, const float* emb, const float* pe,
-                           const float* prefix, int prefix_stride, float* H, int n_lanes,
+                           const float* prefix, int prefix_stride, float* H, bf16* Hb, int n_lanes,
                            cudaStream_t s) {
-    decode_embed_kernel<<<ceil_div(n_lanes, 2), 256, 0, s>>>(st, emb, pe, prefix, prefix_stride, H, n_lanes);
-    MRMT3_CHECK_LAUNCH();
+    MRMT3_TRY(launch_pdl(decode_embed_kernel, dim3(ceil_div(n_lanes, 2)), dim3(256), 0, s, st, emb, pe, prefix,
+                         prefix_stride, H, Hb, n_lanes));
     return OkStatus();
 }
 
@@ -180,6 +218,9 @@ Status launch_decode_embed(const DecodeState& st, const float* emb, const float*
 __global__ void __launch_bounds__(256)
     argmax_advance_kernel(DecodeState st, const float* __restrict__ logits, size_t lane_stride,
                           size_t step_stride, int n_lanes, int vocab) {
+    trace_begin(st.trace);
+    pdl_wait();
+    pdl_launch_dependents();
     const int lane = blockIdx.x * 8 + (threadIdx.x >> 5);
     const int t = threadIdx.x & 31;
     const int step = st.step[0];
@@ -228,18 +269,18 @@ __global__ void __launch_bounds__(256)
             st.step[0] = step + 1;
         }
     }
+    trace_end(st.trace);
 }
 
 Status launch_argmax_advance(const DecodeState& st, const float* logits, size_t lane_stride,
                              size_t step_stride, int n_lanes, int vocab, cudaStream_t s) {
-    argmax_advance_kernel<<<ceil_div(n_lanes, 8), 256, 0, s>>>(st, logits, lane_stride, step_stride,
-                                                               n_lanes, vocab);
-    MRMT3_CHECK_LAUNCH();
+    MRMT3_TRY(launch_pdl(argmax_advance_kernel, dim3(ceil_div(n_lanes, 8)), dim3(256), 0, s, st, logits,
+                         lane_stride, step_stride, n_lanes, vocab));
     return OkStatus();
 }
 
 __global__ void decode_init_kernel(DecodeState st, int n_lanes, const int* __restrict__ init_active,
-                                   int n_active, int start_id) {
+                                   int n_active, int start_id, int n_groups, int group_stride) {
     int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i < n_lanes) {
         int a = init_active ? init_active[i] : 1;
@@ -248,25 +289,29 @@ __global__ void decode_init_kernel(DecodeState st, int n_lanes, const int* __res
         st.finish_step[i] = a ? st.max_tokens : 0;
         if (a) st.out[(size_t)st.out_row[i] * st.out_stride] = start_id;
     }
-    if (i == 0) {
-        st.step[0] = 0;
-        st.n_active[0] = n_active;
-        st.ticket[0] = 0;
+    if (i == 0) st.n_active[0] = n_active;
+    if (i < n_groups) {
+        st.step[i * group_stride] = 0;
+        st.ticket[i * group_stride] = 0;
     }
 }
 
 Status launch_decode_init(const DecodeState& st, int n_lanes, const int* init_active, int n_active,
-                          int start_id, cudaStream_t s) {
-    decode_init_kernel<<<ceil_div(n_lanes, 256), 256, 0, s>>>(st, n_lanes, init_active, n_active, start_id);
+                          int start_id, int n_groups, int group_stride, cudaStream_t s) {
+    decode_init_kernel<<<ceil_div(std::max(n_lanes, n_groups), 256), 256, 0, s>>>(
+        st, n_lanes, init_active, n_active, start_id, n_groups, group_stride);
     MRMT3_CHECK_LAUNCH();
     return OkStatus();
 }
 
-__global__ void advance_only_kernel(DecodeState st) { st.step[0] += 1; }
+__global__ void advance_only_kernel(DecodeState st) {
+    pdl_wait();
+    pdl_launch_dependents();
+    st.step[0] += 1;
+}
 
 Status launch_advance_only(const DecodeState& st, cudaStream_t s) {
-    advance_only_kernel<<<1, 1, 0, s>>>(st);
-    MRMT3_CHECK_LAUNCH();
+    MRMT3_TRY(launch_pdl(advance_only_kernel, dim3(1), dim3(1), 0, s, st));
     return OkStatus();
 }
 

@@ -12,6 +12,12 @@ Status launch_cast_bf16(const float* src, bf16* dst, size_t n, cudaStream_t s);
 Status launch_pack_weight(const float* src, bf16* dst, int rows, int cols, int row_mul, int row_off,
                           cudaStream_t s);
 
+// same row mapping, fp32 destination (masters of the norm-folded decoder weights)
+Status launch_pack_weight_f32(const float* src, float* dst, int rows, int cols, int row_mul, int row_off,
+                              cudaStream_t s);
+// dst[n][k] = bf16(master[n][k] * g[k])
+Status launch_fold_norm(const float* master, const float* g, bf16* dst, int rows, int cols, cudaStream_t s);
+
 // T5LayerNorm (RMSNorm, fp32 statistics): y = w * x * rsqrt(mean(x^2) + eps), rows of 512.
 // active (optional): per-lane flag, row r belongs to lane r / rows_per_lane.
 Status launch_rmsnorm(const float* x, const float* w, float eps, bf16* out_bf16, float* out_f32,
@@ -45,12 +51,13 @@ struct DecodeState {
     int forced_stride;
     int eos_id, pad_id;
     int max_tokens;       // stop a lane after this many emitted tokens
+    TraceSlot trace;      // timeline trace slot of the kernel this state is passed to
 };
 
 // H[lane] = Emb[tok[lane]] + PE[step]     (prefix == nullptr)
 // H[lane] = prefix[lane][step] + PE[step] (V1 memory prefix, step < prefix_len)
 Status launch_decode_embed(const DecodeState& st, const float* emb, const float* pe,
-                           const float* prefix, int prefix_stride, float* H, int n_lanes,
+                           const float* prefix, int prefix_stride, float* H, bf16* Hb, int n_lanes,
                            cudaStream_t s);
 
 // greedy head: argmax over V logits (lowest index wins ties, as torch.argmax), EOS bookkeeping
@@ -62,7 +69,7 @@ Status launch_argmax_advance(const DecodeState& st, const float* logits, size_t 
 
 // start-of-segment state: tok = start_id, active = init_active (or 1), step = 0
 Status launch_decode_init(const DecodeState& st, int n_lanes, const int* init_active, int n_active,
-                          int start_id, cudaStream_t s);
+                          int start_id, int n_groups, int group_stride, cudaStream_t s);
 
 // prefix steps produce no token: just advance the position
 Status launch_advance_only(const DecodeState& st, cudaStream_t s);

@@ -9,7 +9,7 @@
 #include <cmath>
 #include <cstring>
 
-#include "gemm_mma.cuh"
+#include "gemm_skinny.cuh"
 
 using namespace mrmt3;
 
@@ -57,6 +57,9 @@ constexpr int kMaxLanes = 512;    // decode lanes per wave
 constexpr int kEncChunk = 256;    // encoder segments per pass (bounds the row workspace)
 constexpr int kNPos = 5000;       // FixedPositionalEmbedding max_length, reference models/t5.py:706
 constexpr int kPollEvery = 8;     // decode steps between early-exit polls
+constexpr int kMaxGroups = 16;    // lane groups decoding concurrently on their own streams
+constexpr int kGroupScalars = 16; // ints per group in the state header: [0] step, [2] ticket
+constexpr int kStateHeader = kMaxGroups * kGroupScalars;
 
 #define RUN(h, call)          \
     do {                      \
@@ -125,6 +128,12 @@ static Status alloc_stack(mrmt3_handle* h, StackW& st, int n_layers, bool decode
         MRMT3_TRY(arena_take(h, (size_t)kDModel * kInner * 2, (void**)&L.wo));
         MRMT3_TRY(arena_take(h, kDModel * 4, (void**)&L.ln_self));
         if (decoder) {
+            MRMT3_TRY(arena_take(h, (size_t)3 * kInner * kDModel * 2, (void**)&L.wqkv_f));
+            MRMT3_TRY(arena_take(h, (size_t)kInner * kDModel * 2, (void**)&L.cq_f));
+            MRMT3_TRY(arena_take(h, (size_t)2 * kDFF * kDModel * 2, (void**)&L.wi_f));
+            MRMT3_TRY(arena_take(h, (size_t)3 * kInner * kDModel * 4, (void**)&L.m_wqkv));
+            MRMT3_TRY(arena_take(h, (size_t)kInner * kDModel * 4, (void**)&L.m_cq));
+            MRMT3_TRY(arena_take(h, (size_t)2 * kDFF * kDModel * 4, (void**)&L.m_wi));
             MRMT3_TRY(arena_take(h, (size_t)kInner * kDModel * 2, (void**)&L.cq));
             MRMT3_TRY(arena_take(h, (size_t)kDModel * kInner * 2, (void**)&L.co));
             MRMT3_TRY(arena_take(h, kDModel * 4, (void**)&L.ln_cross));
@@ -151,8 +160,9 @@ Status handle_init(mrmt3_handle* h) {
     MRMT3_CUDA_TRY(cudaSetDevice(h->device));
     int n_mem = c.mem_variant ? c.n_mem_layers : 0;
     size_t per_enc = (size_t)(3 * kInner * kDModel + kDModel * kInner + 2 * kDFF * kDModel + kDModel * kDFF) * 2 + 3 * 4096;
-    size_t per_dec = per_enc + (size_t)(2 * kInner * kDModel) * 2 + 2 * 4096;
-    size_t total = (size_t)kDModel * kDModel * 2 * 2 + (size_t)kVocab * kDModel * (4 + 2) +
+    size_t per_dec = per_enc + (size_t)(2 * kInner * kDModel) * 2 + 2 * 4096 +
+                     (size_t)(3 * kInner * kDModel + kInner * kDModel + 2 * kDFF * kDModel) * (2 + 4) + 6 * 4096;
+    size_t total = (size_t)kDModel * kDModel * 2 * 2 + (size_t)kVocab * kDModel * (4 + 2 + 2 + 4) +
                    (size_t)c.n_dec_layers * 2 * kInner * kDModel * 2 +
                    per_enc * (c.n_enc_layers + n_mem) + per_dec * c.n_dec_layers +
                    (size_t)kNPos * kDModel * 4 + (1 << 20);
@@ -161,6 +171,8 @@ Status handle_init(mrmt3_handle* h) {
     MRMT3_TRY(arena_take(h, (size_t)kDModel * kDModel * 2, (void**)&h->proj));
     MRMT3_TRY(arena_take(h, (size_t)kVocab * kDModel * 4, (void**)&h->emb));
     MRMT3_TRY(arena_take(h, (size_t)kVocab * kDModel * 2, (void**)&h->lm_head));
+    MRMT3_TRY(arena_take(h, (size_t)kVocab * kDModel * 2, (void**)&h->lm_head_f));
+    MRMT3_TRY(arena_take(h, (size_t)kVocab * kDModel * 4, (void**)&h->m_lm_head));
     MRMT3_TRY(arena_take(h, (size_t)c.n_dec_layers * 2 * kInner * kDModel * 2, (void**)&h->cross_kv_w));
     MRMT3_TRY(alloc_stack(h, h->enc, c.n_enc_layers, false));
     MRMT3_TRY(alloc_stack(h, h->dec, c.n_dec_layers, true));
@@ -177,6 +189,7 @@ Status handle_init(mrmt3_handle* h) {
     MRMT3_CUDA_TRY(cudaEventCreateWithFlags(&h->poll_ev[1], cudaEventDisableTiming));
     const char* ng = getenv("MRMT3_NO_GRAPH");
     h->use_graphs = !(ng && ng[0] == '1');
+    if (const char* gl = getenv("MRMT3_GROUP_LANES")) h->group_lanes = atoi(gl);
     return OkStatus();
 }
 
@@ -184,6 +197,16 @@ static void destroy_graphs(mrmt3_handle* h) {
     for (auto& kv : h->graphs)
         if (kv.second.exec) cudaGraphExecDestroy(kv.second.exec);
     h->graphs.clear();
+}
+
+Status trace_enable(mrmt3_handle* h, bool on) {
+    destroy_graphs(h);
+    h->trace_on = on;
+    if (on) {
+        MRMT3_TRY(h->trace_buf.reserve(256 * 16));
+        MRMT3_CUDA_TRY(cudaMemset(h->trace_buf.p, 0, 256 * 16));
+    }
+    return OkStatus();
 }
 
 // buffers whose address is baked into captured decode-step graphs
@@ -205,13 +228,19 @@ void handle_destroy(mrmt3_handle* h) {
     h->d_h32.release(); h->d_n_bf16.release(); h->d_qkv.release(); h->d_ctx.release();
     h->d_qc.release(); h->d_ff.release(); h->d_logits.release(); h->d_state.release();
     h->kv_pool.release(); h->block_table.release(); h->cross_cache.release(); h->lane_tab.release();
+    h->attn_scratch.release(); h->attn_tickets.release();
     if (h->h_pinned) cudaFreeHost(h->h_pinned);
     if (h->poll_ev[0]) cudaEventDestroy(h->poll_ev[0]);
     if (h->poll_ev[1]) cudaEventDestroy(h->poll_ev[1]);
+    for (int g = 0; g < 16; ++g) {
+        if (h->gstream[g]) cudaStreamDestroy(h->gstream[g]);
+        if (h->gdone[g]) cudaEventDestroy(h->gdone[g]);
+    }
+    if (h->gfork) cudaEventDestroy(h->gfork);
 }
 
 static Status pack(mrmt3_handle* h, const float* src, int rows, int cols, int want_rows,
-                   int want_cols, bf16* dst, int row_mul, int row_off) {
+                   int want_cols, bf16* dst, int row_mul, int row_off, float* master = nullptr) {
     if (rows != want_rows || cols != want_cols) {
         char b[160];
         snprintf(b, sizeof(b), "shape mismatch: got (%d,%d), expected (%d,%d)", rows, cols, want_rows, want_cols);
@@ -221,6 +250,7 @@ static Status pack(mrmt3_handle* h, const float* src, int rows, int cols, int wa
     MRMT3_TRY(h->stage.reserve(bytes));
     MRMT3_CUDA_TRY(cudaMemcpy(h->stage.p, src, bytes, cudaMemcpyDefault));
     MRMT3_TRY(launch_pack_weight(h->stage.as<float>(), dst, rows, cols, row_mul, row_off, 0));
+    if (master) MRMT3_TRY(launch_pack_weight_f32(h->stage.as<float>(), master, rows, cols, row_mul, row_off, 0));
     MRMT3_CUDA_TRY(cudaStreamSynchronize(0));
     return OkStatus();
 }
@@ -238,7 +268,7 @@ Status set_weight(mrmt3_handle* h, const std::string& name, const float* data, i
     bool known = true;
     if (name == "proj.weight") st = pack(h, data, rows, cols, d, d, h->proj, 1, 0);
     else if (name == "decoder_embed_tokens.weight") st = copy_f32(data, rows, cols, kVocab * d, h->emb);
-    else if (name == "lm_head.weight") st = pack(h, data, rows, cols, kVocab, d, h->lm_head, 1, 0);
+    else if (name == "lm_head.weight") st = pack(h, data, rows, cols, kVocab, d, h->lm_head, 1, 0, h->m_lm_head);
     else if (name == "segmem_proj.weight") {
         if (!h->segmem_proj) return Error(3, "segmem_proj.weight given to a model without a memory variant");
         st = pack(h, data, rows, cols, d, d, h->segmem_proj, 1, 0);
@@ -268,18 +298,18 @@ Status set_weight(mrmt3_handle* h, const std::string& name, const float* data, i
             std::string sub = rest.substr(consumed);
             const int ff_idx = sk.dec ? 2 : 1;
             known = true;
-            if (li == 0 && sub == "SelfAttention.q.weight") st = pack(h, data, rows, cols, in, d, L.wqkv, 1, 0);
-            else if (li == 0 && sub == "SelfAttention.k.weight") st = pack(h, data, rows, cols, in, d, L.wqkv, 1, in);
-            else if (li == 0 && sub == "SelfAttention.v.weight") st = pack(h, data, rows, cols, in, d, L.wqkv, 1, 2 * in);
+            if (li == 0 && sub == "SelfAttention.q.weight") st = pack(h, data, rows, cols, in, d, L.wqkv, 1, 0, L.m_wqkv);
+            else if (li == 0 && sub == "SelfAttention.k.weight") st = pack(h, data, rows, cols, in, d, L.wqkv, 1, in, L.m_wqkv);
+            else if (li == 0 && sub == "SelfAttention.v.weight") st = pack(h, data, rows, cols, in, d, L.wqkv, 1, 2 * in, L.m_wqkv);
             else if (li == 0 && sub == "SelfAttention.o.weight") st = pack(h, data, rows, cols, d, in, L.wo, 1, 0);
             else if (li == 0 && sub == "layer_norm.weight") st = copy_f32(data, rows, cols, d, L.ln_self);
-            else if (sk.dec && li == 1 && sub == "EncDecAttention.q.weight") st = pack(h, data, rows, cols, in, d, L.cq, 1, 0);
+            else if (sk.dec && li == 1 && sub == "EncDecAttention.q.weight") st = pack(h, data, rows, cols, in, d, L.cq, 1, 0, L.m_cq);
             else if (sk.dec && li == 1 && sub == "EncDecAttention.k.weight") st = pack(h, data, rows, cols, in, d, h->cross_kv_w, 1, bi * 2 * in);
             else if (sk.dec && li == 1 && sub == "EncDecAttention.v.weight") st = pack(h, data, rows, cols, in, d, h->cross_kv_w, 1, bi * 2 * in + in);
             else if (sk.dec && li == 1 && sub == "EncDecAttention.o.weight") st = pack(h, data, rows, cols, d, in, L.co, 1, 0);
             else if (sk.dec && li == 1 && sub == "layer_norm.weight") st = copy_f32(data, rows, cols, d, L.ln_cross);
-            else if (li == ff_idx && sub == "DenseReluDense.wi_0.weight") st = pack(h, data, rows, cols, kDFF, d, L.wi, 2, 0);
-            else if (li == ff_idx && sub == "DenseReluDense.wi_1.weight") st = pack(h, data, rows, cols, kDFF, d, L.wi, 2, 1);
+            else if (li == ff_idx && sub == "DenseReluDense.wi_0.weight") st = pack(h, data, rows, cols, kDFF, d, L.wi, 2, 0, L.m_wi);
+            else if (li == ff_idx && sub == "DenseReluDense.wi_1.weight") st = pack(h, data, rows, cols, kDFF, d, L.wi, 2, 1, L.m_wi);
             else if (li == ff_idx && sub == "DenseReluDense.wo.weight") st = pack(h, data, rows, cols, d, kDFF, L.wff, 1, 0);
             else if (li == ff_idx && sub == "layer_norm.weight") st = copy_f32(data, rows, cols, d, L.ln_ff);
             else known = false;
@@ -334,6 +364,14 @@ Status commit_weights(mrmt3_handle* h) {
             pe[(size_t)p * kDModel + 256 + j] = (float)std::cos((double)ang);
         }
     MRMT3_CUDA_TRY(cudaMemcpy(h->pe, pe.data(), pe.size() * 4, cudaMemcpyHostToDevice));
+    // norm-folded decoder weights for the fused-RMSNorm decode GEMMs (gemm_skinny.cuh)
+    for (auto& L : h->dec.layers) {
+        MRMT3_TRY(launch_fold_norm(L.m_wqkv, L.ln_self, L.wqkv_f, 3 * kInner, kDModel, 0));
+        MRMT3_TRY(launch_fold_norm(L.m_cq, L.ln_cross, L.cq_f, kInner, kDModel, 0));
+        MRMT3_TRY(launch_fold_norm(L.m_wi, L.ln_ff, L.wi_f, 2 * kDFF, kDModel, 0));
+    }
+    MRMT3_TRY(launch_fold_norm(h->m_lm_head, h->dec.final_ln, h->lm_head_f, kVocab, kDModel, 0));
+    MRMT3_CUDA_TRY(cudaStreamSynchronize(0));
     h->committed = true;
     return OkStatus();
 }
@@ -468,7 +506,7 @@ static LaneArrays lane_arrays(const mrmt3_handle* h) {
     a.step = s;
     a.n_active = s + 1;
     a.ticket = s + 2;
-    a.tok = s + 16;
+    a.tok = s + kStateHeader;
     a.active = a.tok + h->lane_cap;
     a.finish_step = a.active + h->lane_cap;
     int* t = h->lane_tab.as<int>();
@@ -497,11 +535,12 @@ static Status ensure_decode_capacity(mrmt3_handle* h, int n_lanes, int tk, int m
     MRMT3_TRY(h->d_qc.reserve(c * kInner * 2));
     MRMT3_TRY(h->d_ff.reserve(c * kDFF * 2));
     MRMT3_TRY(h->d_logits.reserve(c * kVocab * 4));
-    MRMT3_TRY(h->d_state.reserve((16 + 3 * c) * sizeof(int)));
+    MRMT3_TRY(h->d_state.reserve((kStateHeader + 3 * c) * sizeof(int)));
     MRMT3_TRY(h->lane_tab.reserve(4 * c * sizeof(int)));
     MRMT3_TRY(h->kv_pool.reserve(c * pgc * page_elems(h) * sizeof(bf16)));
     MRMT3_TRY(h->cross_cache.reserve(c * h->cfg.n_dec_layers * 2 * kHeads * (size_t)tkc * kDKV * sizeof(bf16)));
     MRMT3_TRY(h->block_table.reserve(c * pgc * sizeof(int)));
+
     MRMT3_CUDA_TRY(cudaMemset(h->d_h32.p, 0, h->d_h32.cap));
     MRMT3_CUDA_TRY(cudaMemset(h->d_state.p, 0, h->d_state.cap));
     MRMT3_CUDA_TRY(cudaMemset(h->lane_tab.p, 0, h->lane_tab.cap));
@@ -516,6 +555,8 @@ static Status ensure_decode_capacity(mrmt3_handle* h, int n_lanes, int tk, int m
 }
 
 struct StepPlan {
+    int self_chunks;       // KV pages the self-attention grid must cover at this step's position
+    int lane0;             // first lane of this group (all per-lane buffers are offset by it)
     int n_lanes, tk;
     DecodeState st;
     const float* prefix;   // V1 memory prefix rows (lanes, prefix_len, d) fp32 or nullptr
@@ -527,19 +568,25 @@ struct StepPlan {
 static Status enqueue_step(mrmt3_handle* h, const StepPlan& pl, int kind, cudaStream_t s) {
     const int n = pl.n_lanes;
     const float eps = h->cfg.ln_eps;
-    float* H = h->d_h32.as<float>();
-    bf16* nb = h->d_n_bf16.as<bf16>();
-    bf16* qkv = h->d_qkv.as<bf16>();
-    bf16* ctx = h->d_ctx.as<bf16>();
-    bf16* qc = h->d_qc.as<bf16>();
-    bf16* ff = h->d_ff.as<bf16>();
-    const ARowMap id{nullptr, 1};
-    RUNC(h, MRMT3_PROF_EMBED, s, launch_decode_embed(pl.st, h->emb, h->pe, pl.prefix, pl.st.prefix_len * kDModel, H, n, s));
+    const size_t l0 = (size_t)pl.lane0;
+    float* H = h->d_h32.as<float>() + l0 * kDModel;      // fp32 residual stream
+    bf16* Hb = h->d_n_bf16.as<bf16>() + l0 * kDModel;    // its bf16 copy (input of the NORM GEMMs)
+    bf16* qkv = h->d_qkv.as<bf16>() + l0 * 3 * kInner;
+    bf16* ctx = h->d_ctx.as<bf16>() + l0 * kInner;
+    bf16* qc = h->d_qc.as<bf16>() + l0 * kInner;
+    bf16* ff = h->d_ff.as<bf16>() + l0 * kDFF;
+    const size_t cross_lane = (size_t)h->cfg.n_dec_layers * 2 * kHeads * h->tk_cap * kDKV;
+    int tslot = 0;
+    auto next_trace = [&]() { return TraceSlot{h->trace_on ? h->trace_buf.as<unsigned long long>() : nullptr, tslot++}; };
+    DecodeState st_embed = pl.st;
+    st_embed.trace = next_trace();
+    RUNC(h, MRMT3_PROF_EMBED, s, launch_decode_embed(st_embed, h->emb, h->pe,
+                                                    pl.prefix ? pl.prefix + l0 * pl.st.prefix_len * kDModel : nullptr,
+                                                    pl.st.prefix_len * kDModel, H, Hb, n, s));
     for (int li = 0; li < h->cfg.n_dec_layers; ++li) {
         const LayerW& L = h->dec.layers[li];
-        RUNC(h, MRMT3_PROF_RMSNORM, s, launch_rmsnorm(H, L.ln_self, eps, nb, nullptr, n, pl.st.active, 1, s));
-        RUNC(h, MRMT3_PROF_GEMM_QKV, s, launch_gemm_mma(nb, kDModel, id, L.wqkv, kDModel, n, 3 * kInner, kDModel,
-                               EpiStoreBf16{qkv, 3 * kInner}, s));
+        RUNC(h, MRMT3_PROF_GEMM_QKV, s, (launch_gemm_skinny<64, kDModel, true>(
+                 Hb, kDModel, L.wqkv_f, kDModel, n, 3 * kInner, eps, EpiStoreBf16{qkv, 3 * kInner}, s, next_trace())));
         AttnDecodeParams ap{};
         ap.q = qkv;
         ap.q_stride = 3 * kInner;
@@ -550,55 +597,62 @@ static Status enqueue_step(mrmt3_handle* h, const StepPlan& pl, int kind, cudaSt
         ap.n_layers = h->cfg.n_dec_layers;
         ap.step_ptr = pl.st.step;
         ap.pos_offset = 0;
-        ap.block_table = h->block_table.as<int>();
+        ap.block_table = h->block_table.as<int>() + l0 * h->page_cap;
         ap.max_pages = h->page_cap;
         ap.page_stride = page_elems(h);
         ap.active = pl.st.active;
+        ap.trace = next_trace();
         RUNC(h, MRMT3_PROF_ATTN_SELF, s, launch_attn_decode(ap, n, true, s));
-        RUNC(h, MRMT3_PROF_GEMM_O, s, launch_gemm_mma(ctx, kInner, id, L.wo, kInner, n, kDModel, kInner, EpiResidual{H, kDModel}, s));
+        RUNC(h, MRMT3_PROF_GEMM_O, s, (launch_gemm_skinny<32, kInner, false>(
+                 ctx, kInner, L.wo, kInner, n, kDModel, eps, EpiResidualBoth{H, Hb, kDModel}, s, next_trace())));
 
-        RUNC(h, MRMT3_PROF_RMSNORM, s, launch_rmsnorm(H, L.ln_cross, eps, nb, nullptr, n, pl.st.active, 1, s));
-        RUNC(h, MRMT3_PROF_GEMM_CQ, s, launch_gemm_mma(nb, kDModel, id, L.cq, kDModel, n, kInner, kDModel, EpiStoreBf16{qc, kInner}, s));
+        RUNC(h, MRMT3_PROF_GEMM_CQ, s, (launch_gemm_skinny<32, kDModel, true>(
+                 Hb, kDModel, L.cq_f, kDModel, n, kInner, eps, EpiStoreBf16{qc, kInner}, s, next_trace())));
         AttnDecodeParams cp{};
         cp.q = qc;
         cp.q_stride = kInner;
         cp.out = ctx;
         cp.out_stride = kInner;
-        cp.kv_pool = h->cross_cache.as<bf16>();
+        cp.kv_pool = h->cross_cache.as<bf16>() + l0 * cross_lane;
         cp.layer = li;
         cp.n_layers = h->cfg.n_dec_layers;
         cp.tk_cap = h->tk_cap;
         cp.n_keys = pl.tk;
         cp.active = pl.st.active;
+        cp.trace = next_trace();
         RUNC(h, MRMT3_PROF_ATTN_CROSS, s, launch_attn_decode(cp, n, false, s));
-        RUNC(h, MRMT3_PROF_GEMM_CO, s, launch_gemm_mma(ctx, kInner, id, L.co, kInner, n, kDModel, kInner, EpiResidual{H, kDModel}, s));
+        RUNC(h, MRMT3_PROF_GEMM_CO, s, (launch_gemm_skinny<32, kInner, false>(
+                 ctx, kInner, L.co, kInner, n, kDModel, eps, EpiResidualBoth{H, Hb, kDModel}, s, next_trace())));
 
-        RUNC(h, MRMT3_PROF_RMSNORM, s, launch_rmsnorm(H, L.ln_ff, eps, nb, nullptr, n, pl.st.active, 1, s));
-        RUNC(h, MRMT3_PROF_GEMM_WI, s, launch_gemm_mma(nb, kDModel, id, L.wi, kDModel, n, 2 * kDFF, kDModel, EpiGatedGelu{ff, kDFF}, s));
-        RUNC(h, MRMT3_PROF_GEMM_WFF, s, launch_gemm_mma(ff, kDFF, id, L.wff, kDFF, n, kDModel, kDFF, EpiResidual{H, kDModel}, s));
+        RUNC(h, MRMT3_PROF_GEMM_WI, s, (launch_gemm_skinny<64, kDModel, true>(
+                 Hb, kDModel, L.wi_f, kDModel, n, 2 * kDFF, eps, EpiGatedGelu{ff, kDFF}, s, next_trace())));
+        RUNC(h, MRMT3_PROF_GEMM_WFF, s, (launch_gemm_skinny<32, kDFF, false>(
+                 ff, kDFF, L.wff, kDFF, n, kDModel, eps, EpiResidualBoth{H, Hb, kDModel}, s, next_trace())));
     }
     if (kind == 1) {
         RUNC(h, MRMT3_PROF_ARGMAX, s, launch_advance_only(pl.st, s));
         return OkStatus();
     }
-    RUNC(h, MRMT3_PROF_RMSNORM, s, launch_rmsnorm(H, h->dec.final_ln, eps, nb, nullptr, n, pl.st.active, 1, s));
+    // final norm is folded into lm_head_f
     if (pl.ext_logits) {
         const size_t lane_stride = (size_t)pl.st.max_tokens * kVocab;
-        RUNC(h, MRMT3_PROF_LM_HEAD, s, launch_gemm_mma(nb, kDModel, id, h->lm_head, kDModel, n, kVocab, kDModel,
-                               EpiStoreF32Step{pl.ext_logits, kVocab, lane_stride, pl.st.step,
-                                               pl.st.prefix_len, pl.st.out_row}, s));
+        RUNC(h, MRMT3_PROF_LM_HEAD, s, (launch_gemm_skinny<64, kDModel, true>(
+                 Hb, kDModel, h->lm_head_f, kDModel, n, kVocab, eps,
+                 EpiStoreF32Step{pl.ext_logits, kVocab, lane_stride, pl.st.step, pl.st.prefix_len, pl.st.out_row}, s, next_trace())));
         RUNC(h, MRMT3_PROF_ARGMAX, s, launch_argmax_advance(pl.st, pl.ext_logits, lane_stride, kVocab, n, kVocab, s));
     } else {
-        float* lg = h->d_logits.as<float>();
-        RUNC(h, MRMT3_PROF_LM_HEAD, s, launch_gemm_mma(nb, kDModel, id, h->lm_head, kDModel, n, kVocab, kDModel,
-                               EpiStoreF32{lg, kVocab}, s));
-        RUNC(h, MRMT3_PROF_ARGMAX, s, launch_argmax_advance(pl.st, lg, kVocab, 0, n, kVocab, s));
+        float* lg = h->d_logits.as<float>() + l0 * kVocab;
+        RUNC(h, MRMT3_PROF_LM_HEAD, s, (launch_gemm_skinny<64, kDModel, true>(
+                 Hb, kDModel, h->lm_head_f, kDModel, n, kVocab, eps, EpiStoreF32{lg, kVocab}, s, next_trace())));
+        DecodeState st_arg = pl.st;
+        st_arg.trace = next_trace();
+        RUNC(h, MRMT3_PROF_ARGMAX, s, launch_argmax_advance(st_arg, lg, kVocab, 0, n, kVocab, s));
     }
     return OkStatus();
 }
 
 static Status get_graph(mrmt3_handle* h, const StepPlan& pl, int kind, StepGraph** out) {
-    StepGraphKey key{pl.n_lanes, pl.tk, pl.st.max_tokens, pl.st.prefix_len, kind};
+    StepGraphKey key{pl.lane0, pl.n_lanes, pl.tk, pl.st.max_tokens, pl.st.prefix_len, kind, pl.self_chunks};
     auto it = h->graphs.find(key);
     if (it != h->graphs.end()) {
         *out = &it->second;
@@ -627,40 +681,87 @@ static Status get_graph(mrmt3_handle* h, const StepPlan& pl, int kind, StepGraph
     return OkStatus();
 }
 
+// view of the decode state for lanes [lane0, lane0 + n): per-lane arrays are offset, the step and
+// ticket scalars are the group's own, n_active is shared by all groups
+static DecodeState group_state(const DecodeState& st, int lane0, int group) {
+    DecodeState g = st;
+    g.step = st.step + group * kGroupScalars;
+    g.ticket = st.ticket + group * kGroupScalars;
+    g.tok = st.tok + lane0;
+    g.active = st.active + lane0;
+    g.finish_step = st.finish_step + lane0;
+    g.out_row = st.out_row + lane0;
+    if (st.forced) g.forced = st.forced + (size_t)lane0 * st.forced_stride;
+    return g;
+}
+
 // Greedy loop over lanes whose state was set by launch_decode_init.  Runs n_prefix prefix steps,
 // then up to max_tokens token steps, stopping early once every lane has emitted EOS (polled
 // every kPollEvery steps without draining the queue).
+//
+// The lanes are split into groups that run the same loop independently, each replaying its own
+// step graph on its own stream: the chain of one step is ~90 dependent kernels, half of them
+// small latency-bound projections, so a single chain leaves HBM idle most of the time; several
+// chains in flight let one group's attention (HBM-bound) overlap the others' projections.
 static Status run_decode(mrmt3_handle* h, StepPlan pl, int n_prefix, bool debug_mode, cudaStream_t s) {
     const bool graphs = h->use_graphs && !debug_mode && !h->prof_on;
-    StepGraph *g_tok = nullptr, *g_pre = nullptr;
-    if (graphs) {
-        MRMT3_TRY(get_graph(h, pl, 0, &g_tok));
-        if (n_prefix) MRMT3_TRY(get_graph(h, pl, 1, &g_pre));
+    int G = 1;
+    if (!debug_mode && !h->prof_on && h->group_lanes > 0)
+        G = std::min(kMaxGroups, ceil_div(pl.n_lanes, h->group_lanes));
+    const int per = ceil_div(pl.n_lanes, G);
+    G = ceil_div(pl.n_lanes, per);
+    std::vector<StepPlan> gp(G);
+    for (int g = 0; g < G; ++g) {
+        gp[g] = pl;
+        gp[g].lane0 = pl.lane0 + g * per;
+        gp[g].n_lanes = std::min(per, pl.n_lanes - g * per);
+        gp[g].st = group_state(pl.st, g * per, g);
     }
-    for (int i = 0; i < n_prefix; ++i) {
-        if (graphs) {
-            MRMT3_CUDA_TRY(cudaGraphLaunch(g_pre->exec, s));
-            h->launches += g_pre->n_kernels;
-        } else {
-            MRMT3_TRY(enqueue_step(h, pl, 1, s));
+    std::vector<cudaStream_t> gs(G, s);
+    if (G > 1 && !h->group_serial) {
+        if (!h->gfork) MRMT3_CUDA_TRY(cudaEventCreateWithFlags(&h->gfork, cudaEventDisableTiming));
+        MRMT3_CUDA_TRY(cudaEventRecord(h->gfork, s));
+        for (int g = 0; g < G; ++g) {
+            if (!h->gstream[g]) {
+                MRMT3_CUDA_TRY(cudaStreamCreateWithFlags(&h->gstream[g], cudaStreamNonBlocking));
+                MRMT3_CUDA_TRY(cudaEventCreateWithFlags(&h->gdone[g], cudaEventDisableTiming));
+            }
+            gs[g] = h->gstream[g];
+            MRMT3_CUDA_TRY(cudaStreamWaitEvent(gs[g], h->gfork, 0));
         }
     }
+    // the self-attention grid covers the KV pages in use at the step's position, so the step
+    // graph exists in one variant per page count (captured on first use, then replayed)
+    auto step_all = [&](int kind, int position) -> Status {
+        const int chunks = 1;  // (graph variants per KV page count were only needed by the split-key kernel)
+        (void)position;
+        for (int g = 0; g < G; ++g) {
+            gp[g].self_chunks = chunks;
+            if (graphs) {
+                StepGraph* sg = nullptr;
+                MRMT3_TRY(get_graph(h, gp[g], kind, &sg));
+                MRMT3_CUDA_TRY(cudaGraphLaunch(sg->exec, gs[g]));
+                h->launches += sg->n_kernels;
+            } else {
+                MRMT3_TRY(enqueue_step(h, gp[g], kind, gs[g]));
+            }
+        }
+        return OkStatus();
+    };
+    for (int i = 0; i < n_prefix; ++i) MRMT3_TRY(step_all(1, i));
     int polls = 0;
     bool pending[2] = {false, false};
     bool all_done = false;
     const bool may_exit_early = pl.st.forced == nullptr;
     for (int t = 0; t < pl.st.max_tokens && !all_done; ++t) {
-        if (graphs) {
-            MRMT3_CUDA_TRY(cudaGraphLaunch(g_tok->exec, s));
-            h->launches += g_tok->n_kernels;
-        } else {
-            MRMT3_TRY(enqueue_step(h, pl, 0, s));
-        }
+        MRMT3_TRY(step_all(0, n_prefix + t));
         if (may_exit_early && (t + 1) % kPollEvery == 0 && t + 1 < pl.st.max_tokens) {
+            // n_active is decremented by every group; a read through any stream can only be
+            // stale-high, which delays the exit but never cuts a lane short
             const int slot = polls & 1;
             MRMT3_CUDA_TRY(cudaMemcpyAsync(&h->h_pinned[slot], pl.st.n_active, sizeof(int),
-                                           cudaMemcpyDeviceToHost, s));
-            MRMT3_CUDA_TRY(cudaEventRecord(h->poll_ev[slot], s));
+                                           cudaMemcpyDeviceToHost, gs[G - 1]));
+            MRMT3_CUDA_TRY(cudaEventRecord(h->poll_ev[slot], gs[G - 1]));
             pending[slot] = true;
             const int prev = slot ^ 1;
             if (pending[prev]) {  // look at the poll issued kPollEvery steps ago
@@ -669,6 +770,12 @@ static Status run_decode(mrmt3_handle* h, StepPlan pl, int n_prefix, bool debug_
                 if (h->h_pinned[prev] == 0) all_done = true;
             }
             ++polls;
+        }
+    }
+    if (G > 1 && !h->group_serial) {
+        for (int g = 0; g < G; ++g) {
+            MRMT3_CUDA_TRY(cudaEventRecord(h->gdone[g], gs[g]));
+            MRMT3_CUDA_TRY(cudaStreamWaitEvent(s, h->gdone[g], 0));
         }
     }
     MRMT3_CUDA_TRY(cudaStreamSynchronize(s));
@@ -756,7 +863,7 @@ Status generate_base(mrmt3_handle* h, const float* mel_f32, const bf16* mel_bf16
         pl.st = make_state(h, tok, stride, max_length, 0, forced);
         pl.prefix = nullptr;
         pl.ext_logits = logits_out;
-        RUN(h, launch_decode_init(pl.st, n, nullptr, n, h->cfg.start_id, s));
+        RUN(h, launch_decode_init(pl.st, n, nullptr, n, h->cfg.start_id, kMaxGroups, kGroupScalars, s));
         MRMT3_TRY(run_decode(h, pl, 0, forced != nullptr || logits_out != nullptr, s));
         MRMT3_CUDA_TRY(cudaMemcpyAsync(h->h_pinned + 8, a.finish_step, n * sizeof(int), cudaMemcpyDeviceToHost, s));
         MRMT3_CUDA_TRY(cudaStreamSynchronize(s));
@@ -860,7 +967,7 @@ Status generate_segmem(mrmt3_handle* h, const float* mel_f32, const bf16* mel_bf
             pl.st = make_state(h, tok, stride, max_length, prefix, nullptr);
             pl.prefix = v1 ? h->mem_f32.as<float>() : nullptr;
             pl.ext_logits = logits_out;
-            RUN(h, launch_decode_init(pl.st, n, a.init_active, n_active, h->cfg.start_id, s));
+            RUN(h, launch_decode_init(pl.st, n, a.init_active, n_active, h->cfg.start_id, kMaxGroups, kGroupScalars, s));
             MRMT3_TRY(run_decode(h, pl, prefix, logits_out != nullptr, s));
         }
     }

@@ -34,6 +34,10 @@ struct LayerW {
     bf16* wi = nullptr;       // (2*d_ff, d)   rows interleaved wi_0[j], wi_1[j]
     bf16* wff = nullptr;      // (d, d_ff)
     float* ln_ff = nullptr;
+    // decoder only: norm-folded copies for the fused-RMSNorm decode GEMMs (W * diag(ln)) and the
+    // fp32 masters they are folded from at commit time
+    bf16 *wqkv_f = nullptr, *cq_f = nullptr, *wi_f = nullptr;
+    float *m_wqkv = nullptr, *m_cq = nullptr, *m_wi = nullptr;
 };
 
 struct StackW {
@@ -50,13 +54,16 @@ struct RowWorkspace {
 };
 
 struct StepGraphKey {
-    int n_lanes, tk, max_tokens, prefix_len, kind;  // kind 0 = token step, 1 = prefix step
+    int lane0, n_lanes, tk, max_tokens, prefix_len, kind;  // kind 0 = token step, 1 = prefix step
+    int self_chunks;                                       // 128-key chunks the self-attention grid covers
     bool operator<(const StepGraphKey& o) const {
+        if (lane0 != o.lane0) return lane0 < o.lane0;
         if (n_lanes != o.n_lanes) return n_lanes < o.n_lanes;
         if (tk != o.tk) return tk < o.tk;
         if (max_tokens != o.max_tokens) return max_tokens < o.max_tokens;
         if (prefix_len != o.prefix_len) return prefix_len < o.prefix_len;
-        return kind < o.kind;
+        if (kind != o.kind) return kind < o.kind;
+        return self_chunks < o.self_chunks;
     }
 };
 
@@ -83,6 +90,8 @@ struct mrmt3_handle {
     mrmt3::bf16* proj = nullptr;         // (d, d)
     float* emb = nullptr;                // (V, d) fp32
     mrmt3::bf16* lm_head = nullptr;      // (V, d)
+    mrmt3::bf16* lm_head_f = nullptr;    // lm_head * diag(decoder.final_layer_norm)
+    float* m_lm_head = nullptr;
     mrmt3::bf16* segmem_proj = nullptr;  // (d, d)
     mrmt3::bf16* cross_kv_w = nullptr;   // (n_dec * 2 * inner, d): layer-major [k; v]
     mrmt3::StackW enc, dec, mem;
@@ -106,6 +115,8 @@ struct mrmt3_handle {
     mrmt3::DeviceBuffer d_h32, d_n_bf16, d_qkv, d_ctx, d_qc, d_ff, d_logits;
     mrmt3::DeviceBuffer d_state;         // ints: step, n_active, ticket, then per-lane arrays
     mrmt3::DeviceBuffer kv_pool, block_table, cross_cache;
+    mrmt3::DeviceBuffer attn_scratch, attn_tickets;  // split-key attention partials + tickets
+    int chunk_cap = 0;
     mrmt3::DeviceBuffer lane_tab;        // per-lane int tables (seg index, prev row, active)
     int* h_pinned = nullptr;             // pinned host ints for polling / finish steps
 
@@ -120,4 +131,13 @@ struct mrmt3_handle {
     double prof_ms[MRMT3_PROF_NCAT] = {0};
     int64_t prof_n[MRMT3_PROF_NCAT] = {0};
     cudaEvent_t poll_ev[2] = {nullptr, nullptr};
+    // lane groups: independent greedy loops on their own streams so that one group's
+    // latency-bound projections overlap another group's HBM-bound attention
+    int group_lanes = 32;
+    bool group_serial = false;
+    mrmt3::DeviceBuffer trace_buf;       // 2 x u64 per decode-step kernel slot (mrmt3_trace_*)
+    bool trace_on = false;           // debugging: run the groups one after another on one stream
+    cudaStream_t gstream[16] = {nullptr};
+    cudaEvent_t gdone[16] = {nullptr};
+    cudaEvent_t gfork = nullptr;
 };

@@ -187,6 +187,21 @@ def test_graph_and_eager_decode_agree(pkg, feats):
     np.testing.assert_array_equal(a[:, :n].cpu().numpy(), b[:, :n].cpu().numpy())
 
 
+def test_lane_groups_do_not_change_tokens(pkg):
+    """Lane groups decode concurrently on their own streams; rows are independent, so any
+    grouping must give the same tokens as one group."""
+    model, _ = _model(pkg, 1239, eos_scale=5.0)
+    eng = model.engine()
+    x = syn.synthetic_features(5, 40).cuda()
+    eng.set_option("group_lanes", 0)
+    one = eng.generate(x, max_length=96)
+    for gl in (8, 16, 3):
+        eng.set_option("group_lanes", gl)
+        many = eng.generate(x, max_length=96)
+        assert torch.equal(one, many), gl
+    eng.set_option("group_lanes", 32)
+
+
 # ---- MR-MT3 -------------------------------------------------------------------------------------
 def test_memory_block(pkg):
     model, sd = _model(pkg, 4322, kind="v2p", eos_scale=3.0)
@@ -238,7 +253,9 @@ def test_segmem_tracks_equal_per_track_calls(pkg):
     x = syn.synthetic_features(21, 9).cuda()
     counts = [4, 2, 3]
     eng = model.engine()
+    eng.set_option("group_lanes", 2)                        # 3 tracks -> 2 lane groups
     batched = eng.generate_segmem(x, counts, max_length=48).cpu().numpy()
+    eng.set_option("group_lanes", 32)
     off = 0
     for c in counts:
         single = eng.generate_segmem(x[off:off + c], [c], max_length=48).cpu().numpy()
