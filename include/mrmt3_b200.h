@@ -99,6 +99,12 @@ int mrmt3_profile_read(mrmt3_handle* h, double* ms_out, int64_t* launches_out, i
 int mrmt3_trace_enable(mrmt3_handle* h, int on);
 int mrmt3_trace_read(mrmt3_handle* h, uint64_t* out, int max_slots);
 
+/* Test hook: C (M,N) fp32 = A (M,K) bf16 * W (N,K)^T bf16 through one of the library's GEMM
+ * kernels: which = 0 mma.sync pipeline, 1 = TMA + tcgen05/TMEM, 2 = decode-step single-shot
+ * kernel (K in {384, 512, 1024}).  Used by tests/test_kernels_gpu.py only. */
+int mrmt3_test_gemm(mrmt3_handle* h, const void* a_bf16, const void* w_bf16, int M, int N, int K,
+                    float* c_f32, int which, void* stream);
+
 /* ---- weights -------------------------------------------------------------------------- */
 /* Replaces: model.load_state_dict(sd) (test.py:106-110, train.py:80-83).  `name` is the
  * reference's state-dict key (weight contract); `data` is fp32 row-major

@@ -37,6 +37,7 @@ _PROTOTYPES = {
     "mrmt3_last_error": (ctypes.c_char_p, [_c_void_p]),
     "mrmt3_launch_count": (_c_i64, [_c_void_p]),
     "mrmt3_set_option": (_c_int, [_c_void_p, ctypes.c_char_p, _c_int]),
+    "mrmt3_test_gemm": (_c_int, [_c_void_p, _c_void_p, _c_void_p, _c_int, _c_int, _c_int, _c_void_p, _c_int, _c_void_p]),
     "mrmt3_trace_enable": (_c_int, [_c_void_p, _c_int]),
     "mrmt3_trace_read": (_c_int, [_c_void_p, _c_void_p, _c_int]),
     "mrmt3_profile_enable": (_c_int, [_c_void_p, _c_int]),
@@ -156,6 +157,17 @@ class Engine:
 
     def set_option(self, key, value):
         self._check(self._lib.mrmt3_set_option(self._h, key.encode(), int(value)))
+
+    def test_gemm(self, a, w, which):
+        """C = a @ w.T through GEMM kernel `which` (0 mma.sync, 1 tcgen05, 2 decode single-shot)."""
+        a = a.to(self.device, torch.bfloat16).contiguous()
+        w = w.to(self.device, torch.bfloat16).contiguous()
+        M, K = a.shape
+        N = w.shape[0]
+        c = torch.empty((M, N), dtype=torch.float32, device=self.device)
+        with torch.cuda.device(self.device):
+            self._check(self._lib.mrmt3_test_gemm(self._h, _ptr(a), _ptr(w), M, N, K, _ptr(c), which, _stream()))
+        return c
 
     def trace_enable(self, on=True):
         self._check(self._lib.mrmt3_trace_enable(self._h, 1 if on else 0))

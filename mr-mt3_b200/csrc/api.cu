@@ -26,6 +26,7 @@ Status api_transcribe_host(mrmt3_handle* h, const float* audio_host, long long n
                            int flags, int max_length, long long* out_ids_host, int* steps_host, cudaStream_t s);
 Status profile_collect(mrmt3_handle* h);
 Status trace_enable(mrmt3_handle* h, bool on);
+Status test_gemm(mrmt3_handle* h, const bf16* A, const bf16* W, int M, int N, int K, float* C, int which, cudaStream_t s);
 }  // namespace mrmt3
 
 using namespace mrmt3;
@@ -130,6 +131,13 @@ int mrmt3_trace_read(mrmt3_handle* h, uint64_t* out, int max_slots) {
     int n = std::min(max_slots, 256);
     if (cudaMemcpy(out, h->trace_buf.p, (size_t)n * 16, cudaMemcpyDeviceToHost) != cudaSuccess) return 0;
     return n;
+    END_GUARD(h)
+}
+
+int mrmt3_test_gemm(mrmt3_handle* h, const void* a_bf16, const void* w_bf16, int M, int N, int K, float* c_f32,
+                    int which, void* stream) {
+    GUARD(h)
+    return finish(h, test_gemm(h, (const bf16*)a_bf16, (const bf16*)w_bf16, M, N, K, c_f32, which, (cudaStream_t)stream));
     END_GUARD(h)
 }
 

@@ -1,0 +1,291 @@
+// C[M,N] = A[M,K] * W[N,K]^T for the large-M GEMMs of the path (encoder, cross-K/V projection,
+// memory block, teacher-forced decoder): TMA-fed tcgen05.mma with the fp32 accumulator in TMEM.
+//
+//   * one 128 x BN output tile per CTA (BN = 128 or 64), BK = 64, 3-stage shared-memory ring
+//   * warp 0  : TMA producer  (cp.async.bulk.tensor.2d, 128-byte swizzle, mbarrier complete_tx)
+//   * warp 1  : allocates TMEM, issues tcgen05.mma.cta_group::1.kind::f16 (one elected lane),
+//               tcgen05.commit frees ring slots / publishes the accumulator
+//   * warps 2-5: epilogue -- tcgen05.ld (32 lanes x 32 columns per warp), the same epilogue
+//               functors as the mma.sync kernels (gemm_mma.cuh), direct global stores
+//   * two CTAs fit per SM (96 KB smem, 128 TMEM columns each), so one CTA's epilogue overlaps the
+//     other's main loop.
+//
+// Descriptor encodings follow the PTX ISA "tcgen05 matrix / instruction descriptor" tables (the
+// same fields CUTLASS's cute/arch/mma_sm100_desc.hpp names): K-major operands, SWIZZLE_128B,
+// 8-row groups 1024 B apart.
+#pragma once
+#include <cuda.h>
+
+#include <map>
+#include <tuple>
+
+#include "gemm_mma.cuh"
+
+namespace mrmt3 {
+
+constexpr int kTcBM = 128;
+constexpr int kTcBK = 64;
+constexpr int kTcStages = 3;
+constexpr int kTcThreads = 192;
+
+// ---- PTX wrappers ---------------------------------------------------------------------------
+__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;\n" ::"r"(bar), "r"(count));
+}
+__device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;\n" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
+    uint32_t done;
+    do {
+        asm volatile(
+            "{\n"
+            ".reg .pred p;\n"
+            "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n"
+            "selp.u32 %0, 1, 0, p;\n"
+            "}\n"
+            : "=r"(done)
+            : "r"(bar), "r"(parity)
+            : "memory");
+    } while (!done);
+}
+__device__ __forceinline__ void tma_load_2d(uint32_t smem_dst, const CUtensorMap* map, int x, int y, uint32_t bar) {
+    asm volatile(
+        "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3}], [%4];\n" ::"r"(
+            smem_dst),
+        "l"(map), "r"(x), "r"(y), "r"(bar)
+        : "memory");
+}
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;\n" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;\n" ::: "memory"); }
+__device__ __forceinline__ void tc_commit(uint32_t bar) {
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];\n" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void tc_mma_f16(uint32_t tmem_d, uint64_t desc_a, uint64_t desc_b, uint32_t idesc,
+                                           uint32_t accumulate) {
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "setp.ne.b32 p, %4, 0;\n"
+        "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n"
+        "}\n" ::"r"(tmem_d),
+        "l"(desc_a), "l"(desc_b), "r"(idesc), "r"(accumulate)
+        : "memory");
+}
+__device__ __forceinline__ void tc_ld_32x32(uint32_t taddr, uint32_t (&r)[32]) {
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+        "{%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,"
+        "%16,%17,%18,%19,%20,%21,%22,%23,%24,%25,%26,%27,%28,%29,%30,%31}, [%32];\n"
+        : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]),
+          "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]),
+          "=r"(r[16]), "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]),
+          "=r"(r[24]), "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+        : "r"(taddr));
+    asm volatile("tcgen05.wait::ld.sync.aligned;\n" ::: "memory");
+}
+
+// K-major SWIZZLE_128B shared-memory matrix descriptor (tile rows are 128 B, 8-row groups 1024 B)
+__device__ __forceinline__ uint64_t tc_smem_desc(uint32_t smem_addr) {
+    uint64_t d = 0;
+    d |= (uint64_t)((smem_addr >> 4) & 0x3FFF);        // start address
+    d |= (uint64_t)1 << 16;                            // leading byte offset (unused for swizzled K-major)
+    d |= (uint64_t)(1024 >> 4) << 32;                  // stride byte offset between 8-row groups
+    d |= (uint64_t)1 << 46;                            // descriptor version (Blackwell)
+    d |= (uint64_t)2 << 61;                            // SWIZZLE_128B
+    return d;
+}
+
+// instruction descriptor: D = f32, A = B = bf16, both K-major, M = 128, N = BN
+__host__ __device__ constexpr uint32_t tc_idesc(int bn) {
+    return (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(bn >> 3) << 17) | ((uint32_t)(kTcBM >> 4) << 24);
+}
+
+template <int BN>
+struct TcSmem {
+    static constexpr int kABytes = kTcBM * kTcBK * 2;
+    static constexpr int kWBytes = BN * kTcBK * 2;
+    static constexpr int kStageBytes = kABytes + kWBytes;
+    static constexpr int kBarOffset = kTcStages * kStageBytes;
+    static constexpr int kTotal = kBarOffset + 256 + 1024;  // barriers + slack for 1024-B alignment
+};
+
+template <int BN, class Epi>
+__global__ void __launch_bounds__(kTcThreads)
+    gemm_tn_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_w,
+                           int M, int K, ARowMap amap, Epi epi) {
+    using S = TcSmem<BN>;
+    extern __shared__ unsigned char tc_smem_raw[];
+    const uint32_t raw = smem_u32(tc_smem_raw);
+    const uint32_t base = (raw + 1023u) & ~1023u;                 // SWIZZLE_128B tiles need 1024-B alignment
+    unsigned char* base_ptr = tc_smem_raw + (base - raw);
+    const uint32_t bar_full = base + S::kBarOffset;               // kTcStages x 8 B
+    const uint32_t bar_empty = bar_full + kTcStages * 8;          // kTcStages x 8 B
+    const uint32_t bar_acc = bar_empty + kTcStages * 8;           // 8 B
+    volatile uint32_t* tmem_slot = reinterpret_cast<volatile uint32_t*>(base_ptr + S::kBarOffset + 128);
+
+    const int warp = threadIdx.x >> 5;
+    const int lane = threadIdx.x & 31;
+    const int m0 = blockIdx.y * kTcBM;
+    const int n0 = blockIdx.x * BN;
+    const int KB = K / kTcBK;
+
+    if (threadIdx.x == 0) {
+        for (int s = 0; s < kTcStages; ++s) {
+            mbar_init(bar_full + s * 8, 1);
+            mbar_init(bar_empty + s * 8, 1);
+        }
+        mbar_init(bar_acc, 1);
+        asm volatile("fence.mbarrier_init.release.cluster;\n" ::: "memory");
+        asm volatile("fence.proxy.async.shared::cta;\n" ::: "memory");
+    }
+    if (warp == 1) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;\n" ::"r"(
+                         smem_u32((const void*)tmem_slot)),
+                     "n"(BN)
+                     : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;\n" ::: "memory");
+    }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+
+    if (warp == 0) {
+        if (lane == 0) {
+            // A rows may be gathered block-wise (cross-K/V projection picks each lane's segment)
+            int arow = m0;
+            if (amap.map) arow = amap.map[m0 / amap.block] * amap.block + m0 % amap.block;
+            for (int kb = 0; kb < KB; ++kb) {
+                const int s = kb % kTcStages;
+                mbar_wait(bar_empty + s * 8, ((kb / kTcStages) & 1) ^ 1);
+                mbar_expect_tx(bar_full + s * 8, S::kStageBytes);
+                const uint32_t sa = base + s * S::kStageBytes;
+                tma_load_2d(sa, &tmap_a, kb * kTcBK, arow, bar_full + s * 8);
+                tma_load_2d(sa + S::kABytes, &tmap_w, kb * kTcBK, n0, bar_full + s * 8);
+            }
+        }
+    } else if (warp == 1) {
+        if (lane == 0) {
+            constexpr uint32_t idesc = tc_idesc(BN);
+            for (int kb = 0; kb < KB; ++kb) {
+                const int s = kb % kTcStages;
+                mbar_wait(bar_full + s * 8, (kb / kTcStages) & 1);
+                tc_fence_after();
+                const uint32_t sa = base + s * S::kStageBytes;
+                const uint64_t da = tc_smem_desc(sa);
+                const uint64_t dw = tc_smem_desc(sa + S::kABytes);
+#pragma unroll
+                for (int k = 0; k < kTcBK / 16; ++k) {
+                    // advance 16 elements (32 B) along K inside the 128-B swizzle atom: +2 in the
+                    // 16-byte-granular start-address field
+                    tc_mma_f16(tmem_base, da + (uint64_t)(2 * k), dw + (uint64_t)(2 * k), idesc, (kb | k) != 0);
+                }
+                tc_commit(bar_empty + s * 8);  // frees the ring slot once the MMAs have read it
+            }
+            tc_commit(bar_acc);  // accumulator complete
+        }
+    } else {
+        // epilogue warps 2..5: TMEM lane quarter = warp % 4
+        const int quarter = warp & 3;
+        mbar_wait(bar_acc, 0);
+        tc_fence_after();
+        const int row = m0 + quarter * 32 + lane;
+#pragma unroll 1
+        for (int c = 0; c < BN / 32; ++c) {
+            uint32_t v[32];
+            tc_ld_32x32(tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(c * 32), v);
+            if (row < M) {
+#pragma unroll
+                for (int j = 0; j < 16; ++j)
+                    epi(row, n0 + c * 32 + 2 * j, __uint_as_float(v[2 * j]), __uint_as_float(v[2 * j + 1]));
+            }
+        }
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 1) {
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;\n" ::"r"(tmem_base), "n"(BN) : "memory");
+    }
+}
+
+// ---- host side: tensor maps -------------------------------------------------------------------
+typedef CUresult (*PFN_tmapEncodeTiled)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                        const cuuint64_t*, const cuuint32_t*, const cuuint32_t*,
+                                        CUtensorMapInterleave, CUtensorMapSwizzle, CUtensorMapL2promotion,
+                                        CUtensorMapFloatOOBfill);
+
+class TmaCache {
+public:
+    // 2-D bf16 row-major tensor (rows, cols) with row pitch ld elements; box = box_rows x 64 cols
+    Status get(const void* ptr, long rows, int cols, int ld, int box_rows, const CUtensorMap** out) {
+        Key key{ptr, rows, cols, ld, box_rows};
+        auto it = maps_.find(key);
+        if (it == maps_.end()) {
+            if (!encode_) {
+                void* fn = nullptr;
+                cudaDriverEntryPointQueryResult qres;
+                MRMT3_CUDA_TRY(cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &qres));
+                if (!fn || qres != cudaDriverEntryPointSuccess) return Error(2, "cuTensorMapEncodeTiled not available");
+                encode_ = reinterpret_cast<PFN_tmapEncodeTiled>(fn);
+            }
+            CUtensorMap m;
+            cuuint64_t dims[2] = {(cuuint64_t)cols, (cuuint64_t)rows};
+            cuuint64_t strides[1] = {(cuuint64_t)ld * 2};
+            cuuint32_t box[2] = {(cuuint32_t)kTcBK, (cuuint32_t)box_rows};
+            cuuint32_t estr[2] = {1, 1};
+            CUresult r = encode_(&m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(ptr), dims, strides, box,
+                                 estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
+                                 CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+            if (r != CUDA_SUCCESS) return Error(2, "cuTensorMapEncodeTiled failed with code " + std::to_string((int)r));
+            if (maps_.size() > 4096) maps_.clear();
+            it = maps_.emplace(key, m).first;
+        }
+        *out = &it->second;
+        return OkStatus();
+    }
+    void clear() { maps_.clear(); }
+
+private:
+    typedef std::tuple<const void*, long, int, int, int> Key;
+    std::map<Key, CUtensorMap> maps_;
+    PFN_tmapEncodeTiled encode_ = nullptr;
+};
+
+// a_rows: rows addressable through A (>= M; larger when amap gathers from a bigger tensor)
+template <class Epi>
+Status launch_gemm_tc(TmaCache& tc, const bf16* A, int lda, long a_rows, ARowMap amap, const bf16* W, int ldw,
+                      int M, int N, int K, const Epi& epi, cudaStream_t stream) {
+    if (M <= 0) return OkStatus();
+    if (K % kTcBK != 0 || N % 64 != 0) return Error(2, "gemm_tc: K and N must be multiples of 64");
+    if (amap.map && amap.block % kTcBM != 0) return Error(2, "gemm_tc: gather block must be a multiple of 128 rows");
+    const CUtensorMap *ma = nullptr, *mw = nullptr;
+    MRMT3_TRY(tc.get(A, a_rows, K, lda, kTcBM, &ma));
+    if (N % 128 == 0) {
+        constexpr int BN = 128;
+        MRMT3_TRY(tc.get(W, N, K, ldw, BN, &mw));
+        auto kern = gemm_tn_tcgen05_kernel<BN, Epi>;
+        static bool attr_set = false;
+        if (!attr_set) {
+            MRMT3_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, TcSmem<BN>::kTotal));
+            attr_set = true;
+        }
+        dim3 grid(N / BN, ceil_div(M, kTcBM));
+        kern<<<grid, kTcThreads, TcSmem<BN>::kTotal, stream>>>(*ma, *mw, M, K, amap, epi);
+    } else {
+        constexpr int BN = 64;
+        MRMT3_TRY(tc.get(W, N, K, ldw, BN, &mw));
+        auto kern = gemm_tn_tcgen05_kernel<BN, Epi>;
+        static bool attr_set = false;
+        if (!attr_set) {
+            MRMT3_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, TcSmem<BN>::kTotal));
+            attr_set = true;
+        }
+        dim3 grid(N / BN, ceil_div(M, kTcBM));
+        kern<<<grid, kTcThreads, TcSmem<BN>::kTotal, stream>>>(*ma, *mw, M, K, amap, epi);
+    }
+    MRMT3_CHECK_LAUNCH();
+    return OkStatus();
+}
+
+}  // namespace mrmt3

@@ -10,6 +10,7 @@
 #include <cstring>
 
 #include "gemm_skinny.cuh"
+#include "gemm_tcgen05.cuh"
 
 using namespace mrmt3;
 
@@ -184,6 +185,7 @@ Status handle_init(mrmt3_handle* h) {
     h->n_pos = kNPos;
     MRMT3_TRY(h->stage.reserve((size_t)2 * kDFF * kDModel * 4));
     MRMT3_TRY(h->frontend.init());
+    h->tma = new TmaCache();
     MRMT3_CUDA_TRY(cudaMallocHost((void**)&h->h_pinned, (kMaxLanes + 64) * sizeof(int)));
     MRMT3_CUDA_TRY(cudaEventCreateWithFlags(&h->poll_ev[0], cudaEventDisableTiming));
     MRMT3_CUDA_TRY(cudaEventCreateWithFlags(&h->poll_ev[1], cudaEventDisableTiming));
@@ -197,6 +199,20 @@ static void destroy_graphs(mrmt3_handle* h) {
     for (auto& kv : h->graphs)
         if (kv.second.exec) cudaGraphExecDestroy(kv.second.exec);
     h->graphs.clear();
+}
+
+Status test_gemm(mrmt3_handle* h, const bf16* A, const bf16* W, int M, int N, int K, float* C, int which,
+                 cudaStream_t s) {
+    MRMT3_CUDA_TRY(cudaSetDevice(h->device));
+    const ARowMap id{nullptr, 1};
+    if (which == 0) return launch_gemm_mma(A, K, id, W, K, M, N, K, EpiStoreF32{C, N}, s);
+    if (which == 1) return launch_gemm_tc(*h->tma, A, K, M, id, W, K, M, N, K, EpiStoreF32{C, N}, s);
+    if (which == 2) {
+        if (K == 384) return launch_gemm_skinny<32, 384, false>(A, K, W, K, M, N, 0.f, EpiStoreF32{C, N}, s);
+        if (K == 512) return launch_gemm_skinny<32, 512, false>(A, K, W, K, M, N, 0.f, EpiStoreF32{C, N}, s);
+        if (K == 1024) return launch_gemm_skinny<32, 1024, false>(A, K, W, K, M, N, 0.f, EpiStoreF32{C, N}, s);
+    }
+    return Error(2, "test_gemm: unsupported kernel / shape");
 }
 
 Status trace_enable(mrmt3_handle* h, bool on) {
@@ -221,6 +237,8 @@ void handle_destroy(mrmt3_handle* h) {
     cudaSetDevice(h->device);
     cudaDeviceSynchronize();
     destroy_graphs(h);
+    delete h->tma;
+    h->tma = nullptr;
     h->frontend.destroy();
     h->arena.release(); h->stage.release(); h->rows.release(); h->enc_bf16.release();
     h->mem_bf16.release(); h->mem_f32.release(); h->mel_f32.release(); h->mel_bf16.release();
@@ -393,7 +411,7 @@ static Status run_encoder_stack(mrmt3_handle* h, const StackW& st, int n_seq, in
         const LayerW& L = st.layers[li];
         const bool reduce = (li + 1 == st.layers.size()) && q_rows < T;
         RUN(h, launch_rmsnorm(hcur, L.ln_self, eps, w.n_bf16.as<bf16>(), nullptr, M, nullptr, 1, s));
-        RUN(h, launch_gemm_mma(w.n_bf16.as<bf16>(), kDModel, ARowMap{nullptr, 1}, L.wqkv, kDModel, M,
+        RUN(h, launch_gemm_tc(*h->tma, w.n_bf16.as<bf16>(), kDModel, M, ARowMap{nullptr, 1}, L.wqkv, kDModel, M,
                                3 * kInner, kDModel, EpiStoreBf16{w.qkv.as<bf16>(), 3 * kInner}, s));
         AttnFullParams ap{};
         ap.Q = w.qkv.as<bf16>();
@@ -417,20 +435,20 @@ static Status run_encoder_stack(mrmt3_handle* h, const StackW& st, int n_seq, in
             RUN(h, launch_gather_rows(hcur, w.hc32.as<float>(), n_seq, q_rows, T, s));
             hcur = w.hc32.as<float>();
             Mcur = n_seq * q_rows;
-            RUN(h, launch_gemm_mma(w.ctx_c.as<bf16>(), kInner, ARowMap{nullptr, 1}, L.wo, kInner, Mcur,
+            RUN(h, launch_gemm_tc(*h->tma, w.ctx_c.as<bf16>(), kInner, Mcur, ARowMap{nullptr, 1}, L.wo, kInner, Mcur,
                                    kDModel, kInner, EpiResidual{hcur, kDModel}, s));
         } else {
             ap.Tq = T;
             ap.O = w.ctx.as<bf16>();
             ap.o_batch_stride = (long)T * kInner;
             RUN(h, launch_attn_full(ap, n_seq, s));
-            RUN(h, launch_gemm_mma(w.ctx.as<bf16>(), kInner, ARowMap{nullptr, 1}, L.wo, kInner, M, kDModel,
+            RUN(h, launch_gemm_tc(*h->tma, w.ctx.as<bf16>(), kInner, M, ARowMap{nullptr, 1}, L.wo, kInner, M, kDModel,
                                    kInner, EpiResidual{hcur, kDModel}, s));
         }
         RUN(h, launch_rmsnorm(hcur, L.ln_ff, eps, w.n_bf16.as<bf16>(), nullptr, Mcur, nullptr, 1, s));
-        RUN(h, launch_gemm_mma(w.n_bf16.as<bf16>(), kDModel, ARowMap{nullptr, 1}, L.wi, kDModel, Mcur,
+        RUN(h, launch_gemm_tc(*h->tma, w.n_bf16.as<bf16>(), kDModel, Mcur, ARowMap{nullptr, 1}, L.wi, kDModel, Mcur,
                                2 * kDFF, kDModel, EpiGatedGelu{w.ff.as<bf16>(), kDFF}, s));
-        RUN(h, launch_gemm_mma(w.ff.as<bf16>(), kDFF, ARowMap{nullptr, 1}, L.wff, kDFF, Mcur, kDModel,
+        RUN(h, launch_gemm_tc(*h->tma, w.ff.as<bf16>(), kDFF, Mcur, ARowMap{nullptr, 1}, L.wff, kDFF, Mcur, kDModel,
                                kDFF, EpiResidual{hcur, kDModel}, s));
     }
     if (Mcur == M && q_rows < T) {
@@ -460,7 +478,7 @@ static Status encode_segments(mrmt3_handle* h, const float* mel_f32, const bf16*
                                     (size_t)M * kMels, s));
             x = h->rows.x_bf16.as<bf16>();
         }
-        RUN(h, launch_gemm_mma(x, kDModel, ARowMap{nullptr, 1}, h->proj, kDModel, M, kDModel, kDModel,
+        RUN(h, launch_gemm_tc(*h->tma, x, kDModel, M, ARowMap{nullptr, 1}, h->proj, kDModel, M, kDModel, kDModel,
                                EpiPosAdd{h->rows.h32.as<float>(), kDModel, h->pe, kSegFrames, 0}, s));
         MRMT3_TRY(run_encoder_stack(
             h, h->enc, n, kSegFrames, kSegFrames,
@@ -483,9 +501,9 @@ static Status memory_block(mrmt3_handle* h, const long long* ids, long ids_strid
         MRMT3_TRY(h->rows.reserve(M));
         RUN(h, launch_embed_bf16(src_row ? ids : ids + (size_t)c0 * ids_stride, ids_stride, Lp, n,
                                  src_row ? src_row + c0 : nullptr, h->emb, h->rows.x_bf16.as<bf16>(), s));
-        RUN(h, launch_gemm_mma(h->rows.x_bf16.as<bf16>(), kDModel, ARowMap{nullptr, 1}, h->segmem_proj,
-                               kDModel, M, kDModel, kDModel,
-                               EpiPosAdd{h->rows.h32.as<float>(), kDModel, h->pe, Lp, 0}, s));
+        RUN(h, launch_gemm_tc(*h->tma, h->rows.x_bf16.as<bf16>(), kDModel, M, ARowMap{nullptr, 1}, h->segmem_proj,
+                              kDModel, M, kDModel, kDModel,
+                              EpiPosAdd{h->rows.h32.as<float>(), kDModel, h->pe, Lp, 0}, s));
         MRMT3_TRY(run_encoder_stack(h, h->mem, n, Lp, n_mem,
                                     out_bf16 ? out_bf16 + (size_t)c0 * n_mem * kDModel : nullptr,
                                     out_f32 ? out_f32 + (size_t)c0 * n_mem * kDModel : nullptr, s));
@@ -807,16 +825,16 @@ static DecodeState make_state(mrmt3_handle* h, long long* out, int out_stride, i
 
 // cross K/V of every decoder layer for `n_lanes` lanes: encoder rows (gathered through
 // seg_index when given) and, for the V2 variant, the memory rows appended at key 256.
-static Status project_cross_kv(mrmt3_handle* h, const bf16* enc, const int* seg_index, int n_lanes,
+static Status project_cross_kv(mrmt3_handle* h, const bf16* enc, long enc_rows, const int* seg_index, int n_lanes,
                                const bf16* mem, int n_mem, cudaStream_t s) {
     const int N = h->cfg.n_dec_layers * 2 * kInner;
-    RUN(h, launch_gemm_mma(enc, kDModel, ARowMap{seg_index, kSegFrames}, h->cross_kv_w, kDModel,
-                           n_lanes * kSegFrames, N, kDModel,
+    RUN(h, launch_gemm_tc(*h->tma, enc, kDModel, enc_rows, ARowMap{seg_index, kSegFrames}, h->cross_kv_w, kDModel,
+                          n_lanes * kSegFrames, N, kDModel,
                            EpiCrossKV{h->cross_cache.as<bf16>(), kSegFrames, 0, h->cfg.n_dec_layers,
                                       h->tk_cap, nullptr}, s));
     if (mem && n_mem > 0)
-        RUN(h, launch_gemm_mma(mem, kDModel, ARowMap{nullptr, 1}, h->cross_kv_w, kDModel, n_lanes * n_mem, N,
-                               kDModel,
+        RUN(h, launch_gemm_tc(*h->tma, mem, kDModel, n_lanes * n_mem, ARowMap{nullptr, 1}, h->cross_kv_w, kDModel,
+                              n_lanes * n_mem, N, kDModel,
                                EpiCrossKV{h->cross_cache.as<bf16>(), n_mem, kSegFrames,
                                           h->cfg.n_dec_layers, h->tk_cap, nullptr}, s));
     return OkStatus();
@@ -851,7 +869,7 @@ Status generate_base(mrmt3_handle* h, const float* mel_f32, const bf16* mel_bf16
         MRMT3_TRY(encode_segments(h, mel_f32 ? mel_f32 + (size_t)c0 * kSegFrames * kMels : nullptr,
                                   mel_bf16 ? mel_bf16 + (size_t)c0 * kSegFrames * kMels : nullptr, n,
                                   h->enc_bf16.as<bf16>(), nullptr, s));
-        MRMT3_TRY(project_cross_kv(h, h->enc_bf16.as<bf16>(), nullptr, n, nullptr, 0, s));
+        MRMT3_TRY(project_cross_kv(h, h->enc_bf16.as<bf16>(), (long)n * kSegFrames, nullptr, n, nullptr, 0, s));
         LaneArrays a = lane_arrays(h);
         std::vector<int> rows(n);
         for (int i = 0; i < n; ++i) rows[i] = c0 + i;
@@ -959,7 +977,7 @@ Status generate_segmem(mrmt3_handle* h, const float* mel_f32, const bf16* mel_bf
             else
                 MRMT3_TRY(memory_block(h, tok, stride, a.prev_row, n, max_length, n_mem,
                                        h->mem_bf16.as<bf16>(), h->mem_f32.as<float>(), s));
-            MRMT3_TRY(project_cross_kv(h, h->enc_bf16.as<bf16>(), a.seg_index, n,
+            MRMT3_TRY(project_cross_kv(h, h->enc_bf16.as<bf16>(), (long)S * kSegFrames, a.seg_index, n,
                                        v1 ? nullptr : h->mem_bf16.as<bf16>(), v1 ? 0 : n_mem, s));
             StepPlan pl{};
             pl.n_lanes = n;
@@ -1012,7 +1030,7 @@ Status api_forward_logits(mrmt3_handle* h, const float* mel, int B, const long l
             MRMT3_TRY(memory_block(h, targets_prev + (size_t)c0 * Lp, Lp, nullptr, n, Lp, n_mem,
                                    h->mem_bf16.as<bf16>(), nullptr, s));
         }
-        MRMT3_TRY(project_cross_kv(h, h->enc_bf16.as<bf16>(), nullptr, n, mem ? h->mem_bf16.as<bf16>() : nullptr, n_mem, s));
+        MRMT3_TRY(project_cross_kv(h, h->enc_bf16.as<bf16>(), (long)n * kSegFrames, nullptr, n, mem ? h->mem_bf16.as<bf16>() : nullptr, n_mem, s));
         // decoder over n*L rows, in row chunks of whole sequences
         const int seq_chunk = std::max(1, (kEncChunk * kSegFrames) / L);
         for (int b0 = 0; b0 < n; b0 += seq_chunk) {
@@ -1026,7 +1044,7 @@ Status api_forward_logits(mrmt3_handle* h, const float* mel, int B, const long l
             for (int li = 0; li < h->cfg.n_dec_layers; ++li) {
                 const LayerW& Lw = h->dec.layers[li];
                 RUN(h, launch_rmsnorm(H, Lw.ln_self, eps, w.n_bf16.as<bf16>(), nullptr, M, nullptr, 1, s));
-                RUN(h, launch_gemm_mma(w.n_bf16.as<bf16>(), kDModel, id, Lw.wqkv, kDModel, M, 3 * kInner, kDModel,
+                RUN(h, launch_gemm_tc(*h->tma, w.n_bf16.as<bf16>(), kDModel, M, id, Lw.wqkv, kDModel, M, 3 * kInner, kDModel,
                                        EpiStoreBf16{w.qkv.as<bf16>(), 3 * kInner}, s));
                 AttnFullParams ap{};
                 ap.Q = w.qkv.as<bf16>();
@@ -1044,10 +1062,10 @@ Status api_forward_logits(mrmt3_handle* h, const float* mel, int B, const long l
                 ap.causal = 1;
                 ap.causal_offset = 0;
                 RUN(h, launch_attn_full(ap, nb, s));
-                RUN(h, launch_gemm_mma(w.ctx.as<bf16>(), kInner, id, Lw.wo, kInner, M, kDModel, kInner, EpiResidual{H, kDModel}, s));
+                RUN(h, launch_gemm_tc(*h->tma, w.ctx.as<bf16>(), kInner, M, id, Lw.wo, kInner, M, kDModel, kInner, EpiResidual{H, kDModel}, s));
 
                 RUN(h, launch_rmsnorm(H, Lw.ln_cross, eps, w.n_bf16.as<bf16>(), nullptr, M, nullptr, 1, s));
-                RUN(h, launch_gemm_mma(w.n_bf16.as<bf16>(), kDModel, id, Lw.cq, kDModel, M, kInner, kDModel,
+                RUN(h, launch_gemm_tc(*h->tma, w.n_bf16.as<bf16>(), kDModel, M, id, Lw.cq, kDModel, M, kInner, kDModel,
                                        EpiStoreBf16{w.qc.as<bf16>(), kInner}, s));
                 AttnFullParams cp{};
                 const size_t lane_sz = (size_t)h->cfg.n_dec_layers * 2 * kHeads * h->tk_cap * kDKV;
@@ -1070,15 +1088,15 @@ Status api_forward_logits(mrmt3_handle* h, const float* mel, int B, const long l
                 cp.Tk = tk;
                 cp.causal = 0;
                 RUN(h, launch_attn_full(cp, nb, s));
-                RUN(h, launch_gemm_mma(w.ctx.as<bf16>(), kInner, id, Lw.co, kInner, M, kDModel, kInner, EpiResidual{H, kDModel}, s));
+                RUN(h, launch_gemm_tc(*h->tma, w.ctx.as<bf16>(), kInner, M, id, Lw.co, kInner, M, kDModel, kInner, EpiResidual{H, kDModel}, s));
 
                 RUN(h, launch_rmsnorm(H, Lw.ln_ff, eps, w.n_bf16.as<bf16>(), nullptr, M, nullptr, 1, s));
-                RUN(h, launch_gemm_mma(w.n_bf16.as<bf16>(), kDModel, id, Lw.wi, kDModel, M, 2 * kDFF, kDModel,
+                RUN(h, launch_gemm_tc(*h->tma, w.n_bf16.as<bf16>(), kDModel, M, id, Lw.wi, kDModel, M, 2 * kDFF, kDModel,
                                        EpiGatedGelu{w.ff.as<bf16>(), kDFF}, s));
-                RUN(h, launch_gemm_mma(w.ff.as<bf16>(), kDFF, id, Lw.wff, kDFF, M, kDModel, kDFF, EpiResidual{H, kDModel}, s));
+                RUN(h, launch_gemm_tc(*h->tma, w.ff.as<bf16>(), kDFF, M, id, Lw.wff, kDFF, M, kDModel, kDFF, EpiResidual{H, kDModel}, s));
             }
             RUN(h, launch_rmsnorm(H, h->dec.final_ln, eps, w.n_bf16.as<bf16>(), nullptr, M, nullptr, 1, s));
-            RUN(h, launch_gemm_mma(w.n_bf16.as<bf16>(), kDModel, id, h->lm_head, kDModel, M, kVocab, kDModel,
+            RUN(h, launch_gemm_tc(*h->tma, w.n_bf16.as<bf16>(), kDModel, M, id, h->lm_head, kDModel, M, kVocab, kDModel,
                                    EpiStoreF32{logits_out + (size_t)(c0 + b0) * L * kVocab, kVocab}, s));
         }
     }

@@ -14,6 +14,8 @@
 
 namespace mrmt3 {
 
+class TmaCache;  // gemm_tcgen05.cuh
+
 struct DeviceBuffer {
     void* p = nullptr;
     size_t cap = 0;
@@ -83,6 +85,7 @@ struct mrmt3_handle {
     bool use_graphs = true;
 
     mrmt3::Frontend frontend;
+    mrmt3::TmaCache* tma = nullptr;      // cuTensorMap cache of the tcgen05 GEMMs
 
     // ---- weights ----
     mrmt3::DeviceBuffer arena;       // every packed tensor lives here

@@ -1,0 +1,2 @@
+python -c "import __graft_entry__ as g; g.build()" 2>&1 | tail -1
+timeout 300 python -m pytest tests/test_kernels_gpu.py -x -q 2>&1 | tail -15

@@ -1,0 +1,53 @@
+"""GPU: the library's three GEMM kernels against torch (bf16 inputs, fp32 accumulate) on the
+shapes the path uses.  bf16 x bf16 products are exact in fp32, so the only difference is the
+order of the fp32 sum: tolerance 1e-3 relative to the row scale."""
+import pytest
+import torch
+
+from helpers import package
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def eng():
+    if not torch.cuda.is_available():
+        pytest.skip("needs a CUDA device")
+    import importlib
+    package()
+    lib = importlib.import_module("mr-mt3_b200._lib")
+    return lib.Engine()
+
+
+def _check(eng, which, M, N, K, seed=0):
+    g = torch.Generator().manual_seed(seed + M + 7 * N + 13 * K)
+    a = torch.randn((M, K), generator=g).bfloat16()
+    w = (torch.randn((N, K), generator=g) * K ** -0.5).bfloat16()
+    got = eng.test_gemm(a, w, which).cpu()
+    want = a.double() @ w.double().T
+    err = (got.double() - want).abs().max().item()
+    assert err < 2e-3, (which, M, N, K, err)
+
+
+# encoder / projection shapes: (M, N, K)
+BIG = [(256, 512, 512), (512, 1152, 512), (300, 384, 512), (1000, 512, 384), (1024, 2048, 512),
+       (640, 512, 1024), (128, 6144, 512), (77, 1536, 512)]
+
+
+@pytest.mark.parametrize("M,N,K", BIG)
+def test_gemm_mma_sync(eng, M, N, K):
+    _check(eng, 0, M, N, K)
+
+
+@pytest.mark.parametrize("M,N,K", BIG)
+def test_gemm_tcgen05(eng, M, N, K):
+    _check(eng, 1, M, N, K)
+
+
+@pytest.mark.parametrize("M,N,K", [(256, 1152, 512), (64, 512, 384), (33, 2048, 512), (256, 512, 1024), (5, 384, 512)])
+def test_gemm_decode_single_shot(eng, M, N, K):
+    _check(eng, 2, M, N, K)
+
+
+def test_tcgen05_large(eng):
+    _check(eng, 1, 65536, 1152, 512)
