@@ -1,14 +1,14 @@
 // C[M,N] = A[M,K] * W[N,K]^T for the large-M GEMMs of the path (encoder, cross-K/V projection,
 // memory block, teacher-forced decoder): TMA-fed tcgen05.mma with the fp32 accumulator in TMEM.
 //
-//   * one 128 x BN output tile per CTA (BN = 128 or 64), BK = 64, 3-stage shared-memory ring
+//   * persistent CTAs (one per SM) walking 128 x BN output tiles (BN = 256/192/128/64, the widest
+//     that divides N), BK = 64, 4-6 stage shared-memory ring, accumulator double-buffered in TMEM
 //   * warp 0  : TMA producer  (cp.async.bulk.tensor.2d, 128-byte swizzle, mbarrier complete_tx)
 //   * warp 1  : allocates TMEM, issues tcgen05.mma.cta_group::1.kind::f16 (one elected lane),
 //               tcgen05.commit frees ring slots / publishes the accumulator
 //   * warps 2-5: epilogue -- tcgen05.ld (32 lanes x 32 columns per warp), the same epilogue
 //               functors as the mma.sync kernels (gemm_mma.cuh), direct global stores
-//   * two CTAs fit per SM (96 KB smem, 128 TMEM columns each), so one CTA's epilogue overlaps the
-//     other's main loop.
+//   * the epilogue warps drain accumulator buffer b while the MMA warp fills buffer b^1.
 //
 // Descriptor encodings follow the PTX ISA "tcgen05 matrix / instruction descriptor" tables (the
 // same fields CUTLASS's cute/arch/mma_sm100_desc.hpp names): K-major operands, SWIZZLE_128B,
@@ -25,7 +25,6 @@ namespace mrmt3 {
 
 constexpr int kTcBM = 128;
 constexpr int kTcBK = 64;
-constexpr int kTcStages = 3;
 constexpr int kTcThreads = 192;
 
 // ---- PTX wrappers ---------------------------------------------------------------------------
@@ -101,48 +100,114 @@ __host__ __device__ constexpr uint32_t tc_idesc(int bn) {
     return (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(bn >> 3) << 17) | ((uint32_t)(kTcBM >> 4) << 24);
 }
 
+// ---- 8-wide epilogue stores --------------------------------------------------------------------
+// An epilogue thread owns one output row and walks its columns, so it can store 8 consecutive
+// columns with one or two 16-byte transactions instead of four 4/8-byte ones.  Generic fallback:
+// the pairwise functor interface of gemm_mma.cuh.
+template <class Epi>
+__device__ __forceinline__ void epi_store8(const Epi& epi, int row, int col, const float (&v)[8]) {
+#pragma unroll
+    for (int j = 0; j < 4; ++j) epi(row, col + 2 * j, v[2 * j], v[2 * j + 1]);
+}
+__device__ __forceinline__ void epi_store8(const EpiStoreBf16& e, int row, int col, const float (&v)[8]) {
+    *reinterpret_cast<uint4*>(e.C + (size_t)row * e.ldc + col) =
+        make_uint4(pack_bf16(v[0], v[1]), pack_bf16(v[2], v[3]), pack_bf16(v[4], v[5]), pack_bf16(v[6], v[7]));
+}
+__device__ __forceinline__ void epi_store8(const EpiStoreF32& e, int row, int col, const float (&v)[8]) {
+    float4* p = reinterpret_cast<float4*>(e.C + (size_t)row * e.ldc + col);
+    p[0] = make_float4(v[0], v[1], v[2], v[3]);
+    p[1] = make_float4(v[4], v[5], v[6], v[7]);
+}
+__device__ __forceinline__ void epi_store8(const EpiResidual& e, int row, int col, const float (&v)[8]) {
+    float4* p = reinterpret_cast<float4*>(e.H + (size_t)row * e.ldh + col);
+    float4 a = p[0], b = p[1];
+    p[0] = make_float4(a.x + v[0], a.y + v[1], a.z + v[2], a.w + v[3]);
+    p[1] = make_float4(b.x + v[4], b.y + v[5], b.z + v[6], b.w + v[7]);
+}
+__device__ __forceinline__ void epi_store8(const EpiPosAdd& e, int row, int col, const float (&v)[8]) {
+    const float4* q = reinterpret_cast<const float4*>(e.pe + (size_t)(e.pos_offset + row % e.period) * e.ldh + col);
+    const float4 a = q[0], b = q[1];
+    float4* p = reinterpret_cast<float4*>(e.H + (size_t)row * e.ldh + col);
+    p[0] = make_float4(a.x + v[0], a.y + v[1], a.z + v[2], a.w + v[3]);
+    p[1] = make_float4(b.x + v[4], b.y + v[5], b.z + v[6], b.w + v[7]);
+}
+__device__ __forceinline__ void epi_store8(const EpiGatedGelu& e, int row, int col, const float (&v)[8]) {
+    *reinterpret_cast<uint2*>(e.C + (size_t)row * e.ldc + (col >> 1)) =
+        make_uint2(pack_bf16(gelu_new(v[0]) * v[1], gelu_new(v[2]) * v[3]),
+                   pack_bf16(gelu_new(v[4]) * v[5], gelu_new(v[6]) * v[7]));
+}
+__device__ __forceinline__ void epi_store8(const EpiCrossKV& e, int row, int col, const float (&v)[8]) {
+    int lane = row / e.rows_per_lane;
+    int t = row - lane * e.rows_per_lane + e.t_offset;
+    if (e.lane_map) lane = e.lane_map[lane];
+    int layer = col / (2 * kInner);
+    int r = col - layer * (2 * kInner);
+    int kv = r / kInner;
+    r -= kv * kInner;
+    size_t off = ((((size_t)lane * e.n_layers + layer) * 2 + kv) * kHeads + (r >> 6)) * e.tk_cap + t;
+    *reinterpret_cast<uint4*>(e.cache + off * kDKV + (r & 63)) =
+        make_uint4(pack_bf16(v[0], v[1]), pack_bf16(v[2], v[3]), pack_bf16(v[4], v[5]), pack_bf16(v[6], v[7]));
+}
+
+__device__ __forceinline__ void mbar_arrive(uint32_t bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];\n" ::"r"(bar) : "memory");
+}
+
 template <int BN>
 struct TcSmem {
+    static constexpr int kStages = BN > 128 ? 4 : 6;
     static constexpr int kABytes = kTcBM * kTcBK * 2;
     static constexpr int kWBytes = BN * kTcBK * 2;
     static constexpr int kStageBytes = kABytes + kWBytes;
-    static constexpr int kBarOffset = kTcStages * kStageBytes;
+    static constexpr int kBarOffset = kStages * kStageBytes;
     static constexpr int kTotal = kBarOffset + 256 + 1024;  // barriers + slack for 1024-B alignment
+    static constexpr int kAccCols = BN > 128 ? 256 : 128;   // TMEM columns per accumulator buffer
+    static constexpr int kTmemCols = 2 * kAccCols;          // double-buffered accumulator
 };
 
+// Persistent: grid = min(#tiles, #SMs); each CTA walks tiles t = blockIdx.x + i * gridDim.x with
+// the n-block fastest, so CTAs running at the same time share their A rows through L2.  The
+// accumulator is double-buffered in TMEM: the epilogue warps drain tile i while the MMA warp
+// already accumulates tile i + 1.
 template <int BN, class Epi>
-__global__ void __launch_bounds__(kTcThreads)
+__global__ void __launch_bounds__(kTcThreads, 1)
     gemm_tn_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_w,
-                           int M, int K, ARowMap amap, Epi epi) {
+                           int M, int N, int K, ARowMap amap, Epi epi) {
     using S = TcSmem<BN>;
+    constexpr int kStages = S::kStages;
     extern __shared__ unsigned char tc_smem_raw[];
     const uint32_t raw = smem_u32(tc_smem_raw);
     const uint32_t base = (raw + 1023u) & ~1023u;                 // SWIZZLE_128B tiles need 1024-B alignment
     unsigned char* base_ptr = tc_smem_raw + (base - raw);
-    const uint32_t bar_full = base + S::kBarOffset;               // kTcStages x 8 B
-    const uint32_t bar_empty = bar_full + kTcStages * 8;          // kTcStages x 8 B
-    const uint32_t bar_acc = bar_empty + kTcStages * 8;           // 8 B
-    volatile uint32_t* tmem_slot = reinterpret_cast<volatile uint32_t*>(base_ptr + S::kBarOffset + 128);
+    const uint32_t bar_full = base + S::kBarOffset;               // kStages x 8 B
+    const uint32_t bar_empty = bar_full + kStages * 8;            // kStages x 8 B
+    const uint32_t bar_acc_full = bar_empty + kStages * 8;        // 2 x 8 B
+    const uint32_t bar_acc_empty = bar_acc_full + 16;             // 2 x 8 B
+    volatile uint32_t* tmem_slot = reinterpret_cast<volatile uint32_t*>(base_ptr + S::kBarOffset + 192);
 
     const int warp = threadIdx.x >> 5;
     const int lane = threadIdx.x & 31;
-    const int m0 = blockIdx.y * kTcBM;
-    const int n0 = blockIdx.x * BN;
     const int KB = K / kTcBK;
+    const int tiles_n = N / BN;
+    const int tiles_m = (M + kTcBM - 1) / kTcBM;
+    const int n_tiles = tiles_n * tiles_m;
 
     if (threadIdx.x == 0) {
-        for (int s = 0; s < kTcStages; ++s) {
+        for (int s = 0; s < kStages; ++s) {
             mbar_init(bar_full + s * 8, 1);
             mbar_init(bar_empty + s * 8, 1);
         }
-        mbar_init(bar_acc, 1);
+        for (int b = 0; b < 2; ++b) {
+            mbar_init(bar_acc_full + b * 8, 1);
+            mbar_init(bar_acc_empty + b * 8, 128);  // every epilogue thread arrives
+        }
         asm volatile("fence.mbarrier_init.release.cluster;\n" ::: "memory");
         asm volatile("fence.proxy.async.shared::cta;\n" ::: "memory");
     }
     if (warp == 1) {
         asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;\n" ::"r"(
                          smem_u32((const void*)tmem_slot)),
-                     "n"(BN)
+                     "n"(S::kTmemCols)
                      : "memory");
         asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;\n" ::: "memory");
     }
@@ -153,59 +218,85 @@ __global__ void __launch_bounds__(kTcThreads)
 
     if (warp == 0) {
         if (lane == 0) {
-            // A rows may be gathered block-wise (cross-K/V projection picks each lane's segment)
-            int arow = m0;
-            if (amap.map) arow = amap.map[m0 / amap.block] * amap.block + m0 % amap.block;
-            for (int kb = 0; kb < KB; ++kb) {
-                const int s = kb % kTcStages;
-                mbar_wait(bar_empty + s * 8, ((kb / kTcStages) & 1) ^ 1);
-                mbar_expect_tx(bar_full + s * 8, S::kStageBytes);
-                const uint32_t sa = base + s * S::kStageBytes;
-                tma_load_2d(sa, &tmap_a, kb * kTcBK, arow, bar_full + s * 8);
-                tma_load_2d(sa + S::kABytes, &tmap_w, kb * kTcBK, n0, bar_full + s * 8);
+            int it = 0;
+            for (int t = blockIdx.x; t < n_tiles; t += gridDim.x) {
+                const int m0 = (t / tiles_n) * kTcBM;
+                const int n0 = (t % tiles_n) * BN;
+                // A rows may be gathered block-wise (cross-K/V projection picks each lane's segment)
+                int arow = m0;
+                if (amap.map) arow = amap.map[m0 / amap.block] * amap.block + m0 % amap.block;
+                for (int kb = 0; kb < KB; ++kb, ++it) {
+                    const int s = it % kStages;
+                    mbar_wait(bar_empty + s * 8, ((it / kStages) & 1) ^ 1);
+                    mbar_expect_tx(bar_full + s * 8, S::kStageBytes);
+                    const uint32_t sa = base + s * S::kStageBytes;
+                    tma_load_2d(sa, &tmap_a, kb * kTcBK, arow, bar_full + s * 8);
+                    tma_load_2d(sa + S::kABytes, &tmap_w, kb * kTcBK, n0, bar_full + s * 8);
+                }
             }
         }
     } else if (warp == 1) {
         if (lane == 0) {
             constexpr uint32_t idesc = tc_idesc(BN);
-            for (int kb = 0; kb < KB; ++kb) {
-                const int s = kb % kTcStages;
-                mbar_wait(bar_full + s * 8, (kb / kTcStages) & 1);
+            int it = 0, i = 0;
+            for (int t = blockIdx.x; t < n_tiles; t += gridDim.x, ++i) {
+                const int buf = i & 1;
+                mbar_wait(bar_acc_empty + buf * 8, ((i >> 1) & 1) ^ 1);  // epilogue has drained this buffer
                 tc_fence_after();
-                const uint32_t sa = base + s * S::kStageBytes;
-                const uint64_t da = tc_smem_desc(sa);
-                const uint64_t dw = tc_smem_desc(sa + S::kABytes);
+                const uint32_t tacc = tmem_base + (uint32_t)(buf * S::kAccCols);
+                for (int kb = 0; kb < KB; ++kb, ++it) {
+                    const int s = it % kStages;
+                    mbar_wait(bar_full + s * 8, (it / kStages) & 1);
+                    tc_fence_after();
+                    const uint32_t sa = base + s * S::kStageBytes;
+                    const uint64_t da = tc_smem_desc(sa);
+                    const uint64_t dw = tc_smem_desc(sa + S::kABytes);
 #pragma unroll
-                for (int k = 0; k < kTcBK / 16; ++k) {
-                    // advance 16 elements (32 B) along K inside the 128-B swizzle atom: +2 in the
-                    // 16-byte-granular start-address field
-                    tc_mma_f16(tmem_base, da + (uint64_t)(2 * k), dw + (uint64_t)(2 * k), idesc, (kb | k) != 0);
+                    for (int k = 0; k < kTcBK / 16; ++k) {
+                        // advance 16 elements (32 B) along K inside the 128-B swizzle atom: +2 in
+                        // the 16-byte-granular start-address field
+                        tc_mma_f16(tacc, da + (uint64_t)(2 * k), dw + (uint64_t)(2 * k), idesc, (kb | k) != 0);
+                    }
+                    tc_commit(bar_empty + s * 8);  // frees the ring slot once the MMAs have read it
                 }
-                tc_commit(bar_empty + s * 8);  // frees the ring slot once the MMAs have read it
+                tc_commit(bar_acc_full + buf * 8);  // accumulator of this tile complete
             }
-            tc_commit(bar_acc);  // accumulator complete
         }
     } else {
         // epilogue warps 2..5: TMEM lane quarter = warp % 4
         const int quarter = warp & 3;
-        mbar_wait(bar_acc, 0);
-        tc_fence_after();
-        const int row = m0 + quarter * 32 + lane;
+        int i = 0;
+        for (int t = blockIdx.x; t < n_tiles; t += gridDim.x, ++i) {
+            const int m0 = (t / tiles_n) * kTcBM;
+            const int n0 = (t % tiles_n) * BN;
+            const int buf = i & 1;
+            mbar_wait(bar_acc_full + buf * 8, (i >> 1) & 1);
+            tc_fence_after();
+            const int row = m0 + quarter * 32 + lane;
+            const uint32_t tacc = tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(buf * S::kAccCols);
 #pragma unroll 1
-        for (int c = 0; c < BN / 32; ++c) {
-            uint32_t v[32];
-            tc_ld_32x32(tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(c * 32), v);
-            if (row < M) {
+            for (int c = 0; c < BN / 32; ++c) {
+                uint32_t v[32];
+                tc_ld_32x32(tacc + (uint32_t)(c * 32), v);
+                if (row < M) {
 #pragma unroll
-                for (int j = 0; j < 16; ++j)
-                    epi(row, n0 + c * 32 + 2 * j, __uint_as_float(v[2 * j]), __uint_as_float(v[2 * j + 1]));
+                    for (int j = 0; j < 4; ++j) {
+                        float f[8];
+#pragma unroll
+                        for (int e = 0; e < 8; ++e) f[e] = __uint_as_float(v[8 * j + e]);
+                        epi_store8(epi, row, n0 + c * 32 + 8 * j, f);
+                    }
+                }
             }
+            tc_fence_before();
+            mbar_arrive(bar_acc_empty + buf * 8);
         }
     }
     tc_fence_before();
     __syncthreads();
     if (warp == 1) {
-        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;\n" ::"r"(tmem_base), "n"(BN) : "memory");
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;\n" ::"r"(tmem_base), "n"(S::kTmemCols)
+                     : "memory");
     }
 }
 
@@ -253,39 +344,42 @@ private:
 };
 
 // a_rows: rows addressable through A (>= M; larger when amap gathers from a bigger tensor)
+template <int BN, class Epi>
+Status launch_gemm_tc_bn(TmaCache& tc, const CUtensorMap* ma, const bf16* W, int ldw, int M, int N, int K,
+                         ARowMap amap, const Epi& epi, int n_sms, cudaStream_t stream) {
+    const CUtensorMap* mw = nullptr;
+    MRMT3_TRY(tc.get(W, N, K, ldw, BN, &mw));
+    auto kern = gemm_tn_tcgen05_kernel<BN, Epi>;
+    static bool attr_set = false;
+    if (!attr_set) {
+        MRMT3_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, TcSmem<BN>::kTotal));
+        attr_set = true;
+    }
+    const int n_tiles = (N / BN) * ceil_div(M, kTcBM);
+    kern<<<std::min(n_tiles, n_sms), kTcThreads, TcSmem<BN>::kTotal, stream>>>(*ma, *mw, M, N, K, amap, epi);
+    MRMT3_CHECK_LAUNCH();
+    return OkStatus();
+}
+
 template <class Epi>
 Status launch_gemm_tc(TmaCache& tc, const bf16* A, int lda, long a_rows, ARowMap amap, const bf16* W, int ldw,
                       int M, int N, int K, const Epi& epi, cudaStream_t stream) {
     if (M <= 0) return OkStatus();
     if (K % kTcBK != 0 || N % 64 != 0) return Error(2, "gemm_tc: K and N must be multiples of 64");
     if (amap.map && amap.block % kTcBM != 0) return Error(2, "gemm_tc: gather block must be a multiple of 128 rows");
-    const CUtensorMap *ma = nullptr, *mw = nullptr;
-    MRMT3_TRY(tc.get(A, a_rows, K, lda, kTcBM, &ma));
-    if (N % 128 == 0) {
-        constexpr int BN = 128;
-        MRMT3_TRY(tc.get(W, N, K, ldw, BN, &mw));
-        auto kern = gemm_tn_tcgen05_kernel<BN, Epi>;
-        static bool attr_set = false;
-        if (!attr_set) {
-            MRMT3_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, TcSmem<BN>::kTotal));
-            attr_set = true;
-        }
-        dim3 grid(N / BN, ceil_div(M, kTcBM));
-        kern<<<grid, kTcThreads, TcSmem<BN>::kTotal, stream>>>(*ma, *mw, M, K, amap, epi);
-    } else {
-        constexpr int BN = 64;
-        MRMT3_TRY(tc.get(W, N, K, ldw, BN, &mw));
-        auto kern = gemm_tn_tcgen05_kernel<BN, Epi>;
-        static bool attr_set = false;
-        if (!attr_set) {
-            MRMT3_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, TcSmem<BN>::kTotal));
-            attr_set = true;
-        }
-        dim3 grid(N / BN, ceil_div(M, kTcBM));
-        kern<<<grid, kTcThreads, TcSmem<BN>::kTotal, stream>>>(*ma, *mw, M, K, amap, epi);
+    static int n_sms = 0;
+    if (!n_sms) {
+        int dev = 0;
+        MRMT3_CUDA_TRY(cudaGetDevice(&dev));
+        MRMT3_CUDA_TRY(cudaDeviceGetAttribute(&n_sms, cudaDevAttrMultiProcessorCount, dev));
     }
-    MRMT3_CHECK_LAUNCH();
-    return OkStatus();
+    const CUtensorMap* ma = nullptr;
+    MRMT3_TRY(tc.get(A, a_rows, K, lda, kTcBM, &ma));
+    // widest tile that divides N: wider tiles move fewer operand bytes per MAC through L2
+    if (N % 256 == 0) return launch_gemm_tc_bn<256>(tc, ma, W, ldw, M, N, K, amap, epi, n_sms, stream);
+    if (N % 192 == 0) return launch_gemm_tc_bn<192>(tc, ma, W, ldw, M, N, K, amap, epi, n_sms, stream);
+    if (N % 128 == 0) return launch_gemm_tc_bn<128>(tc, ma, W, ldw, M, N, K, amap, epi, n_sms, stream);
+    return launch_gemm_tc_bn<64>(tc, ma, W, ldw, M, N, K, amap, epi, n_sms, stream);
 }
 
 }  // namespace mrmt3

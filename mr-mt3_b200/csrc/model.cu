@@ -207,6 +207,8 @@ Status test_gemm(mrmt3_handle* h, const bf16* A, const bf16* W, int M, int N, in
     const ARowMap id{nullptr, 1};
     if (which == 0) return launch_gemm_mma(A, K, id, W, K, M, N, K, EpiStoreF32{C, N}, s);
     if (which == 1) return launch_gemm_tc(*h->tma, A, K, M, id, W, K, M, N, K, EpiStoreF32{C, N}, s);
+    if (which == 3)  // tcgen05 with the bf16 store epilogue the encoder uses (C holds M*N bf16)
+        return launch_gemm_tc(*h->tma, A, K, M, id, W, K, M, N, K, EpiStoreBf16{reinterpret_cast<bf16*>(C), N}, s);
     if (which == 2) {
         if (K == 384) return launch_gemm_skinny<32, 384, false>(A, K, W, K, M, N, 0.f, EpiStoreF32{C, N}, s);
         if (K == 512) return launch_gemm_skinny<32, 512, false>(A, K, W, K, M, N, 0.f, EpiStoreF32{C, N}, s);
