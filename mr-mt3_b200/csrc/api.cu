@@ -26,6 +26,7 @@ Status api_transcribe_host(mrmt3_handle* h, const float* audio_host, long long n
                            int flags, int max_length, long long* out_ids_host, int* steps_host, cudaStream_t s);
 Status profile_collect(mrmt3_handle* h);
 Status trace_enable(mrmt3_handle* h, bool on);
+void drop_graphs(mrmt3_handle* h);
 Status test_gemm(mrmt3_handle* h, const bf16* A, const bf16* W, int M, int N, int K, float* C, int which, cudaStream_t s);
 }  // namespace mrmt3
 
@@ -109,6 +110,21 @@ int mrmt3_set_option(mrmt3_handle* h, const char* key, int value) {
     if (k == "group_lanes") h->group_lanes = value;
     else if (k == "use_graphs") h->use_graphs = value != 0;
     else if (k == "group_serial") h->group_serial = value != 0;
+    else if (k == "attn_variant" || k == "attn_ring_stages" || k == "attn_ring_ctas") {
+        // the kernel choice is baked into the captured step graphs
+        cudaSetDevice(h->device);
+        cudaDeviceSynchronize();
+        drop_graphs(h);
+        if (k == "attn_variant") attn_decode_configure(value ? 1 : 0, 0, 0);
+        else if (k == "attn_ring_stages") {
+            if (value != 2 && value != 3 && value != 4 && value != 6)
+                return finish(h, Error(2, "attn_ring_stages must be 2, 3, 4 or 6"));
+            attn_decode_configure(-1, value, 0);
+        } else {
+            if (value < 1 || value > 8) return finish(h, Error(2, "attn_ring_ctas must be in 1..8"));
+            attn_decode_configure(-1, 0, value);
+        }
+    }
     else return finish(h, Error(3, "unknown option: " + k));
     return 0;
     END_GUARD(h)

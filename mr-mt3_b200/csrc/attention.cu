@@ -10,6 +10,10 @@
 //                         appends the step's K/V; cross-attention reads the static cross cache.
 #include "attention.cuh"
 
+#include <cuda.h>
+
+#include <algorithm>
+
 namespace mrmt3 {
 
 // =============================================================================================
@@ -434,8 +438,322 @@ __global__ void __launch_bounds__(kDecThreads)
     trace_end(p.trace);
 }
 
+// =============================================================================================
+// decode-step attention, persistent TMA-ring + tensor-core variant (the default)
+//
+// The per-item kernel above is limited by wave quantisation (1536 CTAs in 1.73 waves of 888
+// register-limited slots), by the ramp of every CTA, and by the CUDA-core instruction stream
+// (bf16 -> fp32 unpacking plus one FMA per cache element).  This kernel removes all three:
+//
+//   * persistent grid: `ctas_per_sm` CTAs per SM walk the work items (lane, head) round-robin;
+//   * a producer warp streams K and V in 64-key chunks (two 32-row TMA boxes each, 128-byte
+//     swizzle, L2 evict-first) into an S-stage shared-memory ring guarded by full/empty
+//     mbarriers.  It runs ahead across item boundaries, so S x 16 KB per CTA are in flight at all
+//     times whatever the register pressure or occupancy of the math warps;
+//   * four math warps share every chunk: warp w owns keys [16w, 16w + 16) of it and computes
+//     s = q K^T and o += p V with mma.sync m16n8k16 (row 0 of the 16-row A tile carries the single
+//     query, the FlashAttention register trick turns the score fragment into the P fragment), fp32
+//     online softmax in registers: ~250 warp instructions per 16 KB chunk instead of ~800, so the
+//     math never limits the stream.  Every warp observes every phase of every stage barrier;
+//   * the four partial (m, l, o) states of an item are merged in fixed warp order through shared
+//     memory -- the result of a (lane, head) does not depend on what else is in the batch.
+//
+// The step's own K/V row (self-attention) is patched into the shared-memory tile from the fused
+// QKV row (the TMA box that covers it reads whatever the page holds at that row) and appended to
+// the cache page with plain stores.  Rows of a box past the valid keys are masked to p = 0; they
+// are cache memory that is zero-initialised at allocation and only ever holds finite values, so
+// 0 * v cannot produce a NaN.
+constexpr int kMmaChunk = 64;     // keys per ring stage
+constexpr int kMmaBox = 32;       // rows per TMA box
+constexpr int kMmaWarps = 4;      // math warps
+constexpr int kMmaThreads = (kMmaWarps + 1) * 32;
+constexpr int kMmaTileBytes = kMmaChunk * kDKV * (int)sizeof(bf16);  // 8 KB, K or V
+constexpr int kMmaStageBytes = 2 * kMmaTileBytes;
+constexpr int kMmaPartFloats = 2 + kDKV;                              // m, l, o[64]
+constexpr int kMmaMergeBytes = 2 * kMmaWarps * kMmaPartFloats * (int)sizeof(float);
+
+__device__ __forceinline__ void tma_box_load(uint32_t smem_dst, const CUtensorMap* map, int row, uint32_t bar,
+                                             uint64_t policy) {
+    asm volatile(
+        "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes.L2::cache_hint "
+        "[%0], [%1, {%2, %3}], [%4], %5;\n" ::"r"(smem_dst),
+        "l"(map), "r"(0), "r"(row), "r"(bar), "l"(policy)
+        : "memory");
+}
+
+struct MmaItem {
+    int n_keys, n_chunks;
+    long long k_row, v_row;  // tensor-map row of key 0 (cross) / of row 0 inside page 0 (paged)
+    const int* pages;
+};
+
+template <bool PAGED>
+__device__ __forceinline__ MmaItem mma_item(const AttnDecodeParams& p, int lane_id, int head, int pos) {
+    MmaItem it;
+    if (PAGED) {
+        it.n_keys = pos + 1;
+        it.pages = p.block_table + (size_t)lane_id * p.max_pages;
+        it.k_row = ((long long)(p.layer * 2 + 0) * kHeads + head) * kKVPage;
+        it.v_row = ((long long)(p.layer * 2 + 1) * kHeads + head) * kKVPage;
+    } else {
+        it.n_keys = p.n_keys_ptr ? p.n_keys_ptr[lane_id] : p.n_keys;
+        it.pages = nullptr;
+        it.k_row = p.tmap_row0 + ((((long long)lane_id * p.n_layers + p.layer) * 2 + 0) * kHeads + head) * p.tk_cap;
+        it.v_row = it.k_row + (long long)kHeads * p.tk_cap;
+    }
+    it.n_chunks = (it.n_keys + kMmaChunk - 1) / kMmaChunk;
+    return it;
+}
+
+template <bool PAGED, int S>
+__global__ void __launch_bounds__(kMmaThreads)
+    attn_decode_mma_kernel(const __grid_constant__ CUtensorMap tmap, AttnDecodeParams p, int n_lanes) {
+    extern __shared__ unsigned char mma_smem_raw[];
+    const uint32_t raw = smem_u32(mma_smem_raw);
+    const uint32_t base = (raw + 1023u) & ~1023u;  // SWIZZLE_128B tiles need 1024-B alignment
+    unsigned char* base_ptr = mma_smem_raw + (base - raw);
+    float* merge = reinterpret_cast<float*>(base_ptr + S * kMmaStageBytes);
+    const uint32_t full0 = base + S * kMmaStageBytes + kMmaMergeBytes;
+    const uint32_t empty0 = full0 + 8 * S;
+
+    trace_begin(p.trace);
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    if (tid == 0) {
+#pragma unroll
+        for (int s = 0; s < S; ++s) {
+            mbar_init(full0 + 8 * s, 1);
+            mbar_init(empty0 + 8 * s, kMmaWarps);
+        }
+        mbar_fence_init();
+        asm volatile("fence.proxy.async.shared::cta;\n" ::: "memory");
+    }
+    __syncthreads();
+
+    const int n_items = n_lanes * kHeads;
+    // `active`, `step` and the block table were written by kernels that completed before this one
+    // was launched (see attn_decode_kernel), so both roles may read them ahead of the PDL wait.
+    const int pos = PAGED ? p.step_ptr[0] + p.pos_offset : 0;
+    const long long rows_per_page = (long long)(p.page_stride / kDKV);
+
+    if (warp == kMmaWarps) {
+        // ---------------- producer ----------------
+        if (lane == 0) {
+            const uint64_t policy = l2_policy_evict_first();
+            int cnt = 0;
+            for (int item = blockIdx.x; item < n_items; item += gridDim.x) {
+                const int lane_id = item / kHeads, head = item - lane_id * kHeads;
+                if (p.active && !p.active[lane_id]) continue;
+                const MmaItem it = mma_item<PAGED>(p, lane_id, head, pos);
+                for (int c = 0; c < it.n_chunks; ++c, ++cnt) {
+                    const int s = cnt % S;
+                    mbar_wait(empty0 + 8 * s, ((cnt / S) & 1) ^ 1);
+                    const int first = c * kMmaChunk;
+                    const int n_box = (min(kMmaChunk, it.n_keys - first) + kMmaBox - 1) / kMmaBox;
+                    long long kr = it.k_row + first, vr = it.v_row + first;
+                    if (PAGED) {
+                        const long long pg = (long long)it.pages[first / kKVPage] * rows_per_page - (first / kKVPage) * kKVPage;
+                        kr += pg;
+                        vr += pg;
+                    }
+                    const uint32_t dst = base + s * kMmaStageBytes;
+                    const uint32_t bar = full0 + 8 * s;
+                    mbar_expect_tx(bar, (uint32_t)n_box * 2 * kMmaBox * kDKV * sizeof(bf16));
+                    for (int b = 0; b < n_box; ++b) {
+                        tma_box_load(dst + b * kMmaBox * kDKV * 2, &tmap, (int)(kr + b * kMmaBox), bar, policy);
+                        tma_box_load(dst + kMmaTileBytes + b * kMmaBox * kDKV * 2, &tmap, (int)(vr + b * kMmaBox), bar, policy);
+                    }
+                }
+            }
+        }
+        return;
+    }
+
+    // ---------------- math warps ----------------
+    pdl_wait();  // the producer kernel's q (and k, v) rows are complete and visible from here on
+    pdl_launch_dependents();
+    const float kLog2e = 1.4426950408889634f;
+    const int quad = lane & 3;
+
+    int cnt = 0, buf = 0;
+    for (int item = blockIdx.x; item < n_items; item += gridDim.x) {
+        const int lane_id = item / kHeads, head = item - lane_id * kHeads;
+        if (p.active && !p.active[lane_id]) continue;
+        const MmaItem it = mma_item<PAGED>(p, lane_id, head, pos);
+
+        // A fragments of q: row 0 of the 16 x 64 tile is the query, rows 1..15 are zero
+        const bf16* qrow = p.q + (size_t)lane_id * p.q_stride + head * kDKV;
+        uint32_t qf[4][4];
+#pragma unroll
+        for (int kk = 0; kk < 4; ++kk) {
+            qf[kk][0] = lane < 4 ? *reinterpret_cast<const uint32_t*>(qrow + kk * 16 + quad * 2) : 0u;
+            qf[kk][1] = 0u;
+            qf[kk][2] = lane < 4 ? *reinterpret_cast<const uint32_t*>(qrow + kk * 16 + 8 + quad * 2) : 0u;
+            qf[kk][3] = 0u;
+        }
+
+        float o[8][4];
+#pragma unroll
+        for (int i = 0; i < 8; ++i)
+#pragma unroll
+            for (int r = 0; r < 4; ++r) o[i][r] = 0.f;
+        float m_run = -INFINITY, l_run = 0.f;
+
+        const int kb = warp * 16;  // this warp's 16 keys of every 64-key chunk
+        for (int c = 0; c < it.n_chunks; ++c, ++cnt) {
+            const int s = cnt % S;
+            mbar_wait(full0 + 8 * s, (cnt / S) & 1);
+            const int k0 = c * kMmaChunk;
+            const int n_valid = min(kMmaChunk, it.n_keys - k0);
+            if (kb < n_valid) {
+                const uint32_t bk = base + s * kMmaStageBytes;
+                const uint32_t bv = bk + kMmaTileBytes;
+                if (PAGED && pos >= k0 + kb && pos < k0 + kb + 16) {
+                    // the step's K and V sit in the fused QKV row right after Q: patch them into
+                    // the tile and append them to the cache page for the steps to come
+                    const int r = pos - k0;
+                    if (lane < 16) {
+                        const int kv = lane >> 3, ch = lane & 7;
+                        const uint4 val = *reinterpret_cast<const uint4*>(qrow + kInner * (1 + kv) + ch * 8);
+                        unsigned char* tile = base_ptr + s * kMmaStageBytes + kv * kMmaTileBytes;
+                        *reinterpret_cast<uint4*>(tile + r * 128 + ((ch ^ (r & 7)) << 4)) = val;
+                        const size_t off = ((size_t)it.pages[pos / kKVPage] * rows_per_page +
+                                            (size_t)(kv ? it.v_row : it.k_row) + (pos % kKVPage)) * kDKV + ch * 8;
+                        *reinterpret_cast<uint4*>(const_cast<bf16*>(p.kv_pool) + off) = val;
+                    }
+                    __syncwarp();
+                }
+                // s = q K^T for this warp's 16 keys (row 0 of two 16 x 8 blocks)
+                float sc[2][4];
+#pragma unroll
+                for (int i = 0; i < 2; ++i)
+#pragma unroll
+                    for (int r = 0; r < 4; ++r) sc[i][r] = 0.f;
+#pragma unroll
+                for (int kk = 0; kk < 4; ++kk) {
+                    int row = kb + (lane & 7) + ((lane >> 4) << 3);
+                    int ch = kk * 2 + ((lane >> 3) & 1);
+                    uint32_t b0, b1, b2, b3;
+                    ldmatrix_x4(b0, b1, b2, b3, bk + row * 128 + ((ch ^ (row & 7)) << 4));
+                    mma_bf16_16816(sc[0], qf[kk], b0, b1);
+                    mma_bf16_16816(sc[1], qf[kk], b2, b3);
+                }
+                // mask + online softmax on row 0 (registers [0], [1]; the row lives in lanes 0..3,
+                // the other lanes carry the all-zero query rows and are never read)
+                float mx = -INFINITY;
+#pragma unroll
+                for (int ni = 0; ni < 2; ++ni) {
+                    const int key = kb + ni * 8 + quad * 2;
+                    sc[ni][0] = key < n_valid ? sc[ni][0] * kLog2e : -INFINITY;
+                    sc[ni][1] = key + 1 < n_valid ? sc[ni][1] * kLog2e : -INFINITY;
+                    mx = fmaxf(mx, fmaxf(sc[ni][0], sc[ni][1]));
+                }
+                mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, 1));
+                mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, 2));
+                const float m_new = fmaxf(m_run, mx);  // finite: key kb of the chunk is valid
+                const float corr = exp2f(m_run - m_new);
+                m_run = m_new;
+                const float p00 = exp2f(sc[0][0] - m_new), p01 = exp2f(sc[0][1] - m_new);
+                const float p10 = exp2f(sc[1][0] - m_new), p11 = exp2f(sc[1][1] - m_new);
+                l_run = l_run * corr + ((p00 + p01) + (p10 + p11));
+                uint32_t pf[4] = {pack_bf16(p00, p01), 0u, pack_bf16(p10, p11), 0u};
+#pragma unroll
+                for (int ni = 0; ni < 8; ++ni) {
+                    o[ni][0] *= corr;
+                    o[ni][1] *= corr;
+                }
+                // o += p V  (V tile is [key][d]; transposed ldmatrix gives the col-major B fragment)
+#pragma unroll
+                for (int nj = 0; nj < 4; ++nj) {
+                    int row = kb + (lane & 7) + (((lane >> 3) & 1) << 3);
+                    int ch = nj * 2 + (lane >> 4);
+                    uint32_t b0, b1, b2, b3;
+                    ldmatrix_x4_trans(b0, b1, b2, b3, bv + row * 128 + ((ch ^ (row & 7)) << 4));
+                    mma_bf16_16816(o[nj * 2], pf, b0, b1);
+                    mma_bf16_16816(o[nj * 2 + 1], pf, b2, b3);
+                }
+            }
+            // every ldmatrix of this stage has been consumed by an mma: hand the stage back
+            __syncwarp();
+            if (lane == 0) mbar_arrive(empty0 + 8 * s);
+        }
+
+        // merge the four warps' partial states in fixed order
+        l_run += __shfl_xor_sync(0xffffffffu, l_run, 1);
+        l_run += __shfl_xor_sync(0xffffffffu, l_run, 2);
+        float* part = merge + (buf * kMmaWarps + warp) * kMmaPartFloats;
+        if (lane < 4) {
+            if (lane == 0) {
+                part[0] = m_run;
+                part[1] = l_run;
+            }
+#pragma unroll
+            for (int ni = 0; ni < 8; ++ni)
+                *reinterpret_cast<float2*>(part + 2 + ni * 8 + quad * 2) = make_float2(o[ni][0], o[ni][1]);
+        }
+        named_bar_sync(1, kMmaWarps * 32);
+        if (warp == 0) {
+            const float* pb = merge + buf * kMmaWarps * kMmaPartFloats;
+            float mx = -INFINITY;
+#pragma unroll
+            for (int w = 0; w < kMmaWarps; ++w) mx = fmaxf(mx, pb[w * kMmaPartFloats]);
+            float den = 0.f, o0 = 0.f, o1 = 0.f;
+#pragma unroll
+            for (int w = 0; w < kMmaWarps; ++w) {
+                const float wgt = exp2f(pb[w * kMmaPartFloats] - mx);  // idle warp: exp2(-inf) = 0
+                den += pb[w * kMmaPartFloats + 1] * wgt;
+                const float2 ov = *reinterpret_cast<const float2*>(pb + w * kMmaPartFloats + 2 + lane * 2);
+                o0 += ov.x * wgt;
+                o1 += ov.y * wgt;
+            }
+            const float inv = 1.f / den;
+            *reinterpret_cast<uint32_t*>(p.out + (size_t)lane_id * p.out_stride + head * kDKV + lane * 2) =
+                pack_bf16(o0 * inv, o1 * inv);
+        }
+        buf ^= 1;  // the other half is free again once every warp has passed the next item's barrier
+    }
+    trace_end(p.trace);
+}
+
+static int g_attn_variant = 1;      // 0: one CTA per (lane, head), CUDA cores; 1: TMA ring + mma.sync
+static int g_ring_stages = 4;
+static int g_ring_ctas_per_sm = 1;
+
+void attn_decode_configure(int variant, int stages, int ctas_per_sm) {
+    if (variant >= 0) g_attn_variant = variant;
+    if (stages > 0) g_ring_stages = stages;
+    if (ctas_per_sm > 0) g_ring_ctas_per_sm = ctas_per_sm;
+}
+
+template <bool PAGED, int S>
+static Status launch_ring(const AttnDecodeParams& p, int n_lanes, cudaStream_t stream) {
+    if (!p.tmap) return Error(2, "attn_decode: the TMA variant needs a tensor map of the cache");
+    auto kern = attn_decode_mma_kernel<PAGED, S>;
+    constexpr int smem = S * kMmaStageBytes + kMmaMergeBytes + 2 * S * 8 + 1024;
+    static int n_sm_of[64] = {0};  // per device: SM count, 0 = attribute not set yet
+    int dev = 0;
+    MRMT3_CUDA_TRY(cudaGetDevice(&dev));
+    if (dev < 0 || dev >= 64) return Error(2, "device index out of range");
+    if (!n_sm_of[dev]) {
+        MRMT3_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+        MRMT3_CUDA_TRY(cudaDeviceGetAttribute(&n_sm_of[dev], cudaDevAttrMultiProcessorCount, dev));
+    }
+    const int grid = std::min(n_lanes * kHeads, n_sm_of[dev] * g_ring_ctas_per_sm);
+    MRMT3_TRY(launch_pdl(kern, dim3(grid), dim3(kMmaThreads), smem, stream,
+                         *reinterpret_cast<const CUtensorMap*>(p.tmap), p, n_lanes));
+    return OkStatus();
+}
+
 Status launch_attn_decode(const AttnDecodeParams& p, int n_lanes, bool paged, cudaStream_t stream) {
     if (n_lanes <= 0) return OkStatus();
+    if (g_attn_variant == 1) {
+        switch (g_ring_stages) {
+            case 2: return paged ? launch_ring<true, 2>(p, n_lanes, stream) : launch_ring<false, 2>(p, n_lanes, stream);
+            case 3: return paged ? launch_ring<true, 3>(p, n_lanes, stream) : launch_ring<false, 3>(p, n_lanes, stream);
+            case 4: return paged ? launch_ring<true, 4>(p, n_lanes, stream) : launch_ring<false, 4>(p, n_lanes, stream);
+            case 6: return paged ? launch_ring<true, 6>(p, n_lanes, stream) : launch_ring<false, 6>(p, n_lanes, stream);
+            default: return Error(2, "attn_ring_stages must be 2, 3, 4 or 6");
+        }
+    }
     dim3 grid(kHeads, n_lanes);
     if (paged)
         MRMT3_TRY(launch_pdl(attn_decode_kernel<true>, grid, dim3(kDecThreads), 0, stream, p));

@@ -50,9 +50,17 @@ struct AttnDecodeParams {
     const int* n_keys_ptr;   // optional per-lane key count
     // early-exit mask: lanes with active[lane] == 0 are skipped
     const int* active;
+    // TMA variant: host pointer to a CUtensorMap over the whole cache viewed as (rows, 64) bf16,
+    // box 32 x 64, 128-byte swizzle; tmap_row0 = row of kv_pool inside that view (cross cache of
+    // a lane group), 0 for the page pool
+    const void* tmap;
+    long long tmap_row0;
     TraceSlot trace;
 };
 Status launch_attn_decode(const AttnDecodeParams& p, int n_lanes, bool paged, cudaStream_t stream);
 int attn_decode_max_keys();
+// process-wide kernel selection: variant 0 = one CTA per (lane, head), 1 = persistent bulk-copy
+// ring (default); negative / zero arguments leave a setting unchanged
+void attn_decode_configure(int variant, int stages, int ctas_per_sm);
 
 }  // namespace mrmt3

@@ -127,6 +127,50 @@ __device__ __forceinline__ uint4 ld_stream16(const void* p) {
     return r;
 }
 
+// ---- mbarrier / bulk-copy (TMA) wrappers ------------------------------------------------------
+__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;\n" ::"r"(bar), "r"(count));
+}
+__device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;\n" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
+    uint32_t done;
+    do {
+        asm volatile(
+            "{\n"
+            ".reg .pred p;\n"
+            "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n"
+            "selp.u32 %0, 1, 0, p;\n"
+            "}\n"
+            : "=r"(done)
+            : "r"(bar), "r"(parity)
+            : "memory");
+    } while (!done);
+}
+__device__ __forceinline__ void mbar_arrive(uint32_t bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];\n" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void mbar_fence_init() { asm volatile("fence.mbarrier_init.release.cluster;\n" ::: "memory"); }
+__device__ __forceinline__ uint64_t l2_policy_evict_first() {
+    uint64_t pol;
+    asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;\n" : "=l"(pol));
+    return pol;
+}
+// 1-D bulk copy global -> shared (bytes % 16 == 0, both addresses 16-byte aligned); completion is
+// signalled on `bar` as `bytes` of transaction count
+__device__ __forceinline__ void bulk_load(uint32_t smem_dst, const void* gsrc, uint32_t bytes, uint32_t bar,
+                                          uint64_t policy) {
+    asm volatile(
+        "cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes.L2::cache_hint [%0], [%1], %2, [%3], %4;\n" ::"r"(
+            smem_dst),
+        "l"(gsrc), "r"(bytes), "r"(bar), "l"(policy)
+        : "memory");
+}
+__device__ __forceinline__ void named_bar_sync(int id, int n_threads) {
+    asm volatile("bar.sync %0, %1;\n" ::"r"(id), "r"(n_threads) : "memory");
+}
+
 inline int ceil_div(int a, int b) { return (a + b - 1) / b; }
 
 // ---- programmatic dependent launch (PDL) -----------------------------------------------------

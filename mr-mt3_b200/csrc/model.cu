@@ -192,6 +192,12 @@ Status handle_init(mrmt3_handle* h) {
     const char* ng = getenv("MRMT3_NO_GRAPH");
     h->use_graphs = !(ng && ng[0] == '1');
     if (const char* gl = getenv("MRMT3_GROUP_LANES")) h->group_lanes = atoi(gl);
+    {   // tuning sweeps (scripts/): decode-attention kernel selection
+        const char* av = getenv("MRMT3_ATTN_VARIANT");
+        const char* as = getenv("MRMT3_ATTN_STAGES");
+        const char* ac = getenv("MRMT3_ATTN_CTAS");
+        attn_decode_configure(av ? atoi(av) : -1, as ? atoi(as) : 0, ac ? atoi(ac) : 0);
+    }
     return OkStatus();
 }
 
@@ -200,6 +206,8 @@ static void destroy_graphs(mrmt3_handle* h) {
         if (kv.second.exec) cudaGraphExecDestroy(kv.second.exec);
     h->graphs.clear();
 }
+
+void drop_graphs(mrmt3_handle* h) { destroy_graphs(h); }
 
 Status test_gemm(mrmt3_handle* h, const bf16* A, const bf16* W, int M, int N, int K, float* C, int which,
                  cudaStream_t s) {
@@ -562,6 +570,10 @@ static Status ensure_decode_capacity(mrmt3_handle* h, int n_lanes, int tk, int m
     MRMT3_TRY(h->block_table.reserve(c * pgc * sizeof(int)));
 
     MRMT3_CUDA_TRY(cudaMemset(h->d_h32.p, 0, h->d_h32.cap));
+    // the TMA attention kernel loads whole 32-row boxes and masks the rows past the valid keys
+    // with p = 0: cache memory must never hold a NaN/Inf bit pattern
+    MRMT3_CUDA_TRY(cudaMemset(h->kv_pool.p, 0, h->kv_pool.cap));
+    MRMT3_CUDA_TRY(cudaMemset(h->cross_cache.p, 0, h->cross_cache.cap));
     MRMT3_CUDA_TRY(cudaMemset(h->d_state.p, 0, h->d_state.cap));
     MRMT3_CUDA_TRY(cudaMemset(h->lane_tab.p, 0, h->lane_tab.cap));
     // static page assignment: lane l owns pages [l*pgc, (l+1)*pgc)
@@ -596,6 +608,10 @@ static Status enqueue_step(mrmt3_handle* h, const StepPlan& pl, int kind, cudaSt
     bf16* qc = h->d_qc.as<bf16>() + l0 * kInner;
     bf16* ff = h->d_ff.as<bf16>() + l0 * kDFF;
     const size_t cross_lane = (size_t)h->cfg.n_dec_layers * 2 * kHeads * h->tk_cap * kDKV;
+    // tensor maps of the two caches viewed as (rows, 64) bf16 for the TMA attention kernel
+    const CUtensorMap *self_map = nullptr, *cross_map = nullptr;
+    MRMT3_TRY(h->tma->get(h->kv_pool.p, (long)(h->kv_pool.cap / (kDKV * sizeof(bf16))), kDKV, kDKV, 32, &self_map));
+    MRMT3_TRY(h->tma->get(h->cross_cache.p, (long)(h->cross_cache.cap / (kDKV * sizeof(bf16))), kDKV, kDKV, 32, &cross_map));
     int tslot = 0;
     auto next_trace = [&]() { return TraceSlot{h->trace_on ? h->trace_buf.as<unsigned long long>() : nullptr, tslot++}; };
     DecodeState st_embed = pl.st;
@@ -621,6 +637,8 @@ static Status enqueue_step(mrmt3_handle* h, const StepPlan& pl, int kind, cudaSt
         ap.max_pages = h->page_cap;
         ap.page_stride = page_elems(h);
         ap.active = pl.st.active;
+        ap.tmap = self_map;
+        ap.tmap_row0 = 0;
         ap.trace = next_trace();
         RUNC(h, MRMT3_PROF_ATTN_SELF, s, launch_attn_decode(ap, n, true, s));
         RUNC(h, MRMT3_PROF_GEMM_O, s, (launch_gemm_skinny<32, kInner, false>(
@@ -639,6 +657,8 @@ static Status enqueue_step(mrmt3_handle* h, const StepPlan& pl, int kind, cudaSt
         cp.tk_cap = h->tk_cap;
         cp.n_keys = pl.tk;
         cp.active = pl.st.active;
+        cp.tmap = cross_map;
+        cp.tmap_row0 = (long long)(l0 * cross_lane / kDKV);
         cp.trace = next_trace();
         RUNC(h, MRMT3_PROF_ATTN_CROSS, s, launch_attn_decode(cp, n, false, s));
         RUNC(h, MRMT3_PROF_GEMM_CO, s, (launch_gemm_skinny<32, kInner, false>(

@@ -202,6 +202,57 @@ def test_lane_groups_do_not_change_tokens(pkg):
     eng.set_option("group_lanes", 32)
 
 
+def test_tma_attention_matches_per_item_attention(pkg, feats):
+    """The two decode-attention kernels (TMA ring + mma.sync, and one CTA per (lane, head) on CUDA
+    cores with fp32 probabilities) fed the same tokens: logits within the rounding of the bf16
+    probabilities, for every ring depth / CTA count, across a KV page boundary (128) and several
+    64-key chunks.  The free-running tokens must agree wherever the top-2 margin is not tiny."""
+    model, _ = _model(pkg, 1239, eos_scale=2.0)
+    eng = model.engine()
+    x = syn.synthetic_features(11, 12).cuda()
+    try:
+        eng.set_option("attn_variant", 0)
+        want_tok = eng.generate(x, max_length=200)
+        forced = torch.zeros((12, 201), dtype=torch.int64)
+        forced[:, :want_tok.shape[1]] = want_tok.cpu()
+        _, want_logits = eng.generate(x, max_length=200, forced_ids=forced, return_logits=True)
+        eng.set_option("attn_variant", 1)
+        for stages, ctas in ((4, 2), (2, 1), (3, 3), (6, 1)):
+            eng.set_option("attn_ring_stages", stages)
+            eng.set_option("attn_ring_ctas", ctas)
+            _, got_logits = eng.generate(x, max_length=200, forced_ids=forced, return_logits=True)
+            err = (got_logits - want_logits).abs().max().item()
+            assert err < 0.03, (stages, ctas, err)
+            got_tok = eng.generate(x, max_length=200)
+            margins = top2_margin(want_logits.cpu())                      # (B, steps)
+            for r in range(12):
+                n = min(got_tok.shape[1], want_tok.shape[1])
+                d = first_divergence(got_tok[r, :n].cpu().numpy(), want_tok[r, :n].cpu().numpy())
+                assert d == n or float(margins[r, d - 1]) < 0.03, (stages, ctas, r, d)
+    finally:
+        eng.set_option("attn_variant", 1)
+        eng.set_option("attn_ring_stages", 4)
+        eng.set_option("attn_ring_ctas", 1)
+
+
+def test_tma_attention_more_items_than_ctas(pkg):
+    """Persistent CTAs walking several (lane, head) items each (ring running across item
+    boundaries), with finished lanes skipped: same tokens as one item per CTA."""
+    model, _ = _model(pkg, 1239, eos_scale=5.0)
+    eng = model.engine()
+    x = syn.synthetic_features(5, 64).cuda()
+    try:
+        eng.set_option("group_lanes", 0)
+        eng.set_option("attn_ring_ctas", 8)           # 64 * 6 = 384 items <= 8 * 148 CTAs
+        one = eng.generate(x, max_length=150)
+        eng.set_option("attn_ring_ctas", 1)           # 148 CTAs: 2-3 items each
+        many = eng.generate(x, max_length=150)
+        assert torch.equal(one, many)
+    finally:
+        eng.set_option("group_lanes", 32)
+        eng.set_option("attn_ring_ctas", 1)
+
+
 # ---- MR-MT3 -------------------------------------------------------------------------------------
 def test_memory_block(pkg):
     model, sd = _model(pkg, 4322, kind="v2p", eos_scale=3.0)
@@ -294,8 +345,9 @@ def test_full_size_batch_properties(pkg):
     model, _ = _model(pkg, 1234, eos_scale=5.0)
     x = syn.synthetic_features(3, 256).cuda()
     a = model.generate(x, max_length=1024)
-    b = model.generate(x, max_length=1024)
-    assert torch.equal(a, b)
+    for _ in range(4):                                       # lane groups run concurrently: no race
+        b = model.generate(x, max_length=1024)
+        assert torch.equal(a, b)
     sub = model.generate(x[100:164], max_length=1024)
     n = min(a.shape[1], sub.shape[1])
     assert torch.equal(a[100:164, :n], sub[:, :n])
