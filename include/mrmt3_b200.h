@@ -69,7 +69,8 @@ int64_t mrmt3_launch_count(const mrmt3_handle* h);
  * decoding lane group (0 = one group), "use_graphs" = replay the decode step as a CUDA graph,
  * "attn_variant" = decode attention kernel (1 = persistent TMA ring + mma.sync, the default;
  * 0 = one CTA per (lane, head) on CUDA cores), "attn_ring_stages" = ring depth of variant 1
- * (2, 3, 4 or 6 stages of 16 KB), "attn_ring_ctas" = its persistent CTAs per SM (1..8).  The
+ * (2, 3, 4 or 6 stages of 16 KB per warp quartet), "attn_ring_quartets" = 1 or 2 math-warp
+ * quartets per CTA, "attn_ring_ctas" = its persistent CTAs per SM (1..8, 0 = by launch size).  The
  * attention settings are process-wide. */
 int mrmt3_set_option(mrmt3_handle* h, const char* key, int value);
 

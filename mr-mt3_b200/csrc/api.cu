@@ -110,19 +110,23 @@ int mrmt3_set_option(mrmt3_handle* h, const char* key, int value) {
     if (k == "group_lanes") h->group_lanes = value;
     else if (k == "use_graphs") h->use_graphs = value != 0;
     else if (k == "group_serial") h->group_serial = value != 0;
-    else if (k == "attn_variant" || k == "attn_ring_stages" || k == "attn_ring_ctas") {
+    else if (k == "attn_variant" || k == "attn_ring_stages" || k == "attn_ring_ctas" || k == "attn_ring_quartets") {
         // the kernel choice is baked into the captured step graphs
         cudaSetDevice(h->device);
         cudaDeviceSynchronize();
         drop_graphs(h);
-        if (k == "attn_variant") attn_decode_configure(value ? 1 : 0, 0, 0);
+        if (k == "attn_variant") attn_decode_configure(value ? 1 : 0, 0, -1, 0);
+        else if (k == "attn_ring_quartets") {
+            if (value != 1 && value != 2) return finish(h, Error(2, "attn_ring_quartets must be 1 or 2"));
+            attn_decode_configure(-1, 0, -1, value);
+        }
         else if (k == "attn_ring_stages") {
             if (value != 2 && value != 3 && value != 4 && value != 6)
                 return finish(h, Error(2, "attn_ring_stages must be 2, 3, 4 or 6"));
-            attn_decode_configure(-1, value, 0);
+            attn_decode_configure(-1, value, -1, 0);
         } else {
-            if (value < 1 || value > 8) return finish(h, Error(2, "attn_ring_ctas must be in 1..8"));
-            attn_decode_configure(-1, 0, value);
+            if (value < 0 || value > 8) return finish(h, Error(2, "attn_ring_ctas must be in 0..8 (0 = automatic)"));
+            attn_decode_configure(-1, 0, value, 0);
         }
     }
     else return finish(h, Error(3, "unknown option: " + k));

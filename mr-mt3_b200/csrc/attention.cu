@@ -447,15 +447,17 @@ __global__ void __launch_bounds__(kDecThreads)
 //
 //   * persistent grid: `ctas_per_sm` CTAs per SM walk the work items (lane, head) round-robin;
 //   * a producer warp streams K and V in 64-key chunks (two 32-row TMA boxes each, 128-byte
-//     swizzle, L2 evict-first) into an S-stage shared-memory ring guarded by full/empty
-//     mbarriers.  It runs ahead across item boundaries, so S x 16 KB per CTA are in flight at all
-//     times whatever the register pressure or occupancy of the math warps;
-//   * four math warps share every chunk: warp w owns keys [16w, 16w + 16) of it and computes
-//     s = q K^T and o += p V with mma.sync m16n8k16 (row 0 of the 16-row A tile carries the single
-//     query, the FlashAttention register trick turns the score fragment into the P fragment), fp32
-//     online softmax in registers: ~250 warp instructions per 16 KB chunk instead of ~800, so the
-//     math never limits the stream.  Every warp observes every phase of every stage barrier;
-//   * the four partial (m, l, o) states of an item are merged in fixed warp order through shared
+//     swizzle, L2 evict-first) into a Q x S-stage shared-memory ring guarded by full/empty
+//     mbarriers.  It runs ahead across item boundaries, so Q S x 16 KB per CTA are in flight at
+//     all times whatever the register pressure or occupancy of the math warps;
+//   * Q = 1 or 2 quartets of math warps work on Q chunks at a time (chunk c of an item goes to
+//     quartet c % Q, which has its own S-stage sub-ring, so every warp observes every phase of the
+//     stage barriers it waits on).  Inside a quartet warp w owns keys [16w, 16w + 16) of the chunk and
+//     computes s = q K^T and o += p V with mma.sync m16n8k16 (row 0 of the 16-row A tile carries
+//     the single query, the FlashAttention register trick turns the score fragment into the P
+//     fragment), fp32 online softmax in registers: ~250 warp instructions per 16 KB chunk
+//     instead of ~800, and two warps per scheduler hide the ldmatrix -> mma -> shuffle chain;
+//   * the eight partial (m, l, o) states of an item are merged in fixed warp order through shared
 //     memory -- the result of a (lane, head) does not depend on what else is in the batch.
 //
 // The step's own K/V row (self-attention) is patched into the shared-memory tile from the fused
@@ -465,12 +467,11 @@ __global__ void __launch_bounds__(kDecThreads)
 // 0 * v cannot produce a NaN.
 constexpr int kMmaChunk = 64;     // keys per ring stage
 constexpr int kMmaBox = 32;       // rows per TMA box
-constexpr int kMmaWarps = 4;      // math warps
-constexpr int kMmaThreads = (kMmaWarps + 1) * 32;
+constexpr int kMmaMaxQuartets = 2;  // warp quartets (template parameter Q), each working on its own chunk
 constexpr int kMmaTileBytes = kMmaChunk * kDKV * (int)sizeof(bf16);  // 8 KB, K or V
 constexpr int kMmaStageBytes = 2 * kMmaTileBytes;
 constexpr int kMmaPartFloats = 2 + kDKV;                              // m, l, o[64]
-constexpr int kMmaMergeBytes = 2 * kMmaWarps * kMmaPartFloats * (int)sizeof(float);
+constexpr int kMmaMergeBytes = 2 * 4 * kMmaMaxQuartets * kMmaPartFloats * (int)sizeof(float);
 
 __device__ __forceinline__ void tma_box_load(uint32_t smem_dst, const CUtensorMap* map, int row, uint32_t bar,
                                              uint64_t policy) {
@@ -505,24 +506,26 @@ __device__ __forceinline__ MmaItem mma_item(const AttnDecodeParams& p, int lane_
     return it;
 }
 
-template <bool PAGED, int S>
-__global__ void __launch_bounds__(kMmaThreads)
+template <bool PAGED, int S, int Q>
+__global__ void __launch_bounds__((4 * Q + 1) * 32)
     attn_decode_mma_kernel(const __grid_constant__ CUtensorMap tmap, AttnDecodeParams p, int n_lanes) {
     extern __shared__ unsigned char mma_smem_raw[];
     const uint32_t raw = smem_u32(mma_smem_raw);
     const uint32_t base = (raw + 1023u) & ~1023u;  // SWIZZLE_128B tiles need 1024-B alignment
     unsigned char* base_ptr = mma_smem_raw + (base - raw);
-    float* merge = reinterpret_cast<float*>(base_ptr + S * kMmaStageBytes);
-    const uint32_t full0 = base + S * kMmaStageBytes + kMmaMergeBytes;
-    const uint32_t empty0 = full0 + 8 * S;
+    constexpr int kMmaQuartets = Q, kMmaWarps = 4 * Q;
+    constexpr int NS = S * kMmaQuartets;  // S stages per quartet
+    float* merge = reinterpret_cast<float*>(base_ptr + NS * kMmaStageBytes);
+    const uint32_t full0 = base + NS * kMmaStageBytes + kMmaMergeBytes;
+    const uint32_t empty0 = full0 + 8 * NS;
 
     trace_begin(p.trace);
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     if (tid == 0) {
 #pragma unroll
-        for (int s = 0; s < S; ++s) {
+        for (int s = 0; s < NS; ++s) {
             mbar_init(full0 + 8 * s, 1);
-            mbar_init(empty0 + 8 * s, kMmaWarps);
+            mbar_init(empty0 + 8 * s, 4);
         }
         mbar_fence_init();
         asm volatile("fence.proxy.async.shared::cta;\n" ::: "memory");
@@ -539,14 +542,16 @@ __global__ void __launch_bounds__(kMmaThreads)
         // ---------------- producer ----------------
         if (lane == 0) {
             const uint64_t policy = l2_policy_evict_first();
-            int cnt = 0;
+            int cnt0 = 0, cnt1 = 0;  // chunks handed to each quartet so far
             for (int item = blockIdx.x; item < n_items; item += gridDim.x) {
                 const int lane_id = item / kHeads, head = item - lane_id * kHeads;
                 if (p.active && !p.active[lane_id]) continue;
                 const MmaItem it = mma_item<PAGED>(p, lane_id, head, pos);
-                for (int c = 0; c < it.n_chunks; ++c, ++cnt) {
-                    const int s = cnt % S;
-                    mbar_wait(empty0 + 8 * s, ((cnt / S) & 1) ^ 1);
+                for (int c = 0; c < it.n_chunks; ++c) {
+                    const int qt = c & (kMmaQuartets - 1);
+                    const int n = qt ? cnt1++ : cnt0++;
+                    const int s = qt * S + n % S;
+                    mbar_wait(empty0 + 8 * s, ((n / S) & 1) ^ 1);
                     const int first = c * kMmaChunk;
                     const int n_box = (min(kMmaChunk, it.n_keys - first) + kMmaBox - 1) / kMmaBox;
                     long long kr = it.k_row + first, vr = it.v_row + first;
@@ -598,9 +603,10 @@ __global__ void __launch_bounds__(kMmaThreads)
             for (int r = 0; r < 4; ++r) o[i][r] = 0.f;
         float m_run = -INFINITY, l_run = 0.f;
 
-        const int kb = warp * 16;  // this warp's 16 keys of every 64-key chunk
-        for (int c = 0; c < it.n_chunks; ++c, ++cnt) {
-            const int s = cnt % S;
+        const int qt = warp >> 2;          // this warp's quartet: chunks with (c % 2) == qt
+        const int kb = (warp & 3) * 16;    // its 16 keys inside every such chunk
+        for (int c = qt; c < it.n_chunks; c += kMmaQuartets, ++cnt) {
+            const int s = qt * S + cnt % S;
             mbar_wait(full0 + 8 * s, (cnt / S) & 1);
             const int k0 = c * kMmaChunk;
             const int n_valid = min(kMmaChunk, it.n_keys - k0);
@@ -622,20 +628,35 @@ __global__ void __launch_bounds__(kMmaThreads)
                     }
                     __syncwarp();
                 }
-                // s = q K^T for this warp's 16 keys (row 0 of two 16 x 8 blocks)
-                float sc[2][4];
-#pragma unroll
-                for (int i = 0; i < 2; ++i)
-#pragma unroll
-                    for (int r = 0; r < 4; ++r) sc[i][r] = 0.f;
+                // all eight fragment loads of this warp's 16 keys up front: the V loads do not
+                // depend on the softmax and overlap the score mma chain
+                uint32_t kf[4][4], vf[4][4];
 #pragma unroll
                 for (int kk = 0; kk < 4; ++kk) {
                     int row = kb + (lane & 7) + ((lane >> 4) << 3);
                     int ch = kk * 2 + ((lane >> 3) & 1);
-                    uint32_t b0, b1, b2, b3;
-                    ldmatrix_x4(b0, b1, b2, b3, bk + row * 128 + ((ch ^ (row & 7)) << 4));
-                    mma_bf16_16816(sc[0], qf[kk], b0, b1);
-                    mma_bf16_16816(sc[1], qf[kk], b2, b3);
+                    ldmatrix_x4(kf[kk][0], kf[kk][1], kf[kk][2], kf[kk][3], bk + row * 128 + ((ch ^ (row & 7)) << 4));
+                }
+#pragma unroll
+                for (int nj = 0; nj < 4; ++nj) {
+                    int row = kb + (lane & 7) + (((lane >> 3) & 1) << 3);
+                    int ch = nj * 2 + (lane >> 4);
+                    ldmatrix_x4_trans(vf[nj][0], vf[nj][1], vf[nj][2], vf[nj][3],
+                                      bv + row * 128 + ((ch ^ (row & 7)) << 4));
+                }
+                // s = q K^T for this warp's 16 keys (row 0 of two 16 x 8 blocks); two independent
+                // accumulator pairs (dims 0-15|32-47 and 16-31|48-63) halve the dependent mma chain
+                float sc[2][4], sd[2][4];
+#pragma unroll
+                for (int i = 0; i < 2; ++i)
+#pragma unroll
+                    for (int r = 0; r < 4; ++r) sc[i][r] = sd[i][r] = 0.f;
+#pragma unroll
+                for (int kk = 0; kk < 4; kk += 2) {
+                    mma_bf16_16816(sc[0], qf[kk], kf[kk][0], kf[kk][1]);
+                    mma_bf16_16816(sc[1], qf[kk], kf[kk][2], kf[kk][3]);
+                    mma_bf16_16816(sd[0], qf[kk + 1], kf[kk + 1][0], kf[kk + 1][1]);
+                    mma_bf16_16816(sd[1], qf[kk + 1], kf[kk + 1][2], kf[kk + 1][3]);
                 }
                 // mask + online softmax on row 0 (registers [0], [1]; the row lives in lanes 0..3,
                 // the other lanes carry the all-zero query rows and are never read)
@@ -643,8 +664,8 @@ __global__ void __launch_bounds__(kMmaThreads)
 #pragma unroll
                 for (int ni = 0; ni < 2; ++ni) {
                     const int key = kb + ni * 8 + quad * 2;
-                    sc[ni][0] = key < n_valid ? sc[ni][0] * kLog2e : -INFINITY;
-                    sc[ni][1] = key + 1 < n_valid ? sc[ni][1] * kLog2e : -INFINITY;
+                    sc[ni][0] = key < n_valid ? (sc[ni][0] + sd[ni][0]) * kLog2e : -INFINITY;
+                    sc[ni][1] = key + 1 < n_valid ? (sc[ni][1] + sd[ni][1]) * kLog2e : -INFINITY;
                     mx = fmaxf(mx, fmaxf(sc[ni][0], sc[ni][1]));
                 }
                 mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, 1));
@@ -661,15 +682,11 @@ __global__ void __launch_bounds__(kMmaThreads)
                     o[ni][0] *= corr;
                     o[ni][1] *= corr;
                 }
-                // o += p V  (V tile is [key][d]; transposed ldmatrix gives the col-major B fragment)
+                // o += p V  (V tile is [key][d]; the transposed ldmatrix gave the col-major B fragment)
 #pragma unroll
                 for (int nj = 0; nj < 4; ++nj) {
-                    int row = kb + (lane & 7) + (((lane >> 3) & 1) << 3);
-                    int ch = nj * 2 + (lane >> 4);
-                    uint32_t b0, b1, b2, b3;
-                    ldmatrix_x4_trans(b0, b1, b2, b3, bv + row * 128 + ((ch ^ (row & 7)) << 4));
-                    mma_bf16_16816(o[nj * 2], pf, b0, b1);
-                    mma_bf16_16816(o[nj * 2 + 1], pf, b2, b3);
+                    mma_bf16_16816(o[nj * 2], pf, vf[nj][0], vf[nj][1]);
+                    mma_bf16_16816(o[nj * 2 + 1], pf, vf[nj][2], vf[nj][3]);
                 }
             }
             // every ldmatrix of this stage has been consumed by an mma: hand the stage back
@@ -677,7 +694,7 @@ __global__ void __launch_bounds__(kMmaThreads)
             if (lane == 0) mbar_arrive(empty0 + 8 * s);
         }
 
-        // merge the four warps' partial states in fixed order
+        // merge the eight warps' partial states in fixed order
         l_run += __shfl_xor_sync(0xffffffffu, l_run, 1);
         l_run += __shfl_xor_sync(0xffffffffu, l_run, 2);
         float* part = merge + (buf * kMmaWarps + warp) * kMmaPartFloats;
@@ -715,20 +732,22 @@ __global__ void __launch_bounds__(kMmaThreads)
 }
 
 static int g_attn_variant = 1;      // 0: one CTA per (lane, head), CUDA cores; 1: TMA ring + mma.sync
-static int g_ring_stages = 4;
-static int g_ring_ctas_per_sm = 1;
+static int g_ring_stages = 4;       // per warp quartet
+static int g_ring_ctas_per_sm = 0;  // 0 = by launch size (see launch_ring)
+static int g_ring_quartets = 1;
 
-void attn_decode_configure(int variant, int stages, int ctas_per_sm) {
+void attn_decode_configure(int variant, int stages, int ctas_per_sm, int quartets) {
     if (variant >= 0) g_attn_variant = variant;
     if (stages > 0) g_ring_stages = stages;
-    if (ctas_per_sm > 0) g_ring_ctas_per_sm = ctas_per_sm;
+    if (ctas_per_sm >= 0) g_ring_ctas_per_sm = ctas_per_sm;
+    if (quartets > 0) g_ring_quartets = quartets;
 }
 
-template <bool PAGED, int S>
+template <bool PAGED, int S, int Q>
 static Status launch_ring(const AttnDecodeParams& p, int n_lanes, cudaStream_t stream) {
     if (!p.tmap) return Error(2, "attn_decode: the TMA variant needs a tensor map of the cache");
-    auto kern = attn_decode_mma_kernel<PAGED, S>;
-    constexpr int smem = S * kMmaStageBytes + kMmaMergeBytes + 2 * S * 8 + 1024;
+    auto kern = attn_decode_mma_kernel<PAGED, S, Q>;
+    constexpr int smem = Q * S * kMmaStageBytes + kMmaMergeBytes + 2 * Q * S * 8 + 1024;
     static int n_sm_of[64] = {0};  // per device: SM count, 0 = attribute not set yet
     int dev = 0;
     MRMT3_CUDA_TRY(cudaGetDevice(&dev));
@@ -737,8 +756,15 @@ static Status launch_ring(const AttnDecodeParams& p, int n_lanes, cudaStream_t s
         MRMT3_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
         MRMT3_CUDA_TRY(cudaDeviceGetAttribute(&n_sm_of[dev], cudaDevAttrMultiProcessorCount, dev));
     }
-    const int grid = std::min(n_lanes * kHeads, n_sm_of[dev] * g_ring_ctas_per_sm);
-    MRMT3_TRY(launch_pdl(kern, dim3(grid), dim3(kMmaThreads), smem, stream,
+    // CTAs per SM: a launch of a 32-lane group (192 items, other groups' kernels running beside
+    // it) wants one light CTA per SM so that the projections of the other groups stay resident; a
+    // launch that has the GPU to itself (one group of 256 lanes = 1536 items) needs 2-3 CTAs per
+    // SM to keep enough bytes in flight
+    const int n_items = n_lanes * kHeads;
+    const int per_sm = g_ring_ctas_per_sm > 0 ? g_ring_ctas_per_sm
+                                              : std::max(1, std::min(3, n_items / (2 * n_sm_of[dev])));
+    const int grid = std::min(n_items, n_sm_of[dev] * per_sm);
+    MRMT3_TRY(launch_pdl(kern, dim3(grid), dim3((4 * Q + 1) * 32), smem, stream,
                          *reinterpret_cast<const CUtensorMap*>(p.tmap), p, n_lanes));
     return OkStatus();
 }
@@ -746,13 +772,19 @@ static Status launch_ring(const AttnDecodeParams& p, int n_lanes, cudaStream_t s
 Status launch_attn_decode(const AttnDecodeParams& p, int n_lanes, bool paged, cudaStream_t stream) {
     if (n_lanes <= 0) return OkStatus();
     if (g_attn_variant == 1) {
-        switch (g_ring_stages) {
-            case 2: return paged ? launch_ring<true, 2>(p, n_lanes, stream) : launch_ring<false, 2>(p, n_lanes, stream);
-            case 3: return paged ? launch_ring<true, 3>(p, n_lanes, stream) : launch_ring<false, 3>(p, n_lanes, stream);
-            case 4: return paged ? launch_ring<true, 4>(p, n_lanes, stream) : launch_ring<false, 4>(p, n_lanes, stream);
-            case 6: return paged ? launch_ring<true, 6>(p, n_lanes, stream) : launch_ring<false, 6>(p, n_lanes, stream);
-            default: return Error(2, "attn_ring_stages must be 2, 3, 4 or 6");
+#define MRMT3_RING(S_, Q_) \
+    return paged ? launch_ring<true, S_, Q_>(p, n_lanes, stream) : launch_ring<false, S_, Q_>(p, n_lanes, stream)
+        switch (g_ring_stages * 10 + g_ring_quartets) {
+            case 21: MRMT3_RING(2, 1);
+            case 31: MRMT3_RING(3, 1);
+            case 41: MRMT3_RING(4, 1);
+            case 61: MRMT3_RING(6, 1);
+            case 22: MRMT3_RING(2, 2);
+            case 32: MRMT3_RING(3, 2);
+            case 42: MRMT3_RING(4, 2);
+            default: return Error(2, "attn ring: stages per quartet must be 2, 3, 4 (or 6 with one quartet)");
         }
+#undef MRMT3_RING
     }
     dim3 grid(kHeads, n_lanes);
     if (paged)

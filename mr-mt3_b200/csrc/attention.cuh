@@ -61,6 +61,6 @@ Status launch_attn_decode(const AttnDecodeParams& p, int n_lanes, bool paged, cu
 int attn_decode_max_keys();
 // process-wide kernel selection: variant 0 = one CTA per (lane, head), 1 = persistent bulk-copy
 // ring (default); negative / zero arguments leave a setting unchanged
-void attn_decode_configure(int variant, int stages, int ctas_per_sm);
+void attn_decode_configure(int variant, int stages, int ctas_per_sm, int quartets);
 
 }  // namespace mrmt3

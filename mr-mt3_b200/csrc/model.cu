@@ -196,7 +196,8 @@ Status handle_init(mrmt3_handle* h) {
         const char* av = getenv("MRMT3_ATTN_VARIANT");
         const char* as = getenv("MRMT3_ATTN_STAGES");
         const char* ac = getenv("MRMT3_ATTN_CTAS");
-        attn_decode_configure(av ? atoi(av) : -1, as ? atoi(as) : 0, ac ? atoi(ac) : 0);
+        const char* aq = getenv("MRMT3_ATTN_QUARTETS");
+        attn_decode_configure(av ? atoi(av) : -1, as ? atoi(as) : 0, ac ? atoi(ac) : -1, aq ? atoi(aq) : 0);
     }
     return OkStatus();
 }

@@ -217,7 +217,7 @@ def test_tma_attention_matches_per_item_attention(pkg, feats):
         forced[:, :want_tok.shape[1]] = want_tok.cpu()
         _, want_logits = eng.generate(x, max_length=200, forced_ids=forced, return_logits=True)
         eng.set_option("attn_variant", 1)
-        for stages, ctas in ((4, 2), (2, 1), (3, 3), (6, 1)):
+        for stages, ctas in ((3, 1), (2, 2), (4, 0), (6, 1)):
             eng.set_option("attn_ring_stages", stages)
             eng.set_option("attn_ring_ctas", ctas)
             _, got_logits = eng.generate(x, max_length=200, forced_ids=forced, return_logits=True)
@@ -232,7 +232,7 @@ def test_tma_attention_matches_per_item_attention(pkg, feats):
     finally:
         eng.set_option("attn_variant", 1)
         eng.set_option("attn_ring_stages", 4)
-        eng.set_option("attn_ring_ctas", 1)
+        eng.set_option("attn_ring_ctas", 0)
 
 
 def test_tma_attention_more_items_than_ctas(pkg):
@@ -243,14 +243,16 @@ def test_tma_attention_more_items_than_ctas(pkg):
     x = syn.synthetic_features(5, 64).cuda()
     try:
         eng.set_option("group_lanes", 0)
-        eng.set_option("attn_ring_ctas", 8)           # 64 * 6 = 384 items <= 8 * 148 CTAs
+        eng.set_option("attn_ring_stages", 2)
+        eng.set_option("attn_ring_ctas", 3)           # 64 * 6 = 384 items <= 3 * 148 CTAs
         one = eng.generate(x, max_length=150)
         eng.set_option("attn_ring_ctas", 1)           # 148 CTAs: 2-3 items each
         many = eng.generate(x, max_length=150)
         assert torch.equal(one, many)
     finally:
         eng.set_option("group_lanes", 32)
-        eng.set_option("attn_ring_ctas", 1)
+        eng.set_option("attn_ring_stages", 4)
+        eng.set_option("attn_ring_ctas", 0)
 
 
 # ---- MR-MT3 -------------------------------------------------------------------------------------
