@@ -1,8 +1,8 @@
-"""Drop-in mirror of the reference's inference.py (`InferenceHandler`, :20-234) up to the token
-rows.  Token -> note-sequence -> MIDI decoding (contrib/metrics_utils.py, note_seq) is the next
-row of the scope table and is not part of this round: `inference()` returns the
-per-segment predictions (`est_tokens`, `start_time`) that the reference hands to
-`metrics_utils.event_predictions_to_ns` (inference.py:217-234).
+"""Drop-in mirror of the reference's inference.py (`InferenceHandler`, :20-234): framing, log-mel,
+batching, `generate`, post-processing of the token rows, and -- host-side, in `notes.py` -- the
+token -> note-sequence decoding the reference does through contrib/metrics_utils.py and note_seq
+(SURVEY 8f N1).  `inference()` returns the per-segment predictions (`est_tokens`, `start_time`)
+and, when `outpath` is given, writes the MIDI file like inference.py:195-201.
 
 Unlike the reference (inference.py:164,203-204) errors are raised, not swallowed.
 """
@@ -11,7 +11,7 @@ import math
 import numpy as np
 import torch
 
-from . import _lib, spectrograms
+from . import _lib, notes, spectrograms
 
 MIN_LOG_MEL = -12
 MAX_LOG_MEL = 5
@@ -39,6 +39,7 @@ class InferenceHandler:
         self.device = torch.device(device)
         self.model.to(self.device)
         self.mel_norm = mel_norm
+        self.codec = notes.build_codec(num_velocity_bins=1)      # inference.py:52-53
 
     # ---- host-side framing, identical to the reference ------------------------------------------
     def _audio_to_frames(self, audio):
@@ -121,7 +122,12 @@ class InferenceHandler:
                                          eos_token_id=self.model.config.eos_token_id,
                                          early_stopping=False, bad_words_ids=None, use_cache=False)
             results.append(self._postprocess_batch(result))
-        return self._to_predictions(results, frame_times)
+        predictions = self._to_predictions(results, frame_times)
+        if outpath is not None:
+            import os
+            os.makedirs(os.path.dirname(os.path.abspath(outpath)), exist_ok=True)
+            notes.note_sequence_to_midi_file(self._predictions_to_ns(predictions), outpath)
+        return predictions
 
     def _postprocess_batch(self, result):
         """Reference inference.py:206-215."""
@@ -142,6 +148,13 @@ class InferenceHandler:
                 start_time -= start_time % (1 / STEPS_PER_SECOND)
                 predictions.append({'est_tokens': tokens, 'start_time': start_time, 'raw_inputs': []})
         return predictions
+
+    def _predictions_to_ns(self, predictions):
+        return notes.event_predictions_to_ns(predictions, codec=self.codec)['est_ns']
+
+    def _to_event(self, predictions_np, frame_times):
+        """Reference inference.py:217-234: token rows -> combined NoteSequence (NoteEncodingWithTiesSpec)."""
+        return self._predictions_to_ns(self._to_predictions(predictions_np, frame_times))
 
     # ---- the B200 fast path: one C call from host audio to host token rows ----------------------
     @torch.no_grad()

@@ -94,9 +94,13 @@ def synthetic_state_dict(seed=1234, segmem=False, eos_scale=1.0, n_layers=8, n_d
     return sd
 
 
-def synthetic_audio(seed, n_samples, sample_rate=16000, n_tones=None, noise=1e-3, peak=0.5):
+def synthetic_audio(seed, n_samples, sample_rate=16000, n_tones=None, noise=1e-3, peak=0.5,
+                    return_notes=False):
     """Sum of harmonic tones (MIDI pitches ~U[36,96], 8 partials, 1/k amplitudes,
-    50-500 ms notes) + N(0, noise) -> float32 (n_samples,), |x| <= peak."""
+    50-500 ms notes) + N(0, noise) -> float32 (n_samples,), |x| <= peak.
+    return_notes: also return the rendered notes as (n, 3) float64 rows (onset s, offset s,
+    nearest MIDI pitch) -- the ground truth of the synthetic audio for the note-F1 checks."""
+    notes = []
     rng = np.random.default_rng(seed)
     t = np.arange(n_samples, dtype=np.float64) / sample_rate
     x = np.zeros(n_samples, dtype=np.float64)
@@ -111,6 +115,7 @@ def synthetic_audio(seed, n_samples, sample_rate=16000, n_tones=None, noise=1e-3
         env = ((t >= start) & (t < start + length)).astype(np.float64)
         env *= np.exp(-3.0 * np.clip(t - start, 0, None))
         amp = rng.uniform(0.2, 1.0)
+        notes.append((start, min(start + length, dur), float(int(round(pitch)))))
         for k in range(1, 9):
             if f0 * k < sample_rate / 2:
                 x += amp / k * env * np.sin(2 * math.pi * f0 * k * t + rng.uniform(0, 2 * math.pi))
@@ -118,6 +123,8 @@ def synthetic_audio(seed, n_samples, sample_rate=16000, n_tones=None, noise=1e-3
     m = np.abs(x).max()
     if m > 0:
         x *= peak / m
+    if return_notes:
+        return x.astype(np.float32), np.asarray(notes, dtype=np.float64).reshape(-1, 3)
     return x.astype(np.float32)
 
 

@@ -341,6 +341,42 @@ def test_transcribe_host_equals_staged_path(pkg):
     np.testing.assert_array_equal(fused, staged)
 
 
+def test_note_f1_unchanged_on_synthetic_rendered_audio(pkg):
+    """north_star: multi-instrument note F1 unchanged to 3 decimals.  Synthetic rendered audio (its
+    notes are the ground truth) -> CUDA path (fused e2e call) and CPU oracle -> token rows ->
+    notes (notes.py, pinned to the reference's decoder) -> evaluate.py scores at the reference's
+    three granularities (evaluate.py:16-22)."""
+    import importlib
+    inf = importlib.import_module("mr-mt3_b200.inference")
+    notes = importlib.import_module("mr-mt3_b200.notes")
+    ev = importlib.import_module("mr-mt3_b200.evaluate")
+    model, sd = _model(pkg, 4322, kind="v2p", eos_scale=6.0)
+    audio, truth = syn.synthetic_audio(seed=9, n_samples=4 * 32768 + 901, return_notes=True)
+    h = inf.InferenceHandler(model=model, mel_norm=True, contiguous_inference=True)
+    L = 48
+    got_rows = h.transcribe(audio, max_length=L).numpy()
+    mel, frame_times = O.preprocess(audio, mel_norm=True)
+    want_rows, traces = O.generate_segmem_v2_with_prev_cached(torch.from_numpy(mel), sd, max_length=L,
+                                                               return_trace=True)
+    want_rows = want_rows.numpy()
+    _check_tokens(got_rows, want_rows, None if traces is None else traces, "e2e vs oracle")
+    ref_ns = notes.NoteSequence()
+    for on, off, pitch in truth:
+        ref_ns.notes.append(notes.Note(on, off, int(pitch), 100, 0, False))
+    ft = np.asarray(frame_times).reshape(len(got_rows), -1)
+    ns_got = notes.event_predictions_to_ns(notes.token_rows_to_predictions(got_rows, ft))['est_ns']
+    ns_want = notes.event_predictions_to_ns(notes.token_rows_to_predictions(want_rows, ft))['est_ns']
+    for gran in ("flat", "midi_class", "full"):
+        a = ev.program_aware_note_scores(ref_ns, ns_got, gran)
+        b = ev.program_aware_note_scores(ref_ns, ns_want, gran)
+        for k in a:
+            if k != "F1 by program":
+                assert round(a[k], 3) == round(b[k], 3), (gran, k, a[k], b[k])
+    if np.array_equal(got_rows, want_rows) and len(ns_want.notes):
+        same = ev.program_aware_note_scores(ns_want, ns_got, "full")
+        assert same["Onset + program F1 (full)"] == 1.0
+
+
 def test_full_size_batch_properties(pkg):
     """BASELINE config 2 size (256 segments, 1024 tokens): determinism and row independence --
     a row's tokens must not depend on which other rows share its batch."""
