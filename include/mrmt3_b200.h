@@ -66,7 +66,7 @@ const char* mrmt3_last_error(const mrmt3_handle* h);
 int64_t mrmt3_launch_count(const mrmt3_handle* h);
 
 /* Tuning knobs (all have working defaults).  key: "group_lanes" = lanes per concurrently
- * decoding lane group (0 = one group), "use_graphs" = replay the decode step as a CUDA graph,
+ * decoding lane group (0 = one group, negative = by batch size: the default), "use_graphs" = replay the decode step as a CUDA graph,
  * "attn_variant" = decode attention kernel (1 = persistent TMA ring + mma.sync, the default;
  * 0 = one CTA per (lane, head) on CUDA cores), "attn_ring_stages" = ring depth of variant 1
  * (2, 3, 4 or 6 stages of 16 KB per warp quartet), "attn_ring_quartets" = 1 or 2 math-warp

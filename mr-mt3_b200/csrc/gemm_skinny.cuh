@@ -13,6 +13,8 @@
 // sees complete rows, computes sum(x^2) from its shared A tiles and scales the accumulators by
 // rsqrt(mean + eps) in the epilogue:  (x * r * g) W^T == r * (x (W g)^T).
 #pragma once
+#include <type_traits>
+
 #include "gemm_mma.cuh"
 
 namespace mrmt3 {
@@ -22,6 +24,19 @@ struct EpiResidualBoth {
     float* H;
     bf16* Hb;
     int ldh;
+    // the residual values can be fetched before the k loop: the L2 round trip of H then overlaps
+    // the operand loads instead of sitting between the last mma and the store
+    static constexpr bool kPrefetch = true;
+    __device__ __forceinline__ float2 load(int row, int col) const {
+        return *reinterpret_cast<const float2*>(H + (size_t)row * ldh + col);
+    }
+    __device__ __forceinline__ void store(int row, int col, float2 h, float v0, float v1) const {
+        size_t o = (size_t)row * ldh + col;
+        h.x += v0;
+        h.y += v1;
+        *reinterpret_cast<float2*>(H + o) = h;
+        *reinterpret_cast<uint32_t*>(Hb + o) = pack_bf16(h.x, h.y);
+    }
     __device__ __forceinline__ void operator()(int row, int col, float v0, float v1) const {
         size_t o = (size_t)row * ldh + col;
         float2* p = reinterpret_cast<float2*>(H + o);
@@ -32,6 +47,11 @@ struct EpiResidualBoth {
         *reinterpret_cast<uint32_t*>(Hb + o) = pack_bf16(h.x, h.y);
     }
 };
+
+template <class Epi, class = void>
+struct EpiPrefetches : std::false_type {};
+template <class Epi>
+struct EpiPrefetches<Epi, std::enable_if_t<Epi::kPrefetch>> : std::true_type {};
 
 __device__ __forceinline__ void cp_async_wait_dyn(int n) {
     switch (n) {
@@ -111,6 +131,16 @@ __global__ void __launch_bounds__(128)
 #pragma unroll
         for (int r = 0; r < 4; ++r) acc[j][r] = 0.f;
     float ss = 0.f;  // NORM: partial sum of squares of row tid/4
+    float2 pre[NI][2];
+    if constexpr (EpiPrefetches<Epi>::value) {
+#pragma unroll
+        for (int ni = 0; ni < NI; ++ni) {
+            const int row = m0 + wm0 + (lane >> 2);
+            const int col = n0 + wn0 + ni * 8 + (lane & 3) * 2;
+            pre[ni][0] = row < M ? epi.load(row, col) : make_float2(0.f, 0.f);
+            pre[ni][1] = row + 8 < M ? epi.load(row + 8, col) : make_float2(0.f, 0.f);
+        }
+    }
 
 #pragma unroll
     for (int kt = 0; kt < KT; ++kt) {
@@ -169,8 +199,13 @@ __global__ void __launch_bounds__(128)
     for (int ni = 0; ni < NI; ++ni) {
         int row = m0 + wm0 + (lane >> 2);
         int col = n0 + wn0 + ni * 8 + (lane & 3) * 2;
-        if (row < M) epi(row, col, acc[ni][0] * sc0, acc[ni][1] * sc0);
-        if (row + 8 < M) epi(row + 8, col, acc[ni][2] * sc1, acc[ni][3] * sc1);
+        if constexpr (EpiPrefetches<Epi>::value) {
+            if (row < M) epi.store(row, col, pre[ni][0], acc[ni][0] * sc0, acc[ni][1] * sc0);
+            if (row + 8 < M) epi.store(row + 8, col, pre[ni][1], acc[ni][2] * sc1, acc[ni][3] * sc1);
+        } else {
+            if (row < M) epi(row, col, acc[ni][0] * sc0, acc[ni][1] * sc0);
+            if (row + 8 < M) epi(row + 8, col, acc[ni][2] * sc1, acc[ni][3] * sc1);
+        }
     }
     trace_end(trace);
 }

@@ -747,8 +747,11 @@ static DecodeState group_state(const DecodeState& st, int lane0, int group) {
 static Status run_decode(mrmt3_handle* h, StepPlan pl, int n_prefix, bool debug_mode, cudaStream_t s) {
     const bool graphs = h->use_graphs && !debug_mode && !h->prof_on;
     int G = 1;
-    if (!debug_mode && !h->prof_on && h->group_lanes > 0)
-        G = std::min(kMaxGroups, ceil_div(pl.n_lanes, h->group_lanes));
+    // default group size (group_lanes < 0): 32 lanes, 16 for small batches (MR-MT3 with one lane per
+    // track: 64 tracks decode fastest as 4 groups; more groups than that only add launches)
+    const int gl = h->group_lanes >= 0 ? h->group_lanes : (pl.n_lanes <= 64 ? 16 : 32);
+    if (!debug_mode && !h->prof_on && gl > 0)
+        G = std::min(kMaxGroups, ceil_div(pl.n_lanes, gl));
     const int per = ceil_div(pl.n_lanes, G);
     G = ceil_div(pl.n_lanes, per);
     std::vector<StepPlan> gp(G);

@@ -136,7 +136,7 @@ struct mrmt3_handle {
     cudaEvent_t poll_ev[2] = {nullptr, nullptr};
     // lane groups: independent greedy loops on their own streams so that one group's
     // latency-bound projections overlap another group's HBM-bound attention
-    int group_lanes = 32;
+    int group_lanes = -1;            // < 0: by batch size (run_decode)
     bool group_serial = false;
     mrmt3::DeviceBuffer trace_buf;       // 2 x u64 per decode-step kernel slot (mrmt3_trace_*)
     bool trace_on = false;           // debugging: run the groups one after another on one stream

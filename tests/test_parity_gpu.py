@@ -199,7 +199,7 @@ def test_lane_groups_do_not_change_tokens(pkg):
         eng.set_option("group_lanes", gl)
         many = eng.generate(x, max_length=96)
         assert torch.equal(one, many), gl
-    eng.set_option("group_lanes", 32)
+    eng.set_option("group_lanes", -1)
 
 
 def test_tma_attention_matches_per_item_attention(pkg, feats):
@@ -250,7 +250,7 @@ def test_tma_attention_more_items_than_ctas(pkg):
         many = eng.generate(x, max_length=150)
         assert torch.equal(one, many)
     finally:
-        eng.set_option("group_lanes", 32)
+        eng.set_option("group_lanes", -1)
         eng.set_option("attn_ring_stages", 4)
         eng.set_option("attn_ring_ctas", 0)
 
@@ -308,7 +308,7 @@ def test_segmem_tracks_equal_per_track_calls(pkg):
     eng = model.engine()
     eng.set_option("group_lanes", 2)                        # 3 tracks -> 2 lane groups
     batched = eng.generate_segmem(x, counts, max_length=48).cpu().numpy()
-    eng.set_option("group_lanes", 32)
+    eng.set_option("group_lanes", -1)
     off = 0
     for c in counts:
         single = eng.generate_segmem(x[off:off + c], [c], max_length=48).cpu().numpy()
