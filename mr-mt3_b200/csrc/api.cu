@@ -148,7 +148,7 @@ int mrmt3_trace_read(mrmt3_handle* h, uint64_t* out, int max_slots) {
     if (!h->trace_buf.p || !out) return 0;
     cudaSetDevice(h->device);
     cudaDeviceSynchronize();
-    int n = std::min(max_slots, 256);
+    int n = std::min(max_slots, 512);
     if (cudaMemcpy(out, h->trace_buf.p, (size_t)n * 16, cudaMemcpyDeviceToHost) != cudaSuccess) return 0;
     return n;
     END_GUARD(h)

@@ -575,6 +575,7 @@ __global__ void __launch_bounds__((4 * Q + 1) * 32)
 
     // ---------------- math warps ----------------
     pdl_wait();  // the producer kernel's q (and k, v) rows are complete and visible from here on
+    trace_mark(p.trace, 0);
     pdl_launch_dependents();
     const float kLog2e = 1.4426950408889634f;
     const int quad = lane & 3;

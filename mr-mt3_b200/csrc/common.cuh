@@ -202,6 +202,12 @@ __device__ __forceinline__ void trace_begin(const TraceSlot& t) {
     if (t.buf && threadIdx.x == 0 && blockIdx.x == 0 && blockIdx.y == 0 && blockIdx.z == 0)
         t.buf[2 * t.slot] = global_timer();
 }
+// optional intermediate stamps of CTA 0 (which = 0: dependency wait returned, 1: operands in shared
+// memory); they live in the upper half of the trace buffer (slot + 128)
+__device__ __forceinline__ void trace_mark(const TraceSlot& t, int which) {
+    if (t.buf && threadIdx.x == 0 && blockIdx.x == 0 && blockIdx.y == 0 && blockIdx.z == 0)
+        t.buf[2 * (t.slot + 128 * (1 + (which >> 1))) + (which & 1)] = global_timer();
+}
 __device__ __forceinline__ void trace_end(const TraceSlot& t) {
     if (t.buf && threadIdx.x == 0) atomicMax(t.buf + 2 * t.slot + 1, global_timer());
 }

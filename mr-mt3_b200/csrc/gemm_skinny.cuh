@@ -16,6 +16,7 @@
 #include <type_traits>
 
 #include "gemm_mma.cuh"
+#include "tma.cuh"
 
 namespace mrmt3 {
 
@@ -76,16 +77,19 @@ __device__ __forceinline__ void cp_async_wait_dyn(int n) {
 
 template <int BN, int K, bool NORM, class Epi>
 __global__ void __launch_bounds__(128)
-    gemm_skinny_kernel(const bf16* __restrict__ A, int lda, const bf16* __restrict__ W, int ldw, int M,
+    gemm_skinny_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant__ CUtensorMap tm_w, int M,
                        float eps, Epi epi, TraceSlot trace) {
     constexpr int BM = 32;
     trace_begin(trace);
     constexpr int KT = K / 64;
     constexpr int NI = BN / 16;  // n-blocks of 8 per warp (warp tile 16 x BN/2)
     static_assert(KT <= 16, "K too large for the single-shot pipeline");
-    extern __shared__ __align__(128) unsigned char smem_raw[];
-    bf16* sA = reinterpret_cast<bf16*>(smem_raw);   // [KT][BM*64]
+    extern __shared__ unsigned char smem_raw[];
+    // 128-byte-swizzled TMA tiles need 1024-byte alignment
+    unsigned char* smem_al = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
+    bf16* sA = reinterpret_cast<bf16*>(smem_al);    // [KT][BM*64]
     bf16* sW = sA + KT * BM * 64;                   // [KT][BN*64]
+    const uint32_t bars = smem_u32(sW + KT * BN * 64);  // KT mbarriers, one per k-tile
     __shared__ float s_scale[BM];
 
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
@@ -94,42 +98,45 @@ __global__ void __launch_bounds__(128)
     const int m0 = blockIdx.y * BM;
     const int n0 = blockIdx.x * BN;
 
-    // Issue every load of this CTA, one commit group per k-tile.  The weight tiles do not depend
-    // on the producer kernel, so they are requested before the programmatic-dependency wait and
-    // their latency overlaps the producer's tail; the activation tiles follow the wait.
+    // Every operand byte of this CTA is requested up front with TMA box loads (one 64-wide k-tile
+    // of W and of A per mbarrier): a handful of bulk requests instead of ~50 cp.async per thread,
+    // whose per-SM request tracking limits a CTA to ~30 GB/s (measured: 2-2.5 us for 100 KB; see
+    // DESIGN.md).  The weight tiles do not depend on the producer kernel, so they are requested
+    // before the programmatic-dependency wait and their latency overlaps the producer's tail; the
+    // activation tiles follow the wait.  Rows past M are zero-filled by the tensor map.
+    if (tid == 0) {
 #pragma unroll
-    for (int kt = 0; kt < KT; ++kt) {
-        const int k0 = kt * 64;
+        for (int kt = 0; kt < KT; ++kt) mbar_init(bars + 8 * kt, 2);
+        mbar_fence_init();
+        asm volatile("fence.proxy.async.shared::cta;\n" ::: "memory");
 #pragma unroll
-        for (int i = 0; i < (BN * 8) / 128; ++i) {
-            int c = tid + i * 128;
-            int row = c >> 3, ch = c & 7;
-            cp_async16(sW + kt * BN * 64 + row * 64 + ((ch ^ (row & 7)) << 3),
-                       W + (size_t)(n0 + row) * ldw + k0 + ch * 8, true);
+        for (int kt = 0; kt < KT; ++kt) {
+            mbar_expect_tx(bars + 8 * kt, BN * 128);
+            tma_load_2d(smem_u32(sW + kt * BN * 64), &tm_w, kt * 64, n0, bars + 8 * kt);
         }
-        cp_async_commit();
     }
     pdl_wait();
+    trace_mark(trace, 0);
     pdl_launch_dependents();
+    if (tid == 0) {
 #pragma unroll
-    for (int kt = 0; kt < KT; ++kt) {
-        const int k0 = kt * 64;
-#pragma unroll
-        for (int i = 0; i < (BM * 8) / 128; ++i) {
-            int c = tid + i * 128;
-            int row = c >> 3, ch = c & 7;
-            bool pred = (m0 + row) < M;
-            cp_async16(sA + kt * BM * 64 + row * 64 + ((ch ^ (row & 7)) << 3),
-                       A + (size_t)(pred ? m0 + row : 0) * lda + k0 + ch * 8, pred);
+        for (int kt = 0; kt < KT; ++kt) {
+            mbar_expect_tx(bars + 8 * kt, BM * 128);
+            tma_load_2d(smem_u32(sA + kt * BM * 64), &tm_a, kt * 64, m0, bars + 8 * kt);
         }
-        cp_async_commit();
     }
+    __syncthreads();  // barrier initialisation is visible to every waiter
 
-    float acc[NI][4];
+    // four independent accumulator sets, one per 16-wide k step of a k-tile: the dependent
+    // mma -> mma chain of an output fragment is K/64 long instead of K/16 (the chain, not the
+    // tensor pipe, is what a single 4-warp CTA waits on); they are summed in fixed order at the end
+    float accs[4][NI][4];
 #pragma unroll
-    for (int j = 0; j < NI; ++j)
+    for (int q = 0; q < 4; ++q)
 #pragma unroll
-        for (int r = 0; r < 4; ++r) acc[j][r] = 0.f;
+        for (int j = 0; j < NI; ++j)
+#pragma unroll
+            for (int r = 0; r < 4; ++r) accs[q][j][r] = 0.f;
     float ss = 0.f;  // NORM: partial sum of squares of row tid/4
     float2 pre[NI][2];
     if constexpr (EpiPrefetches<Epi>::value) {
@@ -144,10 +151,32 @@ __global__ void __launch_bounds__(128)
 
 #pragma unroll
     for (int kt = 0; kt < KT; ++kt) {
-        cp_async_wait_dyn(KT - 1 - kt);
-        __syncthreads();
+        mbar_wait(bars + 8 * kt, 0);
+        if (kt == 0) trace_mark(trace, 2);
+        if (kt == KT / 2) trace_mark(trace, 3);
+        if (kt == KT - 1) trace_mark(trace, 1);
         const uint32_t baseA = smem_u32(sA + kt * BM * 64);
         const uint32_t baseW = smem_u32(sW + kt * BN * 64);
+        // all fragment loads of the k-tile first, then the math: issued back to back the ldmatrix
+        // latencies overlap (interleaved with their mma, every 16-wide k step paid one in full:
+        // 220-440 cycles per k-tile, measured with the in-kernel trace stamps)
+        uint32_t af[4][4], wf[4][NI / 2][4];
+#pragma unroll
+        for (int kk = 0; kk < 4; ++kk) {
+            int row = wm0 + (lane & 15);
+            int ch = kk * 2 + (lane >> 4);
+            ldmatrix_x4(af[kk][0], af[kk][1], af[kk][2], af[kk][3], baseA + row * 128 + ((ch ^ (row & 7)) << 4));
+        }
+#pragma unroll
+        for (int kk = 0; kk < 4; ++kk) {
+#pragma unroll
+            for (int nj = 0; nj < NI / 2; ++nj) {
+                int row = wn0 + nj * 16 + (lane & 7) + ((lane >> 4) << 3);
+                int ch = kk * 2 + ((lane >> 3) & 1);
+                ldmatrix_x4(wf[kk][nj][0], wf[kk][nj][1], wf[kk][nj][2], wf[kk][nj][3],
+                            baseW + row * 128 + ((ch ^ (row & 7)) << 4));
+            }
+        }
         if (NORM) {
             // 4 threads per row, 2 of the 8 16-byte chunks each.  The chunks are addressed
             // LOGICALLY (un-swizzled), so the order of the fp32 sum -- and with it the result --
@@ -168,23 +197,19 @@ __global__ void __launch_bounds__(128)
         }
 #pragma unroll
         for (int kk = 0; kk < 4; ++kk) {
-            uint32_t af[4];
-            {
-                int row = wm0 + (lane & 15);
-                int ch = kk * 2 + (lane >> 4);
-                ldmatrix_x4(af[0], af[1], af[2], af[3], baseA + row * 128 + ((ch ^ (row & 7)) << 4));
-            }
 #pragma unroll
             for (int nj = 0; nj < NI / 2; ++nj) {
-                int row = wn0 + nj * 16 + (lane & 7) + ((lane >> 4) << 3);
-                int ch = kk * 2 + ((lane >> 3) & 1);
-                uint32_t b0, b1, b2, b3;
-                ldmatrix_x4(b0, b1, b2, b3, baseW + row * 128 + ((ch ^ (row & 7)) << 4));
-                mma_bf16_16816(acc[nj * 2], af, b0, b1);
-                mma_bf16_16816(acc[nj * 2 + 1], af, b2, b3);
+                mma_bf16_16816(accs[kk][nj * 2], af[kk], wf[kk][nj][0], wf[kk][nj][1]);
+                mma_bf16_16816(accs[kk][nj * 2 + 1], af[kk], wf[kk][nj][2], wf[kk][nj][3]);
             }
         }
     }
+
+    float acc[NI][4];
+#pragma unroll
+    for (int j = 0; j < NI; ++j)
+#pragma unroll
+        for (int r = 0; r < 4; ++r) acc[j][r] = (accs[0][j][r] + accs[1][j][r]) + (accs[2][j][r] + accs[3][j][r]);
 
     float sc0 = 1.f, sc1 = 1.f;
     if (NORM) {
@@ -211,20 +236,23 @@ __global__ void __launch_bounds__(128)
 }
 
 template <int BN, int K, bool NORM, class Epi>
-Status launch_gemm_skinny(const bf16* A, int lda, const bf16* W, int ldw, int M, int N, float eps,
+Status launch_gemm_skinny(TmaCache& tc, const bf16* A, int lda, const bf16* W, int ldw, int M, int N, float eps,
                           const Epi& epi, cudaStream_t stream, TraceSlot trace = TraceSlot{nullptr, 0}) {
     if (M <= 0) return OkStatus();
     if (N % BN != 0) return Error(2, "gemm_skinny: N must be a multiple of the column tile");
     static_assert(!NORM || K == kDModel, "fused RMSNorm needs complete rows: K == d_model");
     auto kern = gemm_skinny_kernel<BN, K, NORM, Epi>;
-    constexpr int smem = (32 + BN) * K * (int)sizeof(bf16);
+    constexpr int smem = (32 + BN) * K * (int)sizeof(bf16) + (K / 64) * 8 + 1024;
     static bool attr_set = false;
     if (!attr_set) {
         MRMT3_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
         attr_set = true;
     }
+    const CUtensorMap *ma = nullptr, *mw = nullptr;
+    MRMT3_TRY(tc.get(A, M, K, lda, 32, &ma));
+    MRMT3_TRY(tc.get(W, N, K, ldw, BN, &mw));
     dim3 grid(N / BN, ceil_div(M, 32));
-    MRMT3_TRY(launch_pdl(kern, grid, dim3(128), smem, stream, A, lda, W, ldw, M, eps, epi, trace));
+    MRMT3_TRY(launch_pdl(kern, grid, dim3(128), smem, stream, *ma, *mw, M, eps, epi, trace));
     return OkStatus();
 }
 

@@ -219,9 +219,9 @@ Status test_gemm(mrmt3_handle* h, const bf16* A, const bf16* W, int M, int N, in
     if (which == 3)  // tcgen05 with the bf16 store epilogue the encoder uses (C holds M*N bf16)
         return launch_gemm_tc(*h->tma, A, K, M, id, W, K, M, N, K, EpiStoreBf16{reinterpret_cast<bf16*>(C), N}, s);
     if (which == 2) {
-        if (K == 384) return launch_gemm_skinny<32, 384, false>(A, K, W, K, M, N, 0.f, EpiStoreF32{C, N}, s);
-        if (K == 512) return launch_gemm_skinny<32, 512, false>(A, K, W, K, M, N, 0.f, EpiStoreF32{C, N}, s);
-        if (K == 1024) return launch_gemm_skinny<32, 1024, false>(A, K, W, K, M, N, 0.f, EpiStoreF32{C, N}, s);
+        if (K == 384) return launch_gemm_skinny<32, 384, false>(*h->tma, A, K, W, K, M, N, 0.f, EpiStoreF32{C, N}, s);
+        if (K == 512) return launch_gemm_skinny<32, 512, false>(*h->tma, A, K, W, K, M, N, 0.f, EpiStoreF32{C, N}, s);
+        if (K == 1024) return launch_gemm_skinny<32, 1024, false>(*h->tma, A, K, W, K, M, N, 0.f, EpiStoreF32{C, N}, s);
     }
     return Error(2, "test_gemm: unsupported kernel / shape");
 }
@@ -230,8 +230,8 @@ Status trace_enable(mrmt3_handle* h, bool on) {
     destroy_graphs(h);
     h->trace_on = on;
     if (on) {
-        MRMT3_TRY(h->trace_buf.reserve(256 * 16));
-        MRMT3_CUDA_TRY(cudaMemset(h->trace_buf.p, 0, 256 * 16));
+        MRMT3_TRY(h->trace_buf.reserve(512 * 16));
+        MRMT3_CUDA_TRY(cudaMemset(h->trace_buf.p, 0, 512 * 16));
     }
     return OkStatus();
 }
@@ -613,6 +613,11 @@ static Status enqueue_step(mrmt3_handle* h, const StepPlan& pl, int kind, cudaSt
     const CUtensorMap *self_map = nullptr, *cross_map = nullptr;
     MRMT3_TRY(h->tma->get(h->kv_pool.p, (long)(h->kv_pool.cap / (kDKV * sizeof(bf16))), kDKV, kDKV, 32, &self_map));
     MRMT3_TRY(h->tma->get(h->cross_cache.p, (long)(h->cross_cache.cap / (kDKV * sizeof(bf16))), kDKV, kDKV, 32, &cross_map));
+    // column-tile width of the wide projections (qkv, ffn-in): a CTA ingests (32 + BN) x K x 2
+    // bytes at the ~70 GB/s one SM gets from L2, so narrow tiles on more SMs win while the launch
+    // has fewer CTAs than the GPU has SMs
+    static const int narrow_env = getenv("MRMT3_SKINNY_NARROW") ? atoi(getenv("MRMT3_SKINNY_NARROW")) : -1;
+    const bool narrow = narrow_env >= 0 ? narrow_env != 0 : n <= 64;
     int tslot = 0;
     auto next_trace = [&]() { return TraceSlot{h->trace_on ? h->trace_buf.as<unsigned long long>() : nullptr, tslot++}; };
     DecodeState st_embed = pl.st;
@@ -622,8 +627,12 @@ static Status enqueue_step(mrmt3_handle* h, const StepPlan& pl, int kind, cudaSt
                                                     pl.st.prefix_len * kDModel, H, Hb, n, s));
     for (int li = 0; li < h->cfg.n_dec_layers; ++li) {
         const LayerW& L = h->dec.layers[li];
-        RUNC(h, MRMT3_PROF_GEMM_QKV, s, (launch_gemm_skinny<64, kDModel, true>(
-                 Hb, kDModel, L.wqkv_f, kDModel, n, 3 * kInner, eps, EpiStoreBf16{qkv, 3 * kInner}, s, next_trace())));
+        if (narrow)
+            RUNC(h, MRMT3_PROF_GEMM_QKV, s, (launch_gemm_skinny<32, kDModel, true>(
+                     *h->tma, Hb, kDModel, L.wqkv_f, kDModel, n, 3 * kInner, eps, EpiStoreBf16{qkv, 3 * kInner}, s, next_trace())));
+        else
+            RUNC(h, MRMT3_PROF_GEMM_QKV, s, (launch_gemm_skinny<64, kDModel, true>(
+                     *h->tma, Hb, kDModel, L.wqkv_f, kDModel, n, 3 * kInner, eps, EpiStoreBf16{qkv, 3 * kInner}, s, next_trace())));
         AttnDecodeParams ap{};
         ap.q = qkv;
         ap.q_stride = 3 * kInner;
@@ -643,10 +652,10 @@ static Status enqueue_step(mrmt3_handle* h, const StepPlan& pl, int kind, cudaSt
         ap.trace = next_trace();
         RUNC(h, MRMT3_PROF_ATTN_SELF, s, launch_attn_decode(ap, n, true, s));
         RUNC(h, MRMT3_PROF_GEMM_O, s, (launch_gemm_skinny<32, kInner, false>(
-                 ctx, kInner, L.wo, kInner, n, kDModel, eps, EpiResidualBoth{H, Hb, kDModel}, s, next_trace())));
+                 *h->tma, ctx, kInner, L.wo, kInner, n, kDModel, eps, EpiResidualBoth{H, Hb, kDModel}, s, next_trace())));
 
         RUNC(h, MRMT3_PROF_GEMM_CQ, s, (launch_gemm_skinny<32, kDModel, true>(
-                 Hb, kDModel, L.cq_f, kDModel, n, kInner, eps, EpiStoreBf16{qc, kInner}, s, next_trace())));
+                 *h->tma, Hb, kDModel, L.cq_f, kDModel, n, kInner, eps, EpiStoreBf16{qc, kInner}, s, next_trace())));
         AttnDecodeParams cp{};
         cp.q = qc;
         cp.q_stride = kInner;
@@ -663,12 +672,16 @@ static Status enqueue_step(mrmt3_handle* h, const StepPlan& pl, int kind, cudaSt
         cp.trace = next_trace();
         RUNC(h, MRMT3_PROF_ATTN_CROSS, s, launch_attn_decode(cp, n, false, s));
         RUNC(h, MRMT3_PROF_GEMM_CO, s, (launch_gemm_skinny<32, kInner, false>(
-                 ctx, kInner, L.co, kInner, n, kDModel, eps, EpiResidualBoth{H, Hb, kDModel}, s, next_trace())));
+                 *h->tma, ctx, kInner, L.co, kInner, n, kDModel, eps, EpiResidualBoth{H, Hb, kDModel}, s, next_trace())));
 
-        RUNC(h, MRMT3_PROF_GEMM_WI, s, (launch_gemm_skinny<64, kDModel, true>(
-                 Hb, kDModel, L.wi_f, kDModel, n, 2 * kDFF, eps, EpiGatedGelu{ff, kDFF}, s, next_trace())));
+        if (narrow)
+            RUNC(h, MRMT3_PROF_GEMM_WI, s, (launch_gemm_skinny<32, kDModel, true>(
+                     *h->tma, Hb, kDModel, L.wi_f, kDModel, n, 2 * kDFF, eps, EpiGatedGelu{ff, kDFF}, s, next_trace())));
+        else
+            RUNC(h, MRMT3_PROF_GEMM_WI, s, (launch_gemm_skinny<64, kDModel, true>(
+                     *h->tma, Hb, kDModel, L.wi_f, kDModel, n, 2 * kDFF, eps, EpiGatedGelu{ff, kDFF}, s, next_trace())));
         RUNC(h, MRMT3_PROF_GEMM_WFF, s, (launch_gemm_skinny<32, kDFF, false>(
-                 ff, kDFF, L.wff, kDFF, n, kDModel, eps, EpiResidualBoth{H, Hb, kDModel}, s, next_trace())));
+                 *h->tma, ff, kDFF, L.wff, kDFF, n, kDModel, eps, EpiResidualBoth{H, Hb, kDModel}, s, next_trace())));
     }
     if (kind == 1) {
         RUNC(h, MRMT3_PROF_ARGMAX, s, launch_advance_only(pl.st, s));
@@ -678,13 +691,13 @@ static Status enqueue_step(mrmt3_handle* h, const StepPlan& pl, int kind, cudaSt
     if (pl.ext_logits) {
         const size_t lane_stride = (size_t)pl.st.max_tokens * kVocab;
         RUNC(h, MRMT3_PROF_LM_HEAD, s, (launch_gemm_skinny<64, kDModel, true>(
-                 Hb, kDModel, h->lm_head_f, kDModel, n, kVocab, eps,
+                 *h->tma, Hb, kDModel, h->lm_head_f, kDModel, n, kVocab, eps,
                  EpiStoreF32Step{pl.ext_logits, kVocab, lane_stride, pl.st.step, pl.st.prefix_len, pl.st.out_row}, s, next_trace())));
         RUNC(h, MRMT3_PROF_ARGMAX, s, launch_argmax_advance(pl.st, pl.ext_logits, lane_stride, kVocab, n, kVocab, s));
     } else {
         float* lg = h->d_logits.as<float>() + l0 * kVocab;
         RUNC(h, MRMT3_PROF_LM_HEAD, s, (launch_gemm_skinny<64, kDModel, true>(
-                 Hb, kDModel, h->lm_head_f, kDModel, n, kVocab, eps, EpiStoreF32{lg, kVocab}, s, next_trace())));
+                 *h->tma, Hb, kDModel, h->lm_head_f, kDModel, n, kVocab, eps, EpiStoreF32{lg, kVocab}, s, next_trace())));
         DecodeState st_arg = pl.st;
         st_arg.trace = next_trace();
         RUNC(h, MRMT3_PROF_ARGMAX, s, launch_argmax_advance(st_arg, lg, kVocab, 0, n, kVocab, s));
