@@ -393,3 +393,63 @@ def test_full_size_batch_properties(pkg):
     eos = (a == 1)
     after = torch.cumsum(eos.int(), 1) - eos.int()
     assert int((a * (after > 0)).abs().sum()) == 0          # pad after EOS (models/t5.py:288)
+
+
+# ---- edge cases: empty / tiny / ragged / oversize inputs ------------------------------------------
+def test_more_segments_than_decode_lanes(pkg):
+    """A batch wider than one wave of decode lanes (512) is decoded in waves; rows are independent,
+    so the result equals decoding the two halves separately."""
+    model, _ = _model(pkg, 1239, eos_scale=5.0)
+    x = syn.synthetic_features(17, 530).cuda()
+    whole = model.generate(x, max_length=6)
+    a = model.generate(x[:512], max_length=6)
+    b = model.generate(x[512:], max_length=6)
+    assert whole.shape[0] == 530
+    n = whole.shape[1]
+    a = torch.nn.functional.pad(a, (0, n - a.shape[1]))
+    b = torch.nn.functional.pad(b, (0, n - b.shape[1]))
+    assert torch.equal(whole, torch.cat([a, b]))
+
+
+def test_max_length_one(pkg, feats):
+    model, sd = _model(pkg, 1234, eos_scale=5.0)
+    got = model.generate(feats.cuda(), max_length=1).cpu().numpy()
+    want = O.generate_cached(feats, sd, max_length=1).numpy()
+    assert got.shape == want.shape == (4, 2)
+    np.testing.assert_array_equal(got[:, 0], 0)
+
+
+def test_segmem_ragged_tracks_with_an_empty_track(pkg):
+    """Tracks of 2, 0, 3 and 1 segments in one call: the empty track contributes no rows and the
+    others equal their single-track calls (lanes of exhausted tracks idle in later rounds)."""
+    model, _ = _model(pkg, 4322, kind="v2p", eos_scale=3.0)
+    eng = model.engine()
+    x = syn.synthetic_features(23, 6).cuda()
+    counts = [2, 0, 3, 1]
+    batched = eng.generate_segmem(x, counts, max_length=20).cpu().numpy()
+    assert batched.shape == (6, 20)
+    off = 0
+    for c in counts:
+        if c:
+            single = eng.generate_segmem(x[off:off + c], [c], max_length=20).cpu().numpy()
+            np.testing.assert_array_equal(batched[off:off + c], single)
+        off += c
+
+
+@pytest.mark.parametrize("n_samples", [0, 1, 127, 128, 32767, 32768])
+def test_tiny_and_boundary_audio_lengths(pkg, n_samples):
+    """inference.py:64-95 pads at least one sample, a whole hop when already aligned: 0 samples is
+    one (all-padding) frame, 32767 samples one segment, 32768 samples TWO segments.
+    The fused host-buffer path must frame, mask and decode exactly like the staged one."""
+    import importlib
+    inf = importlib.import_module("mr-mt3_b200.inference")
+    model, _ = _model(pkg, 4322, kind="v2p", eos_scale=3.0)
+    audio = syn.synthetic_audio(seed=3, n_samples=max(n_samples, 1))[:n_samples]
+    h = inf.InferenceHandler(model=model, mel_norm=True, contiguous_inference=True)
+    inputs, frame_times = h._preprocess(audio)
+    want_mel, want_times = O.preprocess(audio, mel_norm=True)
+    assert inputs.shape == want_mel.shape == ((2 if n_samples == 32768 else 1), 256, 512)
+    assert logmel_rel_err(inputs, want_mel) < 1e-3
+    staged = model.generate(torch.from_numpy(inputs).cuda(), max_length=10).cpu().numpy()
+    fused = h.transcribe(audio, max_length=10).numpy()
+    np.testing.assert_array_equal(fused, staged)
