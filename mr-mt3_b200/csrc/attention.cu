@@ -749,14 +749,12 @@ static Status launch_ring(const AttnDecodeParams& p, int n_lanes, cudaStream_t s
     if (!p.tmap) return Error(2, "attn_decode: the TMA variant needs a tensor map of the cache");
     auto kern = attn_decode_mma_kernel<PAGED, S, Q>;
     constexpr int smem = Q * S * kMmaStageBytes + kMmaMergeBytes + 2 * Q * S * 8 + 1024;
-    static int n_sm_of[64] = {0};  // per device: SM count, 0 = attribute not set yet
+    static int n_sm_of[64] = {0};  // per device: SM count
     int dev = 0;
     MRMT3_CUDA_TRY(cudaGetDevice(&dev));
     if (dev < 0 || dev >= 64) return Error(2, "device index out of range");
-    if (!n_sm_of[dev]) {
-        MRMT3_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
-        MRMT3_CUDA_TRY(cudaDeviceGetAttribute(&n_sm_of[dev], cudaDevAttrMultiProcessorCount, dev));
-    }
+    MRMT3_TRY(ensure_dynamic_smem(kern, smem));
+    if (!n_sm_of[dev]) MRMT3_CUDA_TRY(cudaDeviceGetAttribute(&n_sm_of[dev], cudaDevAttrMultiProcessorCount, dev));
     // CTAs per SM: a launch of a 32-lane group (192 items, other groups' kernels running beside
     // it) wants one light CTA per SM so that the projections of the other groups stay resident; a
     // launch that has the GPU to itself (one group of 256 lanes = 1536 items) needs 2-3 CTAs per

@@ -5,7 +5,10 @@
 #include <stdint.h>
 
 #include <cstdio>
+#include <mutex>
+#include <set>
 #include <string>
+#include <utility>
 
 namespace mrmt3 {
 
@@ -172,6 +175,22 @@ __device__ __forceinline__ void named_bar_sync(int id, int n_threads) {
 }
 
 inline int ceil_div(int a, int b) { return (a + b - 1) / b; }
+
+// cudaFuncAttributeMaxDynamicSharedMemorySize is a per-device property of a kernel: opt in once per
+// (device, kernel), whichever handle / thread launches it first
+template <class Kernel>
+inline Status ensure_dynamic_smem(Kernel kern, int bytes) {
+    static std::mutex mu;
+    static std::set<std::pair<int, const void*>> done;
+    int dev = 0;
+    MRMT3_CUDA_TRY(cudaGetDevice(&dev));
+    std::lock_guard<std::mutex> lock(mu);
+    const auto key = std::make_pair(dev, reinterpret_cast<const void*>(kern));
+    if (done.count(key)) return OkStatus();
+    MRMT3_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes));
+    done.insert(key);
+    return OkStatus();
+}
 
 // ---- programmatic dependent launch (PDL) -----------------------------------------------------
 // The decode step is a chain of ~70 short dependent kernels.  Launched with the programmatic

@@ -251,33 +251,21 @@ Status launch_gemm_mma(const bf16* A, int lda, ARowMap amap, const bf16* W, int 
         constexpr int BM = 128, BN = 128;
         auto kern = gemm_tn_mma_kernel<BM, BN, 2, 4, Epi>;
         constexpr int smem = gemm_smem_bytes<BM, BN>();
-        static bool attr_set = false;
-        if (!attr_set) {
-            MRMT3_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
-            attr_set = true;
-        }
+        MRMT3_TRY(ensure_dynamic_smem(kern, smem));
         dim3 grid(N / BN, ceil_div(M, BM));
         kern<<<grid, 256, smem, stream>>>(A, lda, amap, W, ldw, M, N, K, epi);
     } else if (M > 64) {
         constexpr int BM = 64, BN = 64;
         auto kern = gemm_tn_mma_kernel<BM, BN, 2, 2, Epi>;
         constexpr int smem = gemm_smem_bytes<BM, BN>();
-        static bool attr_set = false;
-        if (!attr_set) {
-            MRMT3_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
-            attr_set = true;
-        }
+        MRMT3_TRY(ensure_dynamic_smem(kern, smem));
         dim3 grid(N / BN, ceil_div(M, BM));
         kern<<<grid, 128, smem, stream>>>(A, lda, amap, W, ldw, M, N, K, epi);
     } else {
         constexpr int BM = 32, BN = 64;
         auto kern = gemm_tn_mma_kernel<BM, BN, 1, 4, Epi>;
         constexpr int smem = gemm_smem_bytes<BM, BN>();
-        static bool attr_set = false;
-        if (!attr_set) {
-            MRMT3_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
-            attr_set = true;
-        }
+        MRMT3_TRY(ensure_dynamic_smem(kern, smem));
         dim3 grid(N / BN, ceil_div(M, BM));
         kern<<<grid, 128, smem, stream>>>(A, lda, amap, W, ldw, M, N, K, epi);
     }

@@ -243,11 +243,7 @@ Status launch_gemm_skinny(TmaCache& tc, const bf16* A, int lda, const bf16* W, i
     static_assert(!NORM || K == kDModel, "fused RMSNorm needs complete rows: K == d_model");
     auto kern = gemm_skinny_kernel<BN, K, NORM, Epi>;
     constexpr int smem = (32 + BN) * K * (int)sizeof(bf16) + (K / 64) * 8 + 1024;
-    static bool attr_set = false;
-    if (!attr_set) {
-        MRMT3_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
-        attr_set = true;
-    }
+    MRMT3_TRY(ensure_dynamic_smem(kern, smem));
     const CUtensorMap *ma = nullptr, *mw = nullptr;
     MRMT3_TRY(tc.get(A, M, K, lda, 32, &ma));
     MRMT3_TRY(tc.get(W, N, K, ldw, BN, &mw));

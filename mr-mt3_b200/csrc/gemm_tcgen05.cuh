@@ -277,11 +277,7 @@ Status launch_gemm_tc_bn(TmaCache& tc, const CUtensorMap* ma, const bf16* W, int
     const CUtensorMap* mw = nullptr;
     MRMT3_TRY(tc.get(W, N, K, ldw, BN, &mw));
     auto kern = gemm_tn_tcgen05_kernel<BN, Epi>;
-    static bool attr_set = false;
-    if (!attr_set) {
-        MRMT3_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, TcSmem<BN>::kTotal));
-        attr_set = true;
-    }
+    MRMT3_TRY(ensure_dynamic_smem(kern, TcSmem<BN>::kTotal));
     const int n_tiles = (N / BN) * ceil_div(M, kTcBM);
     kern<<<std::min(n_tiles, n_sms), kTcThreads, TcSmem<BN>::kTotal, stream>>>(*ma, *mw, M, N, K, amap, epi);
     MRMT3_CHECK_LAUNCH();
