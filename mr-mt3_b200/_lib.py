@@ -58,6 +58,16 @@ _PROTOTYPES = {
     "mrmt3_transcribe_host": (_c_int, [_c_void_p, _c_void_p, _c_i64, _c_void_p, _c_void_p, _c_void_p,
                                        _c_int, _c_void_p, _c_int, _c_int, _c_int, _c_void_p, _c_void_p,
                                        _c_void_p]),
+    "mrmt3_train_init": (_c_int, [_c_void_p, ctypes.POINTER(_c_i64)]),
+    "mrmt3_train_locate": (_c_int, [_c_void_p, ctypes.c_char_p, ctypes.POINTER(_c_i64), ctypes.POINTER(ctypes.c_int32),
+                                    ctypes.POINTER(ctypes.c_int32), ctypes.POINTER(ctypes.c_int32),
+                                    ctypes.POINTER(ctypes.c_int32)]),
+    "mrmt3_train_forward": (_c_int, [_c_void_p, _c_void_p, _c_int, _c_void_p, _c_void_p, _c_int, _c_void_p,
+                                     ctypes.POINTER(ctypes.c_float), _c_void_p]),
+    "mrmt3_train_backward": (_c_int, [_c_void_p, _c_void_p, _c_void_p]),
+    "mrmt3_train_apply": (_c_int, [_c_void_p, _c_void_p, ctypes.c_float, ctypes.c_float, ctypes.c_float,
+                                   ctypes.c_float, ctypes.c_float, _c_void_p]),
+    "mrmt3_train_read_master": (_c_int, [_c_void_p, _c_void_p, _c_void_p]),
 }
 EXPORTED_SYMBOLS = tuple(_PROTOTYPES)
 
@@ -298,6 +308,63 @@ class Engine:
         out = torch.empty((B, n_mem, D_MODEL), dtype=torch.float32, device=self.device)
         with torch.cuda.device(self.device):
             self._check(self._lib.mrmt3_memory_block(self._h, _ptr(prev), B, Lp, _ptr(out), _stream()))
+        return out
+
+    # ---- fine-tune step (reference tasks/mt3_net.py training_step) -----------------------------
+    def train_init(self):
+        """Allocate fp32 masters / Adam moments; returns the length of the flat parameter order."""
+        n = ctypes.c_int64(0)
+        with torch.cuda.device(self.device):
+            self._check(self._lib.mrmt3_train_init(self._h, ctypes.byref(n)))
+        self._n_params = int(n.value)
+        return self._n_params
+
+    def train_locate(self, name):
+        """(offset, rows, cols, row_mul, row_off) of a reference state-dict tensor in the flat order."""
+        off = ctypes.c_int64(0)
+        r, c, mul, ro = (ctypes.c_int32(0) for _ in range(4))
+        self._check(self._lib.mrmt3_train_locate(self._h, name.encode(), ctypes.byref(off), ctypes.byref(r),
+                                                 ctypes.byref(c), ctypes.byref(mul), ctypes.byref(ro)))
+        return int(off.value), int(r.value), int(c.value), int(mul.value), int(ro.value)
+
+    def flat_view(self, flat, name):
+        """The (rows, cols) tensor `name` as a view of a flat buffer (gradients, masters)."""
+        off, rows, cols, mul, ro = self.train_locate(name)
+        packed = flat[off:off + ((rows - 1) * mul + ro + 1) * cols].view(-1, cols)
+        return packed[ro::mul][:rows]
+
+    def train_forward(self, inputs, decoder_input_ids, labels):
+        """-> (logits (B, L, V) fp32, mean cross-entropy over labels != -100)."""
+        x = self._mel(inputs)
+        ids = decoder_input_ids.to(self.device, torch.int64).contiguous()
+        lab = labels.to(self.device, torch.int64).contiguous()
+        B, L = ids.shape
+        logits = torch.empty((B, L, VOCAB), dtype=torch.float32, device=self.device)
+        loss = ctypes.c_float(0.0)
+        with torch.cuda.device(self.device):
+            self._check(self._lib.mrmt3_train_forward(self._h, _ptr(x), B, _ptr(ids), _ptr(lab), L, _ptr(logits),
+                                                      ctypes.byref(loss), _stream()))
+        return logits, float(loss.value)
+
+    def train_backward(self, grad=None):
+        """Gradient of the last train_forward's loss into a flat fp32 tensor (allocated if None)."""
+        n = getattr(self, "_n_params", None) or self.train_init()
+        if grad is None:
+            grad = torch.empty(n, dtype=torch.float32, device=self.device)
+        with torch.cuda.device(self.device):
+            self._check(self._lib.mrmt3_train_backward(self._h, _ptr(grad), _stream()))
+        return grad
+
+    def train_apply(self, grad, lr, betas=(0.9, 0.999), eps=1e-8, weight_decay=0.01):
+        with torch.cuda.device(self.device):
+            self._check(self._lib.mrmt3_train_apply(self._h, _ptr(grad), lr, betas[0], betas[1], eps, weight_decay,
+                                                    _stream()))
+
+    def train_read_master(self):
+        n = getattr(self, "_n_params", None) or self.train_init()
+        out = torch.empty(n, dtype=torch.float32, device=self.device)
+        with torch.cuda.device(self.device):
+            self._check(self._lib.mrmt3_train_read_master(self._h, _ptr(out), _stream()))
         return out
 
     def transcribe_host(self, audio, seg_start, seg_len, valid_frames, seg_counts=None, mel_norm=True,

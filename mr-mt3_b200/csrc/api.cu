@@ -24,6 +24,16 @@ Status api_transcribe_host(mrmt3_handle* h, const float* audio_host, long long n
                            const long long* seg_start_host, const int* seg_len_host,
                            const int* valid_frames_host, int n_seg, const int* seg_counts_host, int n_tracks,
                            int flags, int max_length, long long* out_ids_host, int* steps_host, cudaStream_t s);
+Status train_init(mrmt3_handle* h);
+size_t train_param_count(mrmt3_handle* h);
+Status train_read_master(mrmt3_handle* h, float* out, cudaStream_t s);
+Status train_locate(mrmt3_handle* h, const std::string& name, long long* offset, int* rows, int* cols, int* row_mul,
+                    int* row_off);
+Status train_forward(mrmt3_handle* h, const float* mel, int B, const long long* dec_ids, const long long* labels, int L,
+                     float* logits_out, float* loss_host, cudaStream_t s);
+Status train_backward(mrmt3_handle* h, float* grad, cudaStream_t s);
+Status train_apply(mrmt3_handle* h, const float* grad, float lr, float beta1, float beta2, float adam_eps, float wd,
+                   cudaStream_t s);
 Status profile_collect(mrmt3_handle* h);
 Status trace_enable(mrmt3_handle* h, bool on);
 void drop_graphs(mrmt3_handle* h);
@@ -250,6 +260,53 @@ int mrmt3_forward_logits(mrmt3_handle* h, const float* mel, int B, const int64_t
 int mrmt3_memory_block(mrmt3_handle* h, const int64_t* prev_ids, int B, int Lp, float* mem_out, void* stream) {
     GUARD(h)
     return finish(h, api_memory_block(h, (const long long*)prev_ids, B, Lp, mem_out, (cudaStream_t)stream));
+    END_GUARD(h)
+}
+
+int mrmt3_train_init(mrmt3_handle* h, int64_t* n_params) {
+    GUARD(h)
+    Status st = train_init(h);
+    if (st.ok() && n_params) *n_params = (int64_t)train_param_count(h);
+    return finish(h, st);
+    END_GUARD(h)
+}
+
+int mrmt3_train_locate(mrmt3_handle* h, const char* name, int64_t* offset, int32_t* rows, int32_t* cols,
+                       int32_t* row_mul, int32_t* row_off) {
+    GUARD(h)
+    if (!name || !offset || !rows || !cols || !row_mul || !row_off) return finish(h, Error(1, "null argument"));
+    long long off = 0;
+    int r = 0, c = 0, mul = 1, ro = 0;
+    Status st = train_locate(h, name, &off, &r, &c, &mul, &ro);
+    *offset = off; *rows = r; *cols = c; *row_mul = mul; *row_off = ro;
+    return finish(h, st);
+    END_GUARD(h)
+}
+
+int mrmt3_train_forward(mrmt3_handle* h, const float* mel, int B, const int64_t* decoder_input_ids,
+                        const int64_t* labels, int L, float* logits_out, float* loss_host, void* stream) {
+    GUARD(h)
+    return finish(h, train_forward(h, mel, B, reinterpret_cast<const long long*>(decoder_input_ids),
+                                   reinterpret_cast<const long long*>(labels), L, logits_out, loss_host, (cudaStream_t)stream));
+    END_GUARD(h)
+}
+
+int mrmt3_train_backward(mrmt3_handle* h, float* grad_flat, void* stream) {
+    GUARD(h)
+    return finish(h, train_backward(h, grad_flat, (cudaStream_t)stream));
+    END_GUARD(h)
+}
+
+int mrmt3_train_apply(mrmt3_handle* h, const float* grad_flat, float lr, float beta1, float beta2, float eps,
+                      float weight_decay, void* stream) {
+    GUARD(h)
+    return finish(h, train_apply(h, grad_flat, lr, beta1, beta2, eps, weight_decay, (cudaStream_t)stream));
+    END_GUARD(h)
+}
+
+int mrmt3_train_read_master(mrmt3_handle* h, float* out_flat, void* stream) {
+    GUARD(h)
+    return finish(h, train_read_master(h, out_flat, (cudaStream_t)stream));
     END_GUARD(h)
 }
 

@@ -188,6 +188,8 @@ __global__ void __launch_bounds__(128)
         float l = l_run[h];
         l += __shfl_xor_sync(0xffffffffu, l, 1);
         l += __shfl_xor_sync(0xffffffffu, l, 2);
+        if (p.lse2 && (lane & 3) == 0 && row_lo + h * 8 < p.Tq)
+            p.lse2[((size_t)b * kHeads + head) * p.Tq + row_lo + h * 8] = m_run[h] * kLog2e + log2f(l);
         l_run[h] = l > 0.f ? 1.f / l : 0.f;
     }
     bf16* O = p.O + (size_t)b * p.o_batch_stride + head * p.o_head_stride;

@@ -26,6 +26,7 @@ struct AttnFullParams {
     int Tq, Tk;
     int causal;         // key j visible to query i iff j <= i + causal_offset
     int causal_offset;
+    float* lse2;        // optional (batch, heads, Tq): m*log2(e) + log2(l), saved for the backward pass
 };
 Status launch_attn_full(const AttnFullParams& p, int batch, cudaStream_t stream);
 

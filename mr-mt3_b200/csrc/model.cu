@@ -54,19 +54,12 @@ void RowWorkspace::release() {
     rows = 0;
 }
 
-constexpr int kMaxLanes = 512;    // decode lanes per wave
 constexpr int kEncChunk = 256;    // encoder segments per pass (bounds the row workspace)
 constexpr int kNPos = 5000;       // FixedPositionalEmbedding max_length, reference models/t5.py:706
 constexpr int kPollEvery = 8;     // decode steps between early-exit polls
 constexpr int kMaxGroups = 16;    // lane groups decoding concurrently on their own streams
 constexpr int kGroupScalars = 16; // ints per group in the state header: [0] step, [2] ticket
 constexpr int kStateHeader = kMaxGroups * kGroupScalars;
-
-#define RUN(h, call)          \
-    do {                      \
-        MRMT3_TRY(call);      \
-        ++(h)->launches;      \
-    } while (0)
 
 static cudaEvent_t prof_event(mrmt3_handle* h) {
     if (!h->prof_pool.empty()) {
@@ -256,6 +249,7 @@ void handle_destroy(mrmt3_handle* h) {
     h->audio.release(); h->seg_tab.release(); h->ids_dev.release(); h->tok_out.release(); h->dummy_ids.release();
     h->d_h32.release(); h->d_n_bf16.release(); h->d_qkv.release(); h->d_ctx.release();
     h->d_qc.release(); h->d_ff.release(); h->d_logits.release(); h->d_state.release();
+    train_destroy(h);
     h->kv_pool.release(); h->block_table.release(); h->cross_cache.release(); h->lane_tab.release();
     h->attn_scratch.release(); h->attn_tickets.release();
     if (h->h_pinned) cudaFreeHost(h->h_pinned);
@@ -546,7 +540,7 @@ static LaneArrays lane_arrays(const mrmt3_handle* h) {
     return a;
 }
 
-static Status ensure_decode_capacity(mrmt3_handle* h, int n_lanes, int tk, int max_positions) {
+Status ensure_decode_capacity(mrmt3_handle* h, int n_lanes, int tk, int max_positions) {
     const int pages = ceil_div(max_positions, kKVPage);
     if (max_positions > attn_decode_max_keys())
         return Error(2, "max_length (+ memory prefix) exceeds the decode attention key capacity");

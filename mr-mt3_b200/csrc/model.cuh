@@ -74,7 +74,15 @@ struct StepGraph {
     int n_kernels = 0;
 };
 
+constexpr int kMaxLanes = 512;    // decode lanes per wave
+
 }  // namespace mrmt3
+
+#define RUN(h, call)          \
+    do {                      \
+        MRMT3_TRY(call);      \
+        ++(h)->launches;      \
+    } while (0)
 
 struct mrmt3_handle {
     mrmt3_config cfg;
@@ -143,4 +151,11 @@ struct mrmt3_handle {
     cudaStream_t gstream[16] = {nullptr};
     cudaEvent_t gdone[16] = {nullptr};
     cudaEvent_t gfork = nullptr;
+    void* train = nullptr;               // mrmt3::TrainState (train.cu), created by the first train call
 };
+
+namespace mrmt3 {
+// sizes the decode-lane buffers (KV pages, cross cache, ...) for n_lanes lanes, tk cross keys
+Status ensure_decode_capacity(mrmt3_handle* h, int n_lanes, int tk, int max_positions);
+void train_destroy(mrmt3_handle* h);
+}  // namespace mrmt3

@@ -1,0 +1,546 @@
+// The fine-tune step (BASELINE configs[4]; reference tasks/mt3_net*.py `training_step` over
+// models/t5.py:99-249): teacher-forced forward with saved activations, cross-entropy with
+// ignore_index -100, hand-written backward through every op of the path, AdamW on fp32 masters.
+// The gradient lives in ONE flat fp32 buffer owned by the caller (packed-weight order), so data
+// parallel training is a single all-reduce of that buffer between `train_backward` and
+// `train_apply`.  Dropout is not applied (the parity oracle is the reference in
+// eval()-mode arithmetic).  Scope of this build: the plain MT3 model (mem_variant NONE).
+//
+// GEMMs reuse the TN tcgen05 kernel:
+//   dgrad  dX[M,Kin] = dY[M,N] . W[N,Kin]        = A(dY) . (W^T)^T      with W^T[Kin,N] re-made per step
+//   wgrad  dW[N,Kin] = dY^T[N,M] . X[M,Kin]      = A(dY^T) . (X^T)^T    with explicit transposes
+#include <algorithm>
+#include <cmath>
+#include <cstring>
+#include <vector>
+
+#include "gemm_tcgen05.cuh"
+#include "model.cuh"
+#include "train.cuh"
+
+namespace mrmt3 {
+
+constexpr int kMaxTrainBatch = kMaxLanes;  // one cross-cache lane per sample
+
+struct ParamSlot {
+    bf16* w16;      // packed bf16 weight in the arena (nullptr for fp32-only parameters)
+    float* w32;     // fp32 parameter in the arena (norm weights, embedding) or nullptr
+    int rows, cols; // packed shape
+    size_t off;     // offset in the flat gradient / master / moment buffers
+    bf16* wt;       // (cols, rows) transposed bf16 copy for dgrad, refreshed every step
+};
+
+struct LayerSlots {
+    int wqkv, wo, ln_self, cq, co, ln_cross, wi, wff, ln_ff;
+};
+
+struct LayerStash {
+    float *h_in, *h_mid2, *h_mid;
+    bf16 *n1, *qkv, *ctx, *nc, *qc, *ctx_c, *n2, *raw, *ff;
+    float *lse, *lse_c;
+};
+
+struct TrainState {
+    std::vector<ParamSlot> slots;
+    std::vector<LayerSlots> enc, dec;
+    int proj = -1, emb = -1, lm_head = -1, cross_kv = -1, enc_final = -1, dec_final = -1;
+    size_t n_total = 0;
+    DeviceBuffer master, m, v, wt_arena, stash, scratch;
+    int step = 0;
+    // the last forward's saved state
+    int B = 0, L = 0;
+    std::vector<LayerStash> enc_st, dec_st;
+    float *enc_h_final = nullptr, *dec_h_final = nullptr;
+    bf16 *mel16 = nullptr, *enc_n_final = nullptr, *dec_n_final = nullptr, *dlogits = nullptr;
+    float* row_loss = nullptr;
+    const long long* dec_ids = nullptr;
+    DeviceBuffer ids_copy;
+};
+
+static TrainState* state(mrmt3_handle* h) { return reinterpret_cast<TrainState*>(h->train); }
+
+void train_destroy(mrmt3_handle* h) {
+    TrainState* t = state(h);
+    if (!t) return;
+    t->master.release(); t->m.release(); t->v.release(); t->wt_arena.release();
+    t->stash.release(); t->scratch.release(); t->ids_copy.release();
+    delete t;
+    h->train = nullptr;
+}
+
+static int add_slot(TrainState* t, bf16* w16, float* w32, int rows, int cols) {
+    ParamSlot s{w16, w32, rows, cols, t->n_total, nullptr};
+    t->n_total += (size_t)rows * cols;
+    t->slots.push_back(s);
+    return (int)t->slots.size() - 1;
+}
+
+static void add_stack(TrainState* t, StackW& st, bool decoder, std::vector<LayerSlots>& out, int& final_slot) {
+    for (auto& L : st.layers) {
+        LayerSlots ls{};
+        ls.wqkv = add_slot(t, L.wqkv, nullptr, 3 * kInner, kDModel);
+        ls.wo = add_slot(t, L.wo, nullptr, kDModel, kInner);
+        ls.ln_self = add_slot(t, nullptr, L.ln_self, 1, kDModel);
+        ls.cq = ls.co = ls.ln_cross = -1;
+        if (decoder) {
+            ls.cq = add_slot(t, L.cq, nullptr, kInner, kDModel);
+            ls.co = add_slot(t, L.co, nullptr, kDModel, kInner);
+            ls.ln_cross = add_slot(t, nullptr, L.ln_cross, 1, kDModel);
+        }
+        ls.wi = add_slot(t, L.wi, nullptr, 2 * kDFF, kDModel);
+        ls.wff = add_slot(t, L.wff, nullptr, kDModel, kDFF);
+        ls.ln_ff = add_slot(t, nullptr, L.ln_ff, 1, kDModel);
+        out.push_back(ls);
+    }
+    final_slot = add_slot(t, nullptr, st.final_ln, 1, kDModel);
+}
+
+Status train_init(mrmt3_handle* h) {
+    if (h->train) return OkStatus();
+    if (!h->committed) return Error(5, "weights not committed");
+    if (h->cfg.mem_variant != MRMT3_MEM_NONE)
+        return Error(2, "the fine-tune step is implemented for the plain MT3 model (mem_variant NONE) in this build");
+    MRMT3_CUDA_TRY(cudaSetDevice(h->device));
+    TrainState* t = new TrainState();
+    h->train = t;
+    t->proj = add_slot(t, h->proj, nullptr, kDModel, kDModel);
+    t->emb = add_slot(t, nullptr, h->emb, kVocab, kDModel);
+    t->lm_head = add_slot(t, h->lm_head, nullptr, kVocab, kDModel);
+    t->cross_kv = add_slot(t, h->cross_kv_w, nullptr, h->cfg.n_dec_layers * 2 * kInner, kDModel);
+    add_stack(t, h->enc, false, t->enc, t->enc_final);
+    add_stack(t, h->dec, true, t->dec, t->dec_final);
+    const size_t n = t->n_total;
+    MRMT3_TRY(t->master.reserve(n * 4));
+    MRMT3_TRY(t->m.reserve(n * 4));
+    MRMT3_TRY(t->v.reserve(n * 4));
+    MRMT3_TRY(t->wt_arena.reserve(n * 2));
+    MRMT3_CUDA_TRY(cudaMemset(t->m.p, 0, n * 4));
+    MRMT3_CUDA_TRY(cudaMemset(t->v.p, 0, n * 4));
+    // fp32 masters: the lm_head and the norm-folded decoder weights kept theirs from set_weight;
+    // the others restart from the bf16 copies (2^-9 relative, once)
+    for (auto& s : t->slots) {
+        float* dst = t->master.as<float>() + s.off;
+        const size_t cnt = (size_t)s.rows * s.cols;
+        if (s.w32) {
+            MRMT3_CUDA_TRY(cudaMemcpy(dst, s.w32, cnt * 4, cudaMemcpyDeviceToDevice));
+        } else {
+            RUN(h, launch_bf16_to_f32(s.w16, dst, cnt, 0));
+        }
+        s.wt = t->wt_arena.as<bf16>() + s.off;
+    }
+    auto copy_master = [&](int slot, const float* src) -> Status {
+        const ParamSlot& s = t->slots[slot];
+        MRMT3_CUDA_TRY(cudaMemcpy(t->master.as<float>() + s.off, src, (size_t)s.rows * s.cols * 4, cudaMemcpyDeviceToDevice));
+        return OkStatus();
+    };
+    MRMT3_TRY(copy_master(t->lm_head, h->m_lm_head));
+    for (size_t i = 0; i < h->dec.layers.size(); ++i) {
+        MRMT3_TRY(copy_master(t->dec[i].wqkv, h->dec.layers[i].m_wqkv));
+        MRMT3_TRY(copy_master(t->dec[i].cq, h->dec.layers[i].m_cq));
+        MRMT3_TRY(copy_master(t->dec[i].wi, h->dec.layers[i].m_wi));
+    }
+    MRMT3_CUDA_TRY(cudaDeviceSynchronize());
+    return OkStatus();
+}
+
+size_t train_param_count(mrmt3_handle* h) { return state(h) ? state(h)->n_total : 0; }
+
+// flat fp32 copy of every trainable tensor (packed order), e.g. to rebuild a state dict after training
+Status train_read_master(mrmt3_handle* h, float* out, cudaStream_t s) {
+    TrainState* t = state(h);
+    if (!t) return Error(5, "mrmt3_train_init first");
+    MRMT3_CUDA_TRY(cudaSetDevice(h->device));
+    for (auto& sl : t->slots) {
+        const float* src = sl.w32 ? sl.w32 : t->master.as<float>() + sl.off;
+        MRMT3_CUDA_TRY(cudaMemcpyAsync(out + sl.off, src, (size_t)sl.rows * sl.cols * 4, cudaMemcpyDeviceToDevice, s));
+    }
+    return OkStatus();
+}
+
+// where a reference state-dict tensor lives inside the flat buffers: element (r, c) of the tensor
+// is flat[offset + ((r * row_mul + row_off) * cols + c)]
+Status train_locate(mrmt3_handle* h, const std::string& name, long long* offset, int* rows, int* cols,
+                    int* row_mul, int* row_off) {
+    TrainState* t = state(h);
+    if (!t) return Error(5, "mrmt3_train_init first");
+    auto set = [&](int slot, int r, int c, int mul, int off) {
+        *offset = (long long)t->slots[slot].off;
+        *rows = r; *cols = c; *row_mul = mul; *row_off = off;
+        return OkStatus();
+    };
+    const int d = kDModel, in = kInner;
+    if (name == "proj.weight") return set(t->proj, d, d, 1, 0);
+    if (name == "decoder_embed_tokens.weight") return set(t->emb, kVocab, d, 1, 0);
+    if (name == "lm_head.weight") return set(t->lm_head, kVocab, d, 1, 0);
+    struct { const char* n; std::vector<LayerSlots>* ls; int* fin; bool dec; } stacks[] = {
+        {"encoder.", &t->enc, &t->enc_final, false}, {"decoder.", &t->dec, &t->dec_final, true}};
+    for (auto& sk : stacks) {
+        size_t pl = strlen(sk.n);
+        if (name.compare(0, pl, sk.n) != 0) continue;
+        std::string rest = name.substr(pl);
+        if (rest == "final_layer_norm.weight") return set(*sk.fin, 1, d, 1, 0);
+        int bi = -1, li = -1, consumed = 0;
+        if (sscanf(rest.c_str(), "block.%d.layer.%d.%n", &bi, &li, &consumed) < 2 || consumed == 0) break;
+        if (bi < 0 || bi >= (int)sk.ls->size()) break;
+        const LayerSlots& L = (*sk.ls)[bi];
+        std::string sub = rest.substr(consumed);
+        const int ffi = sk.dec ? 2 : 1;
+        if (li == 0 && sub == "SelfAttention.q.weight") return set(L.wqkv, in, d, 1, 0);
+        if (li == 0 && sub == "SelfAttention.k.weight") return set(L.wqkv, in, d, 1, in);
+        if (li == 0 && sub == "SelfAttention.v.weight") return set(L.wqkv, in, d, 1, 2 * in);
+        if (li == 0 && sub == "SelfAttention.o.weight") return set(L.wo, d, in, 1, 0);
+        if (li == 0 && sub == "layer_norm.weight") return set(L.ln_self, 1, d, 1, 0);
+        if (sk.dec && li == 1 && sub == "EncDecAttention.q.weight") return set(L.cq, in, d, 1, 0);
+        if (sk.dec && li == 1 && sub == "EncDecAttention.k.weight") return set(t->cross_kv, in, d, 1, bi * 2 * in);
+        if (sk.dec && li == 1 && sub == "EncDecAttention.v.weight") return set(t->cross_kv, in, d, 1, bi * 2 * in + in);
+        if (sk.dec && li == 1 && sub == "EncDecAttention.o.weight") return set(L.co, d, in, 1, 0);
+        if (sk.dec && li == 1 && sub == "layer_norm.weight") return set(L.ln_cross, 1, d, 1, 0);
+        if (li == ffi && sub == "DenseReluDense.wi_0.weight") return set(L.wi, kDFF, d, 2, 0);
+        if (li == ffi && sub == "DenseReluDense.wi_1.weight") return set(L.wi, kDFF, d, 2, 1);
+        if (li == ffi && sub == "DenseReluDense.wo.weight") return set(L.wff, d, kDFF, 1, 0);
+        if (li == ffi && sub == "layer_norm.weight") return set(L.ln_ff, 1, d, 1, 0);
+        break;
+    }
+    return Error(3, "no trainable tensor named " + name);
+}
+
+// ---------------------------------------------------------------------------------------------
+struct Bump {
+    char* p;
+    size_t used = 0, cap;
+    template <class T>
+    T* take(size_t n) {
+        used = (used + 255) & ~size_t(255);
+        T* r = reinterpret_cast<T*>(p + used);
+        used += n * sizeof(T);
+        return r;
+    }
+};
+
+static size_t stash_bytes(int n_enc, int n_dec, size_t Me, size_t Md, int B, int L) {
+    auto layer = [&](size_t M, size_t T, bool dec) {
+        size_t b = M * kDModel * 4 * (dec ? 3 : 2) + M * kDModel * 2 * (dec ? 3 : 2) + M * 3 * kInner * 2 +
+                   M * kInner * 2 * (dec ? 3 : 1) + M * 2 * kDFF * 2 + M * kDFF * 2 + (size_t)B * kHeads * T * 4 * (dec ? 2 : 1);
+        return b + 16 * 256;
+    };
+    return n_enc * layer(Me, kSegFrames, false) + n_dec * layer(Md, L, true) + Me * kDModel * (2 + 4 + 2) +
+           Md * kDModel * (4 + 2) + Md * (size_t)kVocab * 2 + Md * 4 + (1 << 16);
+}
+
+// forward over B segments with teacher forcing; logits (B, L, V) fp32 to the caller, loss to *loss_host
+Status train_forward(mrmt3_handle* h, const float* mel, int B, const long long* dec_ids, const long long* labels,
+                     int L, float* logits_out, float* loss_host, cudaStream_t s) {
+    MRMT3_TRY(train_init(h));
+    TrainState* t = state(h);
+    if (B <= 0 || L <= 0 || B > kMaxTrainBatch) return Error(2, "bad batch or length");
+    MRMT3_CUDA_TRY(cudaSetDevice(h->device));
+    const int n_enc = h->cfg.n_enc_layers, n_dec = h->cfg.n_dec_layers;
+    const size_t Me = (size_t)B * kSegFrames, Md = (size_t)B * L;
+    const float eps = h->cfg.ln_eps;
+    const ARowMap id{nullptr, 1};
+    MRMT3_TRY(t->stash.reserve(stash_bytes(n_enc, n_dec, Me, Md, B, L)));
+    Bump bp{reinterpret_cast<char*>(t->stash.p), 0, t->stash.cap};
+    t->B = B;
+    t->L = L;
+    MRMT3_TRY(t->ids_copy.reserve(Md * sizeof(long long)));
+    MRMT3_CUDA_TRY(cudaMemcpyAsync(t->ids_copy.p, dec_ids, Md * sizeof(long long), cudaMemcpyDeviceToDevice, s));
+    t->dec_ids = t->ids_copy.as<long long>();
+
+    // ---- encoder (reference models/t5.py:253-258) ----
+    t->mel16 = bp.take<bf16>(Me * kMels);
+    RUN(h, launch_cast_bf16(mel, t->mel16, Me * kMels, s));
+    float* H = bp.take<float>(Me * kDModel);  // running residual stream; each layer snapshots what it needs
+    RUN(h, launch_gemm_tc(*h->tma, t->mel16, kDModel, Me, id, h->proj, kDModel, (int)Me, kDModel, kDModel,
+                          EpiPosAdd{H, kDModel, h->pe, kSegFrames, 0}, s));
+    auto attn_fwd = [&](const bf16* Q, long qb, int qr, const bf16* K, const bf16* V, long kb, long kh, int kr, bf16* O,
+                        int Tq, int Tk, int causal, float* lse, int nb) -> Status {
+        AttnFullParams ap{};
+        ap.Q = Q; ap.q_batch_stride = qb; ap.q_head_stride = kDKV; ap.q_row_stride = qr;
+        ap.K = K; ap.V = V;
+        ap.k_batch_stride = ap.v_batch_stride = kb;
+        ap.k_head_stride = ap.v_head_stride = kh;
+        ap.k_row_stride = ap.v_row_stride = kr;
+        ap.O = O; ap.o_batch_stride = (long)Tq * kInner; ap.o_head_stride = kDKV; ap.o_row_stride = kInner;
+        ap.Tq = Tq; ap.Tk = Tk; ap.causal = causal; ap.causal_offset = 0; ap.lse2 = lse;
+        RUN(h, launch_attn_full(ap, nb, s));
+        return OkStatus();
+    };
+    auto snapshot = [&](float* dst, const float* src, size_t n) -> Status {
+        MRMT3_CUDA_TRY(cudaMemcpyAsync(dst, src, n * 4, cudaMemcpyDeviceToDevice, s));
+        return OkStatus();
+    };
+    auto ffn_fwd = [&](const LayerW& Lw, LayerStash& st, float* Hres, size_t M) -> Status {
+        st.h_mid = bp.take<float>(M * kDModel);
+        MRMT3_TRY(snapshot(st.h_mid, Hres, M * kDModel));
+        st.n2 = bp.take<bf16>(M * kDModel);
+        st.raw = bp.take<bf16>(M * 2 * kDFF);
+        st.ff = bp.take<bf16>(M * kDFF);
+        RUN(h, launch_rmsnorm(Hres, Lw.ln_ff, eps, st.n2, nullptr, (int)M, nullptr, 1, s));
+        RUN(h, launch_gemm_tc(*h->tma, st.n2, kDModel, M, id, Lw.wi, kDModel, (int)M, 2 * kDFF, kDModel,
+                              EpiStoreBf16{st.raw, 2 * kDFF}, s));
+        RUN(h, launch_gated_gelu_fwd(st.raw, st.ff, M, s));
+        RUN(h, launch_gemm_tc(*h->tma, st.ff, kDFF, M, id, Lw.wff, kDFF, (int)M, kDModel, kDFF, EpiResidual{Hres, kDModel}, s));
+        return OkStatus();
+    };
+    auto self_fwd = [&](const LayerW& Lw, LayerStash& st, float* Hres, size_t M, int T, int causal) -> Status {
+        st.h_in = bp.take<float>(M * kDModel);
+        MRMT3_TRY(snapshot(st.h_in, Hres, M * kDModel));
+        st.n1 = bp.take<bf16>(M * kDModel);
+        st.qkv = bp.take<bf16>(M * 3 * kInner);
+        st.ctx = bp.take<bf16>(M * kInner);
+        st.lse = bp.take<float>((size_t)B * kHeads * T);
+        RUN(h, launch_rmsnorm(Hres, Lw.ln_self, eps, st.n1, nullptr, (int)M, nullptr, 1, s));
+        RUN(h, launch_gemm_tc(*h->tma, st.n1, kDModel, M, id, Lw.wqkv, kDModel, (int)M, 3 * kInner, kDModel,
+                              EpiStoreBf16{st.qkv, 3 * kInner}, s));
+        MRMT3_TRY(attn_fwd(st.qkv, (long)T * 3 * kInner, 3 * kInner, st.qkv + kInner, st.qkv + 2 * kInner,
+                           (long)T * 3 * kInner, kDKV, 3 * kInner, st.ctx, T, T, causal, st.lse, B));
+        RUN(h, launch_gemm_tc(*h->tma, st.ctx, kInner, M, id, Lw.wo, kInner, (int)M, kDModel, kInner, EpiResidual{Hres, kDModel}, s));
+        return OkStatus();
+    };
+    t->enc_st.assign(n_enc, LayerStash{});
+    for (int li = 0; li < n_enc; ++li) {
+        MRMT3_TRY(self_fwd(h->enc.layers[li], t->enc_st[li], H, Me, kSegFrames, 0));
+        MRMT3_TRY(ffn_fwd(h->enc.layers[li], t->enc_st[li], H, Me));
+    }
+    t->enc_h_final = H;
+    t->enc_n_final = bp.take<bf16>(Me * kDModel);
+    RUN(h, launch_rmsnorm(H, h->enc.final_ln, eps, t->enc_n_final, nullptr, (int)Me, nullptr, 1, s));
+
+    // ---- cross K/V of all decoder layers (one GEMM into the cross cache) ----
+    MRMT3_TRY(ensure_decode_capacity(h, B, kSegFrames, 1));
+    RUN(h, launch_gemm_tc(*h->tma, t->enc_n_final, kDModel, Me, id, h->cross_kv_w, kDModel, (int)Me,
+                          n_dec * 2 * kInner, kDModel,
+                          EpiCrossKV{h->cross_cache.as<bf16>(), kSegFrames, 0, n_dec, h->tk_cap, nullptr}, s));
+
+    // ---- decoder, teacher forced (reference models/t5.py:99-180) ----
+    float* Hd = bp.take<float>(Md * kDModel);
+    RUN(h, launch_embed_tokens(t->dec_ids, h->emb, h->pe, Hd, B, L, 0, s));
+    t->dec_st.assign(n_dec, LayerStash{});
+    const size_t lane_sz = (size_t)n_dec * 2 * kHeads * h->tk_cap * kDKV;
+    for (int li = 0; li < n_dec; ++li) {
+        const LayerW& Lw = h->dec.layers[li];
+        LayerStash& st = t->dec_st[li];
+        MRMT3_TRY(self_fwd(Lw, st, Hd, Md, L, 1));
+        st.h_mid2 = bp.take<float>(Md * kDModel);
+        MRMT3_TRY(snapshot(st.h_mid2, Hd, Md * kDModel));
+        st.nc = bp.take<bf16>(Md * kDModel);
+        st.qc = bp.take<bf16>(Md * kInner);
+        st.ctx_c = bp.take<bf16>(Md * kInner);
+        st.lse_c = bp.take<float>((size_t)B * kHeads * L);
+        RUN(h, launch_rmsnorm(Hd, Lw.ln_cross, eps, st.nc, nullptr, (int)Md, nullptr, 1, s));
+        RUN(h, launch_gemm_tc(*h->tma, st.nc, kDModel, Md, id, Lw.cq, kDModel, (int)Md, kInner, kDModel,
+                              EpiStoreBf16{st.qc, kInner}, s));
+        const bf16* kbase = h->cross_cache.as<bf16>() + (size_t)li * 2 * kHeads * h->tk_cap * kDKV;
+        MRMT3_TRY(attn_fwd(st.qc, (long)L * kInner, kInner, kbase, kbase + (size_t)kHeads * h->tk_cap * kDKV, (long)lane_sz,
+                           (long)h->tk_cap * kDKV, kDKV, st.ctx_c, L, kSegFrames, 0, st.lse_c, B));
+        RUN(h, launch_gemm_tc(*h->tma, st.ctx_c, kInner, Md, id, Lw.co, kInner, (int)Md, kDModel, kInner, EpiResidual{Hd, kDModel}, s));
+        MRMT3_TRY(ffn_fwd(Lw, st, Hd, Md));
+    }
+    t->dec_h_final = Hd;
+    t->dec_n_final = bp.take<bf16>(Md * kDModel);
+    RUN(h, launch_rmsnorm(Hd, h->dec.final_ln, eps, t->dec_n_final, nullptr, (int)Md, nullptr, 1, s));
+    RUN(h, launch_gemm_tc(*h->tma, t->dec_n_final, kDModel, Md, id, h->lm_head, kDModel, (int)Md, kVocab, kDModel,
+                          EpiStoreF32{logits_out, kVocab}, s));
+
+    // ---- loss (tasks/mt3_net.py: CrossEntropyLoss(ignore_index=-100) over (B*L, V)) ----
+    t->dlogits = bp.take<bf16>(Md * kVocab);
+    t->row_loss = bp.take<float>(Md);
+    if (bp.used > bp.cap) return Error(2, "internal: activation stash overflow");
+    std::vector<long long> lab(Md);
+    MRMT3_CUDA_TRY(cudaMemcpyAsync(lab.data(), labels, Md * sizeof(long long), cudaMemcpyDeviceToHost, s));
+    MRMT3_CUDA_TRY(cudaStreamSynchronize(s));
+    size_t count = 0;
+    for (auto v : lab) count += v >= 0;
+    const float inv = count ? 1.0f / (float)count : 0.f;
+    RUN(h, launch_xent(logits_out, labels, (int)Md, kVocab, inv, t->row_loss, t->dlogits, s));
+    std::vector<float> rl(Md);
+    MRMT3_CUDA_TRY(cudaMemcpyAsync(rl.data(), t->row_loss, Md * 4, cudaMemcpyDeviceToHost, s));
+    MRMT3_CUDA_TRY(cudaStreamSynchronize(s));
+    double sum = 0;
+    for (auto v : rl) sum += v;
+    if (loss_host) *loss_host = (float)(sum * inv);
+    return OkStatus();
+}
+
+// ---------------------------------------------------------------------------------------------
+// backward of the last train_forward into the caller's flat fp32 gradient buffer (overwritten)
+Status train_backward(mrmt3_handle* h, float* grad, cudaStream_t s) {
+    TrainState* t = state(h);
+    if (!t || !t->B) return Error(5, "mrmt3_train_forward first");
+    MRMT3_CUDA_TRY(cudaSetDevice(h->device));
+    const int B = t->B, L = t->L, n_enc = h->cfg.n_enc_layers, n_dec = h->cfg.n_dec_layers;
+    const size_t Me = (size_t)B * kSegFrames, Md = (size_t)B * L;
+    const size_t Mmax = std::max(Me, Md), Mp = (Mmax + 63) & ~size_t(63);
+    const float eps = h->cfg.ln_eps;
+    const ARowMap id{nullptr, 1};
+    MRMT3_CUDA_TRY(cudaMemsetAsync(grad, 0, t->n_total * 4, s));
+
+    // W^T copies for the dgrad GEMMs
+    for (auto& sl : t->slots)
+        if (sl.w16) RUN(h, launch_transpose_bf16(sl.w16, sl.cols, sl.wt, sl.rows, sl.rows, sl.cols, s));
+
+    // scratch
+    const size_t kvN = (size_t)n_dec * 2 * kInner;
+    size_t need = Mmax * kDModel * 4 * 2 + Mmax * kDModel * 2 * 2 + Mmax * 2 * kDFF * 2 + Mmax * kDFF * 2 +
+                  Mmax * 3 * kInner * 2 + Mmax * kInner * 2 * 2 + Mp * 2 * kDFF * 2 * 2 + Mp * kvN * 2 * 2 +
+                  Me * kvN * 2 + (size_t)B * kHeads * std::max(L, kSegFrames) * 4 + (1 << 16);
+    MRMT3_TRY(t->scratch.reserve(need));
+    Bump bp{reinterpret_cast<char*>(t->scratch.p), 0, t->scratch.cap};
+    float* dH = bp.take<float>(Mmax * kDModel);
+    bf16* dHb = bp.take<bf16>(Mmax * kDModel);
+    bf16* dn = bp.take<bf16>(Mmax * kDModel);
+    bf16* draw = bp.take<bf16>(Mmax * 2 * kDFF);
+    bf16* dff = bp.take<bf16>(Mmax * kDFF);
+    bf16* dqkv = bp.take<bf16>(Mmax * 3 * kInner);
+    bf16* dctx = bp.take<bf16>(Mmax * kInner);
+    bf16* dqc = bp.take<bf16>(Mmax * kInner);
+    bf16* yT = bp.take<bf16>(std::max((size_t)2 * kDFF, kvN) * Mp);
+    bf16* xT = bp.take<bf16>(std::max((size_t)2 * kDFF, (size_t)kDModel) * Mp);
+    bf16* dkv = bp.take<bf16>(Me * kvN);
+    float* delta = bp.take<float>((size_t)B * kHeads * std::max(L, kSegFrames));
+    if (bp.used > bp.cap) return Error(2, "internal: backward scratch overflow");
+
+    auto G = [&](int slot) { return grad + t->slots[slot].off; };
+    // dX (M, Kin) bf16 = dY (M, N) . W (N, Kin)
+    auto dgrad = [&](const bf16* dY, int N, int slot, bf16* dX, size_t M) -> Status {
+        const ParamSlot& sl = t->slots[slot];
+        RUN(h, launch_gemm_tc(*h->tma, dY, N, M, id, sl.wt, N, (int)M, sl.cols, N, EpiStoreBf16{dX, sl.cols}, s));
+        return OkStatus();
+    };
+    // dW (N, Kin) fp32 = dY^T . X ; dY (M, N) with pitch ldy, X (M, Kin) with pitch ldx
+    auto wgrad = [&](const bf16* dY, int ldy, int N, const bf16* X, int ldx, int Kin, float* dW, size_t M) -> Status {
+        const size_t mp = (M + 63) & ~size_t(63);
+        if (mp != M) {
+            MRMT3_CUDA_TRY(cudaMemset2DAsync(yT + M, mp * 2, 0, (mp - M) * 2, N, s));
+            MRMT3_CUDA_TRY(cudaMemset2DAsync(xT + M, mp * 2, 0, (mp - M) * 2, Kin, s));
+        }
+        RUN(h, launch_transpose_bf16(dY, ldy, yT, (int)mp, (int)M, N, s));
+        RUN(h, launch_transpose_bf16(X, ldx, xT, (int)mp, (int)M, Kin, s));
+        RUN(h, launch_gemm_tc(*h->tma, yT, (int)mp, N, id, xT, (int)mp, N, Kin, (int)mp, EpiStoreF32{dW, Kin}, s));
+        return OkStatus();
+    };
+    auto cast_dH = [&](size_t M) -> Status {
+        RUN(h, launch_cast_f32_bf16(dH, dHb, M * kDModel, s));
+        return OkStatus();
+    };
+    auto attn_bwd = [&](const bf16* Q, long qb, int qr, const bf16* K, const bf16* V, long kb, long kh, int kr,
+                        const bf16* O, const bf16* dO, bf16* dQ, bf16* dK, bf16* dV, long dkb, long dkh, int dkr,
+                        const float* lse, int Tq, int Tk, int causal) -> Status {
+        AttnBwdParams ap{};
+        ap.Q = Q; ap.K = K; ap.V = V; ap.O = O; ap.dO = dO; ap.dQ = dQ; ap.dK = dK; ap.dV = dV;
+        ap.q_batch_stride = qb; ap.q_head_stride = kDKV; ap.q_row_stride = qr;
+        ap.k_batch_stride = ap.v_batch_stride = kb;
+        ap.k_head_stride = ap.v_head_stride = kh;
+        ap.k_row_stride = ap.v_row_stride = kr;
+        ap.o_batch_stride = (long)Tq * kInner; ap.o_head_stride = kDKV; ap.o_row_stride = kInner;
+        ap.dk_batch_stride = dkb; ap.dk_head_stride = dkh; ap.dk_row_stride = dkr;
+        ap.lse2 = lse; ap.delta = delta; ap.Tq = Tq; ap.Tk = Tk; ap.causal = causal; ap.causal_offset = 0;
+        RUN(h, launch_attn_bwd(ap, B, s));
+        h->launches += 1;
+        return OkStatus();
+    };
+    auto ffn_bwd = [&](const LayerSlots& ls, const LayerW& Lw, const LayerStash& st, size_t M) -> Status {
+        MRMT3_TRY(cast_dH(M));
+        MRMT3_TRY(dgrad(dHb, kDModel, ls.wff, dff, M));
+        MRMT3_TRY(wgrad(dHb, kDModel, kDModel, st.ff, kDFF, kDFF, G(ls.wff), M));
+        RUN(h, launch_gated_gelu_bwd(st.raw, dff, draw, M, s));
+        MRMT3_TRY(dgrad(draw, 2 * kDFF, ls.wi, dn, M));
+        MRMT3_TRY(wgrad(draw, 2 * kDFF, 2 * kDFF, st.n2, kDModel, kDModel, G(ls.wi), M));
+        RUN(h, launch_rmsnorm_bwd(st.h_mid, Lw.ln_ff, eps, dn, (int)M, dH, G(ls.ln_ff), s));
+        return OkStatus();
+    };
+    auto self_bwd = [&](const LayerSlots& ls, const LayerW& Lw, const LayerStash& st, size_t M, int T, int causal) -> Status {
+        MRMT3_TRY(cast_dH(M));
+        MRMT3_TRY(dgrad(dHb, kDModel, ls.wo, dctx, M));
+        MRMT3_TRY(wgrad(dHb, kDModel, kDModel, st.ctx, kInner, kInner, G(ls.wo), M));
+        const long tb = (long)T * 3 * kInner;
+        MRMT3_TRY(attn_bwd(st.qkv, tb, 3 * kInner, st.qkv + kInner, st.qkv + 2 * kInner, tb, kDKV, 3 * kInner, st.ctx, dctx,
+                           dqkv, dqkv + kInner, dqkv + 2 * kInner, tb, kDKV, 3 * kInner, st.lse, T, T, causal));
+        MRMT3_TRY(dgrad(dqkv, 3 * kInner, ls.wqkv, dn, M));
+        MRMT3_TRY(wgrad(dqkv, 3 * kInner, 3 * kInner, st.n1, kDModel, kDModel, G(ls.wqkv), M));
+        RUN(h, launch_rmsnorm_bwd(st.h_in, Lw.ln_self, eps, dn, (int)M, dH, G(ls.ln_self), s));
+        return OkStatus();
+    };
+
+    // ---- head ----
+    MRMT3_CUDA_TRY(cudaMemsetAsync(dH, 0, Md * kDModel * 4, s));
+    MRMT3_TRY(dgrad(t->dlogits, kVocab, t->lm_head, dn, Md));
+    MRMT3_TRY(wgrad(t->dlogits, kVocab, kVocab, t->dec_n_final, kDModel, kDModel, G(t->lm_head), Md));
+    RUN(h, launch_rmsnorm_bwd(t->dec_h_final, h->dec.final_ln, eps, dn, (int)Md, dH, G(t->dec_final), s));
+
+    // ---- decoder layers, last to first ----
+    MRMT3_CUDA_TRY(cudaMemsetAsync(dkv, 0, Me * kvN * 2, s));
+    const size_t lane_sz = (size_t)n_dec * 2 * kHeads * h->tk_cap * kDKV;
+    for (int li = n_dec - 1; li >= 0; --li) {
+        const LayerW& Lw = h->dec.layers[li];
+        const LayerSlots& ls = t->dec[li];
+        const LayerStash& st = t->dec_st[li];
+        MRMT3_TRY(ffn_bwd(ls, Lw, st, Md));
+        // cross-attention sublayer
+        MRMT3_TRY(cast_dH(Md));
+        MRMT3_TRY(dgrad(dHb, kDModel, ls.co, dctx, Md));
+        MRMT3_TRY(wgrad(dHb, kDModel, kDModel, st.ctx_c, kInner, kInner, G(ls.co), Md));
+        const bf16* kbase = h->cross_cache.as<bf16>() + (size_t)li * 2 * kHeads * h->tk_cap * kDKV;
+        // dK / dV of this layer go straight into the (B*256, n_dec*768) operand of the stacked K/V weight
+        bf16* dk_l = dkv + (size_t)li * 2 * kInner;
+        MRMT3_TRY(attn_bwd(st.qc, (long)L * kInner, kInner, kbase, kbase + (size_t)kHeads * h->tk_cap * kDKV, (long)lane_sz,
+                           (long)h->tk_cap * kDKV, kDKV, st.ctx_c, dctx, dqc, dk_l, dk_l + kInner,
+                           (long)kSegFrames * (long)kvN, kDKV, (int)kvN, st.lse_c, L, kSegFrames, 0));
+        MRMT3_TRY(dgrad(dqc, kInner, ls.cq, dn, Md));
+        MRMT3_TRY(wgrad(dqc, kInner, kInner, st.nc, kDModel, kDModel, G(ls.cq), Md));
+        RUN(h, launch_rmsnorm_bwd(st.h_mid2, Lw.ln_cross, eps, dn, (int)Md, dH, G(ls.ln_cross), s));
+        MRMT3_TRY(self_bwd(ls, Lw, st, Md, L, 1));
+    }
+    RUN(h, launch_embed_bwd(t->dec_ids, dH, G(t->emb), (int)Md, s));
+
+    // ---- cross K/V projection -> encoder output ----
+    MRMT3_CUDA_TRY(cudaMemsetAsync(dH, 0, Me * kDModel * 4, s));
+    MRMT3_TRY(dgrad(dkv, (int)kvN, t->cross_kv, dn, Me));
+    MRMT3_TRY(wgrad(dkv, (int)kvN, (int)kvN, t->enc_n_final, kDModel, kDModel, G(t->cross_kv), Me));
+    RUN(h, launch_rmsnorm_bwd(t->enc_h_final, h->enc.final_ln, eps, dn, (int)Me, dH, G(t->enc_final), s));
+    for (int li = n_enc - 1; li >= 0; --li) {
+        MRMT3_TRY(ffn_bwd(t->enc[li], h->enc.layers[li], t->enc_st[li], Me));
+        MRMT3_TRY(self_bwd(t->enc[li], h->enc.layers[li], t->enc_st[li], Me, kSegFrames, 0));
+    }
+    // proj: h0 = mel . Wproj^T + PE
+    MRMT3_TRY(cast_dH(Me));
+    MRMT3_TRY(wgrad(dHb, kDModel, kDModel, t->mel16, kMels, kMels, G(t->proj), Me));
+    return OkStatus();
+}
+
+// AdamW step on the (possibly all-reduced) flat gradient; refreshes the bf16 weights and the
+// norm-folded decoder copies
+Status train_apply(mrmt3_handle* h, const float* grad, float lr, float beta1, float beta2, float adam_eps, float wd,
+                   cudaStream_t s) {
+    TrainState* t = state(h);
+    if (!t) return Error(5, "mrmt3_train_init first");
+    MRMT3_CUDA_TRY(cudaSetDevice(h->device));
+    ++t->step;
+    for (auto& sl : t->slots) {
+        const size_t n = (size_t)sl.rows * sl.cols;
+        float* p = sl.w32 ? sl.w32 : t->master.as<float>() + sl.off;
+        RUN(h, launch_adamw(p, grad + sl.off, t->m.as<float>() + sl.off, t->v.as<float>() + sl.off, sl.w16, n, lr, beta1,
+                            beta2, adam_eps, wd, t->step, s));
+    }
+    // masters of the norm-folded decode weights follow their training masters
+    auto sync_master = [&](float* dst, int slot) -> Status {
+        const ParamSlot& sl = t->slots[slot];
+        MRMT3_CUDA_TRY(cudaMemcpyAsync(dst, t->master.as<float>() + sl.off, (size_t)sl.rows * sl.cols * 4,
+                                       cudaMemcpyDeviceToDevice, s));
+        return OkStatus();
+    };
+    MRMT3_TRY(sync_master(h->m_lm_head, t->lm_head));
+    for (size_t i = 0; i < h->dec.layers.size(); ++i) {
+        LayerW& Lw = h->dec.layers[i];
+        MRMT3_TRY(sync_master(Lw.m_wqkv, t->dec[i].wqkv));
+        MRMT3_TRY(sync_master(Lw.m_cq, t->dec[i].cq));
+        MRMT3_TRY(sync_master(Lw.m_wi, t->dec[i].wi));
+        RUN(h, launch_fold_norm(Lw.m_wqkv, Lw.ln_self, Lw.wqkv_f, 3 * kInner, kDModel, s));
+        RUN(h, launch_fold_norm(Lw.m_cq, Lw.ln_cross, Lw.cq_f, kInner, kDModel, s));
+        RUN(h, launch_fold_norm(Lw.m_wi, Lw.ln_ff, Lw.wi_f, 2 * kDFF, kDModel, s));
+    }
+    RUN(h, launch_fold_norm(h->m_lm_head, h->dec.final_ln, h->lm_head_f, kVocab, kDModel, s));
+    return OkStatus();
+}
+
+}  // namespace mrmt3

@@ -1,0 +1,44 @@
+// Backward-pass and optimizer kernels of the fine-tune step (train_kernels.cu) and the training
+// state kept in the handle (train.cu).
+#pragma once
+#include "attention.cuh"
+#include "common.cuh"
+
+namespace mrmt3 {
+
+Status launch_xent(const float* logits, const long long* labels, int rows, int V, float inv_count,
+                   float* row_loss, bf16* dlogits, cudaStream_t s);
+Status launch_rmsnorm_bwd(const float* x, const float* g, float eps, const bf16* dy, int rows, float* dres,
+                          float* dg, cudaStream_t s);
+Status launch_gated_gelu_fwd(const bf16* raw, bf16* ff, size_t rows, cudaStream_t s);
+Status launch_gated_gelu_bwd(const bf16* raw, const bf16* dff, bf16* draw, size_t rows, cudaStream_t s);
+Status launch_transpose_bf16(const bf16* in, int ld_in, bf16* out, int ld_out, int R, int C, cudaStream_t s);
+Status launch_transpose_f32_to_bf16(const float* in, bf16* out, int R, int C, cudaStream_t s);
+Status launch_embed_bwd(const long long* ids, const float* dH, float* dEmb, int rows, cudaStream_t s);
+Status launch_cast_f32_bf16(const float* in, bf16* out, size_t n, cudaStream_t s);
+Status launch_bf16_to_f32(const bf16* in, float* out, size_t n, cudaStream_t s);
+Status launch_adamw(float* p, const float* g, float* m, float* v, bf16* p_bf16, size_t n, float lr, float beta1,
+                    float beta2, float eps, float wd, int step, cudaStream_t s);
+
+// attention backward; Q/K/V/O layouts as AttnFullParams, dQ in Q's layout, dO in O's layout,
+// dK/dV in their own (dk_*) layout; lse2 / delta are (batch, heads, Tq) fp32
+struct AttnBwdParams {
+    const bf16 *Q, *K, *V, *O, *dO;
+    bf16 *dQ, *dK, *dV;
+    long q_batch_stride, q_head_stride;
+    int q_row_stride;
+    long k_batch_stride, k_head_stride;
+    int k_row_stride;
+    long v_batch_stride, v_head_stride;
+    int v_row_stride;
+    long o_batch_stride, o_head_stride;
+    int o_row_stride;
+    long dk_batch_stride, dk_head_stride;
+    int dk_row_stride;
+    const float* lse2;
+    float* delta;
+    int Tq, Tk, causal, causal_offset;
+};
+Status launch_attn_bwd(const AttnBwdParams& p, int batch, cudaStream_t s);
+
+}  // namespace mrmt3

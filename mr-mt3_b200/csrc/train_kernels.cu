@@ -1,0 +1,574 @@
+// Backward-pass and optimizer kernels of the fine-tune step (BASELINE configs[4]; reference
+// tasks/mt3_net*.py training_step: logits -> cross-entropy(ignore_index=-100) -> autograd ->
+// AdamW).  The reference gets all of this from PyTorch autograd; here every op of the forward path
+// has a hand-written backward:
+//
+//   xent_kernel            softmax cross-entropy forward + d(logits), rows with label -100 ignored
+//   rmsnorm_bwd_kernel     T5LayerNorm backward (dx accumulated into the residual gradient, dg)
+//   gated_gelu_*           gated-GELU forward from the saved raw ffn-in output, and its backward
+//   transpose_bf16_kernel  (R, C) -> (C, R): dgrad / wgrad reuse the TN tcgen05 GEMM
+//   embed_bwd_kernel       scatter-add of the stack-input gradient into the embedding table
+//   attn_bwd_*             flash-style attention backward (no 1/sqrt(d) scale, no bias): row
+//                          statistics D = rowsum(dO * O), then dK/dV per key tile and dQ per query
+//                          tile, recomputing P from the saved log-sum-exp
+//   adamw_kernel           AdamW on fp32 masters, refreshed bf16 copy
+#include "train.cuh"
+
+#include <algorithm>
+
+namespace mrmt3 {
+
+// ---------------------------------------------------------------------------------------------
+// cross-entropy: one warp per row of V logits
+__global__ void __launch_bounds__(256)
+    xent_kernel(const float* __restrict__ logits, const long long* __restrict__ labels, int rows, int V,
+                float inv_count, float* __restrict__ row_loss, bf16* __restrict__ dlogits) {
+    const int row = blockIdx.x * 8 + (threadIdx.x >> 5);
+    const int lane = threadIdx.x & 31;
+    if (row >= rows) return;
+    const float* x = logits + (size_t)row * V;
+    bf16* dx = dlogits + (size_t)row * V;
+    const long long label = labels[row];
+    if (label < 0) {  // ignore_index
+        if (lane == 0) row_loss[row] = 0.f;
+        for (int j = lane * 2; j < V; j += 64) *reinterpret_cast<uint32_t*>(dx + j) = 0u;
+        return;
+    }
+    float mx = -INFINITY;
+    for (int j = lane; j < V; j += 32) mx = fmaxf(mx, x[j]);
+    mx = warp_max(mx);
+    float se = 0.f;
+    for (int j = lane; j < V; j += 32) se += __expf(x[j] - mx);
+    se = warp_sum(se);
+    const float lse = mx + __logf(se);
+    if (lane == 0) row_loss[row] = lse - x[label];
+    const float inv_se = 1.f / se;
+    for (int j = lane * 2; j < V; j += 64) {
+        float p0 = __expf(x[j] - mx) * inv_se - (j == label ? 1.f : 0.f);
+        float p1 = __expf(x[j + 1] - mx) * inv_se - (j + 1 == label ? 1.f : 0.f);
+        *reinterpret_cast<uint32_t*>(dx + j) = pack_bf16(p0 * inv_count, p1 * inv_count);
+    }
+}
+
+Status launch_xent(const float* logits, const long long* labels, int rows, int V, float inv_count,
+                   float* row_loss, bf16* dlogits, cudaStream_t s) {
+    if (rows <= 0) return OkStatus();
+    xent_kernel<<<ceil_div(rows, 8), 256, 0, s>>>(logits, labels, rows, V, inv_count, row_loss, dlogits);
+    MRMT3_CHECK_LAUNCH();
+    return OkStatus();
+}
+
+// ---------------------------------------------------------------------------------------------
+// RMSNorm backward.  y = g * x * r, r = rsqrt(mean(x^2) + eps):
+//   dx = r * (g * dy) - x * r^3 / d * sum_j (g_j dy_j x_j);  dg_j = sum_rows dy_j x_j r
+// dx is ADDED to dres (the gradient of the residual stream the norm branched from).
+__global__ void __launch_bounds__(256)
+    rmsnorm_bwd_kernel(const float* __restrict__ x, const float* __restrict__ g, float eps,
+                       const bf16* __restrict__ dy, int rows, float* __restrict__ dres, float* __restrict__ dg) {
+    __shared__ float s_dg[kDModel];
+    for (int i = threadIdx.x; i < kDModel; i += 256) s_dg[i] = 0.f;
+    __syncthreads();
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    float acc_dg[16];
+#pragma unroll
+    for (int i = 0; i < 16; ++i) acc_dg[i] = 0.f;
+    const float4* gr = reinterpret_cast<const float4*>(g);
+    float4 gv[4];
+#pragma unroll
+    for (int i = 0; i < 4; ++i) gv[i] = gr[lane + i * 32];
+    for (int row = blockIdx.x * 8 + warp; row < rows; row += gridDim.x * 8) {
+        const float4* xr = reinterpret_cast<const float4*>(x + (size_t)row * kDModel);
+        const uint2* dyr = reinterpret_cast<const uint2*>(dy + (size_t)row * kDModel);
+        float4 xv[4], dv[4];
+        float ss = 0.f, dot = 0.f;
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+            xv[i] = xr[lane + i * 32];
+            uint2 raw = dyr[lane + i * 32];
+            float2 a = __bfloat1622float2(*reinterpret_cast<bf162*>(&raw.x));
+            float2 b = __bfloat1622float2(*reinterpret_cast<bf162*>(&raw.y));
+            dv[i] = make_float4(a.x, a.y, b.x, b.y);
+            ss += xv[i].x * xv[i].x + xv[i].y * xv[i].y + xv[i].z * xv[i].z + xv[i].w * xv[i].w;
+            dot += gv[i].x * dv[i].x * xv[i].x + gv[i].y * dv[i].y * xv[i].y + gv[i].z * dv[i].z * xv[i].z +
+                   gv[i].w * dv[i].w * xv[i].w;
+        }
+        ss = warp_sum(ss);
+        dot = warp_sum(dot);
+        const float r = rsqrtf(ss * (1.0f / kDModel) + eps);
+        const float c = dot * r * r * r * (1.0f / kDModel);
+        float4* dr = reinterpret_cast<float4*>(dres + (size_t)row * kDModel);
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+            float4 d = dr[lane + i * 32];
+            d.x += r * gv[i].x * dv[i].x - xv[i].x * c;
+            d.y += r * gv[i].y * dv[i].y - xv[i].y * c;
+            d.z += r * gv[i].z * dv[i].z - xv[i].z * c;
+            d.w += r * gv[i].w * dv[i].w - xv[i].w * c;
+            dr[lane + i * 32] = d;
+            acc_dg[i * 4 + 0] += dv[i].x * xv[i].x * r;
+            acc_dg[i * 4 + 1] += dv[i].y * xv[i].y * r;
+            acc_dg[i * 4 + 2] += dv[i].z * xv[i].z * r;
+            acc_dg[i * 4 + 3] += dv[i].w * xv[i].w * r;
+        }
+    }
+#pragma unroll
+    for (int i = 0; i < 4; ++i)
+#pragma unroll
+        for (int k = 0; k < 4; ++k) atomicAdd(&s_dg[(lane + i * 32) * 4 + k], acc_dg[i * 4 + k]);
+    __syncthreads();
+    for (int i = threadIdx.x; i < kDModel; i += 256) atomicAdd(dg + i, s_dg[i]);
+}
+
+Status launch_rmsnorm_bwd(const float* x, const float* g, float eps, const bf16* dy, int rows, float* dres,
+                          float* dg, cudaStream_t s) {
+    if (rows <= 0) return OkStatus();
+    rmsnorm_bwd_kernel<<<std::min(ceil_div(rows, 8), 592), 256, 0, s>>>(x, g, eps, dy, rows, dres, dg);
+    MRMT3_CHECK_LAUNCH();
+    return OkStatus();
+}
+
+// ---------------------------------------------------------------------------------------------
+// gated GELU from the raw ffn-in output (columns interleaved: 2j -> wi_0, 2j+1 -> wi_1)
+__global__ void gated_gelu_fwd_kernel(const uint32_t* __restrict__ raw, bf16* __restrict__ ff, size_t n) {
+    size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    uint32_t v = raw[i];
+    float2 ab = __bfloat1622float2(*reinterpret_cast<bf162*>(&v));
+    ff[i] = __float2bfloat16(gelu_new(ab.x) * ab.y);
+}
+
+__global__ void gated_gelu_bwd_kernel(const uint32_t* __restrict__ raw, const bf16* __restrict__ dff,
+                                      uint32_t* __restrict__ draw, size_t n) {
+    size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    uint32_t v = raw[i];
+    float2 ab = __bfloat1622float2(*reinterpret_cast<bf162*>(&v));
+    const float a = ab.x, b = ab.y, d = __bfloat162float(dff[i]);
+    const float k = 0.7978845608028654f;
+    const float t = tanhf(k * (a + 0.044715f * a * a * a));
+    const float gelu = 0.5f * a * (1.0f + t);
+    const float dgelu = 0.5f * (1.0f + t) + 0.5f * a * (1.0f - t * t) * k * (1.0f + 3.0f * 0.044715f * a * a);
+    draw[i] = pack_bf16(d * b * dgelu, d * gelu);
+}
+
+Status launch_gated_gelu_fwd(const bf16* raw, bf16* ff, size_t rows, cudaStream_t s) {
+    size_t n = rows * kDFF;
+    if (!n) return OkStatus();
+    gated_gelu_fwd_kernel<<<(unsigned)((n + 255) / 256), 256, 0, s>>>(reinterpret_cast<const uint32_t*>(raw), ff, n);
+    MRMT3_CHECK_LAUNCH();
+    return OkStatus();
+}
+Status launch_gated_gelu_bwd(const bf16* raw, const bf16* dff, bf16* draw, size_t rows, cudaStream_t s) {
+    size_t n = rows * kDFF;
+    if (!n) return OkStatus();
+    gated_gelu_bwd_kernel<<<(unsigned)((n + 255) / 256), 256, 0, s>>>(reinterpret_cast<const uint32_t*>(raw), dff,
+                                                                    reinterpret_cast<uint32_t*>(draw), n);
+    MRMT3_CHECK_LAUNCH();
+    return OkStatus();
+}
+
+// ---------------------------------------------------------------------------------------------
+// (R, C) bf16 row-major with row pitch ld_in -> (C, R) with row pitch ld_out
+__global__ void __launch_bounds__(256)
+    transpose_bf16_kernel(const bf16* __restrict__ in, int ld_in, bf16* __restrict__ out, int ld_out, int R, int C) {
+    __shared__ bf16 tile[64][66];
+    const int r0 = blockIdx.y * 64, c0 = blockIdx.x * 64;
+    for (int i = threadIdx.x; i < 64 * 64; i += 256) {
+        int r = i >> 6, c = i & 63;
+        tile[r][c] = (r0 + r < R && c0 + c < C) ? in[(size_t)(r0 + r) * ld_in + c0 + c] : __float2bfloat16(0.f);
+    }
+    __syncthreads();
+    for (int i = threadIdx.x; i < 64 * 64; i += 256) {
+        int c = i >> 6, r = i & 63;
+        if (c0 + c < C && r0 + r < R) out[(size_t)(c0 + c) * ld_out + r0 + r] = tile[r][c];
+    }
+}
+
+Status launch_transpose_bf16(const bf16* in, int ld_in, bf16* out, int ld_out, int R, int C, cudaStream_t s) {
+    if (R <= 0 || C <= 0) return OkStatus();
+    transpose_bf16_kernel<<<dim3(ceil_div(C, 64), ceil_div(R, 64)), 256, 0, s>>>(in, ld_in, out, ld_out, R, C);
+    MRMT3_CHECK_LAUNCH();
+    return OkStatus();
+}
+
+// fp32 -> bf16 transpose of a weight (used for the dgrad operand W^T): (R, C) fp32 -> (C, R) bf16
+__global__ void __launch_bounds__(256)
+    transpose_f32_to_bf16_kernel(const float* __restrict__ in, bf16* __restrict__ out, int R, int C) {
+    __shared__ float tile[32][33];
+    const int r0 = blockIdx.y * 32, c0 = blockIdx.x * 32;
+    for (int i = threadIdx.x; i < 32 * 32; i += 256) {
+        int r = i >> 5, c = i & 31;
+        tile[r][c] = (r0 + r < R && c0 + c < C) ? in[(size_t)(r0 + r) * C + c0 + c] : 0.f;
+    }
+    __syncthreads();
+    for (int i = threadIdx.x; i < 32 * 32; i += 256) {
+        int c = i >> 5, r = i & 31;
+        if (c0 + c < C && r0 + r < R) out[(size_t)(c0 + c) * R + r0 + r] = __float2bfloat16(tile[r][c]);
+    }
+}
+
+Status launch_transpose_f32_to_bf16(const float* in, bf16* out, int R, int C, cudaStream_t s) {
+    transpose_f32_to_bf16_kernel<<<dim3(ceil_div(C, 32), ceil_div(R, 32)), 256, 0, s>>>(in, out, R, C);
+    MRMT3_CHECK_LAUNCH();
+    return OkStatus();
+}
+
+// ---------------------------------------------------------------------------------------------
+// dEmb[ids[r]] += dH[r]   (rows of 512 fp32)
+__global__ void embed_bwd_kernel(const long long* __restrict__ ids, const float* __restrict__ dH,
+                                 float* __restrict__ dEmb, int rows) {
+    int row = blockIdx.x * 2 + (threadIdx.x >> 7);
+    if (row >= rows) return;
+    int c = (threadIdx.x & 127) * 4;
+    const float4 v = *reinterpret_cast<const float4*>(dH + (size_t)row * kDModel + c);
+    float* d = dEmb + (size_t)ids[row] * kDModel + c;
+    atomicAdd(d + 0, v.x);
+    atomicAdd(d + 1, v.y);
+    atomicAdd(d + 2, v.z);
+    atomicAdd(d + 3, v.w);
+}
+
+Status launch_embed_bwd(const long long* ids, const float* dH, float* dEmb, int rows, cudaStream_t s) {
+    if (rows <= 0) return OkStatus();
+    embed_bwd_kernel<<<ceil_div(rows, 2), 256, 0, s>>>(ids, dH, dEmb, rows);
+    MRMT3_CHECK_LAUNCH();
+    return OkStatus();
+}
+
+__global__ void bf16_to_f32_kernel(const bf16* __restrict__ in, float* __restrict__ out, size_t n) {
+    size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) out[i] = __bfloat162float(in[i]);
+}
+Status launch_bf16_to_f32(const bf16* in, float* out, size_t n, cudaStream_t s) {
+    if (!n) return OkStatus();
+    bf16_to_f32_kernel<<<(unsigned)((n + 255) / 256), 256, 0, s>>>(in, out, n);
+    MRMT3_CHECK_LAUNCH();
+    return OkStatus();
+}
+
+// fp32 (n) -> bf16
+__global__ void cast_f32_bf16_kernel(const float* __restrict__ in, bf16* __restrict__ out, size_t n) {
+    size_t i = ((size_t)blockIdx.x * blockDim.x + threadIdx.x) * 2;
+    if (i + 1 < n) *reinterpret_cast<uint32_t*>(out + i) = pack_bf16(in[i], in[i + 1]);
+    else if (i < n) out[i] = __float2bfloat16(in[i]);
+}
+Status launch_cast_f32_bf16(const float* in, bf16* out, size_t n, cudaStream_t s) {
+    if (!n) return OkStatus();
+    cast_f32_bf16_kernel<<<(unsigned)((n / 2 + 256) / 256), 256, 0, s>>>(in, out, n);
+    MRMT3_CHECK_LAUNCH();
+    return OkStatus();
+}
+
+// ---------------------------------------------------------------------------------------------
+// AdamW (torch.optim.AdamW semantics: decoupled weight decay, bias-corrected moments)
+__global__ void adamw_kernel(float* __restrict__ p, const float* __restrict__ g, float* __restrict__ m,
+                             float* __restrict__ v, bf16* __restrict__ p_bf16, size_t n, float lr, float beta1,
+                             float beta2, float eps, float wd, float bc1, float bc2) {
+    size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    float pi = p[i], gi = g[i];
+    pi *= 1.f - lr * wd;
+    float mi = beta1 * m[i] + (1.f - beta1) * gi;
+    float vi = beta2 * v[i] + (1.f - beta2) * gi * gi;
+    m[i] = mi;
+    v[i] = vi;
+    pi -= lr * (mi / bc1) / (sqrtf(vi / bc2) + eps);
+    p[i] = pi;
+    if (p_bf16) p_bf16[i] = __float2bfloat16(pi);
+}
+
+Status launch_adamw(float* p, const float* g, float* m, float* v, bf16* p_bf16, size_t n, float lr, float beta1,
+                    float beta2, float eps, float wd, int step, cudaStream_t s) {
+    if (!n) return OkStatus();
+    const float bc1 = 1.f - powf(beta1, (float)step), bc2 = 1.f - powf(beta2, (float)step);
+    adamw_kernel<<<(unsigned)((n + 255) / 256), 256, 0, s>>>(p, g, m, v, p_bf16, n, lr, beta1, beta2, eps, wd, bc1, bc2);
+    MRMT3_CHECK_LAUNCH();
+    return OkStatus();
+}
+
+// ---------------------------------------------------------------------------------------------
+// attention backward.  Layout conventions are those of AttnFullParams (attention.cuh): element
+// (b, head, row, d) of X at X + b*x_batch_stride + head*x_head_stride + row*x_row_stride + d.
+// lse2[b][head][row] = m*log2(e) + log2(l) from the forward kernel, so p = exp2(s*log2(e) - lse2).
+// The dQ kernel runs first and leaves delta[b][head][row] = sum_k P dP for the dK/dV kernel.
+constexpr int kBwdT = 64;  // query and key tile
+
+__device__ __forceinline__ void bwd_load_tile(bf16* dst, const bf16* src, int row_stride, int r0, int rmax) {
+    // 64 rows x 8 chunks of 16 B, 128 threads -> 4 chunks each, XOR-swizzled like attn_full_kernel
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+        int c = threadIdx.x + i * 128;
+        int row = c >> 3, ch = c & 7;
+        bool pred = (r0 + row) < rmax;
+        const bf16* g = src + (size_t)(pred ? r0 + row : 0) * row_stride + ch * 8;
+        cp_async16(dst + row * kDKV + ((ch ^ (row & 7)) << 3), g, pred);
+    }
+}
+
+// A fragments (16 rows of this warp x 64 cols) of a [64][64] swizzled tile
+__device__ __forceinline__ void bwd_a_frags(uint32_t (&f)[4][4], const bf16* tile, int warp, int lane) {
+    const uint32_t base = smem_u32(tile);
+#pragma unroll
+    for (int kk = 0; kk < 4; ++kk) {
+        int row = warp * 16 + (lane & 15);
+        int ch = kk * 2 + (lane >> 4);
+        ldmatrix_x4(f[kk][0], f[kk][1], f[kk][2], f[kk][3], base + row * 128 + ((ch ^ (row & 7)) << 4));
+    }
+}
+
+// acc(16 x 64) += A(16 x 64 over k) * T^T where T is a [64 n][64 k] swizzled tile ("K-style" operand)
+__device__ __forceinline__ void bwd_mma_nt(float (&acc)[8][4], const uint32_t (&a)[4][4], const bf16* tile, int lane) {
+    const uint32_t base = smem_u32(tile);
+#pragma unroll
+    for (int kk = 0; kk < 4; ++kk) {
+#pragma unroll
+        for (int nj = 0; nj < 4; ++nj) {
+            int row = nj * 16 + (lane & 7) + ((lane >> 4) << 3);
+            int ch = kk * 2 + ((lane >> 3) & 1);
+            uint32_t b0, b1, b2, b3;
+            ldmatrix_x4(b0, b1, b2, b3, base + row * 128 + ((ch ^ (row & 7)) << 4));
+            mma_bf16_16816(acc[nj * 2], a[kk], b0, b1);
+            mma_bf16_16816(acc[nj * 2 + 1], a[kk], b2, b3);
+        }
+    }
+}
+
+// acc(16 x 64) += A(16 x 64 over k) * T where T is a [64 k][64 n] swizzled tile ("V-style" operand)
+__device__ __forceinline__ void bwd_mma_nn(float (&acc)[8][4], const uint32_t (&a)[4][4], const bf16* tile, int lane) {
+    const uint32_t base = smem_u32(tile);
+#pragma unroll
+    for (int kk = 0; kk < 4; ++kk) {
+#pragma unroll
+        for (int nj = 0; nj < 4; ++nj) {
+            int row = kk * 16 + (lane & 7) + (((lane >> 3) & 1) << 3);
+            int ch = nj * 2 + (lane >> 4);
+            uint32_t b0, b1, b2, b3;
+            ldmatrix_x4_trans(b0, b1, b2, b3, base + row * 128 + ((ch ^ (row & 7)) << 4));
+            mma_bf16_16816(acc[nj * 2], a[kk], b0, b1);
+            mma_bf16_16816(acc[nj * 2 + 1], a[kk], b2, b3);
+        }
+    }
+}
+
+// C fragment (16 x 64 fp32) -> A fragments (bf16), the FlashAttention register trick
+__device__ __forceinline__ void bwd_c_to_a(uint32_t (&a)[4][4], const float (&c)[8][4]) {
+#pragma unroll
+    for (int ni = 0; ni < 8; ++ni) {
+        a[ni >> 1][(ni & 1) * 2 + 0] = pack_bf16(c[ni][0], c[ni][1]);
+        a[ni >> 1][(ni & 1) * 2 + 1] = pack_bf16(c[ni][2], c[ni][3]);
+    }
+}
+
+__device__ __forceinline__ void bwd_zero(float (&c)[8][4]) {
+#pragma unroll
+    for (int i = 0; i < 8; ++i)
+#pragma unroll
+        for (int r = 0; r < 4; ++r) c[i][r] = 0.f;
+}
+
+// dQ: one CTA per (query tile, head, batch); loops over the key tiles.
+//   S = Q K^T, P = exp2(S log2e - lse2[row]), dP = dO V^T, dS = P * (dP - delta[row]), dQ += dS K
+__global__ void __launch_bounds__(128)
+    attn_bwd_dq_kernel(AttnBwdParams p) {
+    __shared__ __align__(128) bf16 sQ[kBwdT * kDKV];
+    __shared__ __align__(128) bf16 sdO[kBwdT * kDKV];
+    __shared__ __align__(128) bf16 sK[kBwdT * kDKV];
+    __shared__ __align__(128) bf16 sV[kBwdT * kDKV];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int q0 = blockIdx.x * kBwdT, head = blockIdx.y, b = blockIdx.z;
+    const bf16* Q = p.Q + (size_t)b * p.q_batch_stride + head * p.q_head_stride;
+    const bf16* K = p.K + (size_t)b * p.k_batch_stride + head * p.k_head_stride;
+    const bf16* V = p.V + (size_t)b * p.v_batch_stride + head * p.v_head_stride;
+    const bf16* dO = p.dO + (size_t)b * p.o_batch_stride + head * p.o_head_stride;
+    const float kLog2e = 1.4426950408889634f;
+
+    bwd_load_tile(sQ, Q, p.q_row_stride, q0, p.Tq);
+    bwd_load_tile(sdO, dO, p.o_row_stride, q0, p.Tq);
+    cp_async_commit();
+    cp_async_wait<0>();
+    __syncthreads();
+    uint32_t qf[4][4], dof[4][4];
+    bwd_a_frags(qf, sQ, warp, lane);
+    bwd_a_frags(dof, sdO, warp, lane);
+
+    const int row_lo = q0 + warp * 16 + (lane >> 2);
+    float lse[2], dl[2] = {0.f, 0.f};
+#pragma unroll
+    for (int h = 0; h < 2; ++h) {
+        int r = row_lo + h * 8;
+        lse[h] = p.lse2[((size_t)b * kHeads + head) * p.Tq + min(r, p.Tq - 1)];
+    }
+    int n_kt = (p.Tk + kBwdT - 1) / kBwdT;
+    if (p.causal) n_kt = min(n_kt, max(0, (q0 + kBwdT - 1 + p.causal_offset) / kBwdT + 1));
+    // pass 1: delta[row] = sum_k P dP with the SAME recomputed P and dP that pass 2 uses, so that
+    // dS = P (dP - delta) sums to zero over every row exactly as in exact arithmetic (taking
+    // delta = sum_d dO O from the bf16 output instead leaves a 2^-9 mismatch that dominates dS on
+    // sharply peaked rows)
+    for (int kt = 0; kt < n_kt; ++kt) {
+        __syncthreads();
+        bwd_load_tile(sK, K, p.k_row_stride, kt * kBwdT, p.Tk);
+        bwd_load_tile(sV, V, p.v_row_stride, kt * kBwdT, p.Tk);
+        cp_async_commit();
+        cp_async_wait<0>();
+        __syncthreads();
+        float s[8][4], dp[8][4];
+        bwd_zero(s);
+        bwd_zero(dp);
+        bwd_mma_nt(s, qf, sK, lane);
+        bwd_mma_nt(dp, dof, sV, lane);
+#pragma unroll
+        for (int ni = 0; ni < 8; ++ni) {
+#pragma unroll
+            for (int r = 0; r < 4; ++r) {
+                const int key = kt * kBwdT + ni * 8 + (lane & 3) * 2 + (r & 1);
+                const int row = row_lo + ((r >> 1) << 3);
+                const bool ok = key < p.Tk && (!p.causal || key <= row + p.causal_offset);
+                if (ok) dl[r >> 1] += exp2f(s[ni][r] * kLog2e - lse[r >> 1]) * dp[ni][r];
+            }
+        }
+    }
+#pragma unroll
+    for (int h = 0; h < 2; ++h) {
+        dl[h] += __shfl_xor_sync(0xffffffffu, dl[h], 1);
+        dl[h] += __shfl_xor_sync(0xffffffffu, dl[h], 2);
+        int r = row_lo + h * 8;
+        if ((lane & 3) == 0 && r < p.Tq) p.delta[((size_t)b * kHeads + head) * p.Tq + r] = dl[h];
+    }
+    float dq[8][4];
+    bwd_zero(dq);
+    for (int kt = 0; kt < n_kt; ++kt) {
+        __syncthreads();  // previous tile fully consumed
+        bwd_load_tile(sK, K, p.k_row_stride, kt * kBwdT, p.Tk);
+        bwd_load_tile(sV, V, p.v_row_stride, kt * kBwdT, p.Tk);
+        cp_async_commit();
+        cp_async_wait<0>();
+        __syncthreads();
+        float s[8][4], dp[8][4];
+        bwd_zero(s);
+        bwd_zero(dp);
+        bwd_mma_nt(s, qf, sK, lane);
+        bwd_mma_nt(dp, dof, sV, lane);
+#pragma unroll
+        for (int ni = 0; ni < 8; ++ni) {
+#pragma unroll
+            for (int r = 0; r < 4; ++r) {
+                const int key = kt * kBwdT + ni * 8 + (lane & 3) * 2 + (r & 1);
+                const int row = row_lo + ((r >> 1) << 3);
+                const bool ok = key < p.Tk && (!p.causal || key <= row + p.causal_offset);
+                const float pr = ok ? exp2f(s[ni][r] * kLog2e - lse[r >> 1]) : 0.f;
+                s[ni][r] = pr * (dp[ni][r] - dl[r >> 1]);  // dS
+            }
+        }
+        uint32_t dsf[4][4];
+        bwd_c_to_a(dsf, s);
+        bwd_mma_nn(dq, dsf, sK, lane);
+    }
+    bf16* dQ = p.dQ + (size_t)b * p.q_batch_stride + head * p.q_head_stride;
+#pragma unroll
+    for (int ni = 0; ni < 8; ++ni) {
+        int col = ni * 8 + (lane & 3) * 2;
+        if (row_lo < p.Tq)
+            *reinterpret_cast<uint32_t*>(dQ + (size_t)row_lo * p.q_row_stride + col) = pack_bf16(dq[ni][0], dq[ni][1]);
+        if (row_lo + 8 < p.Tq)
+            *reinterpret_cast<uint32_t*>(dQ + (size_t)(row_lo + 8) * p.q_row_stride + col) = pack_bf16(dq[ni][2], dq[ni][3]);
+    }
+}
+
+// dK, dV: one CTA per (key tile, head, batch); loops over the query tiles, everything transposed
+// (rows = keys):  S^T = K Q^T, P^T = exp2(S^T log2e - lse2[col]), dV += P^T dO,
+//                 dP^T = V dO^T, dS^T = P^T * (dP^T - delta[col]), dK += dS^T Q
+__global__ void __launch_bounds__(128)
+    attn_bwd_dkv_kernel(AttnBwdParams p) {
+    __shared__ __align__(128) bf16 sK[kBwdT * kDKV];
+    __shared__ __align__(128) bf16 sV[kBwdT * kDKV];
+    __shared__ __align__(128) bf16 sQ[kBwdT * kDKV];
+    __shared__ __align__(128) bf16 sdO[kBwdT * kDKV];
+    __shared__ float s_lse[kBwdT], s_dl[kBwdT];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int k0 = blockIdx.x * kBwdT, head = blockIdx.y, b = blockIdx.z;
+    const bf16* Q = p.Q + (size_t)b * p.q_batch_stride + head * p.q_head_stride;
+    const bf16* K = p.K + (size_t)b * p.k_batch_stride + head * p.k_head_stride;
+    const bf16* V = p.V + (size_t)b * p.v_batch_stride + head * p.v_head_stride;
+    const bf16* dO = p.dO + (size_t)b * p.o_batch_stride + head * p.o_head_stride;
+    const float kLog2e = 1.4426950408889634f;
+
+    bwd_load_tile(sK, K, p.k_row_stride, k0, p.Tk);
+    bwd_load_tile(sV, V, p.v_row_stride, k0, p.Tk);
+    cp_async_commit();
+    cp_async_wait<0>();
+    __syncthreads();
+    uint32_t kf[4][4], vf[4][4];
+    bwd_a_frags(kf, sK, warp, lane);
+    bwd_a_frags(vf, sV, warp, lane);
+
+    const int key_lo = k0 + warp * 16 + (lane >> 2);  // this thread's keys: key_lo, key_lo + 8
+    const int n_qt = (p.Tq + kBwdT - 1) / kBwdT;
+    int qt0 = 0;
+    if (p.causal) qt0 = max(0, (k0 - p.causal_offset) / kBwdT);  // first query tile that can see key k0
+    float dk[8][4], dv[8][4];
+    bwd_zero(dk);
+    bwd_zero(dv);
+    for (int qt = qt0; qt < n_qt; ++qt) {
+        __syncthreads();
+        bwd_load_tile(sQ, Q, p.q_row_stride, qt * kBwdT, p.Tq);
+        bwd_load_tile(sdO, dO, p.o_row_stride, qt * kBwdT, p.Tq);
+        cp_async_commit();
+        if (threadIdx.x < kBwdT) {
+            int r = qt * kBwdT + threadIdx.x;
+            size_t idx = ((size_t)b * kHeads + head) * p.Tq + min(r, p.Tq - 1);
+            s_lse[threadIdx.x] = p.lse2[idx];
+            s_dl[threadIdx.x] = p.delta[idx];
+        }
+        cp_async_wait<0>();
+        __syncthreads();
+        float st[8][4], dpt[8][4];
+        bwd_zero(st);
+        bwd_zero(dpt);
+        bwd_mma_nt(st, kf, sQ, lane);    // S^T = K Q^T
+        bwd_mma_nt(dpt, vf, sdO, lane);  // dP^T = V dO^T
+        float pt[8][4];
+#pragma unroll
+        for (int ni = 0; ni < 8; ++ni) {
+#pragma unroll
+            for (int r = 0; r < 4; ++r) {
+                const int qc = ni * 8 + (lane & 3) * 2 + (r & 1);
+                const int row = qt * kBwdT + qc;              // query index
+                const int key = key_lo + ((r >> 1) << 3);
+                const bool ok = row < p.Tq && key < p.Tk && (!p.causal || key <= row + p.causal_offset);
+                const float pr = ok ? exp2f(st[ni][r] * kLog2e - s_lse[qc]) : 0.f;
+                pt[ni][r] = pr;
+                st[ni][r] = pr * (dpt[ni][r] - s_dl[qc]);     // dS^T
+            }
+        }
+        uint32_t af[4][4];
+        bwd_c_to_a(af, pt);
+        bwd_mma_nn(dv, af, sdO, lane);  // dV += P^T dO
+        bwd_c_to_a(af, st);
+        bwd_mma_nn(dk, af, sQ, lane);   // dK += dS^T Q
+    }
+    bf16* dK = p.dK + (size_t)b * p.dk_batch_stride + head * p.dk_head_stride;
+    bf16* dV = p.dV + (size_t)b * p.dk_batch_stride + head * p.dk_head_stride;
+#pragma unroll
+    for (int ni = 0; ni < 8; ++ni) {
+        int col = ni * 8 + (lane & 3) * 2;
+        if (key_lo < p.Tk) {
+            *reinterpret_cast<uint32_t*>(dK + (size_t)key_lo * p.dk_row_stride + col) = pack_bf16(dk[ni][0], dk[ni][1]);
+            *reinterpret_cast<uint32_t*>(dV + (size_t)key_lo * p.dk_row_stride + col) = pack_bf16(dv[ni][0], dv[ni][1]);
+        }
+        if (key_lo + 8 < p.Tk) {
+            *reinterpret_cast<uint32_t*>(dK + (size_t)(key_lo + 8) * p.dk_row_stride + col) = pack_bf16(dk[ni][2], dk[ni][3]);
+            *reinterpret_cast<uint32_t*>(dV + (size_t)(key_lo + 8) * p.dk_row_stride + col) = pack_bf16(dv[ni][2], dv[ni][3]);
+        }
+    }
+}
+
+Status launch_attn_bwd(const AttnBwdParams& p, int batch, cudaStream_t s) {
+    if (batch <= 0 || p.Tq <= 0 || p.Tk <= 0) return OkStatus();
+    attn_bwd_dq_kernel<<<dim3(ceil_div(p.Tq, kBwdT), kHeads, batch), 128, 0, s>>>(p);
+    MRMT3_CHECK_LAUNCH();
+    attn_bwd_dkv_kernel<<<dim3(ceil_div(p.Tk, kBwdT), kHeads, batch), 128, 0, s>>>(p);
+    MRMT3_CHECK_LAUNCH();
+    return OkStatus();
+}
+
+}  // namespace mrmt3

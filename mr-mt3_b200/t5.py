@@ -266,6 +266,39 @@ class T5ForConditionalGeneration(nn.Module):
         enc = (self.engine().encode(inputs),) if output_hidden_states else None
         return logits, enc, None
 
+    def train_step(self, inputs, labels, lr=1e-5, betas=(0.9, 0.999), eps=1e-8, weight_decay=0.01,
+                   process_group=None, apply=True):
+        """One fine-tune step of reference tasks/mt3_net.py `training_step` + AdamW
+        (`train.sh:78`: lr 1e-5): teacher-forced forward, CrossEntropyLoss(ignore_index=-100),
+        hand-written backward, mean all-reduce of the flat gradient over `process_group` (or the
+        default group when torch.distributed is initialised), AdamW.  Returns (loss, flat grad).
+        The engine's weights are updated in place; `sync_parameters_from_engine()` copies them back
+        into this module's parameters.  No dropout is applied."""
+        eng = self.engine()
+        eng.train_init()
+        logits, loss = eng.train_forward(inputs, self._shift_right(labels), labels)
+        grad = eng.train_backward()
+        import torch.distributed as dist
+        if dist.is_available() and dist.is_initialized() and dist.get_world_size(process_group) > 1:
+            dist.all_reduce(grad, op=dist.ReduceOp.SUM, group=process_group)
+            grad /= dist.get_world_size(process_group)
+        if apply:
+            eng.train_apply(grad, lr, betas, eps, weight_decay)
+        return loss, grad
+
+    @torch.no_grad()
+    def sync_parameters_from_engine(self):
+        """Copy the engine's trained fp32 masters back into this module's parameters."""
+        eng = self.engine()
+        flat = eng.train_read_master()
+        for name, p in self.state_dict().items():
+            try:
+                view = eng.flat_view(flat, name)
+            except _lib.MrMt3Error:
+                continue
+            p.copy_(view.reshape(p.shape).to(p.device))
+        self._engine_sig = self._weights_signature() if hasattr(self, "_weights_signature") else self._engine_sig
+
     def forward(self, inputs=None, labels=None, decoder_input_ids=None, **kwargs):
         """Reference models/t5.py:182-249: returns the logits tensor only."""
         kwargs.pop("num_insts", None)
