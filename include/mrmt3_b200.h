@@ -179,17 +179,19 @@ int mrmt3_memory_block(mrmt3_handle* h, const int64_t* prev_ids, int B, int Lp, 
                        void* stream);
 
 /* ---- fine-tune step ---------------------------------------------------------------------
- * Replaces: one `training_step` of tasks/mt3_net.py (forward models/t5.py:182-249 ->
- * CrossEntropyLoss(ignore_index=-100) -> loss.backward() -> AdamW.step()), for the plain MT3 model
- * (mem_variant NONE).  No dropout is applied.  Every trainable tensor lives in ONE flat fp32 order
+ * Replaces: one `training_step` of tasks/mt3_net.py / mt3_net_segmem_v2_with_prev.py (forward
+ * models/t5.py:182-249 or models/t5_segmem_v2_with_prev.py:155-224 -> CrossEntropyLoss(
+ * ignore_index=-100) -> loss.backward() -> AdamW.step()), for the MT3 and V2WithPrev models.
+ * No dropout is applied.  Every trainable tensor lives in ONE flat fp32 order
  * (the library's packed layouts); the caller owns the flat gradient buffer, so data-parallel
  * training is train_forward + train_backward on every rank, one all-reduce (mean) of the flat
  * buffer, train_apply on every rank.
  *   mrmt3_train_init     allocates fp32 masters and Adam moments; *n_params = flat length
  *   mrmt3_train_locate   where a reference state-dict tensor `name` (rows, cols) sits in the flat
  *                        order: element (r, c) at flat[offset + ((r*row_mul + row_off)*cols + c)]
- *   mrmt3_train_forward  mel (B,256,512) fp32, decoder_input_ids / labels (B,L) int64 ->
- *                        logits_out (B,L,vocab) fp32 and the mean loss in *loss_host
+ *   mrmt3_train_forward  mel (B,256,512) fp32, decoder_input_ids / labels (B,L) int64, for
+ *                        V2WithPrev also targets_prev (B,Lp) int64 with -100 already replaced by
+ *                        pad (else NULL, 0) -> logits_out (B,L,vocab) fp32, mean loss in *loss_host
  *   mrmt3_train_backward gradient of that loss w.r.t. every trainable tensor -> grad_flat (fp32)
  *   mrmt3_train_apply    AdamW (torch.optim.AdamW semantics) with grad_flat; refreshes the bf16
  *                        weights used by every other entry point
@@ -198,7 +200,8 @@ int mrmt3_train_init(mrmt3_handle* h, int64_t* n_params);
 int mrmt3_train_locate(mrmt3_handle* h, const char* name, int64_t* offset, int32_t* rows, int32_t* cols,
                        int32_t* row_mul, int32_t* row_off);
 int mrmt3_train_forward(mrmt3_handle* h, const float* mel, int B, const int64_t* decoder_input_ids,
-                        const int64_t* labels, int L, float* logits_out, float* loss_host, void* stream);
+                        const int64_t* labels, int L, const int64_t* targets_prev, int Lp, float* logits_out,
+                        float* loss_host, void* stream);
 int mrmt3_train_backward(mrmt3_handle* h, float* grad_flat, void* stream);
 int mrmt3_train_apply(mrmt3_handle* h, const float* grad_flat, float lr, float beta1, float beta2, float eps,
                       float weight_decay, void* stream);

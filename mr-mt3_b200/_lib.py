@@ -62,8 +62,8 @@ _PROTOTYPES = {
     "mrmt3_train_locate": (_c_int, [_c_void_p, ctypes.c_char_p, ctypes.POINTER(_c_i64), ctypes.POINTER(ctypes.c_int32),
                                     ctypes.POINTER(ctypes.c_int32), ctypes.POINTER(ctypes.c_int32),
                                     ctypes.POINTER(ctypes.c_int32)]),
-    "mrmt3_train_forward": (_c_int, [_c_void_p, _c_void_p, _c_int, _c_void_p, _c_void_p, _c_int, _c_void_p,
-                                     ctypes.POINTER(ctypes.c_float), _c_void_p]),
+    "mrmt3_train_forward": (_c_int, [_c_void_p, _c_void_p, _c_int, _c_void_p, _c_void_p, _c_int, _c_void_p, _c_int,
+                                     _c_void_p, ctypes.POINTER(ctypes.c_float), _c_void_p]),
     "mrmt3_train_backward": (_c_int, [_c_void_p, _c_void_p, _c_void_p]),
     "mrmt3_train_apply": (_c_int, [_c_void_p, _c_void_p, ctypes.c_float, ctypes.c_float, ctypes.c_float,
                                    ctypes.c_float, ctypes.c_float, _c_void_p]),
@@ -333,17 +333,21 @@ class Engine:
         packed = flat[off:off + ((rows - 1) * mul + ro + 1) * cols].view(-1, cols)
         return packed[ro::mul][:rows]
 
-    def train_forward(self, inputs, decoder_input_ids, labels):
+    def train_forward(self, inputs, decoder_input_ids, labels, targets_prev=None):
         """-> (logits (B, L, V) fp32, mean cross-entropy over labels != -100)."""
         x = self._mel(inputs)
         ids = decoder_input_ids.to(self.device, torch.int64).contiguous()
         lab = labels.to(self.device, torch.int64).contiguous()
         B, L = ids.shape
+        prev, Lp = None, 0
+        if targets_prev is not None:
+            prev = targets_prev.to(self.device, torch.int64).contiguous()
+            Lp = prev.shape[1]
         logits = torch.empty((B, L, VOCAB), dtype=torch.float32, device=self.device)
         loss = ctypes.c_float(0.0)
         with torch.cuda.device(self.device):
-            self._check(self._lib.mrmt3_train_forward(self._h, _ptr(x), B, _ptr(ids), _ptr(lab), L, _ptr(logits),
-                                                      ctypes.byref(loss), _stream()))
+            self._check(self._lib.mrmt3_train_forward(self._h, _ptr(x), B, _ptr(ids), _ptr(lab), L, _ptr(prev), Lp,
+                                                      _ptr(logits), ctypes.byref(loss), _stream()))
         return logits, float(loss.value)
 
     def train_backward(self, grad=None):

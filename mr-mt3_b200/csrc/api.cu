@@ -30,7 +30,7 @@ Status train_read_master(mrmt3_handle* h, float* out, cudaStream_t s);
 Status train_locate(mrmt3_handle* h, const std::string& name, long long* offset, int* rows, int* cols, int* row_mul,
                     int* row_off);
 Status train_forward(mrmt3_handle* h, const float* mel, int B, const long long* dec_ids, const long long* labels, int L,
-                     float* logits_out, float* loss_host, cudaStream_t s);
+                     const long long* targets_prev, int Lp, float* logits_out, float* loss_host, cudaStream_t s);
 Status train_backward(mrmt3_handle* h, float* grad, cudaStream_t s);
 Status train_apply(mrmt3_handle* h, const float* grad, float lr, float beta1, float beta2, float adam_eps, float wd,
                    cudaStream_t s);
@@ -284,10 +284,13 @@ int mrmt3_train_locate(mrmt3_handle* h, const char* name, int64_t* offset, int32
 }
 
 int mrmt3_train_forward(mrmt3_handle* h, const float* mel, int B, const int64_t* decoder_input_ids,
-                        const int64_t* labels, int L, float* logits_out, float* loss_host, void* stream) {
+                        const int64_t* labels, int L, const int64_t* targets_prev, int Lp, float* logits_out,
+                        float* loss_host, void* stream) {
     GUARD(h)
     return finish(h, train_forward(h, mel, B, reinterpret_cast<const long long*>(decoder_input_ids),
-                                   reinterpret_cast<const long long*>(labels), L, logits_out, loss_host, (cudaStream_t)stream));
+                                   reinterpret_cast<const long long*>(labels), L,
+                                   reinterpret_cast<const long long*>(targets_prev), Lp, logits_out, loss_host,
+                                   (cudaStream_t)stream));
     END_GUARD(h)
 }
 

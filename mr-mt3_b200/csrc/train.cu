@@ -4,7 +4,8 @@
 // The gradient lives in ONE flat fp32 buffer owned by the caller (packed-weight order), so data
 // parallel training is a single all-reduce of that buffer between `train_backward` and
 // `train_apply`.  Dropout is not applied (the parity oracle is the reference in
-// eval()-mode arithmetic).  Scope of this build: the plain MT3 model (mem_variant NONE).
+// eval()-mode arithmetic).  Models: plain MT3 (models/t5.py) and MR-MT3 V2WithPrev
+// (models/t5_segmem_v2_with_prev.py:60-153: memory block appended to the encoder output).
 //
 // GEMMs reuse the TN tcgen05 kernel:
 //   dgrad  dX[M,Kin] = dY[M,N] . W[N,Kin]        = A(dY) . (W^T)^T      with W^T[Kin,N] re-made per step
@@ -42,16 +43,19 @@ struct LayerStash {
 
 struct TrainState {
     std::vector<ParamSlot> slots;
-    std::vector<LayerSlots> enc, dec;
-    int proj = -1, emb = -1, lm_head = -1, cross_kv = -1, enc_final = -1, dec_final = -1;
+    std::vector<LayerSlots> enc, dec, mem;
+    int proj = -1, emb = -1, lm_head = -1, cross_kv = -1, enc_final = -1, dec_final = -1, mem_final = -1, segmem_proj = -1;
     size_t n_total = 0;
     DeviceBuffer master, m, v, wt_arena, stash, scratch;
     int step = 0;
     // the last forward's saved state
-    int B = 0, L = 0;
-    std::vector<LayerStash> enc_st, dec_st;
-    float *enc_h_final = nullptr, *dec_h_final = nullptr;
+    int B = 0, L = 0, Lp = 0, n_mem = 0;
+    std::vector<LayerStash> enc_st, dec_st, mem_st;
+    float *enc_h_final = nullptr, *dec_h_final = nullptr, *mem_h_final = nullptr;
     bf16 *mel16 = nullptr, *enc_n_final = nullptr, *dec_n_final = nullptr, *dlogits = nullptr;
+    bf16 *mem_emb16 = nullptr, *mem_n_final = nullptr, *kv_in = nullptr;  // kv_in: (B, T_k, d) rows fed to the K/V projection
+    const long long* prev_ids = nullptr;
+    DeviceBuffer prev_copy;
     float* row_loss = nullptr;
     const long long* dec_ids = nullptr;
     DeviceBuffer ids_copy;
@@ -63,7 +67,7 @@ void train_destroy(mrmt3_handle* h) {
     TrainState* t = state(h);
     if (!t) return;
     t->master.release(); t->m.release(); t->v.release(); t->wt_arena.release();
-    t->stash.release(); t->scratch.release(); t->ids_copy.release();
+    t->stash.release(); t->scratch.release(); t->ids_copy.release(); t->prev_copy.release();
     delete t;
     h->train = nullptr;
 }
@@ -98,8 +102,8 @@ static void add_stack(TrainState* t, StackW& st, bool decoder, std::vector<Layer
 Status train_init(mrmt3_handle* h) {
     if (h->train) return OkStatus();
     if (!h->committed) return Error(5, "weights not committed");
-    if (h->cfg.mem_variant != MRMT3_MEM_NONE)
-        return Error(2, "the fine-tune step is implemented for the plain MT3 model (mem_variant NONE) in this build");
+    if (h->cfg.mem_variant == MRMT3_MEM_V1_PREPEND)
+        return Error(2, "the fine-tune step is implemented for the MT3 and V2WithPrev models");
     MRMT3_CUDA_TRY(cudaSetDevice(h->device));
     TrainState* t = new TrainState();
     h->train = t;
@@ -109,6 +113,10 @@ Status train_init(mrmt3_handle* h) {
     t->cross_kv = add_slot(t, h->cross_kv_w, nullptr, h->cfg.n_dec_layers * 2 * kInner, kDModel);
     add_stack(t, h->enc, false, t->enc, t->enc_final);
     add_stack(t, h->dec, true, t->dec, t->dec_final);
+    if (h->cfg.mem_variant == MRMT3_MEM_V2_APPEND) {
+        t->segmem_proj = add_slot(t, h->segmem_proj, nullptr, kDModel, kDModel);
+        add_stack(t, h->mem, false, t->mem, t->mem_final);
+    }
     const size_t n = t->n_total;
     MRMT3_TRY(t->master.reserve(n * 4));
     MRMT3_TRY(t->m.reserve(n * 4));
@@ -172,8 +180,10 @@ Status train_locate(mrmt3_handle* h, const std::string& name, long long* offset,
     if (name == "proj.weight") return set(t->proj, d, d, 1, 0);
     if (name == "decoder_embed_tokens.weight") return set(t->emb, kVocab, d, 1, 0);
     if (name == "lm_head.weight") return set(t->lm_head, kVocab, d, 1, 0);
+    if (name == "segmem_proj.weight" && t->segmem_proj >= 0) return set(t->segmem_proj, d, d, 1, 0);
     struct { const char* n; std::vector<LayerSlots>* ls; int* fin; bool dec; } stacks[] = {
-        {"encoder.", &t->enc, &t->enc_final, false}, {"decoder.", &t->dec, &t->dec_final, true}};
+        {"encoder.", &t->enc, &t->enc_final, false}, {"decoder.", &t->dec, &t->dec_final, true},
+        {"segmem_encoder.", &t->mem, &t->mem_final, false}};
     for (auto& sk : stacks) {
         size_t pl = strlen(sk.n);
         if (name.compare(0, pl, sk.n) != 0) continue;
@@ -217,28 +227,36 @@ struct Bump {
     }
 };
 
-static size_t stash_bytes(int n_enc, int n_dec, size_t Me, size_t Md, int B, int L) {
+static size_t stash_bytes(int n_enc, int n_dec, int n_mem_layers, size_t Me, size_t Md, size_t Mm, int B, int L, int Lp) {
     auto layer = [&](size_t M, size_t T, bool dec) {
         size_t b = M * kDModel * 4 * (dec ? 3 : 2) + M * kDModel * 2 * (dec ? 3 : 2) + M * 3 * kInner * 2 +
                    M * kInner * 2 * (dec ? 3 : 1) + M * 2 * kDFF * 2 + M * kDFF * 2 + (size_t)B * kHeads * T * 4 * (dec ? 2 : 1);
         return b + 16 * 256;
     };
-    return n_enc * layer(Me, kSegFrames, false) + n_dec * layer(Md, L, true) + Me * kDModel * (2 + 4 + 2) +
+    return n_enc * layer(Me, kSegFrames, false) + n_dec * layer(Md, L, true) + n_mem_layers * layer(Mm, Lp, false) +
+           Me * kDModel * (2 + 4 + 2) + Mm * kDModel * (2 + 4 + 2) + (Me + Mm) * kDModel * 2 +
            Md * kDModel * (4 + 2) + Md * (size_t)kVocab * 2 + Md * 4 + (1 << 16);
 }
 
 // forward over B segments with teacher forcing; logits (B, L, V) fp32 to the caller, loss to *loss_host
 Status train_forward(mrmt3_handle* h, const float* mel, int B, const long long* dec_ids, const long long* labels,
-                     int L, float* logits_out, float* loss_host, cudaStream_t s) {
+                     int L, const long long* targets_prev, int Lp, float* logits_out, float* loss_host, cudaStream_t s) {
     MRMT3_TRY(train_init(h));
     TrainState* t = state(h);
     if (B <= 0 || L <= 0 || B > kMaxTrainBatch) return Error(2, "bad batch or length");
     MRMT3_CUDA_TRY(cudaSetDevice(h->device));
     const int n_enc = h->cfg.n_enc_layers, n_dec = h->cfg.n_dec_layers;
-    const size_t Me = (size_t)B * kSegFrames, Md = (size_t)B * L;
+    const bool with_mem = h->cfg.mem_variant == MRMT3_MEM_V2_APPEND;
+    if (with_mem && (!targets_prev || Lp <= 0)) return Error(2, "targets_prev required for the memory variant");
+    if (!with_mem) Lp = 0;
+    const int n_mem = with_mem ? std::min(h->cfg.mem_len, Lp) : 0;
+    const int tk = kSegFrames + n_mem;
+    const size_t Me = (size_t)B * kSegFrames, Md = (size_t)B * L, Mm = (size_t)B * Lp;
     const float eps = h->cfg.ln_eps;
     const ARowMap id{nullptr, 1};
-    MRMT3_TRY(t->stash.reserve(stash_bytes(n_enc, n_dec, Me, Md, B, L)));
+    MRMT3_TRY(t->stash.reserve(stash_bytes(n_enc, n_dec, with_mem ? h->cfg.n_mem_layers : 0, Me, Md, Mm, B, L, Lp)));
+    t->Lp = Lp;
+    t->n_mem = n_mem;
     Bump bp{reinterpret_cast<char*>(t->stash.p), 0, t->stash.cap};
     t->B = B;
     t->L = L;
@@ -283,17 +301,18 @@ Status train_forward(mrmt3_handle* h, const float* mel, int B, const long long* 
         return OkStatus();
     };
     auto self_fwd = [&](const LayerW& Lw, LayerStash& st, float* Hres, size_t M, int T, int causal) -> Status {
+        const int nb = (int)(M / T);
         st.h_in = bp.take<float>(M * kDModel);
         MRMT3_TRY(snapshot(st.h_in, Hres, M * kDModel));
         st.n1 = bp.take<bf16>(M * kDModel);
         st.qkv = bp.take<bf16>(M * 3 * kInner);
         st.ctx = bp.take<bf16>(M * kInner);
-        st.lse = bp.take<float>((size_t)B * kHeads * T);
+        st.lse = bp.take<float>((size_t)nb * kHeads * T);
         RUN(h, launch_rmsnorm(Hres, Lw.ln_self, eps, st.n1, nullptr, (int)M, nullptr, 1, s));
         RUN(h, launch_gemm_tc(*h->tma, st.n1, kDModel, M, id, Lw.wqkv, kDModel, (int)M, 3 * kInner, kDModel,
                               EpiStoreBf16{st.qkv, 3 * kInner}, s));
         MRMT3_TRY(attn_fwd(st.qkv, (long)T * 3 * kInner, 3 * kInner, st.qkv + kInner, st.qkv + 2 * kInner,
-                           (long)T * 3 * kInner, kDKV, 3 * kInner, st.ctx, T, T, causal, st.lse, B));
+                           (long)T * 3 * kInner, kDKV, 3 * kInner, st.ctx, T, T, causal, st.lse, nb));
         RUN(h, launch_gemm_tc(*h->tma, st.ctx, kInner, M, id, Lw.wo, kInner, (int)M, kDModel, kInner, EpiResidual{Hres, kDModel}, s));
         return OkStatus();
     };
@@ -306,11 +325,38 @@ Status train_forward(mrmt3_handle* h, const float* mel, int B, const long long* 
     t->enc_n_final = bp.take<bf16>(Me * kDModel);
     RUN(h, launch_rmsnorm(H, h->enc.final_ln, eps, t->enc_n_final, nullptr, (int)Me, nullptr, 1, s));
 
-    // ---- cross K/V of all decoder layers (one GEMM into the cross cache) ----
-    MRMT3_TRY(ensure_decode_capacity(h, B, kSegFrames, 1));
-    RUN(h, launch_gemm_tc(*h->tma, t->enc_n_final, kDModel, Me, id, h->cross_kv_w, kDModel, (int)Me,
+    // ---- MR-MT3 memory block (models/t5_segmem_v2_with_prev.py:119-128): Emb[prev] -> segmem_proj
+    //      (+PE) -> memory encoder over all Lp positions -> final norm -> first n_mem rows ----
+    if (with_mem) {
+        MRMT3_TRY(t->prev_copy.reserve(Mm * sizeof(long long)));
+        MRMT3_CUDA_TRY(cudaMemcpyAsync(t->prev_copy.p, targets_prev, Mm * sizeof(long long), cudaMemcpyDeviceToDevice, s));
+        t->prev_ids = t->prev_copy.as<long long>();
+        t->mem_emb16 = bp.take<bf16>(Mm * kDModel);
+        RUN(h, launch_embed_bf16(t->prev_ids, Lp, Lp, B, nullptr, h->emb, t->mem_emb16, s));
+        float* Hm = bp.take<float>(Mm * kDModel);
+        RUN(h, launch_gemm_tc(*h->tma, t->mem_emb16, kDModel, Mm, id, h->segmem_proj, kDModel, (int)Mm, kDModel, kDModel,
+                              EpiPosAdd{Hm, kDModel, h->pe, Lp, 0}, s));
+        t->mem_st.assign(h->cfg.n_mem_layers, LayerStash{});
+        for (int li = 0; li < h->cfg.n_mem_layers; ++li) {
+            MRMT3_TRY(self_fwd(h->mem.layers[li], t->mem_st[li], Hm, Mm, Lp, 0));
+            MRMT3_TRY(ffn_fwd(h->mem.layers[li], t->mem_st[li], Hm, Mm));
+        }
+        t->mem_h_final = Hm;
+        t->mem_n_final = bp.take<bf16>(Mm * kDModel);
+        RUN(h, launch_rmsnorm(Hm, h->mem.final_ln, eps, t->mem_n_final, nullptr, (int)Mm, nullptr, 1, s));
+    }
+
+    // ---- cross K/V of all decoder layers: rows [encoder states ; memory rows] per sample ----
+    MRMT3_TRY(ensure_decode_capacity(h, B, tk, 1));
+    t->kv_in = bp.take<bf16>((size_t)B * tk * kDModel);
+    MRMT3_CUDA_TRY(cudaMemcpy2DAsync(t->kv_in, (size_t)tk * kDModel * 2, t->enc_n_final, (size_t)kSegFrames * kDModel * 2,
+                                     (size_t)kSegFrames * kDModel * 2, B, cudaMemcpyDeviceToDevice, s));
+    if (n_mem)
+        MRMT3_CUDA_TRY(cudaMemcpy2DAsync(t->kv_in + (size_t)kSegFrames * kDModel, (size_t)tk * kDModel * 2, t->mem_n_final,
+                                         (size_t)Lp * kDModel * 2, (size_t)n_mem * kDModel * 2, B, cudaMemcpyDeviceToDevice, s));
+    RUN(h, launch_gemm_tc(*h->tma, t->kv_in, kDModel, (long)B * tk, id, h->cross_kv_w, kDModel, B * tk,
                           n_dec * 2 * kInner, kDModel,
-                          EpiCrossKV{h->cross_cache.as<bf16>(), kSegFrames, 0, n_dec, h->tk_cap, nullptr}, s));
+                          EpiCrossKV{h->cross_cache.as<bf16>(), tk, 0, n_dec, h->tk_cap, nullptr}, s));
 
     // ---- decoder, teacher forced (reference models/t5.py:99-180) ----
     float* Hd = bp.take<float>(Md * kDModel);
@@ -332,7 +378,7 @@ Status train_forward(mrmt3_handle* h, const float* mel, int B, const long long* 
                               EpiStoreBf16{st.qc, kInner}, s));
         const bf16* kbase = h->cross_cache.as<bf16>() + (size_t)li * 2 * kHeads * h->tk_cap * kDKV;
         MRMT3_TRY(attn_fwd(st.qc, (long)L * kInner, kInner, kbase, kbase + (size_t)kHeads * h->tk_cap * kDKV, (long)lane_sz,
-                           (long)h->tk_cap * kDKV, kDKV, st.ctx_c, L, kSegFrames, 0, st.lse_c, B));
+                           (long)h->tk_cap * kDKV, kDKV, st.ctx_c, L, tk, 0, st.lse_c, B));
         RUN(h, launch_gemm_tc(*h->tma, st.ctx_c, kInner, Md, id, Lw.co, kInner, (int)Md, kDModel, kInner, EpiResidual{Hd, kDModel}, s));
         MRMT3_TRY(ffn_fwd(Lw, st, Hd, Md));
     }
@@ -368,9 +414,10 @@ Status train_backward(mrmt3_handle* h, float* grad, cudaStream_t s) {
     TrainState* t = state(h);
     if (!t || !t->B) return Error(5, "mrmt3_train_forward first");
     MRMT3_CUDA_TRY(cudaSetDevice(h->device));
-    const int B = t->B, L = t->L, n_enc = h->cfg.n_enc_layers, n_dec = h->cfg.n_dec_layers;
-    const size_t Me = (size_t)B * kSegFrames, Md = (size_t)B * L;
-    const size_t Mmax = std::max(Me, Md), Mp = (Mmax + 63) & ~size_t(63);
+    const int B = t->B, L = t->L, Lp = t->Lp, n_mem = t->n_mem, n_enc = h->cfg.n_enc_layers, n_dec = h->cfg.n_dec_layers;
+    const int tk = kSegFrames + n_mem;
+    const size_t Me = (size_t)B * kSegFrames, Md = (size_t)B * L, Mm = (size_t)B * Lp, Mk = (size_t)B * tk;
+    const size_t Mmax = std::max(std::max(Me, Md), std::max(Mm, Mk)), Mp = (Mmax + 63) & ~size_t(63);
     const float eps = h->cfg.ln_eps;
     const ARowMap id{nullptr, 1};
     MRMT3_CUDA_TRY(cudaMemsetAsync(grad, 0, t->n_total * 4, s));
@@ -383,7 +430,8 @@ Status train_backward(mrmt3_handle* h, float* grad, cudaStream_t s) {
     const size_t kvN = (size_t)n_dec * 2 * kInner;
     size_t need = Mmax * kDModel * 4 * 2 + Mmax * kDModel * 2 * 2 + Mmax * 2 * kDFF * 2 + Mmax * kDFF * 2 +
                   Mmax * 3 * kInner * 2 + Mmax * kInner * 2 * 2 + Mp * 2 * kDFF * 2 * 2 + Mp * kvN * 2 * 2 +
-                  Me * kvN * 2 + (size_t)B * kHeads * std::max(L, kSegFrames) * 4 + (1 << 16);
+                  Mk * kvN * 2 + (size_t)B * kHeads * std::max(std::max(L, Lp), kSegFrames) * 4 + Mmax * kDModel * 2 +
+                  (1 << 16);
     MRMT3_TRY(t->scratch.reserve(need));
     Bump bp{reinterpret_cast<char*>(t->scratch.p), 0, t->scratch.cap};
     float* dH = bp.take<float>(Mmax * kDModel);
@@ -396,8 +444,9 @@ Status train_backward(mrmt3_handle* h, float* grad, cudaStream_t s) {
     bf16* dqc = bp.take<bf16>(Mmax * kInner);
     bf16* yT = bp.take<bf16>(std::max((size_t)2 * kDFF, kvN) * Mp);
     bf16* xT = bp.take<bf16>(std::max((size_t)2 * kDFF, (size_t)kDModel) * Mp);
-    bf16* dkv = bp.take<bf16>(Me * kvN);
-    float* delta = bp.take<float>((size_t)B * kHeads * std::max(L, kSegFrames));
+    bf16* dkv = bp.take<bf16>(Mk * kvN);
+    bf16* dsplit = bp.take<bf16>(Mmax * kDModel);  // rows of the K/V-input gradient regrouped per consumer
+    float* delta = bp.take<float>((size_t)B * kHeads * std::max(std::max(L, Lp), kSegFrames));
     if (bp.used > bp.cap) return Error(2, "internal: backward scratch overflow");
 
     auto G = [&](int slot) { return grad + t->slots[slot].off; };
@@ -469,7 +518,7 @@ Status train_backward(mrmt3_handle* h, float* grad, cudaStream_t s) {
     RUN(h, launch_rmsnorm_bwd(t->dec_h_final, h->dec.final_ln, eps, dn, (int)Md, dH, G(t->dec_final), s));
 
     // ---- decoder layers, last to first ----
-    MRMT3_CUDA_TRY(cudaMemsetAsync(dkv, 0, Me * kvN * 2, s));
+    MRMT3_CUDA_TRY(cudaMemsetAsync(dkv, 0, Mk * kvN * 2, s));
     const size_t lane_sz = (size_t)n_dec * 2 * kHeads * h->tk_cap * kDKV;
     for (int li = n_dec - 1; li >= 0; --li) {
         const LayerW& Lw = h->dec.layers[li];
@@ -485,7 +534,7 @@ Status train_backward(mrmt3_handle* h, float* grad, cudaStream_t s) {
         bf16* dk_l = dkv + (size_t)li * 2 * kInner;
         MRMT3_TRY(attn_bwd(st.qc, (long)L * kInner, kInner, kbase, kbase + (size_t)kHeads * h->tk_cap * kDKV, (long)lane_sz,
                            (long)h->tk_cap * kDKV, kDKV, st.ctx_c, dctx, dqc, dk_l, dk_l + kInner,
-                           (long)kSegFrames * (long)kvN, kDKV, (int)kvN, st.lse_c, L, kSegFrames, 0));
+                           (long)tk * (long)kvN, kDKV, (int)kvN, st.lse_c, L, tk, 0));
         MRMT3_TRY(dgrad(dqc, kInner, ls.cq, dn, Md));
         MRMT3_TRY(wgrad(dqc, kInner, kInner, st.nc, kDModel, kDModel, G(ls.cq), Md));
         RUN(h, launch_rmsnorm_bwd(st.h_mid2, Lw.ln_cross, eps, dn, (int)Md, dH, G(ls.ln_cross), s));
@@ -493,11 +542,40 @@ Status train_backward(mrmt3_handle* h, float* grad, cudaStream_t s) {
     }
     RUN(h, launch_embed_bwd(t->dec_ids, dH, G(t->emb), (int)Md, s));
 
-    // ---- cross K/V projection -> encoder output ----
+    // ---- cross K/V projection -> [encoder output ; memory rows] ----
+    MRMT3_TRY(dgrad(dkv, (int)kvN, t->cross_kv, dn, Mk));
+    MRMT3_TRY(wgrad(dkv, (int)kvN, (int)kvN, t->kv_in, kDModel, kDModel, G(t->cross_kv), Mk));
+
+    // ---- memory block backward (MR-MT3) ----
+    if (n_mem) {
+        // rows 256.. of every sample are the first n_mem rows of its memory sequence; the other
+        // Lp - n_mem rows of the memory encoder output receive no gradient
+        MRMT3_CUDA_TRY(cudaMemsetAsync(dsplit, 0, Mm * kDModel * 2, s));
+        MRMT3_CUDA_TRY(cudaMemcpy2DAsync(dsplit, (size_t)Lp * kDModel * 2, dn + (size_t)kSegFrames * kDModel,
+                                         (size_t)tk * kDModel * 2, (size_t)n_mem * kDModel * 2, B, cudaMemcpyDeviceToDevice, s));
+        MRMT3_CUDA_TRY(cudaMemsetAsync(dH, 0, Mm * kDModel * 4, s));
+        RUN(h, launch_rmsnorm_bwd(t->mem_h_final, h->mem.final_ln, eps, dsplit, (int)Mm, dH, G(t->mem_final), s));
+        // dsplit is free again; keep the encoder rows of dn for later in it
+        MRMT3_CUDA_TRY(cudaMemcpy2DAsync(dsplit, (size_t)kSegFrames * kDModel * 2, dn, (size_t)tk * kDModel * 2,
+                                         (size_t)kSegFrames * kDModel * 2, B, cudaMemcpyDeviceToDevice, s));
+        for (int li = h->cfg.n_mem_layers - 1; li >= 0; --li) {
+            MRMT3_TRY(ffn_bwd(t->mem[li], h->mem.layers[li], t->mem_st[li], Mm));
+            MRMT3_TRY(self_bwd(t->mem[li], h->mem.layers[li], t->mem_st[li], Mm, Lp, 0));
+        }
+        // stack input = segmem_proj(Emb[prev]) + PE
+        MRMT3_TRY(cast_dH(Mm));
+        MRMT3_TRY(wgrad(dHb, kDModel, kDModel, t->mem_emb16, kDModel, kDModel, G(t->segmem_proj), Mm));
+        const ParamSlot& sp = t->slots[t->segmem_proj];
+        RUN(h, launch_gemm_tc(*h->tma, dHb, kDModel, Mm, id, sp.wt, kDModel, (int)Mm, kDModel, kDModel,
+                              EpiStoreF32{dH, kDModel}, s));
+        RUN(h, launch_embed_bwd(t->prev_ids, dH, G(t->emb), (int)Mm, s));
+    } else {
+        MRMT3_CUDA_TRY(cudaMemcpyAsync(dsplit, dn, Me * kDModel * 2, cudaMemcpyDeviceToDevice, s));
+    }
+
+    // ---- encoder ----
     MRMT3_CUDA_TRY(cudaMemsetAsync(dH, 0, Me * kDModel * 4, s));
-    MRMT3_TRY(dgrad(dkv, (int)kvN, t->cross_kv, dn, Me));
-    MRMT3_TRY(wgrad(dkv, (int)kvN, (int)kvN, t->enc_n_final, kDModel, kDModel, G(t->cross_kv), Me));
-    RUN(h, launch_rmsnorm_bwd(t->enc_h_final, h->enc.final_ln, eps, dn, (int)Me, dH, G(t->enc_final), s));
+    RUN(h, launch_rmsnorm_bwd(t->enc_h_final, h->enc.final_ln, eps, dsplit, (int)Me, dH, G(t->enc_final), s));
     for (int li = n_enc - 1; li >= 0; --li) {
         MRMT3_TRY(ffn_bwd(t->enc[li], h->enc.layers[li], t->enc_st[li], Me));
         MRMT3_TRY(self_bwd(t->enc[li], h->enc.layers[li], t->enc_st[li], Me, kSegFrames, 0));

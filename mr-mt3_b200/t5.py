@@ -267,7 +267,7 @@ class T5ForConditionalGeneration(nn.Module):
         return logits, enc, None
 
     def train_step(self, inputs, labels, lr=1e-5, betas=(0.9, 0.999), eps=1e-8, weight_decay=0.01,
-                   process_group=None, apply=True):
+                   process_group=None, apply=True, targets_prev=None):
         """One fine-tune step of reference tasks/mt3_net.py `training_step` + AdamW
         (`train.sh:78`: lr 1e-5): teacher-forced forward, CrossEntropyLoss(ignore_index=-100),
         hand-written backward, mean all-reduce of the flat gradient over `process_group` (or the
@@ -276,7 +276,9 @@ class T5ForConditionalGeneration(nn.Module):
         into this module's parameters.  No dropout is applied."""
         eng = self.engine()
         eng.train_init()
-        logits, loss = eng.train_forward(inputs, self._shift_right(labels), labels)
+        if targets_prev is not None:
+            targets_prev[targets_prev == -100] = 0        # in place, as t5_segmem_v2_with_prev.py:119
+        logits, loss = eng.train_forward(inputs, self._shift_right(labels), labels, targets_prev)
         grad = eng.train_backward()
         import torch.distributed as dist
         if dist.is_available() and dist.is_initialized() and dist.get_world_size(process_group) > 1:
