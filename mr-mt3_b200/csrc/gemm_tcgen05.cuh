@@ -142,7 +142,7 @@ struct TcSmem {
 template <int BN, class Epi>
 __global__ void __launch_bounds__(kTcThreads, 1)
     gemm_tn_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_w,
-                           int M, int N, int K, ARowMap amap, Epi epi) {
+                           int M, int N, int K, ARowMap amap, Epi epi, int k_splits) {
     using S = TcSmem<BN>;
     constexpr int kStages = S::kStages;
     extern __shared__ unsigned char tc_smem_raw[];
@@ -157,10 +157,13 @@ __global__ void __launch_bounds__(kTcThreads, 1)
 
     const int warp = threadIdx.x >> 5;
     const int lane = threadIdx.x & 31;
-    const int KB = K / kTcBK;
+    // split-K (wgrad: small output, long reduction): work item t -> output tile t % n_out, k range
+    // split t / n_out; split s stores its partial sums at rows [s*M, (s+1)*M) of the output
+    const int KB = K / kTcBK / k_splits;
     const int tiles_n = N / BN;
     const int tiles_m = (M + kTcBM - 1) / kTcBM;
-    const int n_tiles = tiles_n * tiles_m;
+    const int n_out = tiles_n * tiles_m;
+    const int n_tiles = n_out * k_splits;
 
     if (threadIdx.x == 0) {
         for (int s = 0; s < kStages; ++s) {
@@ -190,8 +193,9 @@ __global__ void __launch_bounds__(kTcThreads, 1)
         if (lane == 0) {
             int it = 0;
             for (int t = blockIdx.x; t < n_tiles; t += gridDim.x) {
-                const int m0 = (t / tiles_n) * kTcBM;
-                const int n0 = (t % tiles_n) * BN;
+                const int to = t % n_out, kb0 = (t / n_out) * KB;
+                const int m0 = (to / tiles_n) * kTcBM;
+                const int n0 = (to % tiles_n) * BN;
                 // A rows may be gathered block-wise (cross-K/V projection picks each lane's segment)
                 int arow = m0;
                 if (amap.map) arow = amap.map[m0 / amap.block] * amap.block + m0 % amap.block;
@@ -200,8 +204,8 @@ __global__ void __launch_bounds__(kTcThreads, 1)
                     mbar_wait(bar_empty + s * 8, ((it / kStages) & 1) ^ 1);
                     mbar_expect_tx(bar_full + s * 8, S::kStageBytes);
                     const uint32_t sa = base + s * S::kStageBytes;
-                    tma_load_2d(sa, &tmap_a, kb * kTcBK, arow, bar_full + s * 8);
-                    tma_load_2d(sa + S::kABytes, &tmap_w, kb * kTcBK, n0, bar_full + s * 8);
+                    tma_load_2d(sa, &tmap_a, (kb0 + kb) * kTcBK, arow, bar_full + s * 8);
+                    tma_load_2d(sa + S::kABytes, &tmap_w, (kb0 + kb) * kTcBK, n0, bar_full + s * 8);
                 }
             }
         }
@@ -237,8 +241,10 @@ __global__ void __launch_bounds__(kTcThreads, 1)
         const int quarter = warp & 3;
         int i = 0;
         for (int t = blockIdx.x; t < n_tiles; t += gridDim.x, ++i) {
-            const int m0 = (t / tiles_n) * kTcBM;
-            const int n0 = (t % tiles_n) * BN;
+            const int to = t % n_out;
+            const int m0 = (to / tiles_n) * kTcBM;
+            const int n0 = (to % tiles_n) * BN;
+            const int out_row0 = (t / n_out) * M;  // split-K partials are stacked along the rows
             const int buf = i & 1;
             mbar_wait(bar_acc_full + buf * 8, (i >> 1) & 1);
             tc_fence_after();
@@ -254,7 +260,7 @@ __global__ void __launch_bounds__(kTcThreads, 1)
                         float f[8];
 #pragma unroll
                         for (int e = 0; e < 8; ++e) f[e] = __uint_as_float(v[8 * j + e]);
-                        epi_store8(epi, row, n0 + c * 32 + 8 * j, f);
+                        epi_store8(epi, out_row0 + row, n0 + c * 32 + 8 * j, f);
                     }
                 }
             }
@@ -273,22 +279,23 @@ __global__ void __launch_bounds__(kTcThreads, 1)
 // a_rows: rows addressable through A (>= M; larger when amap gathers from a bigger tensor)
 template <int BN, class Epi>
 Status launch_gemm_tc_bn(TmaCache& tc, const CUtensorMap* ma, const bf16* W, int ldw, int M, int N, int K,
-                         ARowMap amap, const Epi& epi, int n_sms, cudaStream_t stream) {
+                         ARowMap amap, const Epi& epi, int n_sms, cudaStream_t stream, int k_splits) {
     const CUtensorMap* mw = nullptr;
     MRMT3_TRY(tc.get(W, N, K, ldw, BN, &mw));
     auto kern = gemm_tn_tcgen05_kernel<BN, Epi>;
     MRMT3_TRY(ensure_dynamic_smem(kern, TcSmem<BN>::kTotal));
-    const int n_tiles = (N / BN) * ceil_div(M, kTcBM);
-    kern<<<std::min(n_tiles, n_sms), kTcThreads, TcSmem<BN>::kTotal, stream>>>(*ma, *mw, M, N, K, amap, epi);
+    const int n_tiles = (N / BN) * ceil_div(M, kTcBM) * k_splits;
+    kern<<<std::min(n_tiles, n_sms), kTcThreads, TcSmem<BN>::kTotal, stream>>>(*ma, *mw, M, N, K, amap, epi, k_splits);
     MRMT3_CHECK_LAUNCH();
     return OkStatus();
 }
 
 template <class Epi>
 Status launch_gemm_tc(TmaCache& tc, const bf16* A, int lda, long a_rows, ARowMap amap, const bf16* W, int ldw,
-                      int M, int N, int K, const Epi& epi, cudaStream_t stream) {
+                      int M, int N, int K, const Epi& epi, cudaStream_t stream, int k_splits = 1) {
     if (M <= 0) return OkStatus();
     if (K % kTcBK != 0 || N % 64 != 0) return Error(2, "gemm_tc: K and N must be multiples of 64");
+    if (k_splits < 1 || (K / kTcBK) % k_splits != 0) return Error(2, "gemm_tc: k_splits must divide K / 64");
     if (amap.map && amap.block % kTcBM != 0) return Error(2, "gemm_tc: gather block must be a multiple of 128 rows");
     static int n_sms = 0;
     if (!n_sms) {
@@ -299,10 +306,10 @@ Status launch_gemm_tc(TmaCache& tc, const bf16* A, int lda, long a_rows, ARowMap
     const CUtensorMap* ma = nullptr;
     MRMT3_TRY(tc.get(A, a_rows, K, lda, kTcBM, &ma));
     // widest tile that divides N: wider tiles move fewer operand bytes per MAC through L2
-    if (N % 256 == 0) return launch_gemm_tc_bn<256>(tc, ma, W, ldw, M, N, K, amap, epi, n_sms, stream);
-    if (N % 192 == 0) return launch_gemm_tc_bn<192>(tc, ma, W, ldw, M, N, K, amap, epi, n_sms, stream);
-    if (N % 128 == 0) return launch_gemm_tc_bn<128>(tc, ma, W, ldw, M, N, K, amap, epi, n_sms, stream);
-    return launch_gemm_tc_bn<64>(tc, ma, W, ldw, M, N, K, amap, epi, n_sms, stream);
+    if (N % 256 == 0) return launch_gemm_tc_bn<256>(tc, ma, W, ldw, M, N, K, amap, epi, n_sms, stream, k_splits);
+    if (N % 192 == 0) return launch_gemm_tc_bn<192>(tc, ma, W, ldw, M, N, K, amap, epi, n_sms, stream, k_splits);
+    if (N % 128 == 0) return launch_gemm_tc_bn<128>(tc, ma, W, ldw, M, N, K, amap, epi, n_sms, stream, k_splits);
+    return launch_gemm_tc_bn<64>(tc, ma, W, ldw, M, N, K, amap, epi, n_sms, stream, k_splits);
 }
 
 }  // namespace mrmt3

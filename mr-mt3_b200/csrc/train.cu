@@ -13,6 +13,8 @@
 #include <algorithm>
 #include <cmath>
 #include <cstring>
+#include <map>
+#include <string>
 #include <vector>
 
 #include "gemm_tcgen05.cuh"
@@ -430,7 +432,7 @@ Status train_backward(mrmt3_handle* h, float* grad, cudaStream_t s) {
     const size_t kvN = (size_t)n_dec * 2 * kInner;
     size_t need = Mmax * kDModel * 4 * 2 + Mmax * kDModel * 2 * 2 + Mmax * 2 * kDFF * 2 + Mmax * kDFF * 2 +
                   Mmax * 3 * kInner * 2 + Mmax * kInner * 2 * 2 + Mp * 2 * kDFF * 2 * 2 + Mp * kvN * 2 * 2 +
-                  Mk * kvN * 2 + (size_t)B * kHeads * std::max(std::max(L, Lp), kSegFrames) * 4 + Mmax * kDModel * 2 +
+                  (size_t)16 * 2 * kDFF * kDModel * 4 + Mk * kvN * 2 + (size_t)B * kHeads * std::max(std::max(L, Lp), kSegFrames) * 4 + Mmax * kDModel * 2 +
                   (1 << 16);
     MRMT3_TRY(t->scratch.reserve(need));
     Bump bp{reinterpret_cast<char*>(t->scratch.p), 0, t->scratch.cap};
@@ -444,16 +446,34 @@ Status train_backward(mrmt3_handle* h, float* grad, cudaStream_t s) {
     bf16* dqc = bp.take<bf16>(Mmax * kInner);
     bf16* yT = bp.take<bf16>(std::max((size_t)2 * kDFF, kvN) * Mp);
     bf16* xT = bp.take<bf16>(std::max((size_t)2 * kDFF, (size_t)kDModel) * Mp);
+    float* wpart = bp.take<float>((size_t)16 * 2 * kDFF * kDModel);  // split-K partials (a split needs <= 160 / splits tiles)
     bf16* dkv = bp.take<bf16>(Mk * kvN);
     bf16* dsplit = bp.take<bf16>(Mmax * kDModel);  // rows of the K/V-input gradient regrouped per consumer
     float* delta = bp.take<float>((size_t)B * kHeads * std::max(std::max(L, Lp), kSegFrames));
     if (bp.used > bp.cap) return Error(2, "internal: backward scratch overflow");
 
+    // optional per-category timing (MRMT3_TRAIN_PROFILE=1): CUDA events around every backward op
+    static const bool prof = getenv("MRMT3_TRAIN_PROFILE") && atoi(getenv("MRMT3_TRAIN_PROFILE")) != 0;
+    struct Rec { const char* cat; cudaEvent_t a, b; };
+    std::vector<Rec> recs;
+    auto tic = [&](const char* cat) {
+        if (!prof) return;
+        Rec r{cat, nullptr, nullptr};
+        cudaEventCreate(&r.a);
+        cudaEventCreate(&r.b);
+        cudaEventRecord(r.a, s);
+        recs.push_back(r);
+    };
+    auto toc = [&]() {
+        if (prof) cudaEventRecord(recs.back().b, s);
+    };
     auto G = [&](int slot) { return grad + t->slots[slot].off; };
     // dX (M, Kin) bf16 = dY (M, N) . W (N, Kin)
     auto dgrad = [&](const bf16* dY, int N, int slot, bf16* dX, size_t M) -> Status {
         const ParamSlot& sl = t->slots[slot];
+        tic("dgrad");
         RUN(h, launch_gemm_tc(*h->tma, dY, N, M, id, sl.wt, N, (int)M, sl.cols, N, EpiStoreBf16{dX, sl.cols}, s));
+        toc();
         return OkStatus();
     };
     // dW (N, Kin) fp32 = dY^T . X ; dY (M, N) with pitch ldy, X (M, Kin) with pitch ldx
@@ -463,9 +483,23 @@ Status train_backward(mrmt3_handle* h, float* grad, cudaStream_t s) {
             MRMT3_CUDA_TRY(cudaMemset2DAsync(yT + M, mp * 2, 0, (mp - M) * 2, N, s));
             MRMT3_CUDA_TRY(cudaMemset2DAsync(xT + M, mp * 2, 0, (mp - M) * 2, Kin, s));
         }
+        tic("wgrad transposes");
         RUN(h, launch_transpose_bf16(dY, ldy, yT, (int)mp, (int)M, N, s));
         RUN(h, launch_transpose_bf16(X, ldx, xT, (int)mp, (int)M, Kin, s));
-        RUN(h, launch_gemm_tc(*h->tma, yT, (int)mp, N, id, xT, (int)mp, N, Kin, (int)mp, EpiStoreF32{dW, Kin}, s));
+        toc();
+        tic("wgrad gemm");
+        // the output has only (N / 128) x (Kin / BN) tiles: split the long reduction over the SMs
+        const int bn = Kin % 256 == 0 ? 256 : (Kin % 192 == 0 ? 192 : (Kin % 128 == 0 ? 128 : 64));
+        const int out_tiles = ceil_div(N, 128) * (Kin / bn);
+        int splits = 1;
+        while (splits < 16 && out_tiles * splits * 2 <= 160 && ((int)(mp / 64) % (splits * 2)) == 0) splits *= 2;
+        if (splits == 1) {
+            RUN(h, launch_gemm_tc(*h->tma, yT, (int)mp, N, id, xT, (int)mp, N, Kin, (int)mp, EpiStoreF32{dW, Kin}, s));
+        } else {
+            RUN(h, launch_gemm_tc(*h->tma, yT, (int)mp, N, id, xT, (int)mp, N, Kin, (int)mp, EpiStoreF32{wpart, Kin}, s, splits));
+            RUN(h, launch_reduce_splits(wpart, dW, (size_t)N * Kin, splits, s));
+        }
+        toc();
         return OkStatus();
     };
     auto cast_dH = [&](size_t M) -> Status {
@@ -484,7 +518,9 @@ Status train_backward(mrmt3_handle* h, float* grad, cudaStream_t s) {
         ap.o_batch_stride = (long)Tq * kInner; ap.o_head_stride = kDKV; ap.o_row_stride = kInner;
         ap.dk_batch_stride = dkb; ap.dk_head_stride = dkh; ap.dk_row_stride = dkr;
         ap.lse2 = lse; ap.delta = delta; ap.Tq = Tq; ap.Tk = Tk; ap.causal = causal; ap.causal_offset = 0;
+        tic(causal ? "attention bwd (causal self)" : (Tk == Tq ? "attention bwd (self)" : "attention bwd (cross)"));
         RUN(h, launch_attn_bwd(ap, B, s));
+        toc();
         h->launches += 1;
         return OkStatus();
     };
@@ -583,6 +619,19 @@ Status train_backward(mrmt3_handle* h, float* grad, cudaStream_t s) {
     // proj: h0 = mel . Wproj^T + PE
     MRMT3_TRY(cast_dH(Me));
     MRMT3_TRY(wgrad(dHb, kDModel, kDModel, t->mel16, kMels, kMels, G(t->proj), Me));
+    if (prof) {
+        MRMT3_CUDA_TRY(cudaStreamSynchronize(s));
+        std::map<std::string, std::pair<double, int>> agg;
+        for (auto& r : recs) {
+            float ms = 0.f;
+            cudaEventElapsedTime(&ms, r.a, r.b);
+            agg[r.cat].first += ms;
+            agg[r.cat].second += 1;
+            cudaEventDestroy(r.a);
+            cudaEventDestroy(r.b);
+        }
+        for (auto& kv : agg) fprintf(stderr, "[train profile] %-28s %8.3f ms in %d calls\n", kv.first.c_str(), kv.second.first, kv.second.second);
+    }
     return OkStatus();
 }
 

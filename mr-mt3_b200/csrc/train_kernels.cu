@@ -168,11 +168,34 @@ Status launch_gated_gelu_bwd(const bf16* raw, const bf16* dff, bf16* draw, size_
 }
 
 // ---------------------------------------------------------------------------------------------
-// (R, C) bf16 row-major with row pitch ld_in -> (C, R) with row pitch ld_out
+// (R, C) bf16 row-major with row pitch ld_in -> (C, R) with row pitch ld_out.  64 x 64 tiles through
+// shared memory; full tiles of 16-byte-aligned matrices move with 16-byte loads and stores.
 __global__ void __launch_bounds__(256)
-    transpose_bf16_kernel(const bf16* __restrict__ in, int ld_in, bf16* __restrict__ out, int ld_out, int R, int C) {
-    __shared__ bf16 tile[64][66];
+    transpose_bf16_kernel(const bf16* __restrict__ in, int ld_in, bf16* __restrict__ out, int ld_out, int R, int C,
+                          int vec_ok) {
+    __shared__ __align__(16) bf16 tile[64][72];
     const int r0 = blockIdx.y * 64, c0 = blockIdx.x * 64;
+    const bool full = vec_ok && r0 + 64 <= R && c0 + 64 <= C;
+    if (full) {
+#pragma unroll
+        for (int i = 0; i < 2; ++i) {
+            int idx = threadIdx.x + i * 256;  // 64 rows x 8 chunks of 8 elements
+            int r = idx >> 3, ch = idx & 7;
+            *reinterpret_cast<uint4*>(&tile[r][ch * 8]) =
+                *reinterpret_cast<const uint4*>(in + (size_t)(r0 + r) * ld_in + c0 + ch * 8);
+        }
+        __syncthreads();
+#pragma unroll
+        for (int i = 0; i < 2; ++i) {
+            int idx = threadIdx.x + i * 256;  // 64 output rows (input cols) x 8 chunks of 8 input rows
+            int c = idx & 63, rc = idx >> 6;
+            bf16 v[8];
+#pragma unroll
+            for (int k = 0; k < 8; ++k) v[k] = tile[rc * 8 + k][c];
+            *reinterpret_cast<uint4*>(out + (size_t)(c0 + c) * ld_out + r0 + rc * 8) = *reinterpret_cast<uint4*>(v);
+        }
+        return;
+    }
     for (int i = threadIdx.x; i < 64 * 64; i += 256) {
         int r = i >> 6, c = i & 63;
         tile[r][c] = (r0 + r < R && c0 + c < C) ? in[(size_t)(r0 + r) * ld_in + c0 + c] : __float2bfloat16(0.f);
@@ -186,7 +209,9 @@ __global__ void __launch_bounds__(256)
 
 Status launch_transpose_bf16(const bf16* in, int ld_in, bf16* out, int ld_out, int R, int C, cudaStream_t s) {
     if (R <= 0 || C <= 0) return OkStatus();
-    transpose_bf16_kernel<<<dim3(ceil_div(C, 64), ceil_div(R, 64)), 256, 0, s>>>(in, ld_in, out, ld_out, R, C);
+    const int vec_ok = (ld_in % 8 == 0) && (ld_out % 8 == 0) && ((reinterpret_cast<uintptr_t>(in) & 15) == 0) &&
+                       ((reinterpret_cast<uintptr_t>(out) & 15) == 0);
+    transpose_bf16_kernel<<<dim3(ceil_div(C, 64), ceil_div(R, 64)), 256, 0, s>>>(in, ld_in, out, ld_out, R, C, vec_ok);
     MRMT3_CHECK_LAUNCH();
     return OkStatus();
 }
@@ -242,6 +267,25 @@ __global__ void bf16_to_f32_kernel(const bf16* __restrict__ in, float* __restric
 Status launch_bf16_to_f32(const bf16* in, float* out, size_t n, cudaStream_t s) {
     if (!n) return OkStatus();
     bf16_to_f32_kernel<<<(unsigned)((n + 255) / 256), 256, 0, s>>>(in, out, n);
+    MRMT3_CHECK_LAUNCH();
+    return OkStatus();
+}
+
+// out[i] = sum_s partials[s * n + i]   (split-K wgrad)
+__global__ void reduce_splits_kernel(const float4* __restrict__ partials, float4* __restrict__ out, size_t n4, int splits) {
+    size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n4) return;
+    float4 a = partials[i];
+    for (int s = 1; s < splits; ++s) {
+        float4 b = partials[(size_t)s * n4 + i];
+        a.x += b.x; a.y += b.y; a.z += b.z; a.w += b.w;
+    }
+    out[i] = a;
+}
+Status launch_reduce_splits(const float* partials, float* out, size_t n, int splits, cudaStream_t s) {
+    if (!n) return OkStatus();
+    reduce_splits_kernel<<<(unsigned)((n / 4 + 255) / 256), 256, 0, s>>>(reinterpret_cast<const float4*>(partials),
+                                                                      reinterpret_cast<float4*>(out), n / 4, splits);
     MRMT3_CHECK_LAUNCH();
     return OkStatus();
 }
