@@ -192,7 +192,9 @@ int mrmt3_memory_block(mrmt3_handle* h, const int64_t* prev_ids, int B, int Lp, 
  *   mrmt3_train_forward  mel (B,256,512) fp32, decoder_input_ids / labels (B,L) int64, for
  *                        V2WithPrev also targets_prev (B,Lp) int64 with -100 already replaced by
  *                        pad (else NULL, 0) -> logits_out (B,L,vocab) fp32, mean loss in *loss_host
- *   mrmt3_train_backward gradient of that loss w.r.t. every trainable tensor -> grad_flat (fp32)
+ *   mrmt3_train_backward gradient w.r.t. every trainable tensor -> grad_flat (fp32): of the built-in
+ *                        loss when dlogits == NULL, else back-propagates the caller's dlogits
+ *                        (B,L,vocab) fp32 (torch autograd over the logits, any loss)
  *   mrmt3_train_apply    AdamW (torch.optim.AdamW semantics) with grad_flat; refreshes the bf16
  *                        weights used by every other entry point
  *   mrmt3_train_read_master  flat fp32 copy of the current parameters */
@@ -202,7 +204,7 @@ int mrmt3_train_locate(mrmt3_handle* h, const char* name, int64_t* offset, int32
 int mrmt3_train_forward(mrmt3_handle* h, const float* mel, int B, const int64_t* decoder_input_ids,
                         const int64_t* labels, int L, const int64_t* targets_prev, int Lp, float* logits_out,
                         float* loss_host, void* stream);
-int mrmt3_train_backward(mrmt3_handle* h, float* grad_flat, void* stream);
+int mrmt3_train_backward(mrmt3_handle* h, float* grad_flat, const float* dlogits, void* stream);
 int mrmt3_train_apply(mrmt3_handle* h, const float* grad_flat, float lr, float beta1, float beta2, float eps,
                       float weight_decay, void* stream);
 int mrmt3_train_read_master(mrmt3_handle* h, float* out_flat, void* stream);

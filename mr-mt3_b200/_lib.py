@@ -64,7 +64,7 @@ _PROTOTYPES = {
                                     ctypes.POINTER(ctypes.c_int32)]),
     "mrmt3_train_forward": (_c_int, [_c_void_p, _c_void_p, _c_int, _c_void_p, _c_void_p, _c_int, _c_void_p, _c_int,
                                      _c_void_p, ctypes.POINTER(ctypes.c_float), _c_void_p]),
-    "mrmt3_train_backward": (_c_int, [_c_void_p, _c_void_p, _c_void_p]),
+    "mrmt3_train_backward": (_c_int, [_c_void_p, _c_void_p, _c_void_p, _c_void_p]),
     "mrmt3_train_apply": (_c_int, [_c_void_p, _c_void_p, ctypes.c_float, ctypes.c_float, ctypes.c_float,
                                    ctypes.c_float, ctypes.c_float, _c_void_p]),
     "mrmt3_train_read_master": (_c_int, [_c_void_p, _c_void_p, _c_void_p]),
@@ -350,13 +350,16 @@ class Engine:
                                                       _ptr(logits), ctypes.byref(loss), _stream()))
         return logits, float(loss.value)
 
-    def train_backward(self, grad=None):
-        """Gradient of the last train_forward's loss into a flat fp32 tensor (allocated if None)."""
+    def train_backward(self, grad=None, dlogits=None):
+        """Gradient into a flat fp32 tensor (allocated if None): of the last train_forward's built-in
+        cross-entropy, or -- when `dlogits` (B, L, V) fp32 is given -- of whatever loss produced it."""
         n = getattr(self, "_n_params", None) or self.train_init()
         if grad is None:
             grad = torch.empty(n, dtype=torch.float32, device=self.device)
+        if dlogits is not None:
+            dlogits = dlogits.to(self.device, torch.float32).contiguous()
         with torch.cuda.device(self.device):
-            self._check(self._lib.mrmt3_train_backward(self._h, _ptr(grad), _stream()))
+            self._check(self._lib.mrmt3_train_backward(self._h, _ptr(grad), _ptr(dlogits), _stream()))
         return grad
 
     def train_apply(self, grad, lr, betas=(0.9, 0.999), eps=1e-8, weight_decay=0.01):

@@ -31,7 +31,7 @@ Status train_locate(mrmt3_handle* h, const std::string& name, long long* offset,
                     int* row_off);
 Status train_forward(mrmt3_handle* h, const float* mel, int B, const long long* dec_ids, const long long* labels, int L,
                      const long long* targets_prev, int Lp, float* logits_out, float* loss_host, cudaStream_t s);
-Status train_backward(mrmt3_handle* h, float* grad, cudaStream_t s);
+Status train_backward(mrmt3_handle* h, float* grad, const float* dlogits_f32, cudaStream_t s);
 Status train_apply(mrmt3_handle* h, const float* grad, float lr, float beta1, float beta2, float adam_eps, float wd,
                    cudaStream_t s);
 Status profile_collect(mrmt3_handle* h);
@@ -294,9 +294,9 @@ int mrmt3_train_forward(mrmt3_handle* h, const float* mel, int B, const int64_t*
     END_GUARD(h)
 }
 
-int mrmt3_train_backward(mrmt3_handle* h, float* grad_flat, void* stream) {
+int mrmt3_train_backward(mrmt3_handle* h, float* grad_flat, const float* dlogits, void* stream) {
     GUARD(h)
-    return finish(h, train_backward(h, grad_flat, (cudaStream_t)stream));
+    return finish(h, train_backward(h, grad_flat, dlogits, (cudaStream_t)stream));
     END_GUARD(h)
 }
 

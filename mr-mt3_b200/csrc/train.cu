@@ -412,10 +412,12 @@ Status train_forward(mrmt3_handle* h, const float* mel, int B, const long long* 
 
 // ---------------------------------------------------------------------------------------------
 // backward of the last train_forward into the caller's flat fp32 gradient buffer (overwritten)
-Status train_backward(mrmt3_handle* h, float* grad, cudaStream_t s) {
+Status train_backward(mrmt3_handle* h, float* grad, const float* dlogits_f32, cudaStream_t s) {
     TrainState* t = state(h);
     if (!t || !t->B) return Error(5, "mrmt3_train_forward first");
     MRMT3_CUDA_TRY(cudaSetDevice(h->device));
+    // an external loss (autograd on the logits) replaces the built-in cross-entropy gradient
+    if (dlogits_f32) RUN(h, launch_cast_f32_bf16(dlogits_f32, t->dlogits, (size_t)t->B * t->L * kVocab, s));
     const int B = t->B, L = t->L, Lp = t->Lp, n_mem = t->n_mem, n_enc = h->cfg.n_enc_layers, n_dec = h->cfg.n_dec_layers;
     const int tk = kSegFrames + n_mem;
     const size_t Me = (size_t)B * kSegFrames, Md = (size_t)B * L, Mm = (size_t)B * Lp, Mk = (size_t)B * tk;

@@ -144,6 +144,32 @@ class T5Stack(nn.Module):
 
 
 # ---- the model ----------------------------------------------------------------------------------
+class _TrainForward(torch.autograd.Function):
+    """Autograd bridge for training mode: forward = the CUDA training forward (activations stashed
+    inside the engine), backward = the hand-written CUDA backward fed the logits gradient of ANY
+    loss; the flat gradient is handed back to autograd tensor by tensor, so `loss.backward()` and
+    torch optimizers work on the mirror module exactly as on the reference's (tasks/mt3_net.py)."""
+
+    @staticmethod
+    def forward(ctx, model, inputs, decoder_input_ids, targets_prev, *params):
+        eng = model.engine()
+        eng.train_init()
+        ignore = torch.full_like(decoder_input_ids, -100)
+        logits, _ = eng.train_forward(inputs, decoder_input_ids, ignore, targets_prev)
+        ctx.model = model
+        return logits
+
+    @staticmethod
+    def backward(ctx, dlogits):
+        model = ctx.model
+        eng = model.engine()
+        flat = eng.train_backward(dlogits=dlogits)
+        grads = []
+        for name, p in model.named_parameters():
+            grads.append(eng.flat_view(flat, name).reshape(p.shape).to(p.dtype).clone())
+        return (None, None, None, None, *grads)
+
+
 class T5ForConditionalGeneration(nn.Module):
     """Reference models/t5.py:37-360.  `generate` / `forward` / `get_model_outputs` keep the
     reference's signatures; extra HF keyword arguments are accepted and ignored exactly as the
@@ -301,9 +327,19 @@ class T5ForConditionalGeneration(nn.Module):
             p.copy_(view.reshape(p.shape).to(p.device))
         self._engine_sig = self._weights_signature() if hasattr(self, "_weights_signature") else self._engine_sig
 
+    def _forward_with_grad(self, inputs, labels, decoder_input_ids, targets_prev=None):
+        if decoder_input_ids is None:
+            decoder_input_ids = self._shift_right(labels)
+        params = [p for _, p in self.named_parameters()]
+        return _TrainForward.apply(self, inputs, decoder_input_ids, targets_prev, *params)
+
     def forward(self, inputs=None, labels=None, decoder_input_ids=None, **kwargs):
-        """Reference models/t5.py:182-249: returns the logits tensor only."""
+        """Reference models/t5.py:182-249: returns the logits tensor only.  In training mode with
+        autograd enabled the logits carry a grad_fn whose backward is the CUDA backward pass
+        (no dropout is applied)."""
         kwargs.pop("num_insts", None)
+        if self.training and torch.is_grad_enabled():
+            return self._forward_with_grad(inputs, labels, decoder_input_ids)
         return self.get_model_outputs(inputs=inputs, labels=labels,
                                       decoder_input_ids=decoder_input_ids, **kwargs)[0]
 

@@ -35,6 +35,9 @@ class T5SegMemV2WithPrev(T5SegMem):
     def forward(self, inputs=None, labels=None, targets_prev=None, decoder_input_ids=None, **kwargs):
         """Reference models/t5_segmem_v2_with_prev.py:155-224: logits only."""
         kwargs.pop("num_insts", None)
+        if self.training and torch.is_grad_enabled():
+            targets_prev.masked_fill_(targets_prev == -100, self.config.pad_token_id)  # in place, reference :119
+            return self._forward_with_grad(inputs, labels, decoder_input_ids, targets_prev)
         return self.get_model_outputs(inputs=inputs, labels=labels, targets_prev=targets_prev,
                                       decoder_input_ids=decoder_input_ids, **kwargs)[0]
 
