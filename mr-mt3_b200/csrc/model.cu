@@ -251,7 +251,6 @@ void handle_destroy(mrmt3_handle* h) {
     h->d_qc.release(); h->d_ff.release(); h->d_logits.release(); h->d_state.release();
     train_destroy(h);
     h->kv_pool.release(); h->block_table.release(); h->cross_cache.release(); h->lane_tab.release();
-    h->attn_scratch.release(); h->attn_tickets.release();
     if (h->h_pinned) cudaFreeHost(h->h_pinned);
     if (h->poll_ev[0]) cudaEventDestroy(h->poll_ev[0]);
     if (h->poll_ev[1]) cudaEventDestroy(h->poll_ev[1]);
@@ -582,7 +581,6 @@ Status ensure_decode_capacity(mrmt3_handle* h, int n_lanes, int tk, int max_posi
 }
 
 struct StepPlan {
-    int self_chunks;       // KV pages the self-attention grid must cover at this step's position
     int lane0;             // first lane of this group (all per-lane buffers are offset by it)
     int n_lanes, tk;
     DecodeState st;
@@ -700,7 +698,7 @@ static Status enqueue_step(mrmt3_handle* h, const StepPlan& pl, int kind, cudaSt
 }
 
 static Status get_graph(mrmt3_handle* h, const StepPlan& pl, int kind, StepGraph** out) {
-    StepGraphKey key{pl.lane0, pl.n_lanes, pl.tk, pl.st.max_tokens, pl.st.prefix_len, kind, pl.self_chunks};
+    StepGraphKey key{pl.lane0, pl.n_lanes, pl.tk, pl.st.max_tokens, pl.st.prefix_len, kind};
     auto it = h->graphs.find(key);
     if (it != h->graphs.end()) {
         *out = &it->second;
@@ -781,13 +779,8 @@ static Status run_decode(mrmt3_handle* h, StepPlan pl, int n_prefix, bool debug_
             MRMT3_CUDA_TRY(cudaStreamWaitEvent(gs[g], h->gfork, 0));
         }
     }
-    // the self-attention grid covers the KV pages in use at the step's position, so the step
-    // graph exists in one variant per page count (captured on first use, then replayed)
-    auto step_all = [&](int kind, int position) -> Status {
-        const int chunks = 1;  // (graph variants per KV page count were only needed by the split-key kernel)
-        (void)position;
+    auto step_all = [&](int kind) -> Status {
         for (int g = 0; g < G; ++g) {
-            gp[g].self_chunks = chunks;
             if (graphs) {
                 StepGraph* sg = nullptr;
                 MRMT3_TRY(get_graph(h, gp[g], kind, &sg));
@@ -799,13 +792,13 @@ static Status run_decode(mrmt3_handle* h, StepPlan pl, int n_prefix, bool debug_
         }
         return OkStatus();
     };
-    for (int i = 0; i < n_prefix; ++i) MRMT3_TRY(step_all(1, i));
+    for (int i = 0; i < n_prefix; ++i) MRMT3_TRY(step_all(1));
     int polls = 0;
     bool pending[2] = {false, false};
     bool all_done = false;
     const bool may_exit_early = pl.st.forced == nullptr;
     for (int t = 0; t < pl.st.max_tokens && !all_done; ++t) {
-        MRMT3_TRY(step_all(0, n_prefix + t));
+        MRMT3_TRY(step_all(0));
         if (may_exit_early && (t + 1) % kPollEvery == 0 && t + 1 < pl.st.max_tokens) {
             // n_active is decremented by every group; a read through any stream can only be
             // stale-high, which delays the exit but never cuts a lane short

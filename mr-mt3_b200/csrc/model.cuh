@@ -57,15 +57,13 @@ struct RowWorkspace {
 
 struct StepGraphKey {
     int lane0, n_lanes, tk, max_tokens, prefix_len, kind;  // kind 0 = token step, 1 = prefix step
-    int self_chunks;                                       // 128-key chunks the self-attention grid covers
     bool operator<(const StepGraphKey& o) const {
         if (lane0 != o.lane0) return lane0 < o.lane0;
         if (n_lanes != o.n_lanes) return n_lanes < o.n_lanes;
         if (tk != o.tk) return tk < o.tk;
         if (max_tokens != o.max_tokens) return max_tokens < o.max_tokens;
         if (prefix_len != o.prefix_len) return prefix_len < o.prefix_len;
-        if (kind != o.kind) return kind < o.kind;
-        return self_chunks < o.self_chunks;
+        return kind < o.kind;
     }
 };
 
@@ -126,8 +124,6 @@ struct mrmt3_handle {
     mrmt3::DeviceBuffer d_h32, d_n_bf16, d_qkv, d_ctx, d_qc, d_ff, d_logits;
     mrmt3::DeviceBuffer d_state;         // ints: step, n_active, ticket, then per-lane arrays
     mrmt3::DeviceBuffer kv_pool, block_table, cross_cache;
-    mrmt3::DeviceBuffer attn_scratch, attn_tickets;  // split-key attention partials + tickets
-    int chunk_cap = 0;
     mrmt3::DeviceBuffer lane_tab;        // per-lane int tables (seg index, prev row, active)
     int* h_pinned = nullptr;             // pinned host ints for polling / finish steps
 
