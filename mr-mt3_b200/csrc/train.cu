@@ -427,9 +427,6 @@ Status train_backward(mrmt3_handle* h, float* grad, const float* dlogits_f32, cu
     MRMT3_CUDA_TRY(cudaMemsetAsync(grad, 0, t->n_total * 4, s));
 
     // W^T copies for the dgrad GEMMs
-    for (auto& sl : t->slots)
-        if (sl.w16) RUN(h, launch_transpose_bf16(sl.w16, sl.cols, sl.wt, sl.rows, sl.rows, sl.cols, s));
-
     // scratch
     const size_t kvN = (size_t)n_dec * 2 * kInner;
     size_t need = Mmax * kDModel * 4 * 2 + Mmax * kDModel * 2 * 2 + Mmax * 2 * kDFF * 2 + Mmax * kDFF * 2 +
@@ -470,6 +467,10 @@ Status train_backward(mrmt3_handle* h, float* grad, const float* dlogits_f32, cu
         if (prof) cudaEventRecord(recs.back().b, s);
     };
     auto G = [&](int slot) { return grad + t->slots[slot].off; };
+    tic("W^T copies");
+    for (auto& sl : t->slots)
+        if (sl.w16) RUN(h, launch_transpose_bf16(sl.w16, sl.cols, sl.wt, sl.rows, sl.rows, sl.cols, s));
+    toc();
     // dX (M, Kin) bf16 = dY (M, N) . W (N, Kin)
     auto dgrad = [&](const bf16* dY, int N, int slot, bf16* dX, size_t M) -> Status {
         const ParamSlot& sl = t->slots[slot];
@@ -504,8 +505,12 @@ Status train_backward(mrmt3_handle* h, float* grad, const float* dlogits_f32, cu
         toc();
         return OkStatus();
     };
-    auto cast_dH = [&](size_t M) -> Status {
-        RUN(h, launch_cast_f32_bf16(dH, dHb, M * kDModel, s));
+    // dHb always mirrors dH: every update of dH goes through norm_bwd, which writes both
+    auto cast_dH = [&](size_t) -> Status { return OkStatus(); };
+    auto norm_bwd = [&](const float* x, const float* g, const bf16* dy, size_t M, float* dg) -> Status {
+        tic("rmsnorm bwd");
+        RUN(h, launch_rmsnorm_bwd(x, g, eps, dy, (int)M, dH, dHb, dg, s));
+        toc();
         return OkStatus();
     };
     auto attn_bwd = [&](const bf16* Q, long qb, int qr, const bf16* K, const bf16* V, long kb, long kh, int kr,
@@ -530,10 +535,12 @@ Status train_backward(mrmt3_handle* h, float* grad, const float* dlogits_f32, cu
         MRMT3_TRY(cast_dH(M));
         MRMT3_TRY(dgrad(dHb, kDModel, ls.wff, dff, M));
         MRMT3_TRY(wgrad(dHb, kDModel, kDModel, st.ff, kDFF, kDFF, G(ls.wff), M));
+        tic("gated gelu bwd");
         RUN(h, launch_gated_gelu_bwd(st.raw, dff, draw, M, s));
+        toc();
         MRMT3_TRY(dgrad(draw, 2 * kDFF, ls.wi, dn, M));
         MRMT3_TRY(wgrad(draw, 2 * kDFF, 2 * kDFF, st.n2, kDModel, kDModel, G(ls.wi), M));
-        RUN(h, launch_rmsnorm_bwd(st.h_mid, Lw.ln_ff, eps, dn, (int)M, dH, G(ls.ln_ff), s));
+        MRMT3_TRY(norm_bwd(st.h_mid, Lw.ln_ff, dn, M, G(ls.ln_ff)));
         return OkStatus();
     };
     auto self_bwd = [&](const LayerSlots& ls, const LayerW& Lw, const LayerStash& st, size_t M, int T, int causal) -> Status {
@@ -545,7 +552,7 @@ Status train_backward(mrmt3_handle* h, float* grad, const float* dlogits_f32, cu
                            dqkv, dqkv + kInner, dqkv + 2 * kInner, tb, kDKV, 3 * kInner, st.lse, T, T, causal));
         MRMT3_TRY(dgrad(dqkv, 3 * kInner, ls.wqkv, dn, M));
         MRMT3_TRY(wgrad(dqkv, 3 * kInner, 3 * kInner, st.n1, kDModel, kDModel, G(ls.wqkv), M));
-        RUN(h, launch_rmsnorm_bwd(st.h_in, Lw.ln_self, eps, dn, (int)M, dH, G(ls.ln_self), s));
+        MRMT3_TRY(norm_bwd(st.h_in, Lw.ln_self, dn, M, G(ls.ln_self)));
         return OkStatus();
     };
 
@@ -553,7 +560,7 @@ Status train_backward(mrmt3_handle* h, float* grad, const float* dlogits_f32, cu
     MRMT3_CUDA_TRY(cudaMemsetAsync(dH, 0, Md * kDModel * 4, s));
     MRMT3_TRY(dgrad(t->dlogits, kVocab, t->lm_head, dn, Md));
     MRMT3_TRY(wgrad(t->dlogits, kVocab, kVocab, t->dec_n_final, kDModel, kDModel, G(t->lm_head), Md));
-    RUN(h, launch_rmsnorm_bwd(t->dec_h_final, h->dec.final_ln, eps, dn, (int)Md, dH, G(t->dec_final), s));
+    MRMT3_TRY(norm_bwd(t->dec_h_final, h->dec.final_ln, dn, Md, G(t->dec_final)));
 
     // ---- decoder layers, last to first ----
     MRMT3_CUDA_TRY(cudaMemsetAsync(dkv, 0, Mk * kvN * 2, s));
@@ -575,10 +582,12 @@ Status train_backward(mrmt3_handle* h, float* grad, const float* dlogits_f32, cu
                            (long)tk * (long)kvN, kDKV, (int)kvN, st.lse_c, L, tk, 0));
         MRMT3_TRY(dgrad(dqc, kInner, ls.cq, dn, Md));
         MRMT3_TRY(wgrad(dqc, kInner, kInner, st.nc, kDModel, kDModel, G(ls.cq), Md));
-        RUN(h, launch_rmsnorm_bwd(st.h_mid2, Lw.ln_cross, eps, dn, (int)Md, dH, G(ls.ln_cross), s));
+        MRMT3_TRY(norm_bwd(st.h_mid2, Lw.ln_cross, dn, Md, G(ls.ln_cross)));
         MRMT3_TRY(self_bwd(ls, Lw, st, Md, L, 1));
     }
+    tic("embedding bwd");
     RUN(h, launch_embed_bwd(t->dec_ids, dH, G(t->emb), (int)Md, s));
+    toc();
 
     // ---- cross K/V projection -> [encoder output ; memory rows] ----
     MRMT3_TRY(dgrad(dkv, (int)kvN, t->cross_kv, dn, Mk));
@@ -592,7 +601,7 @@ Status train_backward(mrmt3_handle* h, float* grad, const float* dlogits_f32, cu
         MRMT3_CUDA_TRY(cudaMemcpy2DAsync(dsplit, (size_t)Lp * kDModel * 2, dn + (size_t)kSegFrames * kDModel,
                                          (size_t)tk * kDModel * 2, (size_t)n_mem * kDModel * 2, B, cudaMemcpyDeviceToDevice, s));
         MRMT3_CUDA_TRY(cudaMemsetAsync(dH, 0, Mm * kDModel * 4, s));
-        RUN(h, launch_rmsnorm_bwd(t->mem_h_final, h->mem.final_ln, eps, dsplit, (int)Mm, dH, G(t->mem_final), s));
+        MRMT3_TRY(norm_bwd(t->mem_h_final, h->mem.final_ln, dsplit, Mm, G(t->mem_final)));
         // dsplit is free again; keep the encoder rows of dn for later in it
         MRMT3_CUDA_TRY(cudaMemcpy2DAsync(dsplit, (size_t)kSegFrames * kDModel * 2, dn, (size_t)tk * kDModel * 2,
                                          (size_t)kSegFrames * kDModel * 2, B, cudaMemcpyDeviceToDevice, s));
@@ -606,14 +615,16 @@ Status train_backward(mrmt3_handle* h, float* grad, const float* dlogits_f32, cu
         const ParamSlot& sp = t->slots[t->segmem_proj];
         RUN(h, launch_gemm_tc(*h->tma, dHb, kDModel, Mm, id, sp.wt, kDModel, (int)Mm, kDModel, kDModel,
                               EpiStoreF32{dH, kDModel}, s));
+        tic("embedding bwd");
         RUN(h, launch_embed_bwd(t->prev_ids, dH, G(t->emb), (int)Mm, s));
+        toc();
     } else {
         MRMT3_CUDA_TRY(cudaMemcpyAsync(dsplit, dn, Me * kDModel * 2, cudaMemcpyDeviceToDevice, s));
     }
 
     // ---- encoder ----
     MRMT3_CUDA_TRY(cudaMemsetAsync(dH, 0, Me * kDModel * 4, s));
-    RUN(h, launch_rmsnorm_bwd(t->enc_h_final, h->enc.final_ln, eps, dsplit, (int)Me, dH, G(t->enc_final), s));
+    MRMT3_TRY(norm_bwd(t->enc_h_final, h->enc.final_ln, dsplit, Me, G(t->enc_final)));
     for (int li = n_enc - 1; li >= 0; --li) {
         MRMT3_TRY(ffn_bwd(t->enc[li], h->enc.layers[li], t->enc_st[li], Me));
         MRMT3_TRY(self_bwd(t->enc[li], h->enc.layers[li], t->enc_st[li], Me, kSegFrames, 0));

@@ -9,7 +9,7 @@ namespace mrmt3 {
 Status launch_xent(const float* logits, const long long* labels, int rows, int V, float inv_count,
                    float* row_loss, bf16* dlogits, cudaStream_t s);
 Status launch_rmsnorm_bwd(const float* x, const float* g, float eps, const bf16* dy, int rows, float* dres,
-                          float* dg, cudaStream_t s);
+                          bf16* dres_bf16, float* dg, cudaStream_t s);
 Status launch_gated_gelu_fwd(const bf16* raw, bf16* ff, size_t rows, cudaStream_t s);
 Status launch_gated_gelu_bwd(const bf16* raw, const bf16* dff, bf16* draw, size_t rows, cudaStream_t s);
 Status launch_transpose_bf16(const bf16* in, int ld_in, bf16* out, int ld_out, int R, int C, cudaStream_t s);

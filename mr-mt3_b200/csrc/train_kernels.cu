@@ -61,10 +61,12 @@ Status launch_xent(const float* logits, const long long* labels, int rows, int V
 // ---------------------------------------------------------------------------------------------
 // RMSNorm backward.  y = g * x * r, r = rsqrt(mean(x^2) + eps):
 //   dx = r * (g * dy) - x * r^3 / d * sum_j (g_j dy_j x_j);  dg_j = sum_rows dy_j x_j r
-// dx is ADDED to dres (the gradient of the residual stream the norm branched from).
+// dx is ADDED to dres (the gradient of the residual stream the norm branched from); the updated
+// rows are also written as bf16 (dres_bf16, optional) for the GEMMs that consume them next.
 __global__ void __launch_bounds__(256)
     rmsnorm_bwd_kernel(const float* __restrict__ x, const float* __restrict__ g, float eps,
-                       const bf16* __restrict__ dy, int rows, float* __restrict__ dres, float* __restrict__ dg) {
+                       const bf16* __restrict__ dy, int rows, float* __restrict__ dres, bf16* __restrict__ dres_bf16,
+                       float* __restrict__ dg) {
     __shared__ float s_dg[kDModel];
     for (int i = threadIdx.x; i < kDModel; i += 256) s_dg[i] = 0.f;
     __syncthreads();
@@ -105,6 +107,9 @@ __global__ void __launch_bounds__(256)
             d.z += r * gv[i].z * dv[i].z - xv[i].z * c;
             d.w += r * gv[i].w * dv[i].w - xv[i].w * c;
             dr[lane + i * 32] = d;
+            if (dres_bf16)  // the next backward GEMMs take the updated residual gradient as a bf16 operand
+                *reinterpret_cast<uint2*>(dres_bf16 + (size_t)row * kDModel + (lane + i * 32) * 4) =
+                    make_uint2(pack_bf16(d.x, d.y), pack_bf16(d.z, d.w));
             acc_dg[i * 4 + 0] += dv[i].x * xv[i].x * r;
             acc_dg[i * 4 + 1] += dv[i].y * xv[i].y * r;
             acc_dg[i * 4 + 2] += dv[i].z * xv[i].z * r;
@@ -120,9 +125,9 @@ __global__ void __launch_bounds__(256)
 }
 
 Status launch_rmsnorm_bwd(const float* x, const float* g, float eps, const bf16* dy, int rows, float* dres,
-                          float* dg, cudaStream_t s) {
+                          bf16* dres_bf16, float* dg, cudaStream_t s) {
     if (rows <= 0) return OkStatus();
-    rmsnorm_bwd_kernel<<<std::min(ceil_div(rows, 8), 592), 256, 0, s>>>(x, g, eps, dy, rows, dres, dg);
+    rmsnorm_bwd_kernel<<<std::min(ceil_div(rows, 8), 592), 256, 0, s>>>(x, g, eps, dy, rows, dres, dres_bf16, dg);
     MRMT3_CHECK_LAUNCH();
     return OkStatus();
 }
@@ -239,23 +244,68 @@ Status launch_transpose_f32_to_bf16(const float* in, bf16* out, int R, int C, cu
 }
 
 // ---------------------------------------------------------------------------------------------
-// dEmb[ids[r]] += dH[r]   (rows of 512 fp32)
-__global__ void embed_bwd_kernel(const long long* __restrict__ ids, const float* __restrict__ dH,
-                                 float* __restrict__ dEmb, int rows) {
-    int row = blockIdx.x * 2 + (threadIdx.x >> 7);
-    if (row >= rows) return;
-    int c = (threadIdx.x & 127) * 4;
-    const float4 v = *reinterpret_cast<const float4*>(dH + (size_t)row * kDModel + c);
-    float* d = dEmb + (size_t)ids[row] * kDModel + c;
-    atomicAdd(d + 0, v.x);
-    atomicAdd(d + 1, v.y);
-    atomicAdd(d + 2, v.z);
-    atomicAdd(d + 3, v.w);
+// dEmb[ids[r]] += dH[r]   (rows of 512 fp32).  Token ids repeat heavily (pad = 0 fills half of a
+// batch), so a plain scatter serialises 16 K x 512 atomics on one row.  Here a CTA owns kEmbIds
+// consecutive ids and one slice of the rows: it scans the slice's ids from shared memory, each warp
+// sums the matching rows it is responsible for in registers (four independent 16-byte loads per
+// lane per row), and only the per-warp totals are added atomically (<= 4 x kEmbSlices per address).
+constexpr int kEmbIds = 4;
+constexpr int kEmbSlices = 16;
+__global__ void __launch_bounds__(128)
+    embed_bwd_kernel(const long long* __restrict__ ids, const float* __restrict__ dH, float* __restrict__ dEmb,
+                     int rows, int vocab) {
+    __shared__ int s_ids[1024];
+    const int id0 = blockIdx.x * kEmbIds;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int per = (rows + kEmbSlices - 1) / kEmbSlices;
+    const int r_begin = blockIdx.y * per, r_end = min(rows, r_begin + per);
+    float4 acc[kEmbIds][4];
+#pragma unroll
+    for (int k = 0; k < kEmbIds; ++k)
+#pragma unroll
+        for (int j = 0; j < 4; ++j) acc[k][j] = make_float4(0.f, 0.f, 0.f, 0.f);
+    for (int r0 = r_begin; r0 < r_end; r0 += 1024) {
+        const int n = min(1024, r_end - r0);
+        __syncthreads();
+        for (int i = threadIdx.x; i < n; i += 128) s_ids[i] = (int)ids[r0 + i];
+        __syncthreads();
+        for (int i = warp; i < n; i += 4) {
+            const int k = s_ids[i] - id0;
+            if (k >= 0 && k < kEmbIds) {  // uniform across the warp
+                const float4* src = reinterpret_cast<const float4*>(dH + (size_t)(r0 + i) * kDModel) + lane;
+                float4 v[4];
+#pragma unroll
+                for (int j = 0; j < 4; ++j) v[j] = src[j * 32];
+#pragma unroll
+                for (int q = 0; q < kEmbIds; ++q)
+                    if (q == k) {
+#pragma unroll
+                        for (int j = 0; j < 4; ++j) {
+                            acc[q][j].x += v[j].x; acc[q][j].y += v[j].y; acc[q][j].z += v[j].z; acc[q][j].w += v[j].w;
+                        }
+                    }
+            }
+        }
+    }
+#pragma unroll
+    for (int k = 0; k < kEmbIds; ++k) {
+        if (id0 + k >= vocab) continue;
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            const float4 a = acc[k][j];
+            if (a.x == 0.f && a.y == 0.f && a.z == 0.f && a.w == 0.f) continue;
+            float* d = dEmb + (size_t)(id0 + k) * kDModel + (j * 32 + lane) * 4;
+            atomicAdd(d + 0, a.x);
+            atomicAdd(d + 1, a.y);
+            atomicAdd(d + 2, a.z);
+            atomicAdd(d + 3, a.w);
+        }
+    }
 }
 
 Status launch_embed_bwd(const long long* ids, const float* dH, float* dEmb, int rows, cudaStream_t s) {
     if (rows <= 0) return OkStatus();
-    embed_bwd_kernel<<<ceil_div(rows, 2), 256, 0, s>>>(ids, dH, dEmb, rows);
+    embed_bwd_kernel<<<dim3(ceil_div(kVocab, kEmbIds), kEmbSlices), 128, 0, s>>>(ids, dH, dEmb, rows, kVocab);
     MRMT3_CHECK_LAUNCH();
     return OkStatus();
 }
