@@ -462,12 +462,12 @@ __device__ __forceinline__ void bwd_zero(float (&c)[8][4]) {
 
 // dQ: one CTA per (query tile, head, batch); loops over the key tiles.
 //   S = Q K^T, P = exp2(S log2e - lse2[row]), dP = dO V^T, dS = P * (dP - delta[row]), dQ += dS K
+// K/V tiles are double-buffered: once the Q / dO fragments are in registers their shared-memory
+// tiles become the second stage, so the next tile's cp.async overlaps this tile's mma.
 __global__ void __launch_bounds__(128)
     attn_bwd_dq_kernel(AttnBwdParams p) {
-    __shared__ __align__(128) bf16 sQ[kBwdT * kDKV];
-    __shared__ __align__(128) bf16 sdO[kBwdT * kDKV];
-    __shared__ __align__(128) bf16 sK[kBwdT * kDKV];
-    __shared__ __align__(128) bf16 sV[kBwdT * kDKV];
+    __shared__ __align__(128) bf16 sA[2][kBwdT * kDKV];  // stage s: K tile   (stage 1 holds Q first)
+    __shared__ __align__(128) bf16 sB[2][kBwdT * kDKV];  // stage s: V tile   (stage 1 holds dO first)
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int q0 = blockIdx.x * kBwdT, head = blockIdx.y, b = blockIdx.z;
     const bf16* Q = p.Q + (size_t)b * p.q_batch_stride + head * p.q_head_stride;
@@ -476,14 +476,23 @@ __global__ void __launch_bounds__(128)
     const bf16* dO = p.dO + (size_t)b * p.o_batch_stride + head * p.o_head_stride;
     const float kLog2e = 1.4426950408889634f;
 
-    bwd_load_tile(sQ, Q, p.q_row_stride, q0, p.Tq);
-    bwd_load_tile(sdO, dO, p.o_row_stride, q0, p.Tq);
+    int n_kt = (p.Tk + kBwdT - 1) / kBwdT;
+    if (p.causal) n_kt = min(n_kt, max(0, (q0 + kBwdT - 1 + p.causal_offset) / kBwdT + 1));
+
+    bwd_load_tile(sA[1], Q, p.q_row_stride, q0, p.Tq);
+    bwd_load_tile(sB[1], dO, p.o_row_stride, q0, p.Tq);
     cp_async_commit();
-    cp_async_wait<0>();
+    if (n_kt > 0) {
+        bwd_load_tile(sA[0], K, p.k_row_stride, 0, p.Tk);
+        bwd_load_tile(sB[0], V, p.v_row_stride, 0, p.Tk);
+    }
+    cp_async_commit();
+    cp_async_wait<1>();
     __syncthreads();
     uint32_t qf[4][4], dof[4][4];
-    bwd_a_frags(qf, sQ, warp, lane);
-    bwd_a_frags(dof, sdO, warp, lane);
+    bwd_a_frags(qf, sA[1], warp, lane);
+    bwd_a_frags(dof, sB[1], warp, lane);
+    __syncthreads();  // stage 1 may now be overwritten
 
     const int row_lo = q0 + warp * 16 + (lane >> 2);
     float lse[2], dl[2] = {0.f, 0.f};
@@ -492,71 +501,68 @@ __global__ void __launch_bounds__(128)
         int r = row_lo + h * 8;
         lse[h] = p.lse2[((size_t)b * kHeads + head) * p.Tq + min(r, p.Tq - 1)];
     }
-    int n_kt = (p.Tk + kBwdT - 1) / kBwdT;
-    if (p.causal) n_kt = min(n_kt, max(0, (q0 + kBwdT - 1 + p.causal_offset) / kBwdT + 1));
-    // pass 1: delta[row] = sum_k P dP with the SAME recomputed P and dP that pass 2 uses, so that
-    // dS = P (dP - delta) sums to zero over every row exactly as in exact arithmetic (taking
-    // delta = sum_d dO O from the bf16 output instead leaves a 2^-9 mismatch that dominates dS on
-    // sharply peaked rows)
-    for (int kt = 0; kt < n_kt; ++kt) {
-        __syncthreads();
-        bwd_load_tile(sK, K, p.k_row_stride, kt * kBwdT, p.Tk);
-        bwd_load_tile(sV, V, p.v_row_stride, kt * kBwdT, p.Tk);
-        cp_async_commit();
-        cp_async_wait<0>();
-        __syncthreads();
-        float s[8][4], dp[8][4];
-        bwd_zero(s);
-        bwd_zero(dp);
-        bwd_mma_nt(s, qf, sK, lane);
-        bwd_mma_nt(dp, dof, sV, lane);
-#pragma unroll
-        for (int ni = 0; ni < 8; ++ni) {
-#pragma unroll
-            for (int r = 0; r < 4; ++r) {
-                const int key = kt * kBwdT + ni * 8 + (lane & 3) * 2 + (r & 1);
-                const int row = row_lo + ((r >> 1) << 3);
-                const bool ok = key < p.Tk && (!p.causal || key <= row + p.causal_offset);
-                if (ok) dl[r >> 1] += exp2f(s[ni][r] * kLog2e - lse[r >> 1]) * dp[ni][r];
-            }
-        }
-    }
-#pragma unroll
-    for (int h = 0; h < 2; ++h) {
-        dl[h] += __shfl_xor_sync(0xffffffffu, dl[h], 1);
-        dl[h] += __shfl_xor_sync(0xffffffffu, dl[h], 2);
-        int r = row_lo + h * 8;
-        if ((lane & 3) == 0 && r < p.Tq) p.delta[((size_t)b * kHeads + head) * p.Tq + r] = dl[h];
-    }
     float dq[8][4];
     bwd_zero(dq);
-    for (int kt = 0; kt < n_kt; ++kt) {
-        __syncthreads();  // previous tile fully consumed
-        bwd_load_tile(sK, K, p.k_row_stride, kt * kBwdT, p.Tk);
-        bwd_load_tile(sV, V, p.v_row_stride, kt * kBwdT, p.Tk);
+    // pass 0: delta[row] = sum_k P dP with the SAME recomputed P and dP that pass 1 uses, so that
+    // dS = P (dP - delta) sums to zero over every row exactly as in exact arithmetic (taking
+    // delta = sum_d dO O from the bf16 output instead leaves a 2^-9 mismatch that dominates dS on
+    // sharply peaked rows).  pass 1: dQ.  The tile sequence runs through both passes: item
+    // i = pass * n_kt + kt lives in stage i & 1, and item i + 1 is requested before item i is used.
+    const int n_items = 2 * n_kt;
+    for (int i = 0; i < n_items; ++i) {
+        const int st = i & 1, kt = i % n_kt, pass = i / n_kt;
+        if (i + 1 < n_items) {
+            const int kn = (i + 1) % n_kt;
+            bwd_load_tile(sA[st ^ 1], K, p.k_row_stride, kn * kBwdT, p.Tk);
+            bwd_load_tile(sB[st ^ 1], V, p.v_row_stride, kn * kBwdT, p.Tk);
+        }
         cp_async_commit();
-        cp_async_wait<0>();
+        cp_async_wait<1>();
         __syncthreads();
         float s[8][4], dp[8][4];
         bwd_zero(s);
         bwd_zero(dp);
-        bwd_mma_nt(s, qf, sK, lane);
-        bwd_mma_nt(dp, dof, sV, lane);
+        bwd_mma_nt(s, qf, sA[st], lane);
+        bwd_mma_nt(dp, dof, sB[st], lane);
+        if (pass == 0) {
 #pragma unroll
-        for (int ni = 0; ni < 8; ++ni) {
+            for (int ni = 0; ni < 8; ++ni) {
 #pragma unroll
-            for (int r = 0; r < 4; ++r) {
-                const int key = kt * kBwdT + ni * 8 + (lane & 3) * 2 + (r & 1);
-                const int row = row_lo + ((r >> 1) << 3);
-                const bool ok = key < p.Tk && (!p.causal || key <= row + p.causal_offset);
-                const float pr = ok ? exp2f(s[ni][r] * kLog2e - lse[r >> 1]) : 0.f;
-                s[ni][r] = pr * (dp[ni][r] - dl[r >> 1]);  // dS
+                for (int r = 0; r < 4; ++r) {
+                    const int key = kt * kBwdT + ni * 8 + (lane & 3) * 2 + (r & 1);
+                    const int row = row_lo + ((r >> 1) << 3);
+                    const bool ok = key < p.Tk && (!p.causal || key <= row + p.causal_offset);
+                    if (ok) dl[r >> 1] += exp2f(s[ni][r] * kLog2e - lse[r >> 1]) * dp[ni][r];
+                }
             }
+            if (kt == n_kt - 1) {
+#pragma unroll
+                for (int h = 0; h < 2; ++h) {
+                    dl[h] += __shfl_xor_sync(0xffffffffu, dl[h], 1);
+                    dl[h] += __shfl_xor_sync(0xffffffffu, dl[h], 2);
+                    int r = row_lo + h * 8;
+                    if ((lane & 3) == 0 && r < p.Tq) p.delta[((size_t)b * kHeads + head) * p.Tq + r] = dl[h];
+                }
+            }
+        } else {
+#pragma unroll
+            for (int ni = 0; ni < 8; ++ni) {
+#pragma unroll
+                for (int r = 0; r < 4; ++r) {
+                    const int key = kt * kBwdT + ni * 8 + (lane & 3) * 2 + (r & 1);
+                    const int row = row_lo + ((r >> 1) << 3);
+                    const bool ok = key < p.Tk && (!p.causal || key <= row + p.causal_offset);
+                    const float pr = ok ? exp2f(s[ni][r] * kLog2e - lse[r >> 1]) : 0.f;
+                    s[ni][r] = pr * (dp[ni][r] - dl[r >> 1]);  // dS
+                }
+            }
+            uint32_t dsf[4][4];
+            bwd_c_to_a(dsf, s);
+            bwd_mma_nn(dq, dsf, sA[st], lane);
         }
-        uint32_t dsf[4][4];
-        bwd_c_to_a(dsf, s);
-        bwd_mma_nn(dq, dsf, sK, lane);
+        __syncthreads();  // every warp is done with stage st before it is refilled
     }
+    cp_async_wait<0>();
     bf16* dQ = p.dQ + (size_t)b * p.q_batch_stride + head * p.q_head_stride;
 #pragma unroll
     for (int ni = 0; ni < 8; ++ni) {
@@ -571,13 +577,12 @@ __global__ void __launch_bounds__(128)
 // dK, dV: one CTA per (key tile, head, batch); loops over the query tiles, everything transposed
 // (rows = keys):  S^T = K Q^T, P^T = exp2(S^T log2e - lse2[col]), dV += P^T dO,
 //                 dP^T = V dO^T, dS^T = P^T * (dP^T - delta[col]), dK += dS^T Q
+// Q / dO tiles are double-buffered the same way (the K / V tiles become stage 1).
 __global__ void __launch_bounds__(128)
     attn_bwd_dkv_kernel(AttnBwdParams p) {
-    __shared__ __align__(128) bf16 sK[kBwdT * kDKV];
-    __shared__ __align__(128) bf16 sV[kBwdT * kDKV];
-    __shared__ __align__(128) bf16 sQ[kBwdT * kDKV];
-    __shared__ __align__(128) bf16 sdO[kBwdT * kDKV];
-    __shared__ float s_lse[kBwdT], s_dl[kBwdT];
+    __shared__ __align__(128) bf16 sA[2][kBwdT * kDKV];  // stage s: Q tile   (stage 1 holds K first)
+    __shared__ __align__(128) bf16 sB[2][kBwdT * kDKV];  // stage s: dO tile  (stage 1 holds V first)
+    __shared__ float s_lse[2][kBwdT], s_dl[2][kBwdT];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int k0 = blockIdx.x * kBwdT, head = blockIdx.y, b = blockIdx.z;
     const bf16* Q = p.Q + (size_t)b * p.q_batch_stride + head * p.q_head_stride;
@@ -586,40 +591,53 @@ __global__ void __launch_bounds__(128)
     const bf16* dO = p.dO + (size_t)b * p.o_batch_stride + head * p.o_head_stride;
     const float kLog2e = 1.4426950408889634f;
 
-    bwd_load_tile(sK, K, p.k_row_stride, k0, p.Tk);
-    bwd_load_tile(sV, V, p.v_row_stride, k0, p.Tk);
-    cp_async_commit();
-    cp_async_wait<0>();
-    __syncthreads();
-    uint32_t kf[4][4], vf[4][4];
-    bwd_a_frags(kf, sK, warp, lane);
-    bwd_a_frags(vf, sV, warp, lane);
-
-    const int key_lo = k0 + warp * 16 + (lane >> 2);  // this thread's keys: key_lo, key_lo + 8
     const int n_qt = (p.Tq + kBwdT - 1) / kBwdT;
     int qt0 = 0;
     if (p.causal) qt0 = max(0, (k0 - p.causal_offset) / kBwdT);  // first query tile that can see key k0
+    auto load_stats = [&](int stg, int qt) {
+        if (threadIdx.x < kBwdT) {
+            int r = qt * kBwdT + threadIdx.x;
+            size_t idx = ((size_t)b * kHeads + head) * p.Tq + min(r, p.Tq - 1);
+            s_lse[stg][threadIdx.x] = p.lse2[idx];
+            s_dl[stg][threadIdx.x] = p.delta[idx];
+        }
+    };
+
+    bwd_load_tile(sA[1], K, p.k_row_stride, k0, p.Tk);
+    bwd_load_tile(sB[1], V, p.v_row_stride, k0, p.Tk);
+    cp_async_commit();
+    if (qt0 < n_qt) {
+        bwd_load_tile(sA[0], Q, p.q_row_stride, qt0 * kBwdT, p.Tq);
+        bwd_load_tile(sB[0], dO, p.o_row_stride, qt0 * kBwdT, p.Tq);
+        load_stats(0, qt0);
+    }
+    cp_async_commit();
+    cp_async_wait<1>();
+    __syncthreads();
+    uint32_t kf[4][4], vf[4][4];
+    bwd_a_frags(kf, sA[1], warp, lane);
+    bwd_a_frags(vf, sB[1], warp, lane);
+    __syncthreads();
+
+    const int key_lo = k0 + warp * 16 + (lane >> 2);  // this thread's keys: key_lo, key_lo + 8
     float dk[8][4], dv[8][4];
     bwd_zero(dk);
     bwd_zero(dv);
     for (int qt = qt0; qt < n_qt; ++qt) {
-        __syncthreads();
-        bwd_load_tile(sQ, Q, p.q_row_stride, qt * kBwdT, p.Tq);
-        bwd_load_tile(sdO, dO, p.o_row_stride, qt * kBwdT, p.Tq);
-        cp_async_commit();
-        if (threadIdx.x < kBwdT) {
-            int r = qt * kBwdT + threadIdx.x;
-            size_t idx = ((size_t)b * kHeads + head) * p.Tq + min(r, p.Tq - 1);
-            s_lse[threadIdx.x] = p.lse2[idx];
-            s_dl[threadIdx.x] = p.delta[idx];
+        const int st = (qt - qt0) & 1;
+        if (qt + 1 < n_qt) {
+            bwd_load_tile(sA[st ^ 1], Q, p.q_row_stride, (qt + 1) * kBwdT, p.Tq);
+            bwd_load_tile(sB[st ^ 1], dO, p.o_row_stride, (qt + 1) * kBwdT, p.Tq);
+            load_stats(st ^ 1, qt + 1);
         }
-        cp_async_wait<0>();
+        cp_async_commit();
+        cp_async_wait<1>();
         __syncthreads();
-        float st[8][4], dpt[8][4];
-        bwd_zero(st);
+        float stt[8][4], dpt[8][4];
+        bwd_zero(stt);
         bwd_zero(dpt);
-        bwd_mma_nt(st, kf, sQ, lane);    // S^T = K Q^T
-        bwd_mma_nt(dpt, vf, sdO, lane);  // dP^T = V dO^T
+        bwd_mma_nt(stt, kf, sA[st], lane);   // S^T = K Q^T
+        bwd_mma_nt(dpt, vf, sB[st], lane);   // dP^T = V dO^T
         float pt[8][4];
 #pragma unroll
         for (int ni = 0; ni < 8; ++ni) {
@@ -629,17 +647,19 @@ __global__ void __launch_bounds__(128)
                 const int row = qt * kBwdT + qc;              // query index
                 const int key = key_lo + ((r >> 1) << 3);
                 const bool ok = row < p.Tq && key < p.Tk && (!p.causal || key <= row + p.causal_offset);
-                const float pr = ok ? exp2f(st[ni][r] * kLog2e - s_lse[qc]) : 0.f;
+                const float pr = ok ? exp2f(stt[ni][r] * kLog2e - s_lse[st][qc]) : 0.f;
                 pt[ni][r] = pr;
-                st[ni][r] = pr * (dpt[ni][r] - s_dl[qc]);     // dS^T
+                stt[ni][r] = pr * (dpt[ni][r] - s_dl[st][qc]);  // dS^T
             }
         }
         uint32_t af[4][4];
         bwd_c_to_a(af, pt);
-        bwd_mma_nn(dv, af, sdO, lane);  // dV += P^T dO
-        bwd_c_to_a(af, st);
-        bwd_mma_nn(dk, af, sQ, lane);   // dK += dS^T Q
+        bwd_mma_nn(dv, af, sB[st], lane);  // dV += P^T dO
+        bwd_c_to_a(af, stt);
+        bwd_mma_nn(dk, af, sA[st], lane);  // dK += dS^T Q
+        __syncthreads();
     }
+    cp_async_wait<0>();
     bf16* dK = p.dK + (size_t)b * p.dk_batch_stride + head * p.dk_head_stride;
     bf16* dV = p.dV + (size_t)b * p.dk_batch_stride + head * p.dk_head_stride;
 #pragma unroll
