@@ -1,4 +1,5 @@
-"""Track sharding across the GPUs of one box.
+"""Track sharding across the GPUs of one box, and the gradient exchange of the fine-tune step
+(SURVEY 8e).
 
 Tracks are independent (reference test.py:45-64 walks them one by one); the segments of one
 MR-MT3 track are sequential (models/t5_segmem_v2_with_prev.py:241-294).  So the unit of
@@ -52,3 +53,18 @@ def gather_token_rows(local_rows, local_track_ids, seg_counts, max_length, group
             out[int(base[t]):int(base[t]) + n] = bufs[r][off:off + n]
             off += n
     return out
+
+
+def allreduce_mean_(flat_grad, group=None):
+    """Data-parallel gradient exchange of the fine-tune step: ONE all-reduce (sum) of the flat fp32
+    gradient buffer, divided by the world size in place -- what DDP's bucketed all-reduce amounts
+    to for the reference (every parameter receives a gradient), without buckets because
+    the whole gradient already is one contiguous 194 MB buffer.  nccl (CUDA) or gloo (CPU).
+    A no-op when torch.distributed is not initialised or the group has one rank."""
+    if not (dist.is_available() and dist.is_initialized()):
+        return flat_grad
+    world = dist.get_world_size(group)
+    if world > 1:
+        dist.all_reduce(flat_grad, op=dist.ReduceOp.SUM, group=group)
+        flat_grad /= world
+    return flat_grad

@@ -306,10 +306,8 @@ class T5ForConditionalGeneration(nn.Module):
             targets_prev[targets_prev == -100] = 0        # in place, as t5_segmem_v2_with_prev.py:119
         logits, loss = eng.train_forward(inputs, self._shift_right(labels), labels, targets_prev)
         grad = eng.train_backward()
-        import torch.distributed as dist
-        if dist.is_available() and dist.is_initialized() and dist.get_world_size(process_group) > 1:
-            dist.all_reduce(grad, op=dist.ReduceOp.SUM, group=process_group)
-            grad /= dist.get_world_size(process_group)
+        from .sharding import allreduce_mean_
+        allreduce_mean_(grad, process_group)
         if apply:
             eng.train_apply(grad, lr, betas, eps, weight_decay)
         return loss, grad

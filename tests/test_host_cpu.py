@@ -152,3 +152,36 @@ def test_gather_token_rows_gloo_world2():
     want = np.concatenate([[1000 * t + s for s in range(c)] for t, c in enumerate(counts)])
     np.testing.assert_array_equal(out[:, 0], want)
     assert out.shape == (sum(counts), max_length)
+
+
+def _allreduce_worker(rank, world, port, q):
+    import torch.distributed as dist
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    sh = importlib.import_module("mr-mt3_b200.sharding")
+    g = torch.arange(1000, dtype=torch.float32) * (rank + 1)
+    out = sh.allreduce_mean_(g)
+    assert out is g
+    q.put((rank, g.numpy().copy()))
+    dist.destroy_process_group()
+
+
+def test_gradient_allreduce_mean_gloo_world2():
+    """The fine-tune step's only collective: mean of the flat gradient over the ranks."""
+    import torch.multiprocessing as mp
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = 31500 + os.getpid() % 2000
+    procs = [ctx.Process(target=_allreduce_worker, args=(r, 2, port, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    got = dict(q.get(timeout=120) for _ in range(2))
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    want = np.arange(1000, dtype=np.float32) * 1.5
+    np.testing.assert_array_equal(got[0], want)
+    np.testing.assert_array_equal(got[1], want)
+    sh = importlib.import_module("mr-mt3_b200.sharding")
+    x = torch.ones(4)
+    assert sh.allreduce_mean_(x) is x and float(x.sum()) == 4.0      # not initialised: no-op
