@@ -182,7 +182,11 @@ int mrmt3_memory_block(mrmt3_handle* h, const int64_t* prev_ids, int B, int Lp, 
  * Replaces: one `training_step` of tasks/mt3_net.py / mt3_net_segmem_v2_with_prev.py (forward
  * models/t5.py:182-249 or models/t5_segmem_v2_with_prev.py:155-224 -> CrossEntropyLoss(
  * ignore_index=-100) -> loss.backward() -> AdamW.step()), for the MT3 and V2WithPrev models.
- * No dropout is applied.  Every trainable tensor lives in ONE flat fp32 order
+ * Dropout (the reference's config.dropout_rate at its six sites: stack input, attention weights,
+ * sublayer outputs, FFN inner, final norm output; never in the memory encoder,
+ * models/t5_segmem.py:64) is off until mrmt3_train_set_dropout(p, seed); the masks come from a
+ * counter-based hash of (seed, site, element index), regenerated in the backward pass, a new seed
+ * being derived after every forward.  Every trainable tensor lives in ONE flat fp32 order
  * (the library's packed layouts); the caller owns the flat gradient buffer, so data-parallel
  * training is train_forward + train_backward on every rank, one all-reduce (mean) of the flat
  * buffer, train_apply on every rank.
@@ -199,6 +203,7 @@ int mrmt3_memory_block(mrmt3_handle* h, const int64_t* prev_ids, int B, int Lp, 
  *                        weights used by every other entry point
  *   mrmt3_train_read_master  flat fp32 copy of the current parameters */
 int mrmt3_train_init(mrmt3_handle* h, int64_t* n_params);
+int mrmt3_train_set_dropout(mrmt3_handle* h, float p, uint64_t seed);
 int mrmt3_train_locate(mrmt3_handle* h, const char* name, int64_t* offset, int32_t* rows, int32_t* cols,
                        int32_t* row_mul, int32_t* row_off);
 int mrmt3_train_forward(mrmt3_handle* h, const float* mel, int B, const int64_t* decoder_input_ids,

@@ -59,6 +59,7 @@ _PROTOTYPES = {
                                        _c_int, _c_void_p, _c_int, _c_int, _c_int, _c_void_p, _c_void_p,
                                        _c_void_p]),
     "mrmt3_train_init": (_c_int, [_c_void_p, ctypes.POINTER(_c_i64)]),
+    "mrmt3_train_set_dropout": (_c_int, [_c_void_p, ctypes.c_float, ctypes.c_uint64]),
     "mrmt3_train_locate": (_c_int, [_c_void_p, ctypes.c_char_p, ctypes.POINTER(_c_i64), ctypes.POINTER(ctypes.c_int32),
                                     ctypes.POINTER(ctypes.c_int32), ctypes.POINTER(ctypes.c_int32),
                                     ctypes.POINTER(ctypes.c_int32)]),
@@ -318,6 +319,11 @@ class Engine:
             self._check(self._lib.mrmt3_train_init(self._h, ctypes.byref(n)))
         self._n_params = int(n.value)
         return self._n_params
+
+    def train_set_dropout(self, p, seed=0):
+        """Dropout probability (reference config.dropout_rate) and mask seed of the next forward."""
+        getattr(self, "_n_params", None) or self.train_init()
+        self._check(self._lib.mrmt3_train_set_dropout(self._h, float(p), int(seed) & 0xFFFFFFFFFFFFFFFF))
 
     def train_locate(self, name):
         """(offset, rows, cols, row_mul, row_off) of a reference state-dict tensor in the flat order."""

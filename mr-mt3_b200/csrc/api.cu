@@ -27,6 +27,8 @@ Status api_transcribe_host(mrmt3_handle* h, const float* audio_host, long long n
 Status train_init(mrmt3_handle* h);
 size_t train_param_count(mrmt3_handle* h);
 Status train_read_master(mrmt3_handle* h, float* out, cudaStream_t s);
+Status train_set_dropout(mrmt3_handle* h, float p, unsigned long long seed);
+Status train_set_dropout_sites(mrmt3_handle* h, int mask);
 Status train_locate(mrmt3_handle* h, const std::string& name, long long* offset, int* rows, int* cols, int* row_mul,
                     int* row_off);
 Status train_forward(mrmt3_handle* h, const float* mel, int B, const long long* dec_ids, const long long* labels, int L,
@@ -120,6 +122,7 @@ int mrmt3_set_option(mrmt3_handle* h, const char* key, int value) {
     if (k == "group_lanes") h->group_lanes = value;
     else if (k == "use_graphs") h->use_graphs = value != 0;
     else if (k == "group_serial") h->group_serial = value != 0;
+    else if (k == "train_dropout_sites") return finish(h, train_set_dropout_sites(h, value));
     else if (k == "attn_variant" || k == "attn_ring_stages" || k == "attn_ring_ctas" || k == "attn_ring_quartets") {
         // the kernel choice is baked into the captured step graphs
         cudaSetDevice(h->device);
@@ -268,6 +271,12 @@ int mrmt3_train_init(mrmt3_handle* h, int64_t* n_params) {
     Status st = train_init(h);
     if (st.ok() && n_params) *n_params = (int64_t)train_param_count(h);
     return finish(h, st);
+    END_GUARD(h)
+}
+
+int mrmt3_train_set_dropout(mrmt3_handle* h, float p, uint64_t seed) {
+    GUARD(h)
+    return finish(h, train_set_dropout(h, p, (unsigned long long)seed));
     END_GUARD(h)
 }
 

@@ -157,6 +157,15 @@ __global__ void __launch_bounds__(128)
             float p3 = exp2f((s[ni][3] - m_use[1]) * kLog2e);
             l_run[0] += p0 + p1;
             l_run[1] += p2 + p3;
+            if (p.drop.on()) {  // dropout(softmax): the normaliser above sums the undropped weights
+                const unsigned long long r0i = ((unsigned long long)(b * kHeads + head) * p.Tq + row_lo) * p.Tk;
+                const unsigned long long r1i = r0i + 8ull * p.Tk;
+                const int key = kt * kAttnBK + ni * 8 + (lane & 3) * 2;
+                p0 *= drop_factor(p.drop, r0i + key);
+                p1 *= drop_factor(p.drop, r0i + key + 1);
+                p2 *= drop_factor(p.drop, r1i + key);
+                p3 *= drop_factor(p.drop, r1i + key + 1);
+            }
             // C-fragment of two adjacent n-blocks == A-fragment of one k16 step
             pf[ni >> 1][(ni & 1) * 2 + 0] = pack_bf16(p0, p1);
             pf[ni >> 1][(ni & 1) * 2 + 1] = pack_bf16(p2, p3);

@@ -27,6 +27,7 @@ struct AttnFullParams {
     int causal;         // key j visible to query i iff j <= i + causal_offset
     int causal_offset;
     float* lse2;        // optional (batch, heads, Tq): m*log2(e) + log2(l), saved for the backward pass
+    DropSpec drop;      // training only: dropout on the attention weights, index ((b*H + h)*Tq + q)*Tk + k
 };
 Status launch_attn_full(const AttnFullParams& p, int batch, cudaStream_t stream);
 

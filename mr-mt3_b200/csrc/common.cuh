@@ -121,6 +121,32 @@ __device__ __forceinline__ float gelu_new(float a) {
     return 0.5f * a * (1.0f + tanhf(inner));
 }
 
+// ---- dropout (fine-tune step) -------------------------------------------------------------------
+// Counter-based: element `index` of tensor `tid` is kept iff hash(seed, tid, index) >= p * 2^32, so
+// the backward regenerates every mask instead of storing it, and the CPU oracle can mirror it
+// (oracle/mt3_oracle.py:dropout_keep).  `scale` = 1 / (1 - p); p == 0 disables everything.
+struct DropSpec {
+    unsigned long long seed;  // already mixed with the tensor id
+    unsigned int threshold;   // p * 2^32
+    float scale;
+    __host__ __device__ bool on() const { return threshold != 0u; }
+};
+__host__ __device__ __forceinline__ unsigned long long drop_mix_tid(unsigned long long seed, unsigned int tid) {
+    return seed ^ ((unsigned long long)tid * 0x9E3779B97F4A7C15ull);
+}
+__host__ __device__ __forceinline__ bool drop_keep(const DropSpec& d, unsigned long long index) {
+    unsigned long long x = d.seed + index * 0xD1B54A32D192ED03ull;
+    x ^= x >> 32;
+    x *= 0xD6E8FEB86659FD93ull;
+    x ^= x >> 32;
+    x *= 0xD6E8FEB86659FD93ull;
+    x ^= x >> 32;
+    return (unsigned int)x >= d.threshold;
+}
+__host__ __device__ __forceinline__ float drop_factor(const DropSpec& d, unsigned long long index) {
+    return d.on() ? (drop_keep(d, index) ? d.scale : 0.f) : 1.f;
+}
+
 // streaming 16 B load that does not allocate in L1 (KV cache / one-shot reads)
 __device__ __forceinline__ uint4 ld_stream16(const void* p) {
     uint4 r;

@@ -58,12 +58,43 @@ struct TrainState {
     bf16 *mem_emb16 = nullptr, *mem_n_final = nullptr, *kv_in = nullptr;  // kv_in: (B, T_k, d) rows fed to the K/V projection
     const long long* prev_ids = nullptr;
     DeviceBuffer prev_copy;
+    // dropout (reference config dropout_rate, 0 in the memory encoder): p, the seed of the next
+    // forward and the seed the last forward used (the backward regenerates its masks from it)
+    float drop_p = 0.f;
+    unsigned long long drop_seed = 0, drop_seed_used = 0;
+    int drop_sites = 0x1ff;  // bit i = site i enabled (tests isolate one site at a time)
     float* row_loss = nullptr;
     const long long* dec_ids = nullptr;
     DeviceBuffer ids_copy;
 };
 
 static TrainState* state(mrmt3_handle* h) { return reinterpret_cast<TrainState*>(h->train); }
+
+// dropout sites; stack 0 encoder, 1 decoder, 2 memory encoder (never dropped: models/t5_segmem.py:64)
+enum { kSiteInput = 1, kSiteSelfProbs = 2, kSiteSelfOut = 3, kSiteFfnInner = 4, kSiteFfnOut = 5, kSiteFinal = 6,
+       kSiteCrossProbs = 7, kSiteCrossOut = 8 };
+static DropSpec drop_spec(const TrainState* t, unsigned long long seed, int stack, int layer, int site) {
+    if (t->drop_p <= 0.f || stack == 2 || !((t->drop_sites >> site) & 1)) return DropSpec{0ull, 0u, 1.f};
+    const double th = (double)t->drop_p * 4294967296.0;
+    return DropSpec{drop_mix_tid(seed, (unsigned)((stack << 16) | (layer << 8) | site)),
+                    (unsigned int)(th > 4294967295.0 ? 4294967295.0 : th), 1.f / (1.f - t->drop_p)};
+}
+
+Status train_set_dropout_sites(mrmt3_handle* h, int mask) {
+    TrainState* t = state(h);
+    if (!t) return Error(5, "mrmt3_train_init first");
+    t->drop_sites = mask;
+    return OkStatus();
+}
+
+Status train_set_dropout(mrmt3_handle* h, float p, unsigned long long seed) {
+    TrainState* t = state(h);
+    if (!t) return Error(5, "mrmt3_train_init first");
+    if (!(p >= 0.f && p < 1.f)) return Error(2, "dropout probability must be in [0, 1)");
+    t->drop_p = p;
+    t->drop_seed = seed;
+    return OkStatus();
+}
 
 void train_destroy(mrmt3_handle* h) {
     TrainState* t = state(h);
@@ -259,6 +290,10 @@ Status train_forward(mrmt3_handle* h, const float* mel, int B, const long long* 
     MRMT3_TRY(t->stash.reserve(stash_bytes(n_enc, n_dec, with_mem ? h->cfg.n_mem_layers : 0, Me, Md, Mm, B, L, Lp)));
     t->Lp = Lp;
     t->n_mem = n_mem;
+    const unsigned long long seed = t->drop_seed;
+    t->drop_seed_used = seed;
+    t->drop_seed = seed * 6364136223846793005ull + 1442695040888963407ull;  // the next step draws new masks
+    auto mk = [&](int stack, int layer, int site) { return drop_spec(t, seed, stack, layer, site); };
     Bump bp{reinterpret_cast<char*>(t->stash.p), 0, t->stash.cap};
     t->B = B;
     t->L = L;
@@ -273,7 +308,7 @@ Status train_forward(mrmt3_handle* h, const float* mel, int B, const long long* 
     RUN(h, launch_gemm_tc(*h->tma, t->mel16, kDModel, Me, id, h->proj, kDModel, (int)Me, kDModel, kDModel,
                           EpiPosAdd{H, kDModel, h->pe, kSegFrames, 0}, s));
     auto attn_fwd = [&](const bf16* Q, long qb, int qr, const bf16* K, const bf16* V, long kb, long kh, int kr, bf16* O,
-                        int Tq, int Tk, int causal, float* lse, int nb) -> Status {
+                        int Tq, int Tk, int causal, float* lse, int nb, DropSpec drop) -> Status {
         AttnFullParams ap{};
         ap.Q = Q; ap.q_batch_stride = qb; ap.q_head_stride = kDKV; ap.q_row_stride = qr;
         ap.K = K; ap.V = V;
@@ -281,15 +316,23 @@ Status train_forward(mrmt3_handle* h, const float* mel, int B, const long long* 
         ap.k_head_stride = ap.v_head_stride = kh;
         ap.k_row_stride = ap.v_row_stride = kr;
         ap.O = O; ap.o_batch_stride = (long)Tq * kInner; ap.o_head_stride = kDKV; ap.o_row_stride = kInner;
-        ap.Tq = Tq; ap.Tk = Tk; ap.causal = causal; ap.causal_offset = 0; ap.lse2 = lse;
+        ap.Tq = Tq; ap.Tk = Tk; ap.causal = causal; ap.causal_offset = 0; ap.lse2 = lse; ap.drop = drop;
         RUN(h, launch_attn_full(ap, nb, s));
+        return OkStatus();
+    };
+    // H += dropout(A . W^T)   (sublayer output)
+    auto out_proj = [&](const bf16* A, int K, const bf16* W, float* Hres, size_t M, DropSpec drop) -> Status {
+        if (drop.on())
+            RUN(h, launch_gemm_tc(*h->tma, A, K, M, id, W, K, (int)M, kDModel, K, EpiResidualDrop{Hres, kDModel, drop}, s));
+        else
+            RUN(h, launch_gemm_tc(*h->tma, A, K, M, id, W, K, (int)M, kDModel, K, EpiResidual{Hres, kDModel}, s));
         return OkStatus();
     };
     auto snapshot = [&](float* dst, const float* src, size_t n) -> Status {
         MRMT3_CUDA_TRY(cudaMemcpyAsync(dst, src, n * 4, cudaMemcpyDeviceToDevice, s));
         return OkStatus();
     };
-    auto ffn_fwd = [&](const LayerW& Lw, LayerStash& st, float* Hres, size_t M) -> Status {
+    auto ffn_fwd = [&](const LayerW& Lw, LayerStash& st, float* Hres, size_t M, int stack, int li) -> Status {
         st.h_mid = bp.take<float>(M * kDModel);
         MRMT3_TRY(snapshot(st.h_mid, Hres, M * kDModel));
         st.n2 = bp.take<bf16>(M * kDModel);
@@ -298,11 +341,11 @@ Status train_forward(mrmt3_handle* h, const float* mel, int B, const long long* 
         RUN(h, launch_rmsnorm(Hres, Lw.ln_ff, eps, st.n2, nullptr, (int)M, nullptr, 1, s));
         RUN(h, launch_gemm_tc(*h->tma, st.n2, kDModel, M, id, Lw.wi, kDModel, (int)M, 2 * kDFF, kDModel,
                               EpiStoreBf16{st.raw, 2 * kDFF}, s));
-        RUN(h, launch_gated_gelu_fwd(st.raw, st.ff, M, s));
-        RUN(h, launch_gemm_tc(*h->tma, st.ff, kDFF, M, id, Lw.wff, kDFF, (int)M, kDModel, kDFF, EpiResidual{Hres, kDModel}, s));
+        RUN(h, launch_gated_gelu_fwd(st.raw, st.ff, M, mk(stack, li, kSiteFfnInner), s));
+        MRMT3_TRY(out_proj(st.ff, kDFF, Lw.wff, Hres, M, mk(stack, li, kSiteFfnOut)));
         return OkStatus();
     };
-    auto self_fwd = [&](const LayerW& Lw, LayerStash& st, float* Hres, size_t M, int T, int causal) -> Status {
+    auto self_fwd = [&](const LayerW& Lw, LayerStash& st, float* Hres, size_t M, int T, int causal, int stack, int li) -> Status {
         const int nb = (int)(M / T);
         st.h_in = bp.take<float>(M * kDModel);
         MRMT3_TRY(snapshot(st.h_in, Hres, M * kDModel));
@@ -314,18 +357,20 @@ Status train_forward(mrmt3_handle* h, const float* mel, int B, const long long* 
         RUN(h, launch_gemm_tc(*h->tma, st.n1, kDModel, M, id, Lw.wqkv, kDModel, (int)M, 3 * kInner, kDModel,
                               EpiStoreBf16{st.qkv, 3 * kInner}, s));
         MRMT3_TRY(attn_fwd(st.qkv, (long)T * 3 * kInner, 3 * kInner, st.qkv + kInner, st.qkv + 2 * kInner,
-                           (long)T * 3 * kInner, kDKV, 3 * kInner, st.ctx, T, T, causal, st.lse, nb));
-        RUN(h, launch_gemm_tc(*h->tma, st.ctx, kInner, M, id, Lw.wo, kInner, (int)M, kDModel, kInner, EpiResidual{Hres, kDModel}, s));
+                           (long)T * 3 * kInner, kDKV, 3 * kInner, st.ctx, T, T, causal, st.lse, nb, mk(stack, li, kSiteSelfProbs)));
+        MRMT3_TRY(out_proj(st.ctx, kInner, Lw.wo, Hres, M, mk(stack, li, kSiteSelfOut)));
         return OkStatus();
     };
+    RUN(h, launch_dropout_f32(H, Me * kDModel, mk(0, 0, kSiteInput), s));
     t->enc_st.assign(n_enc, LayerStash{});
     for (int li = 0; li < n_enc; ++li) {
-        MRMT3_TRY(self_fwd(h->enc.layers[li], t->enc_st[li], H, Me, kSegFrames, 0));
-        MRMT3_TRY(ffn_fwd(h->enc.layers[li], t->enc_st[li], H, Me));
+        MRMT3_TRY(self_fwd(h->enc.layers[li], t->enc_st[li], H, Me, kSegFrames, 0, 0, li));
+        MRMT3_TRY(ffn_fwd(h->enc.layers[li], t->enc_st[li], H, Me, 0, li));
     }
     t->enc_h_final = H;
     t->enc_n_final = bp.take<bf16>(Me * kDModel);
     RUN(h, launch_rmsnorm(H, h->enc.final_ln, eps, t->enc_n_final, nullptr, (int)Me, nullptr, 1, s));
+    RUN(h, launch_dropout_bf16(t->enc_n_final, Me * kDModel, mk(0, 0, kSiteFinal), s));
 
     // ---- MR-MT3 memory block (models/t5_segmem_v2_with_prev.py:119-128): Emb[prev] -> segmem_proj
     //      (+PE) -> memory encoder over all Lp positions -> final norm -> first n_mem rows ----
@@ -340,8 +385,8 @@ Status train_forward(mrmt3_handle* h, const float* mel, int B, const long long* 
                               EpiPosAdd{Hm, kDModel, h->pe, Lp, 0}, s));
         t->mem_st.assign(h->cfg.n_mem_layers, LayerStash{});
         for (int li = 0; li < h->cfg.n_mem_layers; ++li) {
-            MRMT3_TRY(self_fwd(h->mem.layers[li], t->mem_st[li], Hm, Mm, Lp, 0));
-            MRMT3_TRY(ffn_fwd(h->mem.layers[li], t->mem_st[li], Hm, Mm));
+            MRMT3_TRY(self_fwd(h->mem.layers[li], t->mem_st[li], Hm, Mm, Lp, 0, 2, li));
+            MRMT3_TRY(ffn_fwd(h->mem.layers[li], t->mem_st[li], Hm, Mm, 2, li));
         }
         t->mem_h_final = Hm;
         t->mem_n_final = bp.take<bf16>(Mm * kDModel);
@@ -363,12 +408,13 @@ Status train_forward(mrmt3_handle* h, const float* mel, int B, const long long* 
     // ---- decoder, teacher forced (reference models/t5.py:99-180) ----
     float* Hd = bp.take<float>(Md * kDModel);
     RUN(h, launch_embed_tokens(t->dec_ids, h->emb, h->pe, Hd, B, L, 0, s));
+    RUN(h, launch_dropout_f32(Hd, Md * kDModel, mk(1, 0, kSiteInput), s));
     t->dec_st.assign(n_dec, LayerStash{});
     const size_t lane_sz = (size_t)n_dec * 2 * kHeads * h->tk_cap * kDKV;
     for (int li = 0; li < n_dec; ++li) {
         const LayerW& Lw = h->dec.layers[li];
         LayerStash& st = t->dec_st[li];
-        MRMT3_TRY(self_fwd(Lw, st, Hd, Md, L, 1));
+        MRMT3_TRY(self_fwd(Lw, st, Hd, Md, L, 1, 1, li));
         st.h_mid2 = bp.take<float>(Md * kDModel);
         MRMT3_TRY(snapshot(st.h_mid2, Hd, Md * kDModel));
         st.nc = bp.take<bf16>(Md * kDModel);
@@ -380,13 +426,14 @@ Status train_forward(mrmt3_handle* h, const float* mel, int B, const long long* 
                               EpiStoreBf16{st.qc, kInner}, s));
         const bf16* kbase = h->cross_cache.as<bf16>() + (size_t)li * 2 * kHeads * h->tk_cap * kDKV;
         MRMT3_TRY(attn_fwd(st.qc, (long)L * kInner, kInner, kbase, kbase + (size_t)kHeads * h->tk_cap * kDKV, (long)lane_sz,
-                           (long)h->tk_cap * kDKV, kDKV, st.ctx_c, L, tk, 0, st.lse_c, B));
-        RUN(h, launch_gemm_tc(*h->tma, st.ctx_c, kInner, Md, id, Lw.co, kInner, (int)Md, kDModel, kInner, EpiResidual{Hd, kDModel}, s));
-        MRMT3_TRY(ffn_fwd(Lw, st, Hd, Md));
+                           (long)h->tk_cap * kDKV, kDKV, st.ctx_c, L, tk, 0, st.lse_c, B, mk(1, li, kSiteCrossProbs)));
+        MRMT3_TRY(out_proj(st.ctx_c, kInner, Lw.co, Hd, Md, mk(1, li, kSiteCrossOut)));
+        MRMT3_TRY(ffn_fwd(Lw, st, Hd, Md, 1, li));
     }
     t->dec_h_final = Hd;
     t->dec_n_final = bp.take<bf16>(Md * kDModel);
     RUN(h, launch_rmsnorm(Hd, h->dec.final_ln, eps, t->dec_n_final, nullptr, (int)Md, nullptr, 1, s));
+    RUN(h, launch_dropout_bf16(t->dec_n_final, Md * kDModel, mk(1, 0, kSiteFinal), s));
     RUN(h, launch_gemm_tc(*h->tma, t->dec_n_final, kDModel, Md, id, h->lm_head, kDModel, (int)Md, kVocab, kDModel,
                           EpiStoreF32{logits_out, kVocab}, s));
 
@@ -425,6 +472,8 @@ Status train_backward(mrmt3_handle* h, float* grad, const float* dlogits_f32, cu
     const float eps = h->cfg.ln_eps;
     const ARowMap id{nullptr, 1};
     MRMT3_CUDA_TRY(cudaMemsetAsync(grad, 0, t->n_total * 4, s));
+    const unsigned long long seed = t->drop_seed_used;
+    auto mk = [&](int stack, int layer, int site) { return drop_spec(t, seed, stack, layer, site); };
 
     // W^T copies for the dgrad GEMMs
     // scratch
@@ -505,8 +554,12 @@ Status train_backward(mrmt3_handle* h, float* grad, const float* dlogits_f32, cu
         toc();
         return OkStatus();
     };
-    // dHb always mirrors dH: every update of dH goes through norm_bwd, which writes both
-    auto cast_dH = [&](size_t) -> Status { return OkStatus(); };
+    // dHb mirrors dH (every update of dH goes through norm_bwd, which writes both); a sublayer
+    // whose output was dropped back-propagates dH * mask / (1 - p) instead
+    auto cast_dH = [&](size_t M, DropSpec drop) -> Status {
+        if (drop.on()) RUN(h, launch_dropout_cast(dH, dHb, M * kDModel, drop, s));
+        return OkStatus();
+    };
     auto norm_bwd = [&](const float* x, const float* g, const bf16* dy, size_t M, float* dg) -> Status {
         tic("rmsnorm bwd");
         RUN(h, launch_rmsnorm_bwd(x, g, eps, dy, (int)M, dH, dHb, dg, s));
@@ -515,8 +568,9 @@ Status train_backward(mrmt3_handle* h, float* grad, const float* dlogits_f32, cu
     };
     auto attn_bwd = [&](const bf16* Q, long qb, int qr, const bf16* K, const bf16* V, long kb, long kh, int kr,
                         const bf16* O, const bf16* dO, bf16* dQ, bf16* dK, bf16* dV, long dkb, long dkh, int dkr,
-                        const float* lse, int Tq, int Tk, int causal) -> Status {
+                        const float* lse, int Tq, int Tk, int causal, DropSpec drop) -> Status {
         AttnBwdParams ap{};
+        ap.drop = drop;
         ap.Q = Q; ap.K = K; ap.V = V; ap.O = O; ap.dO = dO; ap.dQ = dQ; ap.dK = dK; ap.dV = dV;
         ap.q_batch_stride = qb; ap.q_head_stride = kDKV; ap.q_row_stride = qr;
         ap.k_batch_stride = ap.v_batch_stride = kb;
@@ -531,25 +585,27 @@ Status train_backward(mrmt3_handle* h, float* grad, const float* dlogits_f32, cu
         h->launches += 1;
         return OkStatus();
     };
-    auto ffn_bwd = [&](const LayerSlots& ls, const LayerW& Lw, const LayerStash& st, size_t M) -> Status {
-        MRMT3_TRY(cast_dH(M));
+    auto ffn_bwd = [&](const LayerSlots& ls, const LayerW& Lw, const LayerStash& st, size_t M, int stack, int li) -> Status {
+        MRMT3_TRY(cast_dH(M, mk(stack, li, kSiteFfnOut)));
         MRMT3_TRY(dgrad(dHb, kDModel, ls.wff, dff, M));
         MRMT3_TRY(wgrad(dHb, kDModel, kDModel, st.ff, kDFF, kDFF, G(ls.wff), M));
         tic("gated gelu bwd");
-        RUN(h, launch_gated_gelu_bwd(st.raw, dff, draw, M, s));
+        RUN(h, launch_gated_gelu_bwd(st.raw, dff, draw, M, mk(stack, li, kSiteFfnInner), s));
         toc();
         MRMT3_TRY(dgrad(draw, 2 * kDFF, ls.wi, dn, M));
         MRMT3_TRY(wgrad(draw, 2 * kDFF, 2 * kDFF, st.n2, kDModel, kDModel, G(ls.wi), M));
         MRMT3_TRY(norm_bwd(st.h_mid, Lw.ln_ff, dn, M, G(ls.ln_ff)));
         return OkStatus();
     };
-    auto self_bwd = [&](const LayerSlots& ls, const LayerW& Lw, const LayerStash& st, size_t M, int T, int causal) -> Status {
-        MRMT3_TRY(cast_dH(M));
+    auto self_bwd = [&](const LayerSlots& ls, const LayerW& Lw, const LayerStash& st, size_t M, int T, int causal,
+                        int stack, int li) -> Status {
+        MRMT3_TRY(cast_dH(M, mk(stack, li, kSiteSelfOut)));
         MRMT3_TRY(dgrad(dHb, kDModel, ls.wo, dctx, M));
         MRMT3_TRY(wgrad(dHb, kDModel, kDModel, st.ctx, kInner, kInner, G(ls.wo), M));
         const long tb = (long)T * 3 * kInner;
         MRMT3_TRY(attn_bwd(st.qkv, tb, 3 * kInner, st.qkv + kInner, st.qkv + 2 * kInner, tb, kDKV, 3 * kInner, st.ctx, dctx,
-                           dqkv, dqkv + kInner, dqkv + 2 * kInner, tb, kDKV, 3 * kInner, st.lse, T, T, causal));
+                           dqkv, dqkv + kInner, dqkv + 2 * kInner, tb, kDKV, 3 * kInner, st.lse, T, T, causal,
+                           mk(stack, li, kSiteSelfProbs)));
         MRMT3_TRY(dgrad(dqkv, 3 * kInner, ls.wqkv, dn, M));
         MRMT3_TRY(wgrad(dqkv, 3 * kInner, 3 * kInner, st.n1, kDModel, kDModel, G(ls.wqkv), M));
         MRMT3_TRY(norm_bwd(st.h_in, Lw.ln_self, dn, M, G(ls.ln_self)));
@@ -560,6 +616,7 @@ Status train_backward(mrmt3_handle* h, float* grad, const float* dlogits_f32, cu
     MRMT3_CUDA_TRY(cudaMemsetAsync(dH, 0, Md * kDModel * 4, s));
     MRMT3_TRY(dgrad(t->dlogits, kVocab, t->lm_head, dn, Md));
     MRMT3_TRY(wgrad(t->dlogits, kVocab, kVocab, t->dec_n_final, kDModel, kDModel, G(t->lm_head), Md));
+    RUN(h, launch_dropout_bf16(dn, Md * kDModel, mk(1, 0, kSiteFinal), s));
     MRMT3_TRY(norm_bwd(t->dec_h_final, h->dec.final_ln, dn, Md, G(t->dec_final)));
 
     // ---- decoder layers, last to first ----
@@ -569,9 +626,9 @@ Status train_backward(mrmt3_handle* h, float* grad, const float* dlogits_f32, cu
         const LayerW& Lw = h->dec.layers[li];
         const LayerSlots& ls = t->dec[li];
         const LayerStash& st = t->dec_st[li];
-        MRMT3_TRY(ffn_bwd(ls, Lw, st, Md));
+        MRMT3_TRY(ffn_bwd(ls, Lw, st, Md, 1, li));
         // cross-attention sublayer
-        MRMT3_TRY(cast_dH(Md));
+        MRMT3_TRY(cast_dH(Md, mk(1, li, kSiteCrossOut)));
         MRMT3_TRY(dgrad(dHb, kDModel, ls.co, dctx, Md));
         MRMT3_TRY(wgrad(dHb, kDModel, kDModel, st.ctx_c, kInner, kInner, G(ls.co), Md));
         const bf16* kbase = h->cross_cache.as<bf16>() + (size_t)li * 2 * kHeads * h->tk_cap * kDKV;
@@ -579,12 +636,13 @@ Status train_backward(mrmt3_handle* h, float* grad, const float* dlogits_f32, cu
         bf16* dk_l = dkv + (size_t)li * 2 * kInner;
         MRMT3_TRY(attn_bwd(st.qc, (long)L * kInner, kInner, kbase, kbase + (size_t)kHeads * h->tk_cap * kDKV, (long)lane_sz,
                            (long)h->tk_cap * kDKV, kDKV, st.ctx_c, dctx, dqc, dk_l, dk_l + kInner,
-                           (long)tk * (long)kvN, kDKV, (int)kvN, st.lse_c, L, tk, 0));
+                           (long)tk * (long)kvN, kDKV, (int)kvN, st.lse_c, L, tk, 0, mk(1, li, kSiteCrossProbs)));
         MRMT3_TRY(dgrad(dqc, kInner, ls.cq, dn, Md));
         MRMT3_TRY(wgrad(dqc, kInner, kInner, st.nc, kDModel, kDModel, G(ls.cq), Md));
         MRMT3_TRY(norm_bwd(st.h_mid2, Lw.ln_cross, dn, Md, G(ls.ln_cross)));
-        MRMT3_TRY(self_bwd(ls, Lw, st, Md, L, 1));
+        MRMT3_TRY(self_bwd(ls, Lw, st, Md, L, 1, 1, li));
     }
+    RUN(h, launch_dropout_f32(dH, Md * kDModel, mk(1, 0, kSiteInput), s));
     tic("embedding bwd");
     RUN(h, launch_embed_bwd(t->dec_ids, dH, G(t->emb), (int)Md, s));
     toc();
@@ -606,11 +664,11 @@ Status train_backward(mrmt3_handle* h, float* grad, const float* dlogits_f32, cu
         MRMT3_CUDA_TRY(cudaMemcpy2DAsync(dsplit, (size_t)kSegFrames * kDModel * 2, dn, (size_t)tk * kDModel * 2,
                                          (size_t)kSegFrames * kDModel * 2, B, cudaMemcpyDeviceToDevice, s));
         for (int li = h->cfg.n_mem_layers - 1; li >= 0; --li) {
-            MRMT3_TRY(ffn_bwd(t->mem[li], h->mem.layers[li], t->mem_st[li], Mm));
-            MRMT3_TRY(self_bwd(t->mem[li], h->mem.layers[li], t->mem_st[li], Mm, Lp, 0));
+            MRMT3_TRY(ffn_bwd(t->mem[li], h->mem.layers[li], t->mem_st[li], Mm, 2, li));
+            MRMT3_TRY(self_bwd(t->mem[li], h->mem.layers[li], t->mem_st[li], Mm, Lp, 0, 2, li));
         }
         // stack input = segmem_proj(Emb[prev]) + PE
-        MRMT3_TRY(cast_dH(Mm));
+        MRMT3_TRY(cast_dH(Mm, mk(2, 0, kSiteInput)));
         MRMT3_TRY(wgrad(dHb, kDModel, kDModel, t->mem_emb16, kDModel, kDModel, G(t->segmem_proj), Mm));
         const ParamSlot& sp = t->slots[t->segmem_proj];
         RUN(h, launch_gemm_tc(*h->tma, dHb, kDModel, Mm, id, sp.wt, kDModel, (int)Mm, kDModel, kDModel,
@@ -623,14 +681,15 @@ Status train_backward(mrmt3_handle* h, float* grad, const float* dlogits_f32, cu
     }
 
     // ---- encoder ----
+    RUN(h, launch_dropout_bf16(dsplit, Me * kDModel, mk(0, 0, kSiteFinal), s));
     MRMT3_CUDA_TRY(cudaMemsetAsync(dH, 0, Me * kDModel * 4, s));
     MRMT3_TRY(norm_bwd(t->enc_h_final, h->enc.final_ln, dsplit, Me, G(t->enc_final)));
     for (int li = n_enc - 1; li >= 0; --li) {
-        MRMT3_TRY(ffn_bwd(t->enc[li], h->enc.layers[li], t->enc_st[li], Me));
-        MRMT3_TRY(self_bwd(t->enc[li], h->enc.layers[li], t->enc_st[li], Me, kSegFrames, 0));
+        MRMT3_TRY(ffn_bwd(t->enc[li], h->enc.layers[li], t->enc_st[li], Me, 0, li));
+        MRMT3_TRY(self_bwd(t->enc[li], h->enc.layers[li], t->enc_st[li], Me, kSegFrames, 0, 0, li));
     }
-    // proj: h0 = mel . Wproj^T + PE
-    MRMT3_TRY(cast_dH(Me));
+    // proj: h0 = dropout(mel . Wproj^T + PE)
+    MRMT3_TRY(cast_dH(Me, mk(0, 0, kSiteInput)));
     MRMT3_TRY(wgrad(dHb, kDModel, kDModel, t->mel16, kMels, kMels, G(t->proj), Me));
     if (prof) {
         MRMT3_CUDA_TRY(cudaStreamSynchronize(s));

@@ -10,8 +10,13 @@ Status launch_xent(const float* logits, const long long* labels, int rows, int V
                    float* row_loss, bf16* dlogits, cudaStream_t s);
 Status launch_rmsnorm_bwd(const float* x, const float* g, float eps, const bf16* dy, int rows, float* dres,
                           bf16* dres_bf16, float* dg, cudaStream_t s);
-Status launch_gated_gelu_fwd(const bf16* raw, bf16* ff, size_t rows, cudaStream_t s);
-Status launch_gated_gelu_bwd(const bf16* raw, const bf16* dff, bf16* draw, size_t rows, cudaStream_t s);
+Status launch_gated_gelu_fwd(const bf16* raw, bf16* ff, size_t rows, DropSpec drop, cudaStream_t s);
+Status launch_gated_gelu_bwd(const bf16* raw, const bf16* dff, bf16* draw, size_t rows, DropSpec drop, cudaStream_t s);
+// x[i] *= keep(i) / (1 - p)   (dropout forward on a value, or backward on its gradient)
+Status launch_dropout_f32(float* x, size_t n, DropSpec drop, cudaStream_t s);
+Status launch_dropout_bf16(bf16* x, size_t n, DropSpec drop, cudaStream_t s);
+// out_bf16[i] = bf16(in[i] * keep(i) / (1 - p))
+Status launch_dropout_cast(const float* in, bf16* out, size_t n, DropSpec drop, cudaStream_t s);
 Status launch_transpose_bf16(const bf16* in, int ld_in, bf16* out, int ld_out, int R, int C, cudaStream_t s);
 Status launch_transpose_f32_to_bf16(const float* in, bf16* out, int R, int C, cudaStream_t s);
 Status launch_embed_bwd(const long long* ids, const float* dH, float* dEmb, int rows, cudaStream_t s);
@@ -39,6 +44,22 @@ struct AttnBwdParams {
     const float* lse2;
     float* delta;
     int Tq, Tk, causal, causal_offset;
+    DropSpec drop;  // the forward's attention-weight dropout
+};
+
+// H (fp32) += dropout(acc): the sublayer-output dropout of the training forward, index row*ld + col
+struct EpiResidualDrop {
+    float* H;
+    int ldh;
+    DropSpec drop;
+    __device__ __forceinline__ void operator()(int row, int col, float v0, float v1) const {
+        const unsigned long long i = (unsigned long long)row * ldh + col;
+        float2* p = reinterpret_cast<float2*>(H + (size_t)row * ldh + col);
+        float2 h = *p;
+        h.x += v0 * drop_factor(drop, i);
+        h.y += v1 * drop_factor(drop, i + 1);
+        *p = h;
+    }
 };
 Status launch_attn_bwd(const AttnBwdParams& p, int batch, cudaStream_t s);
 

@@ -134,21 +134,21 @@ Status launch_rmsnorm_bwd(const float* x, const float* g, float eps, const bf16*
 
 // ---------------------------------------------------------------------------------------------
 // gated GELU from the raw ffn-in output (columns interleaved: 2j -> wi_0, 2j+1 -> wi_1)
-__global__ void gated_gelu_fwd_kernel(const uint32_t* __restrict__ raw, bf16* __restrict__ ff, size_t n) {
+__global__ void gated_gelu_fwd_kernel(const uint32_t* __restrict__ raw, bf16* __restrict__ ff, size_t n, DropSpec drop) {
     size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
     uint32_t v = raw[i];
     float2 ab = __bfloat1622float2(*reinterpret_cast<bf162*>(&v));
-    ff[i] = __float2bfloat16(gelu_new(ab.x) * ab.y);
+    ff[i] = __float2bfloat16(gelu_new(ab.x) * ab.y * drop_factor(drop, i));
 }
 
 __global__ void gated_gelu_bwd_kernel(const uint32_t* __restrict__ raw, const bf16* __restrict__ dff,
-                                      uint32_t* __restrict__ draw, size_t n) {
+                                      uint32_t* __restrict__ draw, size_t n, DropSpec drop) {
     size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
     uint32_t v = raw[i];
     float2 ab = __bfloat1622float2(*reinterpret_cast<bf162*>(&v));
-    const float a = ab.x, b = ab.y, d = __bfloat162float(dff[i]);
+    const float a = ab.x, b = ab.y, d = __bfloat162float(dff[i]) * drop_factor(drop, i);
     const float k = 0.7978845608028654f;
     const float t = tanhf(k * (a + 0.044715f * a * a * a));
     const float gelu = 0.5f * a * (1.0f + t);
@@ -156,18 +156,51 @@ __global__ void gated_gelu_bwd_kernel(const uint32_t* __restrict__ raw, const bf
     draw[i] = pack_bf16(d * b * dgelu, d * gelu);
 }
 
-Status launch_gated_gelu_fwd(const bf16* raw, bf16* ff, size_t rows, cudaStream_t s) {
+Status launch_gated_gelu_fwd(const bf16* raw, bf16* ff, size_t rows, DropSpec drop, cudaStream_t s) {
     size_t n = rows * kDFF;
     if (!n) return OkStatus();
-    gated_gelu_fwd_kernel<<<(unsigned)((n + 255) / 256), 256, 0, s>>>(reinterpret_cast<const uint32_t*>(raw), ff, n);
+    gated_gelu_fwd_kernel<<<(unsigned)((n + 255) / 256), 256, 0, s>>>(reinterpret_cast<const uint32_t*>(raw), ff, n, drop);
     MRMT3_CHECK_LAUNCH();
     return OkStatus();
 }
-Status launch_gated_gelu_bwd(const bf16* raw, const bf16* dff, bf16* draw, size_t rows, cudaStream_t s) {
+Status launch_gated_gelu_bwd(const bf16* raw, const bf16* dff, bf16* draw, size_t rows, DropSpec drop, cudaStream_t s) {
     size_t n = rows * kDFF;
     if (!n) return OkStatus();
     gated_gelu_bwd_kernel<<<(unsigned)((n + 255) / 256), 256, 0, s>>>(reinterpret_cast<const uint32_t*>(raw), dff,
-                                                                    reinterpret_cast<uint32_t*>(draw), n);
+                                                                    reinterpret_cast<uint32_t*>(draw), n, drop);
+    MRMT3_CHECK_LAUNCH();
+    return OkStatus();
+}
+
+// ---------------------------------------------------------------------------------------------
+// elementwise dropout (forward on a value, backward on its gradient: the same factor)
+__global__ void dropout_f32_kernel(float* __restrict__ x, size_t n, DropSpec drop) {
+    size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) x[i] *= drop_factor(drop, i);
+}
+__global__ void dropout_bf16_kernel(bf16* __restrict__ x, size_t n, DropSpec drop) {
+    size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) x[i] = __float2bfloat16(__bfloat162float(x[i]) * drop_factor(drop, i));
+}
+__global__ void dropout_cast_kernel(const float* __restrict__ in, bf16* __restrict__ out, size_t n, DropSpec drop) {
+    size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) out[i] = __float2bfloat16(in[i] * drop_factor(drop, i));
+}
+Status launch_dropout_f32(float* x, size_t n, DropSpec drop, cudaStream_t s) {
+    if (!n || !drop.on()) return OkStatus();
+    dropout_f32_kernel<<<(unsigned)((n + 255) / 256), 256, 0, s>>>(x, n, drop);
+    MRMT3_CHECK_LAUNCH();
+    return OkStatus();
+}
+Status launch_dropout_bf16(bf16* x, size_t n, DropSpec drop, cudaStream_t s) {
+    if (!n || !drop.on()) return OkStatus();
+    dropout_bf16_kernel<<<(unsigned)((n + 255) / 256), 256, 0, s>>>(x, n, drop);
+    MRMT3_CHECK_LAUNCH();
+    return OkStatus();
+}
+Status launch_dropout_cast(const float* in, bf16* out, size_t n, DropSpec drop, cudaStream_t s) {
+    if (!n) return OkStatus();
+    dropout_cast_kernel<<<(unsigned)((n + 255) / 256), 256, 0, s>>>(in, out, n, drop);
     MRMT3_CHECK_LAUNCH();
     return OkStatus();
 }
@@ -495,6 +528,7 @@ __global__ void __launch_bounds__(128)
     __syncthreads();  // stage 1 may now be overwritten
 
     const int row_lo = q0 + warp * 16 + (lane >> 2);
+    const unsigned long long bh_row0 = (unsigned long long)(b * kHeads + head) * p.Tq;
     float lse[2], dl[2] = {0.f, 0.f};
 #pragma unroll
     for (int h = 0; h < 2; ++h) {
@@ -532,7 +566,9 @@ __global__ void __launch_bounds__(128)
                     const int key = kt * kBwdT + ni * 8 + (lane & 3) * 2 + (r & 1);
                     const int row = row_lo + ((r >> 1) << 3);
                     const bool ok = key < p.Tk && (!p.causal || key <= row + p.causal_offset);
-                    if (ok) dl[r >> 1] += exp2f(s[ni][r] * kLog2e - lse[r >> 1]) * dp[ni][r];
+                    if (ok)
+                        dl[r >> 1] += exp2f(s[ni][r] * kLog2e - lse[r >> 1]) * dp[ni][r] *
+                                      drop_factor(p.drop, (bh_row0 + row) * p.Tk + key);
                 }
             }
             if (kt == n_kt - 1) {
@@ -553,7 +589,9 @@ __global__ void __launch_bounds__(128)
                     const int row = row_lo + ((r >> 1) << 3);
                     const bool ok = key < p.Tk && (!p.causal || key <= row + p.causal_offset);
                     const float pr = ok ? exp2f(s[ni][r] * kLog2e - lse[r >> 1]) : 0.f;
-                    s[ni][r] = pr * (dp[ni][r] - dl[r >> 1]);  // dS
+                    // dropout sits between softmax and P V: dP = dP' * m / (1 - p)
+                    const float dpe = p.drop.on() ? dp[ni][r] * drop_factor(p.drop, (bh_row0 + row) * p.Tk + key) : dp[ni][r];
+                    s[ni][r] = pr * (dpe - dl[r >> 1]);  // dS
                 }
             }
             uint32_t dsf[4][4];
@@ -620,6 +658,7 @@ __global__ void __launch_bounds__(128)
     __syncthreads();
 
     const int key_lo = k0 + warp * 16 + (lane >> 2);  // this thread's keys: key_lo, key_lo + 8
+    const unsigned long long bh_row0 = (unsigned long long)(b * kHeads + head) * p.Tq;
     float dk[8][4], dv[8][4];
     bwd_zero(dk);
     bwd_zero(dv);
@@ -648,8 +687,9 @@ __global__ void __launch_bounds__(128)
                 const int key = key_lo + ((r >> 1) << 3);
                 const bool ok = row < p.Tq && key < p.Tk && (!p.causal || key <= row + p.causal_offset);
                 const float pr = ok ? exp2f(stt[ni][r] * kLog2e - s_lse[st][qc]) : 0.f;
-                pt[ni][r] = pr;
-                stt[ni][r] = pr * (dpt[ni][r] - s_dl[st][qc]);  // dS^T
+                const float mk = (ok && p.drop.on()) ? drop_factor(p.drop, (bh_row0 + row) * p.Tk + key) : 1.f;
+                pt[ni][r] = pr * mk;                                   // P'^T = dropout(P)^T
+                stt[ni][r] = pr * (dpt[ni][r] * mk - s_dl[st][qc]);    // dS^T
             }
         }
         uint32_t af[4][4];

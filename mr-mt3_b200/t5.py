@@ -154,6 +154,10 @@ class _TrainForward(torch.autograd.Function):
     def forward(ctx, model, inputs, decoder_input_ids, targets_prev, *params):
         eng = model.engine()
         eng.train_init()
+        # training mode applies the reference's dropout (config.dropout_rate, models/t5.py:493) with
+        # a fresh mask seed drawn from torch's generator, so torch.manual_seed makes a run repeatable
+        p = float(getattr(model.config, "dropout_rate", 0.0) or 0.0)
+        eng.train_set_dropout(p, int(torch.randint(0, 2 ** 62, (1,)).item()) if p > 0 else 0)
         ignore = torch.full_like(decoder_input_ids, -100)
         logits, _ = eng.train_forward(inputs, decoder_input_ids, ignore, targets_prev)
         ctx.model = model
@@ -293,15 +297,18 @@ class T5ForConditionalGeneration(nn.Module):
         return logits, enc, None
 
     def train_step(self, inputs, labels, lr=1e-5, betas=(0.9, 0.999), eps=1e-8, weight_decay=0.01,
-                   process_group=None, apply=True, targets_prev=None):
+                   process_group=None, apply=True, targets_prev=None, dropout=None, seed=None):
         """One fine-tune step of reference tasks/mt3_net.py `training_step` + AdamW
         (`train.sh:78`: lr 1e-5): teacher-forced forward, CrossEntropyLoss(ignore_index=-100),
         hand-written backward, mean all-reduce of the flat gradient over `process_group` (or the
         default group when torch.distributed is initialised), AdamW.  Returns (loss, flat grad).
         The engine's weights are updated in place; `sync_parameters_from_engine()` copies them back
-        into this module's parameters.  No dropout is applied."""
+        into this module's parameters.  `dropout` (default: leave the engine's setting, initially 0)
+        is the reference's config.dropout_rate; `seed` fixes this step's masks."""
         eng = self.engine()
         eng.train_init()
+        if dropout is not None:
+            eng.train_set_dropout(dropout, int(torch.randint(0, 2 ** 62, (1,)).item()) if seed is None else seed)
         if targets_prev is not None:
             targets_prev[targets_prev == -100] = 0        # in place, as t5_segmem_v2_with_prev.py:119
         logits, loss = eng.train_forward(inputs, self._shift_right(labels), labels, targets_prev)

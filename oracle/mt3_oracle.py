@@ -172,6 +172,50 @@ def positional_table(n, d_model=D_MODEL, dtype=torch.float64):
     return torch.cat((sinusoid.sin(), sinusoid.cos()), dim=-1).to(dtype)
 
 
+# ---- dropout mirror of the CUDA fine-tune step (csrc/common.cuh:drop_keep) -----------------------
+# The reference uses torch's RNG (nn.Dropout, models/t5.py:493,601,678 and HF T5 layers); masks
+# cannot be matched to it, so parity under dropout is defined with THIS counter-based mask on both
+# sides: same sites, same scaling 1/(1-p), keep iff hash(seed, tensor id, flat index) >= p * 2^32.
+DROP_SITES = {"input": 1, "self_probs": 2, "self_out": 3, "ffn_inner": 4, "ffn_out": 5, "final": 6,
+              "cross_probs": 7, "cross_out": 8}
+DROP_STACKS = {"encoder": 0, "decoder": 1, "segmem_encoder": 2}
+
+
+def dropout_keep(seed, tid, n):
+    """Boolean keep-mask for flat indices 0..n-1 of tensor `tid` (threshold applied by the caller)."""
+    M = np.uint64(0xFFFFFFFFFFFFFFFF)
+    with np.errstate(over="ignore"):
+        s = np.uint64(seed) ^ (np.uint64(tid) * np.uint64(0x9E3779B97F4A7C15) & M)
+        x = s + np.arange(n, dtype=np.uint64) * np.uint64(0xD1B54A32D192ED03)
+        x ^= x >> np.uint64(32)
+        x *= np.uint64(0xD6E8FEB86659FD93)
+        x ^= x >> np.uint64(32)
+        x *= np.uint64(0xD6E8FEB86659FD93)
+        x ^= x >> np.uint64(32)
+    return (x & np.uint64(0xFFFFFFFF)).astype(np.uint32)
+
+
+class Dropout:
+    """drop(x, stack, layer, site) -> x * mask / (1 - p); p = 0 is the identity."""
+
+    def __init__(self, p=0.0, seed=0, site_mask=0x1ff):
+        self.p, self.seed, self.site_mask = float(p), int(seed), int(site_mask)
+        self.threshold = np.uint32(min(int(self.p * 4294967296.0), 0xFFFFFFFF))
+
+    def __call__(self, x, stack, layer, site):
+        if self.p <= 0.0 or stack == "segmem_encoder":      # models/t5_segmem.py:64: dropout 0 in the memory encoder
+            return x
+        if not (self.site_mask >> DROP_SITES[site]) & 1:    # debugging: only some sites
+            return x
+        tid = (DROP_STACKS[stack] << 16) | (layer << 8) | DROP_SITES[site]
+        keep = dropout_keep(self.seed, tid, x.numel()) >= self.threshold
+        mask = torch.from_numpy(keep.astype(np.float64)).reshape(x.shape).to(x.dtype)
+        return x * mask / (1.0 - self.p)
+
+
+NO_DROP = Dropout(0.0)
+
+
 def rms_norm(x, w, eps=1e-6):
     var = x.pow(2).mean(-1, keepdim=True)
     return w * (x * torch.rsqrt(var + eps))
@@ -186,7 +230,7 @@ def _heads(x, n_heads=N_HEADS):
     return x.view(b, t, n_heads, -1).transpose(1, 2)          # (b, h, t, d_kv)
 
 
-def attention(xq, xkv, sd, prefix, causal=False, q_offset=0):
+def attention(xq, xkv, sd, prefix, causal=False, q_offset=0, drop=None):
     """softmax(q k^T + M) v with NO 1/sqrt(d) scale and no relative bias.
 
     q_offset: absolute position of xq[:, 0] when xq is a suffix of the causal sequence."""
@@ -200,14 +244,19 @@ def attention(xq, xkv, sd, prefix, causal=False, q_offset=0):
         ki = torch.arange(tk)[None, :]
         scores = scores.masked_fill(ki > qi, float("-inf"))
     p = torch.softmax(scores, dim=-1)
+    if drop is not None:
+        p = drop(p)                                   # HF T5Attention: dropout on the attention weights
     ctx = (p @ v).transpose(1, 2).reshape(xq.shape[0], xq.shape[1], -1)
     return ctx @ sd[prefix + ".o.weight"].T
 
 
-def ffn(x, sd, prefix):
+def ffn(x, sd, prefix, drop=None):
     g = gelu_new(x @ sd[prefix + ".wi_0.weight"].T)
     u = x @ sd[prefix + ".wi_1.weight"].T
-    return (g * u) @ sd[prefix + ".wo.weight"].T
+    y = g * u
+    if drop is not None:
+        y = drop(y)                                   # HF T5DenseGatedGeluDense: dropout before wo
+    return y @ sd[prefix + ".wo.weight"].T
 
 
 def _n_blocks(sd, stack):
@@ -217,32 +266,36 @@ def _n_blocks(sd, stack):
     return n
 
 
-def encoder_stack(h, sd, stack="encoder"):
+def encoder_stack(h, sd, stack="encoder", drop=NO_DROP):
     """T5Stack.forward for a non-decoder stack given embedded input h (b, t, d):
-    + PE[0:t]; n x {self-attn, FFN}; final norm.  Reference models/t5.py:507-702."""
-    h = h + positional_table(h.shape[1], dtype=h.dtype)
+    + PE[0:t]; n x {self-attn, FFN}; final norm.  Reference models/t5.py:507-702.
+    `drop` (training mode only) marks the reference's dropout sites: stack input (:601), attention
+    weights, sublayer outputs, FFN inner, final norm output (:678)."""
+    d = lambda site, i=0: (lambda x: drop(x, stack, i, site))
+    h = d("input")(h + positional_table(h.shape[1], dtype=h.dtype))
     for i in range(_n_blocks(sd, stack)):
         p = f"{stack}.block.{i}.layer"
         n = rms_norm(h, sd[f"{p}.0.layer_norm.weight"])
-        h = h + attention(n, n, sd, f"{p}.0.SelfAttention")
+        h = h + d("self_out", i)(attention(n, n, sd, f"{p}.0.SelfAttention", drop=d("self_probs", i)))
         n = rms_norm(h, sd[f"{p}.1.layer_norm.weight"])
-        h = h + ffn(n, sd, f"{p}.1.DenseReluDense")
-    return rms_norm(h, sd[f"{stack}.final_layer_norm.weight"])
+        h = h + d("ffn_out", i)(ffn(n, sd, f"{p}.1.DenseReluDense", drop=d("ffn_inner", i)))
+    return d("final")(rms_norm(h, sd[f"{stack}.final_layer_norm.weight"]))
 
 
-def decoder_stack(h, enc, sd, stack="decoder"):
+def decoder_stack(h, enc, sd, stack="decoder", drop=NO_DROP):
     """T5Stack.forward for the decoder over the WHOLE prefix h (b, t, d) (already embedded),
     attending to enc (b, Tk, d).  Reference models/t5.py:507-702."""
-    h = h + positional_table(h.shape[1], dtype=h.dtype)
+    d = lambda site, i=0: (lambda x: drop(x, stack, i, site))
+    h = d("input")(h + positional_table(h.shape[1], dtype=h.dtype))
     for i in range(_n_blocks(sd, stack)):
         p = f"{stack}.block.{i}.layer"
         n = rms_norm(h, sd[f"{p}.0.layer_norm.weight"])
-        h = h + attention(n, n, sd, f"{p}.0.SelfAttention", causal=True)
+        h = h + d("self_out", i)(attention(n, n, sd, f"{p}.0.SelfAttention", causal=True, drop=d("self_probs", i)))
         n = rms_norm(h, sd[f"{p}.1.layer_norm.weight"])
-        h = h + attention(n, enc, sd, f"{p}.1.EncDecAttention")
+        h = h + d("cross_out", i)(attention(n, enc, sd, f"{p}.1.EncDecAttention", drop=d("cross_probs", i)))
         n = rms_norm(h, sd[f"{p}.2.layer_norm.weight"])
-        h = h + ffn(n, sd, f"{p}.2.DenseReluDense")
-    return rms_norm(h, sd[f"{stack}.final_layer_norm.weight"])
+        h = h + d("ffn_out", i)(ffn(n, sd, f"{p}.2.DenseReluDense", drop=d("ffn_inner", i)))
+    return d("final")(rms_norm(h, sd[f"{stack}.final_layer_norm.weight"]))
 
 
 def cast_state_dict(sd, dtype=torch.float64):
@@ -250,16 +303,16 @@ def cast_state_dict(sd, dtype=torch.float64):
             for k, v in sd.items()}
 
 
-def encode(inputs, sd):
+def encode(inputs, sd, drop=NO_DROP):
     """proj + encoder.  Reference models/t5.py:253-258."""
     x = torch.as_tensor(inputs).to(sd["proj.weight"].dtype)
-    return encoder_stack(x @ sd["proj.weight"].T, sd, "encoder")
+    return encoder_stack(x @ sd["proj.weight"].T, sd, "encoder", drop=drop)
 
 
-def decoder_logits(ids, enc, sd):
+def decoder_logits(ids, enc, sd, drop=NO_DROP):
     """Full-prefix decoder pass + lm_head -> (b, t, V).  Reference models/t5.py:268-285."""
     h = sd["decoder_embed_tokens.weight"][ids]
-    return decoder_stack(h, enc, sd) @ sd["lm_head.weight"].T
+    return decoder_stack(h, enc, sd, drop=drop) @ sd["lm_head.weight"].T
 
 
 def memory_block(prev_ids, sd, segmem_length=64):
@@ -369,17 +422,18 @@ def shift_right(labels):
     return out.masked_fill(out == -100, PAD_ID)
 
 
-def forward_logits(inputs, labels, sd):
+def forward_logits(inputs, labels, sd, drop=NO_DROP):
     """Reference T5ForConditionalGeneration.forward, models/t5.py:182-249 -> (B, L, V)."""
-    return decoder_logits(shift_right(labels), encode(inputs, sd), sd)
+    return decoder_logits(shift_right(labels), encode(inputs, sd, drop), sd, drop)
 
 
-def forward_logits_segmem_v2_with_prev(inputs, labels, targets_prev, sd, segmem_length=64):
-    """Reference T5SegMemV2WithPrev.forward, models/t5_segmem_v2_with_prev.py:60-224."""
-    enc = encode(inputs, sd)
+def forward_logits_segmem_v2_with_prev(inputs, labels, targets_prev, sd, segmem_length=64, drop=NO_DROP):
+    """Reference T5SegMemV2WithPrev.forward, models/t5_segmem_v2_with_prev.py:60-224 (the memory
+    encoder has dropout 0, models/t5_segmem.py:64)."""
+    enc = encode(inputs, sd, drop)
     prev = targets_prev.masked_fill(targets_prev == -100, PAD_ID)
     mem = memory_block(prev, sd, segmem_length)
-    return decoder_logits(shift_right(labels), torch.cat([enc, mem], dim=1), sd)
+    return decoder_logits(shift_right(labels), torch.cat([enc, mem], dim=1), sd, drop)
 
 
 # ---------------------------------------------------------------------------------------------

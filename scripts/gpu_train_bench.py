@@ -14,8 +14,10 @@ if world > 1:
 B = int(sys.argv[1]) if len(sys.argv) > 1 else 32
 L = int(sys.argv[2]) if len(sys.argv) > 2 else 1024
 steps = int(sys.argv[3]) if len(sys.argv) > 3 else 3
+dropout = float(sys.argv[4]) if len(sys.argv) > 4 else 0.0
 m = v2.T5SegMemV2WithPrev(t5.T5Config(), 1, 64); m.load_state_dict(syn.synthetic_state_dict(4322, segmem=True)); m = m.eval().cuda()
 eng = m.engine(); n_params = eng.train_init()
+eng.train_set_dropout(dropout, 1234 + rank)
 g = torch.Generator().manual_seed(100 + rank)
 x = torch.rand((B, 256, 512), generator=g).cuda()
 def toks():
@@ -47,7 +49,7 @@ tot = r[:, :4].sum(1).mean()
 if world > 1:
     t = torch.tensor([tot], device="cuda"); dist.all_reduce(t, op=dist.ReduceOp.MAX); tot = float(t)
 if rank == 0:
-    print(json.dumps({"config": f"MR-MT3 V2WithPrev fine-tune step, batch {B}/GPU, L = Lp = {L}, {world} GPU(s)", "params": n_params,
+    print(json.dumps({"config": f"MR-MT3 V2WithPrev fine-tune step, batch {B}/GPU, L = Lp = {L}, {world} GPU(s), dropout {dropout}", "params": n_params,
                       "ms_forward": round(r[:, 0].mean(), 2), "ms_backward": round(r[:, 1].mean(), 2),
                       "ms_allreduce": round(r[:, 2].mean(), 2), "ms_adamw": round(r[:, 3].mean(), 2), "ms_step": round(tot, 2),
                       "samples_per_s": round(B * world / (tot / 1e3), 1),

@@ -46,7 +46,7 @@ def _setup(seed=1234, B=2, L=16, segmem=False):
     return model, sd, x, labels
 
 
-def _oracle_grads(sd, x, labels, prev=None):
+def _oracle_grads(sd, x, labels, prev=None, drop=O.NO_DROP):
     sd64 = {}
     for k, v in sd.items():
         if v.is_floating_point() and "inv_freq" not in k:
@@ -54,8 +54,8 @@ def _oracle_grads(sd, x, labels, prev=None):
             sd64[k] = sd64[same[0]] if same else v.detach().double().requires_grad_(True)
         else:
             sd64[k] = v
-    logits = O.forward_logits(x, labels, sd64) if prev is None else \
-        O.forward_logits_segmem_v2_with_prev(x, labels, prev, sd64)
+    logits = O.forward_logits(x, labels, sd64, drop=drop) if prev is None else \
+        O.forward_logits_segmem_v2_with_prev(x, labels, prev, sd64, drop=drop)
     loss = F.cross_entropy(logits.reshape(-1, logits.shape[-1]), labels.reshape(-1), ignore_index=-100)
     loss.backward()
     return float(loss), {k: v.grad for k, v in sd64.items() if torch.is_tensor(v) and v.requires_grad}, logits.detach()
@@ -164,6 +164,7 @@ def test_autograd_bridge_and_torch_optimizer():
     torch.optim.AdamW.step().  The logits carry a grad_fn whose backward is the CUDA backward; the
     parameter gradients must equal the built-in loss path's and the loop must learn."""
     model, sd, x, labels = _setup(seed=31, B=2, L=24)
+    model.config.dropout_rate = 0.0          # two separate forwards are compared below
     model.train()
     xg, lg = x.cuda(), labels.cuda()
     logits = model(inputs=xg, labels=lg)
@@ -197,3 +198,82 @@ def test_autograd_bridge_and_torch_optimizer():
     model.eval()
     with torch.no_grad():
         assert not model(inputs=xg, labels=lg).requires_grad
+
+
+def _compare_grads(eng, grad, want, n_expected, rel_tol=GRAD_REL_TOL, cos_tol=GRAD_COS_TOL):
+    worst, seen = [], set()
+    for name, g_ref in want.items():
+        if g_ref is None or id(g_ref) in seen or \
+                name.startswith(("encoder.embed_tokens", "decoder.embed_tokens", "segmem_encoder.embed_tokens")):
+            continue
+        seen.add(id(g_ref))
+        got = eng.flat_view(grad, name).cpu().double().reshape(g_ref.shape)
+        ref_n = g_ref.norm().item()
+        worst.append(((got - g_ref).norm().item() / max(ref_n, 1e-12),
+                      float((got * g_ref).sum() / max(got.norm().item() * ref_n, 1e-30)), name))
+    worst.sort(reverse=True)
+    print("WORST", ["%.4f %.5f %s" % w for w in worst[:12]])
+    assert len(worst) == n_expected
+    for rel, cos, name in worst:
+        assert rel < rel_tol and cos > cos_tol, (name, rel, cos)
+
+
+SITE_MASKS = [(1 << i, GRAD_REL_TOL, GRAD_COS_TOL) for i in range(1, 9)] + [(0x1ff, 0.2, 0.985)]
+
+
+@pytest.mark.parametrize("sites,rel_tol,cos_tol", SITE_MASKS)
+def test_dropout_matches_oracle_with_the_same_masks(sites, rel_tol, cos_tol):
+    """Training-mode dropout (reference config.dropout_rate = 0.1 at the HF T5 sites: 1 stack input,
+    2 / 7 self / cross attention weights, 3 / 8 / 5 sublayer outputs, 4 FFN inner, 6 final norm
+    output).  torch's RNG stream cannot be reproduced, so both sides use the counter-based mask of
+    csrc/common.cuh:drop_keep / mt3_oracle.dropout_keep with the same seed.  One site at a time the
+    agreement is as tight as without dropout (a wrong index or scale at any site would show at once);
+    with all sites on, the sharper attention of the larger activations roughly doubles the bf16
+    noise of the q/k gradients, hence the looser bound there."""
+    B, L = 2, 40
+    model, sd, x, labels = _setup(seed=1234, B=B, L=L)
+    p, seed = 0.1, 987654321
+    want_loss, want, want_logits = _oracle_grads(sd, x, labels, None, drop=O.Dropout(p, seed, site_mask=sites))
+    eng = model.engine()
+    eng.train_init()
+    try:
+        eng.set_option("train_dropout_sites", sites)
+        eng.train_set_dropout(p, seed)
+        logits, loss = eng.train_forward(x.cuda(), model._shift_right(labels), labels, None)
+        err = (logits.cpu().double() - want_logits).abs().max().item()
+        assert err < (0.08 if sites != 0x1ff else 0.2), err
+        assert abs(loss - want_loss) < 0.02, (loss, want_loss)
+        grad = eng.train_backward()
+        assert torch.isfinite(grad).all()
+        _compare_grads(eng, grad, want, 189, rel_tol, cos_tol)
+    finally:
+        eng.set_option("train_dropout_sites", 0x1ff)
+        eng.train_set_dropout(0.0, 0)
+
+
+def test_dropout_segmem_new_masks_every_step_and_off_switch():
+    """MR-MT3: all sites on (none inside the memory encoder, models/t5_segmem.py:64); every forward
+    draws new masks; p = 0 restores the deterministic forward."""
+    B, L, Lp = 2, 40, 96
+    model, sd, x, labels = _setup(seed=4322, B=B, L=L, segmem=True)
+    prev = torch.randint(3, 1391, (B, Lp), generator=torch.Generator().manual_seed(5))
+    prev[:, 70:] = 0
+    p, seed = 0.1, 424242
+    want_loss, want, want_logits = _oracle_grads(sd, x, labels, prev, drop=O.Dropout(p, seed))
+    base_loss, _, base_logits = _oracle_grads(sd, x, labels, prev)
+    assert (want_logits - base_logits).abs().max().item() > 0.2          # the masks do change the result
+    eng = model.engine()
+    eng.train_init()
+    eng.train_set_dropout(p, seed)
+    logits, loss = eng.train_forward(x.cuda(), model._shift_right(labels), labels, prev)
+    assert (logits.cpu().double() - want_logits).abs().max().item() < 0.2
+    assert abs(loss - want_loss) < 0.02, (loss, want_loss)
+    grad = eng.train_backward()
+    _compare_grads(eng, grad, want, 200, 0.2, 0.985)
+    logits2, _ = eng.train_forward(x.cuda(), model._shift_right(labels), labels, prev)
+    assert (logits2 - logits).abs().max().item() > 0.05                  # new masks on the next step
+    eng.train_set_dropout(0.0, 0)
+    a, _ = eng.train_forward(x.cuda(), model._shift_right(labels), labels, prev)
+    b, _ = eng.train_forward(x.cuda(), model._shift_right(labels), labels, prev)
+    assert torch.equal(a, b)
+    assert (a.cpu().double() - base_logits).abs().max().item() < 0.1
