@@ -149,6 +149,7 @@ __global__ void __launch_bounds__(128)
             l_run[h] *= scale_old[h];
         }
         uint32_t pf[4][4];
+        uint32_t keep_lo = 0, keep_hi = 0;
 #pragma unroll
         for (int ni = 0; ni < 8; ++ni) {
             float p0 = exp2f((s[ni][0] - m_use[0]) * kLog2e);
@@ -161,16 +162,28 @@ __global__ void __launch_bounds__(128)
                 const unsigned long long r0i = ((unsigned long long)(b * kHeads + head) * p.Tq + row_lo) * p.Tk;
                 const unsigned long long r1i = r0i + 8ull * p.Tk;
                 const int key = kt * kAttnBK + ni * 8 + (lane & 3) * 2;
-                p0 *= drop_factor(p.drop, r0i + key);
-                p1 *= drop_factor(p.drop, r0i + key + 1);
-                p2 *= drop_factor(p.drop, r1i + key);
-                p3 *= drop_factor(p.drop, r1i + key + 1);
+                float f0, f1, f2, f3;
+                drop_factor2(p.drop, r0i + key, f0, f1);
+                drop_factor2(p.drop, r1i + key, f2, f3);
+                p0 *= f0;
+                p1 *= f1;
+                p2 *= f2;
+                p3 *= f3;
+                keep_lo |= ((f0 != 0.f ? 1u : 0u) | (f1 != 0.f ? 2u : 0u)) << (2 * ni);
+                keep_hi |= ((f2 != 0.f ? 1u : 0u) | (f3 != 0.f ? 2u : 0u)) << (2 * ni);
             }
             // C-fragment of two adjacent n-blocks == A-fragment of one k16 step
             pf[ni >> 1][(ni & 1) * 2 + 0] = pack_bf16(p0, p1);
             pf[ni >> 1][(ni & 1) * 2 + 1] = pack_bf16(p2, p3);
 #pragma unroll
             for (int r = 0; r < 4; ++r) o[ni][r] *= scale_old[r >> 1];
+        }
+
+        if (p.drop.on() && p.keep) {
+            const int n_words = ((p.Tk + kAttnBK - 1) / kAttnBK) * 4;
+            unsigned short* w = p.keep + ((size_t)(b * kHeads + head) * p.Tq + row_lo) * n_words + kt * 4 + (lane & 3);
+            if (row_lo < p.Tq) w[0] = (unsigned short)keep_lo;
+            if (row_lo + 8 < p.Tq) w[(size_t)8 * n_words] = (unsigned short)keep_hi;
         }
 
         // O += P V   (V tile is [key][d]; transposed ldmatrix gives the col-major B fragment)

@@ -28,6 +28,9 @@ struct AttnFullParams {
     int causal_offset;
     float* lse2;        // optional (batch, heads, Tq): m*log2(e) + log2(l), saved for the backward pass
     DropSpec drop;      // training only: dropout on the attention weights, index ((b*H + h)*Tq + q)*Tk + k
+    unsigned short* keep;  // optional with `drop`: the keep bits, saved for the backward pass
+                           // [(b*H + h)*Tq + q][ceil(Tk/64)][4] words; word (kt, j) bit 2*ni + e is key
+                           // 64 kt + 8 ni + 2 j + e  (the mma C-fragment order of a 64-key tile)
 };
 Status launch_attn_full(const AttnFullParams& p, int batch, cudaStream_t stream);
 

@@ -122,29 +122,47 @@ __device__ __forceinline__ float gelu_new(float a) {
 }
 
 // ---- dropout (fine-tune step) -------------------------------------------------------------------
-// Counter-based: element `index` of tensor `tid` is kept iff hash(seed, tid, index) >= p * 2^32, so
-// the backward regenerates every mask instead of storing it, and the CPU oracle can mirror it
-// (oracle/mt3_oracle.py:dropout_keep).  `scale` = 1 / (1 - p); p == 0 disables everything.
+// Counter-based: one 64-bit hash of (seed, tensor id, index / 4) yields four 16-bit draws, element
+// `index` is kept iff its draw >= p * 65536.  The backward regenerates every mask instead of storing
+// it, and the CPU oracle mirrors it (oracle/mt3_oracle.py:dropout_keep).  `scale` = 1 / (1 - p);
+// p == 0 disables everything.
 struct DropSpec {
     unsigned long long seed;  // already mixed with the tensor id
-    unsigned int threshold;   // p * 2^32
+    unsigned int threshold;   // p * 2^16
     float scale;
     __host__ __device__ bool on() const { return threshold != 0u; }
 };
 __host__ __device__ __forceinline__ unsigned long long drop_mix_tid(unsigned long long seed, unsigned int tid) {
     return seed ^ ((unsigned long long)tid * 0x9E3779B97F4A7C15ull);
 }
-__host__ __device__ __forceinline__ bool drop_keep(const DropSpec& d, unsigned long long index) {
-    unsigned long long x = d.seed + index * 0xD1B54A32D192ED03ull;
+// the four draws of the aligned group index / 4
+__host__ __device__ __forceinline__ unsigned long long drop_hash4(const DropSpec& d, unsigned long long group) {
+    unsigned long long x = d.seed + group * 0xD1B54A32D192ED03ull;
     x ^= x >> 32;
     x *= 0xD6E8FEB86659FD93ull;
     x ^= x >> 32;
     x *= 0xD6E8FEB86659FD93ull;
     x ^= x >> 32;
-    return (unsigned int)x >= d.threshold;
+    return x;
+}
+__host__ __device__ __forceinline__ float drop_lane(const DropSpec& d, unsigned long long h, unsigned int lane) {
+    return ((unsigned int)(h >> (16u * lane)) & 0xFFFFu) >= d.threshold ? d.scale : 0.f;
 }
 __host__ __device__ __forceinline__ float drop_factor(const DropSpec& d, unsigned long long index) {
-    return d.on() ? (drop_keep(d, index) ? d.scale : 0.f) : 1.f;
+    return d.on() ? drop_lane(d, drop_hash4(d, index >> 2), (unsigned int)index & 3u) : 1.f;
+}
+// factors of two consecutive elements (one hash when they share a group)
+__host__ __device__ __forceinline__ void drop_factor2(const DropSpec& d, unsigned long long index, float& f0, float& f1) {
+    const unsigned long long h0 = drop_hash4(d, index >> 2);
+    const unsigned long long h1 = ((index + 1) >> 2) == (index >> 2) ? h0 : drop_hash4(d, (index + 1) >> 2);
+    f0 = drop_lane(d, h0, (unsigned int)index & 3u);
+    f1 = drop_lane(d, h1, (unsigned int)(index + 1) & 3u);
+}
+// factors of the aligned group 4g .. 4g+3
+__host__ __device__ __forceinline__ void drop_factor4(const DropSpec& d, unsigned long long group, float (&f)[4]) {
+    const unsigned long long h = drop_hash4(d, group);
+#pragma unroll
+    for (unsigned int k = 0; k < 4; ++k) f[k] = drop_lane(d, h, k);
 }
 
 // streaming 16 B load that does not allocate in L1 (KV cache / one-shot reads)

@@ -41,6 +41,7 @@ struct LayerStash {
     float *h_in, *h_mid2, *h_mid;
     bf16 *n1, *qkv, *ctx, *nc, *qc, *ctx_c, *n2, *raw, *ff;
     float *lse, *lse_c;
+    unsigned short *keep, *keep_c;  // attention-dropout keep bits (AttnFullParams::keep)
 };
 
 struct TrainState {
@@ -75,9 +76,9 @@ enum { kSiteInput = 1, kSiteSelfProbs = 2, kSiteSelfOut = 3, kSiteFfnInner = 4, 
        kSiteCrossProbs = 7, kSiteCrossOut = 8 };
 static DropSpec drop_spec(const TrainState* t, unsigned long long seed, int stack, int layer, int site) {
     if (t->drop_p <= 0.f || stack == 2 || !((t->drop_sites >> site) & 1)) return DropSpec{0ull, 0u, 1.f};
-    const double th = (double)t->drop_p * 4294967296.0;
+    const float th = t->drop_p * 65536.0f;
     return DropSpec{drop_mix_tid(seed, (unsigned)((stack << 16) | (layer << 8) | site)),
-                    (unsigned int)(th > 4294967295.0 ? 4294967295.0 : th), 1.f / (1.f - t->drop_p)};
+                    (unsigned int)(th > 65535.f ? 65535.f : th), 1.f / (1.f - t->drop_p)};
 }
 
 Status train_set_dropout_sites(mrmt3_handle* h, int mask) {
@@ -260,11 +261,15 @@ struct Bump {
     }
 };
 
-static size_t stash_bytes(int n_enc, int n_dec, int n_mem_layers, size_t Me, size_t Md, size_t Mm, int B, int L, int Lp) {
+static size_t keep_bytes(size_t nb, size_t Tq, size_t Tk) { return nb * kHeads * Tq * ((Tk + 63) / 64) * 8; }
+
+static size_t stash_bytes(int n_enc, int n_dec, int n_mem_layers, size_t Me, size_t Md, size_t Mm, int B, int L, int Lp,
+                          int tk, bool drop) {
     auto layer = [&](size_t M, size_t T, bool dec) {
         size_t b = M * kDModel * 4 * (dec ? 3 : 2) + M * kDModel * 2 * (dec ? 3 : 2) + M * 3 * kInner * 2 +
                    M * kInner * 2 * (dec ? 3 : 1) + M * 2 * kDFF * 2 + M * kDFF * 2 + (size_t)B * kHeads * T * 4 * (dec ? 2 : 1);
-        return b + 16 * 256;
+        if (drop) b += keep_bytes(B, T, T) + (dec ? keep_bytes(B, T, tk) : 0);
+        return b + 24 * 256;
     };
     return n_enc * layer(Me, kSegFrames, false) + n_dec * layer(Md, L, true) + n_mem_layers * layer(Mm, Lp, false) +
            Me * kDModel * (2 + 4 + 2) + Mm * kDModel * (2 + 4 + 2) + (Me + Mm) * kDModel * 2 +
@@ -287,7 +292,8 @@ Status train_forward(mrmt3_handle* h, const float* mel, int B, const long long* 
     const size_t Me = (size_t)B * kSegFrames, Md = (size_t)B * L, Mm = (size_t)B * Lp;
     const float eps = h->cfg.ln_eps;
     const ARowMap id{nullptr, 1};
-    MRMT3_TRY(t->stash.reserve(stash_bytes(n_enc, n_dec, with_mem ? h->cfg.n_mem_layers : 0, Me, Md, Mm, B, L, Lp)));
+    MRMT3_TRY(t->stash.reserve(stash_bytes(n_enc, n_dec, with_mem ? h->cfg.n_mem_layers : 0, Me, Md, Mm, B, L, Lp, tk,
+                                           t->drop_p > 0.f)));
     t->Lp = Lp;
     t->n_mem = n_mem;
     const unsigned long long seed = t->drop_seed;
@@ -308,8 +314,10 @@ Status train_forward(mrmt3_handle* h, const float* mel, int B, const long long* 
     RUN(h, launch_gemm_tc(*h->tma, t->mel16, kDModel, Me, id, h->proj, kDModel, (int)Me, kDModel, kDModel,
                           EpiPosAdd{H, kDModel, h->pe, kSegFrames, 0}, s));
     auto attn_fwd = [&](const bf16* Q, long qb, int qr, const bf16* K, const bf16* V, long kb, long kh, int kr, bf16* O,
-                        int Tq, int Tk, int causal, float* lse, int nb, DropSpec drop) -> Status {
+                        int Tq, int Tk, int causal, float* lse, int nb, DropSpec drop, unsigned short*& keep) -> Status {
         AttnFullParams ap{};
+        keep = drop.on() ? bp.take<unsigned short>(keep_bytes(nb, Tq, Tk) / 2) : nullptr;
+        ap.keep = keep;
         ap.Q = Q; ap.q_batch_stride = qb; ap.q_head_stride = kDKV; ap.q_row_stride = qr;
         ap.K = K; ap.V = V;
         ap.k_batch_stride = ap.v_batch_stride = kb;
@@ -357,7 +365,8 @@ Status train_forward(mrmt3_handle* h, const float* mel, int B, const long long* 
         RUN(h, launch_gemm_tc(*h->tma, st.n1, kDModel, M, id, Lw.wqkv, kDModel, (int)M, 3 * kInner, kDModel,
                               EpiStoreBf16{st.qkv, 3 * kInner}, s));
         MRMT3_TRY(attn_fwd(st.qkv, (long)T * 3 * kInner, 3 * kInner, st.qkv + kInner, st.qkv + 2 * kInner,
-                           (long)T * 3 * kInner, kDKV, 3 * kInner, st.ctx, T, T, causal, st.lse, nb, mk(stack, li, kSiteSelfProbs)));
+                           (long)T * 3 * kInner, kDKV, 3 * kInner, st.ctx, T, T, causal, st.lse, nb, mk(stack, li, kSiteSelfProbs),
+                           st.keep));
         MRMT3_TRY(out_proj(st.ctx, kInner, Lw.wo, Hres, M, mk(stack, li, kSiteSelfOut)));
         return OkStatus();
     };
@@ -426,7 +435,7 @@ Status train_forward(mrmt3_handle* h, const float* mel, int B, const long long* 
                               EpiStoreBf16{st.qc, kInner}, s));
         const bf16* kbase = h->cross_cache.as<bf16>() + (size_t)li * 2 * kHeads * h->tk_cap * kDKV;
         MRMT3_TRY(attn_fwd(st.qc, (long)L * kInner, kInner, kbase, kbase + (size_t)kHeads * h->tk_cap * kDKV, (long)lane_sz,
-                           (long)h->tk_cap * kDKV, kDKV, st.ctx_c, L, tk, 0, st.lse_c, B, mk(1, li, kSiteCrossProbs)));
+                           (long)h->tk_cap * kDKV, kDKV, st.ctx_c, L, tk, 0, st.lse_c, B, mk(1, li, kSiteCrossProbs), st.keep_c));
         MRMT3_TRY(out_proj(st.ctx_c, kInner, Lw.co, Hd, Md, mk(1, li, kSiteCrossOut)));
         MRMT3_TRY(ffn_fwd(Lw, st, Hd, Md, 1, li));
     }
@@ -568,9 +577,11 @@ Status train_backward(mrmt3_handle* h, float* grad, const float* dlogits_f32, cu
     };
     auto attn_bwd = [&](const bf16* Q, long qb, int qr, const bf16* K, const bf16* V, long kb, long kh, int kr,
                         const bf16* O, const bf16* dO, bf16* dQ, bf16* dK, bf16* dV, long dkb, long dkh, int dkr,
-                        const float* lse, int Tq, int Tk, int causal, DropSpec drop) -> Status {
+                        const float* lse, int Tq, int Tk, int causal, DropSpec drop, const unsigned short* keep) -> Status {
         AttnBwdParams ap{};
         ap.drop = drop;
+        ap.keep = keep;
+        if (drop.on() && !keep) return Error(3, "attention dropout keep bits missing (forward ran without dropout?)");
         ap.Q = Q; ap.K = K; ap.V = V; ap.O = O; ap.dO = dO; ap.dQ = dQ; ap.dK = dK; ap.dV = dV;
         ap.q_batch_stride = qb; ap.q_head_stride = kDKV; ap.q_row_stride = qr;
         ap.k_batch_stride = ap.v_batch_stride = kb;
@@ -605,7 +616,7 @@ Status train_backward(mrmt3_handle* h, float* grad, const float* dlogits_f32, cu
         const long tb = (long)T * 3 * kInner;
         MRMT3_TRY(attn_bwd(st.qkv, tb, 3 * kInner, st.qkv + kInner, st.qkv + 2 * kInner, tb, kDKV, 3 * kInner, st.ctx, dctx,
                            dqkv, dqkv + kInner, dqkv + 2 * kInner, tb, kDKV, 3 * kInner, st.lse, T, T, causal,
-                           mk(stack, li, kSiteSelfProbs)));
+                           mk(stack, li, kSiteSelfProbs), st.keep));
         MRMT3_TRY(dgrad(dqkv, 3 * kInner, ls.wqkv, dn, M));
         MRMT3_TRY(wgrad(dqkv, 3 * kInner, 3 * kInner, st.n1, kDModel, kDModel, G(ls.wqkv), M));
         MRMT3_TRY(norm_bwd(st.h_in, Lw.ln_self, dn, M, G(ls.ln_self)));
@@ -636,7 +647,7 @@ Status train_backward(mrmt3_handle* h, float* grad, const float* dlogits_f32, cu
         bf16* dk_l = dkv + (size_t)li * 2 * kInner;
         MRMT3_TRY(attn_bwd(st.qc, (long)L * kInner, kInner, kbase, kbase + (size_t)kHeads * h->tk_cap * kDKV, (long)lane_sz,
                            (long)h->tk_cap * kDKV, kDKV, st.ctx_c, dctx, dqc, dk_l, dk_l + kInner,
-                           (long)tk * (long)kvN, kDKV, (int)kvN, st.lse_c, L, tk, 0, mk(1, li, kSiteCrossProbs)));
+                           (long)tk * (long)kvN, kDKV, (int)kvN, st.lse_c, L, tk, 0, mk(1, li, kSiteCrossProbs), st.keep_c));
         MRMT3_TRY(dgrad(dqc, kInner, ls.cq, dn, Md));
         MRMT3_TRY(wgrad(dqc, kInner, kInner, st.nc, kDModel, kDModel, G(ls.cq), Md));
         MRMT3_TRY(norm_bwd(st.h_mid2, Lw.ln_cross, dn, Md, G(ls.ln_cross)));

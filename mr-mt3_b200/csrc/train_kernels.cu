@@ -134,73 +134,109 @@ Status launch_rmsnorm_bwd(const float* x, const float* g, float eps, const bf16*
 
 // ---------------------------------------------------------------------------------------------
 // gated GELU from the raw ffn-in output (columns interleaved: 2j -> wi_0, 2j+1 -> wi_1)
-__global__ void gated_gelu_fwd_kernel(const uint32_t* __restrict__ raw, bf16* __restrict__ ff, size_t n, DropSpec drop) {
-    size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= n) return;
-    uint32_t v = raw[i];
-    float2 ab = __bfloat1622float2(*reinterpret_cast<bf162*>(&v));
-    ff[i] = __float2bfloat16(gelu_new(ab.x) * ab.y * drop_factor(drop, i));
+__global__ void gated_gelu_fwd_kernel(const uint4* __restrict__ raw, uint2* __restrict__ ff, size_t n4, DropSpec drop) {
+    size_t g = (size_t)blockIdx.x * blockDim.x + threadIdx.x;  // four outputs per thread = one mask group
+    if (g >= n4) return;
+    const uint4 v = raw[g];
+    float f[4] = {1.f, 1.f, 1.f, 1.f};
+    if (drop.on()) drop_factor4(drop, g, f);
+    const uint32_t w[4] = {v.x, v.y, v.z, v.w};
+    float o[4];
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+        float2 ab = __bfloat1622float2(*reinterpret_cast<const bf162*>(&w[k]));
+        o[k] = gelu_new(ab.x) * ab.y * f[k];
+    }
+    ff[g] = make_uint2(pack_bf16(o[0], o[1]), pack_bf16(o[2], o[3]));
 }
 
-__global__ void gated_gelu_bwd_kernel(const uint32_t* __restrict__ raw, const bf16* __restrict__ dff,
-                                      uint32_t* __restrict__ draw, size_t n, DropSpec drop) {
-    size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= n) return;
-    uint32_t v = raw[i];
-    float2 ab = __bfloat1622float2(*reinterpret_cast<bf162*>(&v));
-    const float a = ab.x, b = ab.y, d = __bfloat162float(dff[i]) * drop_factor(drop, i);
+__global__ void gated_gelu_bwd_kernel(const uint4* __restrict__ raw, const uint2* __restrict__ dff,
+                                      uint4* __restrict__ draw, size_t n4, DropSpec drop) {
+    size_t g = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (g >= n4) return;
+    const uint4 v = raw[g];
+    const uint2 dv = dff[g];
+    float f[4] = {1.f, 1.f, 1.f, 1.f};
+    if (drop.on()) drop_factor4(drop, g, f);
+    const uint32_t w[4] = {v.x, v.y, v.z, v.w};
+    float2 d01 = __bfloat1622float2(*reinterpret_cast<const bf162*>(&dv.x));
+    float2 d23 = __bfloat1622float2(*reinterpret_cast<const bf162*>(&dv.y));
+    const float dd[4] = {d01.x * f[0], d01.y * f[1], d23.x * f[2], d23.y * f[3]};
+    uint32_t out[4];
     const float k = 0.7978845608028654f;
-    const float t = tanhf(k * (a + 0.044715f * a * a * a));
-    const float gelu = 0.5f * a * (1.0f + t);
-    const float dgelu = 0.5f * (1.0f + t) + 0.5f * a * (1.0f - t * t) * k * (1.0f + 3.0f * 0.044715f * a * a);
-    draw[i] = pack_bf16(d * b * dgelu, d * gelu);
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+        float2 ab = __bfloat1622float2(*reinterpret_cast<const bf162*>(&w[q]));
+        const float a = ab.x, b = ab.y, d = dd[q];
+        const float t = tanhf(k * (a + 0.044715f * a * a * a));
+        const float gelu = 0.5f * a * (1.0f + t);
+        const float dgelu = 0.5f * (1.0f + t) + 0.5f * a * (1.0f - t * t) * k * (1.0f + 3.0f * 0.044715f * a * a);
+        out[q] = pack_bf16(d * b * dgelu, d * gelu);
+    }
+    draw[g] = make_uint4(out[0], out[1], out[2], out[3]);
 }
 
 Status launch_gated_gelu_fwd(const bf16* raw, bf16* ff, size_t rows, DropSpec drop, cudaStream_t s) {
     size_t n = rows * kDFF;
     if (!n) return OkStatus();
-    gated_gelu_fwd_kernel<<<(unsigned)((n + 255) / 256), 256, 0, s>>>(reinterpret_cast<const uint32_t*>(raw), ff, n, drop);
+    gated_gelu_fwd_kernel<<<(unsigned)((n / 4 + 255) / 256), 256, 0, s>>>(reinterpret_cast<const uint4*>(raw),
+                                                                        reinterpret_cast<uint2*>(ff), n / 4, drop);
     MRMT3_CHECK_LAUNCH();
     return OkStatus();
 }
 Status launch_gated_gelu_bwd(const bf16* raw, const bf16* dff, bf16* draw, size_t rows, DropSpec drop, cudaStream_t s) {
     size_t n = rows * kDFF;
     if (!n) return OkStatus();
-    gated_gelu_bwd_kernel<<<(unsigned)((n + 255) / 256), 256, 0, s>>>(reinterpret_cast<const uint32_t*>(raw), dff,
-                                                                    reinterpret_cast<uint32_t*>(draw), n, drop);
+    gated_gelu_bwd_kernel<<<(unsigned)((n / 4 + 255) / 256), 256, 0, s>>>(reinterpret_cast<const uint4*>(raw),
+                                                                        reinterpret_cast<const uint2*>(dff),
+                                                                        reinterpret_cast<uint4*>(draw), n / 4, drop);
     MRMT3_CHECK_LAUNCH();
     return OkStatus();
 }
 
 // ---------------------------------------------------------------------------------------------
 // elementwise dropout (forward on a value, backward on its gradient: the same factor)
-__global__ void dropout_f32_kernel(float* __restrict__ x, size_t n, DropSpec drop) {
-    size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (i < n) x[i] *= drop_factor(drop, i);
+__global__ void dropout_f32_kernel(float4* __restrict__ x, size_t n4, DropSpec drop) {
+    size_t g = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (g >= n4) return;
+    float f[4];
+    drop_factor4(drop, g, f);
+    float4 v = x[g];
+    x[g] = make_float4(v.x * f[0], v.y * f[1], v.z * f[2], v.w * f[3]);
 }
-__global__ void dropout_bf16_kernel(bf16* __restrict__ x, size_t n, DropSpec drop) {
-    size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (i < n) x[i] = __float2bfloat16(__bfloat162float(x[i]) * drop_factor(drop, i));
+__global__ void dropout_bf16_kernel(uint2* __restrict__ x, size_t n4, DropSpec drop) {
+    size_t g = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (g >= n4) return;
+    float f[4];
+    drop_factor4(drop, g, f);
+    uint2 v = x[g];
+    float2 a = __bfloat1622float2(*reinterpret_cast<bf162*>(&v.x)), b = __bfloat1622float2(*reinterpret_cast<bf162*>(&v.y));
+    x[g] = make_uint2(pack_bf16(a.x * f[0], a.y * f[1]), pack_bf16(b.x * f[2], b.y * f[3]));
 }
-__global__ void dropout_cast_kernel(const float* __restrict__ in, bf16* __restrict__ out, size_t n, DropSpec drop) {
-    size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (i < n) out[i] = __float2bfloat16(in[i] * drop_factor(drop, i));
+__global__ void dropout_cast_kernel(const float4* __restrict__ in, uint2* __restrict__ out, size_t n4, DropSpec drop) {
+    size_t g = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (g >= n4) return;
+    float f[4] = {1.f, 1.f, 1.f, 1.f};
+    if (drop.on()) drop_factor4(drop, g, f);
+    float4 v = in[g];
+    out[g] = make_uint2(pack_bf16(v.x * f[0], v.y * f[1]), pack_bf16(v.z * f[2], v.w * f[3]));
 }
 Status launch_dropout_f32(float* x, size_t n, DropSpec drop, cudaStream_t s) {
     if (!n || !drop.on()) return OkStatus();
-    dropout_f32_kernel<<<(unsigned)((n + 255) / 256), 256, 0, s>>>(x, n, drop);
+    dropout_f32_kernel<<<(unsigned)((n / 4 + 255) / 256), 256, 0, s>>>(reinterpret_cast<float4*>(x), n / 4, drop);
     MRMT3_CHECK_LAUNCH();
     return OkStatus();
 }
 Status launch_dropout_bf16(bf16* x, size_t n, DropSpec drop, cudaStream_t s) {
     if (!n || !drop.on()) return OkStatus();
-    dropout_bf16_kernel<<<(unsigned)((n + 255) / 256), 256, 0, s>>>(x, n, drop);
+    dropout_bf16_kernel<<<(unsigned)((n / 4 + 255) / 256), 256, 0, s>>>(reinterpret_cast<uint2*>(x), n / 4, drop);
     MRMT3_CHECK_LAUNCH();
     return OkStatus();
 }
 Status launch_dropout_cast(const float* in, bf16* out, size_t n, DropSpec drop, cudaStream_t s) {
     if (!n) return OkStatus();
-    dropout_cast_kernel<<<(unsigned)((n + 255) / 256), 256, 0, s>>>(in, out, n, drop);
+    dropout_cast_kernel<<<(unsigned)((n / 4 + 255) / 256), 256, 0, s>>>(reinterpret_cast<const float4*>(in),
+                                                                      reinterpret_cast<uint2*>(out), n / 4, drop);
     MRMT3_CHECK_LAUNCH();
     return OkStatus();
 }
@@ -529,6 +565,8 @@ __global__ void __launch_bounds__(128)
 
     const int row_lo = q0 + warp * 16 + (lane >> 2);
     const unsigned long long bh_row0 = (unsigned long long)(b * kHeads + head) * p.Tq;
+    const int keep_words = ((p.Tk + kBwdT - 1) / kBwdT) * 4;
+    const float fscale = p.drop.on() ? p.drop.scale : 1.f;
     float lse[2], dl[2] = {0.f, 0.f};
 #pragma unroll
     for (int h = 0; h < 2; ++h) {
@@ -551,6 +589,12 @@ __global__ void __launch_bounds__(128)
             bwd_load_tile(sB[st ^ 1], V, p.v_row_stride, kn * kBwdT, p.Tk);
         }
         cp_async_commit();
+        uint32_t kb[2] = {0u, 0u};
+        if (p.drop.on()) {
+#pragma unroll
+            for (int h = 0; h < 2; ++h)
+                kb[h] = __ldg(p.keep + (bh_row0 + min(row_lo + h * 8, p.Tq - 1)) * keep_words + kt * 4 + (lane & 3));
+        }
         cp_async_wait<1>();
         __syncthreads();
         float s[8][4], dp[8][4];
@@ -558,6 +602,14 @@ __global__ void __launch_bounds__(128)
         bwd_zero(dp);
         bwd_mma_nt(s, qf, sA[st], lane);
         bwd_mma_nt(dp, dof, sB[st], lane);
+        // dropout factors of this thread's 32 (row, key) elements from the forward's keep bits
+        float fdrop[8][4];
+#pragma unroll
+        for (int ni = 0; ni < 8; ++ni) {
+#pragma unroll
+            for (int r = 0; r < 4; ++r)
+                fdrop[ni][r] = !p.drop.on() || ((kb[r >> 1] >> (2 * ni + (r & 1))) & 1u) ? fscale : 0.f;
+        }
         if (pass == 0) {
 #pragma unroll
             for (int ni = 0; ni < 8; ++ni) {
@@ -567,8 +619,7 @@ __global__ void __launch_bounds__(128)
                     const int row = row_lo + ((r >> 1) << 3);
                     const bool ok = key < p.Tk && (!p.causal || key <= row + p.causal_offset);
                     if (ok)
-                        dl[r >> 1] += exp2f(s[ni][r] * kLog2e - lse[r >> 1]) * dp[ni][r] *
-                                      drop_factor(p.drop, (bh_row0 + row) * p.Tk + key);
+                        dl[r >> 1] += exp2f(s[ni][r] * kLog2e - lse[r >> 1]) * dp[ni][r] * fdrop[ni][r];
                 }
             }
             if (kt == n_kt - 1) {
@@ -590,7 +641,7 @@ __global__ void __launch_bounds__(128)
                     const bool ok = key < p.Tk && (!p.causal || key <= row + p.causal_offset);
                     const float pr = ok ? exp2f(s[ni][r] * kLog2e - lse[r >> 1]) : 0.f;
                     // dropout sits between softmax and P V: dP = dP' * m / (1 - p)
-                    const float dpe = p.drop.on() ? dp[ni][r] * drop_factor(p.drop, (bh_row0 + row) * p.Tk + key) : dp[ni][r];
+                    const float dpe = dp[ni][r] * fdrop[ni][r];
                     s[ni][r] = pr * (dpe - dl[r >> 1]);  // dS
                 }
             }
@@ -659,6 +710,10 @@ __global__ void __launch_bounds__(128)
 
     const int key_lo = k0 + warp * 16 + (lane >> 2);  // this thread's keys: key_lo, key_lo + 8
     const unsigned long long bh_row0 = (unsigned long long)(b * kHeads + head) * p.Tq;
+    const int keep_words = ((p.Tk + kBwdT - 1) / kBwdT) * 4;
+    // key_lo = 64 kt + 8 (2 warp) + 2 (lane >> 3) + ((lane >> 2) & 1): word lane >> 3, bit 2 (2 warp) + e; key_lo + 8 two bits up
+    const int keep_shift = 4 * warp + ((lane >> 2) & 1);
+    const float fscale = p.drop.on() ? p.drop.scale : 1.f;
     float dk[8][4], dv[8][4];
     bwd_zero(dk);
     bwd_zero(dv);
@@ -670,6 +725,18 @@ __global__ void __launch_bounds__(128)
             load_stats(st ^ 1, qt + 1);
         }
         cp_async_commit();
+        // keep bits of this thread's 16 query rows x 2 keys: both keys sit in the same saved word
+        uint32_t kbw[8][2];
+        if (p.drop.on()) {
+#pragma unroll
+            for (int ni = 0; ni < 8; ++ni) {
+#pragma unroll
+                for (int e = 0; e < 2; ++e) {
+                    const int row = min(qt * kBwdT + ni * 8 + (lane & 3) * 2 + e, p.Tq - 1);
+                    kbw[ni][e] = __ldg(p.keep + (bh_row0 + row) * keep_words + blockIdx.x * 4 + (lane >> 3)) >> keep_shift;
+                }
+            }
+        }
         cp_async_wait<1>();
         __syncthreads();
         float stt[8][4], dpt[8][4];
@@ -687,7 +754,7 @@ __global__ void __launch_bounds__(128)
                 const int key = key_lo + ((r >> 1) << 3);
                 const bool ok = row < p.Tq && key < p.Tk && (!p.causal || key <= row + p.causal_offset);
                 const float pr = ok ? exp2f(stt[ni][r] * kLog2e - s_lse[st][qc]) : 0.f;
-                const float mk = (ok && p.drop.on()) ? drop_factor(p.drop, (bh_row0 + row) * p.Tk + key) : 1.f;
+                const float mk = !p.drop.on() || ((kbw[ni][r & 1] >> ((r >> 1) << 1)) & 1u) ? fscale : 0.f;
                 pt[ni][r] = pr * mk;                                   // P'^T = dropout(P)^T
                 stt[ni][r] = pr * (dpt[ni][r] * mk - s_dl[st][qc]);    // dS^T
             }

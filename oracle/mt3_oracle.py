@@ -182,17 +182,19 @@ DROP_STACKS = {"encoder": 0, "decoder": 1, "segmem_encoder": 2}
 
 
 def dropout_keep(seed, tid, n):
-    """Boolean keep-mask for flat indices 0..n-1 of tensor `tid` (threshold applied by the caller)."""
+    """The 16-bit draw of flat indices 0..n-1 of tensor `tid`: one 64-bit hash per aligned group of
+    four elements, element i takes bits [16 (i % 4), 16 (i % 4) + 16); kept iff draw >= p * 65536."""
     M = np.uint64(0xFFFFFFFFFFFFFFFF)
     with np.errstate(over="ignore"):
         s = np.uint64(seed) ^ (np.uint64(tid) * np.uint64(0x9E3779B97F4A7C15) & M)
-        x = s + np.arange(n, dtype=np.uint64) * np.uint64(0xD1B54A32D192ED03)
+        x = s + np.arange((n + 3) // 4, dtype=np.uint64) * np.uint64(0xD1B54A32D192ED03)
         x ^= x >> np.uint64(32)
         x *= np.uint64(0xD6E8FEB86659FD93)
         x ^= x >> np.uint64(32)
         x *= np.uint64(0xD6E8FEB86659FD93)
         x ^= x >> np.uint64(32)
-    return (x & np.uint64(0xFFFFFFFF)).astype(np.uint32)
+    i = np.arange(n, dtype=np.uint64)
+    return ((x[i >> np.uint64(2)] >> (np.uint64(16) * (i & np.uint64(3)))) & np.uint64(0xFFFF)).astype(np.uint32)
 
 
 class Dropout:
@@ -200,7 +202,7 @@ class Dropout:
 
     def __init__(self, p=0.0, seed=0, site_mask=0x1ff):
         self.p, self.seed, self.site_mask = float(p), int(seed), int(site_mask)
-        self.threshold = np.uint32(min(int(self.p * 4294967296.0), 0xFFFFFFFF))
+        self.threshold = np.uint32(min(int(np.float32(self.p) * np.float32(65536.0)), 0xFFFF))
 
     def __call__(self, x, stack, layer, site):
         if self.p <= 0.0 or stack == "segmem_encoder":      # models/t5_segmem.py:64: dropout 0 in the memory encoder

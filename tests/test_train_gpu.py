@@ -266,7 +266,12 @@ def test_dropout_segmem_new_masks_every_step_and_off_switch():
     eng.train_init()
     eng.train_set_dropout(p, seed)
     logits, loss = eng.train_forward(x.cuda(), model._shift_right(labels), labels, prev)
-    assert (logits.cpu().double() - want_logits).abs().max().item() < 0.2
+    # bf16 rounding passes through ~40 rescaled (1/(1-p)) sites: bound the worst logit loosely and the
+    # whole tensor tightly (a wrong mask at any site moves both by an order of magnitude more; the
+    # per-site test above pins each mask exactly)
+    err = logits.cpu().double() - want_logits
+    assert err.abs().max().item() < 0.35
+    assert (err.norm() / want_logits.norm()).item() < 0.04
     assert abs(loss - want_loss) < 0.02, (loss, want_loss)
     grad = eng.train_backward()
     _compare_grads(eng, grad, want, 200, 0.2, 0.985)
