@@ -69,9 +69,25 @@ __device__ __forceinline__ uint64_t tc_smem_desc(uint32_t smem_addr) {
     return d;
 }
 
-// instruction descriptor: D = f32, A = B = bf16, both K-major, M = 128, N = BN
-__host__ __device__ constexpr uint32_t tc_idesc(int bn) {
-    return (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(bn >> 3) << 17) | ((uint32_t)(kTcBM >> 4) << 24);
+// MN-major SWIZZLE_128B descriptor: the tile is a stack of TMA boxes of 64 reduction rows x 64
+// M/N elements (128 B per row, 8-row swizzle atoms of 1024 B).  In CuTe's canonical form
+// ((8,n),(8,k)):((1,LBO),(8,SBO)) (16-byte units): LBO = distance between 64-element blocks along
+// M/N = one box, SBO = distance between 8-row groups along the reduction = 1024 B.
+__device__ __forceinline__ uint64_t tc_smem_desc_mn(uint32_t smem_addr, uint32_t box_bytes) {
+    uint64_t d = 0;
+    d |= (uint64_t)((smem_addr >> 4) & 0x3FFF);
+    d |= (uint64_t)((box_bytes >> 4) & 0x3FFF) << 16;  // leading byte offset
+    d |= (uint64_t)(1024 >> 4) << 32;                  // stride byte offset
+    d |= (uint64_t)1 << 46;
+    d |= (uint64_t)2 << 61;
+    return d;
+}
+
+// instruction descriptor: D = f32, A = B = bf16, M = 128, N = BN; both operands K-major, or (mn)
+// both MN-major (bits 15 / 16)
+__host__ __device__ constexpr uint32_t tc_idesc(int bn, bool mn = false) {
+    return (1u << 4) | (1u << 7) | (1u << 10) | (mn ? (3u << 15) : 0u) | ((uint32_t)(bn >> 3) << 17) |
+           ((uint32_t)(kTcBM >> 4) << 24);
 }
 
 // ---- 8-wide epilogue stores --------------------------------------------------------------------
@@ -139,7 +155,12 @@ struct TcSmem {
 // the n-block fastest, so CTAs running at the same time share their A rows through L2.  The
 // accumulator is double-buffered in TMEM: the epilogue warps drain tile i while the MMA warp
 // already accumulates tile i + 1.
-template <int BN, class Epi>
+//
+// MN = true is the weight-gradient form D[m, n] = sum_r A[r, m] B[r, n] on ROW-major A (R x M) and
+// B (R x N) -- both operands MN-major, so neither has to be transposed in memory first.  K is then
+// the number of reduction rows R (any value: TMA zero-fills rows past the end) and the k ranges of
+// the splits are ceil(ceil(R / 64) / k_splits) blocks each.
+template <int BN, class Epi, bool MN = false>
 __global__ void __launch_bounds__(kTcThreads, 1)
     gemm_tn_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_w,
                            int M, int N, int K, ARowMap amap, Epi epi, int k_splits) {
@@ -159,7 +180,7 @@ __global__ void __launch_bounds__(kTcThreads, 1)
     const int lane = threadIdx.x & 31;
     // split-K (wgrad: small output, long reduction): work item t -> output tile t % n_out, k range
     // split t / n_out; split s stores its partial sums at rows [s*M, (s+1)*M) of the output
-    const int KB = K / kTcBK / k_splits;
+    const int KB = MN ? ((K + kTcBK - 1) / kTcBK + k_splits - 1) / k_splits : K / kTcBK / k_splits;
     const int tiles_n = N / BN;
     const int tiles_m = (M + kTcBM - 1) / kTcBM;
     const int n_out = tiles_n * tiles_m;
@@ -204,14 +225,25 @@ __global__ void __launch_bounds__(kTcThreads, 1)
                     mbar_wait(bar_empty + s * 8, ((it / kStages) & 1) ^ 1);
                     mbar_expect_tx(bar_full + s * 8, S::kStageBytes);
                     const uint32_t sa = base + s * S::kStageBytes;
-                    tma_load_2d(sa, &tmap_a, (kb0 + kb) * kTcBK, arow, bar_full + s * 8);
-                    tma_load_2d(sa + S::kABytes, &tmap_w, (kb0 + kb) * kTcBK, n0, bar_full + s * 8);
+                    if constexpr (MN) {
+                        constexpr int kBox = 64 * kTcBK * 2;  // 64 reduction rows x 64 columns
+                        const int r0 = (kb0 + kb) * kTcBK;
+#pragma unroll
+                        for (int j = 0; j < kTcBM / 64; ++j)
+                            tma_load_2d(sa + j * kBox, &tmap_a, m0 + 64 * j, r0, bar_full + s * 8);
+#pragma unroll
+                        for (int j = 0; j < BN / 64; ++j)
+                            tma_load_2d(sa + S::kABytes + j * kBox, &tmap_w, n0 + 64 * j, r0, bar_full + s * 8);
+                    } else {
+                        tma_load_2d(sa, &tmap_a, (kb0 + kb) * kTcBK, arow, bar_full + s * 8);
+                        tma_load_2d(sa + S::kABytes, &tmap_w, (kb0 + kb) * kTcBK, n0, bar_full + s * 8);
+                    }
                 }
             }
         }
     } else if (warp == 1) {
         if (lane == 0) {
-            constexpr uint32_t idesc = tc_idesc(BN);
+            constexpr uint32_t idesc = tc_idesc(BN, MN);
             int it = 0, i = 0;
             for (int t = blockIdx.x; t < n_tiles; t += gridDim.x, ++i) {
                 const int buf = i & 1;
@@ -223,14 +255,15 @@ __global__ void __launch_bounds__(kTcThreads, 1)
                     mbar_wait(bar_full + s * 8, (it / kStages) & 1);
                     tc_fence_after();
                     const uint32_t sa = base + s * S::kStageBytes;
-                    const uint64_t da = tc_smem_desc(sa);
-                    const uint64_t dw = tc_smem_desc(sa + S::kABytes);
+                    const uint64_t da = MN ? tc_smem_desc_mn(sa, 64 * kTcBK * 2) : tc_smem_desc(sa);
+                    const uint64_t dw = MN ? tc_smem_desc_mn(sa + S::kABytes, 64 * kTcBK * 2) : tc_smem_desc(sa + S::kABytes);
+                    // K-major: advance 16 elements (32 B) along K inside the 128-B swizzle atom, +2
+                    // in the 16-byte-granular start-address field; MN-major: 16 reduction rows = two
+                    // whole 1024-B atoms, +128
+                    constexpr uint64_t kStep = MN ? 128 : 2;
 #pragma unroll
-                    for (int k = 0; k < kTcBK / 16; ++k) {
-                        // advance 16 elements (32 B) along K inside the 128-B swizzle atom: +2 in
-                        // the 16-byte-granular start-address field
-                        tc_mma_f16(tacc, da + (uint64_t)(2 * k), dw + (uint64_t)(2 * k), idesc, (kb | k) != 0);
-                    }
+                    for (int k = 0; k < kTcBK / 16; ++k)
+                        tc_mma_f16(tacc, da + kStep * k, dw + kStep * k, idesc, (kb | k) != 0);
                     tc_commit(bar_empty + s * 8);  // frees the ring slot once the MMAs have read it
                 }
                 tc_commit(bar_acc_full + buf * 8);  // accumulator of this tile complete
@@ -288,6 +321,41 @@ Status launch_gemm_tc_bn(TmaCache& tc, const CUtensorMap* ma, const bf16* W, int
     kern<<<std::min(n_tiles, n_sms), kTcThreads, TcSmem<BN>::kTotal, stream>>>(*ma, *mw, M, N, K, amap, epi, k_splits);
     MRMT3_CHECK_LAUNCH();
     return OkStatus();
+}
+
+// D (M x N) = A^T B over R rows; A (R x M, pitch lda) and B (R x N, pitch ldb) row-major bf16.
+// With k_splits > 1, split s stores its partial sums at rows [s*M, (s+1)*M) of the output.
+template <int BN, class Epi>
+Status launch_gemm_tc_mn_bn(const CUtensorMap* ma, const CUtensorMap* mb, int M, int N, int R, const Epi& epi, int n_sms,
+                            cudaStream_t stream, int k_splits) {
+    auto kern = gemm_tn_tcgen05_kernel<BN, Epi, true>;
+    MRMT3_TRY(ensure_dynamic_smem(kern, TcSmem<BN>::kTotal));
+    const int n_tiles = (N / BN) * ceil_div(M, kTcBM) * k_splits;
+    kern<<<std::min(n_tiles, n_sms), kTcThreads, TcSmem<BN>::kTotal, stream>>>(*ma, *mb, M, N, R, ARowMap{nullptr, 1}, epi, k_splits);
+    MRMT3_CHECK_LAUNCH();
+    return OkStatus();
+}
+
+template <class Epi>
+Status launch_gemm_tc_mn(TmaCache& tc, const bf16* A, int lda, int M, const bf16* B, int ldb, int N, int R,
+                         const Epi& epi, cudaStream_t stream, int k_splits = 1) {
+    if (M <= 0 || R <= 0) return OkStatus();
+    if (N % 64 != 0 || k_splits < 1) return Error(2, "gemm_tc_mn: N must be a multiple of 64");
+    static int n_sms = 0;
+    if (!n_sms) {
+        int dev = 0;
+        MRMT3_CUDA_TRY(cudaGetDevice(&dev));
+        MRMT3_CUDA_TRY(cudaDeviceGetAttribute(&n_sms, cudaDevAttrMultiProcessorCount, dev));
+    }
+    const CUtensorMap *pa = nullptr, *mb = nullptr;
+    MRMT3_TRY(tc.get(A, R, M, lda, 64, &pa));
+    const CUtensorMap a_copy = *pa;  // the second lookup may evict the cache
+    const CUtensorMap* ma = &a_copy;
+    MRMT3_TRY(tc.get(B, R, N, ldb, 64, &mb));
+    if (N % 256 == 0) return launch_gemm_tc_mn_bn<256>(ma, mb, M, N, R, epi, n_sms, stream, k_splits);
+    if (N % 192 == 0) return launch_gemm_tc_mn_bn<192>(ma, mb, M, N, R, epi, n_sms, stream, k_splits);
+    if (N % 128 == 0) return launch_gemm_tc_mn_bn<128>(ma, mb, M, N, R, epi, n_sms, stream, k_splits);
+    return launch_gemm_tc_mn_bn<64>(ma, mb, M, N, R, epi, n_sms, stream, k_splits);
 }
 
 template <class Epi>

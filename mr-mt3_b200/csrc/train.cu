@@ -269,7 +269,7 @@ static size_t stash_bytes(int n_enc, int n_dec, int n_mem_layers, size_t Me, siz
         size_t b = M * kDModel * 4 * (dec ? 3 : 2) + M * kDModel * 2 * (dec ? 3 : 2) + M * 3 * kInner * 2 +
                    M * kInner * 2 * (dec ? 3 : 1) + M * 2 * kDFF * 2 + M * kDFF * 2 + (size_t)B * kHeads * T * 4 * (dec ? 2 : 1);
         if (drop) b += keep_bytes(B, T, T) + (dec ? keep_bytes(B, T, tk) : 0);
-        return b + 24 * 256;
+        return b + 32 * 256;
     };
     return n_enc * layer(Me, kSegFrames, false) + n_dec * layer(Md, L, true) + n_mem_layers * layer(Mm, Lp, false) +
            Me * kDModel * (2 + 4 + 2) + Mm * kDModel * (2 + 4 + 2) + (Me + Mm) * kDModel * 2 +
@@ -538,8 +538,31 @@ Status train_backward(mrmt3_handle* h, float* grad, const float* dlogits_f32, cu
         return OkStatus();
     };
     // dW (N, Kin) fp32 = dY^T . X ; dY (M, N) with pitch ldy, X (M, Kin) with pitch ldx
+    static const bool wgrad_via_transpose = [] {
+        const char* e = getenv("MRMT3_WGRAD_TRANSPOSE");
+        return e && atoi(e) != 0;
+    }();
     auto wgrad = [&](const bf16* dY, int ldy, int N, const bf16* X, int ldx, int Kin, float* dW, size_t M) -> Status {
-        const size_t mp = (M + 63) & ~size_t(63);
+        // the output has only (N / 128) x (Kin / BN) tiles: split the long reduction over the SMs
+        const int bn = Kin % 256 == 0 ? 256 : (Kin % 192 == 0 ? 192 : (Kin % 128 == 0 ? 128 : 64));
+        const int out_tiles = ceil_div(N, 128) * (Kin / bn);
+        const int blocks = (int)((M + 63) / 64);
+        int splits = 1;
+        if (!wgrad_via_transpose) {
+            // both operands straight from their row-major buffers (MN-major tcgen05 operands)
+            while (splits < 16 && out_tiles * splits * 2 <= 160 && splits * 2 <= blocks) splits *= 2;
+            tic("wgrad gemm");
+            if (splits == 1) {
+                RUN(h, launch_gemm_tc_mn(*h->tma, dY, ldy, N, X, ldx, Kin, (int)M, EpiStoreF32{dW, Kin}, s));
+            } else {
+                RUN(h, launch_gemm_tc_mn(*h->tma, dY, ldy, N, X, ldx, Kin, (int)M, EpiStoreF32{wpart, Kin}, s, splits));
+                RUN(h, launch_reduce_splits(wpart, dW, (size_t)N * Kin, splits, s));
+            }
+            toc();
+            return OkStatus();
+        }
+        // MRMT3_WGRAD_TRANSPOSE=1: the earlier route, K-major operands through explicit transposes
+        const size_t mp = (size_t)blocks * 64;
         if (mp != M) {
             MRMT3_CUDA_TRY(cudaMemset2DAsync(yT + M, mp * 2, 0, (mp - M) * 2, N, s));
             MRMT3_CUDA_TRY(cudaMemset2DAsync(xT + M, mp * 2, 0, (mp - M) * 2, Kin, s));
@@ -549,11 +572,7 @@ Status train_backward(mrmt3_handle* h, float* grad, const float* dlogits_f32, cu
         RUN(h, launch_transpose_bf16(X, ldx, xT, (int)mp, (int)M, Kin, s));
         toc();
         tic("wgrad gemm");
-        // the output has only (N / 128) x (Kin / BN) tiles: split the long reduction over the SMs
-        const int bn = Kin % 256 == 0 ? 256 : (Kin % 192 == 0 ? 192 : (Kin % 128 == 0 ? 128 : 64));
-        const int out_tiles = ceil_div(N, 128) * (Kin / bn);
-        int splits = 1;
-        while (splits < 16 && out_tiles * splits * 2 <= 160 && ((int)(mp / 64) % (splits * 2)) == 0) splits *= 2;
+        while (splits < 16 && out_tiles * splits * 2 <= 160 && (blocks % (splits * 2)) == 0) splits *= 2;
         if (splits == 1) {
             RUN(h, launch_gemm_tc(*h->tma, yT, (int)mp, N, id, xT, (int)mp, N, Kin, (int)mp, EpiStoreF32{dW, Kin}, s));
         } else {
