@@ -195,7 +195,9 @@ int mrmt3_memory_block(mrmt3_handle* h, const int64_t* prev_ids, int B, int Lp, 
  *                        order: element (r, c) at flat[offset + ((r*row_mul + row_off)*cols + c)]
  *   mrmt3_train_forward  mel (B,256,512) fp32, decoder_input_ids / labels (B,L) int64, for
  *                        V2WithPrev also targets_prev (B,Lp) int64 with -100 already replaced by
- *                        pad (else NULL, 0) -> logits_out (B,L,vocab) fp32, mean loss in *loss_host
+ *                        pad (else NULL, 0) -> logits_out (B,L,vocab) fp32, mean loss in *loss_host;
+ *                        the label count and the loss are reduced on the device: loss_host != NULL
+ *                        costs the call's only stream synchronisation, NULL keeps it asynchronous
  *   mrmt3_train_backward gradient w.r.t. every trainable tensor -> grad_flat (fp32): of the built-in
  *                        loss when dlogits == NULL, else back-propagates the caller's dlogits
  *                        (B,L,vocab) fp32 (torch autograd over the logits, any loss)

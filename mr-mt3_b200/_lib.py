@@ -339,8 +339,9 @@ class Engine:
         packed = flat[off:off + ((rows - 1) * mul + ro + 1) * cols].view(-1, cols)
         return packed[ro::mul][:rows]
 
-    def train_forward(self, inputs, decoder_input_ids, labels, targets_prev=None):
-        """-> (logits (B, L, V) fp32, mean cross-entropy over labels != -100)."""
+    def train_forward(self, inputs, decoder_input_ids, labels, targets_prev=None, want_loss=True):
+        """-> (logits (B, L, V) fp32, mean cross-entropy over labels != -100).  Fetching the loss is the
+        forward's only host synchronisation; `want_loss=False` returns None for it and stays asynchronous."""
         x = self._mel(inputs)
         ids = decoder_input_ids.to(self.device, torch.int64).contiguous()
         lab = labels.to(self.device, torch.int64).contiguous()
@@ -353,8 +354,9 @@ class Engine:
         loss = ctypes.c_float(0.0)
         with torch.cuda.device(self.device):
             self._check(self._lib.mrmt3_train_forward(self._h, _ptr(x), B, _ptr(ids), _ptr(lab), L, _ptr(prev), Lp,
-                                                      _ptr(logits), ctypes.byref(loss), _stream()))
-        return logits, float(loss.value)
+                                                      _ptr(logits), ctypes.byref(loss) if want_loss else None,
+                                                      _stream()))
+        return logits, (float(loss.value) if want_loss else None)
 
     def train_backward(self, grad=None, dlogits=None):
         """Gradient into a flat fp32 tensor (allocated if None): of the last train_forward's built-in

@@ -65,6 +65,7 @@ struct TrainState {
     unsigned long long drop_seed = 0, drop_seed_used = 0;
     int drop_sites = 0x1ff;  // bit i = site i enabled (tests isolate one site at a time)
     float* row_loss = nullptr;
+    float* loss_pinned = nullptr;  // pinned landing spot of the loss scalar
     const long long* dec_ids = nullptr;
     DeviceBuffer ids_copy;
 };
@@ -102,6 +103,7 @@ void train_destroy(mrmt3_handle* h) {
     if (!t) return;
     t->master.release(); t->m.release(); t->v.release(); t->wt_arena.release();
     t->stash.release(); t->scratch.release(); t->ids_copy.release(); t->prev_copy.release();
+    if (t->loss_pinned) cudaFreeHost(t->loss_pinned);
     delete t;
     h->train = nullptr;
 }
@@ -450,19 +452,17 @@ Status train_forward(mrmt3_handle* h, const float* mel, int B, const long long* 
     t->dlogits = bp.take<bf16>(Md * kVocab);
     t->row_loss = bp.take<float>(Md);
     if (bp.used > bp.cap) return Error(2, "internal: activation stash overflow");
-    std::vector<long long> lab(Md);
-    MRMT3_CUDA_TRY(cudaMemcpyAsync(lab.data(), labels, Md * sizeof(long long), cudaMemcpyDeviceToHost, s));
-    MRMT3_CUDA_TRY(cudaStreamSynchronize(s));
-    size_t count = 0;
-    for (auto v : lab) count += v >= 0;
-    const float inv = count ? 1.0f / (float)count : 0.f;
-    RUN(h, launch_xent(logits_out, labels, (int)Md, kVocab, inv, t->row_loss, t->dlogits, s));
-    std::vector<float> rl(Md);
-    MRMT3_CUDA_TRY(cudaMemcpyAsync(rl.data(), t->row_loss, Md * 4, cudaMemcpyDeviceToHost, s));
-    MRMT3_CUDA_TRY(cudaStreamSynchronize(s));
-    double sum = 0;
-    for (auto v : rl) sum += v;
-    if (loss_host) *loss_host = (float)(sum * inv);
+    float* scal = bp.take<float>(2);
+    if (bp.used > bp.cap) return Error(2, "internal: activation stash overflow");
+    RUN(h, launch_xent(logits_out, labels, (int)Md, kVocab, scal, t->row_loss, t->dlogits, s));
+    h->launches += 2;
+    // the only host round trip of the forward, and only when the caller wants the number now
+    if (loss_host) {
+        if (!t->loss_pinned) MRMT3_CUDA_TRY(cudaMallocHost(&t->loss_pinned, sizeof(float)));
+        MRMT3_CUDA_TRY(cudaMemcpyAsync(t->loss_pinned, scal + 1, sizeof(float), cudaMemcpyDeviceToHost, s));
+        MRMT3_CUDA_TRY(cudaStreamSynchronize(s));
+        *loss_host = *t->loss_pinned;
+    }
     return OkStatus();
 }
 

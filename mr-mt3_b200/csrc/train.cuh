@@ -6,7 +6,7 @@
 
 namespace mrmt3 {
 
-Status launch_xent(const float* logits, const long long* labels, int rows, int V, float inv_count,
+Status launch_xent(const float* logits, const long long* labels, int rows, int V, float* scal /* [1/count, mean loss] */,
                    float* row_loss, bf16* dlogits, cudaStream_t s);
 Status launch_rmsnorm_bwd(const float* x, const float* g, float eps, const bf16* dy, int rows, float* dres,
                           bf16* dres_bf16, float* dg, cudaStream_t s);

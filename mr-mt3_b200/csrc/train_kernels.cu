@@ -19,10 +19,42 @@
 namespace mrmt3 {
 
 // ---------------------------------------------------------------------------------------------
-// cross-entropy: one warp per row of V logits
+// cross-entropy, all on the device so that the forward needs no host round trip:
+//   scal[0] = 1 / #(labels != ignore_index), row losses + logits gradient, scal[1] = mean loss
+__global__ void __launch_bounds__(1024)
+    xent_count_kernel(const long long* __restrict__ labels, int rows, float* __restrict__ scal) {
+    __shared__ int part[32];
+    int c = 0;
+    for (int i = threadIdx.x; i < rows; i += 1024) c += labels[i] >= 0;
+    c = (int)warp_sum((float)c);  // <= 32 * ceil(rows / 1024): exact in fp32 for any batch the stash can hold
+    if ((threadIdx.x & 31) == 0) part[threadIdx.x >> 5] = c;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        int n = 0;
+        for (int w = 0; w < 32; ++w) n += part[w];
+        scal[0] = n ? 1.0f / (float)n : 0.f;
+    }
+}
+
+__global__ void __launch_bounds__(1024)
+    xent_mean_kernel(const float* __restrict__ row_loss, int rows, float* __restrict__ scal) {
+    __shared__ double part[1024];
+    double a = 0.0;
+    for (int i = threadIdx.x; i < rows; i += 1024) a += (double)row_loss[i];
+    part[threadIdx.x] = a;
+    __syncthreads();
+    for (int w = 512; w > 0; w >>= 1) {  // fixed tree: the same bits every run
+        if ((int)threadIdx.x < w) part[threadIdx.x] += part[threadIdx.x + w];
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) scal[1] = (float)(part[0] * (double)scal[0]);
+}
+
+// one warp per row of V logits
 __global__ void __launch_bounds__(256)
     xent_kernel(const float* __restrict__ logits, const long long* __restrict__ labels, int rows, int V,
-                float inv_count, float* __restrict__ row_loss, bf16* __restrict__ dlogits) {
+                const float* __restrict__ scal, float* __restrict__ row_loss, bf16* __restrict__ dlogits) {
+    const float inv_count = scal[0];
     const int row = blockIdx.x * 8 + (threadIdx.x >> 5);
     const int lane = threadIdx.x & 31;
     if (row >= rows) return;
@@ -50,10 +82,14 @@ __global__ void __launch_bounds__(256)
     }
 }
 
-Status launch_xent(const float* logits, const long long* labels, int rows, int V, float inv_count,
+Status launch_xent(const float* logits, const long long* labels, int rows, int V, float* scal,
                    float* row_loss, bf16* dlogits, cudaStream_t s) {
     if (rows <= 0) return OkStatus();
-    xent_kernel<<<ceil_div(rows, 8), 256, 0, s>>>(logits, labels, rows, V, inv_count, row_loss, dlogits);
+    xent_count_kernel<<<1, 1024, 0, s>>>(labels, rows, scal);
+    MRMT3_CHECK_LAUNCH();
+    xent_kernel<<<ceil_div(rows, 8), 256, 0, s>>>(logits, labels, rows, V, scal, row_loss, dlogits);
+    MRMT3_CHECK_LAUNCH();
+    xent_mean_kernel<<<1, 1024, 0, s>>>(row_loss, rows, scal);
     MRMT3_CHECK_LAUNCH();
     return OkStatus();
 }
@@ -533,7 +569,8 @@ __device__ __forceinline__ void bwd_zero(float (&c)[8][4]) {
 //   S = Q K^T, P = exp2(S log2e - lse2[row]), dP = dO V^T, dS = P * (dP - delta[row]), dQ += dS K
 // K/V tiles are double-buffered: once the Q / dO fragments are in registers their shared-memory
 // tiles become the second stage, so the next tile's cp.async overlaps this tile's mma.
-__global__ void __launch_bounds__(128)
+template <int CTAS>  // resident CTAs per SM the register budget is cut for (2: 255, 3: 168 registers)
+__global__ void __launch_bounds__(128, CTAS)
     attn_bwd_dq_kernel(AttnBwdParams p) {
     __shared__ __align__(128) bf16 sA[2][kBwdT * kDKV];  // stage s: K tile   (stage 1 holds Q first)
     __shared__ __align__(128) bf16 sB[2][kBwdT * kDKV];  // stage s: V tile   (stage 1 holds dO first)
@@ -602,14 +639,10 @@ __global__ void __launch_bounds__(128)
         bwd_zero(dp);
         bwd_mma_nt(s, qf, sA[st], lane);
         bwd_mma_nt(dp, dof, sB[st], lane);
-        // dropout factors of this thread's 32 (row, key) elements from the forward's keep bits
-        float fdrop[8][4];
-#pragma unroll
-        for (int ni = 0; ni < 8; ++ni) {
-#pragma unroll
-            for (int r = 0; r < 4; ++r)
-                fdrop[ni][r] = !p.drop.on() || ((kb[r >> 1] >> (2 * ni + (r & 1))) & 1u) ? fscale : 0.f;
-        }
+        // dropout factor of element (ni, r) from the forward's keep bits
+        auto fdrop = [&](int ni, int r) -> float {
+            return !p.drop.on() || ((kb[r >> 1] >> (2 * ni + (r & 1))) & 1u) ? fscale : 0.f;
+        };
         if (pass == 0) {
 #pragma unroll
             for (int ni = 0; ni < 8; ++ni) {
@@ -619,7 +652,7 @@ __global__ void __launch_bounds__(128)
                     const int row = row_lo + ((r >> 1) << 3);
                     const bool ok = key < p.Tk && (!p.causal || key <= row + p.causal_offset);
                     if (ok)
-                        dl[r >> 1] += exp2f(s[ni][r] * kLog2e - lse[r >> 1]) * dp[ni][r] * fdrop[ni][r];
+                        dl[r >> 1] += exp2f(s[ni][r] * kLog2e - lse[r >> 1]) * dp[ni][r] * fdrop(ni, r);
                 }
             }
             if (kt == n_kt - 1) {
@@ -641,7 +674,7 @@ __global__ void __launch_bounds__(128)
                     const bool ok = key < p.Tk && (!p.causal || key <= row + p.causal_offset);
                     const float pr = ok ? exp2f(s[ni][r] * kLog2e - lse[r >> 1]) : 0.f;
                     // dropout sits between softmax and P V: dP = dP' * m / (1 - p)
-                    const float dpe = dp[ni][r] * fdrop[ni][r];
+                    const float dpe = dp[ni][r] * fdrop(ni, r);
                     s[ni][r] = pr * (dpe - dl[r >> 1]);  // dS
                 }
             }
@@ -667,7 +700,8 @@ __global__ void __launch_bounds__(128)
 // (rows = keys):  S^T = K Q^T, P^T = exp2(S^T log2e - lse2[col]), dV += P^T dO,
 //                 dP^T = V dO^T, dS^T = P^T * (dP^T - delta[col]), dK += dS^T Q
 // Q / dO tiles are double-buffered the same way (the K / V tiles become stage 1).
-__global__ void __launch_bounds__(128)
+template <int CTAS>
+__global__ void __launch_bounds__(128, CTAS)
     attn_bwd_dkv_kernel(AttnBwdParams p) {
     __shared__ __align__(128) bf16 sA[2][kBwdT * kDKV];  // stage s: Q tile   (stage 1 holds K first)
     __shared__ __align__(128) bf16 sB[2][kBwdT * kDKV];  // stage s: dO tile  (stage 1 holds V first)
@@ -785,9 +819,22 @@ __global__ void __launch_bounds__(128)
 
 Status launch_attn_bwd(const AttnBwdParams& p, int batch, cudaStream_t s) {
     if (batch <= 0 || p.Tq <= 0 || p.Tk <= 0) return OkStatus();
-    attn_bwd_dq_kernel<<<dim3(ceil_div(p.Tq, kBwdT), kHeads, batch), 128, 0, s>>>(p);
-    MRMT3_CHECK_LAUNCH();
-    attn_bwd_dkv_kernel<<<dim3(ceil_div(p.Tk, kBwdT), kHeads, batch), 128, 0, s>>>(p);
+    // the kernels wait on mma.sync latency with few warps per scheduler: three CTAs per SM at 168
+    // registers (a few hundred bytes of spills) against two at 255; MRMT3_ATTN_BWD_CTAS=2 for A/B
+    static const int ctas = [] {
+        const char* e = getenv("MRMT3_ATTN_BWD_CTAS");
+        return e && atoi(e) == 2 ? 2 : 3;
+    }();
+    const dim3 gq(ceil_div(p.Tq, kBwdT), kHeads, batch), gk(ceil_div(p.Tk, kBwdT), kHeads, batch);
+    if (ctas == 3) {
+        attn_bwd_dq_kernel<3><<<gq, 128, 0, s>>>(p);
+        MRMT3_CHECK_LAUNCH();
+        attn_bwd_dkv_kernel<3><<<gk, 128, 0, s>>>(p);
+    } else {
+        attn_bwd_dq_kernel<2><<<gq, 128, 0, s>>>(p);
+        MRMT3_CHECK_LAUNCH();
+        attn_bwd_dkv_kernel<2><<<gk, 128, 0, s>>>(p);
+    }
     MRMT3_CHECK_LAUNCH();
     return OkStatus();
 }

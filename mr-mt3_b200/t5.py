@@ -159,7 +159,7 @@ class _TrainForward(torch.autograd.Function):
         p = float(getattr(model.config, "dropout_rate", 0.0) or 0.0)
         eng.train_set_dropout(p, int(torch.randint(0, 2 ** 62, (1,)).item()) if p > 0 else 0)
         ignore = torch.full_like(decoder_input_ids, -100)
-        logits, _ = eng.train_forward(inputs, decoder_input_ids, ignore, targets_prev)
+        logits, _ = eng.train_forward(inputs, decoder_input_ids, ignore, targets_prev, want_loss=False)
         ctx.model = model
         return logits
 
