@@ -83,11 +83,10 @@ __device__ __forceinline__ uint64_t tc_smem_desc_mn(uint32_t smem_addr, uint32_t
     return d;
 }
 
-// instruction descriptor: D = f32, A = B = bf16, M = 128, N = BN; both operands K-major, or (mn)
-// both MN-major (bits 15 / 16)
-__host__ __device__ constexpr uint32_t tc_idesc(int bn, bool mn = false) {
-    return (1u << 4) | (1u << 7) | (1u << 10) | (mn ? (3u << 15) : 0u) | ((uint32_t)(bn >> 3) << 17) |
-           ((uint32_t)(kTcBM >> 4) << 24);
+// instruction descriptor: D = f32, A = B = bf16, M = 128, N = BN; bit 15 / 16 = A / B is MN-major
+__host__ __device__ constexpr uint32_t tc_idesc(int bn, bool a_mn = false, bool b_mn = false) {
+    return (1u << 4) | (1u << 7) | (1u << 10) | (a_mn ? (1u << 15) : 0u) | (b_mn ? (1u << 16) : 0u) |
+           ((uint32_t)(bn >> 3) << 17) | ((uint32_t)(kTcBM >> 4) << 24);
 }
 
 // ---- 8-wide epilogue stores --------------------------------------------------------------------
@@ -156,16 +155,19 @@ struct TcSmem {
 // accumulator is double-buffered in TMEM: the epilogue warps drain tile i while the MMA warp
 // already accumulates tile i + 1.
 //
-// MN = true is the weight-gradient form D[m, n] = sum_r A[r, m] B[r, n] on ROW-major A (R x M) and
-// B (R x N) -- both operands MN-major, so neither has to be transposed in memory first.  K is then
-// the number of reduction rows R (any value: TMA zero-fills rows past the end) and the k ranges of
-// the splits are ceil(ceil(R / 64) / k_splits) blocks each.
-template <int BN, class Epi, bool MN = false>
+// MODE 0: D = A W^T, both operands K-major (A (M x K), W (N x K) row-major).
+// MODE 1, the weight-gradient form D[m, n] = sum_r A[r, m] B[r, n] on ROW-major A (R x M) and
+// B (R x N): both operands MN-major, so neither has to be transposed in memory first.
+// MODE 2, the data-gradient form D = A B on row-major A (M x K) and B (K x N): A K-major, B MN-major.
+// In modes 1 and 2 K is the number of reduction rows (any value: TMA zero-fills past the end) and
+// the k ranges of the splits are ceil(ceil(K / 64) / k_splits) blocks each.
+template <int BN, class Epi, int MODE = 0>
 __global__ void __launch_bounds__(kTcThreads, 1)
     gemm_tn_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_w,
                            int M, int N, int K, ARowMap amap, Epi epi, int k_splits) {
     using S = TcSmem<BN>;
     constexpr int kStages = S::kStages;
+    constexpr bool MN = MODE != 0, kAMn = MODE == 1, kBMn = MODE != 0;
     extern __shared__ unsigned char tc_smem_raw[];
     const uint32_t raw = smem_u32(tc_smem_raw);
     const uint32_t base = (raw + 1023u) & ~1023u;                 // SWIZZLE_128B tiles need 1024-B alignment
@@ -225,25 +227,28 @@ __global__ void __launch_bounds__(kTcThreads, 1)
                     mbar_wait(bar_empty + s * 8, ((it / kStages) & 1) ^ 1);
                     mbar_expect_tx(bar_full + s * 8, S::kStageBytes);
                     const uint32_t sa = base + s * S::kStageBytes;
-                    if constexpr (MN) {
-                        constexpr int kBox = 64 * kTcBK * 2;  // 64 reduction rows x 64 columns
-                        const int r0 = (kb0 + kb) * kTcBK;
+                    constexpr int kBox = 64 * kTcBK * 2;  // MN-major: 64 reduction rows x 64 columns
+                    const int r0 = (kb0 + kb) * kTcBK;
+                    if constexpr (kAMn) {
 #pragma unroll
                         for (int j = 0; j < kTcBM / 64; ++j)
                             tma_load_2d(sa + j * kBox, &tmap_a, m0 + 64 * j, r0, bar_full + s * 8);
+                    } else {
+                        tma_load_2d(sa, &tmap_a, r0, arow, bar_full + s * 8);
+                    }
+                    if constexpr (kBMn) {
 #pragma unroll
                         for (int j = 0; j < BN / 64; ++j)
                             tma_load_2d(sa + S::kABytes + j * kBox, &tmap_w, n0 + 64 * j, r0, bar_full + s * 8);
                     } else {
-                        tma_load_2d(sa, &tmap_a, (kb0 + kb) * kTcBK, arow, bar_full + s * 8);
-                        tma_load_2d(sa + S::kABytes, &tmap_w, (kb0 + kb) * kTcBK, n0, bar_full + s * 8);
+                        tma_load_2d(sa + S::kABytes, &tmap_w, r0, n0, bar_full + s * 8);
                     }
                 }
             }
         }
     } else if (warp == 1) {
         if (lane == 0) {
-            constexpr uint32_t idesc = tc_idesc(BN, MN);
+            constexpr uint32_t idesc = tc_idesc(BN, kAMn, kBMn);
             int it = 0, i = 0;
             for (int t = blockIdx.x; t < n_tiles; t += gridDim.x, ++i) {
                 const int buf = i & 1;
@@ -255,15 +260,15 @@ __global__ void __launch_bounds__(kTcThreads, 1)
                     mbar_wait(bar_full + s * 8, (it / kStages) & 1);
                     tc_fence_after();
                     const uint32_t sa = base + s * S::kStageBytes;
-                    const uint64_t da = MN ? tc_smem_desc_mn(sa, 64 * kTcBK * 2) : tc_smem_desc(sa);
-                    const uint64_t dw = MN ? tc_smem_desc_mn(sa + S::kABytes, 64 * kTcBK * 2) : tc_smem_desc(sa + S::kABytes);
+                    const uint64_t da = kAMn ? tc_smem_desc_mn(sa, 64 * kTcBK * 2) : tc_smem_desc(sa);
+                    const uint64_t dw = kBMn ? tc_smem_desc_mn(sa + S::kABytes, 64 * kTcBK * 2) : tc_smem_desc(sa + S::kABytes);
                     // K-major: advance 16 elements (32 B) along K inside the 128-B swizzle atom, +2
                     // in the 16-byte-granular start-address field; MN-major: 16 reduction rows = two
                     // whole 1024-B atoms, +128
-                    constexpr uint64_t kStep = MN ? 128 : 2;
+                    constexpr uint64_t kStepA = kAMn ? 128 : 2, kStepB = kBMn ? 128 : 2;
 #pragma unroll
                     for (int k = 0; k < kTcBK / 16; ++k)
-                        tc_mma_f16(tacc, da + kStep * k, dw + kStep * k, idesc, (kb | k) != 0);
+                        tc_mma_f16(tacc, da + kStepA * k, dw + kStepB * k, idesc, (kb | k) != 0);
                     tc_commit(bar_empty + s * 8);  // frees the ring slot once the MMAs have read it
                 }
                 tc_commit(bar_acc_full + buf * 8);  // accumulator of this tile complete
@@ -325,10 +330,10 @@ Status launch_gemm_tc_bn(TmaCache& tc, const CUtensorMap* ma, const bf16* W, int
 
 // D (M x N) = A^T B over R rows; A (R x M, pitch lda) and B (R x N, pitch ldb) row-major bf16.
 // With k_splits > 1, split s stores its partial sums at rows [s*M, (s+1)*M) of the output.
-template <int BN, class Epi>
+template <int BN, int MODE, class Epi>
 Status launch_gemm_tc_mn_bn(const CUtensorMap* ma, const CUtensorMap* mb, int M, int N, int R, const Epi& epi, int n_sms,
                             cudaStream_t stream, int k_splits) {
-    auto kern = gemm_tn_tcgen05_kernel<BN, Epi, true>;
+    auto kern = gemm_tn_tcgen05_kernel<BN, Epi, MODE>;
     MRMT3_TRY(ensure_dynamic_smem(kern, TcSmem<BN>::kTotal));
     const int n_tiles = (N / BN) * ceil_div(M, kTcBM) * k_splits;
     kern<<<std::min(n_tiles, n_sms), kTcThreads, TcSmem<BN>::kTotal, stream>>>(*ma, *mb, M, N, R, ARowMap{nullptr, 1}, epi, k_splits);
@@ -352,10 +357,34 @@ Status launch_gemm_tc_mn(TmaCache& tc, const bf16* A, int lda, int M, const bf16
     const CUtensorMap a_copy = *pa;  // the second lookup may evict the cache
     const CUtensorMap* ma = &a_copy;
     MRMT3_TRY(tc.get(B, R, N, ldb, 64, &mb));
-    if (N % 256 == 0) return launch_gemm_tc_mn_bn<256>(ma, mb, M, N, R, epi, n_sms, stream, k_splits);
-    if (N % 192 == 0) return launch_gemm_tc_mn_bn<192>(ma, mb, M, N, R, epi, n_sms, stream, k_splits);
-    if (N % 128 == 0) return launch_gemm_tc_mn_bn<128>(ma, mb, M, N, R, epi, n_sms, stream, k_splits);
-    return launch_gemm_tc_mn_bn<64>(ma, mb, M, N, R, epi, n_sms, stream, k_splits);
+    if (N % 256 == 0) return launch_gemm_tc_mn_bn<256, 1>(ma, mb, M, N, R, epi, n_sms, stream, k_splits);
+    if (N % 192 == 0) return launch_gemm_tc_mn_bn<192, 1>(ma, mb, M, N, R, epi, n_sms, stream, k_splits);
+    if (N % 128 == 0) return launch_gemm_tc_mn_bn<128, 1>(ma, mb, M, N, R, epi, n_sms, stream, k_splits);
+    return launch_gemm_tc_mn_bn<64, 1>(ma, mb, M, N, R, epi, n_sms, stream, k_splits);
+}
+
+// D (M x N) = A B; A (M x K, pitch lda) and B (K x N, pitch ldb) row-major bf16 (the data gradient
+// dX = dY W with the weight as stored, no W^T copy)
+template <class Epi>
+Status launch_gemm_tc_nn(TmaCache& tc, const bf16* A, int lda, int M, const bf16* B, int ldb, int N, int K,
+                         const Epi& epi, cudaStream_t stream) {
+    if (M <= 0 || K <= 0) return OkStatus();
+    if (N % 64 != 0) return Error(2, "gemm_tc_nn: N must be a multiple of 64");
+    static int n_sms = 0;
+    if (!n_sms) {
+        int dev = 0;
+        MRMT3_CUDA_TRY(cudaGetDevice(&dev));
+        MRMT3_CUDA_TRY(cudaDeviceGetAttribute(&n_sms, cudaDevAttrMultiProcessorCount, dev));
+    }
+    const CUtensorMap *pa = nullptr, *mb = nullptr;
+    MRMT3_TRY(tc.get(A, M, K, lda, kTcBM, &pa));
+    const CUtensorMap a_copy = *pa;
+    const CUtensorMap* ma = &a_copy;
+    MRMT3_TRY(tc.get(B, K, N, ldb, 64, &mb));
+    if (N % 256 == 0) return launch_gemm_tc_mn_bn<256, 2>(ma, mb, M, N, K, epi, n_sms, stream, 1);
+    if (N % 192 == 0) return launch_gemm_tc_mn_bn<192, 2>(ma, mb, M, N, K, epi, n_sms, stream, 1);
+    if (N % 128 == 0) return launch_gemm_tc_mn_bn<128, 2>(ma, mb, M, N, K, epi, n_sms, stream, 1);
+    return launch_gemm_tc_mn_bn<64, 2>(ma, mb, M, N, K, epi, n_sms, stream, 1);
 }
 
 template <class Epi>

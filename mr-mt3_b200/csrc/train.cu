@@ -3,13 +3,13 @@
 // ignore_index -100, hand-written backward through every op of the path, AdamW on fp32 masters.
 // The gradient lives in ONE flat fp32 buffer owned by the caller (packed-weight order), so data
 // parallel training is a single all-reduce of that buffer between `train_backward` and
-// `train_apply`.  Dropout is not applied (the parity oracle is the reference in
-// eval()-mode arithmetic).  Models: plain MT3 (models/t5.py) and MR-MT3 V2WithPrev
+// `train_apply`.  Dropout at the reference's sites is a counter-based hash the oracle
+// mirrors (mrmt3_train_set_dropout; p = 0 is the reference's eval()-mode arithmetic).  Models: plain MT3 (models/t5.py) and MR-MT3 V2WithPrev
 // (models/t5_segmem_v2_with_prev.py:60-153: memory block appended to the encoder output).
 //
-// GEMMs reuse the TN tcgen05 kernel:
-//   dgrad  dX[M,Kin] = dY[M,N] . W[N,Kin]        = A(dY) . (W^T)^T      with W^T[Kin,N] re-made per step
-//   wgrad  dW[N,Kin] = dY^T[N,M] . X[M,Kin]      = A(dY^T) . (X^T)^T    with explicit transposes
+// GEMMs are the tcgen05 kernel with the operands as they lie in memory (no transposed copies):
+//   dgrad  dX[M,Kin] = dY[M,N] . W[N,Kin]        A = dY K-major, B = W as stored, MN-major (gemm_tcgen05 MODE 2)
+//   wgrad  dW[N,Kin] = dY^T[N,M] . X[M,Kin]      A = dY, B = X, both MN-major (MODE 1), split over the rows
 #include <algorithm>
 #include <cmath>
 #include <cstring>
@@ -525,17 +525,30 @@ Status train_backward(mrmt3_handle* h, float* grad, const float* dlogits_f32, cu
         if (prof) cudaEventRecord(recs.back().b, s);
     };
     auto G = [&](int slot) { return grad + t->slots[slot].off; };
-    tic("W^T copies");
-    for (auto& sl : t->slots)
-        if (sl.w16) RUN(h, launch_transpose_bf16(sl.w16, sl.cols, sl.wt, sl.rows, sl.rows, sl.cols, s));
-    toc();
-    // dX (M, Kin) bf16 = dY (M, N) . W (N, Kin)
-    auto dgrad = [&](const bf16* dY, int N, int slot, bf16* dX, size_t M) -> Status {
+    // dX (M, Kin) = dY (M, N) . W (N, Kin): the weight as stored is the MN-major B operand of the
+    // tcgen05 GEMM; MRMT3_DGRAD_WT=1 selects the earlier route through per-step W^T copies
+    static const bool dgrad_via_wt = [] {
+        const char* e = getenv("MRMT3_DGRAD_WT");
+        return e && atoi(e) != 0;
+    }();
+    if (dgrad_via_wt) {
+        tic("W^T copies");
+        for (auto& sl : t->slots)
+            if (sl.w16) RUN(h, launch_transpose_bf16(sl.w16, sl.cols, sl.wt, sl.rows, sl.rows, sl.cols, s));
+        toc();
+    }
+    auto dgrad_to = [&](const bf16* dY, int N, int slot, auto epi, size_t M) -> Status {
         const ParamSlot& sl = t->slots[slot];
         tic("dgrad");
-        RUN(h, launch_gemm_tc(*h->tma, dY, N, M, id, sl.wt, N, (int)M, sl.cols, N, EpiStoreBf16{dX, sl.cols}, s));
+        if (dgrad_via_wt)
+            RUN(h, launch_gemm_tc(*h->tma, dY, N, M, id, sl.wt, N, (int)M, sl.cols, N, epi, s));
+        else
+            RUN(h, launch_gemm_tc_nn(*h->tma, dY, N, (int)M, sl.w16, sl.cols, sl.cols, N, epi, s));
         toc();
         return OkStatus();
+    };
+    auto dgrad = [&](const bf16* dY, int N, int slot, bf16* dX, size_t M) -> Status {
+        return dgrad_to(dY, N, slot, EpiStoreBf16{dX, t->slots[slot].cols}, M);
     };
     // dW (N, Kin) fp32 = dY^T . X ; dY (M, N) with pitch ldy, X (M, Kin) with pitch ldx
     static const bool wgrad_via_transpose = [] {
@@ -700,9 +713,7 @@ Status train_backward(mrmt3_handle* h, float* grad, const float* dlogits_f32, cu
         // stack input = segmem_proj(Emb[prev]) + PE
         MRMT3_TRY(cast_dH(Mm, mk(2, 0, kSiteInput)));
         MRMT3_TRY(wgrad(dHb, kDModel, kDModel, t->mem_emb16, kDModel, kDModel, G(t->segmem_proj), Mm));
-        const ParamSlot& sp = t->slots[t->segmem_proj];
-        RUN(h, launch_gemm_tc(*h->tma, dHb, kDModel, Mm, id, sp.wt, kDModel, (int)Mm, kDModel, kDModel,
-                              EpiStoreF32{dH, kDModel}, s));
+        MRMT3_TRY(dgrad_to(dHb, kDModel, t->segmem_proj, EpiStoreF32{dH, kDModel}, Mm));
         tic("embedding bwd");
         RUN(h, launch_embed_bwd(t->prev_ids, dH, G(t->emb), (int)Mm, s));
         toc();
