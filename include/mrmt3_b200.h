@@ -206,6 +206,10 @@ int mrmt3_memory_block(mrmt3_handle* h, const int64_t* prev_ids, int B, int Lp, 
  *   mrmt3_train_read_master  flat fp32 copy of the current parameters */
 int mrmt3_train_init(mrmt3_handle* h, int64_t* n_params);
 int mrmt3_train_set_dropout(mrmt3_handle* h, float p, uint64_t seed);
+/* Host only, no GPU, no handle: keep_out[i] = 1 iff flat element i of the tensor `tensor_id`
+ * ((stack << 16) | (layer << 8) | site) survives dropout p under step seed `seed` -- the mask
+ * definition the kernels evaluate, exposed so that CPU tests can pin the oracle's mirror of it. */
+int mrmt3_dropout_keep_host(float p, uint64_t seed, uint32_t tensor_id, int64_t n, uint8_t* keep_out);
 int mrmt3_train_locate(mrmt3_handle* h, const char* name, int64_t* offset, int32_t* rows, int32_t* cols,
                        int32_t* row_mul, int32_t* row_off);
 int mrmt3_train_forward(mrmt3_handle* h, const float* mel, int B, const int64_t* decoder_input_ids,

@@ -60,6 +60,7 @@ _PROTOTYPES = {
                                        _c_void_p]),
     "mrmt3_train_init": (_c_int, [_c_void_p, ctypes.POINTER(_c_i64)]),
     "mrmt3_train_set_dropout": (_c_int, [_c_void_p, ctypes.c_float, ctypes.c_uint64]),
+    "mrmt3_dropout_keep_host": (_c_int, [ctypes.c_float, ctypes.c_uint64, ctypes.c_uint32, ctypes.c_int64, _c_void_p]),
     "mrmt3_train_locate": (_c_int, [_c_void_p, ctypes.c_char_p, ctypes.POINTER(_c_i64), ctypes.POINTER(ctypes.c_int32),
                                     ctypes.POINTER(ctypes.c_int32), ctypes.POINTER(ctypes.c_int32),
                                     ctypes.POINTER(ctypes.c_int32)]),

@@ -280,6 +280,13 @@ int mrmt3_train_set_dropout(mrmt3_handle* h, float p, uint64_t seed) {
     END_GUARD(h)
 }
 
+int mrmt3_dropout_keep_host(float p, uint64_t seed, uint32_t tensor_id, int64_t n, uint8_t* keep_out) {
+    if (n < 0 || (n > 0 && !keep_out) || !(p >= 0.f && p < 1.f)) return 1;
+    const DropSpec d = make_drop_spec(p, (unsigned long long)seed, tensor_id);
+    for (int64_t i = 0; i < n; ++i) keep_out[i] = drop_factor(d, (unsigned long long)i) != 0.f;
+    return 0;
+}
+
 int mrmt3_train_locate(mrmt3_handle* h, const char* name, int64_t* offset, int32_t* rows, int32_t* cols,
                        int32_t* row_mul, int32_t* row_off) {
     GUARD(h)

@@ -124,7 +124,8 @@ __device__ __forceinline__ float gelu_new(float a) {
 // ---- dropout (fine-tune step) -------------------------------------------------------------------
 // Counter-based: one 64-bit hash of (seed, tensor id, index / 4) yields four 16-bit draws, element
 // `index` is kept iff its draw >= p * 65536.  The backward regenerates every mask instead of storing
-// it, and the CPU oracle mirrors it (oracle/mt3_oracle.py:dropout_keep).  `scale` = 1 / (1 - p);
+// it, and the CPU oracle mirrors it (oracle/mt3_oracle.py:dropout_keep; mrmt3_dropout_keep_host
+// exposes this definition to the CPU tests).  `scale` = 1 / (1 - p);
 // p == 0 disables everything.
 struct DropSpec {
     unsigned long long seed;  // already mixed with the tensor id
@@ -134,6 +135,12 @@ struct DropSpec {
 };
 __host__ __device__ __forceinline__ unsigned long long drop_mix_tid(unsigned long long seed, unsigned int tid) {
     return seed ^ ((unsigned long long)tid * 0x9E3779B97F4A7C15ull);
+}
+// the spec of tensor `tid` under dropout probability p and step seed `seed`
+__host__ __device__ __forceinline__ DropSpec make_drop_spec(float p, unsigned long long seed, unsigned int tid) {
+    if (!(p > 0.f)) return DropSpec{0ull, 0u, 1.f};
+    const float th = p * 65536.0f;
+    return DropSpec{drop_mix_tid(seed, tid), (unsigned int)(th > 65535.f ? 65535.f : th), 1.f / (1.f - p)};
 }
 // the four draws of the aligned group index / 4
 __host__ __device__ __forceinline__ unsigned long long drop_hash4(const DropSpec& d, unsigned long long group) {

@@ -77,9 +77,7 @@ enum { kSiteInput = 1, kSiteSelfProbs = 2, kSiteSelfOut = 3, kSiteFfnInner = 4, 
        kSiteCrossProbs = 7, kSiteCrossOut = 8 };
 static DropSpec drop_spec(const TrainState* t, unsigned long long seed, int stack, int layer, int site) {
     if (t->drop_p <= 0.f || stack == 2 || !((t->drop_sites >> site) & 1)) return DropSpec{0ull, 0u, 1.f};
-    const float th = t->drop_p * 65536.0f;
-    return DropSpec{drop_mix_tid(seed, (unsigned)((stack << 16) | (layer << 8) | site)),
-                    (unsigned int)(th > 65535.f ? 65535.f : th), 1.f / (1.f - t->drop_p)};
+    return make_drop_spec(t->drop_p, seed, (unsigned)((stack << 16) | (layer << 8) | site));
 }
 
 Status train_set_dropout_sites(mrmt3_handle* h, int mask) {

@@ -185,3 +185,27 @@ def test_gradient_allreduce_mean_gloo_world2():
     sh = importlib.import_module("mr-mt3_b200.sharding")
     x = torch.ones(4)
     assert sh.allreduce_mean_(x) is x and float(x.sum()) == 4.0      # not initialised: no-op
+
+
+def test_dropout_mask_definition_equals_oracle_mirror():
+    """The fine-tune step's dropout masks are a counter-based hash evaluated inside the CUDA kernels
+    (csrc/common.cuh:drop_factor); `mrmt3_dropout_keep_host` is the same C++ definition compiled
+    for the host.  The oracle mirrors it in numpy (mt3_oracle.dropout_keep / Dropout): both must
+    agree bit for bit, for every site id, across group boundaries and for ragged lengths."""
+    lib = _lib().load_library()
+    for p, seed, n in [(0.1, 424242, 4099), (0.1, 2 ** 63 + 12345, 17), (0.5, 7, 1000), (0.999, 1, 64), (1e-5, 3, 64)]:
+        drop = O.Dropout(p, seed)
+        for stack, layer, site in [("encoder", 0, "input"), ("decoder", 7, "cross_probs"), ("decoder", 3, "ffn_inner")]:
+            tid = (O.DROP_STACKS[stack] << 16) | (layer << 8) | O.DROP_SITES[site]
+            got = np.zeros(n, dtype=np.uint8)
+            rc = lib.mrmt3_dropout_keep_host(p, seed, tid, n, got.ctypes.data_as(ctypes.c_void_p))
+            assert rc == 0
+            want = (O.dropout_keep(seed, tid, n) >= drop.threshold).astype(np.uint8)
+            np.testing.assert_array_equal(got, want)
+    # the keep rate is 1 - p to within sampling error, and p = 0 keeps everything
+    got = np.zeros(1 << 20, dtype=np.uint8)
+    assert lib.mrmt3_dropout_keep_host(0.1, 99, 65539, got.size, got.ctypes.data_as(ctypes.c_void_p)) == 0
+    assert abs(got.mean() - 0.9) < 2e-3
+    assert lib.mrmt3_dropout_keep_host(0.0, 99, 65539, got.size, got.ctypes.data_as(ctypes.c_void_p)) == 0
+    assert got.all()
+    assert lib.mrmt3_dropout_keep_host(1.0, 99, 65539, 4, got.ctypes.data_as(ctypes.c_void_p)) != 0
