@@ -310,7 +310,7 @@ Status train_forward(mrmt3_handle* h, const float* mel, int B, const long long* 
     // ---- encoder (reference models/t5.py:253-258) ----
     t->mel16 = bp.take<bf16>(Me * kMels);
     RUN(h, launch_cast_bf16(mel, t->mel16, Me * kMels, s));
-    float* H = bp.take<float>(Me * kDModel);  // running residual stream; each layer snapshots what it needs
+    float* H = bp.take<float>(Me * kDModel);  // residual stream: every sublayer writes its output into a fresh buffer
     RUN(h, launch_gemm_tc(*h->tma, t->mel16, kDModel, Me, id, h->proj, kDModel, (int)Me, kDModel, kDModel,
                           EpiPosAdd{H, kDModel, h->pe, kSegFrames, 0}, s));
     auto attn_fwd = [&](const bf16* Q, long qb, int qr, const bf16* K, const bf16* V, long kb, long kh, int kr, bf16* O,
@@ -328,21 +328,16 @@ Status train_forward(mrmt3_handle* h, const float* mel, int B, const long long* 
         RUN(h, launch_attn_full(ap, nb, s));
         return OkStatus();
     };
-    // H += dropout(A . W^T)   (sublayer output)
-    auto out_proj = [&](const bf16* A, int K, const bf16* W, float* Hres, size_t M, DropSpec drop) -> Status {
-        if (drop.on())
-            RUN(h, launch_gemm_tc(*h->tma, A, K, M, id, W, K, (int)M, kDModel, K, EpiResidualDrop{Hres, kDModel, drop}, s));
-        else
-            RUN(h, launch_gemm_tc(*h->tma, A, K, M, id, W, K, (int)M, kDModel, K, EpiResidual{Hres, kDModel}, s));
+    // H' = H + dropout(A . W^T)   (sublayer output) into a fresh buffer: the old H is exactly the
+    // activation the backward needs for this sublayer's norm, so it stays in the stash as it is
+    auto out_proj = [&](const bf16* A, int K, const bf16* W, float*& Hres, size_t M, DropSpec drop) -> Status {
+        float* Hnew = bp.take<float>(M * kDModel);
+        RUN(h, launch_gemm_tc(*h->tma, A, K, M, id, W, K, (int)M, kDModel, K, EpiResidualTo{Hres, Hnew, kDModel, drop}, s));
+        Hres = Hnew;
         return OkStatus();
     };
-    auto snapshot = [&](float* dst, const float* src, size_t n) -> Status {
-        MRMT3_CUDA_TRY(cudaMemcpyAsync(dst, src, n * 4, cudaMemcpyDeviceToDevice, s));
-        return OkStatus();
-    };
-    auto ffn_fwd = [&](const LayerW& Lw, LayerStash& st, float* Hres, size_t M, int stack, int li) -> Status {
-        st.h_mid = bp.take<float>(M * kDModel);
-        MRMT3_TRY(snapshot(st.h_mid, Hres, M * kDModel));
+    auto ffn_fwd = [&](const LayerW& Lw, LayerStash& st, float*& Hres, size_t M, int stack, int li) -> Status {
+        st.h_mid = Hres;
         st.n2 = bp.take<bf16>(M * kDModel);
         st.raw = bp.take<bf16>(M * 2 * kDFF);
         st.ff = bp.take<bf16>(M * kDFF);
@@ -353,10 +348,9 @@ Status train_forward(mrmt3_handle* h, const float* mel, int B, const long long* 
         MRMT3_TRY(out_proj(st.ff, kDFF, Lw.wff, Hres, M, mk(stack, li, kSiteFfnOut)));
         return OkStatus();
     };
-    auto self_fwd = [&](const LayerW& Lw, LayerStash& st, float* Hres, size_t M, int T, int causal, int stack, int li) -> Status {
+    auto self_fwd = [&](const LayerW& Lw, LayerStash& st, float*& Hres, size_t M, int T, int causal, int stack, int li) -> Status {
         const int nb = (int)(M / T);
-        st.h_in = bp.take<float>(M * kDModel);
-        MRMT3_TRY(snapshot(st.h_in, Hres, M * kDModel));
+        st.h_in = Hres;
         st.n1 = bp.take<bf16>(M * kDModel);
         st.qkv = bp.take<bf16>(M * 3 * kInner);
         st.ctx = bp.take<bf16>(M * kInner);
@@ -424,8 +418,7 @@ Status train_forward(mrmt3_handle* h, const float* mel, int B, const long long* 
         const LayerW& Lw = h->dec.layers[li];
         LayerStash& st = t->dec_st[li];
         MRMT3_TRY(self_fwd(Lw, st, Hd, Md, L, 1, 1, li));
-        st.h_mid2 = bp.take<float>(Md * kDModel);
-        MRMT3_TRY(snapshot(st.h_mid2, Hd, Md * kDModel));
+        st.h_mid2 = Hd;
         st.nc = bp.take<bf16>(Md * kDModel);
         st.qc = bp.take<bf16>(Md * kInner);
         st.ctx_c = bp.take<bf16>(Md * kInner);

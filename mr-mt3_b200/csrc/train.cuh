@@ -48,32 +48,37 @@ struct AttnBwdParams {
     const unsigned short* keep;  // its keep bits as the forward saved them (AttnFullParams::keep); required when drop.on()
 };
 
-// H (fp32) += dropout(acc): the sublayer-output dropout of the training forward, index row*ld + col
-struct EpiResidualDrop {
-    float* H;
+// Hout (fp32) = Hin + dropout(acc): the sublayer output of the training forward, mask index
+// row*ld + col.  Out of place, so that the sublayer's input stays behind as the activation the
+// backward needs (no snapshot copy of the residual stream); drop may be off.
+struct EpiResidualTo {
+    const float* Hin;
+    float* Hout;
     int ldh;
     DropSpec drop;
     __device__ __forceinline__ void operator()(int row, int col, float v0, float v1) const {
         const unsigned long long i = (unsigned long long)row * ldh + col;
-        float2* p = reinterpret_cast<float2*>(H + (size_t)row * ldh + col);
-        float2 h = *p;
-        float f0, f1;
-        drop_factor2(drop, i, f0, f1);
+        float2 h = *reinterpret_cast<const float2*>(Hin + (size_t)row * ldh + col);
+        float f0 = 1.f, f1 = 1.f;
+        if (drop.on()) drop_factor2(drop, i, f0, f1);
         h.x += v0 * f0;
         h.y += v1 * f1;
-        *p = h;
+        *reinterpret_cast<float2*>(Hout + (size_t)row * ldh + col) = h;
     }
 };
-// 8 consecutive columns of one row (col % 8 == 0, ldh % 4 == 0): two aligned mask groups, 16-byte RMW
-__device__ __forceinline__ void epi_store8(const EpiResidualDrop& e, int row, int col, const float (&v)[8]) {
-    const unsigned long long g = ((unsigned long long)row * e.ldh + col) >> 2;
-    float f0[4], f1[4];
-    drop_factor4(e.drop, g, f0);
-    drop_factor4(e.drop, g + 1, f1);
-    float4* p = reinterpret_cast<float4*>(e.H + (size_t)row * e.ldh + col);
-    float4 a = p[0], b = p[1];
-    p[0] = make_float4(a.x + v[0] * f0[0], a.y + v[1] * f0[1], a.z + v[2] * f0[2], a.w + v[3] * f0[3]);
-    p[1] = make_float4(b.x + v[4] * f1[0], b.y + v[5] * f1[1], b.z + v[6] * f1[2], b.w + v[7] * f1[3]);
+// 8 consecutive columns of one row (col % 8 == 0, ldh % 4 == 0): two aligned mask groups, 16-byte accesses
+__device__ __forceinline__ void epi_store8(const EpiResidualTo& e, int row, int col, const float (&v)[8]) {
+    float f0[4] = {1.f, 1.f, 1.f, 1.f}, f1[4] = {1.f, 1.f, 1.f, 1.f};
+    if (e.drop.on()) {
+        const unsigned long long g = ((unsigned long long)row * e.ldh + col) >> 2;
+        drop_factor4(e.drop, g, f0);
+        drop_factor4(e.drop, g + 1, f1);
+    }
+    const float4* p = reinterpret_cast<const float4*>(e.Hin + (size_t)row * e.ldh + col);
+    float4* q = reinterpret_cast<float4*>(e.Hout + (size_t)row * e.ldh + col);
+    const float4 a = p[0], b = p[1];
+    q[0] = make_float4(a.x + v[0] * f0[0], a.y + v[1] * f0[1], a.z + v[2] * f0[2], a.w + v[3] * f0[3]);
+    q[1] = make_float4(b.x + v[4] * f1[0], b.y + v[5] * f1[1], b.z + v[6] * f1[2], b.w + v[7] * f1[3]);
 }
 Status launch_attn_bwd(const AttnBwdParams& p, int batch, cudaStream_t s);
 
