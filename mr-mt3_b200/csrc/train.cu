@@ -481,7 +481,7 @@ Status train_backward(mrmt3_handle* h, float* grad, const float* dlogits_f32, cu
     size_t need = Mmax * kDModel * 4 * 2 + Mmax * kDModel * 2 * 2 + Mmax * 2 * kDFF * 2 + Mmax * kDFF * 2 +
                   Mmax * 3 * kInner * 2 + Mmax * kInner * 2 * 2 + Mp * 2 * kDFF * 2 * 2 + Mp * kvN * 2 * 2 +
                   (size_t)16 * 2 * kDFF * kDModel * 4 + Mk * kvN * 2 + (size_t)B * kHeads * std::max(std::max(L, Lp), kSegFrames) * 4 + Mmax * kDModel * 2 +
-                  (1 << 16);
+                  embed_bwd_scratch_bytes((int)Mmax) + (size_t)kNormBwdMaxNorms * kNormBwdMaxParts * kDModel * 4 + (1 << 16);
     MRMT3_TRY(t->scratch.reserve(need));
     Bump bp{reinterpret_cast<char*>(t->scratch.p), 0, t->scratch.cap};
     float* dH = bp.take<float>(Mmax * kDModel);
@@ -498,6 +498,9 @@ Status train_backward(mrmt3_handle* h, float* grad, const float* dlogits_f32, cu
     bf16* dkv = bp.take<bf16>(Mk * kvN);
     bf16* dsplit = bp.take<bf16>(Mmax * kDModel);  // rows of the K/V-input gradient regrouped per consumer
     float* delta = bp.take<float>((size_t)B * kHeads * std::max(std::max(L, Lp), kSegFrames));
+    void* emb_scratch = bp.take<char>(embed_bwd_scratch_bytes((int)Mmax));
+    float* norm_parts = bp.take<float>((size_t)kNormBwdMaxNorms * kNormBwdMaxParts * kDModel);
+    NormDgList norm_list{};
     if (bp.used > bp.cap) return Error(2, "internal: backward scratch overflow");
 
     // optional per-category timing (MRMT3_TRAIN_PROFILE=1): CUDA events around every backward op
@@ -594,7 +597,12 @@ Status train_backward(mrmt3_handle* h, float* grad, const float* dlogits_f32, cu
     };
     auto norm_bwd = [&](const float* x, const float* g, const bf16* dy, size_t M, float* dg) -> Status {
         tic("rmsnorm bwd");
-        RUN(h, launch_rmsnorm_bwd(x, g, eps, dy, (int)M, dH, dHb, dg, s));
+        if (norm_list.n >= kNormBwdMaxNorms) return Error(2, "internal: too many norms in one backward pass");
+        float* part = norm_parts + (size_t)norm_list.n * kNormBwdMaxParts * kDModel;
+        norm_list.dst[norm_list.n] = dg;
+        norm_list.n_parts[norm_list.n] = rmsnorm_bwd_parts((int)M);
+        norm_list.n += 1;
+        RUN(h, launch_rmsnorm_bwd(x, g, eps, dy, (int)M, dH, dHb, part, s));
         toc();
         return OkStatus();
     };
@@ -678,7 +686,8 @@ Status train_backward(mrmt3_handle* h, float* grad, const float* dlogits_f32, cu
     }
     RUN(h, launch_dropout_f32(dH, Md * kDModel, mk(1, 0, kSiteInput), s));
     tic("embedding bwd");
-    RUN(h, launch_embed_bwd(t->dec_ids, dH, G(t->emb), (int)Md, s));
+    RUN(h, launch_embed_bwd(t->dec_ids, dH, G(t->emb), (int)Md, emb_scratch, s));
+    h->launches += 1;
     toc();
 
     // ---- cross K/V projection -> [encoder output ; memory rows] ----
@@ -706,7 +715,8 @@ Status train_backward(mrmt3_handle* h, float* grad, const float* dlogits_f32, cu
         MRMT3_TRY(wgrad(dHb, kDModel, kDModel, t->mem_emb16, kDModel, kDModel, G(t->segmem_proj), Mm));
         MRMT3_TRY(dgrad_to(dHb, kDModel, t->segmem_proj, EpiStoreF32{dH, kDModel}, Mm));
         tic("embedding bwd");
-        RUN(h, launch_embed_bwd(t->prev_ids, dH, G(t->emb), (int)Mm, s));
+        RUN(h, launch_embed_bwd(t->prev_ids, dH, G(t->emb), (int)Mm, emb_scratch, s));
+        h->launches += 1;
         toc();
     } else {
         MRMT3_CUDA_TRY(cudaMemcpyAsync(dsplit, dn, Me * kDModel * 2, cudaMemcpyDeviceToDevice, s));
@@ -723,6 +733,8 @@ Status train_backward(mrmt3_handle* h, float* grad, const float* dlogits_f32, cu
     // proj: h0 = dropout(mel . Wproj^T + PE)
     MRMT3_TRY(cast_dH(Me, mk(0, 0, kSiteInput)));
     MRMT3_TRY(wgrad(dHb, kDModel, kDModel, t->mel16, kMels, kMels, G(t->proj), Me));
+    // norm-weight gradients: the partial rows of every norm of the step, added in a fixed order
+    RUN(h, launch_norm_dg_reduce(norm_list, norm_parts, s));
     if (prof) {
         MRMT3_CUDA_TRY(cudaStreamSynchronize(s));
         std::map<std::string, std::pair<double, int>> agg;

@@ -8,8 +8,19 @@ namespace mrmt3 {
 
 Status launch_xent(const float* logits, const long long* labels, int rows, int V, float* scal /* [1/count, mean loss] */,
                    float* row_loss, bf16* dlogits, cudaStream_t s);
+// the norm-weight gradient is left as rmsnorm_bwd_parts(rows) partial rows in dg_part; after the
+// last norm of the step, launch_norm_dg_reduce adds them up in a fixed order into the gradient
+constexpr int kNormBwdMaxParts = 592;
+constexpr int kNormBwdMaxNorms = 64;
+struct NormDgList {
+    float* dst[kNormBwdMaxNorms];
+    int n_parts[kNormBwdMaxNorms];
+    int n;
+};
+int rmsnorm_bwd_parts(int rows);
+Status launch_norm_dg_reduce(const NormDgList& list, const float* parts /* [n][kNormBwdMaxParts][512] */, cudaStream_t s);
 Status launch_rmsnorm_bwd(const float* x, const float* g, float eps, const bf16* dy, int rows, float* dres,
-                          bf16* dres_bf16, float* dg, cudaStream_t s);
+                          bf16* dres_bf16, float* dg_part, cudaStream_t s);
 Status launch_gated_gelu_fwd(const bf16* raw, bf16* ff, size_t rows, DropSpec drop, cudaStream_t s);
 Status launch_gated_gelu_bwd(const bf16* raw, const bf16* dff, bf16* draw, size_t rows, DropSpec drop, cudaStream_t s);
 // x[i] *= keep(i) / (1 - p)   (dropout forward on a value, or backward on its gradient)
@@ -19,7 +30,8 @@ Status launch_dropout_bf16(bf16* x, size_t n, DropSpec drop, cudaStream_t s);
 Status launch_dropout_cast(const float* in, bf16* out, size_t n, DropSpec drop, cudaStream_t s);
 Status launch_transpose_bf16(const bf16* in, int ld_in, bf16* out, int ld_out, int R, int C, cudaStream_t s);
 Status launch_transpose_f32_to_bf16(const float* in, bf16* out, int R, int C, cudaStream_t s);
-Status launch_embed_bwd(const long long* ids, const float* dH, float* dEmb, int rows, cudaStream_t s);
+size_t embed_bwd_scratch_bytes(int rows);
+Status launch_embed_bwd(const long long* ids, const float* dH, float* dEmb, int rows, void* scratch, cudaStream_t s);
 Status launch_cast_f32_bf16(const float* in, bf16* out, size_t n, cudaStream_t s);
 Status launch_bf16_to_f32(const bf16* in, float* out, size_t n, cudaStream_t s);
 Status launch_reduce_splits(const float* partials, float* out, size_t n, int splits, cudaStream_t s);

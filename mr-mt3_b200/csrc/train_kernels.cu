@@ -99,13 +99,14 @@ Status launch_xent(const float* logits, const long long* labels, int rows, int V
 //   dx = r * (g * dy) - x * r^3 / d * sum_j (g_j dy_j x_j);  dg_j = sum_rows dy_j x_j r
 // dx is ADDED to dres (the gradient of the residual stream the norm branched from); the updated
 // rows are also written as bf16 (dres_bf16, optional) for the GEMMs that consume them next.
+// dg: every CTA combines its eight warps in a fixed order and stores ONE partial row,
+// dg_part[blockIdx.x][512]; norm_dg_reduce_kernel adds the partial rows of all norms of the step in
+// CTA order at the end of the backward pass -- no float atomics, the same bits every run.
 __global__ void __launch_bounds__(256)
     rmsnorm_bwd_kernel(const float* __restrict__ x, const float* __restrict__ g, float eps,
                        const bf16* __restrict__ dy, int rows, float* __restrict__ dres, bf16* __restrict__ dres_bf16,
-                       float* __restrict__ dg) {
-    __shared__ float s_dg[kDModel];
-    for (int i = threadIdx.x; i < kDModel; i += 256) s_dg[i] = 0.f;
-    __syncthreads();
+                       float* __restrict__ dg_part) {
+    __shared__ float s_dg[8][kDModel];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     float acc_dg[16];
 #pragma unroll
@@ -154,16 +155,51 @@ __global__ void __launch_bounds__(256)
     }
 #pragma unroll
     for (int i = 0; i < 4; ++i)
-#pragma unroll
-        for (int k = 0; k < 4; ++k) atomicAdd(&s_dg[(lane + i * 32) * 4 + k], acc_dg[i * 4 + k]);
+        *reinterpret_cast<float4*>(&s_dg[warp][(lane + i * 32) * 4]) =
+            make_float4(acc_dg[i * 4 + 0], acc_dg[i * 4 + 1], acc_dg[i * 4 + 2], acc_dg[i * 4 + 3]);
     __syncthreads();
-    for (int i = threadIdx.x; i < kDModel; i += 256) atomicAdd(dg + i, s_dg[i]);
+    for (int i = threadIdx.x; i < kDModel; i += 256) {
+        float a = s_dg[0][i];
+#pragma unroll
+        for (int w = 1; w < 8; ++w) a += s_dg[w][i];
+        dg_part[(size_t)blockIdx.x * kDModel + i] = a;
+    }
 }
 
+int rmsnorm_bwd_parts(int rows) { return std::min(ceil_div(rows, 8), kNormBwdMaxParts); }
+
 Status launch_rmsnorm_bwd(const float* x, const float* g, float eps, const bf16* dy, int rows, float* dres,
-                          bf16* dres_bf16, float* dg, cudaStream_t s) {
+                          bf16* dres_bf16, float* dg_part, cudaStream_t s) {
     if (rows <= 0) return OkStatus();
-    rmsnorm_bwd_kernel<<<std::min(ceil_div(rows, 8), 592), 256, 0, s>>>(x, g, eps, dy, rows, dres, dres_bf16, dg);
+    rmsnorm_bwd_kernel<<<rmsnorm_bwd_parts(rows), 256, 0, s>>>(x, g, eps, dy, rows, dres, dres_bf16, dg_part);
+    MRMT3_CHECK_LAUNCH();
+    return OkStatus();
+}
+
+// dst[i][col] = sum over the n_parts[i] partial rows of norm i, in order: 8 row groups per column
+// run in parallel and are combined in a fixed order
+__global__ void __launch_bounds__(1024)
+    norm_dg_reduce_kernel(NormDgList list, const float* __restrict__ parts) {
+    __shared__ float s[8][128];
+    const int i = blockIdx.x, col = blockIdx.y * 128 + (threadIdx.x & 127), grp = threadIdx.x >> 7;
+    const int n = list.n_parts[i];
+    const float* p = parts + (size_t)i * kNormBwdMaxParts * kDModel + col;
+    const int per = (n + 7) / 8, b0 = grp * per, b1 = min(n, b0 + per);
+    float a = 0.f;
+    for (int b = b0; b < b1; ++b) a += p[(size_t)b * kDModel];
+    s[grp][threadIdx.x & 127] = a;
+    __syncthreads();
+    if (grp == 0) {
+        float t = s[0][threadIdx.x];
+#pragma unroll
+        for (int g2 = 1; g2 < 8; ++g2) t += s[g2][threadIdx.x];
+        list.dst[i][col] = t;
+    }
+}
+
+Status launch_norm_dg_reduce(const NormDgList& list, const float* parts, cudaStream_t s) {
+    if (list.n <= 0) return OkStatus();
+    norm_dg_reduce_kernel<<<dim3(list.n, kDModel / 128), 1024, 0, s>>>(list, parts);
     MRMT3_CHECK_LAUNCH();
     return OkStatus();
 }
@@ -350,67 +386,123 @@ Status launch_transpose_f32_to_bf16(const float* in, bf16* out, int R, int C, cu
 
 // ---------------------------------------------------------------------------------------------
 // dEmb[ids[r]] += dH[r]   (rows of 512 fp32).  Token ids repeat heavily (pad = 0 fills half of a
-// batch), so a plain scatter serialises 16 K x 512 atomics on one row.  Here a CTA owns kEmbIds
-// consecutive ids and one slice of the rows: it scans the slice's ids from shared memory, each warp
-// sums the matching rows it is responsible for in registers (four independent 16-byte loads per
-// lane per row), and only the per-warp totals are added atomically (<= 4 x kEmbSlices per address).
+// batch), so a plain scatter serialises 16 K x 512 atomics on one row -- and any atomic float
+// accumulation makes the step irreproducible.  Two deterministic levels instead:
+//   1. a CTA owns kEmbIds consecutive ids and one slice of kEmbSliceRows rows: it scans the slice's
+//      ids from shared memory, each warp sums the matching rows it is responsible for in registers
+//      (four independent 16-byte loads per lane per row), the four warps are combined in a fixed
+//      order, and the partial row goes to a compact scratch list; only its SLOT is drawn from an
+//      atomic counter, and slot_tab[slice][id] remembers it (-1: the slice has no such id)
+//   2. one CTA per id adds that id's partial rows in slice order and updates dEmb (plain RMW: calls
+//      are ordered by the stream)
+// The values are therefore a fixed function of the inputs; only their scratch location varies.
 constexpr int kEmbIds = 4;
-constexpr int kEmbSlices = 16;
+constexpr int kEmbSliceRows = 256;
 __global__ void __launch_bounds__(128)
-    embed_bwd_kernel(const long long* __restrict__ ids, const float* __restrict__ dH, float* __restrict__ dEmb,
-                     int rows, int vocab) {
-    __shared__ int s_ids[1024];
+    embed_bwd_partial_kernel(const long long* __restrict__ ids, const float* __restrict__ dH, float4* __restrict__ part,
+                             int* __restrict__ slot_tab, int* __restrict__ counter, int rows, int vocab) {
+    __shared__ int s_ids[kEmbSliceRows];
+    __shared__ float4 s_acc[4][kEmbIds][128];
+    __shared__ int s_has[kEmbIds], s_slot[kEmbIds];
     const int id0 = blockIdx.x * kEmbIds;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    const int per = (rows + kEmbSlices - 1) / kEmbSlices;
-    const int r_begin = blockIdx.y * per, r_end = min(rows, r_begin + per);
+    const int r0 = blockIdx.y * kEmbSliceRows, n = min(kEmbSliceRows, rows - r0);
+    if (threadIdx.x < kEmbIds) s_has[threadIdx.x] = 0;
+    for (int i = threadIdx.x; i < n; i += 128) s_ids[i] = (int)ids[r0 + i];
+    __syncthreads();
     float4 acc[kEmbIds][4];
 #pragma unroll
     for (int k = 0; k < kEmbIds; ++k)
 #pragma unroll
         for (int j = 0; j < 4; ++j) acc[k][j] = make_float4(0.f, 0.f, 0.f, 0.f);
-    for (int r0 = r_begin; r0 < r_end; r0 += 1024) {
-        const int n = min(1024, r_end - r0);
-        __syncthreads();
-        for (int i = threadIdx.x; i < n; i += 128) s_ids[i] = (int)ids[r0 + i];
-        __syncthreads();
-        for (int i = warp; i < n; i += 4) {
-            const int k = s_ids[i] - id0;
-            if (k >= 0 && k < kEmbIds) {  // uniform across the warp
-                const float4* src = reinterpret_cast<const float4*>(dH + (size_t)(r0 + i) * kDModel) + lane;
-                float4 v[4];
+    bool any = false;
+    for (int i = warp; i < n; i += 4) {
+        const int k = s_ids[i] - id0;
+        if (k >= 0 && k < kEmbIds) {  // uniform across the warp
+            any = true;
+            const float4* src = reinterpret_cast<const float4*>(dH + (size_t)(r0 + i) * kDModel) + lane;
+            float4 v[4];
 #pragma unroll
-                for (int j = 0; j < 4; ++j) v[j] = src[j * 32];
+            for (int j = 0; j < 4; ++j) v[j] = src[j * 32];
+            if (lane == 0) s_has[k] = 1;  // same value from every writer
 #pragma unroll
-                for (int q = 0; q < kEmbIds; ++q)
-                    if (q == k) {
+            for (int q = 0; q < kEmbIds; ++q)
+                if (q == k) {
 #pragma unroll
-                        for (int j = 0; j < 4; ++j) {
-                            acc[q][j].x += v[j].x; acc[q][j].y += v[j].y; acc[q][j].z += v[j].z; acc[q][j].w += v[j].w;
-                        }
+                    for (int j = 0; j < 4; ++j) {
+                        acc[q][j].x += v[j].x; acc[q][j].y += v[j].y; acc[q][j].z += v[j].z; acc[q][j].w += v[j].w;
                     }
-            }
+                }
         }
     }
+    const bool cta_any = __syncthreads_or(any);
+    if (!cta_any) {  // the common case: none of these ids occurs in the slice
+        if (threadIdx.x < kEmbIds && id0 + threadIdx.x < vocab)
+            slot_tab[(size_t)blockIdx.y * vocab + id0 + threadIdx.x] = -1;
+        return;
+    }
+#pragma unroll
+    for (int k = 0; k < kEmbIds; ++k)
+#pragma unroll
+        for (int j = 0; j < 4; ++j) s_acc[warp][k][j * 32 + lane] = acc[k][j];
+    if (threadIdx.x < kEmbIds) {
+        const int k = threadIdx.x;
+        const int slot = s_has[k] ? atomicAdd(counter, 1) : -1;
+        s_slot[k] = slot;
+        if (id0 + k < vocab) slot_tab[(size_t)blockIdx.y * vocab + id0 + k] = slot;
+    }
+    __syncthreads();
 #pragma unroll
     for (int k = 0; k < kEmbIds; ++k) {
-        if (id0 + k >= vocab) continue;
+        const int slot = s_slot[k];
+        if (slot < 0) continue;
+        float4 a = s_acc[0][k][threadIdx.x];
 #pragma unroll
-        for (int j = 0; j < 4; ++j) {
-            const float4 a = acc[k][j];
-            if (a.x == 0.f && a.y == 0.f && a.z == 0.f && a.w == 0.f) continue;
-            float* d = dEmb + (size_t)(id0 + k) * kDModel + (j * 32 + lane) * 4;
-            atomicAdd(d + 0, a.x);
-            atomicAdd(d + 1, a.y);
-            atomicAdd(d + 2, a.z);
-            atomicAdd(d + 3, a.w);
+        for (int w = 1; w < 4; ++w) {
+            const float4 b = s_acc[w][k][threadIdx.x];
+            a.x += b.x; a.y += b.y; a.z += b.z; a.w += b.w;
         }
+        part[(size_t)slot * 128 + threadIdx.x] = a;
     }
 }
 
-Status launch_embed_bwd(const long long* ids, const float* dH, float* dEmb, int rows, cudaStream_t s) {
+__global__ void __launch_bounds__(128)
+    embed_bwd_combine_kernel(const float4* __restrict__ part, const int* __restrict__ slot_tab, float4* __restrict__ dEmb,
+                             int n_slices, int vocab) {
+    const int id = blockIdx.x;
+    float4 a = make_float4(0.f, 0.f, 0.f, 0.f);
+    bool any = false;
+    for (int sl = 0; sl < n_slices; ++sl) {
+        const int slot = slot_tab[(size_t)sl * vocab + id];
+        if (slot < 0) continue;
+        any = true;
+        const float4 b = part[(size_t)slot * 128 + threadIdx.x];
+        a.x += b.x; a.y += b.y; a.z += b.z; a.w += b.w;
+    }
+    if (!any) return;
+    float4* d = dEmb + (size_t)id * 128 + threadIdx.x;
+    float4 c = *d;
+    c.x += a.x; c.y += a.y; c.z += a.z; c.w += a.w;
+    *d = c;
+}
+
+size_t embed_bwd_scratch_bytes(int rows) {
+    const size_t slices = ceil_div(rows, kEmbSliceRows);
+    // every partial row belongs to a distinct (slice, id) pair that owns at least one input row
+    return (size_t)rows * kDModel * 4 + slices * kVocab * 4 + 256;
+}
+
+Status launch_embed_bwd(const long long* ids, const float* dH, float* dEmb, int rows, void* scratch, cudaStream_t s) {
     if (rows <= 0) return OkStatus();
-    embed_bwd_kernel<<<dim3(ceil_div(kVocab, kEmbIds), kEmbSlices), 128, 0, s>>>(ids, dH, dEmb, rows, kVocab);
+    static_assert(kDModel == 512, "one float4 column per thread of a 128-thread CTA");
+    const int slices = ceil_div(rows, kEmbSliceRows);
+    float4* part = reinterpret_cast<float4*>(scratch);
+    int* slot_tab = reinterpret_cast<int*>(reinterpret_cast<char*>(scratch) + (size_t)rows * kDModel * 4);
+    int* counter = slot_tab + (size_t)slices * kVocab;
+    MRMT3_CUDA_TRY(cudaMemsetAsync(counter, 0, sizeof(int), s));
+    embed_bwd_partial_kernel<<<dim3(ceil_div(kVocab, kEmbIds), slices), 128, 0, s>>>(ids, dH, part, slot_tab, counter, rows, kVocab);
+    MRMT3_CHECK_LAUNCH();
+    embed_bwd_combine_kernel<<<kVocab, 128, 0, s>>>(part, slot_tab, reinterpret_cast<float4*>(dEmb), slices, kVocab);
     MRMT3_CHECK_LAUNCH();
     return OkStatus();
 }
