@@ -30,7 +30,6 @@ struct ParamSlot {
     float* w32;     // fp32 parameter in the arena (norm weights, embedding) or nullptr
     int rows, cols; // packed shape
     size_t off;     // offset in the flat gradient / master / moment buffers
-    bf16* wt;       // (cols, rows) transposed bf16 copy for dgrad, refreshed every step
 };
 
 struct LayerSlots {
@@ -49,7 +48,7 @@ struct TrainState {
     std::vector<LayerSlots> enc, dec, mem;
     int proj = -1, emb = -1, lm_head = -1, cross_kv = -1, enc_final = -1, dec_final = -1, mem_final = -1, segmem_proj = -1;
     size_t n_total = 0;
-    DeviceBuffer master, m, v, wt_arena, stash, scratch;
+    DeviceBuffer master, m, v, stash, scratch;
     int step = 0;
     // the last forward's saved state
     int B = 0, L = 0, Lp = 0, n_mem = 0;
@@ -99,7 +98,7 @@ Status train_set_dropout(mrmt3_handle* h, float p, unsigned long long seed) {
 void train_destroy(mrmt3_handle* h) {
     TrainState* t = state(h);
     if (!t) return;
-    t->master.release(); t->m.release(); t->v.release(); t->wt_arena.release();
+    t->master.release(); t->m.release(); t->v.release();
     t->stash.release(); t->scratch.release(); t->ids_copy.release(); t->prev_copy.release();
     if (t->loss_pinned) cudaFreeHost(t->loss_pinned);
     delete t;
@@ -107,7 +106,7 @@ void train_destroy(mrmt3_handle* h) {
 }
 
 static int add_slot(TrainState* t, bf16* w16, float* w32, int rows, int cols) {
-    ParamSlot s{w16, w32, rows, cols, t->n_total, nullptr};
+    ParamSlot s{w16, w32, rows, cols, t->n_total};
     t->n_total += (size_t)rows * cols;
     t->slots.push_back(s);
     return (int)t->slots.size() - 1;
@@ -155,7 +154,6 @@ Status train_init(mrmt3_handle* h) {
     MRMT3_TRY(t->master.reserve(n * 4));
     MRMT3_TRY(t->m.reserve(n * 4));
     MRMT3_TRY(t->v.reserve(n * 4));
-    MRMT3_TRY(t->wt_arena.reserve(n * 2));
     MRMT3_CUDA_TRY(cudaMemset(t->m.p, 0, n * 4));
     MRMT3_CUDA_TRY(cudaMemset(t->v.p, 0, n * 4));
     // fp32 masters: the lm_head and the norm-folded decoder weights kept theirs from set_weight;
@@ -168,7 +166,6 @@ Status train_init(mrmt3_handle* h) {
         } else {
             RUN(h, launch_bf16_to_f32(s.w16, dst, cnt, 0));
         }
-        s.wt = t->wt_arena.as<bf16>() + s.off;
     }
     auto copy_master = [&](int slot, const float* src) -> Status {
         const ParamSlot& s = t->slots[slot];
@@ -475,11 +472,10 @@ Status train_backward(mrmt3_handle* h, float* grad, const float* dlogits_f32, cu
     const unsigned long long seed = t->drop_seed_used;
     auto mk = [&](int stack, int layer, int site) { return drop_spec(t, seed, stack, layer, site); };
 
-    // W^T copies for the dgrad GEMMs
     // scratch
     const size_t kvN = (size_t)n_dec * 2 * kInner;
     size_t need = Mmax * kDModel * 4 * 2 + Mmax * kDModel * 2 * 2 + Mmax * 2 * kDFF * 2 + Mmax * kDFF * 2 +
-                  Mmax * 3 * kInner * 2 + Mmax * kInner * 2 * 2 + Mp * 2 * kDFF * 2 * 2 + Mp * kvN * 2 * 2 +
+                  Mmax * 3 * kInner * 2 + Mmax * kInner * 2 * 2 +
                   (size_t)16 * 2 * kDFF * kDModel * 4 + Mk * kvN * 2 + (size_t)B * kHeads * std::max(std::max(L, Lp), kSegFrames) * 4 + Mmax * kDModel * 2 +
                   embed_bwd_scratch_bytes((int)Mmax) + (size_t)kNormBwdMaxNorms * kNormBwdMaxParts * kDModel * 4 + (1 << 16);
     MRMT3_TRY(t->scratch.reserve(need));
@@ -492,8 +488,6 @@ Status train_backward(mrmt3_handle* h, float* grad, const float* dlogits_f32, cu
     bf16* dqkv = bp.take<bf16>(Mmax * 3 * kInner);
     bf16* dctx = bp.take<bf16>(Mmax * kInner);
     bf16* dqc = bp.take<bf16>(Mmax * kInner);
-    bf16* yT = bp.take<bf16>(std::max((size_t)2 * kDFF, kvN) * Mp);
-    bf16* xT = bp.take<bf16>(std::max((size_t)2 * kDFF, (size_t)kDModel) * Mp);
     float* wpart = bp.take<float>((size_t)16 * 2 * kDFF * kDModel);  // split-K partials (a split needs <= 160 / splits tiles)
     bf16* dkv = bp.take<bf16>(Mk * kvN);
     bf16* dsplit = bp.take<bf16>(Mmax * kDModel);  // rows of the K/V-input gradient regrouped per consumer
@@ -520,24 +514,11 @@ Status train_backward(mrmt3_handle* h, float* grad, const float* dlogits_f32, cu
     };
     auto G = [&](int slot) { return grad + t->slots[slot].off; };
     // dX (M, Kin) = dY (M, N) . W (N, Kin): the weight as stored is the MN-major B operand of the
-    // tcgen05 GEMM; MRMT3_DGRAD_WT=1 selects the earlier route through per-step W^T copies
-    static const bool dgrad_via_wt = [] {
-        const char* e = getenv("MRMT3_DGRAD_WT");
-        return e && atoi(e) != 0;
-    }();
-    if (dgrad_via_wt) {
-        tic("W^T copies");
-        for (auto& sl : t->slots)
-            if (sl.w16) RUN(h, launch_transpose_bf16(sl.w16, sl.cols, sl.wt, sl.rows, sl.rows, sl.cols, s));
-        toc();
-    }
+    // tcgen05 GEMM (no transposed weight copies)
     auto dgrad_to = [&](const bf16* dY, int N, int slot, auto epi, size_t M) -> Status {
         const ParamSlot& sl = t->slots[slot];
         tic("dgrad");
-        if (dgrad_via_wt)
-            RUN(h, launch_gemm_tc(*h->tma, dY, N, M, id, sl.wt, N, (int)M, sl.cols, N, epi, s));
-        else
-            RUN(h, launch_gemm_tc_nn(*h->tma, dY, N, (int)M, sl.w16, sl.cols, sl.cols, N, epi, s));
+        RUN(h, launch_gemm_tc_nn(*h->tma, dY, N, (int)M, sl.w16, sl.cols, sl.cols, N, epi, s));
         toc();
         return OkStatus();
     };
@@ -545,45 +526,19 @@ Status train_backward(mrmt3_handle* h, float* grad, const float* dlogits_f32, cu
         return dgrad_to(dY, N, slot, EpiStoreBf16{dX, t->slots[slot].cols}, M);
     };
     // dW (N, Kin) fp32 = dY^T . X ; dY (M, N) with pitch ldy, X (M, Kin) with pitch ldx
-    static const bool wgrad_via_transpose = [] {
-        const char* e = getenv("MRMT3_WGRAD_TRANSPOSE");
-        return e && atoi(e) != 0;
-    }();
     auto wgrad = [&](const bf16* dY, int ldy, int N, const bf16* X, int ldx, int Kin, float* dW, size_t M) -> Status {
-        // the output has only (N / 128) x (Kin / BN) tiles: split the long reduction over the SMs
+        // both operands straight from their row-major buffers (MN-major tcgen05 operands).  The output
+        // has only (N / 128) x (Kin / BN) tiles: split the long reduction over the SMs
         const int bn = Kin % 256 == 0 ? 256 : (Kin % 192 == 0 ? 192 : (Kin % 128 == 0 ? 128 : 64));
         const int out_tiles = ceil_div(N, 128) * (Kin / bn);
         const int blocks = (int)((M + 63) / 64);
         int splits = 1;
-        if (!wgrad_via_transpose) {
-            // both operands straight from their row-major buffers (MN-major tcgen05 operands)
-            while (splits < 16 && out_tiles * splits * 2 <= 160 && splits * 2 <= blocks) splits *= 2;
-            tic("wgrad gemm");
-            if (splits == 1) {
-                RUN(h, launch_gemm_tc_mn(*h->tma, dY, ldy, N, X, ldx, Kin, (int)M, EpiStoreF32{dW, Kin}, s));
-            } else {
-                RUN(h, launch_gemm_tc_mn(*h->tma, dY, ldy, N, X, ldx, Kin, (int)M, EpiStoreF32{wpart, Kin}, s, splits));
-                RUN(h, launch_reduce_splits(wpart, dW, (size_t)N * Kin, splits, s));
-            }
-            toc();
-            return OkStatus();
-        }
-        // MRMT3_WGRAD_TRANSPOSE=1: the earlier route, K-major operands through explicit transposes
-        const size_t mp = (size_t)blocks * 64;
-        if (mp != M) {
-            MRMT3_CUDA_TRY(cudaMemset2DAsync(yT + M, mp * 2, 0, (mp - M) * 2, N, s));
-            MRMT3_CUDA_TRY(cudaMemset2DAsync(xT + M, mp * 2, 0, (mp - M) * 2, Kin, s));
-        }
-        tic("wgrad transposes");
-        RUN(h, launch_transpose_bf16(dY, ldy, yT, (int)mp, (int)M, N, s));
-        RUN(h, launch_transpose_bf16(X, ldx, xT, (int)mp, (int)M, Kin, s));
-        toc();
+        while (splits < 16 && out_tiles * splits * 2 <= 160 && splits * 2 <= blocks) splits *= 2;
         tic("wgrad gemm");
-        while (splits < 16 && out_tiles * splits * 2 <= 160 && (blocks % (splits * 2)) == 0) splits *= 2;
         if (splits == 1) {
-            RUN(h, launch_gemm_tc(*h->tma, yT, (int)mp, N, id, xT, (int)mp, N, Kin, (int)mp, EpiStoreF32{dW, Kin}, s));
+            RUN(h, launch_gemm_tc_mn(*h->tma, dY, ldy, N, X, ldx, Kin, (int)M, EpiStoreF32{dW, Kin}, s));
         } else {
-            RUN(h, launch_gemm_tc(*h->tma, yT, (int)mp, N, id, xT, (int)mp, N, Kin, (int)mp, EpiStoreF32{wpart, Kin}, s, splits));
+            RUN(h, launch_gemm_tc_mn(*h->tma, dY, ldy, N, X, ldx, Kin, (int)M, EpiStoreF32{wpart, Kin}, s, splits));
             RUN(h, launch_reduce_splits(wpart, dW, (size_t)N * Kin, splits, s));
         }
         toc();

@@ -28,8 +28,6 @@ Status launch_dropout_f32(float* x, size_t n, DropSpec drop, cudaStream_t s);
 Status launch_dropout_bf16(bf16* x, size_t n, DropSpec drop, cudaStream_t s);
 // out_bf16[i] = bf16(in[i] * keep(i) / (1 - p))
 Status launch_dropout_cast(const float* in, bf16* out, size_t n, DropSpec drop, cudaStream_t s);
-Status launch_transpose_bf16(const bf16* in, int ld_in, bf16* out, int ld_out, int R, int C, cudaStream_t s);
-Status launch_transpose_f32_to_bf16(const float* in, bf16* out, int R, int C, cudaStream_t s);
 size_t embed_bwd_scratch_bytes(int rows);
 Status launch_embed_bwd(const long long* ids, const float* dH, float* dEmb, int rows, void* scratch, cudaStream_t s);
 Status launch_cast_f32_bf16(const float* in, bf16* out, size_t n, cudaStream_t s);

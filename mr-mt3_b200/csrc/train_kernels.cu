@@ -4,13 +4,16 @@
 // has a hand-written backward:
 //
 //   xent_kernel            softmax cross-entropy forward + d(logits), rows with label -100 ignored
-//   rmsnorm_bwd_kernel     T5LayerNorm backward (dx accumulated into the residual gradient, dg)
+//   rmsnorm_bwd_kernel     T5LayerNorm backward (dx accumulated into the residual gradient; dg as
+//                          per-CTA partial rows, norm_dg_reduce_kernel adds them in a fixed order)
 //   gated_gelu_*           gated-GELU forward from the saved raw ffn-in output, and its backward
-//   transpose_bf16_kernel  (R, C) -> (C, R): dgrad / wgrad reuse the TN tcgen05 GEMM
-//   embed_bwd_kernel       scatter-add of the stack-input gradient into the embedding table
-//   attn_bwd_*             flash-style attention backward (no 1/sqrt(d) scale, no bias): row
-//                          statistics D = rowsum(dO * O), then dK/dV per key tile and dQ per query
-//                          tile, recomputing P from the saved log-sum-exp
+//   dropout_*              the elementwise dropout sites (counter-based hash, common.cuh)
+//   embed_bwd_*            the stack-input gradient summed per token id into the embedding table,
+//                          two levels, no atomics on values
+//   attn_bwd_*             flash-style attention backward (no 1/sqrt(d) scale, no bias): dQ per
+//                          query tile (first a pass forming delta = sum P dP), dK/dV per key tile,
+//                          P recomputed from the saved log-sum-exp, dropout from the saved keep bits
+//   (dgrad / wgrad are the tcgen05 GEMM of gemm_tcgen05.cuh in its MN-major operand modes)
 //   adamw_kernel           AdamW on fp32 masters, refreshed bf16 copy
 #include "train.cuh"
 
@@ -309,77 +312,6 @@ Status launch_dropout_cast(const float* in, bf16* out, size_t n, DropSpec drop, 
     if (!n) return OkStatus();
     dropout_cast_kernel<<<(unsigned)((n / 4 + 255) / 256), 256, 0, s>>>(reinterpret_cast<const float4*>(in),
                                                                       reinterpret_cast<uint2*>(out), n / 4, drop);
-    MRMT3_CHECK_LAUNCH();
-    return OkStatus();
-}
-
-// ---------------------------------------------------------------------------------------------
-// (R, C) bf16 row-major with row pitch ld_in -> (C, R) with row pitch ld_out.  64 x 64 tiles through
-// shared memory; full tiles of 16-byte-aligned matrices move with 16-byte loads and stores.
-__global__ void __launch_bounds__(256)
-    transpose_bf16_kernel(const bf16* __restrict__ in, int ld_in, bf16* __restrict__ out, int ld_out, int R, int C,
-                          int vec_ok) {
-    __shared__ __align__(16) bf16 tile[64][72];
-    const int r0 = blockIdx.y * 64, c0 = blockIdx.x * 64;
-    const bool full = vec_ok && r0 + 64 <= R && c0 + 64 <= C;
-    if (full) {
-#pragma unroll
-        for (int i = 0; i < 2; ++i) {
-            int idx = threadIdx.x + i * 256;  // 64 rows x 8 chunks of 8 elements
-            int r = idx >> 3, ch = idx & 7;
-            *reinterpret_cast<uint4*>(&tile[r][ch * 8]) =
-                *reinterpret_cast<const uint4*>(in + (size_t)(r0 + r) * ld_in + c0 + ch * 8);
-        }
-        __syncthreads();
-#pragma unroll
-        for (int i = 0; i < 2; ++i) {
-            int idx = threadIdx.x + i * 256;  // 64 output rows (input cols) x 8 chunks of 8 input rows
-            int c = idx & 63, rc = idx >> 6;
-            bf16 v[8];
-#pragma unroll
-            for (int k = 0; k < 8; ++k) v[k] = tile[rc * 8 + k][c];
-            *reinterpret_cast<uint4*>(out + (size_t)(c0 + c) * ld_out + r0 + rc * 8) = *reinterpret_cast<uint4*>(v);
-        }
-        return;
-    }
-    for (int i = threadIdx.x; i < 64 * 64; i += 256) {
-        int r = i >> 6, c = i & 63;
-        tile[r][c] = (r0 + r < R && c0 + c < C) ? in[(size_t)(r0 + r) * ld_in + c0 + c] : __float2bfloat16(0.f);
-    }
-    __syncthreads();
-    for (int i = threadIdx.x; i < 64 * 64; i += 256) {
-        int c = i >> 6, r = i & 63;
-        if (c0 + c < C && r0 + r < R) out[(size_t)(c0 + c) * ld_out + r0 + r] = tile[r][c];
-    }
-}
-
-Status launch_transpose_bf16(const bf16* in, int ld_in, bf16* out, int ld_out, int R, int C, cudaStream_t s) {
-    if (R <= 0 || C <= 0) return OkStatus();
-    const int vec_ok = (ld_in % 8 == 0) && (ld_out % 8 == 0) && ((reinterpret_cast<uintptr_t>(in) & 15) == 0) &&
-                       ((reinterpret_cast<uintptr_t>(out) & 15) == 0);
-    transpose_bf16_kernel<<<dim3(ceil_div(C, 64), ceil_div(R, 64)), 256, 0, s>>>(in, ld_in, out, ld_out, R, C, vec_ok);
-    MRMT3_CHECK_LAUNCH();
-    return OkStatus();
-}
-
-// fp32 -> bf16 transpose of a weight (used for the dgrad operand W^T): (R, C) fp32 -> (C, R) bf16
-__global__ void __launch_bounds__(256)
-    transpose_f32_to_bf16_kernel(const float* __restrict__ in, bf16* __restrict__ out, int R, int C) {
-    __shared__ float tile[32][33];
-    const int r0 = blockIdx.y * 32, c0 = blockIdx.x * 32;
-    for (int i = threadIdx.x; i < 32 * 32; i += 256) {
-        int r = i >> 5, c = i & 31;
-        tile[r][c] = (r0 + r < R && c0 + c < C) ? in[(size_t)(r0 + r) * C + c0 + c] : 0.f;
-    }
-    __syncthreads();
-    for (int i = threadIdx.x; i < 32 * 32; i += 256) {
-        int c = i >> 5, r = i & 31;
-        if (c0 + c < C && r0 + r < R) out[(size_t)(c0 + c) * R + r0 + r] = __float2bfloat16(tile[r][c]);
-    }
-}
-
-Status launch_transpose_f32_to_bf16(const float* in, bf16* out, int R, int C, cudaStream_t s) {
-    transpose_f32_to_bf16_kernel<<<dim3(ceil_div(C, 32), ceil_div(R, 32)), 256, 0, s>>>(in, out, R, C);
     MRMT3_CHECK_LAUNCH();
     return OkStatus();
 }
