@@ -137,3 +137,52 @@ def test_postprocess_quirks():
     rows = O.trim_rows(pp)
     np.testing.assert_array_equal(rows[0], [7, 8])
     assert len(rows[1]) == 0                                   # no EOS -> empty row (R11)
+
+
+# ---- fine-tune step (R10): autograd through the oracle against the reference's own autograd ------
+def _oracle_step(sd32, x, labels, prev):
+    import torch.nn.functional as F
+    sd64 = {}
+    for k, v in sd32.items():
+        if v.is_floating_point() and "inv_freq" not in k:
+            same = [k2 for k2 in sd64 if sd32[k2] is v]
+            sd64[k] = sd64[same[0]] if same else v.detach().double().requires_grad_(True)
+        else:
+            sd64[k] = v
+    if prev is None:
+        logits = O.forward_logits(x, labels, sd64)
+    else:
+        logits = O.forward_logits_segmem_v2_with_prev(x, labels, prev.masked_fill(prev == -100, 0), sd64)
+    loss = F.cross_entropy(logits.reshape(-1, logits.shape[-1]), labels.reshape(-1), ignore_index=-100)
+    loss.backward()
+    return float(loss.detach()), {k: v.grad for k, v in sd64.items() if torch.is_tensor(v) and v.requires_grad}
+
+
+@pytest.mark.parametrize("tag", ["mt3", "v2p"])
+def test_training_loss_and_gradients_match_reference_autograd(tag):
+    """tests/golden/train.npz holds the loss, every parameter-gradient norm and a few gradient corners
+    of one reference `training_step` (oracle/make_golden_train.py: the reference's models + torch
+    autograd, fp32).  Autograd through the oracle -- what tests/test_train_gpu.py holds the CUDA
+    backward against -- must reproduce them: fp32-vs-fp64 differences only."""
+    g = golden("train.npz")
+    labels = torch.as_tensor(g[f"{tag}/labels"])
+    if tag == "mt3":
+        sd, x, prev = syn.synthetic_state_dict(1234), syn.synthetic_features(int(g["mt3_seed"]) + 1, 2), None
+    else:
+        sd = syn.synthetic_state_dict(4322, segmem=True)
+        x, prev = syn.synthetic_features(int(g["v2p_seed"]) + 1, 2), torch.as_tensor(g["v2p/targets_prev"])
+    loss, grads = _oracle_step(sd, x, labels, prev)
+    assert abs(loss - float(g[f"{tag}/loss"])) < 2e-5               # measured 1e-6
+    names, norms = [str(n) for n in g[f"{tag}/grad_names"]], g[f"{tag}/grad_norms"]
+    assert len(names) == (189 if tag == "mt3" else 200)          # every trainable tensor of the reference
+    for name, want in zip(names, norms):
+        got = float(grads[name].norm())
+        assert abs(got - want) <= 2e-4 * want + 1e-9, (name, got, want)   # measured <= 3.5e-6
+    corners = [k for k in g.files if k.startswith(f"{tag}/corner/")]
+    assert len(corners) >= 7
+    for key in corners:
+        name = key.split("corner/", 1)[1]
+        gr = grads[name]
+        got = (gr[:6, :8] if gr.dim() == 2 else gr[:8]).numpy()
+        want = g[key]
+        assert np.max(np.abs(got - want)) <= 2e-4 * np.max(np.abs(want)) + 1e-9, name
