@@ -23,7 +23,12 @@ filterbank).  Parity pin: the reference ships NO tests or golden vectors for thi
 pin is `tests/golden/*.npz`, produced by `oracle/make_golden.py` from the reference's own
 code (run unmodified through oracle/ref_shim.py in the build container) and from the same
 torchaudio call the reference makes; `tests/test_oracle_golden.py` checks this file against
-them on every CPU run.
+them on every CPU run.  The fine-tune step is pinned the same way: `oracle/make_golden_train.py`
+stores the loss and every parameter gradient norm of one reference `training_step` (torch
+autograd through the reference's models), and autograd through this file must reproduce them.
+Dropout cannot be pinned to torch's RNG stream; its masks are a counter-based hash defined in
+csrc/common.cuh, mirrored by `dropout_keep` below and pinned to the C++ definition bit for bit
+(`mrmt3_dropout_keep_host`, tests/test_host_cpu.py).
 """
 import math
 
