@@ -9,6 +9,8 @@ repository root.  Sub-modules mirror the reference's files for this path:
   t5_segmem.py               <- reference models/t5_segmem.py (V1)
   t5_segmem_v2_with_prev.py  <- reference models/t5_segmem_v2_with_prev.py
   inference.py               <- reference inference.py (InferenceHandler)
+  notes.py, evaluate.py      <- token rows -> notes / MIDI, multi-instrument onset F1 (contrib/*, evaluate.py)
+  audio.py                   <- WAV decode as librosa.load does it (test.py:36-40), pinned staging
   sharding.py                <- track sharding across GPUs (no reference counterpart)
   _lib.py                    <- ctypes binding of the C-ABI library (include/mrmt3_b200.h)
   csrc/                      <- the CUDA kernels and the extern "C" boundary

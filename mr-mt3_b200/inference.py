@@ -105,7 +105,13 @@ class InferenceHandler:
     def inference(self, audio, audio_path=None, outpath=None, valid_programs=None, num_beams=1,
                   batch_size=5, max_length=1024, verbose=False):
         """Reference inference.py:149-204 up to `_to_event`'s per-row cut: returns the list of
-        {'est_tokens', 'start_time'} predictions (one per segment)."""
+        {'est_tokens', 'start_time'} predictions (one per segment).  `audio=None` reads `audio_path`
+        the way the reference's caller does (test.py:36-40, `librosa.load(fname, sr=16000)`)."""
+        if audio is None:
+            if audio_path is None:
+                raise ValueError("inference() needs `audio` or `audio_path`")
+            from . import audio as audio_io
+            audio, _ = audio_io.load(audio_path, sr=16000)
         inputs, frame_times = self._preprocess(audio)
         inputs_tensor = torch.from_numpy(inputs)
         inputs_tensor, frame_times = self._batching(inputs_tensor, frame_times, batch_size=batch_size)
