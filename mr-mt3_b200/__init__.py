@@ -11,6 +11,7 @@ repository root.  Sub-modules mirror the reference's files for this path:
   inference.py               <- reference inference.py (InferenceHandler)
   notes.py, evaluate.py      <- token rows -> notes / MIDI, multi-instrument onset F1 (contrib/*, evaluate.py)
   audio.py                   <- WAV decode as librosa.load does it (test.py:36-40), pinned staging
+  targets.py                 <- notes -> labels / targets_prev rows (dataset_2_random*.py, contrib encoders)
   sharding.py                <- track sharding across GPUs (no reference counterpart)
   _lib.py                    <- ctypes binding of the C-ABI library (include/mrmt3_b200.h)
   csrc/                      <- the CUDA kernels and the extern "C" boundary

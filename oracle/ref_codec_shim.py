@@ -40,6 +40,11 @@ def _fake_note_seq():
             self.notes = _Notes()
             self.total_time = 0.0
 
+        def CopyFrom(self, other):                # protobuf deep copy (note_sequences.trim_overlapping_notes)
+            self.ticks_per_quarter = other.ticks_per_quarter
+            self.total_time = other.total_time
+            self.notes = _Notes(_Note(**vars(n)) for n in other.notes)
+
     m.NoteSequence = NoteSequence
     return m
 
