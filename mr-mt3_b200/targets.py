@@ -12,6 +12,7 @@ What is restated, on the plain `NoteSequence` of notes.py (no note_seq):
   contrib/vocabularies.py:62-67      velocity_to_bin
   contrib/run_length_encoding.py:81-189  encode_and_index_events (single-step shifts + per-frame
                                      event / state-event indices)
+  contrib/preprocessor.py:47-111      Slakh class -> program map, add_track_to_notesequence (no sustain pedal)
   dataset/dataset_2_random.py:81-98   _audio_to_frames (frame times only)
   dataset/dataset_2_random.py:198-279 _run_length_encode_shifts, _remove_redundant_tokens
   dataset/dataset_2_random.py:308-344 _split_frame, _random_chunk
@@ -39,6 +40,44 @@ NUM_SPECIAL_TOKENS = 3
 TIE_ONLY_PREV = (1131, 1)          # dataset_2_random_segmem_prev.py:96: no previous segment -> [tie, 1]
 INDEXED_KEYS = ("inputs", "input_times", "input_event_start_indices", "input_event_end_indices",
                 "input_state_event_indices")          # per-frame arrays: sliced together with the audio frames
+
+
+# ---- stems -> one NoteSequence -----------------------------------------------------------------------
+# General MIDI program per Slakh instrument class (contrib/preprocessor.py:47-82); 'Drums' is the
+# percussion channel.
+SLAKH_CLASS_PROGRAMS = {
+    "Acoustic Piano": 0, "Electric Piano": 4, "Chromatic Percussion": 8, "Organ": 16, "Acoustic Guitar": 24,
+    "Clean Electric Guitar": 26, "Distorted Electric Guitar": 29, "Acoustic Bass": 32, "Electric Bass": 33,
+    "Violin": 40, "Viola": 41, "Cello": 42, "Contrabass": 43, "Orchestral Harp": 46, "Timpani": 47,
+    "String Ensemble": 48, "Synth Strings": 50, "Choir and Voice": 52, "Orchestral Hit": 55, "Trumpet": 56,
+    "Trombone": 57, "Tuba": 58, "French Horn": 60, "Brass Section": 61, "Soprano/Alto Sax": 64, "Tenor Sax": 66,
+    "Baritone Sax": 67, "Oboe": 68, "English Horn": 69, "Bassoon": 70, "Clarinet": 71, "Pipe": 73,
+    "Synth Lead": 80, "Synth Pad": 88,
+}
+
+
+def slakh_class_to_program_and_is_drum(slakh_class: str) -> Tuple[int, bool]:
+    """contrib/preprocessor.py:85-92."""
+    if slakh_class == "Drums":
+        return 0, True
+    if slakh_class not in SLAKH_CLASS_PROGRAMS:
+        raise ValueError("unknown Slakh class: %s" % slakh_class)
+    return SLAKH_CLASS_PROGRAMS[slakh_class], False
+
+
+def merge_tracks(tracks: Sequence[NoteSequence], inst_names: Sequence[str]) -> NoteSequence:
+    """One NoteSequence from per-stem sequences, every note re-labelled with its stem's Slakh class
+    (dataset_2_random.py:113-128, contrib/preprocessor.py:99-111).  The reference first extends notes
+    over sustain-pedal spans (`note_seq.apply_sustain_control_changes`); the plain NoteSequence of
+    notes.py carries no control changes, so stems are expected with the pedal already applied."""
+    assert len(tracks) == len(inst_names)
+    ns = NoteSequence(ticks_per_quarter=220)
+    for track, name in zip(tracks, inst_names):
+        program, is_drum = slakh_class_to_program_and_is_drum(name)
+        for n in track.notes:
+            ns.notes.append(dataclasses.replace(n, program=program, is_drum=is_drum))
+            ns.total_time = max(ns.total_time, n.end_time)
+    return ns
 
 
 # ---- notes -> timed events ------------------------------------------------------------------------

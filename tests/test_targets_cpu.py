@@ -109,3 +109,19 @@ def test_rows_have_the_shape_the_fine_tune_step_takes():
     assert len(got) > 10 and got <= all_onsets
     in_window = {(s, p) for (s, p) in all_onsets if t0 * 100 < s < (t0 + 2.0) * 100}
     assert in_window <= got
+
+
+def test_merge_tracks_relabels_stems():
+    T, N = _mods()
+    assert T.slakh_class_to_program_and_is_drum("Drums") == (0, True)
+    assert T.slakh_class_to_program_and_is_drum("Electric Bass") == (33, False)
+    assert len(T.SLAKH_CLASS_PROGRAMS) == 34
+    with pytest.raises(ValueError):
+        T.slakh_class_to_program_and_is_drum("Kazoo")
+    a = N.NoteSequence(notes=[N.Note(0.0, 1.0, 60, 90, 5, False), N.Note(0.5, 0.75, 64, 70, 5, False)])
+    d = N.NoteSequence(notes=[N.Note(0.25, 0.3, 38, 100, 0, False)])
+    ns = T.merge_tracks([a, d], ["Violin", "Drums"])
+    assert [(n.program, n.is_drum) for n in ns.notes] == [(40, False), (40, False), (0, True)]
+    assert ns.total_time == 1.0 and a.notes[0].program == 5      # the stems are left untouched
+    labels, prevs = T.make_rows(ns, 16000, [0])
+    assert labels.shape == (1, 1024) and prevs[0][:2].tolist() == [1134, 1]
