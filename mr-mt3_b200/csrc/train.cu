@@ -465,9 +465,8 @@ Status train_backward(mrmt3_handle* h, float* grad, const float* dlogits_f32, cu
     const int B = t->B, L = t->L, Lp = t->Lp, n_mem = t->n_mem, n_enc = h->cfg.n_enc_layers, n_dec = h->cfg.n_dec_layers;
     const int tk = kSegFrames + n_mem;
     const size_t Me = (size_t)B * kSegFrames, Md = (size_t)B * L, Mm = (size_t)B * Lp, Mk = (size_t)B * tk;
-    const size_t Mmax = std::max(std::max(Me, Md), std::max(Mm, Mk)), Mp = (Mmax + 63) & ~size_t(63);
+    const size_t Mmax = std::max(std::max(Me, Md), std::max(Mm, Mk));
     const float eps = h->cfg.ln_eps;
-    const ARowMap id{nullptr, 1};
     MRMT3_CUDA_TRY(cudaMemsetAsync(grad, 0, t->n_total * 4, s));
     const unsigned long long seed = t->drop_seed_used;
     auto mk = [&](int stack, int layer, int site) { return drop_spec(t, seed, stack, layer, site); };
