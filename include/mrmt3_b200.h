@@ -71,7 +71,9 @@ int64_t mrmt3_launch_count(const mrmt3_handle* h);
  * 0 = one CTA per (lane, head) on CUDA cores), "attn_ring_stages" = ring depth of variant 1
  * (2, 3, 4 or 6 stages of 16 KB per warp quartet), "attn_ring_quartets" = 1 or 2 math-warp
  * quartets per CTA, "attn_ring_ctas" = its persistent CTAs per SM (1..8, 0 = by launch size).  The
- * attention settings are process-wide. */
+ * attention settings are process-wide.  "hooks_fast_path" = 1 sends calls that use the parity hooks of
+ * mrmt3_generate / mrmt3_generate_segmem (forced_ids, logits_out) through the production decode path
+ * (CUDA-graph replay, concurrent lane groups) instead of the eager single-group debug path. */
 int mrmt3_set_option(mrmt3_handle* h, const char* key, int value);
 
 /* ---- per-kernel timing (bench.py's roofline leg) ---------------------------------------
@@ -106,7 +108,11 @@ int mrmt3_trace_read(mrmt3_handle* h, uint64_t* out, int max_slots);
 
 /* Test hook: C (M,N) fp32 = A (M,K) bf16 * W (N,K)^T bf16 through one of the library's GEMM
  * kernels: which = 0 mma.sync pipeline, 1 = TMA + tcgen05/TMEM, 2 = decode-step single-shot
- * kernel (K in {384, 512, 1024}).  Used by tests/test_kernels_gpu.py only. */
+ * kernel (K in {384, 512, 1024}), 3 = tcgen05 with the bf16 store epilogue (c holds M*N bf16).
+ * The two operand forms of the fine-tune backward, on ROW-major operands as they lie in memory:
+ * which = 4: C (M,N) = A^T W with A (K,M), W (K,N) -- both MN-major, reduction over the K rows,
+ * split-K chosen as the weight-gradient path chooses it; which = 5: C (M,N) = A W with A (M,K),
+ * W (K,N) -- the data-gradient form (B operand MN-major).  Used by tests/test_kernels_gpu.py only. */
 int mrmt3_test_gemm(mrmt3_handle* h, const void* a_bf16, const void* w_bf16, int M, int N, int K,
                     float* c_f32, int which, void* stream);
 
@@ -163,6 +169,15 @@ int mrmt3_generate(mrmt3_handle* h, const float* mel, int B, int max_length, int
 int mrmt3_generate_segmem(mrmt3_handle* h, const float* mel, const int32_t* seg_counts_host,
                           int n_tracks, int max_length, int64_t* out_ids, float* logits_out,
                           void* stream);
+
+/* Parity hook of mrmt3_generate_segmem (tests only): forced_ids (S_total, max_length+1) int64 feeds
+ * these tokens instead of the arg-max, row by row, so that every segment's memory block is built
+ * from the caller's (the oracle's) previous row and each step's logits can be compared at every
+ * position of every segment even after a low-margin token flip.  Rows are run for all max_length
+ * steps (no early exit).  Same reference lines as mrmt3_generate_segmem. */
+int mrmt3_generate_segmem_forced(mrmt3_handle* h, const float* mel, const int32_t* seg_counts_host,
+                                 int n_tracks, int max_length, const int64_t* forced_ids,
+                                 int64_t* out_ids, float* logits_out, void* stream);
 
 /* ---- teacher-forced forward ------------------------------------------------------------
  * Replaces: model.forward / get_model_outputs (models/t5.py:99-249,

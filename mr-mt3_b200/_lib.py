@@ -52,6 +52,8 @@ _PROTOTYPES = {
                                 _c_void_p, _c_void_p]),
     "mrmt3_generate_segmem": (_c_int, [_c_void_p, _c_void_p, _c_void_p, _c_int, _c_int, _c_void_p,
                                        _c_void_p, _c_void_p]),
+    "mrmt3_generate_segmem_forced": (_c_int, [_c_void_p, _c_void_p, _c_void_p, _c_int, _c_int, _c_void_p,
+                                              _c_void_p, _c_void_p, _c_void_p]),
     "mrmt3_forward_logits": (_c_int, [_c_void_p, _c_void_p, _c_int, _c_void_p, _c_int, _c_void_p, _c_int,
                                       _c_void_p, _c_void_p]),
     "mrmt3_memory_block": (_c_int, [_c_void_p, _c_void_p, _c_int, _c_int, _c_void_p, _c_void_p]),
@@ -171,11 +173,20 @@ class Engine:
         self._check(self._lib.mrmt3_set_option(self._h, key.encode(), int(value)))
 
     def test_gemm(self, a, w, which):
-        """C = a @ w.T through GEMM kernel `which` (0 mma.sync, 1 tcgen05, 2 decode single-shot)."""
+        """C = a @ w.T through GEMM kernel `which` (0 mma.sync, 1 tcgen05, 2 decode single-shot);
+        which = 4: C = a.T @ w for a (K, M), w (K, N) (weight-gradient form, split-K);
+        which = 5: C = a @ w for a (M, K), w (K, N) (data-gradient form)."""
         a = a.to(self.device, torch.bfloat16).contiguous()
         w = w.to(self.device, torch.bfloat16).contiguous()
-        M, K = a.shape
-        N = w.shape[0]
+        if which == 4:
+            K, M = a.shape
+            N = w.shape[1]
+        elif which == 5:
+            M, K = a.shape
+            N = w.shape[1]
+        else:
+            M, K = a.shape
+            N = w.shape[0]
         c = torch.empty((M, N), dtype=torch.float32, device=self.device)
         with torch.cuda.device(self.device):
             self._check(self._lib.mrmt3_test_gemm(self._h, _ptr(a), _ptr(w), M, N, K, _ptr(c), which, _stream()))
@@ -274,7 +285,7 @@ class Engine:
         ids = out[:, :1 + steps.value]
         return (ids, logits) if return_logits else ids
 
-    def generate_segmem(self, inputs, seg_counts=None, max_length=1024, return_logits=False):
+    def generate_segmem(self, inputs, seg_counts=None, max_length=1024, return_logits=False, forced_ids=None):
         x = self._mel(inputs)
         S = x.shape[0]
         counts = np.asarray([S] if seg_counts is None else seg_counts, dtype=np.int32)
@@ -284,9 +295,17 @@ class Engine:
         logits = torch.zeros((S, max_length, VOCAB), dtype=torch.float32, device=self.device) \
             if return_logits else None
         with torch.cuda.device(self.device):
-            self._check(self._lib.mrmt3_generate_segmem(
-                self._h, _ptr(x), counts.ctypes.data_as(ctypes.c_void_p), len(counts), max_length,
-                _ptr(out), _ptr(logits), _stream()))
+            if forced_ids is not None:
+                forced = forced_ids.to(self.device, torch.int64).contiguous()
+                if tuple(forced.shape) != (S, max_length + 1):
+                    raise MrMt3Error("forced_ids must be (S, max_length + 1)")
+                self._check(self._lib.mrmt3_generate_segmem_forced(
+                    self._h, _ptr(x), counts.ctypes.data_as(ctypes.c_void_p), len(counts), max_length,
+                    _ptr(forced), _ptr(out), _ptr(logits), _stream()))
+            else:
+                self._check(self._lib.mrmt3_generate_segmem(
+                    self._h, _ptr(x), counts.ctypes.data_as(ctypes.c_void_p), len(counts), max_length,
+                    _ptr(out), _ptr(logits), _stream()))
         return (out, logits) if return_logits else out
 
     def forward_logits(self, inputs, decoder_input_ids, targets_prev=None):

@@ -14,7 +14,8 @@ Status generate_base(mrmt3_handle* h, const float* mel_f32, const bf16* mel_bf16
                      long long* out_ids, int* steps_host, const long long* forced, float* logits_out,
                      cudaStream_t s);
 Status generate_segmem(mrmt3_handle* h, const float* mel_f32, const bf16* mel_bf16, const int* seg_counts,
-                       int n_tracks, int max_length, long long* out_ids, float* logits_out, cudaStream_t s);
+                       int n_tracks, int max_length, long long* out_ids, float* logits_out, cudaStream_t s,
+                       const long long* forced);
 Status api_memory_block(mrmt3_handle* h, const long long* prev_ids, int B, int Lp, float* mem_out, cudaStream_t s);
 Status api_forward_logits(mrmt3_handle* h, const float* mel, int B, const long long* dec_ids, int L,
                           const long long* targets_prev, int Lp, float* logits_out, cudaStream_t s);
@@ -122,6 +123,7 @@ int mrmt3_set_option(mrmt3_handle* h, const char* key, int value) {
     if (k == "group_lanes") h->group_lanes = value;
     else if (k == "use_graphs") h->use_graphs = value != 0;
     else if (k == "group_serial") h->group_serial = value != 0;
+    else if (k == "hooks_fast_path") h->hooks_fast_path = value != 0;
     else if (k == "train_dropout_sites") return finish(h, train_set_dropout_sites(h, value));
     else if (k == "attn_variant" || k == "attn_ring_stages" || k == "attn_ring_ctas" || k == "attn_ring_quartets") {
         // the kernel choice is baked into the captured step graphs
@@ -248,7 +250,17 @@ int mrmt3_generate_segmem(mrmt3_handle* h, const float* mel, const int32_t* seg_
     GUARD(h)
     if (!seg_counts_host) return finish(h, Error(1, "null seg_counts_host"));
     return finish(h, generate_segmem(h, mel, nullptr, seg_counts_host, n_tracks, max_length,
-                                     (long long*)out_ids, logits_out, (cudaStream_t)stream));
+                                     (long long*)out_ids, logits_out, (cudaStream_t)stream, nullptr));
+    END_GUARD(h)
+}
+
+int mrmt3_generate_segmem_forced(mrmt3_handle* h, const float* mel, const int32_t* seg_counts_host, int n_tracks,
+                                 int max_length, const int64_t* forced_ids, int64_t* out_ids, float* logits_out,
+                                 void* stream) {
+    GUARD(h)
+    if (!seg_counts_host || !forced_ids) return finish(h, Error(1, "null argument"));
+    return finish(h, generate_segmem(h, mel, nullptr, seg_counts_host, n_tracks, max_length, (long long*)out_ids,
+                                     logits_out, (cudaStream_t)stream, (const long long*)forced_ids));
     END_GUARD(h)
 }
 

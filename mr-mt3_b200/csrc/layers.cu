@@ -121,6 +121,7 @@ __global__ void embed_tokens_kernel(const long long* __restrict__ ids, const flo
     if (row >= rows) return;
     int c = (threadIdx.x & 127) * 4;
     long long id = ids[row];
+    if (id < 0 || id >= kVocab) id = 0;  // -100 (ignore_index) and junk read the pad row, never out of bounds
     int pos = pos0 + row % L;
     float4 e = *reinterpret_cast<const float4*>(emb + (size_t)id * kDModel + c);
     float4 p = *reinterpret_cast<const float4*>(pe + (size_t)pos * kDModel + c);
@@ -146,6 +147,7 @@ __global__ void embed_bf16_kernel(const long long* __restrict__ ids, long ids_ro
     int lane = row / rows_per_lane, j = row % rows_per_lane;
     long src_row = lane_src_row ? lane_src_row[lane] : lane;
     long long id = ids[src_row * ids_row_stride + j];
+    if (id < 0 || id >= kVocab) id = 0;  // targets_prev is padded with -100 (reference masks it to pad)
     float4 e = *reinterpret_cast<const float4*>(emb + (size_t)id * kDModel + c);
     *reinterpret_cast<uint2*>(out + (size_t)row * kDModel + c) =
         make_uint2(pack_bf16(e.x, e.y), pack_bf16(e.z, e.w));
@@ -249,7 +251,11 @@ __global__ void __launch_bounds__(256)
         if (t == 0) {
             const int n_emitted = step - st.prefix_len + 1;  // tokens emitted incl. this one
             int next = best_i;
-            if (st.forced) next = (int)st.forced[(size_t)lane * st.forced_stride + n_emitted];
+            if (st.forced) {
+                const size_t frow = st.forced_by_row ? (size_t)st.out_row[lane] : (size_t)lane;
+                const long long f = st.forced[frow * st.forced_stride + n_emitted];
+                next = (f < 0 || f >= vocab) ? st.pad_id : (int)f;
+            }
             st.out[(size_t)st.out_row[lane] * st.out_stride + n_emitted] = next;
             st.tok[lane] = next;
             bool done = (!st.forced && next == st.eos_id) || n_emitted >= st.max_tokens;

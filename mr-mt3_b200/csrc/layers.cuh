@@ -49,6 +49,7 @@ struct DecodeState {
     int prefix_len;       // V1 memory prefix length (0 otherwise): out col = step - prefix + 1
     const long long* forced;  // optional teacher forcing: (lanes, forced_stride) next-token ids
     int forced_stride;
+    int forced_by_row;        // 0: row = lane index; 1: row = out_row[lane] (MR-MT3: lanes change rows per round)
     int eos_id, pad_id;
     int max_tokens;       // stop a lane after this many emitted tokens
     TraceSlot trace;      // timeline trace slot of the kernel this state is passed to

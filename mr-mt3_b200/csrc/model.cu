@@ -203,9 +203,13 @@ static void destroy_graphs(mrmt3_handle* h) {
 
 void drop_graphs(mrmt3_handle* h) { destroy_graphs(h); }
 
+Status test_gemm_train(mrmt3_handle* h, const bf16* A, const bf16* W, int M, int N, int K, float* C, int which,
+                       cudaStream_t s);  // train.cu
+
 Status test_gemm(mrmt3_handle* h, const bf16* A, const bf16* W, int M, int N, int K, float* C, int which,
                  cudaStream_t s) {
     MRMT3_CUDA_TRY(cudaSetDevice(h->device));
+    if (which == 4 || which == 5) return test_gemm_train(h, A, W, M, N, K, C, which, s);
     const ARowMap id{nullptr, 1};
     if (which == 0) return launch_gemm_mma(A, K, id, W, K, M, N, K, EpiStoreF32{C, N}, s);
     if (which == 1) return launch_gemm_tc(*h->tma, A, K, M, id, W, K, M, N, K, EpiStoreF32{C, N}, s);
@@ -261,6 +265,10 @@ void handle_destroy(mrmt3_handle* h) {
     if (h->gfork) cudaEventDestroy(h->gfork);
 }
 
+// train.cu: keeps the fine-tune state consistent with weights (re)loaded after mrmt3_train_init
+Status train_on_set_weight(mrmt3_handle* h, const std::string& name, const float* staged_f32);
+void train_on_commit(mrmt3_handle* h);
+
 static Status pack(mrmt3_handle* h, const float* src, int rows, int cols, int want_rows,
                    int want_cols, bf16* dst, int row_mul, int row_off, float* master = nullptr) {
     if (rows != want_rows || cols != want_cols) {
@@ -274,6 +282,7 @@ static Status pack(mrmt3_handle* h, const float* src, int rows, int cols, int wa
     MRMT3_TRY(launch_pack_weight(h->stage.as<float>(), dst, rows, cols, row_mul, row_off, 0));
     if (master) MRMT3_TRY(launch_pack_weight_f32(h->stage.as<float>(), master, rows, cols, row_mul, row_off, 0));
     MRMT3_CUDA_TRY(cudaStreamSynchronize(0));
+    h->stage_holds_tensor = true;
     return OkStatus();
 }
 
@@ -288,6 +297,7 @@ Status set_weight(mrmt3_handle* h, const std::string& name, const float* data, i
     const int d = kDModel, in = kInner;
     Status st = OkStatus();
     bool known = true;
+    h->stage_holds_tensor = false;
     if (name == "proj.weight") st = pack(h, data, rows, cols, d, d, h->proj, 1, 0);
     else if (name == "decoder_embed_tokens.weight") st = copy_f32(data, rows, cols, kVocab * d, h->emb);
     else if (name == "lm_head.weight") st = pack(h, data, rows, cols, kVocab, d, h->lm_head, 1, 0, h->m_lm_head);
@@ -340,6 +350,8 @@ Status set_weight(mrmt3_handle* h, const std::string& name, const float* data, i
     }
     if (!known) return Error(3, "unknown state-dict key: " + name);
     if (!st.ok()) return Error(st.code, name + ": " + st.msg);
+    // a (re)load after mrmt3_train_init: the fp32 master of this tensor takes the exact value too
+    if (h->train && h->stage_holds_tensor) MRMT3_TRY(train_on_set_weight(h, name, h->stage.as<float>()));
     h->seen.insert(name);
     h->committed = false;
     return OkStatus();
@@ -395,6 +407,7 @@ Status commit_weights(mrmt3_handle* h) {
     MRMT3_TRY(launch_fold_norm(h->m_lm_head, h->dec.final_ln, h->lm_head_f, kVocab, kDModel, 0));
     MRMT3_CUDA_TRY(cudaStreamSynchronize(0));
     h->committed = true;
+    train_on_commit(h);
     return OkStatus();
 }
 
@@ -698,7 +711,7 @@ static Status enqueue_step(mrmt3_handle* h, const StepPlan& pl, int kind, cudaSt
 }
 
 static Status get_graph(mrmt3_handle* h, const StepPlan& pl, int kind, StepGraph** out) {
-    StepGraphKey key{pl.lane0, pl.n_lanes, pl.tk, pl.st.max_tokens, pl.st.prefix_len, kind};
+    StepGraphKey key{pl.lane0, pl.n_lanes, pl.tk, pl.st.max_tokens, pl.st.prefix_len, kind, pl.st.forced, pl.ext_logits};
     auto it = h->graphs.find(key);
     if (it != h->graphs.end()) {
         *out = &it->second;
@@ -737,7 +750,7 @@ static DecodeState group_state(const DecodeState& st, int lane0, int group) {
     g.active = st.active + lane0;
     g.finish_step = st.finish_step + lane0;
     g.out_row = st.out_row + lane0;
-    if (st.forced) g.forced = st.forced + (size_t)lane0 * st.forced_stride;
+    if (st.forced && !st.forced_by_row) g.forced = st.forced + (size_t)lane0 * st.forced_stride;
     return g;
 }
 
@@ -750,6 +763,11 @@ static DecodeState group_state(const DecodeState& st, int lane0, int group) {
 // small latency-bound projections, so a single chain leaves HBM idle most of the time; several
 // chains in flight let one group's attention (HBM-bound) overlap the others' projections.
 static Status run_decode(mrmt3_handle* h, StepPlan pl, int n_prefix, bool debug_mode, cudaStream_t s) {
+    if (h->hooks_fast_path) debug_mode = false;
+    if (h->graphs.size() > 256) {  // hook pointers are part of the key and change per call: bound the cache
+        MRMT3_CUDA_TRY(cudaDeviceSynchronize());
+        destroy_graphs(h);
+    }
     const bool graphs = h->use_graphs && !debug_mode && !h->prof_on;
     int G = 1;
     // default group size (group_lanes < 0): 32 lanes, 16 for small batches (MR-MT3 with one lane per
@@ -879,8 +897,8 @@ Status generate_base(mrmt3_handle* h, const float* mel_f32, const bf16* mel_bf16
                      long long* out_ids, int* steps_host, const long long* forced, float* logits_out,
                      cudaStream_t s) {
     if (!h->committed) return Error(5, "weights not committed");
-    if (h->cfg.mem_variant != MRMT3_MEM_NONE)
-        return Error(2, "mrmt3_generate is the plain MT3 loop; use mrmt3_generate_segmem for memory variants");
+    // a handle with a memory variant may run this loop too: T5SegMem.generate (reference
+    // models/t5_segmem.py:254-311) is the plain batched loop, its memory weights unused
     if (B <= 0 || max_length <= 0) return Error(2, "B and max_length must be positive");
     MRMT3_CUDA_TRY(cudaSetDevice(h->device));
     const int stride = max_length + 1;
@@ -923,7 +941,7 @@ Status generate_base(mrmt3_handle* h, const float* mel_f32, const bf16* mel_bf16
 // MR-MT3 greedy transcription batched across tracks (see include/mrmt3_b200.h).
 Status generate_segmem(mrmt3_handle* h, const float* mel_f32, const bf16* mel_bf16, const int* seg_counts,
                        int n_tracks, int max_length, long long* out_ids, float* logits_out,
-                       cudaStream_t s) {
+                       cudaStream_t s, const long long* forced) {
     if (!h->committed) return Error(5, "weights not committed");
     if (h->cfg.mem_variant == MRMT3_MEM_NONE) return Error(2, "model has no memory variant");
     if (n_tracks <= 0 || max_length <= 0) return Error(2, "n_tracks and max_length must be positive");
@@ -1009,10 +1027,16 @@ Status generate_segmem(mrmt3_handle* h, const float* mel_f32, const bf16* mel_bf
             pl.n_lanes = n;
             pl.tk = tk;
             pl.st = make_state(h, tok, stride, max_length, prefix, nullptr);
+            if (forced) {
+                // parity hook: lane i is fed row out_row[i] of `forced` (S_total, max_length + 1), so
+                // every segment's memory block is built from the caller's tokens, not the arg-max
+                pl.st.forced = forced;
+                pl.st.forced_by_row = 1;
+            }
             pl.prefix = v1 ? h->mem_f32.as<float>() : nullptr;
             pl.ext_logits = logits_out;
             RUN(h, launch_decode_init(pl.st, n, a.init_active, n_active, h->cfg.start_id, kMaxGroups, kGroupScalars, s));
-            MRMT3_TRY(run_decode(h, pl, prefix, logits_out != nullptr, s));
+            MRMT3_TRY(run_decode(h, pl, prefix, logits_out != nullptr || forced != nullptr, s));
         }
     }
     // 4. (S, max_length+1) -> (S, max_length): F.pad incl. the negative pad that drops the last
@@ -1168,7 +1192,7 @@ Status api_transcribe_host(mrmt3_handle* h, const float* audio_host, long long n
     MRMT3_TRY(ids.reserve((size_t)n_seg * width * sizeof(long long)));
     if (mem)
         MRMT3_TRY(generate_segmem(h, nullptr, h->mel_bf16.as<bf16>(), seg_counts_host, n_tracks, max_length,
-                                  ids.as<long long>(), nullptr, s));
+                                  ids.as<long long>(), nullptr, s, nullptr));
     else
         MRMT3_TRY(generate_base(h, nullptr, h->mel_bf16.as<bf16>(), n_seg, max_length, ids.as<long long>(),
                                 steps_host, nullptr, nullptr, s));

@@ -57,7 +57,11 @@ struct RowWorkspace {
 
 struct StepGraphKey {
     int lane0, n_lanes, tk, max_tokens, prefix_len, kind;  // kind 0 = token step, 1 = prefix step
+    // parity hooks baked into the step (forced tokens, per-step logits sink); null on the plain path
+    const void *forced, *ext_logits;
     bool operator<(const StepGraphKey& o) const {
+        if (forced != o.forced) return forced < o.forced;
+        if (ext_logits != o.ext_logits) return ext_logits < o.ext_logits;
         if (lane0 != o.lane0) return lane0 < o.lane0;
         if (n_lanes != o.n_lanes) return n_lanes < o.n_lanes;
         if (tk != o.tk) return tk < o.tk;
@@ -110,6 +114,7 @@ struct mrmt3_handle {
     bool have_inv_freq = false;
     std::set<std::string> seen;
     mrmt3::DeviceBuffer stage;           // fp32 staging for set_weight
+    bool stage_holds_tensor = false;     // the last set_weight left its fp32 tensor in `stage`
 
     // ---- workspaces ----
     mrmt3::RowWorkspace rows;
@@ -142,6 +147,9 @@ struct mrmt3_handle {
     // latency-bound projections overlap another group's HBM-bound attention
     int group_lanes = -1;            // < 0: by batch size (run_decode)
     bool group_serial = false;
+    // parity hooks (forced tokens / per-step logits) normally run eagerly as one lane group; with
+    // this set they go through the production path (CUDA-graph replay, concurrent lane groups)
+    bool hooks_fast_path = false;
     mrmt3::DeviceBuffer trace_buf;       // 2 x u64 per decode-step kernel slot (mrmt3_trace_*)
     bool trace_on = false;           // debugging: run the groups one after another on one stream
     cudaStream_t gstream[16] = {nullptr};

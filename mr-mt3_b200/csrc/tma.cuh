@@ -49,17 +49,26 @@ public:
                                  estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
                                  CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
             if (r != CUDA_SUCCESS) return Error(2, "cuTensorMapEncodeTiled failed with code " + std::to_string((int)r));
-            if (maps_.size() > 4096) maps_.clear();
+            // bound the cache without invalidating pointers handed out recently: the full map becomes
+            // the previous generation (its nodes keep their addresses) and is only destroyed at the
+            // NEXT rotation, thousands of lookups later
+            if (maps_.size() > 4096) {
+                old_ = std::move(maps_);
+                maps_.clear();
+            }
             it = maps_.emplace(key, m).first;
         }
         *out = &it->second;
         return OkStatus();
     }
-    void clear() { maps_.clear(); }
+    void clear() {
+        maps_.clear();
+        old_.clear();
+    }
 
 private:
     typedef std::tuple<const void*, long, int, int, int> Key;
-    std::map<Key, CUtensorMap> maps_;
+    std::map<Key, CUtensorMap> maps_, old_;
     PFN_tmapEncodeTiled encode_ = nullptr;
 };
 

@@ -67,6 +67,7 @@ struct TrainState {
     float* loss_pinned = nullptr;  // pinned landing spot of the loss scalar
     const long long* dec_ids = nullptr;
     DeviceBuffer ids_copy;
+    bool reloaded = false;  // weights were set after train_init: the optimizer state restarts at the next commit
 };
 
 static TrainState* state(mrmt3_handle* h) { return reinterpret_cast<TrainState*>(h->train); }
@@ -184,6 +185,37 @@ Status train_init(mrmt3_handle* h) {
 
 size_t train_param_count(mrmt3_handle* h) { return state(h) ? state(h)->n_total : 0; }
 
+Status train_locate(mrmt3_handle* h, const std::string& name, long long* offset, int* rows, int* cols,
+                    int* row_mul, int* row_off);
+
+// mrmt3_set_weight after mrmt3_train_init (a checkpoint loaded into the module, a torch optimizer
+// step on the mirror parameters): the tensor's fp32 master takes the exact fp32 value that was just
+// staged, so that the next AdamW step starts from the loaded weights and not from stale masters.
+// Tensors whose parameter IS the fp32 arena copy (embedding, norms) were already overwritten in place.
+Status train_on_set_weight(mrmt3_handle* h, const std::string& name, const float* staged_f32) {
+    TrainState* t = state(h);
+    if (!t) return OkStatus();
+    long long off = 0;
+    int rows = 0, cols = 0, mul = 1, ro = 0;
+    Status st = train_locate(h, name, &off, &rows, &cols, &mul, &ro);
+    if (!st.ok()) return OkStatus();  // not a trainable tensor (aliases, inv_freq)
+    MRMT3_TRY(launch_pack_weight_f32(staged_f32, t->master.as<float>() + off, rows, cols, mul, ro, 0));
+    MRMT3_CUDA_TRY(cudaStreamSynchronize(0));
+    t->reloaded = true;
+    return OkStatus();
+}
+
+// mrmt3_commit_weights after such a reload: Adam moments and the step count restart (the loaded
+// weights are a new starting point; torch keeps optimizer state outside the model the same way)
+void train_on_commit(mrmt3_handle* h) {
+    TrainState* t = state(h);
+    if (!t || !t->reloaded) return;
+    cudaMemset(t->m.p, 0, t->n_total * 4);
+    cudaMemset(t->v.p, 0, t->n_total * 4);
+    t->step = 0;
+    t->reloaded = false;
+}
+
 // flat fp32 copy of every trainable tensor (packed order), e.g. to rebuild a state dict after training
 Status train_read_master(mrmt3_handle* h, float* out, cudaStream_t s) {
     TrainState* t = state(h);
@@ -245,18 +277,65 @@ Status train_locate(mrmt3_handle* h, const std::string& name, long long* offset,
     return Error(3, "no trainable tensor named " + name);
 }
 
+// dW (N, Kin) fp32 = dY^T . X with dY (M, N) pitch ldy and X (M, Kin) pitch ldx, both row-major and
+// used as they lie (MN-major tcgen05 operands).  The output has only (N / 128) x (Kin / BN) tiles:
+// the long reduction over M is split over the SMs (partials in `wpart`, 16 x the largest weight).
+Status wgrad_gemm(mrmt3_handle* h, const bf16* dY, int ldy, int N, const bf16* X, int ldx, int Kin, float* dW, size_t M,
+                  float* wpart, cudaStream_t s, int* splits_out) {
+    const int bn = Kin % 256 == 0 ? 256 : (Kin % 192 == 0 ? 192 : (Kin % 128 == 0 ? 128 : 64));
+    const int out_tiles = ceil_div(N, 128) * (Kin / bn);
+    const int blocks = (int)((M + 63) / 64);
+    int splits = 1;
+    while (splits < 16 && out_tiles * splits * 2 <= 160 && splits * 2 <= blocks) splits *= 2;
+    if (splits_out) *splits_out = splits;
+    if (splits == 1) {
+        RUN(h, launch_gemm_tc_mn(*h->tma, dY, ldy, N, X, ldx, Kin, (int)M, EpiStoreF32{dW, Kin}, s));
+    } else {
+        RUN(h, launch_gemm_tc_mn(*h->tma, dY, ldy, N, X, ldx, Kin, (int)M, EpiStoreF32{wpart, Kin}, s, splits));
+        RUN(h, launch_reduce_splits(wpart, dW, (size_t)N * Kin, splits, s));
+    }
+    return OkStatus();
+}
+
+// test hook (mrmt3_test_gemm which = 4 / 5): the backward's two GEMM forms on caller data
+Status test_gemm_train(mrmt3_handle* h, const bf16* A, const bf16* W, int M, int N, int K, float* C, int which,
+                       cudaStream_t s) {
+    if (which == 4) {  // C (M, N) = A^T W: A (K, M), W (K, N) row-major, reduction over the K rows (split-K as wgrad)
+        DeviceBuffer part;
+        MRMT3_TRY(part.reserve((size_t)16 * M * N * 4));
+        Status st = wgrad_gemm(h, A, M, M, W, N, N, C, (size_t)K, part.as<float>(), s, nullptr);
+        cudaStreamSynchronize(s);
+        part.release();
+        return st;
+    }
+    // which == 5: C (M, N) = A W: A (M, K) K-major, W (K, N) row-major taken MN-major (the dgrad form)
+    RUN(h, launch_gemm_tc_nn(*h->tma, A, K, M, W, N, N, K, EpiStoreF32{C, N}, s));
+    return OkStatus();
+}
+
 // ---------------------------------------------------------------------------------------------
 struct Bump {
     char* p;
     size_t used = 0, cap;
+    bool overflow = false;
+    // a request past the reservation sets `overflow` and returns the base (valid memory): callers
+    // check the flag BEFORE launching anything that would write through the pointer
     template <class T>
     T* take(size_t n) {
         used = (used + 255) & ~size_t(255);
         T* r = reinterpret_cast<T*>(p + used);
         used += n * sizeof(T);
+        if (used > cap) {
+            overflow = true;
+            return reinterpret_cast<T*>(p);
+        }
         return r;
     }
 };
+#define BUMP_CHECK(bp)                                                                                    \
+    do {                                                                                                  \
+        if ((bp).overflow) return Error(2, "internal: activation stash / scratch reservation too small"); \
+    } while (0)
 
 static size_t keep_bytes(size_t nb, size_t Tq, size_t Tk) { return nb * kHeads * Tq * ((Tk + 63) / 64) * 8; }
 
@@ -279,6 +358,7 @@ Status train_forward(mrmt3_handle* h, const float* mel, int B, const long long* 
     MRMT3_TRY(train_init(h));
     TrainState* t = state(h);
     if (B <= 0 || L <= 0 || B > kMaxTrainBatch) return Error(2, "bad batch or length");
+    if (L > h->n_pos || Lp > h->n_pos) return Error(2, "L / Lp exceed the positional table (reference FixedPositionalEmbedding max_length 5000)");
     MRMT3_CUDA_TRY(cudaSetDevice(h->device));
     const int n_enc = h->cfg.n_enc_layers, n_dec = h->cfg.n_dec_layers;
     const bool with_mem = h->cfg.mem_variant == MRMT3_MEM_V2_APPEND;
@@ -301,19 +381,21 @@ Status train_forward(mrmt3_handle* h, const float* mel, int B, const long long* 
     t->B = B;
     t->L = L;
     MRMT3_TRY(t->ids_copy.reserve(Md * sizeof(long long)));
-    MRMT3_CUDA_TRY(cudaMemcpyAsync(t->ids_copy.p, dec_ids, Md * sizeof(long long), cudaMemcpyDeviceToDevice, s));
+    RUN(h, launch_sanitize_ids(dec_ids, t->ids_copy.as<long long>(), Md, h->cfg.pad_id, s));
     t->dec_ids = t->ids_copy.as<long long>();
 
     // ---- encoder (reference models/t5.py:253-258) ----
     t->mel16 = bp.take<bf16>(Me * kMels);
-    RUN(h, launch_cast_bf16(mel, t->mel16, Me * kMels, s));
     float* H = bp.take<float>(Me * kDModel);  // residual stream: every sublayer writes its output into a fresh buffer
+    BUMP_CHECK(bp);
+    RUN(h, launch_cast_bf16(mel, t->mel16, Me * kMels, s));
     RUN(h, launch_gemm_tc(*h->tma, t->mel16, kDModel, Me, id, h->proj, kDModel, (int)Me, kDModel, kDModel,
                           EpiPosAdd{H, kDModel, h->pe, kSegFrames, 0}, s));
     auto attn_fwd = [&](const bf16* Q, long qb, int qr, const bf16* K, const bf16* V, long kb, long kh, int kr, bf16* O,
                         int Tq, int Tk, int causal, float* lse, int nb, DropSpec drop, unsigned short*& keep) -> Status {
         AttnFullParams ap{};
         keep = drop.on() ? bp.take<unsigned short>(keep_bytes(nb, Tq, Tk) / 2) : nullptr;
+        BUMP_CHECK(bp);
         ap.keep = keep;
         ap.Q = Q; ap.q_batch_stride = qb; ap.q_head_stride = kDKV; ap.q_row_stride = qr;
         ap.K = K; ap.V = V;
@@ -329,6 +411,7 @@ Status train_forward(mrmt3_handle* h, const float* mel, int B, const long long* 
     // activation the backward needs for this sublayer's norm, so it stays in the stash as it is
     auto out_proj = [&](const bf16* A, int K, const bf16* W, float*& Hres, size_t M, DropSpec drop) -> Status {
         float* Hnew = bp.take<float>(M * kDModel);
+        BUMP_CHECK(bp);
         RUN(h, launch_gemm_tc(*h->tma, A, K, M, id, W, K, (int)M, kDModel, K, EpiResidualTo{Hres, Hnew, kDModel, drop}, s));
         Hres = Hnew;
         return OkStatus();
@@ -338,6 +421,7 @@ Status train_forward(mrmt3_handle* h, const float* mel, int B, const long long* 
         st.n2 = bp.take<bf16>(M * kDModel);
         st.raw = bp.take<bf16>(M * 2 * kDFF);
         st.ff = bp.take<bf16>(M * kDFF);
+        BUMP_CHECK(bp);
         RUN(h, launch_rmsnorm(Hres, Lw.ln_ff, eps, st.n2, nullptr, (int)M, nullptr, 1, s));
         RUN(h, launch_gemm_tc(*h->tma, st.n2, kDModel, M, id, Lw.wi, kDModel, (int)M, 2 * kDFF, kDModel,
                               EpiStoreBf16{st.raw, 2 * kDFF}, s));
@@ -352,6 +436,7 @@ Status train_forward(mrmt3_handle* h, const float* mel, int B, const long long* 
         st.qkv = bp.take<bf16>(M * 3 * kInner);
         st.ctx = bp.take<bf16>(M * kInner);
         st.lse = bp.take<float>((size_t)nb * kHeads * T);
+        BUMP_CHECK(bp);
         RUN(h, launch_rmsnorm(Hres, Lw.ln_self, eps, st.n1, nullptr, (int)M, nullptr, 1, s));
         RUN(h, launch_gemm_tc(*h->tma, st.n1, kDModel, M, id, Lw.wqkv, kDModel, (int)M, 3 * kInner, kDModel,
                               EpiStoreBf16{st.qkv, 3 * kInner}, s));
@@ -369,6 +454,7 @@ Status train_forward(mrmt3_handle* h, const float* mel, int B, const long long* 
     }
     t->enc_h_final = H;
     t->enc_n_final = bp.take<bf16>(Me * kDModel);
+    BUMP_CHECK(bp);
     RUN(h, launch_rmsnorm(H, h->enc.final_ln, eps, t->enc_n_final, nullptr, (int)Me, nullptr, 1, s));
     RUN(h, launch_dropout_bf16(t->enc_n_final, Me * kDModel, mk(0, 0, kSiteFinal), s));
 
@@ -376,11 +462,12 @@ Status train_forward(mrmt3_handle* h, const float* mel, int B, const long long* 
     //      (+PE) -> memory encoder over all Lp positions -> final norm -> first n_mem rows ----
     if (with_mem) {
         MRMT3_TRY(t->prev_copy.reserve(Mm * sizeof(long long)));
-        MRMT3_CUDA_TRY(cudaMemcpyAsync(t->prev_copy.p, targets_prev, Mm * sizeof(long long), cudaMemcpyDeviceToDevice, s));
+        RUN(h, launch_sanitize_ids(targets_prev, t->prev_copy.as<long long>(), Mm, h->cfg.pad_id, s));
         t->prev_ids = t->prev_copy.as<long long>();
         t->mem_emb16 = bp.take<bf16>(Mm * kDModel);
-        RUN(h, launch_embed_bf16(t->prev_ids, Lp, Lp, B, nullptr, h->emb, t->mem_emb16, s));
         float* Hm = bp.take<float>(Mm * kDModel);
+        BUMP_CHECK(bp);
+        RUN(h, launch_embed_bf16(t->prev_ids, Lp, Lp, B, nullptr, h->emb, t->mem_emb16, s));
         RUN(h, launch_gemm_tc(*h->tma, t->mem_emb16, kDModel, Mm, id, h->segmem_proj, kDModel, (int)Mm, kDModel, kDModel,
                               EpiPosAdd{Hm, kDModel, h->pe, Lp, 0}, s));
         t->mem_st.assign(h->cfg.n_mem_layers, LayerStash{});
@@ -390,12 +477,14 @@ Status train_forward(mrmt3_handle* h, const float* mel, int B, const long long* 
         }
         t->mem_h_final = Hm;
         t->mem_n_final = bp.take<bf16>(Mm * kDModel);
+        BUMP_CHECK(bp);
         RUN(h, launch_rmsnorm(Hm, h->mem.final_ln, eps, t->mem_n_final, nullptr, (int)Mm, nullptr, 1, s));
     }
 
     // ---- cross K/V of all decoder layers: rows [encoder states ; memory rows] per sample ----
     MRMT3_TRY(ensure_decode_capacity(h, B, tk, 1));
     t->kv_in = bp.take<bf16>((size_t)B * tk * kDModel);
+    BUMP_CHECK(bp);
     MRMT3_CUDA_TRY(cudaMemcpy2DAsync(t->kv_in, (size_t)tk * kDModel * 2, t->enc_n_final, (size_t)kSegFrames * kDModel * 2,
                                      (size_t)kSegFrames * kDModel * 2, B, cudaMemcpyDeviceToDevice, s));
     if (n_mem)
@@ -407,6 +496,7 @@ Status train_forward(mrmt3_handle* h, const float* mel, int B, const long long* 
 
     // ---- decoder, teacher forced (reference models/t5.py:99-180) ----
     float* Hd = bp.take<float>(Md * kDModel);
+    BUMP_CHECK(bp);
     RUN(h, launch_embed_tokens(t->dec_ids, h->emb, h->pe, Hd, B, L, 0, s));
     RUN(h, launch_dropout_f32(Hd, Md * kDModel, mk(1, 0, kSiteInput), s));
     t->dec_st.assign(n_dec, LayerStash{});
@@ -420,6 +510,7 @@ Status train_forward(mrmt3_handle* h, const float* mel, int B, const long long* 
         st.qc = bp.take<bf16>(Md * kInner);
         st.ctx_c = bp.take<bf16>(Md * kInner);
         st.lse_c = bp.take<float>((size_t)B * kHeads * L);
+        BUMP_CHECK(bp);
         RUN(h, launch_rmsnorm(Hd, Lw.ln_cross, eps, st.nc, nullptr, (int)Md, nullptr, 1, s));
         RUN(h, launch_gemm_tc(*h->tma, st.nc, kDModel, Md, id, Lw.cq, kDModel, (int)Md, kInner, kDModel,
                               EpiStoreBf16{st.qc, kInner}, s));
@@ -431,17 +522,16 @@ Status train_forward(mrmt3_handle* h, const float* mel, int B, const long long* 
     }
     t->dec_h_final = Hd;
     t->dec_n_final = bp.take<bf16>(Md * kDModel);
+    t->dlogits = bp.take<bf16>(Md * kVocab);
+    t->row_loss = bp.take<float>(Md);
+    float* scal = bp.take<float>(2);
+    BUMP_CHECK(bp);
     RUN(h, launch_rmsnorm(Hd, h->dec.final_ln, eps, t->dec_n_final, nullptr, (int)Md, nullptr, 1, s));
     RUN(h, launch_dropout_bf16(t->dec_n_final, Md * kDModel, mk(1, 0, kSiteFinal), s));
     RUN(h, launch_gemm_tc(*h->tma, t->dec_n_final, kDModel, Md, id, h->lm_head, kDModel, (int)Md, kVocab, kDModel,
                           EpiStoreF32{logits_out, kVocab}, s));
 
     // ---- loss (tasks/mt3_net.py: CrossEntropyLoss(ignore_index=-100) over (B*L, V)) ----
-    t->dlogits = bp.take<bf16>(Md * kVocab);
-    t->row_loss = bp.take<float>(Md);
-    if (bp.used > bp.cap) return Error(2, "internal: activation stash overflow");
-    float* scal = bp.take<float>(2);
-    if (bp.used > bp.cap) return Error(2, "internal: activation stash overflow");
     RUN(h, launch_xent(logits_out, labels, (int)Md, kVocab, scal, t->row_loss, t->dlogits, s));
     h->launches += 2;
     // the only host round trip of the forward, and only when the caller wants the number now
@@ -494,7 +584,7 @@ Status train_backward(mrmt3_handle* h, float* grad, const float* dlogits_f32, cu
     void* emb_scratch = bp.take<char>(embed_bwd_scratch_bytes((int)Mmax));
     float* norm_parts = bp.take<float>((size_t)kNormBwdMaxNorms * kNormBwdMaxParts * kDModel);
     NormDgList norm_list{};
-    if (bp.used > bp.cap) return Error(2, "internal: backward scratch overflow");
+    BUMP_CHECK(bp);
 
     // optional per-category timing (MRMT3_TRAIN_PROFILE=1): CUDA events around every backward op
     static const bool prof = getenv("MRMT3_TRAIN_PROFILE") && atoi(getenv("MRMT3_TRAIN_PROFILE")) != 0;
@@ -526,20 +616,8 @@ Status train_backward(mrmt3_handle* h, float* grad, const float* dlogits_f32, cu
     };
     // dW (N, Kin) fp32 = dY^T . X ; dY (M, N) with pitch ldy, X (M, Kin) with pitch ldx
     auto wgrad = [&](const bf16* dY, int ldy, int N, const bf16* X, int ldx, int Kin, float* dW, size_t M) -> Status {
-        // both operands straight from their row-major buffers (MN-major tcgen05 operands).  The output
-        // has only (N / 128) x (Kin / BN) tiles: split the long reduction over the SMs
-        const int bn = Kin % 256 == 0 ? 256 : (Kin % 192 == 0 ? 192 : (Kin % 128 == 0 ? 128 : 64));
-        const int out_tiles = ceil_div(N, 128) * (Kin / bn);
-        const int blocks = (int)((M + 63) / 64);
-        int splits = 1;
-        while (splits < 16 && out_tiles * splits * 2 <= 160 && splits * 2 <= blocks) splits *= 2;
         tic("wgrad gemm");
-        if (splits == 1) {
-            RUN(h, launch_gemm_tc_mn(*h->tma, dY, ldy, N, X, ldx, Kin, (int)M, EpiStoreF32{dW, Kin}, s));
-        } else {
-            RUN(h, launch_gemm_tc_mn(*h->tma, dY, ldy, N, X, ldx, Kin, (int)M, EpiStoreF32{wpart, Kin}, s, splits));
-            RUN(h, launch_reduce_splits(wpart, dW, (size_t)N * Kin, splits, s));
-        }
+        MRMT3_TRY(wgrad_gemm(h, dY, ldy, N, X, ldx, Kin, dW, M, wpart, s, nullptr));
         toc();
         return OkStatus();
     };

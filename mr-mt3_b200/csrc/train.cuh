@@ -31,6 +31,7 @@ Status launch_dropout_cast(const float* in, bf16* out, size_t n, DropSpec drop, 
 size_t embed_bwd_scratch_bytes(int rows);
 Status launch_embed_bwd(const long long* ids, const float* dH, float* dEmb, int rows, void* scratch, cudaStream_t s);
 Status launch_cast_f32_bf16(const float* in, bf16* out, size_t n, cudaStream_t s);
+Status launch_sanitize_ids(const long long* in, long long* out, size_t n, int pad, cudaStream_t s);
 Status launch_bf16_to_f32(const bf16* in, float* out, size_t n, cudaStream_t s);
 Status launch_reduce_splits(const float* partials, float* out, size_t n, int splits, cudaStream_t s);
 Status launch_adamw(float* p, const float* g, float* m, float* v, bf16* p_bf16, size_t n, float lr, float beta1,

@@ -25,10 +25,10 @@ namespace mrmt3 {
 // cross-entropy, all on the device so that the forward needs no host round trip:
 //   scal[0] = 1 / #(labels != ignore_index), row losses + logits gradient, scal[1] = mean loss
 __global__ void __launch_bounds__(1024)
-    xent_count_kernel(const long long* __restrict__ labels, int rows, float* __restrict__ scal) {
+    xent_count_kernel(const long long* __restrict__ labels, int rows, int V, float* __restrict__ scal) {
     __shared__ int part[32];
     int c = 0;
-    for (int i = threadIdx.x; i < rows; i += 1024) c += labels[i] >= 0;
+    for (int i = threadIdx.x; i < rows; i += 1024) c += labels[i] >= 0 && labels[i] < V;
     c = (int)warp_sum((float)c);  // <= 32 * ceil(rows / 1024): exact in fp32 for any batch the stash can hold
     if ((threadIdx.x & 31) == 0) part[threadIdx.x >> 5] = c;
     __syncthreads();
@@ -64,7 +64,7 @@ __global__ void __launch_bounds__(256)
     const float* x = logits + (size_t)row * V;
     bf16* dx = dlogits + (size_t)row * V;
     const long long label = labels[row];
-    if (label < 0) {  // ignore_index
+    if (label < 0 || label >= V) {  // ignore_index (and anything that is not a class: never indexed)
         if (lane == 0) row_loss[row] = 0.f;
         for (int j = lane * 2; j < V; j += 64) *reinterpret_cast<uint32_t*>(dx + j) = 0u;
         return;
@@ -88,7 +88,7 @@ __global__ void __launch_bounds__(256)
 Status launch_xent(const float* logits, const long long* labels, int rows, int V, float* scal,
                    float* row_loss, bf16* dlogits, cudaStream_t s) {
     if (rows <= 0) return OkStatus();
-    xent_count_kernel<<<1, 1024, 0, s>>>(labels, rows, scal);
+    xent_count_kernel<<<1, 1024, 0, s>>>(labels, rows, V, scal);
     MRMT3_CHECK_LAUNCH();
     xent_kernel<<<ceil_div(rows, 8), 256, 0, s>>>(logits, labels, rows, V, scal, row_loss, dlogits);
     MRMT3_CHECK_LAUNCH();
@@ -475,6 +475,22 @@ __global__ void cast_f32_bf16_kernel(const float* __restrict__ in, bf16* __restr
     if (i + 1 < n) *reinterpret_cast<uint32_t*>(out + i) = pack_bf16(in[i], in[i + 1]);
     else if (i < n) out[i] = __float2bfloat16(in[i]);
 }
+// token ids as the embedding kernels read them: anything outside [0, vocab) -- the -100 padding of
+// targets_prev in particular (reference models/t5_segmem_v2_with_prev.py:119 masks it to pad) --
+// becomes the pad id, so that the forward gather and the backward scatter agree on the row
+__global__ void sanitize_ids_kernel(const long long* __restrict__ in, long long* __restrict__ out, size_t n, int pad) {
+    size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const long long v = in[i];
+    out[i] = (v < 0 || v >= kVocab) ? (long long)pad : v;
+}
+Status launch_sanitize_ids(const long long* in, long long* out, size_t n, int pad, cudaStream_t s) {
+    if (n == 0) return OkStatus();
+    sanitize_ids_kernel<<<(unsigned)((n + 255) / 256), 256, 0, s>>>(in, out, n, pad);
+    MRMT3_CHECK_LAUNCH();
+    return OkStatus();
+}
+
 Status launch_cast_f32_bf16(const float* in, bf16* out, size_t n, cudaStream_t s) {
     if (!n) return OkStatus();
     cast_f32_bf16_kernel<<<(unsigned)((n / 2 + 256) / 256), 256, 0, s>>>(in, out, n);

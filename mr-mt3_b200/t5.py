@@ -10,7 +10,9 @@ and checkpoints keep working; its sub-modules have no forward of their own.
 Differences from the reference, all deliberate:
   * `generate` uses a KV cache (the reference re-runs the whole prefix every step, SURVEY D2);
     results are the reference's up to bf16 rounding (tests/test_parity_gpu.py).
-  * `forward` has no autograd graph (inference / evaluation only in this round).
+  * in training mode with autograd enabled, `forward` returns logits whose grad_fn is the
+    hand-written CUDA backward (`_TrainForward`); dropout follows `config.dropout_rate` with a
+    counter-based mask stream instead of torch's.
   * errors raise (`_lib.MrMt3Error`) instead of being swallowed.
 """
 import copy
@@ -152,8 +154,7 @@ class _TrainForward(torch.autograd.Function):
 
     @staticmethod
     def forward(ctx, model, inputs, decoder_input_ids, targets_prev, *params):
-        eng = model.engine()
-        eng.train_init()
+        eng = model._train_engine()
         # training mode applies the reference's dropout (config.dropout_rate, models/t5.py:493) with
         # a fresh mask seed drawn from torch's generator, so torch.manual_seed makes a run repeatable
         p = float(getattr(model.config, "dropout_rate", 0.0) or 0.0)
@@ -305,8 +306,7 @@ class T5ForConditionalGeneration(nn.Module):
         The engine's weights are updated in place; `sync_parameters_from_engine()` copies them back
         into this module's parameters.  `dropout` (default: leave the engine's setting, initially 0)
         is the reference's config.dropout_rate; `seed` fixes this step's masks."""
-        eng = self.engine()
-        eng.train_init()
+        eng = self._train_engine()
         if dropout is not None:
             eng.train_set_dropout(dropout, int(torch.randint(0, 2 ** 62, (1,)).item()) if seed is None else seed)
         if targets_prev is not None:
@@ -318,6 +318,16 @@ class T5ForConditionalGeneration(nn.Module):
         if apply:
             eng.train_apply(grad, lr, betas, eps, weight_decay)
         return loss, grad
+
+    def _train_engine(self):
+        """The engine with its fine-tune state allocated.  The first call re-sends the fp32 state dict
+        after mrmt3_train_init, so that the AdamW masters start from the exact fp32 parameters (as the
+        reference's optimizer does) and not from the bf16 inference copies."""
+        eng = self.engine()
+        if not getattr(eng, "_n_params", None):
+            eng.train_init()
+            eng.load_state_dict(self.state_dict(), strict=True)
+        return eng
 
     @torch.no_grad()
     def sync_parameters_from_engine(self):
@@ -340,8 +350,8 @@ class T5ForConditionalGeneration(nn.Module):
 
     def forward(self, inputs=None, labels=None, decoder_input_ids=None, **kwargs):
         """Reference models/t5.py:182-249: returns the logits tensor only.  In training mode with
-        autograd enabled the logits carry a grad_fn whose backward is the CUDA backward pass
-        (no dropout is applied)."""
+        autograd enabled the logits carry a grad_fn whose backward is the CUDA backward pass, and
+        `config.dropout_rate` is applied at the reference's sites (`_TrainForward`)."""
         kwargs.pop("num_insts", None)
         if self.training and torch.is_grad_enabled():
             return self._forward_with_grad(inputs, labels, decoder_input_ids)

@@ -49,13 +49,17 @@ class T5SegMem(T5ForConditionalGeneration):
 
     @torch.no_grad()
     def generate(self, inputs, max_length=1024, output_hidden_states=False, **kwargs):
-        """The reference's T5SegMem.generate (models/t5_segmem.py:254-311) decodes WITHOUT the
-        memory block, one segment at a time; that equals the plain MT3 loop on each segment,
-        padded to max_length with the same negative-pad rule."""
-        raise NotImplementedError(
-            "T5SegMem.generate (no-memory path) is unused by the reference's shipped experiments; "
-            "use generate_2 (with memory) or the plain T5ForConditionalGeneration")
+        """Reference models/t5_segmem.py:254-311: T5SegMem.generate decodes WITHOUT the memory block --
+        it is the plain batched greedy loop of models/t5.py:251-302 over encoder + decoder (the
+        segmem weights are not touched) -> (B, 1+steps) int64 incl. the start token."""
+        ids = self.engine().generate(inputs, max_length=max_length)
+        if output_hidden_states:
+            return ids, self.engine().encode(inputs)
+        return ids
 
     def forward(self, *args, **kwargs):
+        # reference models/t5_segmem.py:68-170 (V1 teacher forcing: row i's memory comes from row i-1
+        # of the SAME batch).  Not on the north_star path (the shipped experiments train V2WithPrev,
+        # config/config_slakh_segmem.yaml); stated in DESIGN.md section 8.
         raise NotImplementedError("teacher-forced forward is implemented for T5ForConditionalGeneration "
                                   "and T5SegMemV2WithPrev only")

@@ -453,8 +453,11 @@ class _CachedDecoder:
         self.sd, self.enc = sd, enc
         self.nb = _n_blocks(sd, "decoder")
         b = enc.shape[0]
-        self.k = [torch.zeros(b, N_HEADS, 0, D_KV, dtype=enc.dtype) for _ in range(self.nb)]
-        self.v = [torch.zeros(b, N_HEADS, 0, D_KV, dtype=enc.dtype) for _ in range(self.nb)]
+        # self-attention K/V grow in place inside buffers that double when full (a torch.cat per
+        # step would make a 1024-step run quadratic in memory traffic)
+        self.cap = 64
+        self.k = [torch.zeros(b, N_HEADS, self.cap, D_KV, dtype=enc.dtype) for _ in range(self.nb)]
+        self.v = [torch.zeros(b, N_HEADS, self.cap, D_KV, dtype=enc.dtype) for _ in range(self.nb)]
         self.ck = [_heads(enc @ sd[f"decoder.block.{i}.layer.1.EncDecAttention.k.weight"].T)
                    for i in range(self.nb)]
         self.cv = [_heads(enc @ sd[f"decoder.block.{i}.layer.1.EncDecAttention.v.weight"].T)
@@ -468,14 +471,19 @@ class _CachedDecoder:
     def step_embeds(self, h):
         sd = self.sd
         h = h + self.pe[self.pos:self.pos + 1]
+        if self.pos >= self.cap:
+            grow = lambda c: torch.cat([c, torch.zeros_like(c)], 2)
+            self.k, self.v = [grow(c) for c in self.k], [grow(c) for c in self.v]
+            self.cap *= 2
         for i in range(self.nb):
             p = f"decoder.block.{i}.layer"
             n = rms_norm(h, sd[f"{p}.0.layer_norm.weight"])
             q = _heads(n @ sd[f"{p}.0.SelfAttention.q.weight"].T)
-            self.k[i] = torch.cat([self.k[i], _heads(n @ sd[f"{p}.0.SelfAttention.k.weight"].T)], 2)
-            self.v[i] = torch.cat([self.v[i], _heads(n @ sd[f"{p}.0.SelfAttention.v.weight"].T)], 2)
-            pr = torch.softmax(q @ self.k[i].transpose(-1, -2), -1)
-            ctx = (pr @ self.v[i]).transpose(1, 2).reshape(h.shape[0], 1, -1)
+            t = self.pos
+            self.k[i][:, :, t:t + 1] = _heads(n @ sd[f"{p}.0.SelfAttention.k.weight"].T)
+            self.v[i][:, :, t:t + 1] = _heads(n @ sd[f"{p}.0.SelfAttention.v.weight"].T)
+            pr = torch.softmax(q @ self.k[i][:, :, :t + 1].transpose(-1, -2), -1)
+            ctx = (pr @ self.v[i][:, :, :t + 1]).transpose(1, 2).reshape(h.shape[0], 1, -1)
             h = h + ctx @ sd[f"{p}.0.SelfAttention.o.weight"].T
             n = rms_norm(h, sd[f"{p}.1.layer_norm.weight"])
             q = _heads(n @ sd[f"{p}.1.EncDecAttention.q.weight"].T)

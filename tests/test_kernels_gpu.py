@@ -51,3 +51,31 @@ def test_gemm_decode_single_shot(eng, M, N, K):
 
 def test_tcgen05_large(eng):
     _check(eng, 1, 65536, 1152, 512)
+
+
+# the fine-tune backward's two operand forms, at the reduction depth of configs[4] (32 x 1024 rows)
+@pytest.mark.parametrize("R,M,N", [(32768, 512, 384), (32768, 1152, 512), (32768, 2048, 512), (10240, 6144, 512),
+                                   (1000, 512, 512), (32768, 512, 1024), (32768, 1536, 512)])
+def test_gemm_tcgen05_wgrad_form_split_k(eng, R, M, N):
+    """which = 4: C (M, N) = A^T W over R rows, both operands row-major (MN-major tcgen05 operands),
+    split-K chosen as the weight-gradient path chooses it + the fixed-order reduce kernel."""
+    g = torch.Generator().manual_seed(R + 3 * M + 5 * N)
+    a = (torch.randn((R, M), generator=g) * R ** -0.5).bfloat16()
+    w = torch.randn((R, N), generator=g).bfloat16()
+    got = eng.test_gemm(a, w, 4).cpu()
+    want = (a.double().T @ w.double())
+    err = (got.double() - want).abs().max().item()
+    assert got.shape == (M, N) and err < 2e-3, (R, M, N, err)
+
+
+@pytest.mark.parametrize("M,K,N", [(32768, 1536, 512), (32768, 512, 384), (8192, 2048, 512), (32768, 1152, 512),
+                                   (777, 384, 512), (32768, 512, 1024)])
+def test_gemm_tcgen05_dgrad_form(eng, M, K, N):
+    """which = 5: C (M, N) = A W with W (K, N) row-major as stored (B operand MN-major)."""
+    g = torch.Generator().manual_seed(M + 3 * K + 5 * N)
+    a = torch.randn((M, K), generator=g).bfloat16()
+    w = (torch.randn((K, N), generator=g) * K ** -0.5).bfloat16()
+    got = eng.test_gemm(a, w, 5).cpu()
+    want = a.double() @ w.double()
+    err = (got.double() - want).abs().max().item()
+    assert got.shape == (M, N) and err < 2e-3, (M, K, N, err)

@@ -453,3 +453,18 @@ def test_tiny_and_boundary_audio_lengths(pkg, n_samples):
     staged = model.generate(torch.from_numpy(inputs).cuda(), max_length=10).cpu().numpy()
     fused = h.transcribe(audio, max_length=10).numpy()
     np.testing.assert_array_equal(fused, staged)
+
+
+def test_segmem_v1_generate_without_memory_is_the_plain_loop(pkg, feats):
+    """Reference models/t5_segmem.py:254-311: T5SegMem.generate never touches the memory weights; it is
+    the batched loop of models/t5.py:251-302 -> bit-identical to the plain model on the shared weights."""
+    v1, _ = _model(pkg, 4322, kind="v1", eos_scale=3.0)
+    sd = syn.synthetic_state_dict(4322, segmem=True, eos_scale=3.0)
+    import importlib
+    t5 = importlib.import_module("mr-mt3_b200.t5")
+    plain = t5.T5ForConditionalGeneration(t5.T5Config())
+    plain.load_state_dict({k: v for k, v in sd.items() if not k.startswith("segmem")}, strict=True)
+    plain = plain.eval().cuda()
+    a = v1.generate(feats.cuda(), max_length=64)
+    b = plain.generate(feats.cuda(), max_length=64)
+    assert a.shape == b.shape and torch.equal(a, b)
