@@ -234,6 +234,18 @@ int mrmt3_train_backward(mrmt3_handle* h, float* grad_flat, const float* dlogits
 int mrmt3_train_apply(mrmt3_handle* h, const float* grad_flat, float lr, float beta1, float beta2, float eps,
                       float weight_decay, void* stream);
 int mrmt3_train_read_master(mrmt3_handle* h, float* out_flat, void* stream);
+/* Data-parallel overlap (reference: DDP's bucketed all-reduce under `train.py`'s Lightning trainer,
+ * config/config.yaml:45-46).  The flat order is laid out in the order the backward FINISHES the
+ * gradients, so it splits into contiguous buckets (lm_head | decoder layers last to first | stacked
+ * cross K/V | memory encoder + segmem_proj | encoder layers last to first | proj, embedding, norms).
+ * mrmt3_train_backward records one event per bucket on its stream; mrmt3_train_wait_bucket makes
+ * another stream wait for bucket i of the most recent backward, so the caller can all-reduce
+ * grad_flat[offset : offset + count] on a side stream while the backward is still running.
+ * mrmt3_train_loss fetches the mean loss of the last forward (synchronises `stream`). */
+int mrmt3_train_bucket_count(mrmt3_handle* h, int32_t* n);
+int mrmt3_train_bucket(mrmt3_handle* h, int i, int64_t* offset, int64_t* count);
+int mrmt3_train_wait_bucket(mrmt3_handle* h, int i, void* stream);
+int mrmt3_train_loss(mrmt3_handle* h, float* loss_host, void* stream);
 
 /* ---- end to end from host buffers ------------------------------------------------------
  * Replaces: InferenceHandler.inference up to the token rows (inference.py:149-191): pinned or

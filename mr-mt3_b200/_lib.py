@@ -72,6 +72,10 @@ _PROTOTYPES = {
     "mrmt3_train_apply": (_c_int, [_c_void_p, _c_void_p, ctypes.c_float, ctypes.c_float, ctypes.c_float,
                                    ctypes.c_float, ctypes.c_float, _c_void_p]),
     "mrmt3_train_read_master": (_c_int, [_c_void_p, _c_void_p, _c_void_p]),
+    "mrmt3_train_bucket_count": (_c_int, [_c_void_p, ctypes.POINTER(ctypes.c_int32)]),
+    "mrmt3_train_bucket": (_c_int, [_c_void_p, _c_int, ctypes.POINTER(_c_i64), ctypes.POINTER(_c_i64)]),
+    "mrmt3_train_wait_bucket": (_c_int, [_c_void_p, _c_int, _c_void_p]),
+    "mrmt3_train_loss": (_c_int, [_c_void_p, ctypes.POINTER(ctypes.c_float), _c_void_p]),
 }
 EXPORTED_SYMBOLS = tuple(_PROTOTYPES)
 
@@ -394,6 +398,28 @@ class Engine:
         with torch.cuda.device(self.device):
             self._check(self._lib.mrmt3_train_apply(self._h, _ptr(grad), lr, betas[0], betas[1], eps, weight_decay,
                                                     _stream()))
+
+    def train_buckets(self):
+        """[(offset, count)] of the flat gradient, in the order the backward completes them."""
+        getattr(self, "_n_params", None) or self.train_init()
+        n = ctypes.c_int32(0)
+        self._check(self._lib.mrmt3_train_bucket_count(self._h, ctypes.byref(n)))
+        out = []
+        for i in range(n.value):
+            off, cnt = ctypes.c_int64(0), ctypes.c_int64(0)
+            self._check(self._lib.mrmt3_train_bucket(self._h, i, ctypes.byref(off), ctypes.byref(cnt)))
+            out.append((int(off.value), int(cnt.value)))
+        return out
+
+    def train_wait_bucket(self, i, stream):
+        """Make `stream` (torch.cuda.Stream) wait until bucket i of the last train_backward is final."""
+        self._check(self._lib.mrmt3_train_wait_bucket(self._h, int(i), ctypes.c_void_p(stream.cuda_stream)))
+
+    def train_loss(self):
+        loss = ctypes.c_float(0.0)
+        with torch.cuda.device(self.device):
+            self._check(self._lib.mrmt3_train_loss(self._h, ctypes.byref(loss), _stream()))
+        return float(loss.value)
 
     def train_read_master(self):
         n = getattr(self, "_n_params", None) or self.train_init()

@@ -37,6 +37,10 @@ Status train_forward(mrmt3_handle* h, const float* mel, int B, const long long* 
 Status train_backward(mrmt3_handle* h, float* grad, const float* dlogits_f32, cudaStream_t s);
 Status train_apply(mrmt3_handle* h, const float* grad, float lr, float beta1, float beta2, float adam_eps, float wd,
                    cudaStream_t s);
+int train_bucket_count(mrmt3_handle* h);
+Status train_bucket(mrmt3_handle* h, int i, long long* offset, long long* count);
+Status train_wait_bucket(mrmt3_handle* h, int i, cudaStream_t stream);
+Status train_loss(mrmt3_handle* h, float* loss_host, cudaStream_t s);
 Status profile_collect(mrmt3_handle* h);
 Status trace_enable(mrmt3_handle* h, bool on);
 void drop_graphs(mrmt3_handle* h);
@@ -332,6 +336,38 @@ int mrmt3_train_apply(mrmt3_handle* h, const float* grad_flat, float lr, float b
                       float weight_decay, void* stream) {
     GUARD(h)
     return finish(h, train_apply(h, grad_flat, lr, beta1, beta2, eps, weight_decay, (cudaStream_t)stream));
+    END_GUARD(h)
+}
+
+int mrmt3_train_bucket_count(mrmt3_handle* h, int32_t* n) {
+    GUARD(h)
+    if (!n) return finish(h, Error(1, "null argument"));
+    *n = train_bucket_count(h);
+    return 0;
+    END_GUARD(h)
+}
+
+int mrmt3_train_bucket(mrmt3_handle* h, int i, int64_t* offset, int64_t* count) {
+    GUARD(h)
+    if (!offset || !count) return finish(h, Error(1, "null argument"));
+    long long o = 0, c = 0;
+    Status st = train_bucket(h, i, &o, &c);
+    *offset = o;
+    *count = c;
+    return finish(h, st);
+    END_GUARD(h)
+}
+
+int mrmt3_train_wait_bucket(mrmt3_handle* h, int i, void* stream) {
+    GUARD(h)
+    return finish(h, train_wait_bucket(h, i, (cudaStream_t)stream));
+    END_GUARD(h)
+}
+
+int mrmt3_train_loss(mrmt3_handle* h, float* loss_host, void* stream) {
+    GUARD(h)
+    if (!loss_host) return finish(h, Error(1, "null argument"));
+    return finish(h, train_loss(h, loss_host, (cudaStream_t)stream));
     END_GUARD(h)
 }
 

@@ -996,18 +996,24 @@ Status generate_segmem(mrmt3_handle* h, const float* mel_f32, const bf16* mel_bf
         MRMT3_TRY(h->mem_bf16.reserve((size_t)n * n_mem * kDModel * sizeof(bf16)));
         MRMT3_TRY(reserve_graph_visible(h, h->mem_f32, (size_t)n * n_mem * kDModel * sizeof(float)));
         LaneArrays a = lane_arrays(h);
-        std::vector<int> tab(4 * (size_t)n);
+        // lanes in order of decreasing track length: the tracks still running in round r are then
+        // the lane PREFIX [0, n_r), and the round launches n_r lanes instead of masking the rest --
+        // in the ragged tail the step shrinks to fewer lane groups instead of idling whole groups
+        std::vector<int> order(n);
+        for (int i = 0; i < n; ++i) order[i] = w0 + i;
+        std::stable_sort(order.begin(), order.end(), [&](int x, int y) { return seg_counts[x] > seg_counts[y]; });
+        const int n_wave = n;
+        std::vector<int> tab(4 * (size_t)n_wave);
         for (int r = 0; r < wave_segs; ++r) {
             int n_active = 0;
+            while (n_active < n_wave && seg_counts[order[n_active]] > r) ++n_active;
+            const int n = n_active;                                   // shadows the wave size: this round's lanes
             for (int i = 0; i < n; ++i) {
-                const int cnt = seg_counts[w0 + i];
-                const bool on = r < cnt;
-                const int seg = (int)seg_base[w0 + i] + (on ? r : std::max(cnt - 1, 0));
+                const int seg = (int)seg_base[order[i]] + r;
                 tab[i] = seg;                                        // out_row
-                tab[n + i] = (r > 0 && on) ? seg - 1 : seg;          // prev_row (r == 0: unused)
-                tab[2 * n + i] = on ? 1 : 0;                         // init_active
+                tab[n + i] = r > 0 ? seg - 1 : seg;                  // prev_row (r == 0: unused)
+                tab[2 * n + i] = 1;                                  // init_active
                 tab[3 * n + i] = seg;                                // seg_index
-                n_active += on;
             }
             MRMT3_CUDA_TRY(cudaMemcpyAsync(a.out_row, tab.data(), n * sizeof(int), cudaMemcpyHostToDevice, s));
             MRMT3_CUDA_TRY(cudaMemcpyAsync(a.prev_row, tab.data() + n, n * sizeof(int), cudaMemcpyHostToDevice, s));

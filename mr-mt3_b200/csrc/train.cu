@@ -67,6 +67,12 @@ struct TrainState {
     float* loss_pinned = nullptr;  // pinned landing spot of the loss scalar
     const long long* dec_ids = nullptr;
     DeviceBuffer ids_copy;
+    // gradient buckets: contiguous ranges of the flat order, in the order the backward completes them
+    // (the flat order is laid out for that), each with an event recorded when its last kernel is queued
+    struct Bucket { size_t off, count; cudaEvent_t done; };
+    std::vector<Bucket> buckets;
+    std::vector<int> bucket_first_slot;  // slot index where each bucket starts
+    float* scal = nullptr;               // [1 / #labels, mean loss] of the last forward (device)
     bool reloaded = false;  // weights were set after train_init: the optimizer state restarts at the next commit
 };
 
@@ -101,6 +107,8 @@ void train_destroy(mrmt3_handle* h) {
     if (!t) return;
     t->master.release(); t->m.release(); t->v.release();
     t->stash.release(); t->scratch.release(); t->ids_copy.release(); t->prev_copy.release();
+    for (auto& b : t->buckets)
+        if (b.done) cudaEventDestroy(b.done);
     if (t->loss_pinned) cudaFreeHost(t->loss_pinned);
     delete t;
     h->train = nullptr;
@@ -113,22 +121,38 @@ static int add_slot(TrainState* t, bf16* w16, float* w32, int rows, int cols) {
     return (int)t->slots.size() - 1;
 }
 
-static void add_stack(TrainState* t, StackW& st, bool decoder, std::vector<LayerSlots>& out, int& final_slot) {
-    for (auto& L : st.layers) {
-        LayerSlots ls{};
-        ls.wqkv = add_slot(t, L.wqkv, nullptr, 3 * kInner, kDModel);
-        ls.wo = add_slot(t, L.wo, nullptr, kDModel, kInner);
-        ls.ln_self = add_slot(t, nullptr, L.ln_self, 1, kDModel);
+// The flat order is the order in which the backward pass FINISHES the gradients, so that every bucket
+// handed to the all-reduce is one contiguous range: lm_head | decoder layers last to first | stacked
+// cross K/V | memory encoder layers + segmem_proj | encoder layers last to first | proj, embedding and
+// every norm weight (the embedding gradient gets its second contribution from the memory block and the
+// norm-weight gradients are reduced at the very end of the backward).
+static void begin_bucket(TrainState* t) { t->bucket_first_slot.push_back((int)t->slots.size()); }
+
+// matrices of one layer, one bucket per layer, layers last to first
+static void add_stack_matrices(TrainState* t, StackW& st, bool decoder, std::vector<LayerSlots>& out, bool bucket_per_layer) {
+    out.assign(st.layers.size(), LayerSlots{});
+    for (int li = (int)st.layers.size() - 1; li >= 0; --li) {
+        LayerW& L = st.layers[li];
+        LayerSlots& ls = out[li];
+        if (bucket_per_layer) begin_bucket(t);
+        ls.wff = add_slot(t, L.wff, nullptr, kDModel, kDFF);
+        ls.wi = add_slot(t, L.wi, nullptr, 2 * kDFF, kDModel);
         ls.cq = ls.co = ls.ln_cross = -1;
         if (decoder) {
-            ls.cq = add_slot(t, L.cq, nullptr, kInner, kDModel);
             ls.co = add_slot(t, L.co, nullptr, kDModel, kInner);
-            ls.ln_cross = add_slot(t, nullptr, L.ln_cross, 1, kDModel);
+            ls.cq = add_slot(t, L.cq, nullptr, kInner, kDModel);
         }
-        ls.wi = add_slot(t, L.wi, nullptr, 2 * kDFF, kDModel);
-        ls.wff = add_slot(t, L.wff, nullptr, kDModel, kDFF);
-        ls.ln_ff = add_slot(t, nullptr, L.ln_ff, 1, kDModel);
-        out.push_back(ls);
+        ls.wo = add_slot(t, L.wo, nullptr, kDModel, kInner);
+        ls.wqkv = add_slot(t, L.wqkv, nullptr, 3 * kInner, kDModel);
+    }
+}
+
+static void add_stack_norms(TrainState* t, StackW& st, bool decoder, std::vector<LayerSlots>& out, int& final_slot) {
+    for (size_t li = 0; li < st.layers.size(); ++li) {
+        LayerW& L = st.layers[li];
+        out[li].ln_self = add_slot(t, nullptr, L.ln_self, 1, kDModel);
+        if (decoder) out[li].ln_cross = add_slot(t, nullptr, L.ln_cross, 1, kDModel);
+        out[li].ln_ff = add_slot(t, nullptr, L.ln_ff, 1, kDModel);
     }
     final_slot = add_slot(t, nullptr, st.final_ln, 1, kDModel);
 }
@@ -141,15 +165,32 @@ Status train_init(mrmt3_handle* h) {
     MRMT3_CUDA_TRY(cudaSetDevice(h->device));
     TrainState* t = new TrainState();
     h->train = t;
+    const bool with_mem = h->cfg.mem_variant == MRMT3_MEM_V2_APPEND;
+    begin_bucket(t);
+    t->lm_head = add_slot(t, h->lm_head, nullptr, kVocab, kDModel);
+    add_stack_matrices(t, h->dec, true, t->dec, true);
+    begin_bucket(t);
+    t->cross_kv = add_slot(t, h->cross_kv_w, nullptr, h->cfg.n_dec_layers * 2 * kInner, kDModel);
+    if (with_mem) {
+        begin_bucket(t);
+        add_stack_matrices(t, h->mem, false, t->mem, false);
+        t->segmem_proj = add_slot(t, h->segmem_proj, nullptr, kDModel, kDModel);
+    }
+    add_stack_matrices(t, h->enc, false, t->enc, true);
+    begin_bucket(t);
     t->proj = add_slot(t, h->proj, nullptr, kDModel, kDModel);
     t->emb = add_slot(t, nullptr, h->emb, kVocab, kDModel);
-    t->lm_head = add_slot(t, h->lm_head, nullptr, kVocab, kDModel);
-    t->cross_kv = add_slot(t, h->cross_kv_w, nullptr, h->cfg.n_dec_layers * 2 * kInner, kDModel);
-    add_stack(t, h->enc, false, t->enc, t->enc_final);
-    add_stack(t, h->dec, true, t->dec, t->dec_final);
-    if (h->cfg.mem_variant == MRMT3_MEM_V2_APPEND) {
-        t->segmem_proj = add_slot(t, h->segmem_proj, nullptr, kDModel, kDModel);
-        add_stack(t, h->mem, false, t->mem, t->mem_final);
+    add_stack_norms(t, h->dec, true, t->dec, t->dec_final);
+    if (with_mem) add_stack_norms(t, h->mem, false, t->mem, t->mem_final);
+    add_stack_norms(t, h->enc, false, t->enc, t->enc_final);
+    for (size_t i = 0; i < t->bucket_first_slot.size(); ++i) {
+        const int s0 = t->bucket_first_slot[i];
+        const int s1 = i + 1 < t->bucket_first_slot.size() ? t->bucket_first_slot[i + 1] : (int)t->slots.size();
+        const size_t off = t->slots[s0].off;
+        const size_t end = t->slots[s1 - 1].off + (size_t)t->slots[s1 - 1].rows * t->slots[s1 - 1].cols;
+        TrainState::Bucket bk{off, end - off, nullptr};
+        MRMT3_CUDA_TRY(cudaEventCreateWithFlags(&bk.done, cudaEventDisableTiming));
+        t->buckets.push_back(bk);
     }
     const size_t n = t->n_total;
     MRMT3_TRY(t->master.reserve(n * 4));
@@ -525,6 +566,7 @@ Status train_forward(mrmt3_handle* h, const float* mel, int B, const long long* 
     t->dlogits = bp.take<bf16>(Md * kVocab);
     t->row_loss = bp.take<float>(Md);
     float* scal = bp.take<float>(2);
+    t->scal = scal;
     BUMP_CHECK(bp);
     RUN(h, launch_rmsnorm(Hd, h->dec.final_ln, eps, t->dec_n_final, nullptr, (int)Md, nullptr, 1, s));
     RUN(h, launch_dropout_bf16(t->dec_n_final, Md * kDModel, mk(1, 0, kSiteFinal), s));
@@ -686,10 +728,20 @@ Status train_backward(mrmt3_handle* h, float* grad, const float* dlogits_f32, cu
         return OkStatus();
     };
 
+    // bucket i of the flat gradient is final once everything queued so far has run
+    const int bk_dec0 = 1, bk_cross = 1 + n_dec, bk_mem = t->mem.empty() ? -1 : 2 + n_dec;
+    const int bk_enc0 = (t->mem.empty() ? 2 : 3) + n_dec, bk_last = bk_enc0 + n_enc;
+    if ((int)t->buckets.size() != bk_last + 1) return Error(2, "internal: gradient bucket table out of step with the backward");
+    auto bucket_done = [&](int i) -> Status {
+        MRMT3_CUDA_TRY(cudaEventRecord(t->buckets[i].done, s));
+        return OkStatus();
+    };
+
     // ---- head ----
     MRMT3_CUDA_TRY(cudaMemsetAsync(dH, 0, Md * kDModel * 4, s));
     MRMT3_TRY(dgrad(t->dlogits, kVocab, t->lm_head, dn, Md));
     MRMT3_TRY(wgrad(t->dlogits, kVocab, kVocab, t->dec_n_final, kDModel, kDModel, G(t->lm_head), Md));
+    MRMT3_TRY(bucket_done(0));
     RUN(h, launch_dropout_bf16(dn, Md * kDModel, mk(1, 0, kSiteFinal), s));
     MRMT3_TRY(norm_bwd(t->dec_h_final, h->dec.final_ln, dn, Md, G(t->dec_final)));
 
@@ -715,6 +767,7 @@ Status train_backward(mrmt3_handle* h, float* grad, const float* dlogits_f32, cu
         MRMT3_TRY(wgrad(dqc, kInner, kInner, st.nc, kDModel, kDModel, G(ls.cq), Md));
         MRMT3_TRY(norm_bwd(st.h_mid2, Lw.ln_cross, dn, Md, G(ls.ln_cross)));
         MRMT3_TRY(self_bwd(ls, Lw, st, Md, L, 1, 1, li));
+        MRMT3_TRY(bucket_done(bk_dec0 + (n_dec - 1 - li)));
     }
     RUN(h, launch_dropout_f32(dH, Md * kDModel, mk(1, 0, kSiteInput), s));
     tic("embedding bwd");
@@ -725,6 +778,7 @@ Status train_backward(mrmt3_handle* h, float* grad, const float* dlogits_f32, cu
     // ---- cross K/V projection -> [encoder output ; memory rows] ----
     MRMT3_TRY(dgrad(dkv, (int)kvN, t->cross_kv, dn, Mk));
     MRMT3_TRY(wgrad(dkv, (int)kvN, (int)kvN, t->kv_in, kDModel, kDModel, G(t->cross_kv), Mk));
+    MRMT3_TRY(bucket_done(bk_cross));
 
     // ---- memory block backward (MR-MT3) ----
     if (n_mem) {
@@ -750,6 +804,7 @@ Status train_backward(mrmt3_handle* h, float* grad, const float* dlogits_f32, cu
         RUN(h, launch_embed_bwd(t->prev_ids, dH, G(t->emb), (int)Mm, emb_scratch, s));
         h->launches += 1;
         toc();
+        MRMT3_TRY(bucket_done(bk_mem));
     } else {
         MRMT3_CUDA_TRY(cudaMemcpyAsync(dsplit, dn, Me * kDModel * 2, cudaMemcpyDeviceToDevice, s));
     }
@@ -761,12 +816,14 @@ Status train_backward(mrmt3_handle* h, float* grad, const float* dlogits_f32, cu
     for (int li = n_enc - 1; li >= 0; --li) {
         MRMT3_TRY(ffn_bwd(t->enc[li], h->enc.layers[li], t->enc_st[li], Me, 0, li));
         MRMT3_TRY(self_bwd(t->enc[li], h->enc.layers[li], t->enc_st[li], Me, kSegFrames, 0, 0, li));
+        MRMT3_TRY(bucket_done(bk_enc0 + (n_enc - 1 - li)));
     }
     // proj: h0 = dropout(mel . Wproj^T + PE)
     MRMT3_TRY(cast_dH(Me, mk(0, 0, kSiteInput)));
     MRMT3_TRY(wgrad(dHb, kDModel, kDModel, t->mel16, kMels, kMels, G(t->proj), Me));
     // norm-weight gradients: the partial rows of every norm of the step, added in a fixed order
     RUN(h, launch_norm_dg_reduce(norm_list, norm_parts, s));
+    MRMT3_TRY(bucket_done(bk_last));
     if (prof) {
         MRMT3_CUDA_TRY(cudaStreamSynchronize(s));
         std::map<std::string, std::pair<double, int>> agg;
@@ -780,6 +837,34 @@ Status train_backward(mrmt3_handle* h, float* grad, const float* dlogits_f32, cu
         }
         for (auto& kv : agg) fprintf(stderr, "[train profile] %-28s %8.3f ms in %d calls\n", kv.first.c_str(), kv.second.first, kv.second.second);
     }
+    return OkStatus();
+}
+
+// ---- gradient buckets (data-parallel overlap: all-reduce bucket i while the backward still runs) ----
+int train_bucket_count(mrmt3_handle* h) { return state(h) ? (int)state(h)->buckets.size() : 0; }
+Status train_bucket(mrmt3_handle* h, int i, long long* offset, long long* count) {
+    TrainState* t = state(h);
+    if (!t) return Error(5, "mrmt3_train_init first");
+    if (i < 0 || i >= (int)t->buckets.size()) return Error(2, "bucket index out of range");
+    *offset = (long long)t->buckets[i].off;
+    *count = (long long)t->buckets[i].count;
+    return OkStatus();
+}
+Status train_wait_bucket(mrmt3_handle* h, int i, cudaStream_t stream) {
+    TrainState* t = state(h);
+    if (!t || !t->B) return Error(5, "mrmt3_train_backward first");
+    if (i < 0 || i >= (int)t->buckets.size()) return Error(2, "bucket index out of range");
+    MRMT3_CUDA_TRY(cudaStreamWaitEvent(stream, t->buckets[i].done, 0));
+    return OkStatus();
+}
+// mean loss of the last train_forward (synchronises `s`)
+Status train_loss(mrmt3_handle* h, float* loss_host, cudaStream_t s) {
+    TrainState* t = state(h);
+    if (!t || !t->scal) return Error(5, "mrmt3_train_forward first");
+    if (!t->loss_pinned) MRMT3_CUDA_TRY(cudaMallocHost(&t->loss_pinned, sizeof(float)));
+    MRMT3_CUDA_TRY(cudaMemcpyAsync(t->loss_pinned, t->scal + 1, sizeof(float), cudaMemcpyDeviceToHost, s));
+    MRMT3_CUDA_TRY(cudaStreamSynchronize(s));
+    *loss_host = *t->loss_pinned;
     return OkStatus();
 }
 

@@ -329,6 +329,12 @@ class T5ForConditionalGeneration(nn.Module):
             eng.load_state_dict(self.state_dict(), strict=True)
         return eng
 
+    def trainer(self, **kw):
+        """A data-parallel fine-tune loop over this model (training.Trainer): forward, loss, backward,
+        bucketed gradient all-reduce overlapped with the backward, AdamW."""
+        from .training import Trainer
+        return Trainer(self, **kw)
+
     @torch.no_grad()
     def sync_parameters_from_engine(self):
         """Copy the engine's trained fp32 masters back into this module's parameters."""

@@ -187,6 +187,62 @@ def test_gradient_allreduce_mean_gloo_world2():
     assert sh.allreduce_mean_(x) is x and float(x.sum()) == 4.0      # not initialised: no-op
 
 
+class _StubEngine:
+    """What training.Trainer needs from the engine for the gradient exchange, on CPU."""
+    device = torch.device("cpu")
+    _n_params = 1000
+
+    def train_buckets(self):
+        return [(0, 300), (300, 1), (301, 450), (751, 249)]
+
+    def train_wait_bucket(self, i, stream):
+        pass
+
+    def train_set_dropout(self, p, seed):
+        pass
+
+
+class _StubModel:
+    class config:
+        dropout_rate = 0.1
+
+
+def _bucket_worker(rank, world, port, q):
+    import torch.distributed as dist
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    tr = importlib.import_module("mr-mt3_b200.training")
+    out = {}
+    for overlap in (True, False):
+        t = tr.Trainer(_StubModel(), engine=_StubEngine(), overlap=overlap)
+        t.grad.copy_(torch.arange(1000, dtype=torch.float32) * (rank + 1))
+        t._allreduce()
+        out[overlap] = t.grad.numpy().copy()
+        assert sum(c for _, c in t.buckets) == t.grad.numel()
+    q.put((rank, out))
+    dist.destroy_process_group()
+
+
+def test_bucketed_gradient_allreduce_gloo_world2():
+    """The overlapped path of the fine-tune step: the flat gradient all-reduced bucket by bucket
+    (training.Trainer._allreduce) equals one all-reduce of the whole buffer = the mean over ranks."""
+    import torch.multiprocessing as mp
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = 33500 + os.getpid() % 2000
+    procs = [ctx.Process(target=_bucket_worker, args=(r, 2, port, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    got = dict(q.get(timeout=120) for _ in range(2))
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    want = np.arange(1000, dtype=np.float32) * 1.5
+    for r in range(2):
+        np.testing.assert_array_equal(got[r][True], want)
+        np.testing.assert_array_equal(got[r][False], want)
+
+
 def test_dropout_mask_definition_equals_oracle_mirror():
     """The fine-tune step's dropout masks are a counter-based hash evaluated inside the CUDA kernels
     (csrc/common.cuh:drop_factor); `mrmt3_dropout_keep_host` is the same C++ definition compiled

@@ -409,3 +409,31 @@ def test_out_of_range_ids_are_masked_not_dereferenced():
     assert torch.equal(la, lb) and loss_a == loss_b and torch.equal(ga, gb)
     with pytest.raises(Exception):
         eng.train_forward(x.cuda(), torch.zeros((2, 6000), dtype=torch.int64), torch.zeros((2, 6000), dtype=torch.int64), good)
+
+
+def test_trainer_step_equals_manual_step_and_buckets_cover_the_gradient():
+    """training.Trainer (forward, backward into a persistent flat buffer, [bucketed all-reduce], AdamW)
+    on one GPU equals the hand-rolled sequence; the buckets tile the flat gradient exactly, in the order
+    lm_head | decoder layers 7..0 | cross K/V | memory | encoder layers 7..0 | proj + embedding + norms."""
+    model, sd, x, labels = _setup(seed=4322, B=2, L=32, segmem=True)
+    prev = torch.randint(3, 1391, (2, 64), generator=torch.Generator().manual_seed(3))
+    tr = model.trainer(lr=1e-3, dropout=0.0)
+    eng = model.engine()
+    bk = tr.buckets
+    assert len(bk) == 1 + 8 + 1 + 1 + 8 + 1
+    assert bk[0][0] == 0 and all(bk[i][0] + bk[i][1] == bk[i + 1][0] for i in range(len(bk) - 1))
+    assert bk[-1][0] + bk[-1][1] == eng._n_params
+    assert bk[0][1] == 1536 * 512 and eng.train_locate("lm_head.weight")[0] == 0
+    off7 = eng.train_locate("decoder.block.7.layer.0.SelfAttention.q.weight")[0]
+    off0 = eng.train_locate("decoder.block.0.layer.0.SelfAttention.q.weight")[0]
+    assert bk[1][0] <= off7 < bk[1][0] + bk[1][1] and bk[8][0] <= off0 < bk[8][0] + bk[8][1]
+    assert eng.train_locate("decoder.block.3.layer.1.layer_norm.weight")[0] >= bk[-1][0]
+    loss_a = tr.step(x.cuda(), labels.cuda(), prev.cuda())
+    after_a = eng.train_read_master().clone()
+    other, _, _, _ = _setup(seed=4322, B=2, L=32, segmem=True)
+    e2 = other._train_engine()
+    _, loss_b = e2.train_forward(x.cuda(), other._shift_right(labels), labels, prev)
+    g = e2.train_backward()
+    e2.train_apply(g, 1e-3)
+    assert abs(loss_a - loss_b) < 1e-6 and torch.equal(tr.grad, g)
+    assert torch.equal(after_a, e2.train_read_master())
