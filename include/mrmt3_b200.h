@@ -71,7 +71,9 @@ int64_t mrmt3_launch_count(const mrmt3_handle* h);
  * 0 = one CTA per (lane, head) on CUDA cores), "attn_ring_stages" = ring depth of variant 1
  * (2, 3, 4 or 6 stages of 16 KB per warp quartet), "attn_ring_quartets" = 1 or 2 math-warp
  * quartets per CTA, "attn_ring_ctas" = its persistent CTAs per SM (1..8, 0 = by launch size).  The
- * attention settings are process-wide.  "hooks_fast_path" = 1 sends calls that use the parity hooks of
+ * attention settings are process-wide.  "attn_part_keys_self" / "attn_part_keys_cross" = split-key work
+ * units of variant 1: an item's keys are cut at fixed multiples of this many keys (0 = off, else a
+ * multiple of 128) and the parts are merged in order by the last finisher.  "hooks_fast_path" = 1 sends calls that use the parity hooks of
  * mrmt3_generate / mrmt3_generate_segmem (forced_ids, logits_out) through the production decode path
  * (CUDA-graph replay, concurrent lane groups) instead of the eager single-group debug path. */
 int mrmt3_set_option(mrmt3_handle* h, const char* key, int value);

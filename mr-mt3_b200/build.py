@@ -14,7 +14,8 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 OBJ = os.path.join(CSRC, "build")
 LIB = os.path.join(HERE, "libmrmt3_b200.so")
-SOURCES = ["frontend.cu", "layers.cu", "attention.cu", "train_kernels.cu", "train.cu", "model.cu", "api.cu"]
+SOURCES = ["frontend.cu", "layers.cu", "attention.cu", "attention_tc.cu", "train_kernels.cu", "train.cu", "model.cu",
+           "api.cu"]
 NVCC = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
 FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
          "-Xcompiler", "-fPIC", "-Xcompiler", "-fvisibility=hidden", "--expt-relaxed-constexpr"]

@@ -128,6 +128,16 @@ int mrmt3_set_option(mrmt3_handle* h, const char* key, int value) {
     else if (k == "use_graphs") h->use_graphs = value != 0;
     else if (k == "group_serial") h->group_serial = value != 0;
     else if (k == "hooks_fast_path") h->hooks_fast_path = value != 0;
+    else if (k == "attn_full_tc") attn_full_configure(value);
+    else if (k == "attn_part_keys_self" || k == "attn_part_keys_cross") {
+        const bool self = k == "attn_part_keys_self";
+        if (value < 0) value = self ? kDefaultPartKeysSelf : kDefaultPartKeysCross;   // -1: the library default
+        if (value % 128 != 0) return finish(h, Error(2, k + " must be 0 (off) or a multiple of 128"));
+        cudaSetDevice(h->device);
+        cudaDeviceSynchronize();
+        drop_graphs(h);  // baked into the captured step graphs
+        (self ? h->attn_part_keys_self : h->attn_part_keys_cross) = value;
+    }
     else if (k == "train_dropout_sites") return finish(h, train_set_dropout_sites(h, value));
     else if (k == "attn_variant" || k == "attn_ring_stages" || k == "attn_ring_ctas" || k == "attn_ring_quartets") {
         // the kernel choice is baked into the captured step graphs

@@ -561,17 +561,26 @@ __global__ void __launch_bounds__((4 * Q + 1) * 32)
     // was launched (see attn_decode_kernel), so both roles may read them ahead of the PDL wait.
     const int pos = PAGED ? p.step_ptr[0] + p.pos_offset : 0;
     const long long rows_per_page = (long long)(p.page_stride / kDKV);
+    // work units: (item, part); all items of a launch have the same key count (self: pos + 1; cross:
+    // n_keys -- the host disables the split when key counts are per lane)
+    const int part_chunks = p.part_keys / kMmaChunk;             // 0: one unit per item
+    const int launch_keys = PAGED ? pos + 1 : p.n_keys;
+    const int n_parts = part_chunks ? max(1, (launch_keys + p.part_keys - 1) / p.part_keys) : 1;
+    const int n_units = n_items * n_parts;
 
     if (warp == kMmaWarps) {
         // ---------------- producer ----------------
         if (lane == 0) {
             const uint64_t policy = l2_policy_evict_first();
             int cnt0 = 0, cnt1 = 0;  // chunks handed to each quartet so far
-            for (int item = blockIdx.x; item < n_items; item += gridDim.x) {
+            for (int unit = blockIdx.x; unit < n_units; unit += gridDim.x) {
+                const int item = unit / n_parts, part = unit - item * n_parts;
                 const int lane_id = item / kHeads, head = item - lane_id * kHeads;
                 if (p.active && !p.active[lane_id]) continue;
                 const MmaItem it = mma_item<PAGED>(p, lane_id, head, pos);
-                for (int c = 0; c < it.n_chunks; ++c) {
+                const int c_begin = part * part_chunks;
+                const int c_end = part_chunks ? min(it.n_chunks, c_begin + part_chunks) : it.n_chunks;
+                for (int c = c_begin; c < c_end; ++c) {
                     const int qt = c & (kMmaQuartets - 1);
                     const int n = qt ? cnt1++ : cnt0++;
                     const int s = qt * S + n % S;
@@ -605,10 +614,13 @@ __global__ void __launch_bounds__((4 * Q + 1) * 32)
     const int quad = lane & 3;
 
     int cnt = 0, buf = 0;
-    for (int item = blockIdx.x; item < n_items; item += gridDim.x) {
+    for (int unit = blockIdx.x; unit < n_units; unit += gridDim.x) {
+        const int item = unit / n_parts, part = unit - item * n_parts;
         const int lane_id = item / kHeads, head = item - lane_id * kHeads;
         if (p.active && !p.active[lane_id]) continue;
         const MmaItem it = mma_item<PAGED>(p, lane_id, head, pos);
+        const int c_begin = part * part_chunks;   // part_chunks is even: chunk parity == ring-quartet parity
+        const int c_end = part_chunks ? min(it.n_chunks, c_begin + part_chunks) : it.n_chunks;
 
         // A fragments of q: row 0 of the 16 x 64 tile is the query, rows 1..15 are zero
         const bf16* qrow = p.q + (size_t)lane_id * p.q_stride + head * kDKV;
@@ -630,7 +642,7 @@ __global__ void __launch_bounds__((4 * Q + 1) * 32)
 
         const int qt = warp >> 2;          // this warp's quartet: chunks with (c % 2) == qt
         const int kb = (warp & 3) * 16;    // its 16 keys inside every such chunk
-        for (int c = qt; c < it.n_chunks; c += kMmaQuartets, ++cnt) {
+        for (int c = c_begin + qt; c < c_end; c += kMmaQuartets, ++cnt) {
             const int s = qt * S + cnt % S;
             mbar_wait(full0 + 8 * s, (cnt / S) & 1);
             const int k0 = c * kMmaChunk;
@@ -722,15 +734,15 @@ __global__ void __launch_bounds__((4 * Q + 1) * 32)
         // merge the eight warps' partial states in fixed order
         l_run += __shfl_xor_sync(0xffffffffu, l_run, 1);
         l_run += __shfl_xor_sync(0xffffffffu, l_run, 2);
-        float* part = merge + (buf * kMmaWarps + warp) * kMmaPartFloats;
+        float* wpart = merge + (buf * kMmaWarps + warp) * kMmaPartFloats;
         if (lane < 4) {
             if (lane == 0) {
-                part[0] = m_run;
-                part[1] = l_run;
+                wpart[0] = m_run;
+                wpart[1] = l_run;
             }
 #pragma unroll
             for (int ni = 0; ni < 8; ++ni)
-                *reinterpret_cast<float2*>(part + 2 + ni * 8 + quad * 2) = make_float2(o[ni][0], o[ni][1]);
+                *reinterpret_cast<float2*>(wpart + 2 + ni * 8 + quad * 2) = make_float2(o[ni][0], o[ni][1]);
         }
         named_bar_sync(1, kMmaWarps * 32);
         if (warp == 0) {
@@ -747,9 +759,44 @@ __global__ void __launch_bounds__((4 * Q + 1) * 32)
                 o0 += ov.x * wgt;
                 o1 += ov.y * wgt;
             }
-            const float inv = 1.f / den;
-            *reinterpret_cast<uint32_t*>(p.out + (size_t)lane_id * p.out_stride + head * kDKV + lane * 2) =
-                pack_bf16(o0 * inv, o1 * inv);
+            bool write_out = true;
+            if (n_parts > 1) {
+                // publish this part's state; whoever completes the item merges the parts in part order
+                // (fixed order: the result is a function of the item alone)
+                float* mine = p.part_scratch + ((size_t)item * p.max_parts + part) * kMmaPartFloats;
+                if (lane == 0) {
+                    mine[0] = mx;
+                    mine[1] = den;
+                }
+                *reinterpret_cast<float2*>(mine + 2 + lane * 2) = make_float2(o0, o1);
+                __threadfence();
+                __syncwarp();
+                int ticket = 0;
+                if (lane == 0) ticket = atomicAdd(p.part_counter + item, 1);
+                ticket = __shfl_sync(0xffffffffu, ticket, 0);
+                write_out = ticket == n_parts - 1;
+                if (write_out) {
+                    __threadfence();
+                    const float* all = p.part_scratch + (size_t)item * p.max_parts * kMmaPartFloats;
+                    float mall = -INFINITY;
+                    for (int q = 0; q < n_parts; ++q) mall = fmaxf(mall, __ldcg(all + q * kMmaPartFloats));
+                    den = 0.f, o0 = 0.f, o1 = 0.f;
+                    for (int q = 0; q < n_parts; ++q) {
+                        const float* pq = all + q * kMmaPartFloats;
+                        const float wgt = exp2f(__ldcg(pq) - mall);
+                        den += __ldcg(pq + 1) * wgt;
+                        const float2 ov = __ldcg(reinterpret_cast<const float2*>(pq + 2 + lane * 2));
+                        o0 += ov.x * wgt;
+                        o1 += ov.y * wgt;
+                    }
+                    if (lane == 0) p.part_counter[item] = 0;  // ready for the next launch (stream-ordered)
+                }
+            }
+            if (write_out) {
+                const float inv = 1.f / den;
+                *reinterpret_cast<uint32_t*>(p.out + (size_t)lane_id * p.out_stride + head * kDKV + lane * 2) =
+                    pack_bf16(o0 * inv, o1 * inv);
+            }
         }
         buf ^= 1;  // the other half is free again once every warp has passed the next item's barrier
     }
@@ -786,9 +833,18 @@ static Status launch_ring(const AttnDecodeParams& p, int n_lanes, cudaStream_t s
     const int n_items = n_lanes * kHeads;
     const int per_sm = g_ring_ctas_per_sm > 0 ? g_ring_ctas_per_sm
                                               : std::max(1, std::min(3, n_items / (2 * n_sm_of[dev])));
-    const int grid = std::min(n_items, n_sm_of[dev] * per_sm);
+    AttnDecodeParams q = p;
+    if (q.part_keys > 0) {
+        if (q.part_keys % (kMmaChunk * Q) != 0 || !q.part_scratch || !q.part_counter || q.max_parts < 1)
+            return Error(2, "attn ring: part_keys must be a multiple of 64 x quartets, with scratch attached");
+        if (!PAGED && q.n_keys_ptr) q.part_keys = 0;  // per-lane key counts: units would not be uniform
+    }
+    // with split keys the number of units depends on the position (a device scalar): size the grid for
+    // the SMs, CTAs that find no unit exit at once
+    const int max_units = q.part_keys > 0 ? n_items * q.max_parts : n_items;
+    const int grid = std::min(max_units, n_sm_of[dev] * per_sm);
     MRMT3_TRY(launch_pdl(kern, dim3(grid), dim3((4 * Q + 1) * 32), smem, stream,
-                         *reinterpret_cast<const CUtensorMap*>(p.tmap), p, n_lanes));
+                         *reinterpret_cast<const CUtensorMap*>(q.tmap), q, n_lanes));
     return OkStatus();
 }
 

@@ -33,6 +33,14 @@ struct AttnFullParams {
                            // 64 kt + 8 ni + 2 j + e  (the mma C-fragment order of a 64-key tile)
 };
 Status launch_attn_full(const AttnFullParams& p, int batch, cudaStream_t stream);
+// tcgen05 / TMEM version of the same contract (attention_tc.cu): S = Q K^T and O = P V as tcgen05.mma with
+// the accumulators in TMEM, one softmax thread per query row.  Selected by launch_attn_full_auto.
+class TmaCache;
+Status launch_attn_full_tc(TmaCache& tc, const AttnFullParams& p, int batch, cudaStream_t stream);
+// the tcgen05 kernel when enabled (MRMT3_ATTN_FULL_TC / option "attn_full_tc") and the problem has at
+// least one full 128-row query tile, else the mma.sync kernel
+Status launch_attn_full_auto(TmaCache& tc, const AttnFullParams& p, int batch, cudaStream_t stream);
+void attn_full_configure(int use_tc);
 
 // decode-step attention (one query per lane and head)
 struct AttnDecodeParams {
@@ -60,6 +68,16 @@ struct AttnDecodeParams {
     // a lane group), 0 for the page pool
     const void* tmap;
     long long tmap_row0;
+    // TMA variant, split-key work units: when part_keys > 0 (a multiple of 64) an item's keys are cut
+    // at FIXED multiples of part_keys, every part is a work unit of its own (partial softmax state
+    // to part_scratch), and the CTA that finishes an item's last outstanding part merges them in part
+    // order.  The cut points depend on the key count only, never on the batch: a row's result does
+    // not depend on its batch neighbours.  part_scratch: (lanes, heads, max_parts, 66) fp32 of this
+    // lane group; part_counter: (lanes, heads) ints, zero between launches (the merger resets them).
+    int part_keys;
+    int max_parts;
+    float* part_scratch;
+    int* part_counter;
     TraceSlot trace;
 };
 Status launch_attn_decode(const AttnDecodeParams& p, int n_lanes, bool paged, cudaStream_t stream);

@@ -185,6 +185,8 @@ Status handle_init(mrmt3_handle* h) {
     const char* ng = getenv("MRMT3_NO_GRAPH");
     h->use_graphs = !(ng && ng[0] == '1');
     if (const char* gl = getenv("MRMT3_GROUP_LANES")) h->group_lanes = atoi(gl);
+    if (const char* e = getenv("MRMT3_ATTN_PART_SELF")) h->attn_part_keys_self = atoi(e);
+    if (const char* e = getenv("MRMT3_ATTN_PART_CROSS")) h->attn_part_keys_cross = atoi(e);
     {   // tuning sweeps (scripts/): decode-attention kernel selection
         const char* av = getenv("MRMT3_ATTN_VARIANT");
         const char* as = getenv("MRMT3_ATTN_STAGES");
@@ -255,6 +257,7 @@ void handle_destroy(mrmt3_handle* h) {
     h->d_qc.release(); h->d_ff.release(); h->d_logits.release(); h->d_state.release();
     train_destroy(h);
     h->kv_pool.release(); h->block_table.release(); h->cross_cache.release(); h->lane_tab.release();
+    h->attn_parts.release(); h->attn_tickets.release();
     if (h->h_pinned) cudaFreeHost(h->h_pinned);
     if (h->poll_ev[0]) cudaEventDestroy(h->poll_ev[0]);
     if (h->poll_ev[1]) cudaEventDestroy(h->poll_ev[1]);
@@ -448,7 +451,7 @@ static Status run_encoder_stack(mrmt3_handle* h, const StackW& st, int n_seq, in
             ap.Tq = q_rows;
             ap.O = w.ctx_c.as<bf16>();
             ap.o_batch_stride = (long)q_rows * kInner;
-            RUN(h, launch_attn_full(ap, n_seq, s));
+            RUN(h, launch_attn_full_auto(*h->tma, ap, n_seq, s));
             RUN(h, launch_gather_rows(hcur, w.hc32.as<float>(), n_seq, q_rows, T, s));
             hcur = w.hc32.as<float>();
             Mcur = n_seq * q_rows;
@@ -458,7 +461,7 @@ static Status run_encoder_stack(mrmt3_handle* h, const StackW& st, int n_seq, in
             ap.Tq = T;
             ap.O = w.ctx.as<bf16>();
             ap.o_batch_stride = (long)T * kInner;
-            RUN(h, launch_attn_full(ap, n_seq, s));
+            RUN(h, launch_attn_full_auto(*h->tma, ap, n_seq, s));
             RUN(h, launch_gemm_tc(*h->tma, w.ctx.as<bf16>(), kInner, M, ARowMap{nullptr, 1}, L.wo, kInner, M, kDModel,
                                    kInner, EpiResidual{hcur, kDModel}, s));
         }
@@ -575,6 +578,10 @@ Status ensure_decode_capacity(mrmt3_handle* h, int n_lanes, int tk, int max_posi
     MRMT3_TRY(h->kv_pool.reserve(c * pgc * page_elems(h) * sizeof(bf16)));
     MRMT3_TRY(h->cross_cache.reserve(c * h->cfg.n_dec_layers * 2 * kHeads * (size_t)tkc * kDKV * sizeof(bf16)));
     MRMT3_TRY(h->block_table.reserve(c * pgc * sizeof(int)));
+    h->attn_max_parts = std::max(pgc * kKVPage, tkc) / 128 + 1;   // parts are >= 128 keys
+    MRMT3_TRY(h->attn_parts.reserve(c * kHeads * h->attn_max_parts * 66 * sizeof(float)));
+    MRMT3_TRY(h->attn_tickets.reserve(c * kHeads * sizeof(int)));
+    MRMT3_CUDA_TRY(cudaMemset(h->attn_tickets.p, 0, h->attn_tickets.cap));
 
     MRMT3_CUDA_TRY(cudaMemset(h->d_h32.p, 0, h->d_h32.cap));
     // the TMA attention kernel loads whole 32-row boxes and masks the rows past the valid keys
@@ -654,6 +661,10 @@ static Status enqueue_step(mrmt3_handle* h, const StepPlan& pl, int kind, cudaSt
         ap.active = pl.st.active;
         ap.tmap = self_map;
         ap.tmap_row0 = 0;
+        ap.part_keys = h->attn_part_keys_self;
+        ap.max_parts = h->attn_max_parts;
+        ap.part_scratch = h->attn_parts.as<float>() + l0 * kHeads * h->attn_max_parts * 66;
+        ap.part_counter = h->attn_tickets.as<int>() + l0 * kHeads;
         ap.trace = next_trace();
         RUNC(h, MRMT3_PROF_ATTN_SELF, s, launch_attn_decode(ap, n, true, s));
         RUNC(h, MRMT3_PROF_GEMM_O, s, (launch_gemm_skinny<32, kInner, false>(
@@ -674,6 +685,10 @@ static Status enqueue_step(mrmt3_handle* h, const StepPlan& pl, int kind, cudaSt
         cp.active = pl.st.active;
         cp.tmap = cross_map;
         cp.tmap_row0 = (long long)(l0 * cross_lane / kDKV);
+        cp.part_keys = h->attn_part_keys_cross;
+        cp.max_parts = h->attn_max_parts;
+        cp.part_scratch = ap.part_scratch;
+        cp.part_counter = ap.part_counter;
         cp.trace = next_trace();
         RUNC(h, MRMT3_PROF_ATTN_CROSS, s, launch_attn_decode(cp, n, false, s));
         RUNC(h, MRMT3_PROF_GEMM_CO, s, (launch_gemm_skinny<32, kInner, false>(
@@ -1117,7 +1132,7 @@ Status api_forward_logits(mrmt3_handle* h, const float* mel, int B, const long l
                 ap.Tk = L;
                 ap.causal = 1;
                 ap.causal_offset = 0;
-                RUN(h, launch_attn_full(ap, nb, s));
+                RUN(h, launch_attn_full_auto(*h->tma, ap, nb, s));
                 RUN(h, launch_gemm_tc(*h->tma, w.ctx.as<bf16>(), kInner, M, id, Lw.wo, kInner, M, kDModel, kInner, EpiResidual{H, kDModel}, s));
 
                 RUN(h, launch_rmsnorm(H, Lw.ln_cross, eps, w.n_bf16.as<bf16>(), nullptr, M, nullptr, 1, s));
@@ -1143,7 +1158,7 @@ Status api_forward_logits(mrmt3_handle* h, const float* mel, int B, const long l
                 cp.Tq = L;
                 cp.Tk = tk;
                 cp.causal = 0;
-                RUN(h, launch_attn_full(cp, nb, s));
+                RUN(h, launch_attn_full_auto(*h->tma, cp, nb, s));
                 RUN(h, launch_gemm_tc(*h->tma, w.ctx.as<bf16>(), kInner, M, id, Lw.co, kInner, M, kDModel, kInner, EpiResidual{H, kDModel}, s));
 
                 RUN(h, launch_rmsnorm(H, Lw.ln_ff, eps, w.n_bf16.as<bf16>(), nullptr, M, nullptr, 1, s));

@@ -77,6 +77,9 @@ struct StepGraph {
 };
 
 constexpr int kMaxLanes = 512;    // decode lanes per wave
+// split-key decode attention defaults (0 = one work unit per (lane, head)); see attention.cuh
+constexpr int kDefaultPartKeysSelf = 0;
+constexpr int kDefaultPartKeysCross = 0;
 
 }  // namespace mrmt3
 
@@ -129,6 +132,10 @@ struct mrmt3_handle {
     mrmt3::DeviceBuffer d_h32, d_n_bf16, d_qkv, d_ctx, d_qc, d_ff, d_logits;
     mrmt3::DeviceBuffer d_state;         // ints: step, n_active, ticket, then per-lane arrays
     mrmt3::DeviceBuffer kv_pool, block_table, cross_cache;
+    // split-key decode attention (attention.cuh): partial softmax states + per-item tickets
+    mrmt3::DeviceBuffer attn_parts, attn_tickets;
+    int attn_max_parts = 0;
+    int attn_part_keys_self = mrmt3::kDefaultPartKeysSelf, attn_part_keys_cross = mrmt3::kDefaultPartKeysCross;
     mrmt3::DeviceBuffer lane_tab;        // per-lane int tables (seg index, prev row, active)
     int* h_pinned = nullptr;             // pinned host ints for polling / finish steps
 

@@ -445,7 +445,7 @@ Status train_forward(mrmt3_handle* h, const float* mel, int B, const long long* 
         ap.k_row_stride = ap.v_row_stride = kr;
         ap.O = O; ap.o_batch_stride = (long)Tq * kInner; ap.o_head_stride = kDKV; ap.o_row_stride = kInner;
         ap.Tq = Tq; ap.Tk = Tk; ap.causal = causal; ap.causal_offset = 0; ap.lse2 = lse; ap.drop = drop;
-        RUN(h, launch_attn_full(ap, nb, s));
+        RUN(h, launch_attn_full_auto(*h->tma, ap, nb, s));
         return OkStatus();
     };
     // H' = H + dropout(A . W^T)   (sublayer output) into a fresh buffer: the old H is exactly the

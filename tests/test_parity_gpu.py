@@ -468,3 +468,39 @@ def test_segmem_v1_generate_without_memory_is_the_plain_loop(pkg, feats):
     a = v1.generate(feats.cuda(), max_length=64)
     b = plain.generate(feats.cuda(), max_length=64)
     assert a.shape == b.shape and torch.equal(a, b)
+
+
+def test_split_key_attention_units(pkg):
+    """Decode attention with an item's keys cut into fixed 128/256-key parts (work units of their own,
+    merged in part order by the last finisher): logits within fp32 merge-order noise of the unsplit
+    kernel over 300 steps (parts appear at step 128/256), tokens independent of the lane grouping and of
+    the batch a row sits in -- the cut points depend on the key count only."""
+    model, _ = _model(pkg, 1239, eos_scale=2.0)
+    eng = model.engine()
+    x = syn.synthetic_features(13, 40).cuda()
+    try:
+        eng.set_option("attn_part_keys_self", 0)
+        eng.set_option("attn_part_keys_cross", 0)
+        want_tok = eng.generate(x, max_length=300)
+        forced = torch.zeros((40, 301), dtype=torch.int64)
+        forced[:, :want_tok.shape[1]] = want_tok.cpu()
+        _, want_logits = eng.generate(x, max_length=300, forced_ids=forced, return_logits=True)
+        for ps, pc in ((128, 128), (256, 128), (256, 0)):
+            eng.set_option("attn_part_keys_self", ps)
+            eng.set_option("attn_part_keys_cross", pc)
+            _, got = eng.generate(x, max_length=300, forced_ids=forced, return_logits=True)
+            err = (got - want_logits).abs().max().item()
+            assert err < 5e-3, (ps, pc, err)
+            eng.set_option("group_lanes", 0)
+            one = eng.generate(x, max_length=300)
+            eng.set_option("group_lanes", 7)
+            many = eng.generate(x, max_length=300)
+            sub = eng.generate(x[11:19], max_length=300)
+            eng.set_option("group_lanes", -1)
+            assert torch.equal(one, many), (ps, pc)
+            n = min(one.shape[1], sub.shape[1])
+            assert torch.equal(one[11:19, :n], sub[:, :n]), (ps, pc)
+    finally:
+        eng.set_option("attn_part_keys_self", -1)
+        eng.set_option("attn_part_keys_cross", -1)
+        eng.set_option("group_lanes", -1)
