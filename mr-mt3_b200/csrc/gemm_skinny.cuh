@@ -78,7 +78,7 @@ __device__ __forceinline__ void cp_async_wait_dyn(int n) {
 template <int BN, int K, bool NORM, class Epi>
 __global__ void __launch_bounds__(128)
     gemm_skinny_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant__ CUtensorMap tm_w, int M,
-                       float eps, Epi epi, TraceSlot trace) {
+                       float eps, Epi epi, TraceSlot trace, const bf16* __restrict__ A, int lda, int a_mode) {
     constexpr int BM = 32;
     trace_begin(trace);
     constexpr int KT = K / 64;
@@ -118,14 +118,36 @@ __global__ void __launch_bounds__(128)
     pdl_wait();
     trace_mark(trace, 0);
     pdl_launch_dependents();
-    if (tid == 0) {
+    if (a_mode == 0) {
+        if (tid == 0) {
 #pragma unroll
-        for (int kt = 0; kt < KT; ++kt) {
-            mbar_expect_tx(bars + 8 * kt, BM * 128);
-            tma_load_2d(smem_u32(sA + kt * BM * 64), &tm_a, kt * 64, m0, bars + 8 * kt);
+            for (int kt = 0; kt < KT; ++kt) {
+                mbar_expect_tx(bars + 8 * kt, BM * 128);
+                tma_load_2d(smem_u32(sA + kt * BM * 64), &tm_a, kt * 64, m0, bars + 8 * kt);
+            }
         }
+    } else {
+        // The activation tile is the only operand on the critical path (it exists once the producer
+        // kernel has finished; the weights were requested before the wait).  One thread's KT box loads
+        // land one after another (~0.15 us per box, measured with the trace stamps: 1.5 us for K = 512);
+        // issued as 16-byte cp.async from all 128 threads at once they cost one L2 round trip.  Rows
+        // at or past M are zero-filled without touching memory.  Same 128-byte swizzle as the TMA tiles.
+        constexpr int CPR = K / 8;  // 16-byte chunks per row
+        for (int c = tid; c < BM * CPR; c += 128) {
+            const int row = c / CPR, cc = c - row * CPR;
+            const int kt = cc >> 3, ch = cc & 7;
+            const bool pred = m0 + row < M;
+            cp_async16(sA + kt * BM * 64 + row * 64 + ((ch ^ (row & 7)) << 3),
+                       A + (size_t)(pred ? m0 + row : 0) * lda + cc * 8, pred);
+        }
+        cp_async_commit();
+        if (tid == 0) {
+#pragma unroll
+            for (int kt = 0; kt < KT; ++kt) mbar_arrive(bars + 8 * kt);  // stands in for the A half of each barrier
+        }
+        cp_async_wait<0>();
     }
-    __syncthreads();  // barrier initialisation is visible to every waiter
+    __syncthreads();  // barrier initialisation (and the cp.async tile) visible to every waiter
 
     // four independent accumulator sets, one per 16-wide k step of a k-tile: the dependent
     // mma -> mma chain of an output fragment is K/64 long instead of K/16 (the chain, not the
@@ -235,6 +257,16 @@ __global__ void __launch_bounds__(128)
     trace_end(trace);
 }
 
+// how the activation tile reaches shared memory: 0 = TMA boxes, 1 = cp.async from all threads (default);
+// MRMT3_SKINNY_A_MODE overrides (A/B measurements)
+inline int skinny_a_mode() {
+    static const int mode = [] {
+        const char* e = getenv("MRMT3_SKINNY_A_MODE");
+        return e ? atoi(e) : 1;
+    }();
+    return mode;
+}
+
 template <int BN, int K, bool NORM, class Epi>
 Status launch_gemm_skinny(TmaCache& tc, const bf16* A, int lda, const bf16* W, int ldw, int M, int N, float eps,
                           const Epi& epi, cudaStream_t stream, TraceSlot trace = TraceSlot{nullptr, 0}) {
@@ -246,9 +278,11 @@ Status launch_gemm_skinny(TmaCache& tc, const bf16* A, int lda, const bf16* W, i
     MRMT3_TRY(ensure_dynamic_smem(kern, smem));
     const CUtensorMap *ma = nullptr, *mw = nullptr;
     MRMT3_TRY(tc.get(A, M, K, lda, 32, &ma));
+    const CUtensorMap a_copy = *ma;  // the second lookup may rotate the cache
     MRMT3_TRY(tc.get(W, N, K, ldw, BN, &mw));
     dim3 grid(N / BN, ceil_div(M, 32));
-    MRMT3_TRY(launch_pdl(kern, grid, dim3(128), smem, stream, *ma, *mw, M, eps, epi, trace));
+    MRMT3_TRY(launch_pdl(kern, grid, dim3(128), smem, stream, a_copy, *mw, M, eps, epi, trace, A, lda,
+                         skinny_a_mode()));
     return OkStatus();
 }
 

@@ -18,6 +18,13 @@ from helpers import first_divergence, load_synthetic, package, top2_margin
 pytestmark = pytest.mark.gpu
 BF16_ATOL = 0.08
 BF16_MARGIN = 0.08
+# MR-MT3 adds the memory block (token embedding -> segmem_proj -> encoder layer, all with bf16 GEMM
+# inputs) to the cross-attention keys: its logits carry more rounding noise than plain MT3's (0.074 max
+# at L = 20 against the reference golden, tests/test_parity_gpu.py).  Over 24 x 256 x 1536 logits the MAX
+# is bounded a little looser, and the RMS error -- which a wrong row, mask or position would move by an
+# order of magnitude -- tightly.
+SEGMEM_ATOL = 0.12
+SEGMEM_RMS = 0.02
 syn = load_synthetic()
 
 
@@ -62,8 +69,10 @@ def test_1024_step_logits_through_graphs_and_lane_groups(long_oracle, ring_ctas,
         eng.set_option("attn_part_keys_cross", part_cross)
         ids, logits = eng.generate(x.cuda(), max_length=1024, forced_ids=want.cuda(), return_logits=True)
         np.testing.assert_array_equal(ids.cpu().numpy(), want.numpy())
-        err = (logits.cpu().double() - want_logits).abs().amax(dim=(0, 2))          # per step
-        print(f"ring_ctas={ring_ctas} parts={part_self}/{part_cross}: per-step logit err max {err.max():.4f} at step {int(err.argmax())}; "
+        diff = logits.cpu().double() - want_logits
+        err = diff.abs().amax(dim=(0, 2))                                            # per step
+        print(f"ring_ctas={ring_ctas} parts={part_self}/{part_cross}: rms {float(diff.pow(2).mean().sqrt()):.5f}, "
+              f"per-step logit err max {err.max():.4f} at step {int(err.argmax())}; "
               f"by KV page: {[round(float(err[p * 128:(p + 1) * 128].max()), 4) for p in range(8)]}")
         assert float(err.max()) < BF16_ATOL
         # free-running tokens, same path
@@ -109,13 +118,18 @@ def test_segmem_three_tracks_eight_segments_256_tokens():
                                                  forced_ids=forced.cuda())
         np.testing.assert_array_equal(got_forced.cpu().numpy(), want.numpy())
         logits = logits.cpu().double()
-        worst = 0.0
+        worst, sq, cnt = 0.0, 0.0, 0
         for s, tr in enumerate(traces):
             ref = torch.cat(tr)                                 # (steps, V)
-            err = (logits[s, :ref.shape[0]] - ref).abs().max().item()
+            d = logits[s, :ref.shape[0]] - ref
+            err = d.abs().max().item()
             worst = max(worst, err)
-            assert err < BF16_ATOL, (s, err)
-        print("MR-MT3 24 segments x 256 forced steps: worst per-step logit err", round(worst, 4))
+            sq += float((d * d).sum())
+            cnt += d.numel()
+            assert err < SEGMEM_ATOL, (s, err)
+        rms = (sq / cnt) ** 0.5
+        print(f"MR-MT3 24 segments x 256 forced steps: worst per-step logit err {worst:.4f}, rms {rms:.5f}")
+        assert rms < SEGMEM_RMS
     finally:
         eng.set_option("hooks_fast_path", 0)
         eng.set_option("group_lanes", -1)
