@@ -73,7 +73,10 @@ int64_t mrmt3_launch_count(const mrmt3_handle* h);
  * quartets per CTA, "attn_ring_ctas" = its persistent CTAs per SM (1..8, 0 = by launch size).  The
  * attention settings are process-wide.  "attn_part_keys_self" / "attn_part_keys_cross" = split-key work
  * units of variant 1: an item's keys are cut at fixed multiples of this many keys (0 = off, else a
- * multiple of 128) and the parts are merged in order by the last finisher.  "hooks_fast_path" = 1 sends calls that use the parity hooks of
+ * multiple of 128) and the parts are merged in order by the last finisher.  "fuse_greedy" = 1 (default):
+ * the vocabulary projection, the arg-max, the EOS bookkeeping and the next step's embedding lookup run as
+ * ONE kernel and the logits never reach memory; 0 = separate lm_head / arg-max / embed kernels.
+ * "hooks_fast_path" = 1 sends calls that use the parity hooks of
  * mrmt3_generate / mrmt3_generate_segmem (forced_ids, logits_out) through the production decode path
  * (CUDA-graph replay, concurrent lane groups) instead of the eager single-group debug path. */
 int mrmt3_set_option(mrmt3_handle* h, const char* key, int value);

@@ -128,6 +128,12 @@ int mrmt3_set_option(mrmt3_handle* h, const char* key, int value) {
     else if (k == "use_graphs") h->use_graphs = value != 0;
     else if (k == "group_serial") h->group_serial = value != 0;
     else if (k == "hooks_fast_path") h->hooks_fast_path = value != 0;
+    else if (k == "fuse_greedy") {
+        cudaSetDevice(h->device);
+        cudaDeviceSynchronize();
+        drop_graphs(h);
+        h->fuse_greedy = value != 0;
+    }
     else if (k == "attn_full_tc") attn_full_configure(value);
     else if (k == "attn_part_keys_self" || k == "attn_part_keys_cross") {
         const bool self = k == "attn_part_keys_self";

@@ -16,6 +16,7 @@
 #include <type_traits>
 
 #include "gemm_mma.cuh"
+#include "layers.cuh"
 #include "tma.cuh"
 
 namespace mrmt3 {
@@ -48,6 +49,29 @@ struct EpiResidualBoth {
         *reinterpret_cast<uint32_t*>(Hb + o) = pack_bf16(h.x, h.y);
     }
 };
+
+// Greedy head fused into the lm_head GEMM (the logits are never materialised).  Every CTA
+// reduces its 64 logit columns to one (value, index) per row; the last CTA of a 32-row tile (atomic
+// ticket) reduces the per-tile candidates in column order -- the lowest index wins ties, as
+// torch.argmax and the stand-alone arg-max kernel do -- and then does what argmax_advance_kernel does
+// (token write-out, EOS bookkeeping of reference models/t5.py:286-291, forced tokens) and, when `emb`
+// is given, the NEXT step's input row H = Emb[token] + PE[step + 1] (decode_embed_kernel); the last
+// tile to finish advances the step counter.
+struct EpiGreedy {
+    static constexpr bool kGreedy = true;
+    DecodeState st;
+    float2* cand;        // (lanes of the group, n column tiles): value, index bits
+    int* tile_ticket;    // one per 32-row tile of the group, zero between launches
+    int vocab;
+    const float* emb;    // nullptr: leave the next step's embedding to decode_embed_kernel
+    const float* pe;
+    float* H;
+    bf16* Hb;
+};
+template <class Epi, class = void>
+struct EpiIsGreedy : std::false_type {};
+template <class Epi>
+struct EpiIsGreedy<Epi, std::enable_if_t<Epi::kGreedy>> : std::true_type {};
 
 template <class Epi, class = void>
 struct EpiPrefetches : std::false_type {};
@@ -242,16 +266,119 @@ __global__ void __launch_bounds__(128)
         sc0 = s_scale[wm0 + (lane >> 2)];
         sc1 = s_scale[wm0 + (lane >> 2) + 8];
     }
+    if constexpr (EpiIsGreedy<Epi>::value) {
+        __shared__ float s_val[2][BM];
+        __shared__ int s_idx[2][BM];
+        __shared__ int s_tok[BM];
+        __shared__ int s_last;
+        // this thread's best over its columns of rows r and r + 8 (ascending columns, strict '>': the
+        // lowest index wins among equals)
+        float b0 = -INFINITY, b1 = -INFINITY;
+        int i0 = 0x7fffffff, i1 = 0x7fffffff;
 #pragma unroll
-    for (int ni = 0; ni < NI; ++ni) {
-        int row = m0 + wm0 + (lane >> 2);
-        int col = n0 + wn0 + ni * 8 + (lane & 3) * 2;
-        if constexpr (EpiPrefetches<Epi>::value) {
-            if (row < M) epi.store(row, col, pre[ni][0], acc[ni][0] * sc0, acc[ni][1] * sc0);
-            if (row + 8 < M) epi.store(row + 8, col, pre[ni][1], acc[ni][2] * sc1, acc[ni][3] * sc1);
-        } else {
-            if (row < M) epi(row, col, acc[ni][0] * sc0, acc[ni][1] * sc0);
-            if (row + 8 < M) epi(row + 8, col, acc[ni][2] * sc1, acc[ni][3] * sc1);
+        for (int ni = 0; ni < NI; ++ni) {
+            const int col = n0 + wn0 + ni * 8 + (lane & 3) * 2;
+            const float v00 = acc[ni][0] * sc0, v01 = acc[ni][1] * sc0, v10 = acc[ni][2] * sc1, v11 = acc[ni][3] * sc1;
+            if (v00 > b0) { b0 = v00; i0 = col; }
+            if (v01 > b0) { b0 = v01; i0 = col + 1; }
+            if (v10 > b1) { b1 = v10; i1 = col; }
+            if (v11 > b1) { b1 = v11; i1 = col + 1; }
+        }
+#pragma unroll
+        for (int o = 1; o <= 2; o <<= 1) {
+            float ob = __shfl_xor_sync(0xffffffffu, b0, o);
+            int oi = __shfl_xor_sync(0xffffffffu, i0, o);
+            if (ob > b0 || (ob == b0 && oi < i0)) { b0 = ob; i0 = oi; }
+            ob = __shfl_xor_sync(0xffffffffu, b1, o);
+            oi = __shfl_xor_sync(0xffffffffu, i1, o);
+            if (ob > b1 || (ob == b1 && oi < i1)) { b1 = ob; i1 = oi; }
+        }
+        if ((lane & 3) == 0) {
+            const int r = wm0 + (lane >> 2);
+            s_val[warp & 1][r] = b0;
+            s_idx[warp & 1][r] = i0;
+            s_val[warp & 1][r + 8] = b1;
+            s_idx[warp & 1][r + 8] = i1;
+        }
+        __syncthreads();
+        if (tid < BM && m0 + tid < M) {
+            float v = s_val[0][tid];
+            int i = s_idx[0][tid];
+            if (s_val[1][tid] > v) { v = s_val[1][tid]; i = s_idx[1][tid]; }  // half 1 holds the higher columns
+            epi.cand[(size_t)(m0 + tid) * gridDim.x + blockIdx.x] = make_float2(v, __int_as_float(i));
+        }
+        __threadfence();
+        __syncthreads();
+        if (tid == 0) s_last = atomicAdd(epi.tile_ticket + blockIdx.y, 1) == (int)gridDim.x - 1;
+        __syncthreads();
+        if (s_last) {
+            __threadfence();
+            const DecodeState& st = epi.st;
+            const int step = st.step[0];  // advanced only after every tile has passed this point
+            if (tid < BM) s_tok[tid] = -1;
+            if (tid < BM && m0 + tid < M && st.active[m0 + tid]) {
+                const int ln = m0 + tid;
+                float best = -INFINITY;
+                int best_i = 0x7fffffff;
+                for (int j = 0; j < (int)gridDim.x; ++j) {  // ascending column tiles
+                    const float2 c = __ldcg(epi.cand + (size_t)ln * gridDim.x + j);
+                    if (c.x > best) { best = c.x; best_i = __float_as_int(c.y); }
+                }
+                const int n_emitted = step - st.prefix_len + 1;  // tokens emitted incl. this one
+                int next = best_i;
+                if (st.forced) {
+                    const size_t frow = st.forced_by_row ? (size_t)st.out_row[ln] : (size_t)ln;
+                    const long long f = st.forced[frow * st.forced_stride + n_emitted];
+                    next = (f < 0 || f >= epi.vocab) ? st.pad_id : (int)f;
+                }
+                st.out[(size_t)st.out_row[ln] * st.out_stride + n_emitted] = next;
+                st.tok[ln] = next;
+                const bool done = (!st.forced && next == st.eos_id) || n_emitted >= st.max_tokens;
+                if (done) {
+                    st.active[ln] = 0;
+                    st.finish_step[ln] = n_emitted;
+                    atomicSub(st.n_active, 1);
+                } else {
+                    s_tok[tid] = next;
+                }
+            }
+            __syncthreads();
+            if (epi.emb) {  // next step's input rows of the lanes that go on
+                const int c = tid * 4;
+                const float4 pv = *reinterpret_cast<const float4*>(epi.pe + (size_t)(step + 1) * kDModel + c);
+                for (int r = 0; r < BM; ++r) {
+                    const int tok = s_tok[r];
+                    if (tok < 0) continue;
+                    const float4 e = *reinterpret_cast<const float4*>(epi.emb + (size_t)tok * kDModel + c);
+                    const float4 hv = make_float4(e.x + pv.x, e.y + pv.y, e.z + pv.z, e.w + pv.w);
+                    *reinterpret_cast<float4*>(epi.H + (size_t)(m0 + r) * kDModel + c) = hv;
+                    *reinterpret_cast<uint2*>(epi.Hb + (size_t)(m0 + r) * kDModel + c) =
+                        make_uint2(pack_bf16(hv.x, hv.y), pack_bf16(hv.z, hv.w));
+                }
+            }
+            __syncthreads();
+            if (tid == 0) {
+                epi.tile_ticket[blockIdx.y] = 0;
+                __threadfence();
+                const int tk = atomicAdd(st.ticket, 1);
+                if (tk == (int)gridDim.y - 1) {
+                    st.ticket[0] = 0;
+                    st.step[0] = step + 1;
+                }
+            }
+        }
+    } else {
+#pragma unroll
+        for (int ni = 0; ni < NI; ++ni) {
+            int row = m0 + wm0 + (lane >> 2);
+            int col = n0 + wn0 + ni * 8 + (lane & 3) * 2;
+            if constexpr (EpiPrefetches<Epi>::value) {
+                if (row < M) epi.store(row, col, pre[ni][0], acc[ni][0] * sc0, acc[ni][1] * sc0);
+                if (row + 8 < M) epi.store(row + 8, col, pre[ni][1], acc[ni][2] * sc1, acc[ni][3] * sc1);
+            } else {
+                if (row < M) epi(row, col, acc[ni][0] * sc0, acc[ni][1] * sc0);
+                if (row + 8 < M) epi(row + 8, col, acc[ni][2] * sc1, acc[ni][3] * sc1);
+            }
         }
     }
     trace_end(trace);

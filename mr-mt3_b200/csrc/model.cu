@@ -257,7 +257,7 @@ void handle_destroy(mrmt3_handle* h) {
     h->d_qc.release(); h->d_ff.release(); h->d_logits.release(); h->d_state.release();
     train_destroy(h);
     h->kv_pool.release(); h->block_table.release(); h->cross_cache.release(); h->lane_tab.release();
-    h->attn_parts.release(); h->attn_tickets.release();
+    h->attn_parts.release(); h->attn_tickets.release(); h->greedy_cand.release(); h->greedy_tickets.release();
     if (h->h_pinned) cudaFreeHost(h->h_pinned);
     if (h->poll_ev[0]) cudaEventDestroy(h->poll_ev[0]);
     if (h->poll_ev[1]) cudaEventDestroy(h->poll_ev[1]);
@@ -582,6 +582,9 @@ Status ensure_decode_capacity(mrmt3_handle* h, int n_lanes, int tk, int max_posi
     MRMT3_TRY(h->attn_parts.reserve(c * kHeads * h->attn_max_parts * 66 * sizeof(float)));
     MRMT3_TRY(h->attn_tickets.reserve(c * kHeads * sizeof(int)));
     MRMT3_CUDA_TRY(cudaMemset(h->attn_tickets.p, 0, h->attn_tickets.cap));
+    MRMT3_TRY(h->greedy_cand.reserve(c * (kVocab / 64) * sizeof(float2)));
+    MRMT3_TRY(h->greedy_tickets.reserve(c * sizeof(int)));
+    MRMT3_CUDA_TRY(cudaMemset(h->greedy_tickets.p, 0, h->greedy_tickets.cap));
 
     MRMT3_CUDA_TRY(cudaMemset(h->d_h32.p, 0, h->d_h32.cap));
     // the TMA attention kernel loads whole 32-row boxes and masks the rows past the valid keys
@@ -632,11 +635,17 @@ static Status enqueue_step(mrmt3_handle* h, const StepPlan& pl, int kind, cudaSt
     const bool narrow = narrow_env >= 0 ? narrow_env != 0 : n <= 64;
     int tslot = 0;
     auto next_trace = [&]() { return TraceSlot{h->trace_on ? h->trace_buf.as<unsigned long long>() : nullptr, tslot++}; };
+    // Plain token steps (no memory prefix, no logits sink) end in the fused greedy head, which also
+    // writes the next step's input rows: such a step has no embed and no arg-max kernel (the rows of
+    // step 0 come from one embed launch ahead of the loop, run_decode).
+    const bool fused_head = h->fuse_greedy && kind == 0 && !pl.ext_logits;
+    const bool fused_embed = fused_head && pl.st.prefix_len == 0 && !pl.prefix;
     DecodeState st_embed = pl.st;
     st_embed.trace = next_trace();
-    RUNC(h, MRMT3_PROF_EMBED, s, launch_decode_embed(st_embed, h->emb, h->pe,
-                                                    pl.prefix ? pl.prefix + l0 * pl.st.prefix_len * kDModel : nullptr,
-                                                    pl.st.prefix_len * kDModel, H, Hb, n, s));
+    if (!fused_embed)
+        RUNC(h, MRMT3_PROF_EMBED, s, launch_decode_embed(st_embed, h->emb, h->pe,
+                                                        pl.prefix ? pl.prefix + l0 * pl.st.prefix_len * kDModel : nullptr,
+                                                        pl.st.prefix_len * kDModel, H, Hb, n, s));
     for (int li = 0; li < h->cfg.n_dec_layers; ++li) {
         const LayerW& L = h->dec.layers[li];
         if (narrow)
@@ -708,6 +717,21 @@ static Status enqueue_step(mrmt3_handle* h, const StepPlan& pl, int kind, cudaSt
         return OkStatus();
     }
     // final norm is folded into lm_head_f
+    if (fused_head) {
+        EpiGreedy eg{};
+        eg.st = pl.st;
+        eg.cand = h->greedy_cand.as<float2>() + l0 * (kVocab / 64);
+        eg.tile_ticket = h->greedy_tickets.as<int>() + l0;
+        eg.vocab = kVocab;
+        eg.emb = fused_embed ? h->emb : nullptr;
+        eg.pe = h->pe;
+        eg.H = H;
+        eg.Hb = Hb;
+        RUNC(h, MRMT3_PROF_LM_HEAD, s, (launch_gemm_skinny<64, kDModel, true>(
+                 *h->tma, Hb, kDModel, h->lm_head_f, kDModel, n, kVocab, eps, eg, s, next_trace())));
+        next_trace();  // the arg-max slot stays empty
+        return OkStatus();
+    }
     if (pl.ext_logits) {
         const size_t lane_stride = (size_t)pl.st.max_tokens * kVocab;
         RUNC(h, MRMT3_PROF_LM_HEAD, s, (launch_gemm_skinny<64, kDModel, true>(
@@ -826,6 +850,15 @@ static Status run_decode(mrmt3_handle* h, StepPlan pl, int n_prefix, bool debug_
         return OkStatus();
     };
     for (int i = 0; i < n_prefix; ++i) MRMT3_TRY(step_all(1));
+    if (h->fuse_greedy && !pl.ext_logits && pl.st.prefix_len == 0 && !pl.prefix) {
+        // the fused greedy head writes the input rows of step t + 1; step 0's rows come from here
+        for (int g = 0; g < G; ++g) {
+            const size_t l0 = (size_t)gp[g].lane0;
+            RUNC(h, MRMT3_PROF_EMBED, gs[g], launch_decode_embed(gp[g].st, h->emb, h->pe, nullptr, 0,
+                                                               h->d_h32.as<float>() + l0 * kDModel,
+                                                               h->d_n_bf16.as<bf16>() + l0 * kDModel, gp[g].n_lanes, gs[g]));
+        }
+    }
     int polls = 0;
     bool pending[2] = {false, false};
     bool all_done = false;

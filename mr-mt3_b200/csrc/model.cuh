@@ -134,6 +134,9 @@ struct mrmt3_handle {
     mrmt3::DeviceBuffer kv_pool, block_table, cross_cache;
     // split-key decode attention (attention.cuh): partial softmax states + per-item tickets
     mrmt3::DeviceBuffer attn_parts, attn_tickets;
+    // fused greedy head (gemm_skinny.cuh EpiGreedy): per-lane arg-max candidates of the column tiles
+    mrmt3::DeviceBuffer greedy_cand, greedy_tickets;
+    bool fuse_greedy = true;             // lm_head + arg-max + next-step embedding in one kernel
     int attn_max_parts = 0;
     int attn_part_keys_self = mrmt3::kDefaultPartKeysSelf, attn_part_keys_cross = mrmt3::kDefaultPartKeysCross;
     mrmt3::DeviceBuffer lane_tab;        // per-lane int tables (seg index, prev row, active)
