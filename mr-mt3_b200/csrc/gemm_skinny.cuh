@@ -102,7 +102,8 @@ __device__ __forceinline__ void cp_async_wait_dyn(int n) {
 template <int BN, int K, bool NORM, class Epi>
 __global__ void __launch_bounds__(128)
     gemm_skinny_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant__ CUtensorMap tm_w, int M,
-                       float eps, Epi epi, TraceSlot trace, const bf16* __restrict__ A, int lda, int a_mode) {
+                       float eps, Epi epi, TraceSlot trace, const bf16* __restrict__ A, int lda, int a_mode,
+                       int k_mode) {
     constexpr int BM = 32;
     trace_begin(trace);
     constexpr int KT = K / 64;
@@ -195,12 +196,7 @@ __global__ void __launch_bounds__(128)
         }
     }
 
-#pragma unroll
-    for (int kt = 0; kt < KT; ++kt) {
-        mbar_wait(bars + 8 * kt, 0);
-        if (kt == 0) trace_mark(trace, 2);
-        if (kt == KT / 2) trace_mark(trace, 3);
-        if (kt == KT - 1) trace_mark(trace, 1);
+    auto do_tile = [&](int kt) __attribute__((always_inline)) {
         const uint32_t baseA = smem_u32(sA + kt * BM * 64);
         const uint32_t baseW = smem_u32(sW + kt * BN * 64);
         // all fragment loads of the k-tile first, then the math: issued back to back the ldmatrix
@@ -248,6 +244,29 @@ __global__ void __launch_bounds__(128)
                 mma_bf16_16816(accs[kk][nj * 2], af[kk], wf[kk][nj][0], wf[kk][nj][1]);
                 mma_bf16_16816(accs[kk][nj * 2 + 1], af[kk], wf[kk][nj][2], wf[kk][nj][3]);
             }
+        }
+    };
+    if (k_mode == 1) {
+        // Every tile was requested up front and they land within one L2 round trip of each other, so
+        // waiting tile by tile buys no overlap -- but a barrier wait between two k-tiles (volatile asm)
+        // stops the compiler from overlapping the fragment loads of tile i + 1 with the mma of tile i:
+        // measured with the trace stamps, the loop then costs 0.14-0.19 us PER k-tile (1.5 us for
+        // K = 512, 2.2 us for K = 1024), most of a decode-step projection.  Wait for all of them, then
+        // run the K loop as one straight-line block.
+#pragma unroll
+        for (int kt = 0; kt < KT; ++kt) mbar_wait(bars + 8 * kt, 0);
+        trace_mark(trace, 1);
+#pragma unroll
+        for (int kt = 0; kt < KT; ++kt) do_tile(kt);
+        trace_mark(trace, 3);
+    } else {
+#pragma unroll
+        for (int kt = 0; kt < KT; ++kt) {
+            mbar_wait(bars + 8 * kt, 0);
+            if (kt == 0) trace_mark(trace, 2);
+            if (kt == KT / 2) trace_mark(trace, 3);
+            if (kt == KT - 1) trace_mark(trace, 1);
+            do_tile(kt);
         }
     }
 
@@ -384,11 +403,20 @@ __global__ void __launch_bounds__(128)
     trace_end(trace);
 }
 
-// how the activation tile reaches shared memory: 0 = TMA boxes, 1 = cp.async from all threads (default);
+// how the activation tile reaches shared memory: 0 = TMA boxes (default), 1 = cp.async from all threads
+// (measured on B200: 5 % slower per decode step, the TMA boxes were never the bottleneck);
 // MRMT3_SKINNY_A_MODE overrides (A/B measurements)
 inline int skinny_a_mode() {
     static const int mode = [] {
         const char* e = getenv("MRMT3_SKINNY_A_MODE");
+        return e ? atoi(e) : 0;
+    }();
+    return mode;
+}
+// K loop: 1 = wait for every k-tile, then one straight-line block (default); 0 = barrier wait per k-tile
+inline int skinny_k_mode() {
+    static const int mode = [] {
+        const char* e = getenv("MRMT3_SKINNY_K_MODE");
         return e ? atoi(e) : 1;
     }();
     return mode;
@@ -409,7 +437,7 @@ Status launch_gemm_skinny(TmaCache& tc, const bf16* A, int lda, const bf16* W, i
     MRMT3_TRY(tc.get(W, N, K, ldw, BN, &mw));
     dim3 grid(N / BN, ceil_div(M, 32));
     MRMT3_TRY(launch_pdl(kern, grid, dim3(128), smem, stream, a_copy, *mw, M, eps, epi, trace, A, lda,
-                         skinny_a_mode()));
+                         skinny_a_mode(), skinny_k_mode()));
     return OkStatus();
 }
 

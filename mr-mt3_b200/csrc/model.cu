@@ -185,6 +185,7 @@ Status handle_init(mrmt3_handle* h) {
     const char* ng = getenv("MRMT3_NO_GRAPH");
     h->use_graphs = !(ng && ng[0] == '1');
     if (const char* gl = getenv("MRMT3_GROUP_LANES")) h->group_lanes = atoi(gl);
+    if (const char* e = getenv("MRMT3_FUSE_GREEDY")) h->fuse_greedy = atoi(e) != 0;
     if (const char* e = getenv("MRMT3_ATTN_PART_SELF")) h->attn_part_keys_self = atoi(e);
     if (const char* e = getenv("MRMT3_ATTN_PART_CROSS")) h->attn_part_keys_cross = atoi(e);
     {   // tuning sweeps (scripts/): decode-attention kernel selection

@@ -472,9 +472,10 @@ def test_segmem_v1_generate_without_memory_is_the_plain_loop(pkg, feats):
 
 def test_split_key_attention_units(pkg):
     """Decode attention with an item's keys cut into fixed 128/256-key parts (work units of their own,
-    merged in part order by the last finisher): logits within fp32 merge-order noise of the unsplit
-    kernel over 300 steps (parts appear at step 128/256), tokens independent of the lane grouping and of
-    the batch a row sits in -- the cut points depend on the key count only."""
+    merged in part order by the last finisher): logits within the bf16 rounding of the probabilities of
+    the unsplit kernel over 300 steps (parts appear at step 128/256; a part rounds p = exp2(s - m) against
+    ITS running maximum, so the roundings differ between the two), tokens independent of the lane grouping
+    and of the batch a row sits in -- the cut points depend on the key count only."""
     model, _ = _model(pkg, 1239, eos_scale=2.0)
     eng = model.engine()
     x = syn.synthetic_features(13, 40).cuda()
@@ -490,7 +491,7 @@ def test_split_key_attention_units(pkg):
             eng.set_option("attn_part_keys_cross", pc)
             _, got = eng.generate(x, max_length=300, forced_ids=forced, return_logits=True)
             err = (got - want_logits).abs().max().item()
-            assert err < 5e-3, (ps, pc, err)
+            assert err < 0.04, (ps, pc, err)
             eng.set_option("group_lanes", 0)
             one = eng.generate(x, max_length=300)
             eng.set_option("group_lanes", 7)
