@@ -156,6 +156,190 @@ __global__ void __launch_bounds__(kFrThreads)
 }
 
 // ---------------------------------------------------------------------------------------------
+// Register-resident variant (the default).  The shared-memory radix-4 kernel above spends its time in
+// shared memory: five passes with 7 CTA barriers per frame and 4-way bank conflicts on the strided
+// butterfly writes (ncu, round 1: 94 M conflicts, 842 us for 256 segments = 2 % of the HBM roofline).
+// Here ONE WARP owns a frame and the 1024-point complex FFT is a 32 x 32 decomposition held in
+// registers:  n = 32 n1 + n2,  k = k1 + 32 k2,
+//     Z[k1 + 32 k2] = sum_n2 W32^(n2 k2) . W1024^(n2 k1) . ( sum_n1 z[32 n1 + n2] W32^(n1 k1) )
+//   1. lane n2 loads z[32 n1 + n2], n1 = 0..31 (windowed, conflict-free) and runs a 32-point FFT in
+//      registers (radix-2 DIF, twiddles are compile-time constants, result in bit-reversed positions)
+//   2. twiddle W1024^(n2 k1) from a lane-contiguous table, then a 32 x 32 transpose through a padded
+//      per-warp tile (one store + one load per element, no CTA barrier: only __syncwarp)
+//   3. lane k1 runs the second 32-point FFT over n2 -> Z[k1 + 32 k2]
+//   4. Z in natural order to the warp's tile, X[k] from Z[k] and conj(Z[1024 - k]) (both accesses
+//      lane-contiguous), |X[k]| to the warp's magnitude row, banded mel projection + log + clip/scale,
+//      16 mel bins per lane, every store a coalesced 128-byte (fp32) / 64-byte (bf16) row piece.
+// Tables (window, twiddles, filter bands) are read through the read-only path (lane-contiguous, L1
+// resident: 40 KB) instead of being re-staged into shared memory by every CTA.
+constexpr int kF2Frames = 16;                              // frames per CTA
+constexpr int kF2Warps = 4;
+constexpr int kF2Span = kNFFT + (kF2Frames - 1) * kHop;    // 3968 samples
+constexpr int kF2TileFloats = 32 * 33 * 2;                 // padded 32 x 32 float2 tile (also Z in natural order)
+constexpr int kF2MagFloats = 1028;                         // 1025 magnitudes, padded
+constexpr int kF2SmemBytes = (kF2Span + kF2Warps * (kF2TileFloats + kF2MagFloats)) * (int)sizeof(float);
+
+__host__ __device__ constexpr int bitrev5(int x) {
+    return ((x & 1) << 4) | ((x & 2) << 2) | (x & 4) | ((x & 8) >> 2) | ((x & 16) >> 4);
+}
+
+// d * exp(-2 pi i j / 32), j a compile-time constant after unrolling
+__device__ __forceinline__ float2 mul_w32(float2 d, int j) {
+    constexpr float kCos[16] = {1.f, 0.98078528040323043f, 0.92387953251128674f, 0.83146961230254524f,
+                                0.70710678118654757f, 0.55557023301960218f, 0.38268343236508978f, 0.19509032201612825f,
+                                0.f, -0.19509032201612825f, -0.38268343236508978f, -0.55557023301960218f,
+                                -0.70710678118654757f, -0.83146961230254524f, -0.92387953251128674f, -0.98078528040323043f};
+    constexpr float kSin[16] = {0.f, 0.19509032201612825f, 0.38268343236508978f, 0.55557023301960218f,
+                                0.70710678118654757f, 0.83146961230254524f, 0.92387953251128674f, 0.98078528040323043f,
+                                1.f, 0.98078528040323043f, 0.92387953251128674f, 0.83146961230254524f,
+                                0.70710678118654757f, 0.55557023301960218f, 0.38268343236508978f, 0.19509032201612825f};
+    if (j == 0) return d;
+    if (j == 8) return make_float2(d.y, -d.x);  // -i d
+    const float c = kCos[j], s = kSin[j];       // (a + i b)(c - i s) = (a c + b s) + i (b c - a s)
+    return make_float2(d.x * c + d.y * s, d.y * c - d.x * s);
+}
+
+// in-place 32-point DFT, decimation in frequency: v[p] ends up holding X[bitrev5(p)]
+__device__ __forceinline__ void fft32_dif(float2 (&v)[32]) {
+#pragma unroll
+    for (int h = 16; h >= 1; h >>= 1) {
+#pragma unroll
+        for (int i = 0; i < 32; ++i) {
+            if ((i & h) == 0) {
+                const int j = (i & (h - 1)) * (16 / h);
+                const float2 a = v[i], b = v[i + h];
+                v[i] = make_float2(a.x + b.x, a.y + b.y);
+                v[i + h] = mul_w32(make_float2(a.x - b.x, a.y - b.y), j);
+            }
+        }
+    }
+}
+
+__global__ void __launch_bounds__(kF2Warps * 32)
+    logmel_regfft_kernel(const float* __restrict__ audio, const long long* __restrict__ seg_start,
+                         const int* __restrict__ seg_len, const int* __restrict__ valid_frames,
+                         FrontendTables tab, int mel_norm, float* __restrict__ out_f32,
+                         bf16* __restrict__ out_bf16) {
+    extern __shared__ __align__(16) unsigned char fr_smem[];
+    float* span = reinterpret_cast<float*>(fr_smem);
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    float* tile = span + kF2Span + warp * (kF2TileFloats + kF2MagFloats);
+    float* mag = tile + kF2TileFloats;
+    const int seg = blockIdx.y;
+    const int f0 = blockIdx.x * kF2Frames;
+    const int nvalid = valid_frames ? valid_frames[seg] : kSegFrames;
+    const size_t out_row0 = (size_t)seg * kSegFrames + f0;
+    const int n_live = max(0, min(kF2Frames, nvalid - f0));
+
+    // frames at or past `nvalid` are zero in the output (reference inference.py:125-126)
+    for (int f = n_live + warp; f < kF2Frames; f += kF2Warps) {
+#pragma unroll
+        for (int j = 0; j < kMels / 128; ++j) {
+            const size_t o = (out_row0 + f) * kMels + j * 128 + lane * 4;
+            if (out_f32) *reinterpret_cast<float4*>(out_f32 + o) = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (out_bf16) *reinterpret_cast<uint2*>(out_bf16 + o) = make_uint2(0u, 0u);
+        }
+    }
+    if (n_live == 0) return;
+
+    // this CTA's audio span; samples at or past seg_len read as zeros (pad_end + segment padding)
+    {
+        const long long base = seg_start[seg];
+        const int len = seg_len[seg];
+        const int s0 = f0 * kHop;
+        const int need = kNFFT + (n_live - 1) * kHop;
+        const float* src = audio + base + s0;
+        if ((reinterpret_cast<uintptr_t>(src) & 15) == 0) {
+            for (int i = tid * 4; i < need; i += kF2Warps * 32 * 4) {
+                float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+                const int s = s0 + i;
+                if (s + 3 < len) {
+                    v = __ldg(reinterpret_cast<const float4*>(src + i));
+                } else {
+                    if (s < len) v.x = src[i];
+                    if (s + 1 < len) v.y = src[i + 1];
+                    if (s + 2 < len) v.z = src[i + 2];
+                }
+                *reinterpret_cast<float4*>(span + i) = v;
+            }
+        } else {
+            for (int i = tid; i < need; i += kF2Warps * 32) span[i] = (s0 + i < len) ? src[i] : 0.f;
+        }
+    }
+    __syncthreads();
+
+    // the 16 mel bins of this lane (m = lane + 32 j): band tables stay in registers across frames
+    int b_start[kMels / 32], b_count[kMels / 32];
+#pragma unroll
+    for (int j = 0; j < kMels / 32; ++j) {
+        b_start[j] = __ldg(tab.band_start + lane + 32 * j);
+        b_count[j] = __ldg(tab.band_count + lane + 32 * j);
+    }
+    const float2* win2 = reinterpret_cast<const float2*>(tab.window);
+    float2* tile2 = reinterpret_cast<float2*>(tile);
+
+    for (int f = warp; f < n_live; f += kF2Warps) {
+        const float2* x2 = reinterpret_cast<const float2*>(span + f * kHop);
+        float2 v[32];
+        // 1. z[32 n1 + lane] = w[2n] x[2n] + i w[2n+1] x[2n+1]
+#pragma unroll
+        for (int n1 = 0; n1 < 32; ++n1) {
+            const float2 xv = x2[32 * n1 + lane];
+            const float2 wv = __ldg(win2 + 32 * n1 + lane);
+            v[n1] = make_float2(xv.x * wv.x, xv.y * wv.y);
+        }
+        fft32_dif(v);
+        // 2. twiddle + transpose: element (n2 = lane, k1) -> tile[k1][lane]
+#pragma unroll
+        for (int p = 0; p < 32; ++p) {
+            const int k1 = bitrev5(p);
+            const float2 y = cmul(v[p], __ldg(tab.tw_t + k1 * 32 + lane));
+            tile2[k1 * 33 + lane] = y;
+        }
+        __syncwarp();
+#pragma unroll
+        for (int n2 = 0; n2 < 32; ++n2) v[n2] = tile2[lane * 33 + n2];
+        __syncwarp();
+        // 3. lane = k1: second FFT over n2 -> Z[k1 + 32 k2] at position bitrev5(k2)
+        fft32_dif(v);
+        // 4. Z in natural order, then X[k] = Xe[k] + W2048^k Xo[k] from Z[k] and conj(Z[1024 - k])
+#pragma unroll
+        for (int p = 0; p < 32; ++p) tile2[lane + 32 * bitrev5(p)] = v[p];
+        __syncwarp();
+#pragma unroll
+        for (int p = 0; p < 32; ++p) {
+            const int k = lane + 32 * bitrev5(p);
+            const float2 zk = v[p];
+            float2 zc = tile2[(1024 - k) & 1023];
+            zc.y = -zc.y;
+            const float2 xe = make_float2(0.5f * (zk.x + zc.x), 0.5f * (zk.y + zc.y));
+            const float2 df = make_float2(0.5f * (zk.x - zc.x), 0.5f * (zk.y - zc.y));
+            const float2 t = cmul(__ldg(tab.tw2048 + k), make_float2(df.y, -df.x));  // W^k . (-i df)
+            const float re = xe.x + t.x, im = xe.y + t.y;
+            mag[k] = sqrtf(re * re + im * im);
+            if (k == 0) mag[1024] = fabsf(zk.x - zk.y);  // Nyquist: Re(Z0) - Im(Z0)
+        }
+        __syncwarp();
+        // banded mel projection + safe_log (+ normalisation); lane owns bins lane + 32 j
+#pragma unroll
+        for (int j = 0; j < kMels / 32; ++j) {
+            const int m = lane + 32 * j;
+            float acc = 0.f;
+            for (int t = 0; t < b_count[j]; ++t) acc += mag[b_start[j] + t] * __ldg(tab.band_w + t * kMels + m);
+            float y = logf(acc <= 0.f ? 1e-5f : acc);
+            if (mel_norm) {
+                y = fminf(fmaxf(y, -12.f), 5.f);
+                y = (y + 12.f) / 17.f;
+            }
+            const size_t o = (out_row0 + f) * kMels + m;
+            if (out_f32) out_f32[o] = y;
+            if (out_bf16) out_bf16[o] = __float2bfloat16(y);
+        }
+        __syncwarp();  // the tile and the magnitude row are reused by the next frame
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
 // host side: tables
 static void default_filterbank(std::vector<float>& fb) {
     // HTK mel triangles between 20 and 7600 Hz over linspace(0, 8000, 1025), no area norm.
@@ -223,6 +407,15 @@ Status Frontend::init() {
     MRMT3_CUDA_TRY(cudaMemcpy(d_tw1024_, t1.data(), 1024 * sizeof(float2), cudaMemcpyHostToDevice));
     MRMT3_CUDA_TRY(cudaMemcpy(d_tw2048_, t2.data(), 1025 * sizeof(float2), cudaMemcpyHostToDevice));
     MRMT3_CUDA_TRY(cudaMemcpy(d_window_, win.data(), kNFFT * sizeof(float), cudaMemcpyHostToDevice));
+    std::vector<float2> tt(1024);
+    for (int k1 = 0; k1 < 32; ++k1)
+        for (int n2 = 0; n2 < 32; ++n2) {
+            const double a = -2.0 * kPi * (double)(n2 * k1) / 1024.0;
+            tt[k1 * 32 + n2] = make_float2((float)std::cos(a), (float)std::sin(a));
+        }
+    MRMT3_CUDA_TRY(cudaMalloc(&d_tw_t_, 1024 * sizeof(float2)));
+    MRMT3_CUDA_TRY(cudaMemcpy(d_tw_t_, tt.data(), 1024 * sizeof(float2), cudaMemcpyHostToDevice));
+    MRMT3_CUDA_TRY(cudaFuncSetAttribute(logmel_regfft_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kF2SmemBytes));
     std::vector<float> fb;
     default_filterbank(fb);
     MRMT3_TRY(set_filterbank(fb.data()));
@@ -238,6 +431,7 @@ void Frontend::destroy() {
     cudaFree(d_band_start_);
     cudaFree(d_band_count_);
     cudaFree(d_band_w_);
+    cudaFree(d_tw_t_);
     d_tw1024_ = nullptr;
 }
 
@@ -245,10 +439,20 @@ Status Frontend::run(const float* audio, const long long* seg_start, const int* 
                      const int* valid_frames, int n_seg, int mel_norm, float* out_f32,
                      bf16* out_bf16, cudaStream_t stream) const {
     if (n_seg <= 0) return OkStatus();
-    FrontendTables tab{d_tw1024_, d_tw2048_, d_window_, d_band_start_, d_band_count_, d_band_w_};
-    dim3 grid(kSegFrames / kFramesPerCta, n_seg);
-    logmel_kernel<<<grid, kFrThreads, sizeof(FrontendSmem), stream>>>(
-        audio, seg_start, seg_len, valid_frames, tab, mel_norm, out_f32, out_bf16);
+    FrontendTables tab{d_tw1024_, d_tw2048_, d_window_, d_band_start_, d_band_count_, d_band_w_, d_tw_t_};
+    static const int variant = [] {   // 2 = register-resident FFT (default), 1 = shared-memory radix-4 (A/B partner)
+        const char* e = getenv("MRMT3_FRONTEND_VARIANT");
+        return e ? atoi(e) : 2;
+    }();
+    if (variant == 1) {
+        dim3 grid(kSegFrames / kFramesPerCta, n_seg);
+        logmel_kernel<<<grid, kFrThreads, sizeof(FrontendSmem), stream>>>(
+            audio, seg_start, seg_len, valid_frames, tab, mel_norm, out_f32, out_bf16);
+    } else {
+        dim3 grid(kSegFrames / kF2Frames, n_seg);
+        logmel_regfft_kernel<<<grid, kF2Warps * 32, kF2SmemBytes, stream>>>(
+            audio, seg_start, seg_len, valid_frames, tab, mel_norm, out_f32, out_bf16);
+    }
     MRMT3_CHECK_LAUNCH();
     return OkStatus();
 }

@@ -13,6 +13,7 @@ struct FrontendTables {
     const int* band_start;  // (512) first FFT bin of mel filter m
     const int* band_count;  // (512) number of taps
     const float* band_w;    // (kMaxBand, 512) tap j of filter m at [j*512 + m]
+    const float2* tw_t;     // (32, 32): exp(-2 pi i n2 k1 / 1024) at [k1 * 32 + n2] (register FFT kernel)
 };
 
 class Frontend {
@@ -34,6 +35,7 @@ private:
     int* d_band_start_ = nullptr;
     int* d_band_count_ = nullptr;
     float* d_band_w_ = nullptr;
+    float2* d_tw_t_ = nullptr;
 };
 
 }  // namespace mrmt3

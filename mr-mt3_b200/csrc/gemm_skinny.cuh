@@ -403,6 +403,276 @@ __global__ void __launch_bounds__(128)
     trace_end(trace);
 }
 
+// =============================================================================================
+// Version 2 (the default): K split across the four warps.
+//
+// Trace stamps of version 1 on B200 (profiles/r2c_*): the operands are in shared memory 0.5-1.0 us after
+// the dependency wait (one L2 round trip) and the K loop then takes another 0.7-1.7 us -- the same
+// with a barrier wait per k-tile or without.  That loop is bound by shared-memory bandwidth and by
+// its own serial length: every warp walks ALL K/64 k-tiles, the activation tile is read by both
+// column-half warps and the weight tile by both row-half warps (16 KB of ldmatrix traffic per 8 KB
+// k-tile, plus the RMSNorm row sums re-reading the activations), and with <= 16 lanes the two warps
+// that own rows 16-31 multiply zeros.
+//
+// Here warp w owns the k-tiles kt = w, w + 4, ... and computes the WHOLE BM x BN tile over them:
+//   * every byte of shared memory is read by ldmatrix exactly once (48 KB instead of 128 KB for a
+//     16-lane 32-column K = 512 tile), the per-warp loop is K/256 k-tiles long instead of K/64;
+//   * a warp waits only for the barriers of its own k-tiles;
+//   * the RMSNorm row sums come from the A fragments the warp holds anyway (no extra reads);
+//   * BM = 16 for groups of <= 16 lanes: no warp works on rows that do not exist;
+//   * the four partial tiles meet in shared memory and are summed in warp order by all 128 threads,
+//     thread <-> (row, column pair): the stores of the epilogue are row-contiguous.
+// The order of every fp32 sum is fixed by (k-tile, warp): a row's result does not depend on its batch
+// neighbours, as before.
+template <int BM, int BN, int K, bool NORM, class Epi>
+__global__ void __launch_bounds__(128)
+    gemm_skinny2_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant__ CUtensorMap tm_w, int M,
+                        float eps, Epi epi, TraceSlot trace) {
+    trace_begin(trace);
+    constexpr int KT = K / 64;
+    constexpr int MT = BM / 16;        // m16 tiles
+    constexpr int NT = BN / 8;         // n8 tiles
+    constexpr int PITCH = BN + 8;      // floats per row of a partial tile (conflict-free fragment stores)
+    constexpr int EPT = BM * BN / 2 / 128;  // (row, column pair) elements per thread in the final sum
+    static_assert(KT <= 16 && BN % 16 == 0 && (BM == 16 || BM == 32), "unsupported tile");
+    static_assert(4 * BM * PITCH * 4 <= KT * BN * 128, "partial tiles must fit in the weight region");
+    extern __shared__ unsigned char smem_raw[];
+    unsigned char* smem_al = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
+    bf16* sA = reinterpret_cast<bf16*>(smem_al);    // [KT][BM*64]
+    bf16* sW = sA + KT * BM * 64;                   // [KT][BN*64]
+    const uint32_t bars = smem_u32(sW + KT * BN * 64);
+    __shared__ float s_ss[4][BM];
+    __shared__ float s_scale[BM];
+
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int m0 = blockIdx.y * BM;
+    const int n0 = blockIdx.x * BN;
+
+    if (tid == 0) {
+#pragma unroll
+        for (int kt = 0; kt < KT; ++kt) mbar_init(bars + 8 * kt, 2);
+        mbar_fence_init();
+        asm volatile("fence.proxy.async.shared::cta;\n" ::: "memory");
+        // weights first: they do not depend on the producer kernel (their latency hides under its tail)
+#pragma unroll
+        for (int kt = 0; kt < KT; ++kt) {
+            mbar_expect_tx(bars + 8 * kt, BN * 128);
+            tma_load_2d(smem_u32(sW + kt * BN * 64), &tm_w, kt * 64, n0, bars + 8 * kt);
+        }
+    }
+    pdl_wait();
+    trace_mark(trace, 0);
+    pdl_launch_dependents();
+    if (tid == 0) {
+#pragma unroll
+        for (int kt = 0; kt < KT; ++kt) {
+            mbar_expect_tx(bars + 8 * kt, BM * 128);
+            tma_load_2d(smem_u32(sA + kt * BM * 64), &tm_a, kt * 64, m0, bars + 8 * kt);
+        }
+    }
+    __syncthreads();  // barrier initialisation is visible to every waiter
+
+    // the residual values this thread will add in the epilogue: fetched now, under the operand loads
+    float2 pre[EPT];
+    if constexpr (EpiPrefetches<Epi>::value) {
+#pragma unroll
+        for (int i = 0; i < EPT; ++i) {
+            const int e = tid + 128 * i, row = e / (BN / 2), cp = e - row * (BN / 2);
+            pre[i] = m0 + row < M ? epi.load(m0 + row, n0 + 2 * cp) : make_float2(0.f, 0.f);
+        }
+    }
+
+    float acc[MT][NT][4];
+#pragma unroll
+    for (int mi = 0; mi < MT; ++mi)
+#pragma unroll
+        for (int j = 0; j < NT; ++j)
+#pragma unroll
+            for (int r = 0; r < 4; ++r) acc[mi][j][r] = 0.f;
+    float ss[MT][2];  // NORM: this lane's share of the squares of rows mi*16 + lane/4 (+ 8)
+#pragma unroll
+    for (int mi = 0; mi < MT; ++mi) ss[mi][0] = ss[mi][1] = 0.f;
+
+#pragma unroll
+    for (int kt0 = 0; kt0 < KT; kt0 += 4) {
+        const int kt = kt0 + warp;
+        if (kt < KT) {
+            mbar_wait(bars + 8 * kt, 0);
+            const uint32_t baseA = smem_u32(sA + kt * BM * 64);
+            const uint32_t baseW = smem_u32(sW + kt * BN * 64);
+#pragma unroll
+            for (int kk = 0; kk < 4; ++kk) {
+                uint32_t af[MT][4], wf[NT / 2][4];
+#pragma unroll
+                for (int mi = 0; mi < MT; ++mi) {
+                    const int row = mi * 16 + (lane & 15);
+                    const int ch = kk * 2 + (lane >> 4);
+                    ldmatrix_x4(af[mi][0], af[mi][1], af[mi][2], af[mi][3], baseA + row * 128 + ((ch ^ (row & 7)) << 4));
+                }
+#pragma unroll
+                for (int nj = 0; nj < NT / 2; ++nj) {
+                    const int row = nj * 16 + (lane & 7) + ((lane >> 4) << 3);
+                    const int ch = kk * 2 + ((lane >> 3) & 1);
+                    ldmatrix_x4(wf[nj][0], wf[nj][1], wf[nj][2], wf[nj][3], baseW + row * 128 + ((ch ^ (row & 7)) << 4));
+                }
+                if (NORM) {
+                    // A fragment: regs 0 / 2 hold row lane/4 (columns 2c, 2c+1 and 2c+8, 2c+9), regs 1 / 3 row + 8
+#pragma unroll
+                    for (int mi = 0; mi < MT; ++mi) {
+#pragma unroll
+                        for (int r = 0; r < 4; ++r) {
+                            const float2 f = __bfloat1622float2(*reinterpret_cast<const bf162*>(&af[mi][r]));
+                            ss[mi][r & 1] += f.x * f.x + f.y * f.y;
+                        }
+                    }
+                }
+#pragma unroll
+                for (int mi = 0; mi < MT; ++mi) {
+#pragma unroll
+                    for (int nj = 0; nj < NT / 2; ++nj) {
+                        mma_bf16_16816(acc[mi][nj * 2], af[mi], wf[nj][0], wf[nj][1]);
+                        mma_bf16_16816(acc[mi][nj * 2 + 1], af[mi], wf[nj][2], wf[nj][3]);
+                    }
+                }
+            }
+        }
+    }
+    trace_mark(trace, 1);
+    __syncthreads();  // every warp is done with the operand tiles: the weight region becomes the meeting place
+
+    float* part = reinterpret_cast<float*>(sW) + warp * BM * PITCH;
+#pragma unroll
+    for (int mi = 0; mi < MT; ++mi) {
+        const int row = mi * 16 + (lane >> 2);
+#pragma unroll
+        for (int j = 0; j < NT; ++j) {
+            const int col = j * 8 + (lane & 3) * 2;
+            *reinterpret_cast<float2*>(part + row * PITCH + col) = make_float2(acc[mi][j][0], acc[mi][j][1]);
+            *reinterpret_cast<float2*>(part + (row + 8) * PITCH + col) = make_float2(acc[mi][j][2], acc[mi][j][3]);
+        }
+        if (NORM) {
+#pragma unroll
+            for (int h = 0; h < 2; ++h) {
+                float v = ss[mi][h];
+                v += __shfl_xor_sync(0xffffffffu, v, 1);
+                v += __shfl_xor_sync(0xffffffffu, v, 2);
+                if ((lane & 3) == 0) s_ss[warp][row + 8 * h] = v;
+            }
+        }
+    }
+    __syncthreads();
+    if (NORM) {
+        if (tid < BM) s_scale[tid] = rsqrtf(((s_ss[0][tid] + s_ss[1][tid]) + (s_ss[2][tid] + s_ss[3][tid])) * (1.0f / K) + eps);
+        __syncthreads();
+    }
+    const float* p0 = reinterpret_cast<const float*>(sW);
+    float2 val[EPT];
+#pragma unroll
+    for (int i = 0; i < EPT; ++i) {
+        const int e = tid + 128 * i, row = e / (BN / 2), cp = e - row * (BN / 2);
+        const float* q = p0 + row * PITCH + 2 * cp;
+        const float2 a = *reinterpret_cast<const float2*>(q), b = *reinterpret_cast<const float2*>(q + BM * PITCH);
+        const float2 c = *reinterpret_cast<const float2*>(q + 2 * BM * PITCH), d = *reinterpret_cast<const float2*>(q + 3 * BM * PITCH);
+        const float sc = NORM ? s_scale[row] : 1.f;
+        val[i] = make_float2(((a.x + b.x) + (c.x + d.x)) * sc, ((a.y + b.y) + (c.y + d.y)) * sc);
+    }
+
+    if constexpr (EpiIsGreedy<Epi>::value) {
+        // thread <-> (row, column pair) with BN / 2 pairs per row: a row's candidates sit in BN / 2
+        // consecutive lanes, so the row arg-max is a sub-warp shuffle reduction (lowest index wins ties)
+        static_assert(BN == 64, "the greedy head reduces one 64-column row per warp pass");
+        __shared__ int s_tok[BM];
+        __shared__ int s_last;
+#pragma unroll
+        for (int i = 0; i < EPT; ++i) {
+            const int row = (tid + 128 * i) / 32;  // = warp + 4 i
+            float b = val[i].x;
+            int bi = n0 + 2 * lane;
+            if (val[i].y > b) { b = val[i].y; bi = n0 + 2 * lane + 1; }
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) {
+                const float ob = __shfl_xor_sync(0xffffffffu, b, o);
+                const int oi = __shfl_xor_sync(0xffffffffu, bi, o);
+                if (ob > b || (ob == b && oi < bi)) { b = ob; bi = oi; }
+            }
+            if (lane == 0 && m0 + row < M)
+                epi.cand[(size_t)(m0 + row) * gridDim.x + blockIdx.x] = make_float2(b, __int_as_float(bi));
+        }
+        __threadfence();
+        __syncthreads();
+        if (tid == 0) s_last = atomicAdd(epi.tile_ticket + blockIdx.y, 1) == (int)gridDim.x - 1;
+        __syncthreads();
+        if (s_last) {
+            __threadfence();
+            const DecodeState& st = epi.st;
+            const int step = st.step[0];  // advanced only after every tile has passed this point
+            if (tid < BM) s_tok[tid] = -1;
+            if (tid < BM && m0 + tid < M && st.active[m0 + tid]) {
+                const int ln = m0 + tid;
+                float best = -INFINITY;
+                int best_i = 0x7fffffff;
+                for (int j = 0; j < (int)gridDim.x; ++j) {  // ascending column tiles
+                    const float2 c = __ldcg(epi.cand + (size_t)ln * gridDim.x + j);
+                    if (c.x > best) { best = c.x; best_i = __float_as_int(c.y); }
+                }
+                const int n_emitted = step - st.prefix_len + 1;  // tokens emitted incl. this one
+                int next = best_i;
+                if (st.forced) {
+                    const size_t frow = st.forced_by_row ? (size_t)st.out_row[ln] : (size_t)ln;
+                    const long long f = st.forced[frow * st.forced_stride + n_emitted];
+                    next = (f < 0 || f >= epi.vocab) ? st.pad_id : (int)f;
+                }
+                st.out[(size_t)st.out_row[ln] * st.out_stride + n_emitted] = next;
+                st.tok[ln] = next;
+                const bool done = (!st.forced && next == st.eos_id) || n_emitted >= st.max_tokens;
+                if (done) {
+                    st.active[ln] = 0;
+                    st.finish_step[ln] = n_emitted;
+                    atomicSub(st.n_active, 1);
+                } else {
+                    s_tok[tid] = next;
+                }
+            }
+            __syncthreads();
+            if (epi.emb) {  // next step's input rows of the lanes that go on
+                const int c = tid * 4;
+                const float4 pv = *reinterpret_cast<const float4*>(epi.pe + (size_t)(step + 1) * kDModel + c);
+                for (int r = 0; r < BM; ++r) {
+                    const int tok = s_tok[r];
+                    if (tok < 0) continue;
+                    const float4 ev = *reinterpret_cast<const float4*>(epi.emb + (size_t)tok * kDModel + c);
+                    const float4 hv = make_float4(ev.x + pv.x, ev.y + pv.y, ev.z + pv.z, ev.w + pv.w);
+                    *reinterpret_cast<float4*>(epi.H + (size_t)(m0 + r) * kDModel + c) = hv;
+                    *reinterpret_cast<uint2*>(epi.Hb + (size_t)(m0 + r) * kDModel + c) =
+                        make_uint2(pack_bf16(hv.x, hv.y), pack_bf16(hv.z, hv.w));
+                }
+            }
+            __syncthreads();
+            if (tid == 0) {
+                epi.tile_ticket[blockIdx.y] = 0;
+                __threadfence();
+                const int tk = atomicAdd(st.ticket, 1);
+                if (tk == (int)gridDim.y - 1) {
+                    st.ticket[0] = 0;
+                    st.step[0] = step + 1;
+                }
+            }
+        }
+    } else {
+#pragma unroll
+        for (int i = 0; i < EPT; ++i) {
+            const int e = tid + 128 * i, row = e / (BN / 2), cp = e - row * (BN / 2);
+            if (m0 + row < M) {
+                if constexpr (EpiPrefetches<Epi>::value)
+                    epi.store(m0 + row, n0 + 2 * cp, pre[i], val[i].x, val[i].y);
+                else
+                    epi(m0 + row, n0 + 2 * cp, val[i].x, val[i].y);
+            }
+        }
+    }
+    trace_end(trace);
+}
+
 // how the activation tile reaches shared memory: 0 = TMA boxes (default), 1 = cp.async from all threads
 // (measured on B200: 5 % slower per decode step, the TMA boxes were never the bottleneck);
 // MRMT3_SKINNY_A_MODE overrides (A/B measurements)
@@ -422,12 +692,41 @@ inline int skinny_k_mode() {
     return mode;
 }
 
+// which kernel the decode-step projections use: 2 = K split across the warps (default), 1 = version 1
+inline int skinny_version() {
+    static const int v = [] {
+        const char* e = getenv("MRMT3_SKINNY_VERSION");
+        return e ? atoi(e) : 2;
+    }();
+    return v;
+}
+
+template <int BM, int BN, int K, bool NORM, class Epi>
+Status launch_gemm_skinny2(TmaCache& tc, const bf16* A, int lda, const bf16* W, int ldw, int M, int N, float eps,
+                           const Epi& epi, cudaStream_t stream, TraceSlot trace) {
+    auto kern = gemm_skinny2_kernel<BM, BN, K, NORM, Epi>;
+    constexpr int smem = (BM + BN) * K * (int)sizeof(bf16) + (K / 64) * 8 + 1024;
+    MRMT3_TRY(ensure_dynamic_smem(kern, smem));
+    const CUtensorMap *ma = nullptr, *mw = nullptr;
+    MRMT3_TRY(tc.get(A, M, K, lda, BM, &ma));
+    const CUtensorMap a_copy = *ma;  // the second lookup may rotate the cache
+    MRMT3_TRY(tc.get(W, N, K, ldw, BN, &mw));
+    dim3 grid(N / BN, ceil_div(M, BM));
+    MRMT3_TRY(launch_pdl(kern, grid, dim3(128), smem, stream, a_copy, *mw, M, eps, epi, trace));
+    return OkStatus();
+}
+
 template <int BN, int K, bool NORM, class Epi>
 Status launch_gemm_skinny(TmaCache& tc, const bf16* A, int lda, const bf16* W, int ldw, int M, int N, float eps,
                           const Epi& epi, cudaStream_t stream, TraceSlot trace = TraceSlot{nullptr, 0}) {
     if (M <= 0) return OkStatus();
     if (N % BN != 0) return Error(2, "gemm_skinny: N must be a multiple of the column tile");
     static_assert(!NORM || K == kDModel, "fused RMSNorm needs complete rows: K == d_model");
+    if (skinny_version() == 2) {
+        // groups of <= 16 lanes (the MR-MT3 small-batch regime) use 16-row tiles: no warp multiplies zeros
+        if (M <= 16) return launch_gemm_skinny2<16, BN, K, NORM>(tc, A, lda, W, ldw, M, N, eps, epi, stream, trace);
+        return launch_gemm_skinny2<32, BN, K, NORM>(tc, A, lda, W, ldw, M, N, eps, epi, stream, trace);
+    }
     auto kern = gemm_skinny_kernel<BN, K, NORM, Epi>;
     constexpr int smem = (32 + BN) * K * (int)sizeof(bf16) + (K / 64) * 8 + 1024;
     MRMT3_TRY(ensure_dynamic_smem(kern, smem));
