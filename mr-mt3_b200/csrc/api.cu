@@ -156,8 +156,8 @@ int mrmt3_set_option(mrmt3_handle* h, const char* key, int value) {
             attn_decode_configure(-1, 0, -1, value);
         }
         else if (k == "attn_ring_stages") {
-            if (value != 2 && value != 3 && value != 4 && value != 6)
-                return finish(h, Error(2, "attn_ring_stages must be 2, 3, 4 or 6"));
+            if (value != 2 && value != 3 && value != 4 && value != 6 && value != 8)
+                return finish(h, Error(2, "attn_ring_stages must be 2, 3, 4, 6 or 8"));
             attn_decode_configure(-1, value, -1, 0);
         } else {
             if (value < 0 || value > 8) return finish(h, Error(2, "attn_ring_ctas must be in 0..8 (0 = automatic)"));

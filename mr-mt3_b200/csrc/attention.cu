@@ -732,6 +732,7 @@ __global__ void __launch_bounds__((4 * Q + 1) * 32)
         }
 
         // merge the eight warps' partial states in fixed order
+        if (warp == 0 && unit == (int)blockIdx.x) trace_mark(p.trace, 2);  // CTA 0: first unit's chunks consumed
         l_run += __shfl_xor_sync(0xffffffffu, l_run, 1);
         l_run += __shfl_xor_sync(0xffffffffu, l_run, 2);
         float* wpart = merge + (buf * kMmaWarps + warp) * kMmaPartFloats;
@@ -798,6 +799,7 @@ __global__ void __launch_bounds__((4 * Q + 1) * 32)
                     pack_bf16(o0 * inv, o1 * inv);
             }
         }
+        if (warp == 0 && unit == (int)blockIdx.x) trace_mark(p.trace, 3);  // ... and merged / written
         buf ^= 1;  // the other half is free again once every warp has passed the next item's barrier
     }
     trace_end(p.trace);
@@ -858,10 +860,11 @@ Status launch_attn_decode(const AttnDecodeParams& p, int n_lanes, bool paged, cu
             case 31: MRMT3_RING(3, 1);
             case 41: MRMT3_RING(4, 1);
             case 61: MRMT3_RING(6, 1);
+            case 81: MRMT3_RING(8, 1);
             case 22: MRMT3_RING(2, 2);
             case 32: MRMT3_RING(3, 2);
             case 42: MRMT3_RING(4, 2);
-            default: return Error(2, "attn ring: stages per quartet must be 2, 3, 4 (or 6 with one quartet)");
+            default: return Error(2, "attn ring: stages per quartet must be 2, 3, 4 (or 6 / 8 with one quartet)");
         }
 #undef MRMT3_RING
     }

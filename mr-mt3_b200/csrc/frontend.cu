@@ -269,11 +269,17 @@ __global__ void __launch_bounds__(kF2Warps * 32)
     __syncthreads();
 
     // the 16 mel bins of this lane (m = lane + 32 j): band tables stay in registers across frames
-    int b_start[kMels / 32], b_count[kMels / 32];
+    // b_cmax[j]: the widest band among the 32 bins of group j (warp-uniform): the tap loop runs to it in
+    // unrolled blocks of four -- taps past a bin's own count carry zero weight in the padded table --
+    // so that four independent load pairs are in flight instead of one dependent pair per iteration
+    int b_start[kMels / 32], b_cmax[kMels / 32];
 #pragma unroll
     for (int j = 0; j < kMels / 32; ++j) {
         b_start[j] = __ldg(tab.band_start + lane + 32 * j);
-        b_count[j] = __ldg(tab.band_count + lane + 32 * j);
+        int c = __ldg(tab.band_count + lane + 32 * j);
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) c = max(c, __shfl_xor_sync(0xffffffffu, c, o));
+        b_cmax[j] = c;
     }
     const float2* win2 = reinterpret_cast<const float2*>(tab.window);
     float2* tile2 = reinterpret_cast<float2*>(tile);
@@ -325,7 +331,16 @@ __global__ void __launch_bounds__(kF2Warps * 32)
         for (int j = 0; j < kMels / 32; ++j) {
             const int m = lane + 32 * j;
             float acc = 0.f;
-            for (int t = 0; t < b_count[j]; ++t) acc += mag[b_start[j] + t] * __ldg(tab.band_w + t * kMels + m);
+            for (int t0 = 0; t0 < b_cmax[j]; t0 += 4) {   // kMaxBand is a multiple of 4: t0 + 3 stays inside the table
+                float mv[4], wv[4];
+#pragma unroll
+                for (int u = 0; u < 4; ++u) {
+                    mv[u] = mag[min(b_start[j] + t0 + u, 1024)];  // clamped: a finite value under a zero weight
+                    wv[u] = __ldg(tab.band_w + (t0 + u) * kMels + m);
+                }
+#pragma unroll
+                for (int u = 0; u < 4; ++u) acc += mv[u] * wv[u];  // taps in ascending order, as the reference's matmul row
+            }
             float y = logf(acc <= 0.f ? 1e-5f : acc);
             if (mel_norm) {
                 y = fminf(fmaxf(y, -12.f), 5.f);

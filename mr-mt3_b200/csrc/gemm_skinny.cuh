@@ -635,16 +635,37 @@ __global__ void __launch_bounds__(128)
             }
             __syncthreads();
             if (epi.emb) {  // next step's input rows of the lanes that go on
-                const int c = tid * 4;
-                const float4 pv = *reinterpret_cast<const float4*>(epi.pe + (size_t)(step + 1) * kDModel + c);
-                for (int r = 0; r < BM; ++r) {
-                    const int tok = s_tok[r];
-                    if (tok < 0) continue;
-                    const float4 ev = *reinterpret_cast<const float4*>(epi.emb + (size_t)tok * kDModel + c);
-                    const float4 hv = make_float4(ev.x + pv.x, ev.y + pv.y, ev.z + pv.z, ev.w + pv.w);
-                    *reinterpret_cast<float4*>(epi.H + (size_t)(m0 + r) * kDModel + c) = hv;
-                    *reinterpret_cast<uint2*>(epi.Hb + (size_t)(m0 + r) * kDModel + c) =
-                        make_uint2(pack_bf16(hv.x, hv.y), pack_bf16(hv.z, hv.w));
+                // warp w takes rows w, w + 4, ...; all loads of a row batch are issued before the first use
+                // (one L2 round trip per batch of four rows instead of one per row)
+                const float* pe_row = epi.pe + (size_t)(step + 1) * kDModel;
+#pragma unroll
+                for (int rb = 0; rb < BM / 4; rb += 4) {
+                    float4 ev[4][4];
+                    int toks[4];
+#pragma unroll
+                    for (int u = 0; u < 4; ++u) {
+                        const int r = warp + 4 * (rb + u);
+                        toks[u] = (rb + u < BM / 4) ? s_tok[r] : -1;
+                        if (toks[u] >= 0) {
+#pragma unroll
+                            for (int q = 0; q < 4; ++q)
+                                ev[u][q] = *reinterpret_cast<const float4*>(epi.emb + (size_t)toks[u] * kDModel + (lane + 32 * q) * 4);
+                        }
+                    }
+#pragma unroll
+                    for (int u = 0; u < 4; ++u) {
+                        if (toks[u] < 0) continue;
+                        const int r = warp + 4 * (rb + u);
+#pragma unroll
+                        for (int q = 0; q < 4; ++q) {
+                            const int c = (lane + 32 * q) * 4;
+                            const float4 pv = *reinterpret_cast<const float4*>(pe_row + c);
+                            const float4 hv = make_float4(ev[u][q].x + pv.x, ev[u][q].y + pv.y, ev[u][q].z + pv.z, ev[u][q].w + pv.w);
+                            *reinterpret_cast<float4*>(epi.H + (size_t)(m0 + r) * kDModel + c) = hv;
+                            *reinterpret_cast<uint2*>(epi.Hb + (size_t)(m0 + r) * kDModel + c) =
+                                make_uint2(pack_bf16(hv.x, hv.y), pack_bf16(hv.z, hv.w));
+                        }
+                    }
                 }
             }
             __syncthreads();

@@ -32,6 +32,9 @@ for i, nm in enumerate(names):
         d["gap_after_prev_end_us"] = (b - prev_end) / 1e3
         if w: d["wait_return_after_prev_end_us"] = (w - prev_end) / 1e3
         if w and ld: d["loaded_after_wait_us"] = (ld - w) / 1e3; d["end_after_loaded_us"] = (e - ld) / 1e3
+        k0, kh = tr[i + 256]
+        if w and k0: d["mark2_after_wait_us"] = (k0 - w) / 1e3
+        if w and kh: d["mark3_after_wait_us"] = (kh - w) / 1e3
         c = cls.setdefault(k, {"n": 0, "span_us": 0.0})
         c["n"] += 1; c["span_us"] += (e - prev_end) / 1e3      # contribution to the critical path
     prev_end = e

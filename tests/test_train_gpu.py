@@ -325,7 +325,8 @@ def test_full_length_step_matches_fp64_autograd_golden():
     attention backward) against tests/golden/train_big.npz = fp64 autograd through the oracle
     (oracle/make_golden_train_big.py).  Per gradient tensor: norm, the relative Frobenius error
     ESTIMATED from 16 fixed +-1 projections (E[(p_k(g) - p_k(g'))^2] = |g - g'|^2; the estimate has
-    a ~18 % standard deviation, so the bound is GRAD_REL_TOL * 1.5), and the cosine on the stored slice."""
+    a ~18 % standard deviation, so the bound is GRAD_REL_TOL * 1.5), and the error of the stored 256-element
+    slice relative to its expected share of the tensor norm."""
     from helpers import golden
     g = golden("train_big.npz")
     B, L, Lp = int(g["B"]), int(g["L"]), int(g["Lp"])
@@ -360,16 +361,18 @@ def test_full_length_step_matches_fp64_autograd_golden():
         norm_ratio = float(np.linalg.norm(got)) / max(ref_n, 1e-30)
         head = g["grad_heads"][i][:got.size]
         gh = got[:head.size]
-        cos = float(gh @ head / max(np.linalg.norm(gh) * np.linalg.norm(head), 1e-300))
-        worst.append((rel_est, norm_ratio, cos, name))
+        # error of the stored slice against the slice's EXPECTED share of the tensor norm (a slice of small
+        # entries would make a plain cosine meaningless)
+        slice_rel = float(np.linalg.norm(gh - head)) / max(ref_n * np.sqrt(head.size / got.size), 1e-300)
+        worst.append((rel_est, norm_ratio, slice_rel, name))
     worst.sort(reverse=True)
-    print("worst gradient tensors (estimated rel err, norm ratio, slice cosine):")
+    print("worst gradient tensors (estimated rel err, norm ratio, slice rel err):")
     for w in worst[:16]:
         print("   %.4f %.4f %.5f %s" % w)
-    for rel_est, norm_ratio, cos, name in worst:
+    for rel_est, norm_ratio, slice_rel, name in worst:
         assert rel_est < GRAD_REL_TOL * 1.5, (name, rel_est)
         assert abs(norm_ratio - 1.0) < 0.05, (name, norm_ratio)
-        assert cos > 0.98, (name, cos)      # 256-element slice of a tensor with ~5 % relative error: a coarse check
+        assert slice_rel < 0.25, (name, slice_rel)
 
 
 def test_weights_reloaded_after_train_init_reach_the_masters():
