@@ -531,7 +531,7 @@ __device__ __forceinline__ MmaItem mma_item(const AttnDecodeParams& p, int lane_
 }
 
 template <bool PAGED, int S, int Q>
-__global__ void __launch_bounds__((4 * Q + 1) * 32)
+__global__ void __launch_bounds__((4 * Q + 1) * 32, Q == 1 ? 3 : 1)   // three 160-thread CTAs per SM: <= 136 registers
     attn_decode_mma_kernel(const __grid_constant__ CUtensorMap tmap, AttnDecodeParams p, int n_lanes) {
     extern __shared__ unsigned char mma_smem_raw[];
     const uint32_t raw = smem_u32(mma_smem_raw);
@@ -642,13 +642,26 @@ __global__ void __launch_bounds__((4 * Q + 1) * 32)
 
         const int qt = warp >> 2;          // this warp's quartet: chunks with (c % 2) == qt
         const int kb = (warp & 3) * 16;    // its 16 keys inside every such chunk
-        for (int c = c_begin + qt; c < c_end; c += kMmaQuartets, ++cnt) {
-            const int s = qt * S + cnt % S;
-            mbar_wait(full0 + 8 * s, (cnt / S) & 1);
+        // Two-stage software pipeline over this warp's chunks: the score mma of chunk c + 1 are issued
+        // BEFORE the softmax and the p V mma of chunk c.  The warp-level mma has a long latency on this part
+        // (scripts/microbench/hmma_latency.cu) and a chunk is a chain of three of them (q K^T in two
+        // dependent steps, then p V) around two shuffles and the exponentials: issued strictly chunk
+        // after chunk, a 16-key block costs ~0.45 us per warp whatever the memory system does (trace
+        // stamps, profiles/r2e_*).  Arithmetic and its order per chunk are unchanged: results are bit-identical.
+        struct ChunkRegs {
+            uint32_t vf[4][4];
+            float sc[2][4], sd[2][4];
+            int s, n_valid;
+            bool live;
+        };
+        auto fetch = [&](int c, int cnt_c, ChunkRegs& R) {
+            R.s = qt * S + cnt_c % S;
+            mbar_wait(full0 + 8 * R.s, (cnt_c / S) & 1);
             const int k0 = c * kMmaChunk;
-            const int n_valid = min(kMmaChunk, it.n_keys - k0);
-            if (kb < n_valid) {
-                const uint32_t bk = base + s * kMmaStageBytes;
+            R.n_valid = min(kMmaChunk, it.n_keys - k0);
+            R.live = kb < R.n_valid;
+            if (R.live) {
+                const uint32_t bk = base + R.s * kMmaStageBytes;
                 const uint32_t bv = bk + kMmaTileBytes;
                 if (PAGED && pos >= k0 + kb && pos < k0 + kb + 16) {
                     // the step's K and V sit in the fused QKV row right after Q: patch them into
@@ -657,7 +670,7 @@ __global__ void __launch_bounds__((4 * Q + 1) * 32)
                     if (lane < 16) {
                         const int kv = lane >> 3, ch = lane & 7;
                         const uint4 val = *reinterpret_cast<const uint4*>(qrow + kInner * (1 + kv) + ch * 8);
-                        unsigned char* tile = base_ptr + s * kMmaStageBytes + kv * kMmaTileBytes;
+                        unsigned char* tile = base_ptr + R.s * kMmaStageBytes + kv * kMmaTileBytes;
                         *reinterpret_cast<uint4*>(tile + r * 128 + ((ch ^ (r & 7)) << 4)) = val;
                         const size_t off = ((size_t)it.pages[pos / kKVPage] * rows_per_page +
                                             (size_t)(kv ? it.v_row : it.k_row) + (pos % kKVPage)) * kDKV + ch * 8;
@@ -665,9 +678,7 @@ __global__ void __launch_bounds__((4 * Q + 1) * 32)
                     }
                     __syncwarp();
                 }
-                // all eight fragment loads of this warp's 16 keys up front: the V loads do not
-                // depend on the softmax and overlap the score mma chain
-                uint32_t kf[4][4], vf[4][4];
+                uint32_t kf[4][4];
 #pragma unroll
                 for (int kk = 0; kk < 4; ++kk) {
                     int row = kb + (lane & 7) + ((lane >> 4) << 3);
@@ -678,40 +689,43 @@ __global__ void __launch_bounds__((4 * Q + 1) * 32)
                 for (int nj = 0; nj < 4; ++nj) {
                     int row = kb + (lane & 7) + (((lane >> 3) & 1) << 3);
                     int ch = nj * 2 + (lane >> 4);
-                    ldmatrix_x4_trans(vf[nj][0], vf[nj][1], vf[nj][2], vf[nj][3],
+                    ldmatrix_x4_trans(R.vf[nj][0], R.vf[nj][1], R.vf[nj][2], R.vf[nj][3],
                                       bv + row * 128 + ((ch ^ (row & 7)) << 4));
                 }
                 // s = q K^T for this warp's 16 keys (row 0 of two 16 x 8 blocks); two independent
                 // accumulator pairs (dims 0-15|32-47 and 16-31|48-63) halve the dependent mma chain
-                float sc[2][4], sd[2][4];
 #pragma unroll
                 for (int i = 0; i < 2; ++i)
 #pragma unroll
-                    for (int r = 0; r < 4; ++r) sc[i][r] = sd[i][r] = 0.f;
+                    for (int r = 0; r < 4; ++r) R.sc[i][r] = R.sd[i][r] = 0.f;
 #pragma unroll
                 for (int kk = 0; kk < 4; kk += 2) {
-                    mma_bf16_16816(sc[0], qf[kk], kf[kk][0], kf[kk][1]);
-                    mma_bf16_16816(sc[1], qf[kk], kf[kk][2], kf[kk][3]);
-                    mma_bf16_16816(sd[0], qf[kk + 1], kf[kk + 1][0], kf[kk + 1][1]);
-                    mma_bf16_16816(sd[1], qf[kk + 1], kf[kk + 1][2], kf[kk + 1][3]);
+                    mma_bf16_16816(R.sc[0], qf[kk], kf[kk][0], kf[kk][1]);
+                    mma_bf16_16816(R.sc[1], qf[kk], kf[kk][2], kf[kk][3]);
+                    mma_bf16_16816(R.sd[0], qf[kk + 1], kf[kk + 1][0], kf[kk + 1][1]);
+                    mma_bf16_16816(R.sd[1], qf[kk + 1], kf[kk + 1][2], kf[kk + 1][3]);
                 }
+            }
+        };
+        auto finish = [&](ChunkRegs& R) {
+            if (R.live) {
                 // mask + online softmax on row 0 (registers [0], [1]; the row lives in lanes 0..3,
                 // the other lanes carry the all-zero query rows and are never read)
                 float mx = -INFINITY;
 #pragma unroll
                 for (int ni = 0; ni < 2; ++ni) {
                     const int key = kb + ni * 8 + quad * 2;
-                    sc[ni][0] = key < n_valid ? (sc[ni][0] + sd[ni][0]) * kLog2e : -INFINITY;
-                    sc[ni][1] = key + 1 < n_valid ? (sc[ni][1] + sd[ni][1]) * kLog2e : -INFINITY;
-                    mx = fmaxf(mx, fmaxf(sc[ni][0], sc[ni][1]));
+                    R.sc[ni][0] = key < R.n_valid ? (R.sc[ni][0] + R.sd[ni][0]) * kLog2e : -INFINITY;
+                    R.sc[ni][1] = key + 1 < R.n_valid ? (R.sc[ni][1] + R.sd[ni][1]) * kLog2e : -INFINITY;
+                    mx = fmaxf(mx, fmaxf(R.sc[ni][0], R.sc[ni][1]));
                 }
                 mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, 1));
                 mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, 2));
                 const float m_new = fmaxf(m_run, mx);  // finite: key kb of the chunk is valid
                 const float corr = exp2f(m_run - m_new);
                 m_run = m_new;
-                const float p00 = exp2f(sc[0][0] - m_new), p01 = exp2f(sc[0][1] - m_new);
-                const float p10 = exp2f(sc[1][0] - m_new), p11 = exp2f(sc[1][1] - m_new);
+                const float p00 = exp2f(R.sc[0][0] - m_new), p01 = exp2f(R.sc[0][1] - m_new);
+                const float p10 = exp2f(R.sc[1][0] - m_new), p11 = exp2f(R.sc[1][1] - m_new);
                 l_run = l_run * corr + ((p00 + p01) + (p10 + p11));
                 uint32_t pf[4] = {pack_bf16(p00, p01), 0u, pack_bf16(p10, p11), 0u};
 #pragma unroll
@@ -722,13 +736,30 @@ __global__ void __launch_bounds__((4 * Q + 1) * 32)
                 // o += p V  (V tile is [key][d]; the transposed ldmatrix gave the col-major B fragment)
 #pragma unroll
                 for (int nj = 0; nj < 4; ++nj) {
-                    mma_bf16_16816(o[nj * 2], pf, vf[nj][0], vf[nj][1]);
-                    mma_bf16_16816(o[nj * 2 + 1], pf, vf[nj][2], vf[nj][3]);
+                    mma_bf16_16816(o[nj * 2], pf, R.vf[nj][0], R.vf[nj][1]);
+                    mma_bf16_16816(o[nj * 2 + 1], pf, R.vf[nj][2], R.vf[nj][3]);
                 }
             }
             // every ldmatrix of this stage has been consumed by an mma: hand the stage back
             __syncwarp();
-            if (lane == 0) mbar_arrive(empty0 + 8 * s);
+            if (lane == 0) mbar_arrive(empty0 + 8 * R.s);
+        };
+        {
+            int c = c_begin + qt;
+            if (c < c_end) {
+                ChunkRegs cur, nxt;
+                fetch(c, cnt, cur);
+                for (;;) {
+                    const int cn = c + kMmaQuartets;
+                    const bool more = cn < c_end;
+                    if (more) fetch(cn, cnt + 1, nxt);
+                    finish(cur);
+                    ++cnt;
+                    if (!more) break;
+                    c = cn;
+                    cur = nxt;
+                }
+            }
         }
 
         // merge the eight warps' partial states in fixed order
