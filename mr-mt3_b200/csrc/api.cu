@@ -135,12 +135,7 @@ int mrmt3_set_option(mrmt3_handle* h, const char* key, int value) {
         h->fuse_greedy = value != 0;
     }
     else if (k == "attn_full_tc") attn_full_configure(value);
-    else if (k == "attn_ring_layout") {
-        cudaSetDevice(h->device);
-        cudaDeviceSynchronize();
-        drop_graphs(h);
-        attn_decode_set_layout(value);
-    }
+
     else if (k == "attn_part_keys_self" || k == "attn_part_keys_cross") {
         const bool self = k == "attn_part_keys_self";
         if (value < 0) value = self ? kDefaultPartKeysSelf : kDefaultPartKeysCross;   // -1: the library default

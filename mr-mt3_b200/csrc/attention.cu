@@ -805,310 +805,10 @@ __global__ void __launch_bounds__((4 * Q + 1) * 32)
     trace_end(p.trace);
 }
 
-// =============================================================================================
-// Warp-per-chunk layout of the same kernel (the default since round 2).
-//
-// In the quartet layout above every math warp touches EVERY 64-key chunk (16 keys each): per chunk and
-// warp one full-barrier wait, one release, two shuffles and a short, strictly serial mma chain -- the
-// in-kernel stamps put that at 0.3-0.45 us per chunk whatever the memory system does (all chunks
-// prefetched, any ring depth; profiles/r2e_trace_segmem_16lanes_attn_marks.json), although the mma
-// themselves take 20 cycles (scripts/microbench/hmma_latency.cu).  A 16-lane MR-MT3 launch (96 items
-// on 96 SMs) is therefore latency-bound in the math warps: 5.1 us per self-attention at 512 keys.
-// Here chunk n of a CTA (counted over all its work units) belongs to warp n % 4 alone: four 16-key
-// blocks of independent mma work per barrier wait, a quarter of the iterations, one release per stage
-// (empty barriers count 1).  Same producer, same ring, same fixed-order merge of the four warps'
-// (m, l, o) states, same masking; the key-to-warp assignment is a function of the item alone.
-template <bool PAGED, int S>
-__global__ void __launch_bounds__(5 * 32, 2)
-    attn_decode_wc_kernel(const __grid_constant__ CUtensorMap tmap, AttnDecodeParams p, int n_lanes) {
-    extern __shared__ unsigned char mma_smem_raw[];
-    const uint32_t raw = smem_u32(mma_smem_raw);
-    const uint32_t base = (raw + 1023u) & ~1023u;  // SWIZZLE_128B tiles need 1024-B alignment
-    unsigned char* base_ptr = mma_smem_raw + (base - raw);
-    constexpr int kWarps = 4;
-    float* merge = reinterpret_cast<float*>(base_ptr + S * kMmaStageBytes);
-    const uint32_t full0 = base + S * kMmaStageBytes + kMmaMergeBytes;
-    const uint32_t empty0 = full0 + 8 * S;
-
-    trace_begin(p.trace);
-    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    if (tid == 0) {
-#pragma unroll
-        for (int s = 0; s < S; ++s) {
-            mbar_init(full0 + 8 * s, 1);
-            mbar_init(empty0 + 8 * s, 1);
-        }
-        mbar_fence_init();
-        asm volatile("fence.proxy.async.shared::cta;\n" ::: "memory");
-    }
-    __syncthreads();
-
-    const int n_items = n_lanes * kHeads;
-    const int pos = PAGED ? p.step_ptr[0] + p.pos_offset : 0;  // final before this kernel was launched (see above)
-    const long long rows_per_page = (long long)(p.page_stride / kDKV);
-    const int part_chunks = p.part_keys / kMmaChunk;             // 0: one unit per item
-    const int launch_keys = PAGED ? pos + 1 : p.n_keys;
-    const int n_parts = part_chunks ? max(1, (launch_keys + p.part_keys - 1) / p.part_keys) : 1;
-    const int n_units = n_items * n_parts;
-
-    if (warp == kWarps) {
-        // ---------------- producer ----------------
-        if (lane == 0) {
-            const uint64_t policy = l2_policy_evict_first();
-            int n = 0;  // chunks issued so far
-            for (int unit = blockIdx.x; unit < n_units; unit += gridDim.x) {
-                const int item = unit / n_parts, part = unit - item * n_parts;
-                const int lane_id = item / kHeads, head = item - lane_id * kHeads;
-                if (p.active && !p.active[lane_id]) continue;
-                const MmaItem it = mma_item<PAGED>(p, lane_id, head, pos);
-                const int c_begin = part * part_chunks;
-                const int c_end = part_chunks ? min(it.n_chunks, c_begin + part_chunks) : it.n_chunks;
-                for (int c = c_begin; c < c_end; ++c, ++n) {
-                    const int s = n % S;
-                    mbar_wait(empty0 + 8 * s, ((n / S) & 1) ^ 1);
-                    const int first = c * kMmaChunk;
-                    const int n_box = (min(kMmaChunk, it.n_keys - first) + kMmaBox - 1) / kMmaBox;
-                    long long kr = it.k_row + first, vr = it.v_row + first;
-                    if (PAGED) {
-                        const long long pg = (long long)it.pages[first / kKVPage] * rows_per_page - (first / kKVPage) * kKVPage;
-                        kr += pg;
-                        vr += pg;
-                    }
-                    const uint32_t dst = base + s * kMmaStageBytes;
-                    const uint32_t bar = full0 + 8 * s;
-                    mbar_expect_tx(bar, (uint32_t)n_box * 2 * kMmaBox * kDKV * sizeof(bf16));
-                    for (int b = 0; b < n_box; ++b) {
-                        tma_box_load(dst + b * kMmaBox * kDKV * 2, &tmap, (int)(kr + b * kMmaBox), bar, policy);
-                        tma_box_load(dst + kMmaTileBytes + b * kMmaBox * kDKV * 2, &tmap, (int)(vr + b * kMmaBox), bar, policy);
-                    }
-                }
-            }
-        }
-        return;
-    }
-
-    // ---------------- math warps ----------------
-    pdl_wait();  // the producer kernel's q (and k, v) rows are complete and visible from here on
-    trace_mark(p.trace, 0);
-    pdl_launch_dependents();
-    const float kLog2e = 1.4426950408889634f;
-    const int quad = lane & 3;
-
-    int n_base = 0, buf = 0;  // chunks of the units before this one
-    for (int unit = blockIdx.x; unit < n_units; unit += gridDim.x) {
-        const int item = unit / n_parts, part = unit - item * n_parts;
-        const int lane_id = item / kHeads, head = item - lane_id * kHeads;
-        if (p.active && !p.active[lane_id]) continue;
-        const MmaItem it = mma_item<PAGED>(p, lane_id, head, pos);
-        const int c_begin = part * part_chunks;
-        const int c_end = part_chunks ? min(it.n_chunks, c_begin + part_chunks) : it.n_chunks;
-
-        // A fragments of q: row 0 of the 16 x 64 tile is the query, rows 1..15 are zero
-        const bf16* qrow = p.q + (size_t)lane_id * p.q_stride + head * kDKV;
-        uint32_t qf[4][4];
-#pragma unroll
-        for (int kk = 0; kk < 4; ++kk) {
-            qf[kk][0] = lane < 4 ? *reinterpret_cast<const uint32_t*>(qrow + kk * 16 + quad * 2) : 0u;
-            qf[kk][1] = 0u;
-            qf[kk][2] = lane < 4 ? *reinterpret_cast<const uint32_t*>(qrow + kk * 16 + 8 + quad * 2) : 0u;
-            qf[kk][3] = 0u;
-        }
-        float o[8][4];
-#pragma unroll
-        for (int i = 0; i < 8; ++i)
-#pragma unroll
-            for (int r = 0; r < 4; ++r) o[i][r] = 0.f;
-        float m_run = -INFINITY, l_run = 0.f;
-
-        // this warp's chunks: global chunk index n = n_base + (c - c_begin), owner n % 4
-        int c = c_begin + ((warp - n_base) & (kWarps - 1));
-        for (; c < c_end; c += kWarps) {
-            const int n = n_base + (c - c_begin);
-            const int s = n % S;
-            mbar_wait(full0 + 8 * s, (n / S) & 1);
-            const int k0 = c * kMmaChunk;
-            const int n_valid = min(kMmaChunk, it.n_keys - k0);
-            const uint32_t bk = base + s * kMmaStageBytes;
-            const uint32_t bv = bk + kMmaTileBytes;
-            if (PAGED && pos >= k0 && pos < k0 + kMmaChunk) {
-                // the step's K and V sit in the fused QKV row right after Q: patch them into the tile
-                // and append them to the cache page for the steps to come
-                const int r = pos - k0;
-                if (lane < 16) {
-                    const int kv = lane >> 3, ch = lane & 7;
-                    const uint4 val = *reinterpret_cast<const uint4*>(qrow + kInner * (1 + kv) + ch * 8);
-                    unsigned char* tile = base_ptr + s * kMmaStageBytes + kv * kMmaTileBytes;
-                    *reinterpret_cast<uint4*>(tile + r * 128 + ((ch ^ (r & 7)) << 4)) = val;
-                    const size_t off = ((size_t)it.pages[pos / kKVPage] * rows_per_page +
-                                        (size_t)(kv ? it.v_row : it.k_row) + (pos % kKVPage)) * kDKV + ch * 8;
-                    *reinterpret_cast<uint4*>(const_cast<bf16*>(p.kv_pool) + off) = val;
-                }
-                __syncwarp();
-            }
-            // s = q K^T: four 16-key blocks, two n8 tiles each, one accumulator chain of four per tile --
-            // eight independent chains
-            float sc[4][2][4];
-#pragma unroll
-            for (int j = 0; j < 4; ++j)
-#pragma unroll
-                for (int t = 0; t < 2; ++t)
-#pragma unroll
-                    for (int r = 0; r < 4; ++r) sc[j][t][r] = 0.f;
-#pragma unroll
-            for (int j = 0; j < 4; ++j) {
-                if (j * 16 < n_valid) {  // warp-uniform
-                    uint32_t kf[4][4];
-#pragma unroll
-                    for (int kk = 0; kk < 4; ++kk) {
-                        const int row = j * 16 + (lane & 7) + ((lane >> 4) << 3);
-                        const int ch = kk * 2 + ((lane >> 3) & 1);
-                        ldmatrix_x4(kf[kk][0], kf[kk][1], kf[kk][2], kf[kk][3], bk + row * 128 + ((ch ^ (row & 7)) << 4));
-                    }
-#pragma unroll
-                    for (int kk = 0; kk < 4; ++kk) {
-                        mma_bf16_16816(sc[j][0], qf[kk], kf[kk][0], kf[kk][1]);
-                        mma_bf16_16816(sc[j][1], qf[kk], kf[kk][2], kf[kk][3]);
-                    }
-                }
-            }
-            // mask + online softmax on row 0 (registers [0], [1] of every tile; the row lives in lanes 0..3)
-            float mx = -INFINITY;
-#pragma unroll
-            for (int j = 0; j < 4; ++j)
-#pragma unroll
-                for (int t = 0; t < 2; ++t) {
-                    const int key = j * 16 + t * 8 + quad * 2;
-                    sc[j][t][0] = key < n_valid ? sc[j][t][0] * kLog2e : -INFINITY;
-                    sc[j][t][1] = key + 1 < n_valid ? sc[j][t][1] * kLog2e : -INFINITY;
-                    mx = fmaxf(mx, fmaxf(sc[j][t][0], sc[j][t][1]));
-                }
-            mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, 1));
-            mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, 2));
-            const float m_new = fmaxf(m_run, mx);  // finite: key 0 of the chunk is valid
-            const float corr = exp2f(m_run - m_new);
-            m_run = m_new;
-            uint32_t pf[4][2];
-            float lsum = 0.f;
-#pragma unroll
-            for (int j = 0; j < 4; ++j) {
-                const float p00 = exp2f(sc[j][0][0] - m_new), p01 = exp2f(sc[j][0][1] - m_new);
-                const float p10 = exp2f(sc[j][1][0] - m_new), p11 = exp2f(sc[j][1][1] - m_new);
-                lsum += (p00 + p01) + (p10 + p11);
-                pf[j][0] = pack_bf16(p00, p01);
-                pf[j][1] = pack_bf16(p10, p11);
-            }
-            l_run = l_run * corr + lsum;
-#pragma unroll
-            for (int ni = 0; ni < 8; ++ni) {
-                o[ni][0] *= corr;
-                o[ni][1] *= corr;
-            }
-            // o += p V  (V tile is [key][d]; the transposed ldmatrix gives the col-major B fragment)
-#pragma unroll
-            for (int j = 0; j < 4; ++j) {
-                if (j * 16 < n_valid) {
-                    uint32_t vf[4][4];
-#pragma unroll
-                    for (int nj = 0; nj < 4; ++nj) {
-                        const int row = j * 16 + (lane & 7) + (((lane >> 3) & 1) << 3);
-                        const int ch = nj * 2 + (lane >> 4);
-                        ldmatrix_x4_trans(vf[nj][0], vf[nj][1], vf[nj][2], vf[nj][3], bv + row * 128 + ((ch ^ (row & 7)) << 4));
-                    }
-                    const uint32_t a[4] = {pf[j][0], 0u, pf[j][1], 0u};
-#pragma unroll
-                    for (int nj = 0; nj < 4; ++nj) {
-                        mma_bf16_16816(o[nj * 2], a, vf[nj][0], vf[nj][1]);
-                        mma_bf16_16816(o[nj * 2 + 1], a, vf[nj][2], vf[nj][3]);
-                    }
-                }
-            }
-            // every ldmatrix of this stage has been consumed by an mma: hand the stage back
-            __syncwarp();
-            if (lane == 0) mbar_arrive(empty0 + 8 * s);
-        }
-        n_base += c_end - c_begin;
-
-        // merge the four warps' partial states in fixed order
-        if (warp == 0 && unit == (int)blockIdx.x) trace_mark(p.trace, 2);
-        l_run += __shfl_xor_sync(0xffffffffu, l_run, 1);
-        l_run += __shfl_xor_sync(0xffffffffu, l_run, 2);
-        float* wpart = merge + (buf * kWarps + warp) * kMmaPartFloats;
-        if (lane < 4) {
-            if (lane == 0) {
-                wpart[0] = m_run;
-                wpart[1] = l_run;
-            }
-#pragma unroll
-            for (int ni = 0; ni < 8; ++ni)
-                *reinterpret_cast<float2*>(wpart + 2 + ni * 8 + quad * 2) = make_float2(o[ni][0], o[ni][1]);
-        }
-        named_bar_sync(1, kWarps * 32);
-        if (warp == 0) {
-            const float* pb = merge + buf * kWarps * kMmaPartFloats;
-            float mx = -INFINITY;
-#pragma unroll
-            for (int w = 0; w < kWarps; ++w) mx = fmaxf(mx, pb[w * kMmaPartFloats]);
-            float den = 0.f, o0 = 0.f, o1 = 0.f;
-#pragma unroll
-            for (int w = 0; w < kWarps; ++w) {
-                const float wgt = exp2f(pb[w * kMmaPartFloats] - mx);  // warp without a chunk: exp2(-inf) = 0
-                den += pb[w * kMmaPartFloats + 1] * wgt;
-                const float2 ov = *reinterpret_cast<const float2*>(pb + w * kMmaPartFloats + 2 + lane * 2);
-                o0 += ov.x * wgt;
-                o1 += ov.y * wgt;
-            }
-            bool write_out = true;
-            if (n_parts > 1) {
-                float* mine = p.part_scratch + ((size_t)item * p.max_parts + part) * kMmaPartFloats;
-                if (lane == 0) {
-                    mine[0] = mx;
-                    mine[1] = den;
-                }
-                *reinterpret_cast<float2*>(mine + 2 + lane * 2) = make_float2(o0, o1);
-                __threadfence();
-                __syncwarp();
-                int ticket = 0;
-                if (lane == 0) ticket = atomicAdd(p.part_counter + item, 1);
-                ticket = __shfl_sync(0xffffffffu, ticket, 0);
-                write_out = ticket == n_parts - 1;
-                if (write_out) {
-                    __threadfence();
-                    const float* all = p.part_scratch + (size_t)item * p.max_parts * kMmaPartFloats;
-                    float mall = -INFINITY;
-                    for (int q = 0; q < n_parts; ++q) mall = fmaxf(mall, __ldcg(all + q * kMmaPartFloats));
-                    den = 0.f, o0 = 0.f, o1 = 0.f;
-                    for (int q = 0; q < n_parts; ++q) {
-                        const float* pq = all + q * kMmaPartFloats;
-                        const float wgt = exp2f(__ldcg(pq) - mall);
-                        den += __ldcg(pq + 1) * wgt;
-                        const float2 ov = __ldcg(reinterpret_cast<const float2*>(pq + 2 + lane * 2));
-                        o0 += ov.x * wgt;
-                        o1 += ov.y * wgt;
-                    }
-                    if (lane == 0) p.part_counter[item] = 0;
-                }
-            }
-            if (write_out) {
-                const float inv = 1.f / den;
-                *reinterpret_cast<uint32_t*>(p.out + (size_t)lane_id * p.out_stride + head * kDKV + lane * 2) =
-                    pack_bf16(o0 * inv, o1 * inv);
-            }
-        }
-        if (warp == 0 && unit == (int)blockIdx.x) trace_mark(p.trace, 3);
-        buf ^= 1;  // the other half is free again once every warp has passed the next unit's barrier
-    }
-    trace_end(p.trace);
-}
-
 static int g_attn_variant = 1;      // 0: one CTA per (lane, head), CUDA cores; 1: TMA ring + mma.sync
 static int g_ring_stages = 4;       // per warp quartet
 static int g_ring_ctas_per_sm = 0;  // 0 = by launch size (see launch_ring)
 static int g_ring_quartets = 1;
-static int g_ring_layout = [] {  // 1: a chunk belongs to one warp (default), 0: a chunk is shared by a warp quartet
-    const char* e = getenv("MRMT3_ATTN_LAYOUT");
-    return e ? atoi(e) : 1;
-}();
-void attn_decode_set_layout(int layout) { g_ring_layout = layout < 0 ? 1 : (layout ? 1 : 0); }
 
 void attn_decode_configure(int variant, int stages, int ctas_per_sm, int quartets) {
     if (variant >= 0) g_attn_variant = variant;
@@ -1120,8 +820,7 @@ void attn_decode_configure(int variant, int stages, int ctas_per_sm, int quartet
 template <bool PAGED, int S, int Q>
 static Status launch_ring(const AttnDecodeParams& p, int n_lanes, cudaStream_t stream) {
     if (!p.tmap) return Error(2, "attn_decode: the TMA variant needs a tensor map of the cache");
-    const bool wc = Q == 1 && g_ring_layout == 1;
-    auto kern = wc ? attn_decode_wc_kernel<PAGED, S> : attn_decode_mma_kernel<PAGED, S, Q>;
+    auto kern = attn_decode_mma_kernel<PAGED, S, Q>;
     constexpr int smem = Q * S * kMmaStageBytes + kMmaMergeBytes + 2 * Q * S * 8 + 1024;
     static int n_sm_of[64] = {0};  // per device: SM count
     int dev = 0;

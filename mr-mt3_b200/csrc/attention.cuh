@@ -85,7 +85,5 @@ int attn_decode_max_keys();
 // process-wide kernel selection: variant 0 = one CTA per (lane, head), 1 = persistent bulk-copy
 // ring (default); negative / zero arguments leave a setting unchanged
 void attn_decode_configure(int variant, int stages, int ctas_per_sm, int quartets);
-// ring layout: 1 = every 64-key chunk belongs to one math warp (default), 0 = shared by a warp quartet
-void attn_decode_set_layout(int layout);
 
 }  // namespace mrmt3

@@ -54,9 +54,8 @@ def long_oracle():
     return x, want, torch.stack(traces, 1)                     # (6, 1025), (6, steps, V)
 
 
-@pytest.mark.parametrize("ring_ctas,part_self,part_cross,layout",
-                         [(1, 0, 0, 1), (3, 0, 0, 1), (0, 256, 128, 1), (2, 128, 128, 0), (0, 0, 0, 0)])
-def test_1024_step_logits_through_graphs_and_lane_groups(long_oracle, ring_ctas, part_self, part_cross, layout):
+@pytest.mark.parametrize("ring_ctas,part_self,part_cross", [(1, 0, 0), (3, 0, 0), (0, 256, 128), (2, 128, 128)])
+def test_1024_step_logits_through_graphs_and_lane_groups(long_oracle, ring_ctas, part_self, part_cross):
     x, want, want_logits = long_oracle
     model, _ = _model("mt3", 1234)
     eng = model.engine()
@@ -68,12 +67,11 @@ def test_1024_step_logits_through_graphs_and_lane_groups(long_oracle, ring_ctas,
         eng.set_option("attn_ring_ctas", ring_ctas)
         eng.set_option("attn_part_keys_self", part_self)        # split-key work units of the decode attention
         eng.set_option("attn_part_keys_cross", part_cross)
-        eng.set_option("attn_ring_layout", layout)              # 1: a chunk per warp (default), 0: per warp quartet
         ids, logits = eng.generate(x.cuda(), max_length=1024, forced_ids=want.cuda(), return_logits=True)
         np.testing.assert_array_equal(ids.cpu().numpy(), want.numpy())
         diff = logits.cpu().double() - want_logits
         err = diff.abs().amax(dim=(0, 2))                                            # per step
-        print(f"ring_ctas={ring_ctas} parts={part_self}/{part_cross} layout={layout}: rms {float(diff.pow(2).mean().sqrt()):.5f}, "
+        print(f"ring_ctas={ring_ctas} parts={part_self}/{part_cross}: rms {float(diff.pow(2).mean().sqrt()):.5f}, "
               f"per-step logit err max {err.max():.4f} at step {int(err.argmax())}; "
               f"by KV page: {[round(float(err[p * 128:(p + 1) * 128].max()), 4) for p in range(8)]}")
         assert float(err.max()) < BF16_ATOL
@@ -93,7 +91,6 @@ def test_1024_step_logits_through_graphs_and_lane_groups(long_oracle, ring_ctas,
         eng.set_option("attn_ring_ctas", 0)
         eng.set_option("attn_part_keys_self", -1)
         eng.set_option("attn_part_keys_cross", -1)
-        eng.set_option("attn_ring_layout", -1)
 
 
 def test_segmem_three_tracks_eight_segments_256_tokens():
