@@ -545,6 +545,38 @@ def run_mt3(args):
             "achieved_GBs_timed_region": round(step_bytes / step_s / 1e9, 1),
             "frac_of_peak_timed_region": round(step_bytes / step_s / 1e9 / peak, 4),
         }
+        # the same two kernels INSIDE the replayed step graph (one lane group, programmatic dependent launch
+        # active, no events between launches): %globaltimer stamps of the last step of runs of growing
+        # length; a kernel's time on the chain = its last CTA's end - the previous kernel's end
+        try:
+            eng.set_option("group_lanes", 0)
+            eng.trace_enable(True)
+            in_graph = {}
+            for t_len in (256, 512, 768, 1024):
+                if t_len > T:
+                    continue
+                model.generate(mel, max_length=t_len)
+                tr = eng.trace_read(80)
+                spans = {"attn_self": [], "attn_cross": []}
+                for layer in range(N_LAYERS):
+                    for name, off in (("attn_self", 2), ("attn_cross", 5)):
+                        i = 8 * layer + off
+                        if tr[i][1] and tr[i - 1][1]:
+                            spans[name].append((tr[i][1] - tr[i - 1][1]) / 1e3)
+                if spans["attn_self"] and spans["attn_cross"]:
+                    us_s, us_c = float(np.median(spans["attn_self"])), float(np.median(spans["attn_cross"]))
+                    b_s = S * (1536 * t_len + 1536 + 2304 + 768)
+                    b_c = S * (1536 * 256 + 768 + 768)
+                    in_graph[f"position_{t_len - 1}"] = {
+                        "attn_self_us": round(us_s, 2), "attn_self_GBs": round(b_s / us_s / 1e3, 1),
+                        "attn_self_frac": round(b_s / us_s / 1e3 / peak, 4),
+                        "attn_cross_us": round(us_c, 2), "attn_cross_GBs": round(b_c / us_c / 1e3, 1),
+                        "attn_cross_frac": round(b_c / us_c / 1e3 / peak, 4)}
+            roofline["in_graph"] = dict(in_graph, how="median over the 8 layers of (end of the kernel's last CTA - end of "
+                                        "the previous kernel) inside the replayed graph, one lane group")
+        finally:
+            eng.trace_enable(False)
+            eng.set_option("group_lanes", -1)
         line["roofline"] = roofline
         line["decode_step_breakdown"] = breakdown
 
@@ -658,6 +690,12 @@ def run_mrmt3(args):
     line["config"].update({"segments_total": int(seg_counts_all.sum()), "audio_seconds_total": round(audio_s, 1),
                            "lanes_per_gpu": [len(s) for s in shards]})
     line["clocks"] = b.sampler.summary()
+    if args.workload == "mrmt3_512_slakh" and args.duration_scale == 1.0 / 16.0 and (args.tracks or 512) == 512:
+        # the N = 1 point of this strong-scaling curve (the N = 1 default of bench.py is configs[1]): measured in
+        # round 2 with this same command at --gpus 1 on one B200 of this pool
+        line["strong_scaling_context"] = {"same_workload_n1_value": 785.72, "unit": UNIT,
+                                          "from": "profiles/r2f_bench_slakh_n1.json (python bench.py --workload "
+                                                  "mrmt3_512_slakh, 1 GPU, round 2)"}
     line["sharding"] = {
         "per_rank_ms": per_rank_ms, "segments_per_rank": seg_load, "rounds_per_rank": rounds,
         "time_imbalance_max_over_mean": round(max(per_rank_ms) / (sum(per_rank_ms) / len(per_rank_ms)), 4),
