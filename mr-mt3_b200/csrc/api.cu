@@ -135,6 +135,12 @@ int mrmt3_set_option(mrmt3_handle* h, const char* key, int value) {
         h->fuse_greedy = value != 0;
     }
     else if (k == "attn_full_tc") attn_full_configure(value);
+    else if (k == "gemm_2cta") {
+        cudaSetDevice(h->device);
+        cudaDeviceSynchronize();
+        drop_graphs(h);  // the encoder GEMMs of a captured graph keep the kernel they were captured with
+        gemm_set_2cta(value);
+    }
 
     else if (k == "attn_part_keys_self" || k == "attn_part_keys_cross") {
         const bool self = k == "attn_part_keys_self";

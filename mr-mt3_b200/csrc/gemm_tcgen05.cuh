@@ -45,6 +45,70 @@ __device__ __forceinline__ void tc_mma_f16(uint32_t tmem_d, uint64_t desc_a, uin
         "l"(desc_a), "l"(desc_b), "r"(idesc), "r"(accumulate)
         : "memory");
 }
+// ---- CTA pair (cta_group::2) forms ---------------------------------------------------------------
+// One tcgen05.mma issued by the even CTA of a 2-CTA cluster multiplies a 256-row A tile (128 rows in
+// each CTA's shared memory, same offset) by an N-row B tile (N / 2 rows in each CTA's shared memory)
+// into 128 x N accumulators in EACH CTA's TMEM: every CTA loads half of each operand.
+__device__ __forceinline__ void tc_mma_f16_2cta(uint32_t tmem_d, uint64_t desc_a, uint64_t desc_b, uint32_t idesc,
+                                                uint32_t accumulate) {
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "setp.ne.b32 p, %4, 0;\n"
+        "tcgen05.mma.cta_group::2.kind::f16 [%0], %1, %2, %3, p;\n"
+        "}\n" ::"r"(tmem_d),
+        "l"(desc_a), "l"(desc_b), "r"(idesc), "r"(accumulate)
+        : "memory");
+}
+// arrives (once all earlier MMAs of this thread are complete) on the barrier at the same shared-memory
+// offset in every CTA of `cta_mask`
+__device__ __forceinline__ void tc_commit_2cta(uint32_t bar, uint16_t cta_mask) {
+    asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;\n" ::"r"(bar),
+                 "h"(cta_mask)
+                 : "memory");
+}
+// TMA load into THIS CTA's shared memory whose bytes are counted on a barrier of the pair's even CTA
+// (`bar_cluster`: a shared::cluster address from mapa)
+__device__ __forceinline__ void tma_load_2d_2cta(uint32_t smem_dst, const CUtensorMap* map, int x, int y, uint32_t bar_cluster) {
+    asm volatile(
+        "cp.async.bulk.tensor.2d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3}], [%4];\n" ::"r"(
+            smem_dst),
+        "l"(map), "r"(x), "r"(y), "r"(bar_cluster)
+        : "memory");
+}
+__device__ __forceinline__ uint32_t cluster_ctarank() {
+    uint32_t r;
+    asm volatile("mov.u32 %0, %%cluster_ctarank;\n" : "=r"(r));
+    return r;
+}
+__device__ __forceinline__ void cluster_sync_all() {
+    asm volatile("barrier.cluster.arrive.release.aligned;\n" ::: "memory");
+    asm volatile("barrier.cluster.wait.acquire.aligned;\n" ::: "memory");
+}
+__device__ __forceinline__ uint32_t mapa_shared(uint32_t addr, uint32_t rank) {
+    uint32_t r;
+    asm volatile("mapa.shared::cluster.u32 %0, %1, %2;\n" : "=r"(r) : "r"(addr), "r"(rank));
+    return r;
+}
+__device__ __forceinline__ void mbar_arrive_cluster(uint32_t bar_cluster) {
+    asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];\n" ::"r"(bar_cluster) : "memory");
+}
+// wait with cluster-scope acquire: the arrivals come from the other CTA of the pair
+__device__ __forceinline__ void mbar_wait_cluster(uint32_t bar, uint32_t parity) {
+    uint32_t done;
+    do {
+        asm volatile(
+            "{\n"
+            ".reg .pred p;\n"
+            "mbarrier.try_wait.parity.acquire.cluster.shared::cta.b64 p, [%1], %2;\n"
+            "selp.u32 %0, 1, 0, p;\n"
+            "}\n"
+            : "=r"(done)
+            : "r"(bar), "r"(parity)
+            : "memory");
+    } while (!done);
+}
+
 __device__ __forceinline__ void tc_ld_32x32(uint32_t taddr, uint32_t (&r)[32]) {
     asm volatile(
         "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
@@ -84,9 +148,9 @@ __device__ __forceinline__ uint64_t tc_smem_desc_mn(uint32_t smem_addr, uint32_t
 }
 
 // instruction descriptor: D = f32, A = B = bf16, M = 128, N = BN; bit 15 / 16 = A / B is MN-major
-__host__ __device__ constexpr uint32_t tc_idesc(int bn, bool a_mn = false, bool b_mn = false) {
+__host__ __device__ constexpr uint32_t tc_idesc(int bn, bool a_mn = false, bool b_mn = false, int bm = kTcBM) {
     return (1u << 4) | (1u << 7) | (1u << 10) | (a_mn ? (1u << 15) : 0u) | (b_mn ? (1u << 16) : 0u) |
-           ((uint32_t)(bn >> 3) << 17) | ((uint32_t)(kTcBM >> 4) << 24);
+           ((uint32_t)(bn >> 3) << 17) | ((uint32_t)(bm >> 4) << 24);
 }
 
 // ---- 8-wide epilogue stores --------------------------------------------------------------------
@@ -138,11 +202,12 @@ __device__ __forceinline__ void epi_store8(const EpiCrossKV& e, int row, int col
         make_uint4(pack_bf16(v[0], v[1]), pack_bf16(v[2], v[3]), pack_bf16(v[4], v[5]), pack_bf16(v[6], v[7]));
 }
 
-template <int BN>
+// NCTA = 2: the CTA pair computes a 256 x BN tile; each CTA stages its 128 rows of A and BN / 2 rows of W
+template <int BN, int NCTA = 1>
 struct TcSmem {
-    static constexpr int kStages = BN > 128 ? 4 : 6;
+    static constexpr int kStages = NCTA == 2 ? (BN > 192 ? 6 : BN > 128 ? 7 : 8) : (BN > 128 ? 4 : 6);
     static constexpr int kABytes = kTcBM * kTcBK * 2;
-    static constexpr int kWBytes = BN * kTcBK * 2;
+    static constexpr int kWBytes = BN / NCTA * kTcBK * 2;
     static constexpr int kStageBytes = kABytes + kWBytes;
     static constexpr int kBarOffset = kStages * kStageBytes;
     static constexpr int kTotal = kBarOffset + 256 + 1024;  // barriers + slack for 1024-B alignment
@@ -161,13 +226,28 @@ struct TcSmem {
 // MODE 2, the data-gradient form D = A B on row-major A (M x K) and B (K x N): A K-major, B MN-major.
 // In modes 1 and 2 K is the number of reduction rows (any value: TMA zero-fills past the end) and
 // the k ranges of the splits are ceil(ceil(K / 64) / k_splits) blocks each.
-template <int BN, class Epi, int MODE = 0>
+//
+// NCTA = 2 (launched as clusters of two CTAs = one TPC): the pair works on 256 x BN output tiles with
+// tcgen05.mma.cta_group::2.  Each CTA stages ITS 128 rows of A and ITS BN / 2 rows of W, so the pair
+// moves (256 + BN) x 64 operand elements per 256 x BN x 64 MACs: 1.5-1.67x fewer bytes through L2 per
+// flop than the single-CTA tile (the kernel sits at the L2-slice throughput cap).
+//   * both producers load with the cta_group::2 TMA form, which counts the bytes on the EVEN CTA's
+//     full barrier; only the even CTA arms it (expect_tx of both halves) and only its MMA warp waits;
+//   * the even CTA's elected thread issues the MMAs; tcgen05.commit multicasts to the barrier at the
+//     same offset in both CTAs: "ring slot free" for both producers, "accumulator complete" for both
+//     epilogues (each drains the 128 x BN accumulator in its own TMEM);
+//   * all 256 epilogue threads of the pair arrive on the even CTA's "accumulator drained" barrier.
+template <int BN, class Epi, int MODE = 0, int NCTA = 1>
 __global__ void __launch_bounds__(kTcThreads, 1)
     gemm_tn_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_w,
                            int M, int N, int K, ARowMap amap, Epi epi, int k_splits) {
-    using S = TcSmem<BN>;
+    using S = TcSmem<BN, NCTA>;
     constexpr int kStages = S::kStages;
     constexpr bool MN = MODE != 0, kAMn = MODE == 1, kBMn = MODE != 0;
+    constexpr bool kPair = NCTA == 2;
+    constexpr int kTileM = kTcBM * NCTA;                          // output rows per work item
+    constexpr int kWRows = BN / NCTA;                             // W rows (output columns) staged by one CTA
+    static_assert(!kPair || (BN % 32 == 0 && (!kBMn || kWRows % 64 == 0)), "tile not splittable across the pair");
     extern __shared__ unsigned char tc_smem_raw[];
     const uint32_t raw = smem_u32(tc_smem_raw);
     const uint32_t base = (raw + 1023u) & ~1023u;                 // SWIZZLE_128B tiles need 1024-B alignment
@@ -180,14 +260,18 @@ __global__ void __launch_bounds__(kTcThreads, 1)
 
     const int warp = threadIdx.x >> 5;
     const int lane = threadIdx.x & 31;
+    const uint32_t rank = kPair ? cluster_ctarank() : 0u;         // 0 = the CTA that issues the MMAs
+    const int worker = kPair ? blockIdx.x >> 1 : blockIdx.x;
+    const int n_workers = kPair ? gridDim.x >> 1 : gridDim.x;
     // split-K (wgrad: small output, long reduction): work item t -> output tile t % n_out, k range
     // split t / n_out; split s stores its partial sums at rows [s*M, (s+1)*M) of the output
     const int KB = MN ? ((K + kTcBK - 1) / kTcBK + k_splits - 1) / k_splits : K / kTcBK / k_splits;
     const int tiles_n = N / BN;
-    const int tiles_m = (M + kTcBM - 1) / kTcBM;
+    const int tiles_m = (M + kTileM - 1) / kTileM;
     const int n_out = tiles_n * tiles_m;
     const int n_tiles = n_out * k_splits;
 
+    if constexpr (kPair) cluster_sync_all();                      // both CTAs of the pair are resident
     if (threadIdx.x == 0) {
         for (int s = 0; s < kStages; ++s) {
             mbar_init(bar_full + s * 8, 1);
@@ -195,69 +279,88 @@ __global__ void __launch_bounds__(kTcThreads, 1)
         }
         for (int b = 0; b < 2; ++b) {
             mbar_init(bar_acc_full + b * 8, 1);
-            mbar_init(bar_acc_empty + b * 8, 128);  // every epilogue thread arrives
+            mbar_init(bar_acc_empty + b * 8, 128 * NCTA);  // every epilogue thread (of the pair) arrives
         }
         asm volatile("fence.mbarrier_init.release.cluster;\n" ::: "memory");
         asm volatile("fence.proxy.async.shared::cta;\n" ::: "memory");
     }
     if (warp == 1) {
-        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;\n" ::"r"(
-                         smem_u32((const void*)tmem_slot)),
-                     "n"(S::kTmemCols)
-                     : "memory");
-        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;\n" ::: "memory");
+        if constexpr (kPair) {
+            asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;\n" ::"r"(
+                             smem_u32((const void*)tmem_slot)),
+                         "n"(S::kTmemCols)
+                         : "memory");
+            asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;\n" ::: "memory");
+        } else {
+            asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;\n" ::"r"(
+                             smem_u32((const void*)tmem_slot)),
+                         "n"(S::kTmemCols)
+                         : "memory");
+            asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;\n" ::: "memory");
+        }
     }
     tc_fence_before();
-    __syncthreads();
+    if constexpr (kPair) cluster_sync_all(); else __syncthreads();
     tc_fence_after();
     const uint32_t tmem_base = *tmem_slot;
 
     if (warp == 0) {
         if (lane == 0) {
             int it = 0;
-            for (int t = blockIdx.x; t < n_tiles; t += gridDim.x) {
+            for (int t = worker; t < n_tiles; t += n_workers) {
                 const int to = t % n_out, kb0 = (t / n_out) * KB;
-                const int m0 = (to / tiles_n) * kTcBM;
-                const int n0 = (to % tiles_n) * BN;
+                const int m0 = (to / tiles_n) * kTileM + (int)rank * kTcBM;   // this CTA's 128 rows of A
+                const int n0 = (to % tiles_n) * BN + (int)rank * kWRows;      // ... and its rows of W
                 // A rows may be gathered block-wise (cross-K/V projection picks each lane's segment)
                 int arow = m0;
                 if (amap.map) arow = amap.map[m0 / amap.block] * amap.block + m0 % amap.block;
                 for (int kb = 0; kb < KB; ++kb, ++it) {
                     const int s = it % kStages;
                     mbar_wait(bar_empty + s * 8, ((it / kStages) & 1) ^ 1);
-                    mbar_expect_tx(bar_full + s * 8, S::kStageBytes);
                     const uint32_t sa = base + s * S::kStageBytes;
                     constexpr int kBox = 64 * kTcBK * 2;  // MN-major: 64 reduction rows x 64 columns
                     const int r0 = (kb0 + kb) * kTcBK;
+                    uint32_t bar = bar_full + s * 8;
+                    if constexpr (kPair) {
+                        if (rank == 0) mbar_expect_tx(bar, 2 * S::kStageBytes);
+                        bar = mapa_shared(bar, 0);
+                    } else {
+                        mbar_expect_tx(bar, S::kStageBytes);
+                    }
+                    auto load = [&](uint32_t dst, const CUtensorMap* map, int x, int y) {
+                        if constexpr (kPair) tma_load_2d_2cta(dst, map, x, y, bar);
+                        else tma_load_2d(dst, map, x, y, bar);
+                    };
                     if constexpr (kAMn) {
 #pragma unroll
-                        for (int j = 0; j < kTcBM / 64; ++j)
-                            tma_load_2d(sa + j * kBox, &tmap_a, m0 + 64 * j, r0, bar_full + s * 8);
+                        for (int j = 0; j < kTcBM / 64; ++j) load(sa + j * kBox, &tmap_a, m0 + 64 * j, r0);
                     } else {
-                        tma_load_2d(sa, &tmap_a, r0, arow, bar_full + s * 8);
+                        load(sa, &tmap_a, r0, arow);
                     }
                     if constexpr (kBMn) {
 #pragma unroll
-                        for (int j = 0; j < BN / 64; ++j)
-                            tma_load_2d(sa + S::kABytes + j * kBox, &tmap_w, n0 + 64 * j, r0, bar_full + s * 8);
+                        for (int j = 0; j < kWRows / 64; ++j) load(sa + S::kABytes + j * kBox, &tmap_w, n0 + 64 * j, r0);
                     } else {
-                        tma_load_2d(sa + S::kABytes, &tmap_w, r0, n0, bar_full + s * 8);
+                        load(sa + S::kABytes, &tmap_w, r0, n0);
                     }
                 }
             }
         }
     } else if (warp == 1) {
-        if (lane == 0) {
-            constexpr uint32_t idesc = tc_idesc(BN, kAMn, kBMn);
+        if (lane == 0 && rank == 0) {
+            constexpr uint32_t idesc = tc_idesc(BN, kAMn, kBMn, kTileM);
             int it = 0, i = 0;
-            for (int t = blockIdx.x; t < n_tiles; t += gridDim.x, ++i) {
+            for (int t = worker; t < n_tiles; t += n_workers, ++i) {
                 const int buf = i & 1;
-                mbar_wait(bar_acc_empty + buf * 8, ((i >> 1) & 1) ^ 1);  // epilogue has drained this buffer
+                // the epilogue (of both CTAs) has drained this buffer
+                if constexpr (kPair) mbar_wait_cluster(bar_acc_empty + buf * 8, ((i >> 1) & 1) ^ 1);
+                else mbar_wait(bar_acc_empty + buf * 8, ((i >> 1) & 1) ^ 1);
                 tc_fence_after();
                 const uint32_t tacc = tmem_base + (uint32_t)(buf * S::kAccCols);
                 for (int kb = 0; kb < KB; ++kb, ++it) {
                     const int s = it % kStages;
-                    mbar_wait(bar_full + s * 8, (it / kStages) & 1);
+                    if constexpr (kPair) mbar_wait_cluster(bar_full + s * 8, (it / kStages) & 1);
+                    else mbar_wait(bar_full + s * 8, (it / kStages) & 1);
                     tc_fence_after();
                     const uint32_t sa = base + s * S::kStageBytes;
                     const uint64_t da = kAMn ? tc_smem_desc_mn(sa, 64 * kTcBK * 2) : tc_smem_desc(sa);
@@ -267,20 +370,26 @@ __global__ void __launch_bounds__(kTcThreads, 1)
                     // whole 1024-B atoms, +128
                     constexpr uint64_t kStepA = kAMn ? 128 : 2, kStepB = kBMn ? 128 : 2;
 #pragma unroll
-                    for (int k = 0; k < kTcBK / 16; ++k)
-                        tc_mma_f16(tacc, da + kStepA * k, dw + kStepB * k, idesc, (kb | k) != 0);
-                    tc_commit(bar_empty + s * 8);  // frees the ring slot once the MMAs have read it
+                    for (int k = 0; k < kTcBK / 16; ++k) {
+                        if constexpr (kPair) tc_mma_f16_2cta(tacc, da + kStepA * k, dw + kStepB * k, idesc, (kb | k) != 0);
+                        else tc_mma_f16(tacc, da + kStepA * k, dw + kStepB * k, idesc, (kb | k) != 0);
+                    }
+                    // frees the ring slot (in both CTAs) once the MMAs have read it
+                    if constexpr (kPair) tc_commit_2cta(bar_empty + s * 8, 3);
+                    else tc_commit(bar_empty + s * 8);
                 }
-                tc_commit(bar_acc_full + buf * 8);  // accumulator of this tile complete
+                // accumulator of this tile complete
+                if constexpr (kPair) tc_commit_2cta(bar_acc_full + buf * 8, 3);
+                else tc_commit(bar_acc_full + buf * 8);
             }
         }
     } else {
         // epilogue warps 2..5: TMEM lane quarter = warp % 4
         const int quarter = warp & 3;
         int i = 0;
-        for (int t = blockIdx.x; t < n_tiles; t += gridDim.x, ++i) {
+        for (int t = worker; t < n_tiles; t += n_workers, ++i) {
             const int to = t % n_out;
-            const int m0 = (to / tiles_n) * kTcBM;
+            const int m0 = (to / tiles_n) * kTileM + (int)rank * kTcBM;
             const int n0 = (to % tiles_n) * BN;
             const int out_row0 = (t / n_out) * M;  // split-K partials are stacked along the rows
             const int buf = i & 1;
@@ -303,42 +412,112 @@ __global__ void __launch_bounds__(kTcThreads, 1)
                 }
             }
             tc_fence_before();
-            mbar_arrive(bar_acc_empty + buf * 8);
+            if constexpr (kPair) mbar_arrive_cluster(mapa_shared(bar_acc_empty + buf * 8, 0));
+            else mbar_arrive(bar_acc_empty + buf * 8);
         }
     }
     tc_fence_before();
-    __syncthreads();
+    if constexpr (kPair) cluster_sync_all(); else __syncthreads();
     if (warp == 1) {
-        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;\n" ::"r"(tmem_base), "n"(S::kTmemCols)
-                     : "memory");
+        if constexpr (kPair)
+            asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;\n" ::"r"(tmem_base), "n"(S::kTmemCols)
+                         : "memory");
+        else
+            asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;\n" ::"r"(tmem_base), "n"(S::kTmemCols)
+                         : "memory");
     }
 }
+
+// ---- launchers ----------------------------------------------------------------------------------
+// CTA-pair tiles: option `gemm_2cta` / MRMT3_GEMM_2CTA (1 = use the pair kernel where the tile splits and
+// the problem has at least one 256-row tile per pair; 0 = single-CTA kernel everywhere)
+constexpr int kGemm2CtaDefault = 0;
+inline int& gemm_2cta_flag() {
+    static int flag = [] {
+        const char* e = getenv("MRMT3_GEMM_2CTA");
+        return e ? atoi(e) : kGemm2CtaDefault;
+    }();
+    return flag;
+}
+inline void gemm_configure_2cta(int on) { gemm_2cta_flag() = on < 0 ? kGemm2CtaDefault : on; }
+
+inline Status tc_sm_count(int* n_sms) {
+    static int cached = 0;
+    if (!cached) {
+        int dev = 0;
+        MRMT3_CUDA_TRY(cudaGetDevice(&dev));
+        MRMT3_CUDA_TRY(cudaDeviceGetAttribute(&cached, cudaDevAttrMultiProcessorCount, dev));
+    }
+    *n_sms = cached;
+    return OkStatus();
+}
+
+template <int BN, class Epi, int MODE, int NCTA>
+Status launch_gemm_tc_kernel(const CUtensorMap* ma, const CUtensorMap* mw, int M, int N, int K, ARowMap amap, const Epi& epi,
+                             cudaStream_t stream, int k_splits) {
+    int n_sms = 0;
+    MRMT3_TRY(tc_sm_count(&n_sms));
+    auto kern = gemm_tn_tcgen05_kernel<BN, Epi, MODE, NCTA>;
+    using S = TcSmem<BN, NCTA>;
+    MRMT3_TRY(ensure_dynamic_smem(kern, S::kTotal));
+    const int n_tiles = (N / BN) * ceil_div(M, kTcBM * NCTA) * k_splits;
+    if constexpr (NCTA == 1) {
+        kern<<<std::min(n_tiles, n_sms), kTcThreads, S::kTotal, stream>>>(*ma, *mw, M, N, K, amap, epi, k_splits);
+    } else {
+        cudaLaunchConfig_t cfg{};
+        cfg.gridDim = dim3(2 * std::min(n_tiles, n_sms / 2));
+        cfg.blockDim = dim3(kTcThreads);
+        cfg.dynamicSmemBytes = S::kTotal;
+        cfg.stream = stream;
+        cudaLaunchAttribute attr[1];
+        attr[0].id = cudaLaunchAttributeClusterDimension;
+        attr[0].val.clusterDim.x = 2;
+        attr[0].val.clusterDim.y = 1;
+        attr[0].val.clusterDim.z = 1;
+        cfg.attrs = attr;
+        cfg.numAttrs = 1;
+        MRMT3_CUDA_TRY(cudaLaunchKernelEx(&cfg, kern, *ma, *mw, M, N, K, amap, epi, k_splits));
+    }
+    MRMT3_CHECK_LAUNCH();
+    return OkStatus();
+}
+
+// the pair kernel pays off when every pair has a full 256-row tile to work on
+inline bool tc_use_pair(int M) { return gemm_2cta_flag() != 0 && M >= 2 * kTcBM; }
 
 // a_rows: rows addressable through A (>= M; larger when amap gathers from a bigger tensor)
 template <int BN, class Epi>
 Status launch_gemm_tc_bn(TmaCache& tc, const CUtensorMap* ma, const bf16* W, int ldw, int M, int N, int K,
-                         ARowMap amap, const Epi& epi, int n_sms, cudaStream_t stream, int k_splits) {
+                         ARowMap amap, const Epi& epi, cudaStream_t stream, int k_splits) {
     const CUtensorMap* mw = nullptr;
+    if constexpr (BN >= 128) {
+        if (tc_use_pair(M)) {
+            const CUtensorMap a_copy = *ma;  // the lookup below may rotate the cache
+            MRMT3_TRY(tc.get(W, N, K, ldw, BN / 2, &mw));
+            return launch_gemm_tc_kernel<BN, Epi, 0, 2>(&a_copy, mw, M, N, K, amap, epi, stream, k_splits);
+        }
+    }
+    const CUtensorMap a_copy = *ma;
     MRMT3_TRY(tc.get(W, N, K, ldw, BN, &mw));
-    auto kern = gemm_tn_tcgen05_kernel<BN, Epi>;
-    MRMT3_TRY(ensure_dynamic_smem(kern, TcSmem<BN>::kTotal));
-    const int n_tiles = (N / BN) * ceil_div(M, kTcBM) * k_splits;
-    kern<<<std::min(n_tiles, n_sms), kTcThreads, TcSmem<BN>::kTotal, stream>>>(*ma, *mw, M, N, K, amap, epi, k_splits);
-    MRMT3_CHECK_LAUNCH();
-    return OkStatus();
+    return launch_gemm_tc_kernel<BN, Epi, 0, 1>(&a_copy, mw, M, N, K, amap, epi, stream, k_splits);
 }
 
-// D (M x N) = A^T B over R rows; A (R x M, pitch lda) and B (R x N, pitch ldb) row-major bf16.
+// D (M x N) = A^T B over R rows (MODE 1) or A B (MODE 2); B (R x N, pitch ldb) row-major bf16, MN-major
+// operand: the pair kernel needs whole 64-column boxes per CTA, i.e. BN = 256 or 128.
 // With k_splits > 1, split s stores its partial sums at rows [s*M, (s+1)*M) of the output.
-template <int BN, int MODE, class Epi>
-Status launch_gemm_tc_mn_bn(const CUtensorMap* ma, const CUtensorMap* mb, int M, int N, int R, const Epi& epi, int n_sms,
-                            cudaStream_t stream, int k_splits) {
-    auto kern = gemm_tn_tcgen05_kernel<BN, Epi, MODE>;
-    MRMT3_TRY(ensure_dynamic_smem(kern, TcSmem<BN>::kTotal));
-    const int n_tiles = (N / BN) * ceil_div(M, kTcBM) * k_splits;
-    kern<<<std::min(n_tiles, n_sms), kTcThreads, TcSmem<BN>::kTotal, stream>>>(*ma, *mb, M, N, R, ARowMap{nullptr, 1}, epi, k_splits);
-    MRMT3_CHECK_LAUNCH();
-    return OkStatus();
+template <int MODE, class Epi>
+Status launch_gemm_tc_mn_any(const CUtensorMap* ma, const CUtensorMap* mb, int M, int N, int R, const Epi& epi,
+                             cudaStream_t stream, int k_splits) {
+    const ARowMap none{nullptr, 1};
+    const bool pair = tc_use_pair(M);
+    if (N % 256 == 0)
+        return pair ? launch_gemm_tc_kernel<256, Epi, MODE, 2>(ma, mb, M, N, R, none, epi, stream, k_splits)
+                    : launch_gemm_tc_kernel<256, Epi, MODE, 1>(ma, mb, M, N, R, none, epi, stream, k_splits);
+    if (N % 192 == 0 && !pair) return launch_gemm_tc_kernel<192, Epi, MODE, 1>(ma, mb, M, N, R, none, epi, stream, k_splits);
+    if (N % 128 == 0)
+        return pair ? launch_gemm_tc_kernel<128, Epi, MODE, 2>(ma, mb, M, N, R, none, epi, stream, k_splits)
+                    : launch_gemm_tc_kernel<128, Epi, MODE, 1>(ma, mb, M, N, R, none, epi, stream, k_splits);
+    return launch_gemm_tc_kernel<64, Epi, MODE, 1>(ma, mb, M, N, R, none, epi, stream, k_splits);
 }
 
 template <class Epi>
@@ -346,21 +525,11 @@ Status launch_gemm_tc_mn(TmaCache& tc, const bf16* A, int lda, int M, const bf16
                          const Epi& epi, cudaStream_t stream, int k_splits = 1) {
     if (M <= 0 || R <= 0) return OkStatus();
     if (N % 64 != 0 || k_splits < 1) return Error(2, "gemm_tc_mn: N must be a multiple of 64");
-    static int n_sms = 0;
-    if (!n_sms) {
-        int dev = 0;
-        MRMT3_CUDA_TRY(cudaGetDevice(&dev));
-        MRMT3_CUDA_TRY(cudaDeviceGetAttribute(&n_sms, cudaDevAttrMultiProcessorCount, dev));
-    }
     const CUtensorMap *pa = nullptr, *mb = nullptr;
     MRMT3_TRY(tc.get(A, R, M, lda, 64, &pa));
     const CUtensorMap a_copy = *pa;  // the second lookup may evict the cache
-    const CUtensorMap* ma = &a_copy;
     MRMT3_TRY(tc.get(B, R, N, ldb, 64, &mb));
-    if (N % 256 == 0) return launch_gemm_tc_mn_bn<256, 1>(ma, mb, M, N, R, epi, n_sms, stream, k_splits);
-    if (N % 192 == 0) return launch_gemm_tc_mn_bn<192, 1>(ma, mb, M, N, R, epi, n_sms, stream, k_splits);
-    if (N % 128 == 0) return launch_gemm_tc_mn_bn<128, 1>(ma, mb, M, N, R, epi, n_sms, stream, k_splits);
-    return launch_gemm_tc_mn_bn<64, 1>(ma, mb, M, N, R, epi, n_sms, stream, k_splits);
+    return launch_gemm_tc_mn_any<1>(&a_copy, mb, M, N, R, epi, stream, k_splits);
 }
 
 // D (M x N) = A B; A (M x K, pitch lda) and B (K x N, pitch ldb) row-major bf16 (the data gradient
@@ -370,21 +539,11 @@ Status launch_gemm_tc_nn(TmaCache& tc, const bf16* A, int lda, int M, const bf16
                          const Epi& epi, cudaStream_t stream) {
     if (M <= 0 || K <= 0) return OkStatus();
     if (N % 64 != 0) return Error(2, "gemm_tc_nn: N must be a multiple of 64");
-    static int n_sms = 0;
-    if (!n_sms) {
-        int dev = 0;
-        MRMT3_CUDA_TRY(cudaGetDevice(&dev));
-        MRMT3_CUDA_TRY(cudaDeviceGetAttribute(&n_sms, cudaDevAttrMultiProcessorCount, dev));
-    }
     const CUtensorMap *pa = nullptr, *mb = nullptr;
     MRMT3_TRY(tc.get(A, M, K, lda, kTcBM, &pa));
     const CUtensorMap a_copy = *pa;
-    const CUtensorMap* ma = &a_copy;
     MRMT3_TRY(tc.get(B, K, N, ldb, 64, &mb));
-    if (N % 256 == 0) return launch_gemm_tc_mn_bn<256, 2>(ma, mb, M, N, K, epi, n_sms, stream, 1);
-    if (N % 192 == 0) return launch_gemm_tc_mn_bn<192, 2>(ma, mb, M, N, K, epi, n_sms, stream, 1);
-    if (N % 128 == 0) return launch_gemm_tc_mn_bn<128, 2>(ma, mb, M, N, K, epi, n_sms, stream, 1);
-    return launch_gemm_tc_mn_bn<64, 2>(ma, mb, M, N, K, epi, n_sms, stream, 1);
+    return launch_gemm_tc_mn_any<2>(&a_copy, mb, M, N, K, epi, stream, 1);
 }
 
 template <class Epi>
@@ -394,19 +553,13 @@ Status launch_gemm_tc(TmaCache& tc, const bf16* A, int lda, long a_rows, ARowMap
     if (K % kTcBK != 0 || N % 64 != 0) return Error(2, "gemm_tc: K and N must be multiples of 64");
     if (k_splits < 1 || (K / kTcBK) % k_splits != 0) return Error(2, "gemm_tc: k_splits must divide K / 64");
     if (amap.map && amap.block % kTcBM != 0) return Error(2, "gemm_tc: gather block must be a multiple of 128 rows");
-    static int n_sms = 0;
-    if (!n_sms) {
-        int dev = 0;
-        MRMT3_CUDA_TRY(cudaGetDevice(&dev));
-        MRMT3_CUDA_TRY(cudaDeviceGetAttribute(&n_sms, cudaDevAttrMultiProcessorCount, dev));
-    }
     const CUtensorMap* ma = nullptr;
     MRMT3_TRY(tc.get(A, a_rows, K, lda, kTcBM, &ma));
     // widest tile that divides N: wider tiles move fewer operand bytes per MAC through L2
-    if (N % 256 == 0) return launch_gemm_tc_bn<256>(tc, ma, W, ldw, M, N, K, amap, epi, n_sms, stream, k_splits);
-    if (N % 192 == 0) return launch_gemm_tc_bn<192>(tc, ma, W, ldw, M, N, K, amap, epi, n_sms, stream, k_splits);
-    if (N % 128 == 0) return launch_gemm_tc_bn<128>(tc, ma, W, ldw, M, N, K, amap, epi, n_sms, stream, k_splits);
-    return launch_gemm_tc_bn<64>(tc, ma, W, ldw, M, N, K, amap, epi, n_sms, stream, k_splits);
+    if (N % 256 == 0) return launch_gemm_tc_bn<256>(tc, ma, W, ldw, M, N, K, amap, epi, stream, k_splits);
+    if (N % 192 == 0) return launch_gemm_tc_bn<192>(tc, ma, W, ldw, M, N, K, amap, epi, stream, k_splits);
+    if (N % 128 == 0) return launch_gemm_tc_bn<128>(tc, ma, W, ldw, M, N, K, amap, epi, stream, k_splits);
+    return launch_gemm_tc_bn<64>(tc, ma, W, ldw, M, N, K, amap, epi, stream, k_splits);
 }
 
 }  // namespace mrmt3

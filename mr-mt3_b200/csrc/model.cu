@@ -206,6 +206,8 @@ static void destroy_graphs(mrmt3_handle* h) {
 
 void drop_graphs(mrmt3_handle* h) { destroy_graphs(h); }
 
+void gemm_set_2cta(int on) { gemm_configure_2cta(on); }
+
 Status test_gemm_train(mrmt3_handle* h, const bf16* A, const bf16* W, int M, int N, int K, float* C, int which,
                        cudaStream_t s);  // train.cu
 

@@ -15,6 +15,7 @@
 namespace mrmt3 {
 
 class TmaCache;  // gemm_tcgen05.cuh
+void gemm_set_2cta(int on);  // option gemm_2cta: CTA-pair tiles in the tcgen05 GEMM (-1 = library default)
 
 struct DeviceBuffer {
     void* p = nullptr;
