@@ -117,7 +117,9 @@ int mrmt3_trace_read(mrmt3_handle* h, uint64_t* out, int max_slots);
  * The two operand forms of the fine-tune backward, on ROW-major operands as they lie in memory:
  * which = 4: C (M,N) = A^T W with A (K,M), W (K,N) -- both MN-major, reduction over the K rows,
  * split-K chosen as the weight-gradient path chooses it; which = 5: C (M,N) = A W with A (M,K),
- * W (K,N) -- the data-gradient form (B operand MN-major).  Used by tests/test_kernels_gpu.py only. */
+ * W (K,N) -- the data-gradient form (B operand MN-major); which = 6: kernel 3 with the epilogue's
+ * global stores dropped (c is not written; measurement only).  Used by tests/test_kernels_gpu.py and
+ * scripts/gpu_gemm_2cta_check.py only. */
 int mrmt3_test_gemm(mrmt3_handle* h, const void* a_bf16, const void* w_bf16, int M, int N, int K,
                     float* c_f32, int which, void* stream);
 

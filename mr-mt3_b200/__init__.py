@@ -12,6 +12,9 @@ repository root.  Sub-modules mirror the reference's files for this path:
   notes.py, evaluate.py      <- token rows -> notes / MIDI, multi-instrument onset F1 (contrib/*, evaluate.py)
   audio.py                   <- WAV decode as librosa.load does it (test.py:36-40), pinned staging
   targets.py                 <- notes -> labels / targets_prev rows (dataset_2_random*.py, contrib encoders)
+  midi.py, dataset.py        <- Slakh stems (MIDI + inst_names.json + audio) -> training rows
+                                (dataset/dataset_2_random_segmem_prev.py); log-mel of a collated batch on the GPU
+  training.py                <- fine-tune step driver: bucketed gradient all-reduce overlapped with the backward
   sharding.py                <- track sharding across GPUs (no reference counterpart)
   _lib.py                    <- ctypes binding of the C-ABI library (include/mrmt3_b200.h)
   csrc/                      <- the CUDA kernels and the extern "C" boundary

@@ -179,7 +179,8 @@ class Engine:
     def test_gemm(self, a, w, which):
         """C = a @ w.T through GEMM kernel `which` (0 mma.sync, 1 tcgen05, 2 decode single-shot);
         which = 4: C = a.T @ w for a (K, M), w (K, N) (weight-gradient form, split-K);
-        which = 5: C = a @ w for a (M, K), w (K, N) (data-gradient form)."""
+        which = 5: C = a @ w for a (M, K), w (K, N) (data-gradient form);
+        which = 3 / 6: kernel 1 with the bf16 store epilogue / with the stores dropped (timing only)."""
         a = a.to(self.device, torch.bfloat16).contiguous()
         w = w.to(self.device, torch.bfloat16).contiguous()
         if which == 4:

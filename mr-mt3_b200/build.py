@@ -19,6 +19,7 @@ SOURCES = ["frontend.cu", "layers.cu", "attention.cu", "attention_tc.cu", "train
 NVCC = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
 FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
          "-Xcompiler", "-fPIC", "-Xcompiler", "-fvisibility=hidden", "--expt-relaxed-constexpr"]
+FLAGS += os.environ.get("MRMT3_NVCC_EXTRA", "").split()      # e.g. -DMRMT3_EPI_WIDE=0 for an A/B build
 
 
 def _newest_dep():

@@ -202,6 +202,143 @@ __device__ __forceinline__ void epi_store8(const EpiCrossKV& e, int row, int col
         make_uint4(pack_bf16(v[0], v[1]), pack_bf16(v[2], v[3]), pack_bf16(v[4], v[5]), pack_bf16(v[6], v[7]));
 }
 
+// ---- 16- and 32-wide epilogue stores: whole 32-byte sectors ----------------------------------------
+// A 16-byte store per thread reaches L2 as HALF a sector: the bf16 epilogue then issues two write
+// requests per sector and 2x the sector count on the L1 -> crossbar request path (ncu, round 2:
+// l1tex__m_l1tex2xbar_write_bytes = 302 MB for a 151 MB output; that path is 69 % busy and shared with the
+// TMA read requests).  sm_100 has 256-bit global accesses (STG.E.256), so a thread that owns 16 consecutive
+// bf16 (or 8 fp32) columns of a row writes a whole sector with one instruction.  MRMT3_EPI_WIDE=0 compiles
+// the 16-byte form back in for A/B runs.
+#ifndef MRMT3_EPI_WIDE
+#define MRMT3_EPI_WIDE 1
+#endif
+__device__ __forceinline__ void st_global_256(void* p, const uint32_t (&w)[8]) {
+    asm volatile("st.global.v8.b32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8};\n" ::"l"(p), "r"(w[0]), "r"(w[1]), "r"(w[2]), "r"(w[3]),
+                 "r"(w[4]), "r"(w[5]), "r"(w[6]), "r"(w[7])
+                 : "memory");
+}
+__device__ __forceinline__ void st_global_256f(void* p, const float* v) {
+    asm volatile("st.global.v8.f32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8};\n" ::"l"(p), "f"(v[0]), "f"(v[1]), "f"(v[2]), "f"(v[3]),
+                 "f"(v[4]), "f"(v[5]), "f"(v[6]), "f"(v[7])
+                 : "memory");
+}
+__device__ __forceinline__ void ld_global_256f(const void* p, float (&v)[8]) {
+    asm volatile("ld.global.v8.f32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];\n"
+                 : "=f"(v[0]), "=f"(v[1]), "=f"(v[2]), "=f"(v[3]), "=f"(v[4]), "=f"(v[5]), "=f"(v[6]), "=f"(v[7])
+                 : "l"(p));
+}
+// a (pointer, pitch in bytes) pair whose rows start on 32-byte boundaries
+__device__ __forceinline__ bool epi_wide_ok(const void* p, size_t pitch_bytes) {
+    return MRMT3_EPI_WIDE && ((reinterpret_cast<size_t>(p) | pitch_bytes) & 31) == 0;
+}
+
+// measurement only (mrmt3_test_gemm which = 6): the accumulator is read out of TMEM and dropped, which
+// separates the cost of the epilogue's global stores from the rest of the kernel
+struct EpiDiscard {
+    __device__ __forceinline__ void operator()(int, int, float, float) const {}
+};
+
+template <class Epi>
+__device__ __forceinline__ void epi_store16(const Epi& epi, int row, int col, const float (&v)[16]) {
+    epi_store8(epi, row, col, *reinterpret_cast<const float(*)[8]>(&v[0]));
+    epi_store8(epi, row, col + 8, *reinterpret_cast<const float(*)[8]>(&v[8]));
+}
+__device__ __forceinline__ void epi_store16(const EpiStoreBf16& e, int row, int col, const float (&v)[16]) {
+    if (!epi_wide_ok(e.C, (size_t)e.ldc * 2)) {
+        epi_store8(e, row, col, *reinterpret_cast<const float(*)[8]>(&v[0]));
+        epi_store8(e, row, col + 8, *reinterpret_cast<const float(*)[8]>(&v[8]));
+        return;
+    }
+    uint32_t w[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) w[j] = pack_bf16(v[2 * j], v[2 * j + 1]);
+    st_global_256(e.C + (size_t)row * e.ldc + col, w);
+}
+__device__ __forceinline__ void epi_store16(const EpiStoreF32& e, int row, int col, const float (&v)[16]) {
+    if (!epi_wide_ok(e.C, (size_t)e.ldc * 4)) {
+        epi_store8(e, row, col, *reinterpret_cast<const float(*)[8]>(&v[0]));
+        epi_store8(e, row, col + 8, *reinterpret_cast<const float(*)[8]>(&v[8]));
+        return;
+    }
+    float* p = e.C + (size_t)row * e.ldc + col;
+    st_global_256f(p, &v[0]);
+    st_global_256f(p + 8, &v[8]);
+}
+__device__ __forceinline__ void epi_store16(const EpiResidual& e, int row, int col, const float (&v)[16]) {
+    if (!epi_wide_ok(e.H, (size_t)e.ldh * 4)) {
+        epi_store8(e, row, col, *reinterpret_cast<const float(*)[8]>(&v[0]));
+        epi_store8(e, row, col + 8, *reinterpret_cast<const float(*)[8]>(&v[8]));
+        return;
+    }
+    float* p = e.H + (size_t)row * e.ldh + col;
+    float a[8], b[8];
+    ld_global_256f(p, a);
+    ld_global_256f(p + 8, b);
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+        a[j] += v[j];
+        b[j] += v[8 + j];
+    }
+    st_global_256f(p, a);
+    st_global_256f(p + 8, b);
+}
+__device__ __forceinline__ void epi_store16(const EpiPosAdd& e, int row, int col, const float (&v)[16]) {
+    if (!epi_wide_ok(e.H, (size_t)e.ldh * 4) || (reinterpret_cast<size_t>(e.pe) & 31) != 0) {
+        epi_store8(e, row, col, *reinterpret_cast<const float(*)[8]>(&v[0]));
+        epi_store8(e, row, col + 8, *reinterpret_cast<const float(*)[8]>(&v[8]));
+        return;
+    }
+    const float* q = e.pe + (size_t)(e.pos_offset + row % e.period) * e.ldh + col;
+    float* p = e.H + (size_t)row * e.ldh + col;
+    float a[8], b[8];
+    ld_global_256f(q, a);
+    ld_global_256f(q + 8, b);
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+        a[j] += v[j];
+        b[j] += v[8 + j];
+    }
+    st_global_256f(p, a);
+    st_global_256f(p + 8, b);
+}
+__device__ __forceinline__ void epi_store16(const EpiCrossKV& e, int row, int col, const float (&v)[16]) {
+    if (!epi_wide_ok(e.cache, 32)) {
+        epi_store8(e, row, col, *reinterpret_cast<const float(*)[8]>(&v[0]));
+        epi_store8(e, row, col + 8, *reinterpret_cast<const float(*)[8]>(&v[8]));
+        return;
+    }
+    int lane = row / e.rows_per_lane;
+    int t = row - lane * e.rows_per_lane + e.t_offset;
+    if (e.lane_map) lane = e.lane_map[lane];
+    int layer = col / (2 * kInner);
+    int r = col - layer * (2 * kInner);
+    int kv = r / kInner;
+    r -= kv * kInner;
+    size_t off = ((((size_t)lane * e.n_layers + layer) * 2 + kv) * kHeads + (r >> 6)) * e.tk_cap + t;
+    uint32_t w[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) w[j] = pack_bf16(v[2 * j], v[2 * j + 1]);
+    st_global_256(e.cache + off * kDKV + (r & 63), w);   // 16 columns never straddle a head (16 | 64)
+}
+
+template <class Epi>
+__device__ __forceinline__ void epi_store32(const Epi& epi, int row, int col, const float (&v)[32]) {
+    epi_store16(epi, row, col, *reinterpret_cast<const float(*)[16]>(&v[0]));
+    epi_store16(epi, row, col + 16, *reinterpret_cast<const float(*)[16]>(&v[16]));
+}
+// gated-GELU halves the width: 32 accumulator columns -> 16 bf16 = one sector
+__device__ __forceinline__ void epi_store32(const EpiGatedGelu& e, int row, int col, const float (&v)[32]) {
+    if (!epi_wide_ok(e.C, (size_t)e.ldc * 2)) {
+#pragma unroll
+        for (int j = 0; j < 4; ++j) epi_store8(e, row, col + 8 * j, *reinterpret_cast<const float(*)[8]>(&v[8 * j]));
+        return;
+    }
+    uint32_t w[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) w[j] = pack_bf16(gelu_new(v[4 * j]) * v[4 * j + 1], gelu_new(v[4 * j + 2]) * v[4 * j + 3]);
+    st_global_256(e.C + (size_t)row * e.ldc + (col >> 1), w);
+}
+
 // NCTA = 2: the CTA pair computes a 256 x BN tile; each CTA stages its 128 rows of A and BN / 2 rows of W
 template <int BN, int NCTA = 1>
 struct TcSmem {
@@ -402,13 +539,10 @@ __global__ void __launch_bounds__(kTcThreads, 1)
                 uint32_t v[32];
                 tc_ld_32x32(tacc + (uint32_t)(c * 32), v);
                 if (row < M) {
+                    float f[32];
 #pragma unroll
-                    for (int j = 0; j < 4; ++j) {
-                        float f[8];
-#pragma unroll
-                        for (int e = 0; e < 8; ++e) f[e] = __uint_as_float(v[8 * j + e]);
-                        epi_store8(epi, out_row0 + row, n0 + c * 32 + 8 * j, f);
-                    }
+                    for (int e = 0; e < 32; ++e) f[e] = __uint_as_float(v[e]);
+                    epi_store32(epi, out_row0 + row, n0 + c * 32, f);
                 }
             }
             tc_fence_before();

@@ -220,6 +220,8 @@ Status test_gemm(mrmt3_handle* h, const bf16* A, const bf16* W, int M, int N, in
     if (which == 1) return launch_gemm_tc(*h->tma, A, K, M, id, W, K, M, N, K, EpiStoreF32{C, N}, s);
     if (which == 3)  // tcgen05 with the bf16 store epilogue the encoder uses (C holds M*N bf16)
         return launch_gemm_tc(*h->tma, A, K, M, id, W, K, M, N, K, EpiStoreBf16{reinterpret_cast<bf16*>(C), N}, s);
+    if (which == 6)  // measurement: the same kernel with the epilogue's stores dropped (C is not written)
+        return launch_gemm_tc(*h->tma, A, K, M, id, W, K, M, N, K, EpiDiscard{}, s);
     if (which == 2) {
         if (K == 384) return launch_gemm_skinny<32, 384, false>(*h->tma, A, K, W, K, M, N, 0.f, EpiStoreF32{C, N}, s);
         if (K == 512) return launch_gemm_skinny<32, 512, false>(*h->tma, A, K, W, K, M, N, 0.f, EpiStoreF32{C, N}, s);

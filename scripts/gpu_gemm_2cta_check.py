@@ -64,6 +64,9 @@ def child_bench():
             eng.set_option("gemm_2cta", flag)
             ms = timed(lambda: eng.test_gemm(a, w, 3))
             row[tag + "_tflops"] = round(2.0 * M * N * K / ms / 1e9, 1)
+        for flag, tag in ((0, "single_nostore"), (1, "pair_nostore")):   # which = 6: accumulator read, stores dropped
+            eng.set_option("gemm_2cta", flag)
+            row[tag + "_tflops"] = round(2.0 * M * N * K / timed(lambda: eng.test_gemm(a, w, 6)) / 1e9, 1)
         row["cublas_tflops"] = round(2.0 * M * N * K / timed(lambda: torch.matmul(a, w.T)) / 1e9, 1)
         print(json.dumps(row), flush=True)
     # fine-tune forms at batch 32 x 1024 rows: dgrad (A B) and wgrad (A^T B over 32768 rows)
@@ -75,14 +78,6 @@ def child_bench():
             eng.set_option("gemm_2cta", flag)
             row[tag + "_tflops"] = round(2.0 * R * N2 * M2 / timed(lambda: eng.test_gemm(a, w, 5)) / 1e9, 1)
         row["cublas_tflops"] = round(2.0 * R * N2 * M2 / timed(lambda: torch.matmul(a, w)) / 1e9, 1)
-        print(json.dumps(row), flush=True)
-    for (M2, N2, name) in [(512, 1152, "dW qkv"), (512, 2048, "dW wi"), (1024, 512, "dW wff"), (512, 1536, "dW lm_head")]:
-        a = torch.randn((R, M2), device="cuda").bfloat16(); w = torch.randn((R, N2), device="cuda").bfloat16()
-        row = {"form": "A^T B (wgrad, split-K)", "shape": f"{M2}x{N2}x{R}", "name": name}
-        for flag, tag in ((0, "single"), (1, "pair")):
-            eng.set_option("gemm_2cta", flag)
-            row[tag + "_tflops"] = round(2.0 * R * N2 * M2 / timed(lambda: eng.test_gemm(a, w, 4)) / 1e9, 1)
-        row["cublas_tflops"] = round(2.0 * R * N2 * M2 / timed(lambda: torch.matmul(a.T, w)) / 1e9, 1)
         print(json.dumps(row), flush=True)
     sys.exit(0)
 
