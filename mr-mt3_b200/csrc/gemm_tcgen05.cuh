@@ -153,64 +153,20 @@ __host__ __device__ constexpr uint32_t tc_idesc(int bn, bool a_mn = false, bool 
            ((uint32_t)(bn >> 3) << 17) | ((uint32_t)(bm >> 4) << 24);
 }
 
-// ---- 8-wide epilogue stores --------------------------------------------------------------------
-// An epilogue thread owns one output row and walks its columns, so it can store 8 consecutive
-// columns with one or two 16-byte transactions instead of four 4/8-byte ones.  Generic fallback:
-// the pairwise functor interface of gemm_mma.cuh.
-template <class Epi>
-__device__ __forceinline__ void epi_store8(const Epi& epi, int row, int col, const float (&v)[8]) {
-#pragma unroll
-    for (int j = 0; j < 4; ++j) epi(row, col + 2 * j, v[2 * j], v[2 * j + 1]);
-}
-__device__ __forceinline__ void epi_store8(const EpiStoreBf16& e, int row, int col, const float (&v)[8]) {
-    *reinterpret_cast<uint4*>(e.C + (size_t)row * e.ldc + col) =
-        make_uint4(pack_bf16(v[0], v[1]), pack_bf16(v[2], v[3]), pack_bf16(v[4], v[5]), pack_bf16(v[6], v[7]));
-}
-__device__ __forceinline__ void epi_store8(const EpiStoreF32& e, int row, int col, const float (&v)[8]) {
-    float4* p = reinterpret_cast<float4*>(e.C + (size_t)row * e.ldc + col);
-    p[0] = make_float4(v[0], v[1], v[2], v[3]);
-    p[1] = make_float4(v[4], v[5], v[6], v[7]);
-}
-__device__ __forceinline__ void epi_store8(const EpiResidual& e, int row, int col, const float (&v)[8]) {
-    float4* p = reinterpret_cast<float4*>(e.H + (size_t)row * e.ldh + col);
-    float4 a = p[0], b = p[1];
-    p[0] = make_float4(a.x + v[0], a.y + v[1], a.z + v[2], a.w + v[3]);
-    p[1] = make_float4(b.x + v[4], b.y + v[5], b.z + v[6], b.w + v[7]);
-}
-__device__ __forceinline__ void epi_store8(const EpiPosAdd& e, int row, int col, const float (&v)[8]) {
-    const float4* q = reinterpret_cast<const float4*>(e.pe + (size_t)(e.pos_offset + row % e.period) * e.ldh + col);
-    const float4 a = q[0], b = q[1];
-    float4* p = reinterpret_cast<float4*>(e.H + (size_t)row * e.ldh + col);
-    p[0] = make_float4(a.x + v[0], a.y + v[1], a.z + v[2], a.w + v[3]);
-    p[1] = make_float4(b.x + v[4], b.y + v[5], b.z + v[6], b.w + v[7]);
-}
-__device__ __forceinline__ void epi_store8(const EpiGatedGelu& e, int row, int col, const float (&v)[8]) {
-    *reinterpret_cast<uint2*>(e.C + (size_t)row * e.ldc + (col >> 1)) =
-        make_uint2(pack_bf16(gelu_new(v[0]) * v[1], gelu_new(v[2]) * v[3]),
-                   pack_bf16(gelu_new(v[4]) * v[5], gelu_new(v[6]) * v[7]));
-}
-__device__ __forceinline__ void epi_store8(const EpiCrossKV& e, int row, int col, const float (&v)[8]) {
-    int lane = row / e.rows_per_lane;
-    int t = row - lane * e.rows_per_lane + e.t_offset;
-    if (e.lane_map) lane = e.lane_map[lane];
-    int layer = col / (2 * kInner);
-    int r = col - layer * (2 * kInner);
-    int kv = r / kInner;
-    r -= kv * kInner;
-    size_t off = ((((size_t)lane * e.n_layers + layer) * 2 + kv) * kHeads + (r >> 6)) * e.tk_cap + t;
-    *reinterpret_cast<uint4*>(e.cache + off * kDKV + (r & 63)) =
-        make_uint4(pack_bf16(v[0], v[1]), pack_bf16(v[2], v[3]), pack_bf16(v[4], v[5]), pack_bf16(v[6], v[7]));
-}
-
-// ---- 16- and 32-wide epilogue stores: whole 32-byte sectors ----------------------------------------
-// A 16-byte store per thread reaches L2 as HALF a sector: the bf16 epilogue then issues two write
-// requests per sector and 2x the sector count on the L1 -> crossbar request path (ncu, round 2:
-// l1tex__m_l1tex2xbar_write_bytes = 302 MB for a 151 MB output; that path is 69 % busy and shared with the
-// TMA read requests).  sm_100 has 256-bit global accesses (STG.E.256), so a thread that owns 16 consecutive
-// bf16 (or 8 fp32) columns of a row writes a whole sector with one instruction.  MRMT3_EPI_WIDE=0 compiles
-// the 16-byte form back in for A/B runs.
+// ---- epilogue stores: whole sectors, whole lines -----------------------------------------------------
+// Measured (round 2, profiles/r2q_*): with the epilogue's global stores dropped the kernel runs at
+// 1.2-1.64 PFLOP/s on the encoder shapes; with them, 0.66-1.05.  The mainloop was never the limit: the
+// store path was.  An epilogue thread owns one accumulator ROW (that is how tcgen05.ld hands out TMEM
+// lanes), so a warp-wide store touches 32 different rows:
+//   MRMT3_EPI_WIDE=0  16-byte stores: HALF a sector each, two L2 write requests per sector
+//                     (l1tex__m_l1tex2xbar_write_bytes = 302 MB for a 151 MB output)           0.66-1.05 PFLOP/s
+//   MRMT3_EPI_WIDE=1  256-bit stores (STG.E.256): one whole sector per thread per instruction,
+//                     still 32 lines per instruction                                           0.78-1.12
+//   MRMT3_EPI_WIDE=2  (default) the warp first transposes its 32 x 64 block through a private, swizzled
+//                     shared-memory tile, so that the threads of a store instruction cover whole
+//                     128-byte lines of 4-16 rows (and the residual epilogues READ the same way)
 #ifndef MRMT3_EPI_WIDE
-#define MRMT3_EPI_WIDE 1
+#define MRMT3_EPI_WIDE 2
 #endif
 __device__ __forceinline__ void st_global_256(void* p, const uint32_t (&w)[8]) {
     asm volatile("st.global.v8.b32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8};\n" ::"l"(p), "r"(w[0]), "r"(w[1]), "r"(w[2]), "r"(w[3]),
@@ -230,6 +186,79 @@ __device__ __forceinline__ void ld_global_256f(const void* p, float (&v)[8]) {
 // a (pointer, pitch in bytes) pair whose rows start on 32-byte boundaries
 __device__ __forceinline__ bool epi_wide_ok(const void* p, size_t pitch_bytes) {
     return MRMT3_EPI_WIDE && ((reinterpret_cast<size_t>(p) | pitch_bytes) & 31) == 0;
+}
+
+// ---- 8-wide epilogue stores --------------------------------------------------------------------
+// An epilogue thread owns one output row and walks its columns, so it can store 8 consecutive
+// columns with one or two 16-byte transactions instead of four 4/8-byte ones.  Generic fallback:
+// the pairwise functor interface of gemm_mma.cuh.
+template <class Epi>
+__device__ __forceinline__ void epi_store8(const Epi& epi, int row, int col, const float (&v)[8]) {
+#pragma unroll
+    for (int j = 0; j < 4; ++j) epi(row, col + 2 * j, v[2 * j], v[2 * j + 1]);
+}
+__device__ __forceinline__ void epi_store8(const EpiStoreBf16& e, int row, int col, const float (&v)[8]) {
+    *reinterpret_cast<uint4*>(e.C + (size_t)row * e.ldc + col) =
+        make_uint4(pack_bf16(v[0], v[1]), pack_bf16(v[2], v[3]), pack_bf16(v[4], v[5]), pack_bf16(v[6], v[7]));
+}
+__device__ __forceinline__ void epi_store8(const EpiStoreF32& e, int row, int col, const float (&v)[8]) {
+    float* c = e.C + (size_t)row * e.ldc + col;
+    if (epi_wide_ok(e.C, (size_t)e.ldc * 4)) {
+        st_global_256f(c, v);
+        return;
+    }
+    float4* p = reinterpret_cast<float4*>(c);
+    p[0] = make_float4(v[0], v[1], v[2], v[3]);
+    p[1] = make_float4(v[4], v[5], v[6], v[7]);
+}
+__device__ __forceinline__ void epi_store8(const EpiResidual& e, int row, int col, const float (&v)[8]) {
+    float* h = e.H + (size_t)row * e.ldh + col;
+    if (epi_wide_ok(e.H, (size_t)e.ldh * 4)) {
+        float a[8];
+        ld_global_256f(h, a);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) a[j] += v[j];
+        st_global_256f(h, a);
+        return;
+    }
+    float4* p = reinterpret_cast<float4*>(h);
+    float4 a = p[0], b = p[1];
+    p[0] = make_float4(a.x + v[0], a.y + v[1], a.z + v[2], a.w + v[3]);
+    p[1] = make_float4(b.x + v[4], b.y + v[5], b.z + v[6], b.w + v[7]);
+}
+__device__ __forceinline__ void epi_store8(const EpiPosAdd& e, int row, int col, const float (&v)[8]) {
+    const float* pe = e.pe + (size_t)(e.pos_offset + row % e.period) * e.ldh + col;
+    float* h = e.H + (size_t)row * e.ldh + col;
+    if (epi_wide_ok(e.H, (size_t)e.ldh * 4) && (reinterpret_cast<size_t>(e.pe) & 31) == 0) {
+        float a[8];
+        ld_global_256f(pe, a);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) a[j] += v[j];
+        st_global_256f(h, a);
+        return;
+    }
+    const float4* q = reinterpret_cast<const float4*>(pe);
+    const float4 a = q[0], b = q[1];
+    float4* p = reinterpret_cast<float4*>(h);
+    p[0] = make_float4(a.x + v[0], a.y + v[1], a.z + v[2], a.w + v[3]);
+    p[1] = make_float4(b.x + v[4], b.y + v[5], b.z + v[6], b.w + v[7]);
+}
+__device__ __forceinline__ void epi_store8(const EpiGatedGelu& e, int row, int col, const float (&v)[8]) {
+    *reinterpret_cast<uint2*>(e.C + (size_t)row * e.ldc + (col >> 1)) =
+        make_uint2(pack_bf16(gelu_new(v[0]) * v[1], gelu_new(v[2]) * v[3]),
+                   pack_bf16(gelu_new(v[4]) * v[5], gelu_new(v[6]) * v[7]));
+}
+__device__ __forceinline__ void epi_store8(const EpiCrossKV& e, int row, int col, const float (&v)[8]) {
+    int lane = row / e.rows_per_lane;
+    int t = row - lane * e.rows_per_lane + e.t_offset;
+    if (e.lane_map) lane = e.lane_map[lane];
+    int layer = col / (2 * kInner);
+    int r = col - layer * (2 * kInner);
+    int kv = r / kInner;
+    r -= kv * kInner;
+    size_t off = ((((size_t)lane * e.n_layers + layer) * 2 + kv) * kHeads + (r >> 6)) * e.tk_cap + t;
+    *reinterpret_cast<uint4*>(e.cache + off * kDKV + (r & 63)) =
+        make_uint4(pack_bf16(v[0], v[1]), pack_bf16(v[2], v[3]), pack_bf16(v[4], v[5]), pack_bf16(v[6], v[7]));
 }
 
 // measurement only (mrmt3_test_gemm which = 6): the accumulator is read out of TMEM and dropped, which
@@ -253,53 +282,6 @@ __device__ __forceinline__ void epi_store16(const EpiStoreBf16& e, int row, int 
 #pragma unroll
     for (int j = 0; j < 8; ++j) w[j] = pack_bf16(v[2 * j], v[2 * j + 1]);
     st_global_256(e.C + (size_t)row * e.ldc + col, w);
-}
-__device__ __forceinline__ void epi_store16(const EpiStoreF32& e, int row, int col, const float (&v)[16]) {
-    if (!epi_wide_ok(e.C, (size_t)e.ldc * 4)) {
-        epi_store8(e, row, col, *reinterpret_cast<const float(*)[8]>(&v[0]));
-        epi_store8(e, row, col + 8, *reinterpret_cast<const float(*)[8]>(&v[8]));
-        return;
-    }
-    float* p = e.C + (size_t)row * e.ldc + col;
-    st_global_256f(p, &v[0]);
-    st_global_256f(p + 8, &v[8]);
-}
-__device__ __forceinline__ void epi_store16(const EpiResidual& e, int row, int col, const float (&v)[16]) {
-    if (!epi_wide_ok(e.H, (size_t)e.ldh * 4)) {
-        epi_store8(e, row, col, *reinterpret_cast<const float(*)[8]>(&v[0]));
-        epi_store8(e, row, col + 8, *reinterpret_cast<const float(*)[8]>(&v[8]));
-        return;
-    }
-    float* p = e.H + (size_t)row * e.ldh + col;
-    float a[8], b[8];
-    ld_global_256f(p, a);
-    ld_global_256f(p + 8, b);
-#pragma unroll
-    for (int j = 0; j < 8; ++j) {
-        a[j] += v[j];
-        b[j] += v[8 + j];
-    }
-    st_global_256f(p, a);
-    st_global_256f(p + 8, b);
-}
-__device__ __forceinline__ void epi_store16(const EpiPosAdd& e, int row, int col, const float (&v)[16]) {
-    if (!epi_wide_ok(e.H, (size_t)e.ldh * 4) || (reinterpret_cast<size_t>(e.pe) & 31) != 0) {
-        epi_store8(e, row, col, *reinterpret_cast<const float(*)[8]>(&v[0]));
-        epi_store8(e, row, col + 8, *reinterpret_cast<const float(*)[8]>(&v[8]));
-        return;
-    }
-    const float* q = e.pe + (size_t)(e.pos_offset + row % e.period) * e.ldh + col;
-    float* p = e.H + (size_t)row * e.ldh + col;
-    float a[8], b[8];
-    ld_global_256f(q, a);
-    ld_global_256f(q + 8, b);
-#pragma unroll
-    for (int j = 0; j < 8; ++j) {
-        a[j] += v[j];
-        b[j] += v[8 + j];
-    }
-    st_global_256f(p, a);
-    st_global_256f(p + 8, b);
 }
 __device__ __forceinline__ void epi_store16(const EpiCrossKV& e, int row, int col, const float (&v)[16]) {
     if (!epi_wide_ok(e.cache, 32)) {
@@ -339,15 +321,31 @@ __device__ __forceinline__ void epi_store32(const EpiGatedGelu& e, int row, int 
     st_global_256(e.C + (size_t)row * e.ldc + (col >> 1), w);
 }
 
+// accumulator columns one thread hands to the functor at a time in the line-coalesced epilogue: 32 bytes
+// of OUTPUT per thread (8 fp32, 16 bf16, 32 accumulator columns for the gated-GELU's 16 bf16)
+template <class Epi> struct EpiWidth { static constexpr int value = 8; };
+template <> struct EpiWidth<EpiStoreBf16> { static constexpr int value = 16; };
+template <> struct EpiWidth<EpiCrossKV> { static constexpr int value = 16; };
+template <> struct EpiWidth<EpiGatedGelu> { static constexpr int value = 32; };
+template <class Epi, int W>
+__device__ __forceinline__ void epi_emit(const Epi& epi, int row, int col, const float (&v)[W]) {
+    if constexpr (W == 8) epi_store8(epi, row, col, v);
+    else if constexpr (W == 16) epi_store16(epi, row, col, v);
+    else epi_store32(epi, row, col, v);
+}
+
 // NCTA = 2: the CTA pair computes a 256 x BN tile; each CTA stages its 128 rows of A and BN / 2 rows of W
 template <int BN, int NCTA = 1>
 struct TcSmem {
-    static constexpr int kStages = NCTA == 2 ? (BN > 192 ? 6 : BN > 128 ? 7 : 8) : (BN > 128 ? 4 : 6);
+    static constexpr int kStages = NCTA == 2 ? (BN > 128 ? 6 : 8) : (BN > 128 ? 4 : 6);
     static constexpr int kABytes = kTcBM * kTcBK * 2;
     static constexpr int kWBytes = BN / NCTA * kTcBK * 2;
     static constexpr int kStageBytes = kABytes + kWBytes;
-    static constexpr int kBarOffset = kStages * kStageBytes;
+    static constexpr int kEpiOffset = kStages * kStageBytes;     // 4 epilogue warps x (32 rows x 64 fp32) transpose tiles
+    static constexpr int kEpiBytes = MRMT3_EPI_WIDE >= 2 ? 4 * 32 * 64 * 4 : 0;
+    static constexpr int kBarOffset = kEpiOffset + kEpiBytes;
     static constexpr int kTotal = kBarOffset + 256 + 1024;  // barriers + slack for 1024-B alignment
+    static_assert(kTotal <= 227 * 1024, "shared memory budget");
     static constexpr int kAccCols = BN > 128 ? 256 : 128;   // TMEM columns per accumulator buffer
     static constexpr int kTmemCols = 2 * kAccCols;          // double-buffered accumulator
 };
@@ -534,6 +532,44 @@ __global__ void __launch_bounds__(kTcThreads, 1)
             tc_fence_after();
             const int row = m0 + quarter * 32 + lane;
             const uint32_t tacc = tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(buf * S::kAccCols);
+#if MRMT3_EPI_WIDE >= 2
+            // 64 accumulator columns at a time: row-per-thread out of TMEM into the warp's swizzled tile
+            // (16-byte unit u of row r at unit (u & 8) | ((u & 7) ^ (r & 7)): conflict-free both ways), then
+            // W columns per thread with the threads of an instruction side by side along the row
+            constexpr int W = EpiWidth<Epi>::value, kPieces = 64 / W, kRowsPerInstr = 32 / kPieces;
+            float* tile = reinterpret_cast<float*>(base_ptr + S::kEpiOffset) + quarter * (32 * 64);
+            const int piece = lane % kPieces, rsub = lane / kPieces;
+#pragma unroll 1
+            for (int c = 0; c < BN / 64; ++c) {
+#pragma unroll
+                for (int h = 0; h < 2; ++h) {
+                    uint32_t v[32];
+                    tc_ld_32x32(tacc + (uint32_t)(c * 64 + h * 32), v);
+#pragma unroll
+                    for (int k = 0; k < 8; ++k)
+                        *reinterpret_cast<uint4*>(tile + lane * 64 + h * 32 + ((k ^ (lane & 7)) << 2)) =
+                            make_uint4(v[4 * k], v[4 * k + 1], v[4 * k + 2], v[4 * k + 3]);
+                }
+                __syncwarp();
+#pragma unroll
+                for (int i = 0; i < kPieces; ++i) {
+                    const int r = rsub + kRowsPerInstr * i;
+                    float f[W];
+#pragma unroll
+                    for (int j = 0; j < W / 4; ++j) {
+                        const int u = piece * (W / 4) + j;
+                        const float4 x = *reinterpret_cast<const float4*>(tile + r * 64 + ((u & 8) << 2) + (((u & 7) ^ (r & 7)) << 2));
+                        f[4 * j] = x.x;
+                        f[4 * j + 1] = x.y;
+                        f[4 * j + 2] = x.z;
+                        f[4 * j + 3] = x.w;
+                    }
+                    const int orow = m0 + quarter * 32 + r;
+                    if (orow < M) epi_emit<Epi, W>(epi, out_row0 + orow, n0 + c * 64 + piece * W, f);
+                }
+                __syncwarp();
+            }
+#else
 #pragma unroll 1
             for (int c = 0; c < BN / 32; ++c) {
                 uint32_t v[32];
@@ -545,6 +581,7 @@ __global__ void __launch_bounds__(kTcThreads, 1)
                     epi_store32(epi, out_row0 + row, n0 + c * 32, f);
                 }
             }
+#endif
             tc_fence_before();
             if constexpr (kPair) mbar_arrive_cluster(mapa_shared(bar_acc_empty + buf * 8, 0));
             else mbar_arrive(bar_acc_empty + buf * 8);

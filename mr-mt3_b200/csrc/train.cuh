@@ -63,7 +63,7 @@ struct AttnBwdParams {
 // row*ld + col.  Out of place, so that the sublayer's input stays behind as the activation the
 // backward needs (no snapshot copy of the residual stream); drop may be off.
 #ifndef MRMT3_EPI_WIDE
-#define MRMT3_EPI_WIDE 1
+#define MRMT3_EPI_WIDE 2
 #endif
 struct EpiResidualTo {
     const float* Hin;
@@ -88,47 +88,28 @@ __device__ __forceinline__ void epi_store8(const EpiResidualTo& e, int row, int 
         drop_factor4(e.drop, g, f0);
         drop_factor4(e.drop, g + 1, f1);
     }
-    const float4* p = reinterpret_cast<const float4*>(e.Hin + (size_t)row * e.ldh + col);
-    float4* q = reinterpret_cast<float4*>(e.Hout + (size_t)row * e.ldh + col);
+    const float* hin = e.Hin + (size_t)row * e.ldh + col;
+    float* hout = e.Hout + (size_t)row * e.ldh + col;
+    if (MRMT3_EPI_WIDE && ((reinterpret_cast<size_t>(e.Hin) | reinterpret_cast<size_t>(e.Hout) | ((size_t)e.ldh * 4)) & 31) == 0) {
+        float a[8];   // one whole 32-byte sector per access (STG.E.256 / LDG.E.256), see gemm_tcgen05.cuh
+        asm volatile("ld.global.v8.f32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];\n"
+                     : "=f"(a[0]), "=f"(a[1]), "=f"(a[2]), "=f"(a[3]), "=f"(a[4]), "=f"(a[5]), "=f"(a[6]), "=f"(a[7])
+                     : "l"(hin));
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            a[j] += v[j] * f0[j];
+            a[4 + j] += v[4 + j] * f1[j];
+        }
+        asm volatile("st.global.v8.f32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8};\n" ::"l"(hout), "f"(a[0]), "f"(a[1]), "f"(a[2]),
+                     "f"(a[3]), "f"(a[4]), "f"(a[5]), "f"(a[6]), "f"(a[7])
+                     : "memory");
+        return;
+    }
+    const float4* p = reinterpret_cast<const float4*>(hin);
+    float4* q = reinterpret_cast<float4*>(hout);
     const float4 a = p[0], b = p[1];
     q[0] = make_float4(a.x + v[0] * f0[0], a.y + v[1] * f0[1], a.z + v[2] * f0[2], a.w + v[3] * f0[3]);
     q[1] = make_float4(b.x + v[4] * f1[0], b.y + v[5] * f1[1], b.z + v[6] * f1[2], b.w + v[7] * f1[3]);
-}
-// 16 columns: whole 32-byte sectors (see gemm_tcgen05.cuh)
-__device__ __forceinline__ void epi_store16(const EpiResidualTo& e, int row, int col, const float (&v)[16]) {
-    if (!(MRMT3_EPI_WIDE && ((reinterpret_cast<size_t>(e.Hin) | reinterpret_cast<size_t>(e.Hout) | ((size_t)e.ldh * 4)) & 31) == 0)) {
-        epi_store8(e, row, col, *reinterpret_cast<const float(*)[8]>(&v[0]));
-        epi_store8(e, row, col + 8, *reinterpret_cast<const float(*)[8]>(&v[8]));
-        return;
-    }
-    float f[16];
-#pragma unroll
-    for (int j = 0; j < 16; ++j) f[j] = 1.f;
-    if (e.drop.on()) {
-        const unsigned long long g = ((unsigned long long)row * e.ldh + col) >> 2;
-#pragma unroll
-        for (int j = 0; j < 4; ++j) drop_factor4(e.drop, g + j, *reinterpret_cast<float(*)[4]>(&f[4 * j]));
-    }
-    const float* p = e.Hin + (size_t)row * e.ldh + col;
-    float* q = e.Hout + (size_t)row * e.ldh + col;
-    float a[8], b[8];
-    asm volatile("ld.global.v8.f32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];\n"
-                 : "=f"(a[0]), "=f"(a[1]), "=f"(a[2]), "=f"(a[3]), "=f"(a[4]), "=f"(a[5]), "=f"(a[6]), "=f"(a[7])
-                 : "l"(p));
-    asm volatile("ld.global.v8.f32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];\n"
-                 : "=f"(b[0]), "=f"(b[1]), "=f"(b[2]), "=f"(b[3]), "=f"(b[4]), "=f"(b[5]), "=f"(b[6]), "=f"(b[7])
-                 : "l"(p + 8));
-#pragma unroll
-    for (int j = 0; j < 8; ++j) {
-        a[j] += v[j] * f[j];
-        b[j] += v[8 + j] * f[8 + j];
-    }
-    asm volatile("st.global.v8.f32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8};\n" ::"l"(q), "f"(a[0]), "f"(a[1]), "f"(a[2]), "f"(a[3]),
-                 "f"(a[4]), "f"(a[5]), "f"(a[6]), "f"(a[7])
-                 : "memory");
-    asm volatile("st.global.v8.f32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8};\n" ::"l"(q + 8), "f"(b[0]), "f"(b[1]), "f"(b[2]), "f"(b[3]),
-                 "f"(b[4]), "f"(b[5]), "f"(b[6]), "f"(b[7])
-                 : "memory");
 }
 Status launch_attn_bwd(const AttnBwdParams& p, int batch, cudaStream_t s);
 
