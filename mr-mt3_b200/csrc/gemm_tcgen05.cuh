@@ -90,8 +90,12 @@ __device__ __forceinline__ uint32_t mapa_shared(uint32_t addr, uint32_t rank) {
     asm volatile("mapa.shared::cluster.u32 %0, %1, %2;\n" : "=r"(r) : "r"(addr), "r"(rank));
     return r;
 }
+// Remote arrive on a barrier of the pair's even CTA.  NOT `.release.cluster`: that form makes the thread
+// wait until its earlier global stores are visible cluster-wide (ERRBAR + membar: 21 % of the pair kernel's
+// stall samples in profiles/r2s_gemm_pair_stalls.txt), and nothing is published through memory here --
+// the TMEM reads it orders are complete (tcgen05.wait::ld) and fenced (tcgen05.fence::before_thread_sync).
 __device__ __forceinline__ void mbar_arrive_cluster(uint32_t bar_cluster) {
-    asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];\n" ::"r"(bar_cluster) : "memory");
+    asm volatile("mbarrier.arrive.shared::cluster.b64 _, [%0];\n" ::"r"(bar_cluster) : "memory");
 }
 // wait with cluster-scope acquire: the arrivals come from the other CTA of the pair
 __device__ __forceinline__ void mbar_wait_cluster(uint32_t bar, uint32_t parity) {
@@ -160,13 +164,18 @@ __host__ __device__ constexpr uint32_t tc_idesc(int bn, bool a_mn = false, bool 
 // lanes), so a warp-wide store touches 32 different rows:
 //   MRMT3_EPI_WIDE=0  16-byte stores: HALF a sector each, two L2 write requests per sector
 //                     (l1tex__m_l1tex2xbar_write_bytes = 302 MB for a 151 MB output)           0.66-1.05 PFLOP/s
-//   MRMT3_EPI_WIDE=1  256-bit stores (STG.E.256): one whole sector per thread per instruction,
+//   MRMT3_EPI_WIDE=1  (default) 256-bit stores (STG.E.256): one whole sector per thread per instruction,
 //                     still 32 lines per instruction                                           0.78-1.12
-//   MRMT3_EPI_WIDE=2  (default) the warp first transposes its 32 x 64 block through a private, swizzled
+//   MRMT3_EPI_WIDE=2  the warp first transposes its 32 x 64 block through a private, swizzled
 //                     shared-memory tile, so that the threads of a store instruction cover whole
-//                     128-byte lines of 4-16 rows (and the residual epilogues READ the same way)
+//                     128-byte lines of 4-16 rows: no better for bf16 outputs (0.72-1.12), +15-30 % on
+//                     fp32-output test shapes, and the fine-tune forward got SLOWER (8.7 -> 10.2 ms:
+//                     the tile round trip lengthens every epilogue) -- kept as a compile-time option.
+// What the three have in common: the extra time over the store-less kernel is ~ output bytes / (32 B per
+// clock per SM) -- the L1 -> crossbar port, one sector-sized packet per cycle, shared with the TMA read
+// requests (l1tex__m_l1tex2xbar_req_cycles_active 59-69 %).
 #ifndef MRMT3_EPI_WIDE
-#define MRMT3_EPI_WIDE 2
+#define MRMT3_EPI_WIDE 1
 #endif
 __device__ __forceinline__ void st_global_256(void* p, const uint32_t (&w)[8]) {
     asm volatile("st.global.v8.b32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8};\n" ::"l"(p), "r"(w[0]), "r"(w[1]), "r"(w[2]), "r"(w[3]),

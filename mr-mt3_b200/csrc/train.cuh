@@ -63,7 +63,7 @@ struct AttnBwdParams {
 // row*ld + col.  Out of place, so that the sublayer's input stays behind as the activation the
 // backward needs (no snapshot copy of the residual stream); drop may be off.
 #ifndef MRMT3_EPI_WIDE
-#define MRMT3_EPI_WIDE 2
+#define MRMT3_EPI_WIDE 1
 #endif
 struct EpiResidualTo {
     const float* Hin;
