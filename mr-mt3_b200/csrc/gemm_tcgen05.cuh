@@ -610,8 +610,11 @@ __global__ void __launch_bounds__(kTcThreads, 1)
 
 // ---- launchers ----------------------------------------------------------------------------------
 // CTA-pair tiles: option `gemm_2cta` / MRMT3_GEMM_2CTA (1 = use the pair kernel where the tile splits and
-// the problem has at least one 256-row tile per pair; 0 = single-CTA kernel everywhere)
-constexpr int kGemm2CtaDefault = 0;
+// the problem has at least one 256-row tile per pair; 0 = single-CTA kernel everywhere).  Measured on the six
+// encoder shapes at M = 65 536 (profiles/r2t_gemm_pair2.jsonl): pair 841-1225 TFLOP/s, single 787-1116,
+// cuBLAS 867-1199.  The weight-gradient form (MODE 1) stays on single-CTA tiles: its outputs are a few
+// dozen tiles, split-K spreads them over the SMs, and 256-row tiles would halve the number of work items.
+constexpr int kGemm2CtaDefault = 1;
 inline int& gemm_2cta_flag() {
     static int flag = [] {
         const char* e = getenv("MRMT3_GEMM_2CTA");
@@ -689,7 +692,7 @@ template <int MODE, class Epi>
 Status launch_gemm_tc_mn_any(const CUtensorMap* ma, const CUtensorMap* mb, int M, int N, int R, const Epi& epi,
                              cudaStream_t stream, int k_splits) {
     const ARowMap none{nullptr, 1};
-    const bool pair = tc_use_pair(M);
+    const bool pair = MODE == 2 && tc_use_pair(M);
     if (N % 256 == 0)
         return pair ? launch_gemm_tc_kernel<256, Epi, MODE, 2>(ma, mb, M, N, R, none, epi, stream, k_splits)
                     : launch_gemm_tc_kernel<256, Epi, MODE, 1>(ma, mb, M, N, R, none, epi, stream, k_splits);

@@ -17,6 +17,8 @@
 //   adamw_kernel           AdamW on fp32 masters, refreshed bf16 copy
 #include "train.cuh"
 
+#include <type_traits>
+
 #include <algorithm>
 
 namespace mrmt3 {
@@ -683,17 +685,25 @@ __global__ void __launch_bounds__(128, CTAS)
         auto fdrop = [&](int ni, int r) -> float {
             return !p.drop.on() || ((kb[r >> 1] >> (2 * ni + (r & 1))) & 1u) ? fscale : 0.f;
         };
+        // only the tiles on the key-length / causal boundary need per-element predicates
+        const bool need_mask = ((kt + 1) * kBwdT > p.Tk) || (p.causal && ((kt + 1) * kBwdT - 1 > q0 + p.causal_offset));
+        auto visible = [&](int ni, int r) -> bool {
+            const int key = kt * kBwdT + ni * 8 + (lane & 3) * 2 + (r & 1);
+            const int row = row_lo + ((r >> 1) << 3);
+            return key < p.Tk && (!p.causal || key <= row + p.causal_offset);
+        };
         if (pass == 0) {
+            if (need_mask) {
 #pragma unroll
-            for (int ni = 0; ni < 8; ++ni) {
+                for (int ni = 0; ni < 8; ++ni)
 #pragma unroll
-                for (int r = 0; r < 4; ++r) {
-                    const int key = kt * kBwdT + ni * 8 + (lane & 3) * 2 + (r & 1);
-                    const int row = row_lo + ((r >> 1) << 3);
-                    const bool ok = key < p.Tk && (!p.causal || key <= row + p.causal_offset);
-                    if (ok)
-                        dl[r >> 1] += exp2f(s[ni][r] * kLog2e - lse[r >> 1]) * dp[ni][r] * fdrop(ni, r);
-                }
+                    for (int r = 0; r < 4; ++r)
+                        if (visible(ni, r)) dl[r >> 1] += exp2f(s[ni][r] * kLog2e - lse[r >> 1]) * dp[ni][r] * fdrop(ni, r);
+            } else {
+#pragma unroll
+                for (int ni = 0; ni < 8; ++ni)
+#pragma unroll
+                    for (int r = 0; r < 4; ++r) dl[r >> 1] += exp2f(s[ni][r] * kLog2e - lse[r >> 1]) * dp[ni][r] * fdrop(ni, r);
             }
             if (kt == n_kt - 1) {
 #pragma unroll
@@ -705,19 +715,22 @@ __global__ void __launch_bounds__(128, CTAS)
                 }
             }
         } else {
+            auto ds_tile = [&](auto masked) {
 #pragma unroll
-            for (int ni = 0; ni < 8; ++ni) {
+                for (int ni = 0; ni < 8; ++ni) {
 #pragma unroll
-                for (int r = 0; r < 4; ++r) {
-                    const int key = kt * kBwdT + ni * 8 + (lane & 3) * 2 + (r & 1);
-                    const int row = row_lo + ((r >> 1) << 3);
-                    const bool ok = key < p.Tk && (!p.causal || key <= row + p.causal_offset);
-                    const float pr = ok ? exp2f(s[ni][r] * kLog2e - lse[r >> 1]) : 0.f;
-                    // dropout sits between softmax and P V: dP = dP' * m / (1 - p)
-                    const float dpe = dp[ni][r] * fdrop(ni, r);
-                    s[ni][r] = pr * (dpe - dl[r >> 1]);  // dS
+                    for (int r = 0; r < 4; ++r) {
+                        bool ok = true;
+                        if constexpr (decltype(masked)::value) ok = visible(ni, r);
+                        const float pr = ok ? exp2f(s[ni][r] * kLog2e - lse[r >> 1]) : 0.f;
+                        // dropout sits between softmax and P V: dP = dP' * m / (1 - p)
+                        const float dpe = dp[ni][r] * fdrop(ni, r);
+                        s[ni][r] = pr * (dpe - dl[r >> 1]);  // dS
+                    }
                 }
-            }
+            };
+            if (need_mask) ds_tile(std::true_type{});
+            else ds_tile(std::false_type{});
             uint32_t dsf[4][4];
             bwd_c_to_a(dsf, s);
             bwd_mma_nn(dq, dsf, sA[st], lane);
@@ -819,20 +832,30 @@ __global__ void __launch_bounds__(128, CTAS)
         bwd_mma_nt(stt, kf, sA[st], lane);   // S^T = K Q^T
         bwd_mma_nt(dpt, vf, sB[st], lane);   // dP^T = V dO^T
         float pt[8][4];
+        // only the tiles on a length / causal boundary need per-element predicates (uniform over the CTA)
+        const bool need_mask = ((qt + 1) * kBwdT > p.Tq) || (k0 + kBwdT > p.Tk) ||
+                               (p.causal && (k0 + kBwdT - 1 > qt * kBwdT + p.causal_offset));
+        auto pds_tile = [&](auto masked) {
 #pragma unroll
-        for (int ni = 0; ni < 8; ++ni) {
+            for (int ni = 0; ni < 8; ++ni) {
 #pragma unroll
-            for (int r = 0; r < 4; ++r) {
-                const int qc = ni * 8 + (lane & 3) * 2 + (r & 1);
-                const int row = qt * kBwdT + qc;              // query index
-                const int key = key_lo + ((r >> 1) << 3);
-                const bool ok = row < p.Tq && key < p.Tk && (!p.causal || key <= row + p.causal_offset);
-                const float pr = ok ? exp2f(stt[ni][r] * kLog2e - s_lse[st][qc]) : 0.f;
-                const float mk = !p.drop.on() || ((kbw[ni][r & 1] >> ((r >> 1) << 1)) & 1u) ? fscale : 0.f;
-                pt[ni][r] = pr * mk;                                   // P'^T = dropout(P)^T
-                stt[ni][r] = pr * (dpt[ni][r] * mk - s_dl[st][qc]);    // dS^T
+                for (int r = 0; r < 4; ++r) {
+                    const int qc = ni * 8 + (lane & 3) * 2 + (r & 1);
+                    bool ok = true;
+                    if constexpr (decltype(masked)::value) {
+                        const int row = qt * kBwdT + qc;              // query index
+                        const int key = key_lo + ((r >> 1) << 3);
+                        ok = row < p.Tq && key < p.Tk && (!p.causal || key <= row + p.causal_offset);
+                    }
+                    const float pr = ok ? exp2f(stt[ni][r] * kLog2e - s_lse[st][qc]) : 0.f;
+                    const float mk = !p.drop.on() || ((kbw[ni][r & 1] >> ((r >> 1) << 1)) & 1u) ? fscale : 0.f;
+                    pt[ni][r] = pr * mk;                                   // P'^T = dropout(P)^T
+                    stt[ni][r] = pr * (dpt[ni][r] * mk - s_dl[st][qc]);    // dS^T
+                }
             }
-        }
+        };
+        if (need_mask) pds_tile(std::true_type{});
+        else pds_tile(std::false_type{});
         uint32_t af[4][4];
         bwd_c_to_a(af, pt);
         bwd_mma_nn(dv, af, sB[st], lane);  // dV += P^T dO

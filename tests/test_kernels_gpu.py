@@ -53,6 +53,37 @@ def test_tcgen05_large(eng):
     _check(eng, 1, 65536, 1152, 512)
 
 
+# CTA-pair tiles (tcgen05.mma.cta_group::2, 256 x BN per two-CTA cluster) against the single-CTA kernel:
+# same products summed in the same order, so the outputs must be BIT-identical; against fp64 as above.
+# Shapes: every BN the pair kernel has (256 / 192 / 128), M not a multiple of 256 (the second CTA of the
+# last pair works on rows past M), M < 256 (launcher falls back to single), K = 64 (one k-block), both
+# K-major (which 1, bf16-out 3) and the data-gradient form (which 5, B operand MN-major).
+PAIR = [(1, 256, 256, 64), (1, 512, 192, 512), (1, 384, 128, 384), (1, 1000, 1152, 512), (1, 4096, 2048, 512),
+        (1, 8192, 512, 1024), (1, 130, 512, 512), (3, 2048, 1152, 512), (3, 777, 512, 384),
+        (5, 1000, 512, 1152), (5, 4096, 384, 512), (5, 8192, 1024, 512), (5, 256, 256, 128)]
+
+
+@pytest.mark.parametrize("which,M,N,K", PAIR)
+def test_gemm_tcgen05_cta_pair_equals_single(eng, which, M, N, K):
+    g = torch.Generator().manual_seed(which + M + 7 * N + 13 * K)
+    a = torch.randn((M, K), generator=g).bfloat16()
+    w = (torch.randn((K, N) if which == 5 else (N, K), generator=g) * K ** -0.5).bfloat16()
+    try:
+        eng.set_option("gemm_2cta", 1)
+        pair = eng.test_gemm(a, w, which)
+        eng.set_option("gemm_2cta", 0)
+        single = eng.test_gemm(a, w, which)
+    finally:
+        eng.set_option("gemm_2cta", -1)
+    if which == 3:                                   # the hook's buffer holds M * N bf16 in its first half
+        pair = pair.view(torch.bfloat16).reshape(-1)[:M * N].reshape(M, N).float()
+        single = single.view(torch.bfloat16).reshape(-1)[:M * N].reshape(M, N).float()
+    assert torch.equal(pair, single)
+    want = a.double() @ (w.double() if which == 5 else w.double().T)
+    err = (pair.cpu().double() - want).abs().max().item()
+    assert err < (2e-2 if which == 3 else 2e-3), (which, M, N, K, err)   # which 3 adds the bf16 output rounding
+
+
 # the fine-tune backward's two operand forms, at the reduction depth of configs[4] (32 x 1024 rows)
 @pytest.mark.parametrize("R,M,N", [(32768, 512, 384), (32768, 1152, 512), (32768, 2048, 512), (10240, 6144, 512),
                                    (1000, 512, 512), (32768, 512, 1024), (32768, 1536, 512)])
