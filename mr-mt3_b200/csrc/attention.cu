@@ -163,8 +163,25 @@ __global__ void __launch_bounds__(128)
                 const unsigned long long r1i = r0i + 8ull * p.Tk;
                 const int key = kt * kAttnBK + ni * 8 + (lane & 3) * 2;
                 float f0, f1, f2, f3;
-                drop_factor2(p.drop, r0i + key, f0, f1);
-                drop_factor2(p.drop, r1i + key, f2, f3);
+                if ((p.Tk & 3) == 0) {
+                    // One hash covers four consecutive keys of a row; a lane pair (lane ^ 1) holds exactly
+                    // those four keys for two rows.  The even lane hashes the group of row_lo, the odd lane
+                    // that of row_lo + 8, and each hands the partner the 32 bits (two draws) it needs:
+                    // 8 hashes per tile and thread instead of 16, same mask bit for bit.
+                    const bool odd = lane & 1;
+                    const unsigned long long h = drop_hash4(p.drop, ((odd ? r1i : r0i) + (unsigned long long)(key & ~3)) >> 2);
+                    const uint32_t lo = (uint32_t)h, hi = (uint32_t)(h >> 32);
+                    const uint32_t got = __shfl_xor_sync(0xffffffffu, odd ? lo : hi, 1);
+                    const uint32_t d0 = odd ? got : lo;   // draws of this lane's two keys in row_lo
+                    const uint32_t d1 = odd ? hi : got;   // ... in row_lo + 8
+                    f0 = (d0 & 0xFFFFu) >= p.drop.threshold ? p.drop.scale : 0.f;
+                    f1 = (d0 >> 16) >= p.drop.threshold ? p.drop.scale : 0.f;
+                    f2 = (d1 & 0xFFFFu) >= p.drop.threshold ? p.drop.scale : 0.f;
+                    f3 = (d1 >> 16) >= p.drop.threshold ? p.drop.scale : 0.f;
+                } else {
+                    drop_factor2(p.drop, r0i + key, f0, f1);
+                    drop_factor2(p.drop, r1i + key, f2, f3);
+                }
                 p0 *= f0;
                 p1 *= f1;
                 p2 *= f2;

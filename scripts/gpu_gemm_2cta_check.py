@@ -87,6 +87,10 @@ if len(sys.argv) > 1 and sys.argv[1] == "--bench": child_bench()
 out_path = sys.argv[1] if len(sys.argv) > 1 else "gpurun_out/gemm_2cta.jsonl"
 lines = []
 for stage, limit in (("--check", 240), ("--bench", 300)):
+    sampler = None
+    if stage == "--bench":   # SM clock and throttle reasons WHILE the GEMMs run (the recipe's clocks line)
+        sampler = subprocess.Popen(["nvidia-smi", "--query-gpu=clocks.sm,clocks.max.sm,clocks_event_reasons.active",
+                                    "--format=csv,noheader,nounits", "-lms", "100"], stdout=subprocess.PIPE, text=True)
     try:
         r = subprocess.run([sys.executable, __file__, stage], capture_output=True, text=True, timeout=limit)
         lines += [l for l in r.stdout.splitlines() if l.startswith("{")]
@@ -98,6 +102,15 @@ for stage, limit in (("--check", 240), ("--bench", 300)):
         lines += [l for l in so.splitlines() if l.startswith("{")]
         lines.append(json.dumps({"stage": stage, "timeout_s": limit}))
         break
+    finally:
+        if sampler is not None:
+            sampler.terminate()
+            rows = [x.split(",") for x in sampler.communicate()[0].splitlines() if x.count(",") == 2]
+            busy = sorted(int(x[0]) for x in rows if int(x[0]) > 1000)      # samples taken under load
+            reasons = sorted({x[2].strip() for x in rows if int(x[0]) > 1000})
+            lines.append(json.dumps({"clocks_during_bench": {"samples_under_load": len(busy), "sm_mhz_median": busy[len(busy) // 2] if busy else None,
+                                                             "sm_mhz_min": busy[0] if busy else None, "sm_max_mhz": int(rows[0][1]) if rows else None,
+                                                             "event_reasons_bitmasks": reasons}}))
 open(out_path, "w").write("\n".join(lines) + "\n")
 print("\n".join(lines))
 sys.exit(0 if not any('"failed"' in l or '"timeout_s"' in l for l in lines) else 1)
