@@ -152,10 +152,10 @@ __global__ void __launch_bounds__(128)
         uint32_t keep_lo = 0, keep_hi = 0;
 #pragma unroll
         for (int ni = 0; ni < 8; ++ni) {
-            float p0 = exp2f((s[ni][0] - m_use[0]) * kLog2e);
-            float p1 = exp2f((s[ni][1] - m_use[0]) * kLog2e);
-            float p2 = exp2f((s[ni][2] - m_use[1]) * kLog2e);
-            float p3 = exp2f((s[ni][3] - m_use[1]) * kLog2e);
+            float p0 = fast_exp2((s[ni][0] - m_use[0]) * kLog2e);
+            float p1 = fast_exp2((s[ni][1] - m_use[0]) * kLog2e);
+            float p2 = fast_exp2((s[ni][2] - m_use[1]) * kLog2e);
+            float p3 = fast_exp2((s[ni][3] - m_use[1]) * kLog2e);
             l_run[0] += p0 + p1;
             l_run[1] += p2 + p3;
             if (p.drop.on()) {  // dropout(softmax): the normaliser above sums the undropped weights

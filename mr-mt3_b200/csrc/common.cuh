@@ -172,6 +172,14 @@ __host__ __device__ __forceinline__ void drop_factor4(const DropSpec& d, unsigne
     for (unsigned int k = 0; k < 4; ++k) f[k] = drop_lane(d, h, k);
 }
 
+// 2^x as one MUFU.EX2 (exp2f adds a range test and two predicated multiplies so that results below
+// 2^-126 come out as denormals; softmax weights that small are zero for every purpose here)
+__device__ __forceinline__ float fast_exp2(float x) {
+    float y;
+    asm("ex2.approx.ftz.f32 %0, %1;\n" : "=f"(y) : "f"(x));
+    return y;
+}
+
 // streaming 16 B load that does not allocate in L1 (KV cache / one-shot reads)
 __device__ __forceinline__ uint4 ld_stream16(const void* p) {
     uint4 r;

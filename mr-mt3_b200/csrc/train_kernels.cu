@@ -698,12 +698,12 @@ __global__ void __launch_bounds__(128, CTAS)
                 for (int ni = 0; ni < 8; ++ni)
 #pragma unroll
                     for (int r = 0; r < 4; ++r)
-                        if (visible(ni, r)) dl[r >> 1] += exp2f(s[ni][r] * kLog2e - lse[r >> 1]) * dp[ni][r] * fdrop(ni, r);
+                        if (visible(ni, r)) dl[r >> 1] += fast_exp2(s[ni][r] * kLog2e - lse[r >> 1]) * dp[ni][r] * fdrop(ni, r);
             } else {
 #pragma unroll
                 for (int ni = 0; ni < 8; ++ni)
 #pragma unroll
-                    for (int r = 0; r < 4; ++r) dl[r >> 1] += exp2f(s[ni][r] * kLog2e - lse[r >> 1]) * dp[ni][r] * fdrop(ni, r);
+                    for (int r = 0; r < 4; ++r) dl[r >> 1] += fast_exp2(s[ni][r] * kLog2e - lse[r >> 1]) * dp[ni][r] * fdrop(ni, r);
             }
             if (kt == n_kt - 1) {
 #pragma unroll
@@ -722,7 +722,7 @@ __global__ void __launch_bounds__(128, CTAS)
                     for (int r = 0; r < 4; ++r) {
                         bool ok = true;
                         if constexpr (decltype(masked)::value) ok = visible(ni, r);
-                        const float pr = ok ? exp2f(s[ni][r] * kLog2e - lse[r >> 1]) : 0.f;
+                        const float pr = ok ? fast_exp2(s[ni][r] * kLog2e - lse[r >> 1]) : 0.f;
                         // dropout sits between softmax and P V: dP = dP' * m / (1 - p)
                         const float dpe = dp[ni][r] * fdrop(ni, r);
                         s[ni][r] = pr * (dpe - dl[r >> 1]);  // dS
@@ -847,7 +847,7 @@ __global__ void __launch_bounds__(128, CTAS)
                         const int key = key_lo + ((r >> 1) << 3);
                         ok = row < p.Tq && key < p.Tk && (!p.causal || key <= row + p.causal_offset);
                     }
-                    const float pr = ok ? exp2f(stt[ni][r] * kLog2e - s_lse[st][qc]) : 0.f;
+                    const float pr = ok ? fast_exp2(stt[ni][r] * kLog2e - s_lse[st][qc]) : 0.f;
                     const float mk = !p.drop.on() || ((kbw[ni][r & 1] >> ((r >> 1) << 1)) & 1u) ? fscale : 0.f;
                     pt[ni][r] = pr * mk;                                   // P'^T = dropout(P)^T
                     stt[ni][r] = pr * (dpt[ni][r] * mk - s_dl[st][qc]);    // dS^T
