@@ -21,7 +21,8 @@ namespace mrmt3 {
 constexpr int kAttnBQ = 64;
 constexpr int kAttnBK = 64;
 
-__global__ void __launch_bounds__(128)
+template <int CTAS>  // resident CTAs per SM the register budget is cut for (3: 168 registers, 4: 128, no spills)
+__global__ void __launch_bounds__(128, CTAS)
     attn_full_kernel(AttnFullParams p) {
     __shared__ __align__(128) bf16 sQ[kAttnBQ * kDKV];
     __shared__ __align__(128) bf16 sK[2][kAttnBK * kDKV];
@@ -247,7 +248,13 @@ __global__ void __launch_bounds__(128)
 Status launch_attn_full(const AttnFullParams& p, int batch, cudaStream_t stream) {
     if (batch <= 0 || p.Tq <= 0) return OkStatus();
     dim3 grid(ceil_div(p.Tq, kAttnBQ), kHeads, batch);
-    attn_full_kernel<<<grid, 128, 0, stream>>>(p);
+    // MRMT3_ATTN_FWD_CTAS=3 for A/B runs against the 4-CTA register budget
+    static const int ctas = [] {
+        const char* e = getenv("MRMT3_ATTN_FWD_CTAS");
+        return e && atoi(e) == 3 ? 3 : 4;
+    }();
+    if (ctas == 4) attn_full_kernel<4><<<grid, 128, 0, stream>>>(p);
+    else attn_full_kernel<3><<<grid, 128, 0, stream>>>(p);
     MRMT3_CHECK_LAUNCH();
     return OkStatus();
 }
