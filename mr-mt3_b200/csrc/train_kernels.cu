@@ -749,6 +749,159 @@ __global__ void __launch_bounds__(128, CTAS)
     }
 }
 
+// dQ in ONE pass over the key tiles (default; MRMT3_ATTN_BWD_DQ_PASSES=2 selects the kernel above).
+// The two-pass kernel exists because delta must be consistent with the recomputed P and dP: taking
+// delta~ = sum_d dO O from the forward's bf16 output leaves an error eps = delta - delta~ of relative size
+// 2^-9, which on sharply peaked rows is as large as dS itself.  That error is, however, a per-row SCALAR,
+// and dQ is linear in it:
+//     dQ = sum_k P (dP - delta) K = sum_k P (dP - delta~) K  -  eps * sum_k P K
+// so one pass accumulates U = sum_k [P (dP - delta~)] K and W = sum_k P K on the tensor cores and
+// delta = sum_k P dP in fp32 on the side, and the end applies dQ = U - (delta - delta~) W.  The rounding of
+// P (dP - delta~) to bf16 now costs 2^-9 * P * |eps| ~ 2^-18 |delta|: the accuracy of the two-pass form at
+// 4 MMA groups (S, dP, U, W) and ONE sweep of exponentials / masks / keep bits instead of 5 and two.
+// delta (exact, for the dK/dV kernel) is written out as before.  Q / dO stay in shared memory and their A
+// fragments are re-read per tile (8 ldmatrix), which keeps the kernel at three CTAs per SM.
+template <int CTAS>
+__global__ void __launch_bounds__(128, CTAS)
+    attn_bwd_dq1_kernel(AttnBwdParams p) {
+    __shared__ __align__(128) bf16 sQ[kBwdT * kDKV];
+    __shared__ __align__(128) bf16 sdO[kBwdT * kDKV];
+    __shared__ __align__(128) bf16 sA[2][kBwdT * kDKV];  // stage s: K tile   (stage 1 holds O first)
+    __shared__ __align__(128) bf16 sB[2][kBwdT * kDKV];  // stage s: V tile
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int q0 = blockIdx.x * kBwdT, head = blockIdx.y, b = blockIdx.z;
+    const bf16* Q = p.Q + (size_t)b * p.q_batch_stride + head * p.q_head_stride;
+    const bf16* K = p.K + (size_t)b * p.k_batch_stride + head * p.k_head_stride;
+    const bf16* V = p.V + (size_t)b * p.v_batch_stride + head * p.v_head_stride;
+    const bf16* O = p.O + (size_t)b * p.o_batch_stride + head * p.o_head_stride;
+    const bf16* dO = p.dO + (size_t)b * p.o_batch_stride + head * p.o_head_stride;
+    const float kLog2e = 1.4426950408889634f;
+
+    int n_kt = (p.Tk + kBwdT - 1) / kBwdT;
+    if (p.causal) n_kt = min(n_kt, max(0, (q0 + kBwdT - 1 + p.causal_offset) / kBwdT + 1));
+
+    bwd_load_tile(sQ, Q, p.q_row_stride, q0, p.Tq);
+    bwd_load_tile(sdO, dO, p.o_row_stride, q0, p.Tq);
+    bwd_load_tile(sA[1], O, p.o_row_stride, q0, p.Tq);
+    cp_async_commit();
+    if (n_kt > 0) {
+        bwd_load_tile(sA[0], K, p.k_row_stride, 0, p.Tk);
+        bwd_load_tile(sB[0], V, p.v_row_stride, 0, p.Tk);
+    }
+    cp_async_commit();
+    cp_async_wait<1>();
+    __syncthreads();
+
+    const int row_lo = q0 + warp * 16 + (lane >> 2);
+    const unsigned long long bh_row0 = (unsigned long long)(b * kHeads + head) * p.Tq;
+    const int keep_words = ((p.Tk + kBwdT - 1) / kBwdT) * 4;
+    const float fscale = p.drop.on() ? p.drop.scale : 1.f;
+    // delta~[row] = sum_d dO O from the A fragments of the two tiles (this thread: rows row_lo, row_lo + 8)
+    float dt[2] = {0.f, 0.f};
+    {
+        uint32_t of[4][4], dof[4][4];
+        bwd_a_frags(of, sA[1], warp, lane);
+        bwd_a_frags(dof, sdO, warp, lane);
+#pragma unroll
+        for (int kk = 0; kk < 4; ++kk)
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {   // registers 0, 2: row lane / 4; 1, 3: row lane / 4 + 8
+                const float2 a = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&of[kk][j]));
+                const float2 g = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&dof[kk][j]));
+                dt[j & 1] += a.x * g.x + a.y * g.y;
+            }
+#pragma unroll
+        for (int h = 0; h < 2; ++h) {
+            dt[h] += __shfl_xor_sync(0xffffffffu, dt[h], 1);
+            dt[h] += __shfl_xor_sync(0xffffffffu, dt[h], 2);
+        }
+    }
+    __syncthreads();  // stage 1 (O) may now be overwritten
+
+    float lse[2], dl[2] = {0.f, 0.f};
+#pragma unroll
+    for (int h = 0; h < 2; ++h) lse[h] = p.lse2[((size_t)b * kHeads + head) * p.Tq + min(row_lo + h * 8, p.Tq - 1)];
+    float u[8][4], w[8][4];
+    bwd_zero(u);
+    bwd_zero(w);
+    for (int kt = 0; kt < n_kt; ++kt) {
+        const int st = kt & 1;
+        if (kt + 1 < n_kt) {
+            bwd_load_tile(sA[st ^ 1], K, p.k_row_stride, (kt + 1) * kBwdT, p.Tk);
+            bwd_load_tile(sB[st ^ 1], V, p.v_row_stride, (kt + 1) * kBwdT, p.Tk);
+        }
+        cp_async_commit();
+        uint32_t kb[2] = {0u, 0u};
+        if (p.drop.on()) {
+#pragma unroll
+            for (int h = 0; h < 2; ++h)
+                kb[h] = __ldg(p.keep + (bh_row0 + min(row_lo + h * 8, p.Tq - 1)) * keep_words + kt * 4 + (lane & 3));
+        }
+        cp_async_wait<1>();
+        __syncthreads();
+        float s[8][4], dp[8][4];
+        bwd_zero(s);
+        bwd_zero(dp);
+        {
+            uint32_t af[4][4];
+            bwd_a_frags(af, sQ, warp, lane);
+            bwd_mma_nt(s, af, sA[st], lane);
+            bwd_a_frags(af, sdO, warp, lane);
+            bwd_mma_nt(dp, af, sB[st], lane);
+        }
+        const bool need_mask = ((kt + 1) * kBwdT > p.Tk) || (p.causal && ((kt + 1) * kBwdT - 1 > q0 + p.causal_offset));
+        auto tile = [&](auto masked) {
+#pragma unroll
+            for (int ni = 0; ni < 8; ++ni) {
+#pragma unroll
+                for (int r = 0; r < 4; ++r) {
+                    bool ok = true;
+                    if constexpr (decltype(masked)::value) {
+                        const int key = kt * kBwdT + ni * 8 + (lane & 3) * 2 + (r & 1);
+                        const int row = row_lo + ((r >> 1) << 3);
+                        ok = key < p.Tk && (!p.causal || key <= row + p.causal_offset);
+                    }
+                    const float pr = ok ? fast_exp2(s[ni][r] * kLog2e - lse[r >> 1]) : 0.f;
+                    const float mk = !p.drop.on() || ((kb[r >> 1] >> (2 * ni + (r & 1))) & 1u) ? fscale : 0.f;
+                    const float dpe = dp[ni][r] * mk;       // dropout sits between softmax and P V
+                    dl[r >> 1] += pr * dpe;
+                    s[ni][r] = pr;                          // P
+                    dp[ni][r] = pr * (dpe - dt[r >> 1]);    // P (dP - delta~)
+                }
+            }
+        };
+        if (need_mask) tile(std::true_type{});
+        else tile(std::false_type{});
+        uint32_t af[4][4];
+        bwd_c_to_a(af, dp);
+        bwd_mma_nn(u, af, sA[st], lane);
+        bwd_c_to_a(af, s);
+        bwd_mma_nn(w, af, sA[st], lane);
+        __syncthreads();  // every warp is done with stage st before it is refilled
+    }
+    cp_async_wait<0>();
+    float eps[2];
+#pragma unroll
+    for (int h = 0; h < 2; ++h) {
+        dl[h] += __shfl_xor_sync(0xffffffffu, dl[h], 1);
+        dl[h] += __shfl_xor_sync(0xffffffffu, dl[h], 2);
+        eps[h] = dl[h] - dt[h];
+        const int r = row_lo + h * 8;
+        if ((lane & 3) == 0 && r < p.Tq) p.delta[((size_t)b * kHeads + head) * p.Tq + r] = dl[h];
+    }
+    bf16* dQ = p.dQ + (size_t)b * p.q_batch_stride + head * p.q_head_stride;
+#pragma unroll
+    for (int ni = 0; ni < 8; ++ni) {
+        int col = ni * 8 + (lane & 3) * 2;
+        if (row_lo < p.Tq)
+            *reinterpret_cast<uint32_t*>(dQ + (size_t)row_lo * p.q_row_stride + col) =
+                pack_bf16(u[ni][0] - eps[0] * w[ni][0], u[ni][1] - eps[0] * w[ni][1]);
+        if (row_lo + 8 < p.Tq)
+            *reinterpret_cast<uint32_t*>(dQ + (size_t)(row_lo + 8) * p.q_row_stride + col) =
+                pack_bf16(u[ni][2] - eps[1] * w[ni][2], u[ni][3] - eps[1] * w[ni][3]);
+    }
+}
+
 // dK, dV: one CTA per (key tile, head, batch); loops over the query tiles, everything transposed
 // (rows = keys):  S^T = K Q^T, P^T = exp2(S^T log2e - lse2[col]), dV += P^T dO,
 //                 dP^T = V dO^T, dS^T = P^T * (dP^T - delta[col]), dK += dS^T Q
@@ -888,13 +1041,19 @@ Status launch_attn_bwd(const AttnBwdParams& p, int batch, cudaStream_t s) {
         const char* e = getenv("MRMT3_ATTN_BWD_CTAS");
         return e && atoi(e) == 2 ? 2 : 3;
     }();
+    static const int dq_passes = [] {
+        const char* e = getenv("MRMT3_ATTN_BWD_DQ_PASSES");
+        return e && atoi(e) == 2 ? 2 : 1;
+    }();
     const dim3 gq(ceil_div(p.Tq, kBwdT), kHeads, batch), gk(ceil_div(p.Tk, kBwdT), kHeads, batch);
     if (ctas == 3) {
-        attn_bwd_dq_kernel<3><<<gq, 128, 0, s>>>(p);
+        if (dq_passes == 1) attn_bwd_dq1_kernel<3><<<gq, 128, 0, s>>>(p);
+        else attn_bwd_dq_kernel<3><<<gq, 128, 0, s>>>(p);
         MRMT3_CHECK_LAUNCH();
         attn_bwd_dkv_kernel<3><<<gk, 128, 0, s>>>(p);
     } else {
-        attn_bwd_dq_kernel<2><<<gq, 128, 0, s>>>(p);
+        if (dq_passes == 1) attn_bwd_dq1_kernel<2><<<gq, 128, 0, s>>>(p);
+        else attn_bwd_dq_kernel<2><<<gq, 128, 0, s>>>(p);
         MRMT3_CHECK_LAUNCH();
         attn_bwd_dkv_kernel<2><<<gk, 128, 0, s>>>(p);
     }
