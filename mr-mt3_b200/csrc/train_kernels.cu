@@ -1035,10 +1035,15 @@ __global__ void __launch_bounds__(128, CTAS)
 
 Status launch_attn_bwd(const AttnBwdParams& p, int batch, cudaStream_t s) {
     if (batch <= 0 || p.Tq <= 0 || p.Tk <= 0) return OkStatus();
-    // the kernels wait on mma.sync latency with few warps per scheduler: three CTAs per SM at 168
-    // registers (a few hundred bytes of spills) against two at 255; MRMT3_ATTN_BWD_CTAS=2 for A/B
-    static const int ctas = [] {
-        const char* e = getenv("MRMT3_ATTN_BWD_CTAS");
+    // Register budgets (resident CTAs per SM), chosen by measurement on the fine-tune step: the single-pass
+    // dQ kernel at 2 CTAs (244 registers, no spills), dK/dV at 3 (168 registers, ~160 B of spills);
+    // MRMT3_ATTN_BWD_DQ_CTAS / MRMT3_ATTN_BWD_DKV_CTAS / MRMT3_ATTN_BWD_DQ_PASSES for A/B runs
+    static const int dq_ctas = [] {
+        const char* e = getenv("MRMT3_ATTN_BWD_DQ_CTAS");
+        return e && atoi(e) == 3 ? 3 : 2;
+    }();
+    static const int dkv_ctas = [] {
+        const char* e = getenv("MRMT3_ATTN_BWD_DKV_CTAS");
         return e && atoi(e) == 2 ? 2 : 3;
     }();
     static const int dq_passes = [] {
@@ -1046,17 +1051,16 @@ Status launch_attn_bwd(const AttnBwdParams& p, int batch, cudaStream_t s) {
         return e && atoi(e) == 2 ? 2 : 1;
     }();
     const dim3 gq(ceil_div(p.Tq, kBwdT), kHeads, batch), gk(ceil_div(p.Tk, kBwdT), kHeads, batch);
-    if (ctas == 3) {
-        if (dq_passes == 1) attn_bwd_dq1_kernel<3><<<gq, 128, 0, s>>>(p);
-        else attn_bwd_dq_kernel<3><<<gq, 128, 0, s>>>(p);
-        MRMT3_CHECK_LAUNCH();
-        attn_bwd_dkv_kernel<3><<<gk, 128, 0, s>>>(p);
+    if (dq_passes == 1) {
+        if (dq_ctas == 2) attn_bwd_dq1_kernel<2><<<gq, 128, 0, s>>>(p);
+        else attn_bwd_dq1_kernel<3><<<gq, 128, 0, s>>>(p);
     } else {
-        if (dq_passes == 1) attn_bwd_dq1_kernel<2><<<gq, 128, 0, s>>>(p);
-        else attn_bwd_dq_kernel<2><<<gq, 128, 0, s>>>(p);
-        MRMT3_CHECK_LAUNCH();
-        attn_bwd_dkv_kernel<2><<<gk, 128, 0, s>>>(p);
+        if (dq_ctas == 2) attn_bwd_dq_kernel<2><<<gq, 128, 0, s>>>(p);
+        else attn_bwd_dq_kernel<3><<<gq, 128, 0, s>>>(p);
     }
+    MRMT3_CHECK_LAUNCH();
+    if (dkv_ctas == 3) attn_bwd_dkv_kernel<3><<<gk, 128, 0, s>>>(p);
+    else attn_bwd_dkv_kernel<2><<<gk, 128, 0, s>>>(p);
     MRMT3_CHECK_LAUNCH();
     return OkStatus();
 }
