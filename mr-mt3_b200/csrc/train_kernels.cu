@@ -1035,16 +1035,17 @@ __global__ void __launch_bounds__(128, CTAS)
 
 Status launch_attn_bwd(const AttnBwdParams& p, int batch, cudaStream_t s) {
     if (batch <= 0 || p.Tq <= 0 || p.Tk <= 0) return OkStatus();
-    // Register budgets (resident CTAs per SM), chosen by measurement on the fine-tune step: the single-pass
-    // dQ kernel at 2 CTAs (244 registers, no spills), dK/dV at 3 (168 registers, ~160 B of spills);
-    // MRMT3_ATTN_BWD_DQ_CTAS / MRMT3_ATTN_BWD_DKV_CTAS / MRMT3_ATTN_BWD_DQ_PASSES for A/B runs
+    // Register budgets (resident CTAs per SM), chosen by measurement on the fine-tune step
+    // (profiles/r3b_bench_finetune_*.json: dQ/dKV at 2/2 CTAs 25.9 ms per step, 2/3 26.3, 3/3 26.6): both kernels
+    // at 2 CTAs per SM (244 / 255 registers, no spills) beat 3 CTAs with spills now that the element-wise work
+    // is small; MRMT3_ATTN_BWD_DQ_CTAS / MRMT3_ATTN_BWD_DKV_CTAS / MRMT3_ATTN_BWD_DQ_PASSES for A/B runs
     static const int dq_ctas = [] {
         const char* e = getenv("MRMT3_ATTN_BWD_DQ_CTAS");
         return e && atoi(e) == 3 ? 3 : 2;
     }();
     static const int dkv_ctas = [] {
         const char* e = getenv("MRMT3_ATTN_BWD_DKV_CTAS");
-        return e && atoi(e) == 2 ? 2 : 3;
+        return e && atoi(e) == 3 ? 3 : 2;
     }();
     static const int dq_passes = [] {
         const char* e = getenv("MRMT3_ATTN_BWD_DQ_PASSES");
