@@ -923,12 +923,14 @@ __global__ void __launch_bounds__(128, CTAS)
     const int n_qt = (p.Tq + kBwdT - 1) / kBwdT;
     int qt0 = 0;
     if (p.causal) qt0 = max(0, (k0 - p.causal_offset) / kBwdT);  // first query tile that can see key k0
+    // per-row statistics of a query tile ride in the same cp.async group as the tile itself: a plain
+    // load + shared store here would expose one global-load latency per tile in front of the barrier
     auto load_stats = [&](int stg, int qt) {
         if (threadIdx.x < kBwdT) {
             int r = qt * kBwdT + threadIdx.x;
             size_t idx = ((size_t)b * kHeads + head) * p.Tq + min(r, p.Tq - 1);
-            s_lse[stg][threadIdx.x] = p.lse2[idx];
-            s_dl[stg][threadIdx.x] = p.delta[idx];
+            cp_async4(&s_lse[stg][threadIdx.x], p.lse2 + idx);
+            cp_async4(&s_dl[stg][threadIdx.x], p.delta + idx);
         }
     };
 
