@@ -164,6 +164,7 @@ __global__ void __launch_bounds__(128, CTAS)
                 const unsigned long long r1i = r0i + 8ull * p.Tk;
                 const int key = kt * kAttnBK + ni * 8 + (lane & 3) * 2;
                 float f0, f1, f2, f3;
+                bool k0, k1, k2, k3;   // keep decisions (the bits the backward reads)
                 if ((p.Tk & 3) == 0) {
                     // One hash covers four consecutive keys of a row; a lane pair (lane ^ 1) holds exactly
                     // those four keys for two rows.  The even lane hashes the group of row_lo, the odd lane
@@ -175,26 +176,40 @@ __global__ void __launch_bounds__(128, CTAS)
                     const uint32_t got = __shfl_xor_sync(0xffffffffu, odd ? lo : hi, 1);
                     const uint32_t d0 = odd ? got : lo;   // draws of this lane's two keys in row_lo
                     const uint32_t d1 = odd ? hi : got;   // ... in row_lo + 8
-                    f0 = (d0 & 0xFFFFu) >= p.drop.threshold ? p.drop.scale : 0.f;
-                    f1 = (d0 >> 16) >= p.drop.threshold ? p.drop.scale : 0.f;
-                    f2 = (d1 & 0xFFFFu) >= p.drop.threshold ? p.drop.scale : 0.f;
-                    f3 = (d1 >> 16) >= p.drop.threshold ? p.drop.scale : 0.f;
+                    k0 = (d0 & 0xFFFFu) >= p.drop.threshold;
+                    k1 = (d0 >> 16) >= p.drop.threshold;
+                    k2 = (d1 & 0xFFFFu) >= p.drop.threshold;
+                    k3 = (d1 >> 16) >= p.drop.threshold;
+                    f0 = k0 ? p.drop.scale : 0.f;
+                    f1 = k1 ? p.drop.scale : 0.f;
+                    f2 = k2 ? p.drop.scale : 0.f;
+                    f3 = k3 ? p.drop.scale : 0.f;
                 } else {
                     drop_factor2(p.drop, r0i + key, f0, f1);
                     drop_factor2(p.drop, r1i + key, f2, f3);
+                    k0 = f0 != 0.f;
+                    k1 = f1 != 0.f;
+                    k2 = f2 != 0.f;
+                    k3 = f3 != 0.f;
                 }
                 p0 *= f0;
                 p1 *= f1;
                 p2 *= f2;
                 p3 *= f3;
-                keep_lo |= ((f0 != 0.f ? 1u : 0u) | (f1 != 0.f ? 2u : 0u)) << (2 * ni);
-                keep_hi |= ((f2 != 0.f ? 1u : 0u) | (f3 != 0.f ? 2u : 0u)) << (2 * ni);
+                keep_lo |= ((k0 ? 1u : 0u) | (k1 ? 2u : 0u)) << (2 * ni);
+                keep_hi |= ((k2 ? 1u : 0u) | (k3 ? 2u : 0u)) << (2 * ni);
             }
             // C-fragment of two adjacent n-blocks == A-fragment of one k16 step
             pf[ni >> 1][(ni & 1) * 2 + 0] = pack_bf16(p0, p1);
             pf[ni >> 1][(ni & 1) * 2 + 1] = pack_bf16(p2, p3);
+        }
+        // rescale the running output only when some row of the warp saw a new maximum (after the first
+        // tiles of a row that is the exception: 32 multiplies per tile saved, same arithmetic otherwise)
+        if (__any_sync(0xffffffffu, scale_old[0] != 1.f || scale_old[1] != 1.f)) {
 #pragma unroll
-            for (int r = 0; r < 4; ++r) o[ni][r] *= scale_old[r >> 1];
+            for (int ni = 0; ni < 8; ++ni)
+#pragma unroll
+                for (int r = 0; r < 4; ++r) o[ni][r] *= scale_old[r >> 1];
         }
 
         if (p.drop.on() && p.keep) {
