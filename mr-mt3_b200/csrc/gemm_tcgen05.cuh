@@ -330,6 +330,39 @@ __device__ __forceinline__ void epi_store32(const EpiGatedGelu& e, int row, int 
     st_global_256(e.C + (size_t)row * e.ldc + (col >> 1), w);
 }
 
+// Epilogues that READ what they add to (the residual stream) pay one global-load round trip per 32-column
+// chunk if the load is issued after the accumulator chunk has arrived: eight dependent round trips per
+// tile, longer than the K = 384 mainloop.  Functors with EpiPrefetch<>::value provide
+//     fetch(row, col, h[32])            -- issue the loads of 32 columns (no use of the values)
+//     store32(row, col, acc[32], h[32]) -- combine and store
+// and the kernel fetches chunk c + 1 (chunk 0 before it even waits for the accumulator) while chunk c is
+// read out of TMEM and stored.
+template <class Epi> struct EpiPrefetch { static constexpr bool value = false; };
+template <> struct EpiPrefetch<EpiResidual> { static constexpr bool value = true; };
+__device__ __forceinline__ void epi_fetch32(const EpiResidual& e, int row, int col, float (&h)[32]) {
+    const float* p = e.H + (size_t)row * e.ldh + col;
+    if (epi_wide_ok(e.H, (size_t)e.ldh * 4)) {
+#pragma unroll
+        for (int j = 0; j < 4; ++j) ld_global_256f(p + 8 * j, *reinterpret_cast<float(*)[8]>(&h[8 * j]));
+    } else {
+#pragma unroll
+        for (int j = 0; j < 8; ++j) *reinterpret_cast<float4*>(&h[4 * j]) = *reinterpret_cast<const float4*>(p + 4 * j);
+    }
+}
+__device__ __forceinline__ void epi_store32_fetched(const EpiResidual& e, int row, int col, const float (&v)[32], const float (&h)[32]) {
+    float* p = e.H + (size_t)row * e.ldh + col;
+    float o[32];
+#pragma unroll
+    for (int j = 0; j < 32; ++j) o[j] = h[j] + v[j];
+    if (epi_wide_ok(e.H, (size_t)e.ldh * 4)) {
+#pragma unroll
+        for (int j = 0; j < 4; ++j) st_global_256f(p + 8 * j, &o[8 * j]);
+    } else {
+#pragma unroll
+        for (int j = 0; j < 8; ++j) *reinterpret_cast<float4*>(p + 4 * j) = make_float4(o[4 * j], o[4 * j + 1], o[4 * j + 2], o[4 * j + 3]);
+    }
+}
+
 // accumulator columns one thread hands to the functor at a time in the line-coalesced epilogue: 32 bytes
 // of OUTPUT per thread (8 fp32, 16 bf16, 32 accumulator columns for the gated-GELU's 16 bf16)
 template <class Epi> struct EpiWidth { static constexpr int value = 8; };
@@ -537,8 +570,10 @@ __global__ void __launch_bounds__(kTcThreads, 1)
             const int n0 = (to % tiles_n) * BN;
             const int out_row0 = (t / n_out) * M;  // split-K partials are stacked along the rows
             const int buf = i & 1;
-            mbar_wait(bar_acc_full + buf * 8, (i >> 1) & 1);
-            tc_fence_after();
+            if constexpr (!(EpiPrefetch<Epi>::value && MRMT3_EPI_WIDE < 2)) {
+                mbar_wait(bar_acc_full + buf * 8, (i >> 1) & 1);
+                tc_fence_after();
+            }
             const int row = m0 + quarter * 32 + lane;
             const uint32_t tacc = tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(buf * S::kAccCols);
 #if MRMT3_EPI_WIDE >= 2
@@ -579,15 +614,36 @@ __global__ void __launch_bounds__(kTcThreads, 1)
                 __syncwarp();
             }
 #else
-#pragma unroll 1
-            for (int c = 0; c < BN / 32; ++c) {
-                uint32_t v[32];
-                tc_ld_32x32(tacc + (uint32_t)(c * 32), v);
-                if (row < M) {
-                    float f[32];
+            if constexpr (EpiPrefetch<Epi>::value) {
+                float hbuf[2][32];
 #pragma unroll
-                    for (int e = 0; e < 32; ++e) f[e] = __uint_as_float(v[e]);
-                    epi_store32(epi, out_row0 + row, n0 + c * 32, f);
+                for (int c = 0; c < BN / 32; ++c) {
+                    if (c == 0 && row < M) epi_fetch32(epi, out_row0 + row, n0, hbuf[0]);   // (hoisted above the accumulator wait below)
+                    if (c + 1 < BN / 32 && row < M) epi_fetch32(epi, out_row0 + row, n0 + (c + 1) * 32, hbuf[(c + 1) & 1]);
+                    if (c == 0) {
+                        mbar_wait(bar_acc_full + buf * 8, (i >> 1) & 1);
+                        tc_fence_after();
+                    }
+                    uint32_t v[32];
+                    tc_ld_32x32(tacc + (uint32_t)(c * 32), v);
+                    if (row < M) {
+                        float f[32];
+#pragma unroll
+                        for (int e = 0; e < 32; ++e) f[e] = __uint_as_float(v[e]);
+                        epi_store32_fetched(epi, out_row0 + row, n0 + c * 32, f, hbuf[c & 1]);
+                    }
+                }
+            } else {
+#pragma unroll 1
+                for (int c = 0; c < BN / 32; ++c) {
+                    uint32_t v[32];
+                    tc_ld_32x32(tacc + (uint32_t)(c * 32), v);
+                    if (row < M) {
+                        float f[32];
+#pragma unroll
+                        for (int e = 0; e < 32; ++e) f[e] = __uint_as_float(v[e]);
+                        epi_store32(epi, out_row0 + row, n0 + c * 32, f);
+                    }
                 }
             }
 #endif

@@ -111,6 +111,50 @@ __device__ __forceinline__ void epi_store8(const EpiResidualTo& e, int row, int 
     q[0] = make_float4(a.x + v[0] * f0[0], a.y + v[1] * f0[1], a.z + v[2] * f0[2], a.w + v[3] * f0[3]);
     q[1] = make_float4(b.x + v[4] * f1[0], b.y + v[5] * f1[1], b.z + v[6] * f1[2], b.w + v[7] * f1[3]);
 }
+// prefetching interface of the tcgen05 GEMM epilogue (gemm_tcgen05.cuh: EpiPrefetch)
+template <class Epi> struct EpiPrefetch;
+template <> struct EpiPrefetch<EpiResidualTo> { static constexpr bool value = true; };
+__device__ __forceinline__ void epi_fetch32(const EpiResidualTo& e, int row, int col, float (&h)[32]) {
+    const float* p = e.Hin + (size_t)row * e.ldh + col;
+    if (MRMT3_EPI_WIDE && ((reinterpret_cast<size_t>(e.Hin) | ((size_t)e.ldh * 4)) & 31) == 0) {
+#pragma unroll
+        for (int j = 0; j < 4; ++j)
+            asm volatile("ld.global.v8.f32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];\n"
+                         : "=f"(h[8 * j]), "=f"(h[8 * j + 1]), "=f"(h[8 * j + 2]), "=f"(h[8 * j + 3]), "=f"(h[8 * j + 4]),
+                           "=f"(h[8 * j + 5]), "=f"(h[8 * j + 6]), "=f"(h[8 * j + 7])
+                         : "l"(p + 8 * j));
+    } else {
+#pragma unroll
+        for (int j = 0; j < 8; ++j) *reinterpret_cast<float4*>(&h[4 * j]) = *reinterpret_cast<const float4*>(p + 4 * j);
+    }
+}
+__device__ __forceinline__ void epi_store32_fetched(const EpiResidualTo& e, int row, int col, const float (&v)[32], const float (&h)[32]) {
+    float o[32];
+    if (e.drop.on()) {
+        const unsigned long long g = ((unsigned long long)row * e.ldh + col) >> 2;
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+            float f[4];
+            drop_factor4(e.drop, g + j, f);
+#pragma unroll
+            for (int k = 0; k < 4; ++k) o[4 * j + k] = h[4 * j + k] + v[4 * j + k] * f[k];
+        }
+    } else {
+#pragma unroll
+        for (int j = 0; j < 32; ++j) o[j] = h[j] + v[j];
+    }
+    float* q = e.Hout + (size_t)row * e.ldh + col;
+    if (MRMT3_EPI_WIDE && ((reinterpret_cast<size_t>(e.Hout) | ((size_t)e.ldh * 4)) & 31) == 0) {
+#pragma unroll
+        for (int j = 0; j < 4; ++j)
+            asm volatile("st.global.v8.f32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8};\n" ::"l"(q + 8 * j), "f"(o[8 * j]), "f"(o[8 * j + 1]),
+                         "f"(o[8 * j + 2]), "f"(o[8 * j + 3]), "f"(o[8 * j + 4]), "f"(o[8 * j + 5]), "f"(o[8 * j + 6]), "f"(o[8 * j + 7])
+                         : "memory");
+    } else {
+#pragma unroll
+        for (int j = 0; j < 8; ++j) *reinterpret_cast<float4*>(q + 4 * j) = make_float4(o[4 * j], o[4 * j + 1], o[4 * j + 2], o[4 * j + 3]);
+    }
+}
 Status launch_attn_bwd(const AttnBwdParams& p, int batch, cudaStream_t s);
 
 }  // namespace mrmt3
