@@ -49,6 +49,9 @@ struct TrainState {
     int proj = -1, emb = -1, lm_head = -1, cross_kv = -1, enc_final = -1, dec_final = -1, mem_final = -1, segmem_proj = -1;
     size_t n_total = 0;
     DeviceBuffer master, m, v, stash, scratch;
+    DeviceBuffer adam_table;   // AdamSlot per tensor (train_apply)
+    int adam_slots = 0;
+    unsigned int adam_blocks = 0;
     int step = 0;
     // the last forward's saved state
     int B = 0, L = 0, Lp = 0, n_mem = 0;
@@ -106,7 +109,7 @@ void train_destroy(mrmt3_handle* h) {
     TrainState* t = state(h);
     if (!t) return;
     t->master.release(); t->m.release(); t->v.release();
-    t->stash.release(); t->scratch.release(); t->ids_copy.release(); t->prev_copy.release();
+    t->stash.release(); t->scratch.release(); t->ids_copy.release(); t->prev_copy.release(); t->adam_table.release();
     for (auto& b : t->buckets)
         if (b.done) cudaEventDestroy(b.done);
     if (t->loss_pinned) cudaFreeHost(t->loss_pinned);
@@ -876,12 +879,23 @@ Status train_apply(mrmt3_handle* h, const float* grad, float lr, float beta1, fl
     if (!t) return Error(5, "mrmt3_train_init first");
     MRMT3_CUDA_TRY(cudaSetDevice(h->device));
     ++t->step;
-    for (auto& sl : t->slots) {
-        const size_t n = (size_t)sl.rows * sl.cols;
-        float* p = sl.w32 ? sl.w32 : t->master.as<float>() + sl.off;
-        RUN(h, launch_adamw(p, grad + sl.off, t->m.as<float>() + sl.off, t->v.as<float>() + sl.off, sl.w16, n, lr, beta1,
-                            beta2, adam_eps, wd, t->step, s));
+    if (!t->adam_table.p) {  // one table entry per tensor, built once (slots and buffers are fixed after train_init)
+        std::vector<AdamSlot> tab;
+        unsigned int blocks = 0;
+        for (auto& sl : t->slots) {
+            const size_t n = (size_t)sl.rows * sl.cols;
+            if (!n) continue;
+            tab.push_back(AdamSlot{sl.w32 ? sl.w32 : t->master.as<float>() + sl.off, sl.w16, sl.off, n, blocks, 0u});
+            blocks += (unsigned int)((n + 255) / 256);
+        }
+        MRMT3_TRY(t->adam_table.reserve(tab.size() * sizeof(AdamSlot)));
+        MRMT3_CUDA_TRY(cudaMemcpyAsync(t->adam_table.p, tab.data(), tab.size() * sizeof(AdamSlot), cudaMemcpyHostToDevice, s));
+        MRMT3_CUDA_TRY(cudaStreamSynchronize(s));  // `tab` is a local
+        t->adam_slots = (int)tab.size();
+        t->adam_blocks = blocks;
     }
+    RUN(h, launch_adamw_multi(t->adam_table.as<AdamSlot>(), t->adam_slots, t->adam_blocks, grad, t->m.as<float>(),
+                              t->v.as<float>(), lr, beta1, beta2, adam_eps, wd, t->step, s));
     // masters of the norm-folded decode weights follow their training masters
     auto sync_master = [&](float* dst, int slot) -> Status {
         const ParamSlot& sl = t->slots[slot];

@@ -36,6 +36,17 @@ Status launch_bf16_to_f32(const bf16* in, float* out, size_t n, cudaStream_t s);
 Status launch_reduce_splits(const float* partials, float* out, size_t n, int splits, cudaStream_t s);
 Status launch_adamw(float* p, const float* g, float* m, float* v, bf16* p_bf16, size_t n, float lr, float beta1,
                     float beta2, float eps, float wd, int step, cudaStream_t s);
+// One launch over every parameter tensor: entry i covers 256-element blocks [first_block, next entry's) of
+// the flat order; p is the tensor's own fp32 storage (arena parameter or master slice), off its offset in the
+// flat gradient / moment buffers
+struct AdamSlot {
+    float* p;
+    bf16* p_bf16;
+    unsigned long long off, n;
+    unsigned int first_block, pad;
+};
+Status launch_adamw_multi(const AdamSlot* table, int n_slots, unsigned int n_blocks, const float* g, float* m, float* v,
+                          float lr, float beta1, float beta2, float eps, float wd, int step, cudaStream_t s);
 
 // attention backward; Q/K/V/O layouts as AttnFullParams, dQ in Q's layout, dO in O's layout,
 // dK/dV in their own (dk_*) layout; lse2 / delta are (batch, heads, Tq) fp32

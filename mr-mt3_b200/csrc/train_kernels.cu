@@ -527,6 +527,41 @@ Status launch_adamw(float* p, const float* g, float* m, float* v, bf16* p_bf16, 
     return OkStatus();
 }
 
+// every tensor in one launch (the per-tensor form spends 134 launches of ~4 us on tensors most of which are
+// a few thousand elements): block -> its tensor by binary search in the table, then the same update
+__global__ void __launch_bounds__(256)
+    adamw_multi_kernel(const AdamSlot* __restrict__ table, int n_slots, const float* __restrict__ g, float* __restrict__ m,
+                       float* __restrict__ v, float lr, float beta1, float beta2, float eps, float wd, float bc1, float bc2) {
+    int lo = 0, hi = n_slots - 1;
+    while (lo < hi) {  // last entry whose first_block <= blockIdx.x
+        const int mid = (lo + hi + 1) >> 1;
+        if (table[mid].first_block <= blockIdx.x) lo = mid;
+        else hi = mid - 1;
+    }
+    const AdamSlot sl = table[lo];
+    const unsigned long long i = (unsigned long long)(blockIdx.x - sl.first_block) * 256 + threadIdx.x;
+    if (i >= sl.n) return;
+    const unsigned long long j = sl.off + i;
+    float pi = sl.p[i], gi = g[j];
+    pi *= 1.f - lr * wd;
+    const float mi = beta1 * m[j] + (1.f - beta1) * gi;
+    const float vi = beta2 * v[j] + (1.f - beta2) * gi * gi;
+    m[j] = mi;
+    v[j] = vi;
+    pi -= lr * (mi / bc1) / (sqrtf(vi / bc2) + eps);
+    sl.p[i] = pi;
+    if (sl.p_bf16) sl.p_bf16[i] = __float2bfloat16(pi);
+}
+
+Status launch_adamw_multi(const AdamSlot* table, int n_slots, unsigned int n_blocks, const float* g, float* m, float* v,
+                          float lr, float beta1, float beta2, float eps, float wd, int step, cudaStream_t s) {
+    if (!n_blocks) return OkStatus();
+    const float bc1 = 1.f - powf(beta1, (float)step), bc2 = 1.f - powf(beta2, (float)step);
+    adamw_multi_kernel<<<n_blocks, 256, 0, s>>>(table, n_slots, g, m, v, lr, beta1, beta2, eps, wd, bc1, bc2);
+    MRMT3_CHECK_LAUNCH();
+    return OkStatus();
+}
+
 // ---------------------------------------------------------------------------------------------
 // attention backward.  Layout conventions are those of AttnFullParams (attention.cuh): element
 // (b, head, row, d) of X at X + b*x_batch_stride + head*x_head_stride + row*x_row_stride + d.
