@@ -78,7 +78,12 @@ int64_t mrmt3_launch_count(const mrmt3_handle* h);
  * ONE kernel and the logits never reach memory; 0 = separate lm_head / arg-max / embed kernels.
  * "hooks_fast_path" = 1 sends calls that use the parity hooks of
  * mrmt3_generate / mrmt3_generate_segmem (forced_ids, logits_out) through the production decode path
- * (CUDA-graph replay, concurrent lane groups) instead of the eager single-group debug path. */
+ * (CUDA-graph replay, concurrent lane groups) instead of the eager single-group debug path.
+ * "gemm_2cta" = 1 (default): the large-M tcgen05 GEMMs (encoder, cross-K/V, teacher-forced decoder,
+ * fine-tune forward and data gradients) run on two-CTA clusters with tcgen05.mma.cta_group::2 tiles of
+ * 256 x BN; 0 = single-CTA 128 x BN tiles (bit-identical results); -1 = the library default.
+ * "attn_full_tc" = 1 selects the tcgen05 whole-sequence attention forward (validated, slower; default 0).
+ * Both are process-wide. */
 int mrmt3_set_option(mrmt3_handle* h, const char* key, int value);
 
 /* ---- per-kernel timing (bench.py's roofline leg) ---------------------------------------
