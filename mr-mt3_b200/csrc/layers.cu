@@ -129,6 +129,37 @@ __global__ void embed_tokens_kernel(const long long* __restrict__ ids, const flo
         make_float4(e.x + p.x, e.y + p.y, e.z + p.z, e.w + p.w);
 }
 
+// V1 (T5SegMem) teacher forcing: the decoder's input rows of sequence b are [memory rows of b ; token rows of
+// b], all with the positional encoding of their place in the (n_mem + L)-long sequence
+// (reference models/t5_segmem.py:136-139 + the stack input of models/t5.py:596-598)
+__global__ void embed_tokens_prefixed_kernel(const long long* __restrict__ ids, const float* __restrict__ emb,
+                                             const float* __restrict__ pe, const float* __restrict__ mem,
+                                             float* __restrict__ H, int L, int n_mem, int rows) {
+    int row = blockIdx.x * 2 + (threadIdx.x >> 7);
+    if (row >= rows) return;
+    const int c = (threadIdx.x & 127) * 4;
+    const int Lt = L + n_mem, b = row / Lt, t = row - b * Lt;
+    float4 e;
+    if (t < n_mem) {
+        e = *reinterpret_cast<const float4*>(mem + ((size_t)b * n_mem + t) * kDModel + c);
+    } else {
+        long long id = ids[(size_t)b * L + (t - n_mem)];
+        if (id < 0 || id >= kVocab) id = 0;
+        e = *reinterpret_cast<const float4*>(emb + (size_t)id * kDModel + c);
+    }
+    const float4 p = *reinterpret_cast<const float4*>(pe + (size_t)t * kDModel + c);
+    *reinterpret_cast<float4*>(H + (size_t)row * kDModel + c) = make_float4(e.x + p.x, e.y + p.y, e.z + p.z, e.w + p.w);
+}
+
+Status launch_embed_tokens_prefixed(const long long* ids, const float* emb, const float* pe, const float* mem, float* H,
+                                    int B, int L, int n_mem, cudaStream_t s) {
+    const int rows = B * (L + n_mem);
+    if (rows <= 0) return OkStatus();
+    embed_tokens_prefixed_kernel<<<ceil_div(rows, 2), 256, 0, s>>>(ids, emb, pe, mem, H, L, n_mem, rows);
+    MRMT3_CHECK_LAUNCH();
+    return OkStatus();
+}
+
 Status launch_embed_tokens(const long long* ids, const float* emb, const float* pe, float* H, int B,
                            int L, int pos0, cudaStream_t s) {
     int rows = B * L;

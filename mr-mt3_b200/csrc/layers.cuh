@@ -26,6 +26,9 @@ Status launch_rmsnorm(const float* x, const float* w, float eps, bf16* out_bf16,
 // decoder input for teacher forcing: H[b*L + l] = Emb[ids[b*L + l]] + PE[pos0 + l]
 Status launch_embed_tokens(const long long* ids, const float* emb, const float* pe, float* H, int B,
                            int L, int pos0, cudaStream_t s);
+// rows of sequence b: n_mem memory rows (mem (B, n_mem, d) fp32) then L token rows, + PE[0 .. n_mem + L)
+Status launch_embed_tokens_prefixed(const long long* ids, const float* emb, const float* pe, const float* mem, float* H,
+                                    int B, int L, int n_mem, cudaStream_t s);
 
 // memory-block input: out_bf16[r] = bf16(Emb[ids[r]])   (ids int64, rows = n)
 Status launch_embed_bf16(const long long* ids, long ids_row_stride, int rows_per_lane, int n_lanes,

@@ -256,7 +256,7 @@ void handle_destroy(mrmt3_handle* h) {
     h->tma = nullptr;
     h->frontend.destroy();
     h->arena.release(); h->stage.release(); h->rows.release(); h->enc_bf16.release();
-    h->mem_bf16.release(); h->mem_f32.release(); h->mel_f32.release(); h->mel_bf16.release();
+    h->mem_bf16.release(); h->mem_f32.release(); h->mel_f32.release(); h->mel_bf16.release(); h->v1_logits.release();
     h->audio.release(); h->seg_tab.release(); h->ids_dev.release(); h->tok_out.release(); h->dummy_ids.release();
     h->d_h32.release(); h->d_n_bf16.release(); h->d_qkv.release(); h->d_ctx.release();
     h->d_qc.release(); h->d_ff.release(); h->d_logits.release(); h->d_state.release();
@@ -1120,36 +1120,50 @@ Status api_memory_block(mrmt3_handle* h, const long long* prev_ids, int B, int L
 Status api_forward_logits(mrmt3_handle* h, const float* mel, int B, const long long* dec_ids, int L,
                           const long long* targets_prev, int Lp, float* logits_out, cudaStream_t s) {
     if (!h->committed) return Error(5, "weights not committed");
-    if (h->cfg.mem_variant == MRMT3_MEM_V1_PREPEND)
-        return Error(2, "teacher-forced forward is implemented for the MT3 and V2WithPrev models only");
+    // V1 (T5SegMem, models/t5_segmem.py:68-170): `targets_prev` holds the segmem ids of every row (the caller
+    // builds them from the previous row's decoder input, as the reference does) and the memory rows are
+    // PREPENDED to the decoder input instead of joining the cross-attention keys
+    const bool v1 = h->cfg.mem_variant == MRMT3_MEM_V1_PREPEND;
     if (B <= 0 || L <= 0 || L > kNPos) return Error(2, "bad B or L");
     MRMT3_CUDA_TRY(cudaSetDevice(h->device));
     const bool mem = h->cfg.mem_variant == MRMT3_MEM_V2_APPEND;
-    if (mem && (!targets_prev || Lp <= 0)) return Error(2, "targets_prev required for the memory variant");
-    const int n_mem = mem ? std::min(h->cfg.mem_len, Lp) : 0;
-    const int tk = kSegFrames + n_mem;
+    if ((mem || v1) && (!targets_prev || Lp <= 0)) return Error(2, "targets_prev required for the memory variants");
+    const int n_mem = (mem || v1) ? std::min(h->cfg.mem_len, Lp) : 0;
+    const int n_pre = v1 ? n_mem : 0;             // memory rows in front of every decoder sequence
+    const int Lt = L + n_pre;                     // decoder rows per sequence
+    if (Lt > kNPos) return Error(2, "L + memory length exceeds the positional table");
+    const int tk = kSegFrames + (mem ? n_mem : 0);
     const float eps = h->cfg.ln_eps;
     for (int c0 = 0; c0 < B; c0 += kMaxLanes) {
         const int n = std::min(kMaxLanes, B - c0);
         MRMT3_TRY(ensure_decode_capacity(h, n, tk, 1));
         MRMT3_TRY(h->enc_bf16.reserve((size_t)n * kSegFrames * kDModel * sizeof(bf16)));
         MRMT3_TRY(encode_segments(h, mel + (size_t)c0 * kSegFrames * kMels, nullptr, n, h->enc_bf16.as<bf16>(), nullptr, s));
-        if (mem) {
+        if (mem || v1) {
             MRMT3_TRY(h->mem_bf16.reserve((size_t)n * n_mem * kDModel * sizeof(bf16)));
+            if (v1) MRMT3_TRY(reserve_graph_visible(h, h->mem_f32, (size_t)n * n_mem * kDModel * sizeof(float)));
             MRMT3_TRY(memory_block(h, targets_prev + (size_t)c0 * Lp, Lp, nullptr, n, Lp, n_mem,
-                                   h->mem_bf16.as<bf16>(), nullptr, s));
+                                   h->mem_bf16.as<bf16>(), v1 ? h->mem_f32.as<float>() : nullptr, s));
         }
-        MRMT3_TRY(project_cross_kv(h, h->enc_bf16.as<bf16>(), (long)n * kSegFrames, nullptr, n, mem ? h->mem_bf16.as<bf16>() : nullptr, n_mem, s));
-        // decoder over n*L rows, in row chunks of whole sequences
-        const int seq_chunk = std::max(1, (kEncChunk * kSegFrames) / L);
+        MRMT3_TRY(project_cross_kv(h, h->enc_bf16.as<bf16>(), (long)n * kSegFrames, nullptr, n, mem ? h->mem_bf16.as<bf16>() : nullptr,
+                                   mem ? n_mem : 0, s));
+        // decoder over n*Lt rows, in row chunks of whole sequences
+        const int seq_chunk = std::max(1, (kEncChunk * kSegFrames) / Lt);
+        if (v1) MRMT3_TRY(h->v1_logits.reserve((size_t)std::min(seq_chunk, n) * Lt * kVocab * sizeof(float)));
         for (int b0 = 0; b0 < n; b0 += seq_chunk) {
             const int nb = std::min(seq_chunk, n - b0);
-            const int M = nb * L;
+            const int M = nb * Lt;
+            const int L_tok = L;   // token rows per sequence (the caller's L)
+            const int L = Lt;      // from here on a "sequence" is memory rows + token rows
             MRMT3_TRY(h->rows.reserve(M));
             RowWorkspace& w = h->rows;
             float* H = w.h32.as<float>();
             const ARowMap id{nullptr, 1};
-            RUN(h, launch_embed_tokens(dec_ids + (size_t)(c0 + b0) * L, h->emb, h->pe, H, nb, L, 0, s));
+            if (v1)
+                RUN(h, launch_embed_tokens_prefixed(dec_ids + (size_t)(c0 + b0) * L_tok, h->emb, h->pe,
+                                                    h->mem_f32.as<float>() + (size_t)b0 * n_mem * kDModel, H, nb, L_tok, n_pre, s));
+            else
+                RUN(h, launch_embed_tokens(dec_ids + (size_t)(c0 + b0) * L, h->emb, h->pe, H, nb, L, 0, s));
             for (int li = 0; li < h->cfg.n_dec_layers; ++li) {
                 const LayerW& Lw = h->dec.layers[li];
                 RUN(h, launch_rmsnorm(H, Lw.ln_self, eps, w.n_bf16.as<bf16>(), nullptr, M, nullptr, 1, s));
@@ -1205,8 +1219,19 @@ Status api_forward_logits(mrmt3_handle* h, const float* mel, int B, const long l
                 RUN(h, launch_gemm_tc(*h->tma, w.ff.as<bf16>(), kDFF, M, id, Lw.wff, kDFF, M, kDModel, kDFF, EpiResidual{H, kDModel}, s));
             }
             RUN(h, launch_rmsnorm(H, h->dec.final_ln, eps, w.n_bf16.as<bf16>(), nullptr, M, nullptr, 1, s));
-            RUN(h, launch_gemm_tc(*h->tma, w.n_bf16.as<bf16>(), kDModel, M, id, h->lm_head, kDModel, M, kVocab, kDModel,
-                                   EpiStoreF32{logits_out + (size_t)(c0 + b0) * L * kVocab, kVocab}, s));
+            if (v1) {
+                // logits of all rows into a scratch, then the token rows of every sequence to the caller
+                // (reference: sequence_output[:, segmem_length:], models/t5_segmem.py:158-159)
+                float* scratch = h->v1_logits.as<float>();
+                RUN(h, launch_gemm_tc(*h->tma, w.n_bf16.as<bf16>(), kDModel, M, id, h->lm_head, kDModel, M, kVocab, kDModel,
+                                       EpiStoreF32{scratch, kVocab}, s));
+                MRMT3_CUDA_TRY(cudaMemcpy2DAsync(logits_out + (size_t)(c0 + b0) * L_tok * kVocab, (size_t)L_tok * kVocab * sizeof(float),
+                                                 scratch + (size_t)n_pre * kVocab, (size_t)L * kVocab * sizeof(float),
+                                                 (size_t)L_tok * kVocab * sizeof(float), nb, cudaMemcpyDeviceToDevice, s));
+            } else {
+                RUN(h, launch_gemm_tc(*h->tma, w.n_bf16.as<bf16>(), kDModel, M, id, h->lm_head, kDModel, M, kVocab, kDModel,
+                                       EpiStoreF32{logits_out + (size_t)(c0 + b0) * L * kVocab, kVocab}, s));
+            }
         }
     }
     return OkStatus();

@@ -124,6 +124,7 @@ struct mrmt3_handle {
     mrmt3::RowWorkspace rows;
     mrmt3::DeviceBuffer enc_bf16;        // (n_seg, 256, d) encoder states of the current call
     mrmt3::DeviceBuffer mem_bf16, mem_f32;  // (lanes, n_mem, d)
+    mrmt3::DeviceBuffer v1_logits;          // V1 teacher forcing: logits of memory + token rows before the slice
     mrmt3::DeviceBuffer mel_f32, mel_bf16, audio, seg_tab, ids_dev;  // e2e path
     mrmt3::DeviceBuffer tok_out;         // (rows, max_length+1) int64 token rows of the call
     mrmt3::DeviceBuffer dummy_ids;       // (max_length) int64 first-segment memory ids

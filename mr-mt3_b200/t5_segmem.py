@@ -57,9 +57,44 @@ class T5SegMem(T5ForConditionalGeneration):
             return ids, self.engine().encode(inputs)
         return ids
 
-    def forward(self, *args, **kwargs):
-        # reference models/t5_segmem.py:68-170 (V1 teacher forcing: row i's memory comes from row i-1
-        # of the SAME batch).  Not on the north_star path (the shipped experiments train V2WithPrev,
-        # config/config_slakh_segmem.yaml); stated in DESIGN.md section 8.
-        raise NotImplementedError("teacher-forced forward is implemented for T5ForConditionalGeneration "
-                                  "and T5SegMemV2WithPrev only")
+    @staticmethod
+    def segmem_ids_from_decoder_input(decoder_input_ids):
+        """The ids the reference feeds row i's memory block (models/t5_segmem.py:123-131): row i - 1's
+        decoder input without its start token, a 0 appended; row 0 gets the dummy [1, 0, 0, ...]."""
+        ids = decoder_input_ids
+        nxt = torch.cat([ids[:, 1:], ids.new_zeros((ids.shape[0], 1))], dim=1)
+        dummy = ids.new_zeros((1, ids.shape[1]))
+        dummy[0, 0] = 1
+        return torch.cat([dummy, nxt[:-1]], dim=0)
+
+    def get_model_outputs(self, inputs=None, labels=None, decoder_input_ids=None, output_hidden_states=None,
+                          **unsupported):
+        """Reference models/t5_segmem.py:68-170 (V1 teacher forcing: the rows of a batch are CONSECUTIVE
+        segments, row i's memory is built from row i - 1's decoder input and prepended to row i's decoder
+        input embeddings; the logits of the memory rows are dropped) -> (logits, encoder_outputs, None)."""
+        for k, v in unsupported.items():
+            if v is not None and k not in ("use_cache", "return_dict", "output_attentions"):
+                raise NotImplementedError(f"{k} is not supported by the CUDA path")
+        if inputs is None:
+            raise ValueError("`inputs` is required")
+        if decoder_input_ids is None:
+            if labels is None:
+                raise ValueError("either labels or decoder_input_ids is required")
+            decoder_input_ids = self._shift_right(labels)
+        if decoder_input_ids.shape[1] < self.segmem_length:
+            # the reference drops `segmem_length` output rows whatever the number of memory rows
+            # (models/t5_segmem.py:158-159), so shorter sequences come back with token rows missing
+            raise ValueError(f"T5SegMem.forward needs at least segmem_length = {self.segmem_length} label positions")
+        segmem_ids = self.segmem_ids_from_decoder_input(decoder_input_ids)
+        logits = self.engine().forward_logits(inputs, decoder_input_ids, segmem_ids)
+        enc = (self.engine().encode(inputs),) if output_hidden_states else None
+        return logits, enc, None
+
+    def forward(self, inputs=None, labels=None, decoder_input_ids=None, **kwargs):
+        """Reference models/t5.py:182-249 over T5SegMem.get_model_outputs: logits only.  Inference-mode
+        (no autograd graph): the hand-written backward covers MT3 and V2WithPrev, the variants the
+        reference's shipped experiments train (config/config_slakh_segmem.yaml)."""
+        kwargs.pop("num_insts", None)
+        if self.training and torch.is_grad_enabled():
+            raise NotImplementedError("T5SegMem (V1) has no CUDA backward; train T5SegMemV2WithPrev or call under no_grad")
+        return self.get_model_outputs(inputs=inputs, labels=labels, decoder_input_ids=decoder_input_ids, **kwargs)[0]

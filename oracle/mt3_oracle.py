@@ -443,6 +443,26 @@ def forward_logits_segmem_v2_with_prev(inputs, labels, targets_prev, sd, segmem_
     return decoder_logits(shift_right(labels), torch.cat([enc, mem], dim=1), sd, drop)
 
 
+def segmem_ids_v1(dec_ids):
+    """Reference models/t5_segmem.py:123-131: row i's memory ids = row i-1's decoder input without the
+    start token (+ a trailing 0); row 0 = the dummy [1, 0, ...]."""
+    nxt = torch.cat([dec_ids[:, 1:], torch.zeros((dec_ids.shape[0], 1), dtype=dec_ids.dtype)], dim=1)
+    dummy = torch.zeros((1, dec_ids.shape[1]), dtype=dec_ids.dtype)
+    dummy[0, 0] = 1
+    return torch.cat([dummy, nxt[:-1]], dim=0)
+
+
+def forward_logits_segmem_v1(inputs, labels, sd, segmem_length=64):
+    """Reference T5SegMem.get_model_outputs, models/t5_segmem.py:68-170 (the rows of the batch are the
+    consecutive segments of one track; memory rows prepended to the decoder input, their logits dropped)."""
+    enc = encode(inputs, sd)
+    dec_ids = shift_right(labels)
+    mem = memory_block(segmem_ids_v1(dec_ids), sd, segmem_length)
+    h = torch.cat([mem, sd["decoder_embed_tokens.weight"][dec_ids]], dim=1)
+    out = decoder_stack(h, enc, sd)[:, mem.shape[1]:]
+    return out @ sd["lm_head.weight"].T
+
+
 # ---------------------------------------------------------------------------------------------
 # KV-cached evaluation of the SAME greedy recurrences.  Mathematically identical to the loops
 # above (causal attention makes earlier positions independent of later ones); used by tests to

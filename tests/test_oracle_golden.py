@@ -122,6 +122,22 @@ def test_segmem_v1_generate(feats):
     np.testing.assert_array_equal(got.numpy(), g["v1_gen_ids"])
 
 
+def test_segmem_v1_teacher_forced_forward_matches_reference():
+    """T5SegMem.get_model_outputs (models/t5_segmem.py:68-170): golden logits minted from the reference
+    itself (oracle/make_golden_v1_forward.py)."""
+    g = golden("segmem_v1_forward.npz")
+    sd = _sd(4322, segmem=True)
+    x = syn.synthetic_features(int(g["feat_seed"]), 3)
+    for tag in ("short", "long"):
+        labels = torch.as_tensor(g[f"{tag}_labels"])
+        got = O.forward_logits_segmem_v1(x, labels, sd)
+        assert got.shape == (3, labels.shape[1], 1536)
+        assert np.max(np.abs(got.numpy()[:, :, ::4] - g[f"{tag}_logits_sub"])) < 2e-4
+        np.testing.assert_array_equal(got.argmax(-1).numpy(), g[f"{tag}_argmax"])
+    ids = O.segmem_ids_v1(torch.tensor([[0, 5, 6, 7], [0, 8, 9, 1]]))
+    np.testing.assert_array_equal(ids.numpy(), [[1, 0, 0, 0], [5, 6, 7, 0]])
+
+
 def test_segmem_v1_uncached_short(feats):
     sd = _sd(4322, segmem=True, eos_scale=3.0)
     a = O.generate_segmem_v1(feats[:1], sd, max_length=66)

@@ -327,6 +327,26 @@ def test_segmem_v1_generate(pkg, feats):
             break
 
 
+def test_segmem_v1_teacher_forced_forward(pkg):
+    """T5SegMem.forward (V1, models/t5_segmem.py:68-170): memory rows built from the previous row's decoder
+    input and PREPENDED to the decoder input; logits of the token rows against the reference's own golden
+    logits and the fp64 oracle."""
+    model, sd = _model(pkg, 4322, kind="v1")
+    g = golden("segmem_v1_forward.npz")
+    x = syn.synthetic_features(int(g["feat_seed"]), 3)
+    for tag in ("short", "long"):
+        labels = torch.as_tensor(g[f"{tag}_labels"])
+        got = model(inputs=x.cuda(), labels=labels.clone().cuda()).cpu()
+        want = O.forward_logits_segmem_v1(x, labels, sd)
+        assert got.shape == want.shape == (3, labels.shape[1], 1536)
+        err = float((got.double() - want).abs().max())
+        print(f"V1 teacher-forced logits ({tag}): max abs err vs fp64 oracle {err:.4f}")
+        assert err < BF16_ATOL
+        assert float(np.max(np.abs(got.numpy()[:, :, ::4] - g[f"{tag}_logits_sub"]))) < BF16_ATOL
+    with pytest.raises(Exception):                       # shorter than segmem_length: the reference returns too few rows
+        model(inputs=x.cuda(), labels=torch.randint(3, 100, (3, 24)).cuda())
+
+
 # ---- end to end and full-size properties ---------------------------------------------------------
 def test_transcribe_host_equals_staged_path(pkg):
     import importlib
