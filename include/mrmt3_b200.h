@@ -195,7 +195,11 @@ int mrmt3_generate_segmem_forced(mrmt3_handle* h, const float* mel, const int32_
  * Replaces: model.forward / get_model_outputs (models/t5.py:99-249,
  * models/t5_segmem_v2_with_prev.py:60-224): logits (B, L, vocab) fp32 for
  * decoder_input_ids (B, L) int64 (= _shift_right(labels)); targets_prev (B, Lp) int64 with
- * -100 already replaced by pad (NULL when mem_variant == NONE). */
+ * -100 already replaced by pad (NULL when mem_variant == NONE).
+ * MRMT3_MEM_V1_PREPEND handles (T5SegMem, models/t5_segmem.py:68-170): targets_prev holds every row's
+ * segmem ids (row i = row i-1's decoder input without its start token + a trailing 0; row 0 = [1, 0, ...],
+ * t5_segmem.py:123-131); the min(mem_len, Lp) memory rows are prepended to the row's decoder input and the
+ * logits of the L token rows are returned; L + memory rows must fit the 1024-entry positional table. */
 int mrmt3_forward_logits(mrmt3_handle* h, const float* mel, int B, const int64_t* decoder_input_ids,
                          int L, const int64_t* targets_prev, int Lp, float* logits_out,
                          void* stream);
