@@ -947,6 +947,7 @@ __global__ void __launch_bounds__(128, CTAS)
     __shared__ __align__(128) bf16 sA[2][kBwdT * kDKV];  // stage s: Q tile   (stage 1 holds K first)
     __shared__ __align__(128) bf16 sB[2][kBwdT * kDKV];  // stage s: dO tile  (stage 1 holds V first)
     __shared__ float s_lse[2][kBwdT], s_dl[2][kBwdT];
+    __shared__ __align__(8) unsigned short s_keep[2][kBwdT][4];   // keep words of (query row, this key tile)
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int k0 = blockIdx.x * kBwdT, head = blockIdx.y, b = blockIdx.z;
     const bf16* Q = p.Q + (size_t)b * p.q_batch_stride + head * p.q_head_stride;
@@ -966,6 +967,11 @@ __global__ void __launch_bounds__(128, CTAS)
             size_t idx = ((size_t)b * kHeads + head) * p.Tq + min(r, p.Tq - 1);
             cp_async4(&s_lse[stg][threadIdx.x], p.lse2 + idx);
             cp_async4(&s_dl[stg][threadIdx.x], p.delta + idx);
+            // the tile's 64 x 4 keep words too (8 bytes per row): sixteen scattered 2-byte global loads per
+            // thread and tile otherwise (ncu: long_scoreboard 1.44 per issue in this kernel, 0.6 in dQ)
+            if (p.drop.on())
+                cp_async8(&s_keep[stg][threadIdx.x][0],
+                          p.keep + idx * (size_t)(((p.Tk + kBwdT - 1) / kBwdT) * 4) + blockIdx.x * 4);
         }
     };
 
@@ -1002,20 +1008,16 @@ __global__ void __launch_bounds__(128, CTAS)
             load_stats(st ^ 1, qt + 1);
         }
         cp_async_commit();
+        cp_async_wait<1>();
+        __syncthreads();
         // keep bits of this thread's 16 query rows x 2 keys: both keys sit in the same saved word
         uint32_t kbw[8][2];
         if (p.drop.on()) {
 #pragma unroll
-            for (int ni = 0; ni < 8; ++ni) {
+            for (int ni = 0; ni < 8; ++ni)
 #pragma unroll
-                for (int e = 0; e < 2; ++e) {
-                    const int row = min(qt * kBwdT + ni * 8 + (lane & 3) * 2 + e, p.Tq - 1);
-                    kbw[ni][e] = __ldg(p.keep + (bh_row0 + row) * keep_words + blockIdx.x * 4 + (lane >> 3)) >> keep_shift;
-                }
-            }
+                for (int e = 0; e < 2; ++e) kbw[ni][e] = (uint32_t)s_keep[st][ni * 8 + (lane & 3) * 2 + e][lane >> 3] >> keep_shift;
         }
-        cp_async_wait<1>();
-        __syncthreads();
         float stt[8][4], dpt[8][4];
         bwd_zero(stt);
         bwd_zero(dpt);
