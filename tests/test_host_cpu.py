@@ -265,3 +265,15 @@ def test_dropout_mask_definition_equals_oracle_mirror():
     assert lib.mrmt3_dropout_keep_host(0.0, 99, 65539, got.size, got.ctypes.data_as(ctypes.c_void_p)) == 0
     assert got.all()
     assert lib.mrmt3_dropout_keep_host(1.0, 99, 65539, 4, got.ctypes.data_as(ctypes.c_void_p)) != 0
+
+
+def test_v1_segmem_ids_mirror_equals_oracle():
+    """T5SegMem.segmem_ids_from_decoder_input (mirror of models/t5_segmem.py:123-131) against the oracle's
+    restatement, which tests/test_oracle_golden.py pins to the reference's logits."""
+    mod = importlib.import_module("mr-mt3_b200.t5_segmem")
+    g = torch.Generator().manual_seed(3)
+    dec = torch.randint(0, 1536, (5, 17), generator=g)
+    dec[:, 0] = 0
+    got = mod.T5SegMem.segmem_ids_from_decoder_input(dec)
+    assert torch.equal(got, O.segmem_ids_v1(dec)) and got.dtype == torch.int64
+    assert got[0].tolist() == [1] + [0] * 16 and got[1, :16].tolist() == dec[0, 1:].tolist() and int(got[1, 16]) == 0
